@@ -1,0 +1,617 @@
+/*
+ * TEST INFRASTRUCTURE -- NOT PART OF THE PRODUCT PATH.
+ *
+ * CPU restatement (plain C, scalar, IEEE double, no FMA contraction) of wildboar's
+ * elastic-distance hot path.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference leg may load this library, and only as the checker
+ * or as the timed CPU baseline -- never as a fallback for the CUDA path.
+ *
+ * Parity status: PINNED.  tests/test_oracle.py checks every function here (a) bit-for-bit
+ * against the reference's own Cython build (oracle/_ref, built by oracle/build_ref.sh)
+ * when that build is present and (b) against the committed golden vectors in
+ * tests/golden/ that were generated from that same reference build
+ * (tests/golden/make_golden.py).
+ *
+ * Citations are file:line in the reference tree (/root/reference/src/wildboar):
+ *   EL = distance/_elastic.pyx   CD = distance/_cdistance.pyx
+ *   MI = utils/_misc.pyx         ST = utils/_stats.pyx      LB = distance/lb.py
+ *
+ * Build: see oracle/Makefile  (gcc -O2 -ffp-contract=off -pthread -shared -fPIC)
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <unistd.h>
+
+enum {
+  ORC_DTW = 0, ORC_WDTW = 1, ORC_DDTW = 2, ORC_ADTW = 3, ORC_LCSS = 4, ORC_ERP = 5,
+  ORC_EDR = 6, ORC_MSM = 7, ORC_TWE = 8, ORC_WDDTW = 9, ORC_WLCSS = 10, ORC_N_METRICS = 11
+};
+
+/* metric_params surface of the reference; epsilon = NaN means
+ * "EDR default": max(std_x, std_y) / 4 per pair (EL:3762-3768). */
+typedef struct {
+  double r;         /* Sakoe-Chiba window fraction, all metrics          */
+  double g;         /* wdtw / wddtw / wlcss weight steepness, erp gap g  */
+  double p;         /* adtw penalty                                      */
+  double c;         /* msm cost                                          */
+  double epsilon;   /* lcss / wlcss / edr threshold (NaN = edr default)  */
+  double penalty;   /* twe                                               */
+  double stiffness; /* twe                                               */
+} orc_params;
+
+static inline int64_t i64max(int64_t a, int64_t b) { return a > b ? a : b; }
+static inline int64_t i64min(int64_t a, int64_t b) { return a < b ? a : b; }
+static inline double dmin(double a, double b) { return a < b ? a : b; }
+static inline double dmax(double a, double b) { return a > b ? a : b; }
+
+/* EL:1924-1925 */
+int64_t orc_compute_r(int64_t length, double r) {
+  return (int64_t)fmax(floor((double)length * r), 1.0);
+}
+
+/* ST:22-42 fast_mean_std: sequential sums, pow(x, 2.0), variance threshold 1e-13 */
+double orc_std(const double *data, int64_t n) {
+  double ex = 0, ex2 = 0;
+  for (int64_t i = 0; i < n; i++) {
+    double v = data[i];
+    ex += v;
+    ex2 += pow(v, 2.0);
+  }
+  double mean = ex / (double)n;
+  ex2 = ex2 / (double)n - mean * mean;
+  return ex2 > 1e-13 ? sqrt(ex2) : 0.0;
+}
+
+/* EL:3339-3341 (N = max(Tx,Ty)); EL:3418-3428 for wddtw (N = max(Tx,Ty)-2) */
+void orc_weights(double g, int64_t n, double *w) {
+  for (int64_t i = 0; i < n; i++) w[i] = 1.0 / (1.0 + exp(-g * ((double)i - (double)n / 2.0)));
+}
+
+/* EL:3220-3225 */
+void orc_average_slope(const double *q, int64_t len, double *d) {
+  int64_t j = 0;
+  for (int64_t i = 1; i < len - 1; i++) {
+    d[j] = ((q[i] - q[i - 1]) + ((q[i + 1] - q[i - 1]) / 2)) / 2;
+    j++;
+  }
+}
+
+/* EL:869-940 (weights may be NULL) */
+static double dtw_distance(const double *X, int64_t xl, const double *Y, int64_t yl, int64_t r,
+                           double *cost, double *cost_prev, const double *wv, double min_dist) {
+  double w = 1.0, v;
+  int64_t max_len = i64max(0, yl - xl) + r;
+  int64_t min_len = i64max(0, xl - yl);
+  v = X[0] - Y[0];
+  if (wv) w = wv[0];
+  cost_prev[0] = v * v * w;
+  for (int64_t i = 1; i < i64min(yl, max_len); i++) {
+    v = X[0] - Y[i];
+    if (wv) w = wv[i - 1];
+    cost_prev[i] = cost_prev[i - 1] + v * v * w;
+  }
+  if (max_len < yl) cost_prev[max_len] = INFINITY;
+  for (int64_t i = 1; i < xl; i++) {
+    int64_t j_start = i64max(0, i - min_len - r + 1);
+    int64_t j_stop = i64min(yl, i + max_len);
+    if (j_start > 0) cost[j_start - 1] = INFINITY;
+    double min_cost = INFINITY;
+    for (int64_t j = j_start; j < j_stop; j++) {
+      double x = cost_prev[j], y, z;
+      if (j > 0) { y = cost[j - 1]; z = cost_prev[j - 1]; }
+      else { y = INFINITY; z = INFINITY; }
+      v = X[i] - Y[j];
+      if (wv) w = wv[llabs(i - j)];
+      cost[j] = dmin(dmin(x, y), z) + v * v * w;
+      if (cost[j] < min_cost) min_cost = cost[j];
+    }
+    if (min_cost > min_dist) return INFINITY;
+    if (j_stop < yl) cost[j_stop] = INFINITY;
+    double *t = cost; cost = cost_prev; cost_prev = t;
+  }
+  return cost_prev[yl - 1];
+}
+
+/* EL:943-1008 */
+static double adtw_distance(const double *X, int64_t xl, const double *Y, int64_t yl, int64_t r,
+                            double *cost, double *cost_prev, double penalty, double min_dist) {
+  double v;
+  int64_t max_len = i64max(0, yl - xl) + r;
+  int64_t min_len = i64max(0, xl - yl);
+  v = X[0] - Y[0];
+  cost_prev[0] = v * v;
+  for (int64_t i = 1; i < i64min(yl, max_len); i++) {
+    v = X[0] - Y[i];
+    cost_prev[i] = cost_prev[i - 1] + v * v;
+  }
+  if (max_len < yl) cost_prev[max_len] = INFINITY;
+  for (int64_t i = 1; i < xl; i++) {
+    int64_t j_start = i64max(0, i - min_len - r + 1);
+    int64_t j_stop = i64min(yl, i + max_len);
+    if (j_start > 0) cost[j_start - 1] = INFINITY;
+    double prev_cost = INFINITY, min_cost = INFINITY;
+    for (int64_t j = j_start; j < j_stop; j++) {
+      double x = cost_prev[j] + penalty, y, z;
+      if (j > 0) { y = prev_cost + penalty; z = cost_prev[j - 1]; }
+      else { y = INFINITY; z = INFINITY; }
+      v = X[i] - Y[j];
+      cost[j] = dmin(dmin(x, y), z) + v * v;
+      if (cost[j] < min_cost) min_cost = cost[j];
+      prev_cost = cost[j];
+    }
+    if (min_cost > min_dist) return INFINITY;
+    if (j_stop < yl) cost[j_stop] = INFINITY;
+    double *t = cost; cost = cost_prev; cost_prev = t;
+  }
+  return cost_prev[yl - 1];
+}
+
+/* EL:1118-1183 */
+static double lcss_distance(const double *X, int64_t xl, const double *Y, int64_t yl, int64_t r,
+                            double epsilon, double *cost, double *cost_prev, const double *wv,
+                            double min_dist) {
+  double w = 1.0;
+  int64_t max_len = i64max(0, yl - xl) + r;
+  int64_t min_len = i64max(0, xl - yl);
+  for (int64_t i = 0; i < i64min(yl, max_len); i++) cost_prev[i] = 0;
+  if (max_len < yl) cost_prev[max_len] = 0;
+  for (int64_t i = 0; i < xl; i++) {
+    int64_t j_start = i64max(0, i - min_len - r + 1);
+    int64_t j_stop = i64min(yl, i + max_len);
+    if (j_start > 0) cost[j_start - 1] = 0;
+    double min_cost = INFINITY;
+    for (int64_t j = j_start; j < j_stop; j++) {
+      double x = cost_prev[j], y, z;
+      if (j > 0) { y = cost_prev[j - 1]; z = cost[j - 1]; }
+      else { y = 0; z = 0; }
+      double v = fabs(X[i] - Y[j]);
+      if (wv) w = wv[llabs(i - j)];
+      if (v <= epsilon) cost[j] = w + y;
+      else cost[j] = dmax(z, x);
+      if (cost[j] < min_cost) min_cost = cost[j];
+    }
+    if (min_cost > min_dist) return INFINITY;
+    if (j_stop < yl) cost[j_stop] = 0;
+    double *t = cost; cost = cost_prev; cost_prev = t;
+  }
+  return 1 - (cost_prev[yl - 1] / (double)i64min(xl, yl));
+}
+
+/* EL:1273-1347 */
+static double erp_distance(const double *X, int64_t xl, const double *Y, int64_t yl, int64_t r,
+                           double g, double *gX, double *gY, double *cost, double *cost_prev,
+                           double min_dist) {
+  double gx_sum = 0, gy_sum = 0, v;
+  int64_t max_len = i64max(0, yl - xl) + r;
+  int64_t min_len = i64max(0, xl - yl);
+  for (int64_t i = 0; i < xl; i++) { v = fabs(X[i] - g); gX[i] = v; gx_sum += v; }
+  for (int64_t i = 0; i < yl; i++) { v = fabs(Y[i] - g); gY[i] = v; gy_sum += v; }
+  for (int64_t i = 0; i < i64min(yl, max_len); i++) cost_prev[i] = gy_sum;
+  if (max_len < yl) cost_prev[max_len] = gy_sum;
+  for (int64_t i = 0; i < xl; i++) {
+    int64_t j_start = i64max(0, i - min_len - r + 1);
+    int64_t j_stop = i64min(yl, i + max_len);
+    if (j_start > 0) cost[j_start - 1] = 0;
+    double min_cost = INFINITY;
+    for (int64_t j = j_start; j < j_stop; j++) {
+      double x = cost_prev[j], y, z;
+      if (j > 0) { y = cost_prev[j - 1]; z = cost[j - 1]; }
+      else { y = (i == 0) ? 0 : gx_sum; z = gx_sum; }
+      v = fabs(X[i] - Y[j]);
+      cost[j] = dmin(y + v, dmin(x + gX[i], z + gY[j]));
+      if (cost[j] < min_cost) min_cost = cost[j];
+    }
+    if (min_cost > min_dist) return INFINITY;
+    if (j_stop < yl) cost[j_stop] = 0;
+    double *t = cost; cost = cost_prev; cost_prev = t;
+  }
+  return cost_prev[yl - 1];
+}
+
+/* EL:1437-1497 */
+static double edr_distance(const double *X, int64_t xl, const double *Y, int64_t yl, int64_t r,
+                           double epsilon, double *cost, double *cost_prev, double min_dist) {
+  int64_t max_len = i64max(0, yl - xl) + r;
+  int64_t min_len = i64max(0, xl - yl);
+  for (int64_t i = 0; i < i64min(yl, max_len); i++) cost_prev[i] = 0;
+  if (max_len < yl) cost_prev[max_len] = 0;
+  for (int64_t i = 0; i < xl; i++) {
+    int64_t j_start = i64max(0, i - min_len - r + 1);
+    int64_t j_stop = i64min(yl, i + max_len);
+    if (j_start > 0) cost[j_start - 1] = 0;
+    double min_cost = INFINITY;
+    for (int64_t j = j_start; j < j_stop; j++) {
+      double x = cost_prev[j], y, z;
+      if (j > 0) { y = cost_prev[j - 1]; z = cost[j - 1]; }
+      else { y = 0; z = 0; }
+      double v = fabs(X[i] - Y[j]);
+      cost[j] = dmin(dmin(y + (v < epsilon ? 0 : 1), x + 1), z + 1);
+      if (cost[j] < min_cost) min_cost = cost[j];
+    }
+    if (min_cost > min_dist) return INFINITY;
+    if (j_stop < yl) cost[j_stop] = 0;
+    double *t = cost; cost = cost_prev; cost_prev = t;
+  }
+  return cost_prev[yl - 1] / (double)i64max(xl, yl);
+}
+
+/* EL:1583-1587 -- the arguments are C floats in the reference */
+static inline double msm_cost(float x, float y, float z, float c) {
+  if ((y <= x && x <= z) || (y >= x && x >= z)) return c;
+  return c + dmin(fabs(x - y), fabs(x - z));
+}
+
+/* EL:1592-1647.  cost[j_start-1] is deliberately NOT reset (stale read);
+ * we reproduce it by using the same two-buffer scheme. */
+static double msm_distance(const double *X, int64_t xl, const double *Y, int64_t yl, int64_t r,
+                           double c, double *cost, double *cost_prev, double *cost_y,
+                           double min_dist) {
+  int64_t max_len = i64max(0, yl - xl) + r;
+  int64_t min_len = i64max(0, xl - yl);
+  cost_prev[0] = fabs(X[0] - Y[0]);
+  for (int64_t i = 1; i < i64min(yl, max_len); i++)
+    cost_prev[i] = cost_prev[i - 1] + msm_cost((float)Y[i], (float)Y[i - 1], (float)X[0], (float)c);
+  {
+    int64_t i = max_len;
+    if (i < yl)
+      cost_prev[i] = cost_prev[i - 1] + msm_cost((float)Y[i], (float)Y[i - 1], (float)X[0], (float)c);
+  }
+  cost_y[0] = cost_prev[0];
+  for (int64_t i = 1; i < xl; i++)
+    cost_y[i] = cost_y[i - 1] + msm_cost((float)X[i], (float)X[i - 1], (float)Y[0], (float)c);
+  for (int64_t i = 1; i < xl; i++) {
+    int64_t j_start = i64max(1, i - min_len - r + 1);
+    int64_t j_stop = i64min(yl, i + max_len);
+    cost[0] = cost_y[i];
+    double min_cost = cost[0];
+    for (int64_t j = j_start; j < j_stop; j++) {
+      double a = cost_prev[j - 1] + fabs(X[i] - Y[j]);
+      double b = cost_prev[j] + msm_cost((float)X[i], (float)X[i - 1], (float)Y[j], (float)c);
+      double d = cost[j - 1] + msm_cost((float)Y[j], (float)X[i], (float)Y[j - 1], (float)c);
+      cost[j] = dmin(dmin(a, b), d);
+      if (cost[j] < min_cost) min_cost = cost[j];
+    }
+    if (min_cost > min_dist) return INFINITY;
+    if (j_stop < yl) cost[j_stop] = 0;
+    double *t = cost; cost = cost_prev; cost_prev = t;
+  }
+  return cost_prev[yl - 1];
+}
+
+/* EL:1733-1829 */
+static double twe_distance(const double *X, int64_t xl, const double *Y, int64_t yl, int64_t r,
+                           double penalty, double stiffness, double *cost, double *cost_prev,
+                           double min_dist) {
+  int64_t max_len = i64max(0, yl - xl) + r;
+  int64_t min_len = i64max(0, xl - yl);
+  for (int64_t i = 0; i < i64min(yl, max_len); i++) cost_prev[i] = INFINITY;
+  if (max_len < yl) cost_prev[max_len] = INFINITY;
+  penalty = penalty + stiffness;
+  for (int64_t i = 0; i < xl; i++) {
+    int64_t j_start = i64max(0, i - min_len - r + 1);
+    int64_t j_stop = i64min(yl, i + max_len);
+    if (j_start > 0) cost[j_start - 1] = 0;
+    double min_cost = INFINITY;
+    for (int64_t j = j_start; j < j_stop; j++) {
+      double up = cost_prev[j], left, up_left, x, y;
+      if (j == 0) { left = INFINITY; up_left = (i == 0) ? 0 : INFINITY; }
+      else { left = cost[j - 1]; up_left = cost_prev[j - 1]; }
+      x = (i == 0) ? 0 : X[i - 1];
+      y = X[i];
+      double del_x = up + fabs(x - y) + penalty;
+      x = (j == 0) ? 0 : Y[j - 1];
+      y = Y[j];
+      double del_y = left + fabs(x - y) + penalty;
+      x = (i == 0) ? 0 : X[i - 1];
+      y = (j == 0) ? 0 : Y[j - 1];
+      double match = up_left + fabs(X[i] - Y[j]) + fabs(x - y) + stiffness * 2 * (double)llabs(i - j);
+      cost[j] = dmin(dmin(del_x, del_y), match);
+      if (cost[j] < min_cost) min_cost = cost[j];
+    }
+    if (min_cost > min_dist) return INFINITY;
+    if (j_stop < yl) cost[j_stop] = 0;
+    double *t = cost; cost = cost_prev; cost_prev = t;
+  }
+  return cost_prev[yl - 1];
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Metric object: mirrors `cdef class Metric` reset/distance/eadistance (CD:694-761) for the
+ * elastic classes EL:3126-4082.  One instance per worker thread (the reference deep-copies
+ * the metric per joblib task, CD:1171).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int metric;
+  orc_params p;
+  int64_t Tx, Ty;
+  double *cost, *cost_prev, *aux_x, *aux_y, *weights;
+  const double *std_x, *std_y; /* shared, per sample (EDR default epsilon) */
+} orc_metric;
+
+
+static void metric_init(orc_metric *m, int metric, const orc_params *p, int64_t Tx, int64_t Ty,
+                        const double *std_x, const double *std_y) {
+  int64_t n = i64max(Tx, Ty);
+  m->metric = metric; m->p = *p; m->Tx = Tx; m->Ty = Ty;
+  m->cost = (double *)malloc(sizeof(double) * (size_t)(n + 1));
+  m->cost_prev = (double *)malloc(sizeof(double) * (size_t)(n + 1));
+  m->aux_x = (double *)malloc(sizeof(double) * (size_t)(Tx + 1));
+  m->aux_y = (double *)malloc(sizeof(double) * (size_t)(Ty + 1));
+  m->weights = NULL;
+  m->std_x = std_x; m->std_y = std_y;
+  if (metric == ORC_WDTW || metric == ORC_WLCSS) {
+    m->weights = (double *)malloc(sizeof(double) * (size_t)n);
+    orc_weights(p->g, n, m->weights);
+  } else if (metric == ORC_WDDTW) {
+    int64_t nn = i64max(Tx - 2, Ty - 2);
+    if (nn > 0) { m->weights = (double *)malloc(sizeof(double) * (size_t)nn); orc_weights(p->g, nn, m->weights); }
+  }
+}
+static void metric_free(orc_metric *m) {
+  free(m->cost); free(m->cost_prev); free(m->aux_x); free(m->aux_y); free(m->weights);
+}
+
+/* `ea` = 0: Metric.distance; `ea` = 1: Metric.eadistance -- returns the raw distance the
+ * reference compares against *min_dist (INFINITY when abandoned); *valid=0 for ddtw's
+ * "return 0/False" early exit (EL:3297-3298). */
+static double metric_eval(orc_metric *m, const double *x, int64_t ix, const double *y, int64_t iy,
+                          int ea, double md, int *valid) {
+  int64_t Tx = m->Tx, Ty = m->Ty;
+  int64_t Tmin = i64min(Tx, Ty), Tmax = i64max(Tx, Ty);
+  int64_t R = orc_compute_r(Tmin, m->p.r);
+  *valid = 1;
+  switch (m->metric) {
+    case ORC_DTW: case ORC_WDTW:
+      return sqrt(dtw_distance(x, Tx, y, Ty, R, m->cost, m->cost_prev, m->weights, ea ? md * md : INFINITY));
+    case ORC_ADTW:
+      return sqrt(adtw_distance(x, Tx, y, Ty, R, m->cost, m->cost_prev, m->p.p, ea ? md * md : INFINITY));
+    case ORC_DDTW: case ORC_WDDTW: {
+      if (Tmin < 3) { *valid = 0; return 0.0; }
+      orc_average_slope(x, Tx, m->aux_x);
+      orc_average_slope(y, Ty, m->aux_y);
+      /* EL:3280 uses the original lengths for R, EL:3308 (eadistance) the derivative lengths */
+      int64_t Rd = ea ? orc_compute_r(i64min(Tx - 2, Ty - 2), m->p.r) : R;
+      return sqrt(dtw_distance(m->aux_x, Tx - 2, m->aux_y, Ty - 2, Rd, m->cost, m->cost_prev, m->weights,
+                               ea ? md * md : INFINITY));
+    }
+    case ORC_LCSS: case ORC_WLCSS: {
+      double t = INFINITY;
+      if (ea && !isinf(md)) t = (double)Tmin - md * (double)Tmin; /* EL:3526-3528 */
+      return lcss_distance(x, Tx, y, Ty, R, m->p.epsilon, m->cost, m->cost_prev, m->weights, t);
+    }
+    case ORC_ERP:
+      return erp_distance(x, Tx, y, Ty, R, m->p.g, m->aux_x, m->aux_y, m->cost, m->cost_prev, ea ? md : INFINITY);
+    case ORC_EDR: {
+      double eps = m->p.epsilon;
+      if (isnan(eps)) eps = dmax(m->std_x[ix], m->std_y[iy]) / 4.0; /* EL:3762-3766 */
+      int64_t Re = ea ? orc_compute_r(Tx, m->p.r) : R;            /* EL:3833 (X twice) */
+      return edr_distance(x, Tx, y, Ty, Re, eps, m->cost, m->cost_prev, ea ? md * (double)Tmax : INFINITY);
+    }
+    case ORC_MSM:
+      return msm_distance(x, Tx, y, Ty, R, m->p.c, m->cost, m->cost_prev, m->aux_x, ea ? md : INFINITY);
+    case ORC_TWE:
+      return twe_distance(x, Tx, y, Ty, R, m->p.penalty, m->p.stiffness, m->cost, m->cost_prev, ea ? md : INFINITY);
+  }
+  *valid = 0;
+  return NAN;
+}
+
+static double *sample_std(int metric, const orc_params *p, const double *x, int64_t n, int64_t T, int64_t stride) {
+  if (metric != ORC_EDR || !isnan(p->epsilon)) return NULL;
+  double *s = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+  for (int64_t i = 0; i < n; i++) s[i] = orc_std(x + i * stride, T); /* EL:3743-3752 */
+  return s;
+}
+
+/* utils/_parallel.py:7-23 contiguous row blocks */
+static void row_block(int64_t n, int nb, int b, int64_t *lo, int64_t *hi) {
+  int64_t bs = n / nb, ov = n % nb;
+  *lo = b * bs + (b < ov ? b : ov);
+  *hi = *lo + bs + (b < ov ? 1 : 0);
+}
+
+static int pick_threads(int nthreads, int64_t n_work) {
+  if (nthreads <= 0) {
+    long nc = sysconf(_SC_NPROCESSORS_ONLN);
+    nthreads = nc > 0 ? (int)nc : 1;
+  }
+  if (nthreads > n_work) nthreads = (int)(n_work > 0 ? n_work : 1);
+  return nthreads;
+}
+
+/* ---- threading: one worker per contiguous row block, like joblib threads (CD:1193-1203) ---- */
+typedef struct orc_job {
+  int kind; /* 0 pairwise, 1 self, 2 paired, 3 argmin */
+  int metric; const orc_params *p;
+  const double *x, *y; int64_t nx, ny, Tx, Ty, xs, ys;
+  const double *sx, *sy;
+  double *out;
+  int64_t k; const double *lower_bound; int64_t *out_idx;
+  int nb;
+} orc_job;
+typedef struct { const orc_job *job; int b; } orc_task;
+
+static void job_block(const orc_job *J, int b);
+static void *task_main(void *arg) { orc_task *t = (orc_task *)arg; job_block(t->job, t->b); return NULL; }
+static void run_job(orc_job *J) {
+  if (J->nb <= 1) { J->nb = 1; job_block(J, 0); return; }
+  pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)J->nb);
+  orc_task *ts = (orc_task *)malloc(sizeof(orc_task) * (size_t)J->nb);
+  for (int b = 0; b < J->nb; b++) { ts[b].job = J; ts[b].b = b; pthread_create(&th[b], NULL, task_main, &ts[b]); }
+  for (int b = 0; b < J->nb; b++) pthread_join(th[b], NULL);
+  free(th); free(ts);
+}
+
+/* MI:18-107 bounded max-heap of the k smallest (value, index) */
+typedef struct { int64_t index; double value; } heap_el;
+static void heap_shift_down(heap_el *h, int64_t startpos, int64_t pos) {
+  heap_el ne = h[pos];
+  while (pos > startpos) {
+    int64_t parent = (pos - 1) >> 1;
+    if (ne.value > h[parent].value) { h[pos] = h[parent]; pos = parent; continue; }
+    break;
+  }
+  h[pos] = ne;
+}
+static void heap_shift_up(heap_el *h, int64_t pos, int64_t endpos) {
+  int64_t startpos = pos;
+  heap_el ne = h[pos];
+  int64_t child = 2 * pos + 1;
+  while (child < endpos) {
+    int64_t right = child + 1;
+    if (right < endpos && h[child].value < h[right].value) child = right;
+    h[pos] = h[child];
+    pos = child;
+    child = 2 * pos + 1;
+  }
+  h[pos] = ne;
+  heap_shift_down(h, startpos, pos);
+}
+typedef struct { heap_el *h; int64_t n, cap; } orc_heap;
+static void heap_push(orc_heap *hp, int64_t index, double value) {
+  heap_el e; e.index = index; e.value = value;
+  if (hp->n == 0) { hp->h[0] = e; hp->n = 1; }
+  else if (hp->n < hp->cap) { hp->h[hp->n] = e; hp->n++; heap_shift_down(hp->h, 0, hp->n - 1); }
+  else if (hp->h[0].value > e.value) { hp->h[0] = e; heap_shift_up(hp->h, 0, hp->cap); }
+}
+
+/* Exposed for host-side replay tests: push (index[i], value[i]) in order, dump heap array. */
+void orc_heap_replay(int64_t k, int64_t n, const int64_t *index, const double *value, int64_t *out_idx,
+                     double *out_val, int64_t *out_n) {
+  orc_heap hp; hp.h = (heap_el *)calloc((size_t)k, sizeof(heap_el)); hp.n = 0; hp.cap = k;
+  for (int64_t i = 0; i < n; i++) heap_push(&hp, index[i], value[i]);
+  for (int64_t i = 0; i < k; i++) { out_idx[i] = hp.h[i].index; out_val[i] = hp.h[i].value; }
+  *out_n = hp.n;
+  free(hp.h);
+}
+
+static void job_block(const orc_job *J, int b) {
+  int64_t lo, hi, n_work = J->nx;
+  row_block(n_work, J->nb, b, &lo, &hi);
+  orc_metric m;
+  int valid;
+  if (J->kind == 0) {        /* CD:1144-1205 */
+    metric_init(&m, J->metric, J->p, J->Tx, J->Ty, J->sx, J->sy);
+    for (int64_t i = lo; i < hi; i++)
+      for (int64_t j = 0; j < J->ny; j++)
+        J->out[i * J->ny + j] = metric_eval(&m, J->x + i * J->xs, i, J->y + j * J->ys, j, 0, INFINITY, &valid);
+  } else if (J->kind == 1) { /* CD:1208-1267: upper triangle computed, mirrored, zero diagonal */
+    metric_init(&m, J->metric, J->p, J->Tx, J->Tx, J->sx, J->sx);
+    for (int64_t i = lo; i < hi; i++)
+      for (int64_t j = i + 1; j < J->nx; j++) {
+        double d = metric_eval(&m, J->x + i * J->xs, i, J->x + j * J->xs, j, 0, INFINITY, &valid);
+        J->out[i * J->nx + j] = d; J->out[j * J->nx + i] = d;
+      }
+  } else if (J->kind == 2) { /* CD:1597-1652: first operand = the USER's y (argument swap) */
+    metric_init(&m, J->metric, J->p, J->Ty, J->Tx, J->sy, J->sx);
+    for (int64_t i = lo; i < hi; i++)
+      J->out[i] = metric_eval(&m, J->y + i * J->ys, i, J->x + i * J->xs, i, 0, INFINITY, &valid);
+  } else {                   /* CD:1270-1378 */
+    metric_init(&m, J->metric, J->p, J->Tx, J->Ty, J->sx, J->sy);
+    orc_heap hp; hp.h = (heap_el *)calloc((size_t)J->k, sizeof(heap_el)); hp.cap = J->k;
+    for (int64_t i = lo; i < hi; i++) {
+      double distance = INFINITY;
+      hp.n = 0;
+      for (int64_t j = 0; j < J->ny; j++) {
+        if (J->lower_bound && J->lower_bound[i * J->ny + j] >= distance) continue;
+        double d = metric_eval(&m, J->x + i * J->xs, i, J->y + j * J->ys, j, 1, distance, &valid);
+        if (valid && d < distance) {
+          heap_push(&hp, j, d);
+          distance = (hp.n == hp.cap) ? hp.h[0].value : INFINITY;
+        }
+      }
+      for (int64_t j = 0; j < J->k; j++) { J->out_idx[i * J->k + j] = hp.h[j].index; J->out[i * J->k + j] = hp.h[j].value; }
+    }
+    free(hp.h);
+  }
+  metric_free(&m);
+}
+
+int orc_pairwise(int metric, const orc_params *p, const double *x, int64_t nx, int64_t Tx, int64_t xs,
+                 const double *y, int64_t ny, int64_t Ty, int64_t ys, double *out, int nthreads) {
+  if (metric < 0 || metric >= ORC_N_METRICS || Tx < 1 || Ty < 1) return 1;
+  orc_job J; memset(&J, 0, sizeof J);
+  J.kind = 0; J.metric = metric; J.p = p; J.x = x; J.y = y; J.nx = nx; J.ny = ny; J.Tx = Tx; J.Ty = Ty; J.xs = xs; J.ys = ys;
+  double *sx = sample_std(metric, p, x, nx, Tx, xs), *sy = sample_std(metric, p, y, ny, Ty, ys);
+  J.sx = sx; J.sy = sy; J.out = out; J.nb = pick_threads(nthreads, nx);
+  run_job(&J);
+  free(sx); free(sy);
+  return 0;
+}
+
+int orc_pairwise_self(int metric, const orc_params *p, const double *x, int64_t n, int64_t T, int64_t xs,
+                      double *out, int nthreads) {
+  if (metric < 0 || metric >= ORC_N_METRICS || T < 1) return 1;
+  orc_job J; memset(&J, 0, sizeof J);
+  J.kind = 1; J.metric = metric; J.p = p; J.x = x; J.nx = n; J.Tx = T; J.xs = xs;
+  double *sx = sample_std(metric, p, x, n, T, xs);
+  J.sx = sx; J.out = out; J.nb = pick_threads(nthreads, n);
+  for (int64_t i = 0; i < n * n; i++) out[i] = 0.0;
+  run_job(&J);
+  free(sx);
+  return 0;
+}
+
+/* `x`/`y` are the USER's x and y; the reference's swap is applied inside (kind 2). */
+int orc_paired(int metric, const orc_params *p, const double *x, int64_t n, int64_t Tx, int64_t xs,
+               const double *y, int64_t Ty, int64_t ys, double *out, int nthreads) {
+  if (metric < 0 || metric >= ORC_N_METRICS || Tx < 1 || Ty < 1) return 1;
+  orc_job J; memset(&J, 0, sizeof J);
+  J.kind = 2; J.metric = metric; J.p = p; J.x = x; J.y = y; J.nx = n; J.ny = n; J.Tx = Tx; J.Ty = Ty; J.xs = xs; J.ys = ys;
+  double *sx = sample_std(metric, p, x, n, Tx, xs), *sy = sample_std(metric, p, y, n, Ty, ys);
+  J.sx = sx; J.sy = sy; J.out = out; J.nb = pick_threads(nthreads, n);
+  run_job(&J);
+  free(sx); free(sy);
+  return 0;
+}
+
+/* lower_bound may be NULL (else nx*ny row-major). Output in the reference heap's array order. */
+int orc_argmin(int metric, const orc_params *p, const double *x, int64_t nx, int64_t Tx, int64_t xs,
+               const double *y, int64_t ny, int64_t Ty, int64_t ys, int64_t k, const double *lower_bound,
+               int64_t *out_idx, double *out_dist, int nthreads) {
+  if (metric < 0 || metric >= ORC_N_METRICS || Tx < 1 || Ty < 1 || k < 1) return 1;
+  orc_job J; memset(&J, 0, sizeof J);
+  J.kind = 3; J.metric = metric; J.p = p; J.x = x; J.y = y; J.nx = nx; J.ny = ny; J.Tx = Tx; J.Ty = Ty; J.xs = xs; J.ys = ys;
+  double *sx = sample_std(metric, p, x, nx, Tx, xs), *sy = sample_std(metric, p, y, ny, Ty, ys);
+  J.sx = sx; J.sy = sy; J.out = out_dist; J.out_idx = out_idx; J.k = k; J.lower_bound = lower_bound;
+  J.nb = pick_threads(nthreads, nx);
+  run_job(&J);
+  free(sx); free(sy);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * DTW lower bounds (LB:198-432, EL:98-151, 228-260, 1076-1115, distance/dtw.py:38-40)
+ * ---------------------------------------------------------------------------------------- */
+
+/* distance/dtw.py:38-40 / EL:1917-1921 */
+int64_t orc_compute_warp_width(int64_t length, double r) {
+  if (r == 1) return length - 1;
+  return (int64_t)floor((double)length * r);
+}
+
+/* EL:98-151 find_min_max semantics: lower[k] = min T[k-w..k+w], upper[k] = max (clipped).
+ * Written directly (O(T w)); min/max of doubles are exact so any evaluation order matches. */
+void orc_envelope(const double *t, int64_t n, int64_t w, double *lower, double *upper) {
+  for (int64_t k = 0; k < n; k++) {
+    int64_t a = i64max(0, k - w), b = i64min(n - 1, k + w);
+    double lo = t[a], hi = t[a];
+    for (int64_t q = a + 1; q <= b; q++) { lo = dmin(lo, t[q]); hi = dmax(hi, t[q]); }
+    lower[k] = lo; upper[k] = hi;
+  }
+}
+
+/* EL:228-260 cumulative_bound summed + EL:1095-1115: sqrt(sum of squared envelope excess) */
+double orc_lb_keogh_one(const double *q, const double *lower, const double *upper, int64_t n) {
+  double s = 0;
+  for (int64_t i = 0; i < n; i++) {
+    double v = q[i], d = 0;
+    if (v > upper[i]) { d = v - upper[i]; d = d * d; }
+    else if (v < lower[i]) { d = lower[i] - v; d = d * d; }
+    s += d;
+  }
+  return sqrt(s);
+}

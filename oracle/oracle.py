@@ -1,0 +1,174 @@
+"""TEST INFRASTRUCTURE -- ctypes front-end of oracle/_build/liboracle.so (elastic_oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) import
+this module.  It mirrors the reference's three entry points on 2-D float64 arrays
+(dim already selected):
+
+  pairwise(metric, x, y=None, **params)  -> (nx, ny)   reference: _distance.py:1178
+  paired(metric, x, y, **params)         -> (n,)       reference: _distance.py:1082 (swapped operands)
+  argmin(metric, x, y, k, lower_bound, **params) -> (idx, dist) in heap order, _distance.py:1320
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+
+METRIC_IDS = {
+    "dtw": 0, "wdtw": 1, "ddtw": 2, "adtw": 3, "lcss": 4, "erp": 5,
+    "edr": 6, "msm": 7, "twe": 8, "wddtw": 9, "wlcss": 10,
+}
+
+# defaults of the reference constructors
+DEFAULTS = {
+    "dtw": dict(r=1.0), "wdtw": dict(r=1.0, g=0.05), "ddtw": dict(r=1.0), "adtw": dict(r=1.0, p=1.0),
+    "lcss": dict(r=1.0, epsilon=1.0), "erp": dict(r=1.0, g=0.0), "edr": dict(r=1.0, epsilon=float("nan")),
+    "msm": dict(r=1.0, c=1.0), "twe": dict(r=1.0, penalty=1.0, stiffness=0.001),
+    "wddtw": dict(r=1.0, g=0.05), "wlcss": dict(r=1.0, epsilon=1.0, g=0.05),
+}
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("r", "g", "p", "c", "epsilon", "penalty", "stiffness")]
+
+
+def build(force=False):
+    if force or not os.path.exists(_LIB_PATH) or (
+        os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "elastic_oracle.c"))
+    ):
+        subprocess.check_call(["make", "-C", _HERE, "_build/liboracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int64)
+        i64 = C.c_int64
+        _lib.orc_pairwise.argtypes = [C.c_int, C.POINTER(Params), dp, i64, i64, i64, dp, i64, i64, i64, dp, C.c_int]
+        _lib.orc_pairwise_self.argtypes = [C.c_int, C.POINTER(Params), dp, i64, i64, i64, dp, C.c_int]
+        _lib.orc_paired.argtypes = [C.c_int, C.POINTER(Params), dp, i64, i64, i64, dp, i64, i64, dp, C.c_int]
+        _lib.orc_argmin.argtypes = [C.c_int, C.POINTER(Params), dp, i64, i64, i64, dp, i64, i64, i64, i64, dp, ip, dp, C.c_int]
+        _lib.orc_heap_replay.argtypes = [i64, i64, ip, dp, ip, dp, ip]
+        _lib.orc_envelope.argtypes = [dp, i64, i64, dp, dp]
+        _lib.orc_lb_keogh_one.argtypes = [dp, dp, dp, i64]
+        _lib.orc_lb_keogh_one.restype = C.c_double
+        _lib.orc_compute_r.argtypes = [i64, C.c_double]
+        _lib.orc_compute_r.restype = i64
+        _lib.orc_std.argtypes = [dp, i64]
+        _lib.orc_std.restype = C.c_double
+    return _lib
+
+
+def make_params(metric, **kw):
+    d = dict(r=1.0, g=0.0, p=1.0, c=1.0, epsilon=1.0, penalty=1.0, stiffness=0.001)
+    d.update(DEFAULTS[metric])
+    for k, v in kw.items():
+        if k not in DEFAULTS[metric]:
+            raise TypeError(f"unexpected metric param {k!r} for {metric}")
+        d[k] = float(v)
+    return Params(**d)
+
+
+def _arr(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if a.ndim == 1:
+        a = a.reshape(1, -1)
+    assert a.ndim == 2
+    return a
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def pairwise(metric, x, y=None, n_jobs=1, **params):
+    p = make_params(metric, **params)
+    x = _arr(x)
+    if y is None:
+        out = np.empty((x.shape[0], x.shape[0]))
+        rc = lib().orc_pairwise_self(METRIC_IDS[metric], C.byref(p), _dp(x), x.shape[0], x.shape[1], x.shape[1], _dp(out), n_jobs)
+    else:
+        y = _arr(y)
+        out = np.empty((x.shape[0], y.shape[0]))
+        rc = lib().orc_pairwise(METRIC_IDS[metric], C.byref(p), _dp(x), x.shape[0], x.shape[1], x.shape[1],
+                                _dp(y), y.shape[0], y.shape[1], y.shape[1], _dp(out), n_jobs)
+    assert rc == 0
+    return out
+
+
+def paired(metric, x, y, n_jobs=1, **params):
+    p = make_params(metric, **params)
+    x, y = _arr(x), _arr(y)
+    assert x.shape[0] == y.shape[0]
+    out = np.empty(x.shape[0])
+    rc = lib().orc_paired(METRIC_IDS[metric], C.byref(p), _dp(x), x.shape[0], x.shape[1], x.shape[1],
+                          _dp(y), y.shape[1], y.shape[1], _dp(out), n_jobs)
+    assert rc == 0
+    return out
+
+
+def argmin(metric, x, y, k=1, lower_bound=None, n_jobs=1, **params):
+    p = make_params(metric, **params)
+    x, y = _arr(x), _arr(y)
+    k = min(k, y.shape[0])
+    idx = np.zeros((x.shape[0], k), dtype=np.int64)
+    dist = np.zeros((x.shape[0], k))
+    lb = None
+    if lower_bound is not None:
+        lb = np.ascontiguousarray(lower_bound, dtype=np.float64)
+        assert lb.shape == (x.shape[0], y.shape[0])
+    rc = lib().orc_argmin(METRIC_IDS[metric], C.byref(p), _dp(x), x.shape[0], x.shape[1], x.shape[1],
+                          _dp(y), y.shape[0], y.shape[1], y.shape[1], k, _dp(lb) if lb is not None else None,
+                          idx.ctypes.data_as(C.POINTER(C.c_int64)), _dp(dist), n_jobs)
+    assert rc == 0
+    return idx, dist
+
+
+def heap_replay(k, index, value):
+    index = np.ascontiguousarray(index, dtype=np.int64)
+    value = np.ascontiguousarray(value, dtype=np.float64)
+    oi = np.zeros(k, dtype=np.int64)
+    ov = np.zeros(k)
+    n = C.c_int64(0)
+    ip = C.POINTER(C.c_int64)
+    lib().orc_heap_replay(k, len(index), index.ctypes.data_as(ip), _dp(value), oi.ctypes.data_as(ip), _dp(ov), C.byref(n))
+    return oi, ov, n.value
+
+
+def envelope(t, w):
+    t = np.ascontiguousarray(t, dtype=np.float64)
+    lo, hi = np.empty_like(t), np.empty_like(t)
+    lib().orc_envelope(_dp(t), len(t), int(w), _dp(lo), _dp(hi))
+    return lo, hi
+
+
+def lb_keogh_one(q, lower, upper):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    return lib().orc_lb_keogh_one(_dp(q), _dp(np.ascontiguousarray(lower)), _dp(np.ascontiguousarray(upper)), len(q))
+
+
+def compute_r(n, r):
+    return lib().orc_compute_r(int(n), float(r))
+
+
+def cells_per_pair(Tx, Ty, r, metric="dtw"):
+    """DP cells the reference evaluates for one pair: sum_i (j_stop(i) - j_start(i))."""
+    R = compute_r(min(Tx, Ty), r)
+    if metric in ("ddtw", "wddtw"):
+        Tx, Ty = Tx - 2, Ty - 2
+        if min(Tx, Ty) < 1:
+            return 0
+    max_len = max(0, Ty - Tx) + R
+    min_len = max(0, Tx - Ty)
+    i = np.arange(Tx)
+    js = np.maximum(0, i - min_len - R + 1)
+    je = np.minimum(Ty, i + max_len)
+    return int(np.sum(np.maximum(je - js, 0)))
