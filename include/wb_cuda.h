@@ -1,0 +1,117 @@
+/*
+ * wb_cuda.h -- C ABI of libwbcuda.so: B200 (sm_100a) kernels for wildboar's elastic-distance
+ * hot path.  Plain pointers and sizes only; no exceptions cross this boundary.
+ *
+ * Each entry point replaces one Cython batch driver of the reference
+ * (src/wildboar/distance/_cdistance.pyx, "CD") specialised to the elastic Metric classes of
+ * src/wildboar/distance/_elastic.pyx ("EL"); the reference-side binding is shown in
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *   - return 0 on success, non-zero on error; wb_cuda_last_error() returns a thread-local
+ *     message for the last failing call on this thread.
+ *   - host entry points take caller-owned HOST buffers (float64, last axis contiguous,
+ *     `*_stride` = elements between consecutive samples, dim already selected -- the
+ *     reference's TSArray view `&X[i, dim, 0]`, utils/__init__.pxd:4); the library stages,
+ *     shards rows over `devices` and gathers.  They may be called with the GIL released.
+ *   - `*_dev` entry points take DEVICE pointers on the current device and enqueue on `stream`
+ *     (a cudaStream_t); they do not synchronise except where stated.
+ *   - there is NO CPU fallback: without an sm_100 device every compute call fails.
+ */
+#ifndef WB_CUDA_H
+#define WB_CUDA_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* metric ids == keys of _METRICS (distance/_distance.py:186-205) that are elastic */
+enum {
+  WB_DTW = 0,   /* DtwMetric                   EL:3126 */
+  WB_WDTW = 1,  /* WeightedDtwMetric           EL:3322 */
+  WB_DDTW = 2,  /* DerivativeDtwMetric         EL:3228 */
+  WB_ADTW = 3,  /* AmercingDtwMetric           EL:3344 */
+  WB_LCSS = 4,  /* LcssMetric                  EL:3433 */
+  WB_ERP = 5,   /* ErpMetric                   EL:3564 */
+  WB_EDR = 6,   /* EdrMetric                   EL:3671 */
+  WB_MSM = 7,   /* MsmMetric                   EL:3887 */
+  WB_TWE = 8,   /* TweMetric                   EL:3985 */
+  WB_WDDTW = 9, /* WeightedDerivativeDtwMetric EL:3404 (Tx <= Ty only: the reference overflows otherwise) */
+  WB_WLCSS = 10 /* WeightedLcssMetric          EL:3542 */
+};
+
+/* metric_params of the reference constructors (already validated by the caller) */
+typedef struct wb_params {
+  double r;         /* all: Sakoe-Chiba window fraction in [0,1]                   */
+  double g;         /* wdtw/wddtw/wlcss: weight steepness; erp: gap value          */
+  double p;         /* adtw: penalty                                               */
+  double c;         /* msm: cost                                                   */
+  double epsilon;   /* lcss/wlcss/edr: threshold; NaN = edr default max(std)/4     */
+  double penalty;   /* twe                                                         */
+  double stiffness; /* twe                                                         */
+  int32_t engine;   /* 0 auto, 1 force row-scan engine, 2 force strip engine       */
+  int32_t reserved;
+} wb_params;
+
+/* timing / work counters of the last call (optional out-parameter) */
+typedef struct wb_stats {
+  double kernel_ms;     /* device time of the DP kernels (CUDA events), max over devices */
+  double total_ms;      /* device time incl. staging copies, max over devices            */
+  int64_t cells;        /* DP cells evaluated (reference cell count)          */
+  int64_t pairs;        /* pairs evaluated                                               */
+  int32_t launches;     /* kernels launched by this call                                 */
+  int32_t engine;       /* engine used for the DP (1 row-scan, 2 strip)                  */
+} wb_stats;
+
+int wb_cuda_device_count(void);
+const char *wb_cuda_last_error(void);
+
+/* out[i*ny + j] = metric(x[i], y[j]).  Replaces _pairwise_distance, CD:1184-1205. */
+int wb_cuda_pairwise(int metric, const wb_params *params,
+                     const double *x, int64_t nx, int64_t Tx, int64_t x_stride,
+                     const double *y, int64_t ny, int64_t Ty, int64_t y_stride,
+                     double *out, const int *devices, int n_devices, wb_stats *stats);
+
+/* out (n*n): j > i computed, mirrored to [j][i], zero diagonal.
+ * Replaces _singleton_pairwise_distance, CD:1248-1267. */
+int wb_cuda_pairwise_self(int metric, const wb_params *params,
+                          const double *x, int64_t n, int64_t T, int64_t x_stride,
+                          double *out, const int *devices, int n_devices, wb_stats *stats);
+
+/* out[i] = metric(y[i], x[i]) -- the reference evaluates the operands swapped (CD:1632-1647);
+ * x and y here are the USER's x and y.  Replaces _paired_distance, CD:1632-1652. */
+int wb_cuda_paired(int metric, const wb_params *params,
+                   const double *x, int64_t n, int64_t Tx, int64_t x_stride,
+                   const double *y, int64_t Ty, int64_t y_stride,
+                   double *out, const int *devices, int n_devices, wb_stats *stats);
+
+/* k nearest y for every x under the reference's sequential early-abandoning scan.
+ * out_idx / out_dist: (nx, k) in the reference heap's array order (utils/_misc.pyx:62-107).
+ * lower_bound: optional (nx, ny) matrix, pairs with lower_bound >= running threshold are
+ * skipped (CD:1331).  use_device_lb != 0 (dtw only): additionally prune with the on-device
+ * LB_Kim / LB_Keogh cascade (never changes the result).
+ * Replaces _argmin_distance, CD:1348-1378. */
+int wb_cuda_argmin(int metric, const wb_params *params,
+                   const double *x, int64_t nx, int64_t Tx, int64_t x_stride,
+                   const double *y, int64_t ny, int64_t Ty, int64_t y_stride,
+                   int64_t k, const double *lower_bound, int use_device_lb,
+                   int64_t *out_idx, double *out_dist,
+                   const int *devices, int n_devices, wb_stats *stats);
+
+/* Device-resident variant of wb_cuda_pairwise: d_x (nx, Tx), d_y (ny, Ty), d_out (nx, ny) are
+ * dense row-major DEVICE arrays on the current device.  Enqueues on `stream`; fills `stats`
+ * (after synchronising the stream) when stats != NULL. */
+int wb_cuda_pairwise_dev(int metric, const wb_params *params,
+                         const double *d_x, int64_t nx, int64_t Tx,
+                         const double *d_y, int64_t ny, int64_t Ty,
+                         double *d_out, void *stream, wb_stats *stats);
+
+/* Measured FP64 issue rate of the current device: runs a register-only DADD/DMUL chain on
+ * every SM and returns FP64 warp-lane instructions per second (the ALU roofline denominator,
+ * SURVEY 8d).  mix: 0 = DADD only, 1 = DTW cell mix (3 arithmetic + 2 compare/select). */
+int wb_cuda_fp64_peak(int mix, double *inst_per_s, double *sm_mhz_est);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WB_CUDA_H */

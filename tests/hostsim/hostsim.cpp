@@ -1,0 +1,76 @@
+// TEST INFRASTRUCTURE: compiles the device engines (wildboar_b200/csrc/engine_*.cuh) for the
+// HOST with g++ and runs them one emulated thread at a time, so the band/strip logic can be
+// checked bit-for-bit against the oracle without a GPU.  Not linked into the product library.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../wildboar_b200/csrc/dispatch.cuh"
+#include "../../wildboar_b200/csrc/engine_rowscan.cuh"
+#include "../../wildboar_b200/csrc/engine_strip.cuh"
+#include "../../wildboar_b200/csrc/prep.hpp"
+
+using namespace wb;
+
+template <int W>
+struct StripRunner {
+  template <class M>
+  static double run(const Geom& g, const M& m, const double* x, const double* y, int NS, int bs, double abandon, int* ok) {
+    if (!strip_supported<M>(g, W)) { *ok = 0; return 0; }
+    *ok = 1;
+    std::vector<double> bnd((size_t)NS * bs + 8, -12345.0);
+    return strip_pair<M, W>(g, m, x, y, bnd.data(), bs, NS, abandon);
+  }
+};
+
+// engine: 1 row-scan, 2 strip.  ea: 0 distance() / 1 eadistance() semantics for R (ddtw, edr).
+// Returns 0 ok, 1 unsupported by this engine, 2 bad args.
+extern "C" int hostsim_pair(int engine, int W, int metric, const wb_params* p, const double* x, int64_t Tx,
+                            const double* y, int64_t Ty, int ea, double min_dist_raw, int ns_extra, int bs,
+                            double* out, double* out_rowminmax) {
+  std::vector<double> dx, dy;
+  int64_t tx = Tx, ty = Ty;
+  int64_t R = compute_r(Tx < Ty ? Tx : Ty, p->r);
+  if (is_derivative(metric)) {
+    if ((Tx < Ty ? Tx : Ty) < 3) { *out = 0.0; return 0; }
+    dx.resize(Tx - 2); dy.resize(Ty - 2);
+    average_slope(x, Tx, dx.data()); average_slope(y, Ty, dy.data());
+    x = dx.data(); y = dy.data(); tx = Tx - 2; ty = Ty - 2;
+    if (ea) R = compute_r(tx < ty ? tx : ty, p->r);
+  }
+  if (metric == M_EDR && ea) R = compute_r(Tx, p->r);
+  int64_t nmax = tx > ty ? tx : ty;
+  std::vector<double> w, tw;
+  if (metric == M_WDTW || metric == M_WLCSS) w = make_weights(p->g, nmax);
+  if (metric == M_WDDTW) w = make_weights(p->g, nmax);
+  if (metric == M_TWE) tw = make_tw(p->stiffness, nmax + 1);
+  Tables t{w.data(), tw.data()};
+  PairCtx pc{0, 0};
+  if (metric == M_ERP) { pc.sx = seq_gap_sum(x, tx, p->g); pc.sy = seq_gap_sum(y, ty, p->g); }
+  if (metric == M_EDR) { pc.sx = seq_std(x, tx); pc.sy = seq_std(y, ty); }
+  Geom g = make_geom((int)tx, (int)ty, (int)R);
+  int rc = 0;
+  bool known = with_policy(metric, *p, t, [&](auto m) {
+    m.begin_pair(pc);
+    if (engine == 1) {
+      std::vector<double> b0((size_t)(nmax + 1) * bs, -777.0), b1((size_t)(nmax + 1) * bs, -888.0);
+      double mm = 0;
+      *out = rowscan_pair(g, m, x, y, b0.data(), b1.data(), (long long)bs, min_dist_raw, &mm);
+      if (out_rowminmax) *out_rowminmax = mm;
+    } else {
+      int NS = strip_ring_slots(g) + ns_extra;
+      int ok = 0;
+      double r = 0;
+      switch (W) {
+        case 2: r = StripRunner<2>::run(g, m, x, y, NS, bs, min_dist_raw, &ok); break;
+        case 3: r = StripRunner<3>::run(g, m, x, y, NS, bs, min_dist_raw, &ok); break;
+        case 4: r = StripRunner<4>::run(g, m, x, y, NS, bs, min_dist_raw, &ok); break;
+        case 8: r = StripRunner<8>::run(g, m, x, y, NS, bs, min_dist_raw, &ok); break;
+        case 16: r = StripRunner<16>::run(g, m, x, y, NS, bs, min_dist_raw, &ok); break;
+        default: ok = 0;
+      }
+      if (!ok) rc = 1; else *out = r;
+    }
+  });
+  if (!known) return 2;
+  return rc;
+}

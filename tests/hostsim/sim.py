@@ -1,0 +1,49 @@
+"""TEST INFRASTRUCTURE: ctypes wrapper around tests/hostsim/_hostsim.so (device engines compiled for the host)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_hostsim.so")
+_ROOT = os.path.join(_HERE, "..", "..")
+
+
+class WbParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("r", "g", "p", "c", "epsilon", "penalty", "stiffness")] + [
+        ("engine", C.c_int32), ("reserved", C.c_int32)]
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, "hostsim.cpp")] + [
+        os.path.join(_ROOT, "wildboar_b200", "csrc", f)
+        for f in ("metrics.cuh", "engine_strip.cuh", "engine_rowscan.cuh", "dispatch.cuh", "prep.hpp")]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared",
+                               "-Wno-unknown-pragmas", "-o", _SO, srcs[0]])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        dp = C.POINTER(C.c_double)
+        _lib.hostsim_pair.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(WbParams), dp, C.c_int64, dp, C.c_int64,
+                                      C.c_int, C.c_double, C.c_int, C.c_int, dp, dp]
+    return _lib
+
+
+def pair(engine, W, metric_id, params, x, y, ea=0, min_dist_raw=float("inf"), ns_extra=0, bs=1):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    out = C.c_double(0)
+    mm = C.c_double(0)
+    dp = C.POINTER(C.c_double)
+    rc = lib().hostsim_pair(engine, W, metric_id, C.byref(params), x.ctypes.data_as(dp), len(x), y.ctypes.data_as(dp),
+                            len(y), ea, min_dist_raw, ns_extra, bs, C.byref(out), C.byref(mm))
+    return rc, out.value, mm.value

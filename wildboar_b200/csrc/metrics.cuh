@@ -1,0 +1,294 @@
+// Metric policies for the banded-DP engines.
+//
+// Every elastic metric of the reference (wildboar/distance/_elastic.pyx, "EL") is expressed
+// as ONE uniform recurrence over DP cells (i, j):
+//
+//     D[i][j] = cell(up = D[i-1][j], left = D[i][j-1], diag = D[i-1][j-1], row ctx, col ctx)
+//
+// plus a small set of boundary constants that reproduce what the reference's two scratch
+// rows contain just outside the Sakoe-Chiba band:
+//
+//     prev_init : value of the virtual row -1 inside the band of row 0
+//     usent     : what a cell reads as `up` when (i-1, j) is above the band
+//     lsent     : what a cell reads as `left` when (i, j-1) is left of the band
+//                 (MSM: never reset by the reference => stale value, handled by the engine)
+//     left0(i), diag0(i) : the j == 0 special cases
+//
+// The reference special-cases row 0 for dtw/adtw/msm (prefix sums); with the constants
+// below the general recurrence produces the identical operations, e.g. for DTW row 0
+// min(min(INF, left), INF) + c == left + c and 0 + c == c are exact.
+//
+// All arithmetic is IEEE double with ONE rounding per operation: the library is compiled with
+// -fmad=false, so no FMA contraction happens and results are bit-identical to the
+// reference's -O2 x86-64 build (which contains no FMA instructions).
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define WB_HD __host__ __device__ __forceinline__
+#else
+#define WB_HD inline
+#endif
+
+namespace wb {
+
+enum MetricId : int {
+  M_DTW = 0, M_WDTW = 1, M_DDTW = 2, M_ADTW = 3, M_LCSS = 4, M_ERP = 5,
+  M_EDR = 6, M_MSM = 7, M_TWE = 8, M_WDDTW = 9, M_WLCSS = 10, M_COUNT = 11
+};
+
+#if defined(__CUDA_ARCH__)
+#define WB_INF __longlong_as_double(0x7ff0000000000000LL)
+#else
+#define WB_INF ((double)INFINITY)
+#endif
+
+WB_HD double dmin2(double a, double b) { return a < b ? a : b; }
+WB_HD double dmax2(double a, double b) { return a > b ? a : b; }
+WB_HD int imin2(int a, int b) { return a < b ? a : b; }
+WB_HD int imax2(int a, int b) { return a > b ? a : b; }
+WB_HD int iabs1(int a) { return a < 0 ? -a : a; }
+
+// Read-only global load (table lookups that are uniform across a warp).
+WB_HD double ldg(const double* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
+// Band geometry shared by every metric (EL:890-891, 909-910 and the same expressions inlined
+// in the other kernels).  R = max(floor(min(Tx,Ty) * r), 1) is computed by the caller.
+struct Geom {
+  int Tx, Ty;   // rows (first operand), columns (second operand)
+  int max_len;  // max(0, Ty-Tx) + R
+  int a;        // min_len + R - 1, min_len = max(0, Tx-Ty): row i starts at max(0, i - a)
+  int H;        // band height of a column: a + max_len
+};
+
+WB_HD Geom make_geom(int Tx, int Ty, int R) {
+  Geom g;
+  g.Tx = Tx; g.Ty = Ty;
+  g.max_len = imax2(0, Ty - Tx) + R;
+  g.a = imax2(0, Tx - Ty) + R - 1;
+  g.H = g.a + g.max_len;
+  return g;
+}
+
+// Per-pair scalars a metric may need (computed by small prologue kernels / the host).
+struct PairCtx {
+  double sx;  // erp: sum |x - g|   edr: std(x)
+  double sy;  // erp: sum |y - g|   edr: std(y)
+};
+
+// ------------------------------------------------------------------------------------------
+// DTW family.  EL:869-940 (dtw / wdtw / ddtw / wddtw), EL:943-1008 (adtw).
+// WEIGHTED: cost is (v*v)*w[widx]; row 0 uses w[max(j-1,0)] (EL:894-903 quirk).
+// AMERCING: min(min(up+p, left+p), diag) + v*v, no penalty on row 0 (EL:966-971).
+// ------------------------------------------------------------------------------------------
+template <bool WEIGHTED, bool AMERCING>
+struct DtwPolicy {
+  static constexpr bool kMsmBand = false;
+  static constexpr bool kNeedPrevX = false;
+  static constexpr bool kColumnMinBound = true;  // column minima lower-bound the result
+  const double* w;  // weights table (WEIGHTED), length >= max(Tx,Ty)
+  double p;         // penalty (AMERCING)
+
+  WB_HD double prev_init() const { return WB_INF; }
+  WB_HD double usent() const { return WB_INF; }
+  WB_HD double lsent() const { return WB_INF; }
+  WB_HD double left0(int) const { return WB_INF; }
+  WB_HD double diag0(int i) const { return i == 0 ? 0.0 : WB_INF; }
+  WB_HD void begin_pair(const PairCtx&) {}
+
+  struct Row { double xi; double p; };
+  struct Col { double yj; };
+  WB_HD Row row(int i, double xi, double) const {
+    Row r; r.xi = xi; r.p = (AMERCING && i > 0) ? p : 0.0; return r;
+  }
+  WB_HD Col col(int, double yj, double) const { Col c; c.yj = yj; return c; }
+
+  WB_HD double cell(double up, double left, double diag, const Row& r, const Col& c, int i, int j) const {
+    double v = r.xi - c.yj;
+    double cost = v * v;
+    if (WEIGHTED) {
+      int k = (i == 0) ? imax2(j - 1, 0) : iabs1(i - j);
+      cost = cost * ldg(w + k);
+    }
+    if (AMERCING) { up = up + r.p; left = left + r.p; }
+    return dmin2(dmin2(up, left), diag) + cost;
+  }
+  WB_HD double finish(double d, const Geom&) const { return sqrt(d); }
+};
+
+// ------------------------------------------------------------------------------------------
+// LCSS / WLCSS.  EL:1118-1183; result 1 - s / min(Tx,Ty).
+// ------------------------------------------------------------------------------------------
+template <bool WEIGHTED>
+struct LcssPolicy {
+  static constexpr bool kMsmBand = false;
+  static constexpr bool kNeedPrevX = false;
+  static constexpr bool kColumnMinBound = false;
+  const double* w;
+  double eps;
+
+  WB_HD double prev_init() const { return 0.0; }
+  WB_HD double usent() const { return 0.0; }
+  WB_HD double lsent() const { return 0.0; }
+  WB_HD double left0(int) const { return 0.0; }
+  WB_HD double diag0(int) const { return 0.0; }
+  WB_HD void begin_pair(const PairCtx&) {}
+
+  struct Row { double xi; };
+  struct Col { double yj; };
+  WB_HD Row row(int, double xi, double) const { Row r; r.xi = xi; return r; }
+  WB_HD Col col(int, double yj, double) const { Col c; c.yj = yj; return c; }
+
+  WB_HD double cell(double up, double left, double diag, const Row& r, const Col& c, int i, int j) const {
+    double v = fabs(r.xi - c.yj);
+    double wv = 1.0;
+    if (WEIGHTED) wv = ldg(w + iabs1(i - j));
+    double hit = wv + diag;
+    double miss = dmax2(left, up);
+    return (v <= eps) ? hit : miss;
+  }
+  WB_HD double finish(double d, const Geom& g) const { return 1 - (d / (double)imin2(g.Tx, g.Ty)); }
+};
+
+// ------------------------------------------------------------------------------------------
+// ERP.  EL:1273-1347.  sx/sy are the whole-series gap sums (sequential order).
+// ------------------------------------------------------------------------------------------
+struct ErpPolicy {
+  static constexpr bool kMsmBand = false;
+  static constexpr bool kNeedPrevX = false;
+  static constexpr bool kColumnMinBound = false;
+  double g;
+  double gx_sum, gy_sum;
+
+  WB_HD double prev_init() const { return gy_sum; }
+  WB_HD double usent() const { return 0.0; }
+  WB_HD double lsent() const { return 0.0; }
+  WB_HD double left0(int) const { return gx_sum; }
+  WB_HD double diag0(int i) const { return i == 0 ? 0.0 : gx_sum; }
+  WB_HD void begin_pair(const PairCtx& pc) { gx_sum = pc.sx; gy_sum = pc.sy; }
+
+  struct Row { double xi, gx; };
+  struct Col { double yj, gy; };
+  WB_HD Row row(int, double xi, double) const { Row r; r.xi = xi; r.gx = fabs(xi - g); return r; }
+  WB_HD Col col(int, double yj, double) const { Col c; c.yj = yj; c.gy = fabs(yj - g); return c; }
+
+  WB_HD double cell(double up, double left, double diag, const Row& r, const Col& c, int, int) const {
+    double v = fabs(r.xi - c.yj);
+    return dmin2(diag + v, dmin2(up + r.gx, left + c.gy));
+  }
+  WB_HD double finish(double d, const Geom&) const { return d; }
+};
+
+// ------------------------------------------------------------------------------------------
+// EDR.  EL:1437-1497; eps < 0 on entry means "default": max(std_x, std_y) / 4 (EL:3762-3766).
+// ------------------------------------------------------------------------------------------
+struct EdrPolicy {
+  static constexpr bool kMsmBand = false;
+  static constexpr bool kNeedPrevX = false;
+  static constexpr bool kColumnMinBound = false;
+  double eps_param;  // NaN => per-pair default
+  double eps;
+
+  WB_HD double prev_init() const { return 0.0; }
+  WB_HD double usent() const { return 0.0; }
+  WB_HD double lsent() const { return 0.0; }
+  WB_HD double left0(int) const { return 0.0; }
+  WB_HD double diag0(int) const { return 0.0; }
+  WB_HD void begin_pair(const PairCtx& pc) {
+    eps = (eps_param != eps_param) ? dmax2(pc.sx, pc.sy) / 4.0 : eps_param;
+  }
+
+  struct Row { double xi; };
+  struct Col { double yj; };
+  WB_HD Row row(int, double xi, double) const { Row r; r.xi = xi; return r; }
+  WB_HD Col col(int, double yj, double) const { Col c; c.yj = yj; return c; }
+
+  WB_HD double cell(double up, double left, double diag, const Row& r, const Col& c, int, int) const {
+    double v = fabs(r.xi - c.yj);
+    double sub = diag + ((v < eps) ? 0.0 : 1.0);
+    return dmin2(dmin2(sub, up + 1.0), left + 1.0);
+  }
+  WB_HD double finish(double d, const Geom& g) const { return d / (double)imax2(g.Tx, g.Ty); }
+};
+
+// ------------------------------------------------------------------------------------------
+// MSM.  EL:1583-1647.  `_msm_cost` takes C floats: operands are rounded to fp32, the two
+// subtractions happen in fp32, fabs/min/+c in double.  min(|(double)a|, |(double)b|) ==
+// (double)min(|a|, |b|) exactly, so one widening conversion per call suffices.
+// Band quirks (column 0 always evaluated, row 0 one cell wider, stale left) live in the engine
+// behind kMsmBand.
+// ------------------------------------------------------------------------------------------
+struct MsmPolicy {
+  static constexpr bool kMsmBand = true;
+  static constexpr bool kNeedPrevX = true;
+  static constexpr bool kColumnMinBound = false;
+  double c;  // (double)(float)c
+  float cf;
+
+  WB_HD double prev_init() const { return WB_INF; }
+  WB_HD double usent() const { return 0.0; }
+  WB_HD double lsent() const { return 0.0; }  // only for bands the stale rule cannot reach
+  WB_HD double left0(int) const { return WB_INF; }
+  WB_HD double diag0(int i) const { return i == 0 ? 0.0 : WB_INF; }
+  WB_HD void begin_pair(const PairCtx&) {}
+
+  struct Row { double xi; float xf, xmf; };
+  struct Col { double yj; float yf, ymf; };
+  WB_HD Row row(int, double xi, double xim) const { Row r; r.xi = xi; r.xf = (float)xi; r.xmf = (float)xim; return r; }
+  WB_HD Col col(int, double yj, double yjm) const { Col c2; c2.yj = yj; c2.yf = (float)yj; c2.ymf = (float)yjm; return c2; }
+
+  WB_HD double cost(float x, float y, float z) const {
+    bool between = (y <= x && x <= z) || (y >= x && x >= z);
+    float d1 = fabsf(x - y), d2 = fabsf(x - z);
+    float m = d1 < d2 ? d1 : d2;
+    return c + (between ? 0.0 : (double)m);
+  }
+  WB_HD double cell(double up, double left, double diag, const Row& r, const Col& cl, int, int) const {
+    double a = diag + fabs(r.xi - cl.yj);
+    double b = up + cost(r.xf, r.xmf, cl.yf);
+    double d = left + cost(cl.yf, r.xf, cl.ymf);
+    return dmin2(dmin2(a, b), d);
+  }
+  WB_HD double finish(double d, const Geom&) const { return d; }
+};
+
+// ------------------------------------------------------------------------------------------
+// TWE.  EL:1733-1829.  Conventions X[-1] = Y[-1] = 0; pen = penalty + stiffness;
+// tw[k] = (stiffness*2)*k is a table so that no int->double conversion sits in the cell.
+// ------------------------------------------------------------------------------------------
+struct TwePolicy {
+  static constexpr bool kMsmBand = false;
+  static constexpr bool kNeedPrevX = true;
+  static constexpr bool kColumnMinBound = false;
+  double pen;        // penalty + stiffness
+  const double* tw;  // tw[k] = (stiffness * 2) * k
+
+  WB_HD double prev_init() const { return WB_INF; }
+  WB_HD double usent() const { return 0.0; }
+  WB_HD double lsent() const { return 0.0; }
+  WB_HD double left0(int) const { return WB_INF; }
+  WB_HD double diag0(int i) const { return i == 0 ? 0.0 : WB_INF; }
+  WB_HD void begin_pair(const PairCtx&) {}
+
+  struct Row { double xi, xim, dx; };
+  struct Col { double yj, yjm, dy; };
+  WB_HD Row row(int, double xi, double xim) const { Row r; r.xi = xi; r.xim = xim; r.dx = fabs(xim - xi); return r; }
+  WB_HD Col col(int, double yj, double yjm) const { Col c; c.yj = yj; c.yjm = yjm; c.dy = fabs(yjm - yj); return c; }
+
+  WB_HD double cell(double up, double left, double diag, const Row& r, const Col& c, int i, int j) const {
+    double del_x = (up + r.dx) + pen;
+    double del_y = (left + c.dy) + pen;
+    double match = ((diag + fabs(r.xi - c.yj)) + fabs(r.xim - c.yjm)) + ldg(tw + iabs1(i - j));
+    return dmin2(dmin2(del_x, del_y), match);
+  }
+  WB_HD double finish(double d, const Geom&) const { return d; }
+};
+
+}  // namespace wb
