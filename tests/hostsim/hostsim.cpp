@@ -18,7 +18,8 @@ struct StripRunner {
     if (!strip_supported<M>(g, W)) { *ok = 0; return 0; }
     *ok = 1;
     std::vector<double> bnd((size_t)NS * bs + 8, -12345.0);
-    return strip_pair<M, W>(g, m, x, y, bnd.data(), bs, NS, abandon);
+    return abandon < INFINITY ? strip_pair<M, W, true>(g, m, x, y, bnd.data(), bs, NS, abandon)
+                              : strip_pair<M, W, false>(g, m, x, y, bnd.data(), bs, NS, abandon);
   }
 };
 

@@ -1,0 +1,79 @@
+"""CPU: host logic of the product package -- validation, shapes of errors, C-ABI exports."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_library_exports_every_declared_symbol(wb):
+    hdr = open(os.path.join(ROOT, "include", "wb_cuda.h")).read()
+    names = set(re.findall(r"\b(wb_cuda_[a-z0-9_]+)\s*\(", hdr))
+    assert {"wb_cuda_pairwise", "wb_cuda_pairwise_self", "wb_cuda_paired", "wb_cuda_argmin",
+            "wb_cuda_pairwise_dev", "wb_cuda_last_error", "wb_cuda_device_count", "wb_cuda_fp64_peak"} <= names
+    L = ctypes.CDLL(wb.library_path())
+    for n in names:
+        assert hasattr(L, n), n
+
+
+def test_no_gpu_means_error_not_fallback(wb):
+    if wb.device_count() > 0:
+        pytest.skip("a GPU is present")
+    x = np.zeros((2, 8))
+    with pytest.raises(RuntimeError, match="no CUDA device|no CPU fallback"):
+        wb.pairwise_distance(x, x.copy(), metric="dtw")
+
+
+def test_product_never_imports_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "wildboar_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp")):
+                src = open(os.path.join(root, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+@pytest.mark.parametrize("metric,params,exc", [
+    ("dtw", {"r": -0.1}, ValueError), ("dtw", {"r": 1.5}, ValueError), ("dtw", {"r": "a"}, TypeError),
+    ("dtw", {"bogus": 1}, TypeError), ("wdtw", {"g": -1.0}, ValueError), ("lcss", {"epsilon": 0.0}, ValueError),
+    ("edr", {"epsilon": -1.0}, ValueError), ("erp", {"g": -0.5}, ValueError), ("msm", {"c": -1.0}, ValueError),
+    ("twe", {"penalty": -1.0}, ValueError), ("twe", {"stiffness": 0.0}, ValueError), ("twe", {"edit_penalty": 1.0}, TypeError),
+])
+def test_metric_param_validation(wb, metric, params, exc):
+    # reference: tests/wildboar/distance/test_distance.py:809-848
+    x = np.zeros((2, 8))
+    with pytest.raises(exc):
+        wb.pairwise_distance(x, x.copy(), metric=metric, metric_params=params)
+
+
+def test_input_validation(wb):
+    x = np.zeros((3, 8))
+    with pytest.raises(ValueError, match="unsupported metric"):
+        wb.pairwise_distance(x, x.copy(), metric="nope")
+    bad = x.copy(); bad[1, 2] = np.nan
+    with pytest.raises(ValueError, match="contains NaN"):
+        wb.pairwise_distance(bad, x, metric="dtw")
+    bad[1, 2] = np.inf
+    with pytest.raises(ValueError, match="contains infinity"):
+        wb.pairwise_distance(bad, x, metric="dtw")
+    with pytest.raises(ValueError, match="same number of samples|broadcast"):
+        wb.paired_distance(np.zeros((3, 8)), np.zeros((4, 8)), metric="dtw")
+    with pytest.raises(ValueError, match="lower bound must be of shape"):
+        wb.argmin_distance(x, x.copy(), metric="dtw", lower_bound=np.zeros((2, 2)))
+    with pytest.raises(ValueError):
+        wb.argmin_distance(x, x.copy(), k=0, metric="dtw")
+    with pytest.raises(ValueError, match="dim must be"):
+        wb.pairwise_distance(np.zeros((3, 2, 8)), np.zeros((3, 2, 8)), dim=5, metric="dtw")
+    assert wb.pairwise_distance(np.zeros(8), metric="dtw") == 0.0  # 1-D self distance (DI:1238-1239)
+    with pytest.warns(FutureWarning):
+        wb.check_metric("lcss")(threshold=0.5)
+
+
+def test_metric_objects_pickle(wb):
+    import pickle
+    for name, cls in wb._METRICS.items():
+        m = cls()
+        m2 = pickle.loads(pickle.dumps(m))
+        assert type(m2) is cls and m2.__reduce__()[1] == m.__reduce__()[1] or name == "edr"

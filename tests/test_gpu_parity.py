@@ -1,0 +1,208 @@
+"""GPU (-m gpu): the CUDA path, called through the public API -> ctypes shim -> C ABI, against
+the oracle on identical seeded inputs.  Bar: bit-exact (np.array_equal) in fp64, which implies
+the north-star's 1e-12 relative tolerance; argmin indices exact."""
+import os
+
+import numpy as np
+import pytest
+
+from util import METRICS, NINE, golden_cases, random_walks
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def W(wb):
+    assert wb.device_count() >= 1, "no CUDA device: the product has no CPU fallback"
+    wb.set_devices([0])
+    return wb
+
+
+def _eq(a, b, what):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    if not np.array_equal(a, b):
+        bad = np.argwhere(a != b)
+        raise AssertionError(f"{what}: {len(bad)} mismatches, first {bad[0]}: got {a[tuple(bad[0])]!r} want {b[tuple(bad[0])]!r}")
+
+
+def test_golden_vectors(W, golden):
+    """Every committed golden vector of the reference (tests/golden/make_golden.py)."""
+    n = 0
+    for case, metric, extra, r, pre in golden_cases(golden):
+        x, y = golden[f"x{case}"], golden[f"y{case}"]
+        mp = dict(extra, r=r)
+        _eq(W.pairwise_distance(x, y, metric=metric, metric_params=mp), golden[pre + "|pairwise"], pre + " pairwise")
+        if pre + "|self" in golden:
+            _eq(W.pairwise_distance(x, metric=metric, metric_params=mp), golden[pre + "|self"], pre + " self")
+            m = min(len(x), len(y))
+            _eq(W.paired_distance(x[:m], y[:m], metric=metric, metric_params=mp), golden[pre + "|paired"], pre + " paired")
+        for k in (1, 2):
+            if pre + f"|argmin{k}|idx" in golden:
+                idx, dist = W.argmin_distance(x, y, k=k, metric=metric, metric_params=mp, return_distance=True)
+                _eq(idx, golden[pre + f"|argmin{k}|idx"], pre + f" argmin{k} idx")
+                _eq(dist, golden[pre + f"|argmin{k}|dist"], pre + f" argmin{k} dist")
+        n += 1
+    assert n > 500
+
+
+def test_cfg1_gunpoint_shape_dtw(W, oracle):
+    """BASELINE configs[0]: 200x150 vs 200x150, dtw r=0.1, full size."""
+    x, y = random_walks(200, 150, 1), random_walks(200, 150, 2)
+    _eq(W.pairwise_distance(x, y, metric="dtw", metric_params={"r": 0.1}), oracle.pairwise("dtw", x, y, r=0.1, n_jobs=0), "cfg1")
+
+
+@pytest.mark.parametrize("metric", NINE + ["wddtw", "wlcss"])
+def test_cfg2_ecg5000_shape_all_metrics(W, oracle, metric):
+    """BASELINE configs[1] (5000x140, default params) on a 160-row slice: two-array and singleton forms."""
+    X = random_walks(5000, 140, 1)[:160]
+    Y = X[40:].copy()
+    _eq(W.pairwise_distance(X[:96], Y, metric=metric), oracle.pairwise(metric, X[:96], Y, n_jobs=0), metric + " two-array")
+    _eq(W.pairwise_distance(X, metric=metric), oracle.pairwise(metric, X, None, n_jobs=0), metric + " singleton")
+    _eq(W.paired_distance(X[:100], X[60:160], metric=metric), oracle.paired(metric, X[:100], X[60:160], n_jobs=0), metric + " paired")
+
+
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("r", [0.0, 0.05, 0.3])
+def test_windows_and_unequal_lengths(W, oracle, metric, r):
+    for (nx, ny, Tx, Ty) in [(33, 70, 64, 64), (20, 45, 50, 77), (45, 20, 77, 50), (5, 40, 9, 120)]:
+        if metric == "wddtw" and Tx > Ty:
+            continue
+        x, y = random_walks(nx, Tx, 5), random_walks(ny, Ty, 6)
+        _eq(W.pairwise_distance(x, y, metric=metric, metric_params={"r": r}), oracle.pairwise(metric, x, y, r=r, n_jobs=0),
+            f"{metric} r={r} {Tx}x{Ty}")
+
+
+def test_cfg3_row_subset(W, oracle):
+    """BASELINE configs[2] shape (T=512, r=0.1): 48 x rows against 300 y rows."""
+    x, y = random_walks(10000, 512, 1)[:48], random_walks(10000, 512, 2)[:300]
+    _eq(W.pairwise_distance(x, y, metric="dtw", metric_params={"r": 0.1}), oracle.pairwise("dtw", x, y, r=0.1, n_jobs=0), "cfg3")
+
+
+@pytest.mark.parametrize("metric", ["msm", "twe"])
+def test_cfg5_long_series_subset(W, oracle, metric):
+    """BASELINE configs[4] shape (T=4096, r=0.05): 6 x 40 pairs."""
+    x, y = random_walks(2000, 4096, 1)[:6], random_walks(2000, 4096, 2)[:40]
+    _eq(W.pairwise_distance(x, y, metric=metric, metric_params={"r": 0.05}), oracle.pairwise(metric, x, y, r=0.05, n_jobs=0), metric)
+
+
+@pytest.mark.parametrize("metric", ["dtw", "adtw", "msm", "erp", "twe", "lcss"])
+def test_engines_agree_on_device(W, oracle, metric, monkeypatch):
+    """Strip engine and row-scan engine are independent formulations: both must equal the oracle."""
+    x, y = random_walks(40, 90, 7), random_walks(70, 90, 8)
+    want = oracle.pairwise(metric, x, y, r=0.15, n_jobs=0)
+    for eng in ("rowscan", "strip"):
+        monkeypatch.setenv("WILDBOAR_CUDA_ENGINE", eng)
+        _eq(W.pairwise_distance(x, y, metric=metric, metric_params={"r": 0.15}), want, f"{metric} {eng}")
+        from wildboar_b200 import last_stats
+        assert last_stats()["engine"] == {"rowscan": 1, "strip": 2}[eng]
+
+
+def test_edge_shapes(W, oracle):
+    for metric in ("dtw", "msm", "edr", "lcss", "twe", "erp"):
+        for (nx, ny, Tx, Ty) in [(1, 1, 1, 1), (3, 2, 1, 5), (2, 3, 5, 1), (1, 65, 2, 2), (31, 1, 3, 3), (2, 33, 17, 17)]:
+            x, y = random_walks(nx, Tx, 11), random_walks(ny, Ty, 12)
+            _eq(W.pairwise_distance(x, y, metric=metric, metric_params={"r": 0.2}), oracle.pairwise(metric, x, y, r=0.2),
+                f"{metric} {nx}x{ny} T={Tx},{Ty}")
+    x = random_walks(4, 20, 13)
+    # 1-D operands and return shapes (DI:514-540)
+    d = W.pairwise_distance(x[0], x[1], metric="dtw")
+    assert isinstance(d, float) and d == oracle.pairwise("dtw", x[:1], x[1:2])[0, 0]
+    assert W.pairwise_distance(x[0], x, metric="dtw").shape == (4,)
+    assert W.pairwise_distance(x, x[0], metric="dtw").shape == (4,)
+    # 3-D input: dim = "mean" / "full" / int (DI:1289-1302)
+    x3, y3 = np.random.default_rng(1).standard_normal((5, 3, 30)), np.random.default_rng(2).standard_normal((6, 3, 30))
+    per_dim = [oracle.pairwise("dtw", x3[:, d], y3[:, d], r=0.5) for d in range(3)]
+    _eq(W.pairwise_distance(x3, y3, dim="full", metric="dtw", metric_params={"r": 0.5}), np.stack(per_dim), "full")
+    _eq(W.pairwise_distance(x3, y3, dim="mean", metric="dtw", metric_params={"r": 0.5}), np.mean(per_dim, axis=0), "mean")
+    _eq(W.pairwise_distance(x3, y3, dim=2, metric="dtw", metric_params={"r": 0.5}), per_dim[2], "dim=2")
+    # non-contiguous rows (strided samples)
+    big = random_walks(20, 40, 14)
+    _eq(W.pairwise_distance(big[::2], big[1::2], metric="dtw"), oracle.pairwise("dtw", big[::2].copy(), big[1::2].copy()), "strided")
+    # identical series -> exact zeros
+    assert W.pairwise_distance(x, x.copy(), metric="dtw").diagonal().max() == 0.0
+
+
+def test_paired_is_swapped_like_the_reference(W, oracle):
+    x, y = random_walks(50, 60, 15), random_walks(50, 60, 16)
+    for metric in ("wdtw", "adtw", "msm"):
+        got = W.paired_distance(x, y, metric=metric, metric_params={"r": 0.3})
+        _eq(got, oracle.paired(metric, x, y, r=0.3), metric)
+        _eq(got, np.diag(oracle.pairwise(metric, y, x, r=0.3)), metric + " == diag(pairwise(y, x))")
+
+
+@pytest.mark.parametrize("metric", METRICS)
+@pytest.mark.parametrize("k", [1, 3, 7])
+def test_argmin_matches_sequential_scan(W, oracle, metric, k):
+    """Indices, distances AND heap order of the reference's scan (CD:1302-1345)."""
+    x, y = random_walks(37, 48, 21), random_walks(150, 48, 22)
+    y[60] = y[10]; y[61] = y[10]; x[5] = y[10]  # exact ties / zero distances
+    for r in (0.1, 1.0):
+        idx, dist = W.argmin_distance(x, y, k=k, metric=metric, metric_params={"r": r}, return_distance=True)
+        oi, od = oracle.argmin(metric, x, y, k=k, r=r, n_jobs=0)
+        _eq(idx, oi, f"{metric} k={k} r={r} idx")
+        _eq(dist, od, f"{metric} k={k} r={r} dist")
+    si, sd = W.argmin_distance(x, y, k=k, metric=metric, sorted=True, return_distance=True)
+    assert np.all(np.diff(sd, axis=1) >= 0)
+
+
+def test_argmin_self_join_and_lower_bound(W, oracle):
+    x = random_walks(64, 40, 23)
+    idx = W.argmin_distance(x, metric="dtw", metric_params={"r": 0.1})
+    _eq(idx[:, 0], np.arange(64), "self join returns the self match")
+    # user lower bound (LB_Keogh, reference lb.py:314-432) skips exactly like CD:1331
+    q, refs = random_walks(20, 40, 24), random_walks(90, 40, 25)
+    R = oracle.compute_r(40, 0.1)
+    lb = np.zeros((20, 90))
+    for j in range(90):
+        lo, hi = oracle.envelope(refs[j], R)
+        for i in range(20):
+            lb[i, j] = oracle.lb_keogh_one(q[i], lo, hi)
+    for k in (1, 4):
+        idx, dist = W.argmin_distance(q, refs, k=k, metric="dtw", metric_params={"r": 0.1}, lower_bound=lb, return_distance=True)
+        oi, od = oracle.argmin("dtw", q, refs, k=k, lower_bound=lb, r=0.1)
+        _eq(idx, oi, "lb idx"); _eq(dist, od, "lb dist")
+
+
+def test_argmin_cfg4_shape_subset(W, oracle):
+    """BASELINE configs[3] shape: T=256, r=0.05, k=1 -- 48 queries x 3000 references."""
+    q, refs = random_walks(20000, 256, 3)[:48], random_walks(200000, 256, 4)[:3000]
+    idx, dist = W.argmin_distance(q, refs, k=1, metric="dtw", metric_params={"r": 0.05}, return_distance=True)
+    oi, od = oracle.argmin("dtw", q, refs, k=1, r=0.05, n_jobs=0)
+    _eq(idx, oi, "cfg4 idx"); _eq(dist, od, "cfg4 dist")
+    # size-independent property: argmin == argmin of the pairwise row
+    full = W.pairwise_distance(q, refs, metric="dtw", metric_params={"r": 0.05})
+    _eq(idx[:, 0], full.argmin(axis=1), "argmin == argmin(pairwise)")
+    _eq(dist[:, 0], full.min(axis=1), "min == min(pairwise)")
+
+
+def test_full_size_properties_cfg3(W, oracle):
+    """Full BASELINE configs[2] rows are too slow for the oracle; check properties instead:
+    a 1536 x 10000 slab, symmetry of equal-length DTW, and a random sample against the oracle."""
+    x, y = random_walks(10000, 512, 1), random_walks(10000, 512, 2)
+    xs = x[:1536]
+    d = W.pairwise_distance(xs, y, metric="dtw", metric_params={"r": 0.1})
+    assert d.shape == (1536, 10000) and np.isfinite(d).all() and (d >= 0).all()
+    dt = W.pairwise_distance(y[:512], xs[:256], metric="dtw", metric_params={"r": 0.1})
+    _eq(dt.T, d[:256, :512], "DTW(x,y) == DTW(y,x) for equal lengths")
+    rng = np.random.default_rng(0)
+    ii, jj = rng.integers(0, 1536, 300), rng.integers(0, 10000, 300)
+    want = oracle.paired("dtw", y[jj], xs[ii], r=0.1, n_jobs=0)  # paired evaluates metric(second, first)
+    _eq(d[ii, jj], want, "random sample vs oracle")
+
+
+def test_multi_gpu_row_sharding_is_transparent(W, oracle):
+    n = W.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    x, y = random_walks(203, 64, 31), random_walks(101, 64, 32)
+    try:
+        W.set_devices(list(range(n)))
+        for metric in ("dtw", "msm"):
+            _eq(W.pairwise_distance(x, y, metric=metric, metric_params={"r": 0.2}), oracle.pairwise(metric, x, y, r=0.2, n_jobs=0), metric)
+            _eq(W.pairwise_distance(x, metric=metric, metric_params={"r": 0.2}), oracle.pairwise(metric, x, None, r=0.2, n_jobs=0), metric + " self")
+            i, d = W.argmin_distance(x, y, k=3, metric=metric, metric_params={"r": 0.2}, return_distance=True)
+            oi, od = oracle.argmin(metric, x, y, k=3, r=0.2, n_jobs=0)
+            _eq(i, oi, metric + " argmin idx"); _eq(d, od, metric + " argmin dist")
+    finally:
+        W.set_devices([0])

@@ -1,0 +1,22 @@
+"""wildboar_b200: B200-native (sm_100a) elastic distances behind wildboar's distance API.
+
+Public surface (mirrors ``wildboar.distance``; reference: src/wildboar/distance/_distance.py):
+
+    pairwise_distance, paired_distance, argmin_distance, check_metric
+
+The compute path is ``libwbcuda.so`` (hand-written CUDA, include/wb_cuda.h).  There is no CPU
+fallback: without the library or without a B200 the calls raise.
+"""
+from .distance import (  # noqa: F401
+    _METRICS,
+    argmin_distance,
+    check_metric,
+    paired_distance,
+    pairwise_distance,
+)
+from ._shim import device_count, last_stats, library_path, set_devices  # noqa: F401
+
+__all__ = [
+    "pairwise_distance", "paired_distance", "argmin_distance", "check_metric",
+    "device_count", "set_devices", "last_stats", "library_path",
+]

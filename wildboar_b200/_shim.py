@@ -1,0 +1,202 @@
+"""ctypes shim over the C ABI of libwbcuda.so (include/wb_cuda.h).
+
+float64 numpy buffers go in and out as plain pointers + sizes; nothing here computes.  The
+library is loaded lazily and loading FAILS LOUDLY if the shared object is missing -- there is
+no CPU fallback (the oracle under oracle/ is test infrastructure and is never imported here).
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libwbcuda.so")
+
+METRIC_IDS = {
+    "dtw": 0, "wdtw": 1, "ddtw": 2, "adtw": 3, "lcss": 4, "erp": 5,
+    "edr": 6, "msm": 7, "twe": 8, "wddtw": 9, "wlcss": 10,
+}
+
+
+class WbParams(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("r", "g", "p", "c", "epsilon", "penalty", "stiffness")] + [
+        ("engine", C.c_int32), ("reserved", C.c_int32)]
+
+
+class WbStats(C.Structure):
+    _fields_ = [("kernel_ms", C.c_double), ("total_ms", C.c_double), ("cells", C.c_int64), ("pairs", C.c_int64),
+                ("launches", C.c_int32), ("engine", C.c_int32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_lib = None
+_lock = threading.Lock()
+_devices = None
+_tls = threading.local()
+
+_DP = C.POINTER(C.c_double)
+_IP = C.POINTER(C.c_int64)
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def lib():
+    """Load libwbcuda.so (raises if it has not been built: no fallback)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(_LIB_PATH):
+                    raise RuntimeError(
+                        f"{_LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(nvcc, sm_100a).  wildboar_b200 has no CPU fallback."
+                    )
+                L = C.CDLL(_LIB_PATH)
+                i64, ci = C.c_int64, C.c_int
+                PP, SP, DV = C.POINTER(WbParams), C.POINTER(WbStats), C.POINTER(C.c_int)
+                L.wb_cuda_device_count.restype = ci
+                L.wb_cuda_last_error.restype = C.c_char_p
+                L.wb_cuda_pairwise.argtypes = [ci, PP, _DP, i64, i64, i64, _DP, i64, i64, i64, _DP, DV, ci, SP]
+                L.wb_cuda_pairwise_self.argtypes = [ci, PP, _DP, i64, i64, i64, _DP, DV, ci, SP]
+                L.wb_cuda_paired.argtypes = [ci, PP, _DP, i64, i64, i64, _DP, i64, i64, _DP, DV, ci, SP]
+                L.wb_cuda_argmin.argtypes = [ci, PP, _DP, i64, i64, i64, _DP, i64, i64, i64, i64, _DP, ci, _IP, _DP,
+                                             DV, ci, SP]
+                L.wb_cuda_pairwise_dev.argtypes = [ci, PP, C.c_void_p, i64, i64, C.c_void_p, i64, i64, C.c_void_p,
+                                                   C.c_void_p, SP]
+                L.wb_cuda_fp64_peak.argtypes = [ci, _DP, _DP]
+                _lib = L
+    return _lib
+
+
+def device_count():
+    return int(lib().wb_cuda_device_count())
+
+
+def set_devices(devices):
+    """Select the CUDA devices the host entry points shard rows over (None = default policy)."""
+    global _devices
+    _devices = None if devices is None else [int(d) for d in devices]
+
+
+def _resolve_devices(work_cells):
+    if _devices is not None:
+        return _devices
+    env = os.environ.get("WILDBOAR_CUDA_DEVICES")
+    if env:
+        if env.strip().lower() == "all":
+            return list(range(max(device_count(), 1)))
+        return [int(t) for t in env.split(",") if t.strip() != ""]
+    # default policy: one device for small jobs, every visible device for big ones
+    if work_cells >= 5e10:
+        n = device_count()
+        if n > 1:
+            return list(range(n))
+    return [0]
+
+
+def last_stats():
+    """wb_stats of the last call on this thread (dict) or None."""
+    return getattr(_tls, "stats", None)
+
+
+def apply_engine_override(params):
+    """WILDBOAR_CUDA_ENGINE=rowscan|strip forces one DP engine (testing / cross-checks)."""
+    e = os.environ.get("WILDBOAR_CUDA_ENGINE", "").strip().lower()
+    params.engine = {"rowscan": 1, "strip": 2}.get(e, 0)
+    return params
+
+
+def _check(rc):
+    if rc != 0:
+        msg = lib().wb_cuda_last_error()
+        raise RuntimeError("wildboar_b200 CUDA call failed: " + (msg.decode() if msg else "unknown error"))
+
+
+def _rows(a):
+    """(pointer, n, T, stride-in-elements) of a 2-D float64 array whose last axis is contiguous."""
+    assert a.dtype == np.float64 and a.ndim == 2 and (a.shape[1] <= 1 or a.strides[1] == 8)
+    stride = a.strides[0] // 8 if a.shape[0] > 1 else a.shape[1]
+    if a.strides[0] % 8 != 0 or stride < a.shape[1]:
+        a = np.ascontiguousarray(a)
+        stride = a.shape[1]
+    return a, a.ctypes.data_as(_DP), a.shape[0], a.shape[1], stride
+
+
+def _dev_array(devs):
+    return (C.c_int * len(devs))(*devs), len(devs)
+
+
+def _est_cells(n_pairs, Tx, Ty, r):
+    R = max(int(min(Tx, Ty) * r), 1)
+    return float(n_pairs) * min(Tx, Ty) * min(2 * R + abs(Tx - Ty), max(Tx, Ty))
+
+
+def pairwise(metric_id, params, x, y):
+    apply_engine_override(params)
+    x, xp, nx, Tx, xs = _rows(x)
+    st = WbStats()
+    if y is None:
+        out = np.empty((nx, nx), dtype=np.float64)
+        dv, nd = _dev_array(_resolve_devices(_est_cells(nx * nx / 2, Tx, Tx, params.r)))
+        _check(lib().wb_cuda_pairwise_self(metric_id, C.byref(params), xp, nx, Tx, xs, out.ctypes.data_as(_DP), dv, nd,
+                                           C.byref(st)))
+    else:
+        y, yp, ny, Ty, ys = _rows(y)
+        out = np.empty((nx, ny), dtype=np.float64)
+        dv, nd = _dev_array(_resolve_devices(_est_cells(nx * ny, Tx, Ty, params.r)))
+        _check(lib().wb_cuda_pairwise(metric_id, C.byref(params), xp, nx, Tx, xs, yp, ny, Ty, ys,
+                                      out.ctypes.data_as(_DP), dv, nd, C.byref(st)))
+    _tls.stats = st.as_dict()
+    return out
+
+
+def paired(metric_id, params, x, y):
+    apply_engine_override(params)
+    x, xp, n, Tx, xs = _rows(x)
+    y, yp, ny, Ty, ys = _rows(y)
+    assert n == ny
+    out = np.empty(n, dtype=np.float64)
+    st = WbStats()
+    dv, nd = _dev_array(_resolve_devices(_est_cells(n, Tx, Ty, params.r)))
+    _check(lib().wb_cuda_paired(metric_id, C.byref(params), xp, n, Tx, xs, yp, Ty, ys, out.ctypes.data_as(_DP), dv, nd,
+                                C.byref(st)))
+    _tls.stats = st.as_dict()
+    return out
+
+
+def argmin(metric_id, params, x, y, k, lower_bound=None, use_device_lb=False):
+    apply_engine_override(params)
+    x, xp, nx, Tx, xs = _rows(x)
+    y, yp, ny, Ty, ys = _rows(y)
+    idx = np.zeros((nx, k), dtype=np.int64)
+    dist = np.zeros((nx, k), dtype=np.float64)
+    lbp = None
+    if lower_bound is not None:
+        lower_bound = np.ascontiguousarray(lower_bound, dtype=np.float64)
+        lbp = lower_bound.ctypes.data_as(_DP)
+    st = WbStats()
+    dv, nd = _dev_array(_resolve_devices(_est_cells(nx * ny, Tx, Ty, params.r)))
+    _check(lib().wb_cuda_argmin(metric_id, C.byref(params), xp, nx, Tx, xs, yp, ny, Ty, ys, k, lbp,
+                                1 if use_device_lb else 0, idx.ctypes.data_as(_IP), dist.ctypes.data_as(_DP), dv, nd,
+                                C.byref(st)))
+    _tls.stats = st.as_dict()
+    return idx.astype(np.intp, copy=False), dist
+
+
+def pairwise_dev(metric_id, params, x_ptr, nx, Tx, y_ptr, ny, Ty, out_ptr, stream=0, want_stats=True):
+    """Device-resident pairwise (raw device pointers, e.g. torch.Tensor.data_ptr())."""
+    st = WbStats()
+    _check(lib().wb_cuda_pairwise_dev(metric_id, C.byref(params), x_ptr, nx, Tx, y_ptr, ny, Ty, out_ptr, stream,
+                                      C.byref(st) if want_stats else None))
+    return st.as_dict() if want_stats else None
+
+
+def fp64_peak(mix=0):
+    a, b = C.c_double(0), C.c_double(0)
+    _check(lib().wb_cuda_fp64_peak(mix, C.byref(a), C.byref(b)))
+    return a.value, b.value

@@ -44,22 +44,42 @@ inline bool strip_supported(const Geom& g, int W) {
 }
 
 // Ring slots needed per pair: every in-band cell of a boundary column (H of them), plus the
-// left-sentinel slot that the producer strip appends below it.
-WB_HD int strip_ring_slots(const Geom& g) { return g.H + 1; }
+// left-sentinel slot that the producer strip appends below it; never more than the Tx rows.
+WB_HD int strip_ring_slots(const Geom& g) { return imax2(2, imin2(g.H + 1, g.Tx)); }
+
+// Opaque select: keeps the compiler from turning a chain of register selects into a
+// dynamically indexed (local-memory) array access.
+WB_HD double sel_f64(bool p, double a, double b) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("{ .reg .pred q; setp.ne.s32 q, %3, 0; selp.f64 %0, %1, %2, q; }" : "=d"(r) : "d"(a), "d"(b), "r"((int)p));
+  return r;
+#else
+  return p ? a : b;
+#endif
+}
 
 // bnd: ring base for this pair; slot s lives at bnd[s * bs].
 // abandon: early-abandon threshold on the RAW dp value (pre-finish); only honoured for
 //          policies whose column minima lower-bound the result (DTW family).  Returns +INF
 //          when abandoned.
-template <class M, int W>
+//
+// Rows of a strip fall in three phases: a top triangle (the band's upper edge crosses the
+// strip), FULL rows (all W cells in band) and a bottom triangle.  Triangle rows go through
+// `generic_row` (per-cell, warp-uniform predicates).  Full rows -- (2R-1-W+1)/(2R-1+W-1) of
+// all rows, 87 % for the headline shape -- take the predicate-free `fast path`, two rows per
+// iteration so that two independent left->right dependency chains are in flight per thread.
+template <class M, int W, bool EA>
 WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
                         const double* __restrict__ y, double* bnd, int bs, int NS, double abandon) {
   const int Tx = g.Tx, Ty = g.Ty;
   double result = 0.0;
+  const double left0c = m.left0(1);
 
   for (int j0 = 0; j0 < Ty; j0 += W) {
     const int wv = imin2(W, Ty - j0);
     const bool last_strip = (j0 + W >= Ty);
+    const bool first_strip = (j0 == 0);
     const int jl = j0 + wv - 1;
     int i_lo = imax2(0, j0 - g.max_len + 1);
     if (M::kMsmBand && j0 == g.max_len) i_lo = 0;
@@ -78,23 +98,28 @@ WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
     for (int c = 0; c < W; ++c) prev[c] = m.usent();
 
     int sl = i_lo % NS;
-    double Dg = 0.0;
-    if (j0 > 0) {
-      if (i_lo == 0) Dg = m.prev_init();
-      else { int sp = (sl == 0) ? NS - 1 : sl - 1; Dg = bnd[sp * bs]; }
-    }
+    double Dg;
+    if (first_strip) {
+      // virtual column -1: left0 is the same constant for every row and diag0(i) == left0(i-1)
+      // for i >= 1, so the first strip simply finds left0 in every ring slot it will read.
+      const int nfill = imin2(NS, i_hi + 2);
+      for (int s = 0; s < nfill; ++s) bnd[s * bs] = left0c;
+      Dg = m.diag0(0);
+    } else if (i_lo == 0) Dg = m.prev_init();
+    else { int sp = (sl == 0) ? NS - 1 : sl - 1; Dg = bnd[sp * bs]; }
     double xi = x[i_lo];
     double xim = (M::kNeedPrevX && i_lo > 0) ? x[i_lo - 1] : 0.0;
     double stale = m.lsent();
     double colmin = WB_INF;
+    int i = i_lo;
 
-    for (int i = i_lo; i <= i_hi; ++i) {
+    auto generic_row = [&]() {
       const double xnext = x[imin2(i + 1, Tx - 1)];  // prefetch next row's sample
       const int js = row_js<M>(g, i), je = row_je<M>(g, i);
       const int clo = imax2(js - j0, 0), chi = imin2(je - j0, wv);
-      double left, diag;
-      if (j0 == 0) { left = m.left0(i); diag = m.diag0(i); }
-      else { left = bnd[sl * bs]; diag = Dg; Dg = left; }
+      double left = bnd[sl * bs];
+      double diag = Dg;
+      Dg = left;
       if (i == 0) {
 #pragma unroll
         for (int c = 0; c < W; ++c) if (c < chi) prev[c] = m.prev_init();
@@ -115,21 +140,68 @@ WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
         diag = up;
       }
       stale = stale_next;
-      if (!last_strip && chi == W) {
+      if (chi == W) {
         const double b = prev[W - 1];
         bnd[sl * bs] = b;
-        if (M::kColumnMinBound) colmin = dmin2(colmin, b);
+        if (EA && M::kColumnMinBound) colmin = dmin2(colmin, b);
       }
       sl = (sl + 1 == NS) ? 0 : sl + 1;
       xim = xi;
       xi = xnext;
+      ++i;
+    };
+
+    // full rows: js(i) <= j0 and je(i) >= jl + 1, i >= 1 (row 0 has its own init rules)
+    const int fa = imax2(imax2(i_lo, 1), jl + 1 - g.max_len);
+    int fb = imin2(i_hi, j0 + g.a);
+    if (M::kMsmBand) fb -= 1;  // the generic row captures the stale-left value for the bottom triangle
+
+    while (i < fa && i <= i_hi) generic_row();
+
+    while (i + 1 <= fb) {
+      // ---- fast path: rows i and i+1, all W cells in band, no predicates ----
+      const double xa = xi;
+      const double xb = x[i + 1];
+      const double xnext = x[imin2(i + 2, Tx - 1)];
+      const int sl1 = (sl + 1 == NS) ? 0 : sl + 1;
+      const double la = bnd[sl * bs];
+      const double lb = bnd[sl1 * bs];
+      const typename M::Row ra = m.row(i, xa, xim);
+      const typename M::Row rb = m.row(i + 1, xb, xa);
+      double diag_a = Dg;
+      double diag_b = la;
+      double left_a = la, left_b = lb;
+#pragma unroll
+      for (int c = 0; c < W; ++c) {
+        const double up = prev[c];
+        const double da = m.cell(up, left_a, diag_a, ra, cols[c], i, j0 + c);
+        const double db = m.cell(da, left_b, diag_b, rb, cols[c], i + 1, j0 + c);
+        diag_a = up;
+        diag_b = da;
+        left_a = da;
+        left_b = db;
+        prev[c] = db;
+      }
+      // left_a / left_b now hold column W-1 of rows i / i+1 (the last strip's writes are
+      // never read; they are kept so the hot loop has no strip-dependent branch)
+      bnd[sl * bs] = left_a;
+      bnd[sl1 * bs] = left_b;
+      if (EA && M::kColumnMinBound) colmin = dmin2(colmin, dmin2(left_a, left_b));
+      Dg = lb;
+      sl = (sl1 + 1 == NS) ? 0 : sl1 + 1;
+      xim = xb;
+      xi = xnext;
+      i += 2;
     }
+
+    while (i <= i_hi) generic_row();
+
     if (!last_strip) {
       if (jl + g.a + 1 <= Tx - 1) bnd[sl * bs] = M::kMsmBand ? stale : m.lsent();
-      if (M::kColumnMinBound && colmin > abandon) return WB_INF;
+      if (EA && M::kColumnMinBound && colmin > abandon) return WB_INF;
     } else {
 #pragma unroll
-      for (int c = 0; c < W; ++c) if (c == wv - 1) result = prev[c];
+      for (int c = 0; c < W; ++c) result = sel_f64(c == wv - 1, prev[c], result);
     }
   }
   return m.finish(result, g);

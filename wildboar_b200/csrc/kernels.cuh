@@ -1,0 +1,194 @@
+// __global__ kernels around the DP engines + small prologue kernels.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include "engine_rowscan.cuh"
+#include "engine_strip.cuh"
+
+namespace wb {
+
+enum PairMode : int {
+  PM_PAIRWISE = 0,  // out[i][j] = d(x_i, y_j)                       (CD:1144-1205)
+  PM_SELF = 1,      // j > i only, also written to out[j][i]          (CD:1208-1267)
+  PM_PAIRED = 2,    // out[i] = d(x_i, y_i)  (caller already swapped)  (CD:1597-1652)
+};
+
+struct KArgs {
+  const double* x;  // (nx, Tx) dense, first operand (rows of the DP)
+  const double* y;  // (ny, Ty) dense, second operand (columns of the DP)
+  long long nx, ny;
+  int Tx, Ty;
+  Geom g;
+  int NS;            // strip engine: ring slots per pair
+  const double* sx;  // per-sample scalars of x (erp gap sums / edr std) or nullptr
+  const double* sy;
+  double* out;
+  long long ld;       // out[i * ld + j]
+  double* out_m;      // optional: max over checked rows of the row minimum (row-scan engine)
+  const double* thr;  // optional per-x-row early-abandon threshold, RAW dp domain
+  unsigned long long* counter;  // persistent-grid work counter (zeroed before launch)
+  long long ntasks;   // warp tasks
+  long long nyb;      // ceil(ny / 32)
+  int mode;
+  long long row0;     // PM_SELF: global index of local x row 0 (row-sharded self join)
+  int mirror;         // PM_SELF: also write out[j][i] (single-device full matrix)
+  double* scratch;    // row-scan engine: 2 rows per thread, interleaved
+  long long sstride;  // = total threads
+  int srows;          // elements per scratch row
+};
+
+// One warp task = 32 consecutive pairs.  Returns false when the whole task is empty.
+__device__ __forceinline__ bool decode_task(const KArgs& a, long long t, int lane, long long& i, long long& j,
+                                            bool& valid) {
+  if (a.mode == PM_PAIRED) {
+    i = t * 32 + lane;
+    valid = i < a.nx;
+    if (!valid) i = a.nx - 1;
+    j = i;
+    return true;
+  }
+  i = t / a.nyb;
+  long long jb = t - i * a.nyb;
+  j = jb * 32 + lane;
+  valid = j < a.ny;
+  if (!valid) j = a.ny - 1;
+  if (a.mode == PM_SELF) {
+    const long long ig = i + a.row0;
+    if (jb * 32 + 31 <= ig) return false;
+    if (j <= ig) valid = false;
+  }
+  return true;
+}
+
+__device__ __forceinline__ long long next_task(unsigned long long* counter, int lane) {
+  unsigned long long t = 0;
+  if (lane == 0) t = atomicAdd(counter, 1ULL);
+  return (long long)__shfl_sync(0xffffffffu, t, 0);
+}
+
+// ---- strip engine: thread per pair, boundary ring in shared memory [warp][slot][lane] ----
+template <class M, int W, int NT, int MINB, bool EA>
+__global__ void __launch_bounds__(NT, MINB) k_strip(KArgs a, M m) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  double* bnd = smem + (size_t)warp * a.NS * 32 + lane;
+  for (;;) {
+    const long long t = next_task(a.counter, lane);
+    if (t >= a.ntasks) break;
+    long long i, j;
+    bool valid;
+    if (!decode_task(a, t, lane, i, j, valid)) continue;
+    M mm = m;
+    PairCtx pc;
+    pc.sx = a.sx ? a.sx[i] : 0.0;
+    pc.sy = a.sy ? a.sy[j] : 0.0;
+    mm.begin_pair(pc);
+    const double ab = EA ? a.thr[i] : WB_INF;
+    const double d = strip_pair<M, W, EA>(a.g, mm, a.x + i * a.Tx, a.y + j * a.Ty, bnd, 32, a.NS, ab);
+    if (valid) {
+      if (a.mode == PM_PAIRED) a.out[i] = d;
+      else {
+        a.out[i * a.ld + j] = d;
+        if (a.mode == PM_SELF && a.mirror) a.out[j * a.ld + i] = d;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---- row-scan engine: thread per pair, two scratch rows per thread in global memory ----
+template <class M, int NT>
+__global__ void __launch_bounds__(NT) k_rowscan(KArgs a, M m) {
+  const int lane = threadIdx.x & 31;
+  const long long gtid = (long long)blockIdx.x * NT + threadIdx.x;
+  double* b0 = a.scratch + gtid;
+  double* b1 = a.scratch + (long long)a.srows * a.sstride + gtid;
+  for (;;) {
+    const long long t = next_task(a.counter, lane);
+    if (t >= a.ntasks) break;
+    long long i, j;
+    bool valid;
+    if (!decode_task(a, t, lane, i, j, valid)) continue;
+    M mm = m;
+    PairCtx pc;
+    pc.sx = a.sx ? a.sx[i] : 0.0;
+    pc.sy = a.sy ? a.sy[j] : 0.0;
+    mm.begin_pair(pc);
+    const double md = a.thr ? a.thr[i] : WB_INF;
+    double mmax = 0.0;
+    const double d = rowscan_pair<M>(a.g, mm, a.x + i * a.Tx, a.y + j * a.Ty, b0, b1, a.sstride, md, &mmax);
+    if (valid) {
+      if (a.mode == PM_PAIRED) a.out[i] = d;
+      else {
+        a.out[i * a.ld + j] = d;
+        if (a.out_m) a.out_m[i * a.ld + j] = mmax;
+        if (a.mode == PM_SELF && a.mirror) a.out[j * a.ld + i] = d;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---- prologues ----
+// EL:3220-3225: d[k] = ((q[k+1]-q[k]) + ((q[k+2]-q[k])/2))/2, k = 0..T-3
+__global__ void k_slope(const double* __restrict__ q, long long n, int T, double* __restrict__ d) {
+  const long long total = n * (long long)(T - 2);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long s = e / (T - 2);
+    const int k = (int)(e - s * (T - 2));
+    const double* p = q + s * T + k;
+    d[e] = ((p[1] - p[0]) + ((p[2] - p[0]) / 2)) / 2;
+  }
+}
+
+// kind 0: erp gap sum  sum_t |x[t] - g| (EL:1295-1303, sequential order)
+// kind 1: std of the series (utils/_stats.pyx:22-42: sequential sums, threshold 1e-13)
+__global__ void k_series_stat(const double* __restrict__ x, long long n, int T, int kind, double g,
+                              double* __restrict__ out) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const double* p = x + s * T;
+  if (kind == 0) {
+    double acc = 0;
+    for (int t = 0; t < T; ++t) acc += fabs(p[t] - g);
+    out[s] = acc;
+  } else {
+    double ex = 0, ex2 = 0;
+    for (int t = 0; t < T; ++t) { const double v = p[t]; ex += v; ex2 += v * v; }
+    const double mean = ex / (double)T;
+    ex2 = ex2 / (double)T - mean * mean;
+    out[s] = ex2 > 1e-13 ? sqrt(ex2) : 0.0;
+  }
+}
+
+// ---- FP64 issue-rate microbenchmark (roofline denominator) ----
+// mix 0: 8 independent DADD chains.  mix 1: the DTW cell's instruction mix on 4 independent
+// chains: sub, mul, add + two compare/selects (min) per "cell".
+__global__ void __launch_bounds__(256) k_fp64_peak(int mix, int iters, double seed, double* out,
+                                                    unsigned long long* cyc) {
+  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+  const double inc = seed * 1e-9 + 1e-7;
+  const unsigned long long c0 = clock64();
+  if (mix == 0) {
+#pragma unroll 4
+    for (int it = 0; it < iters; ++it) {
+      a0 += inc; a1 += inc; a2 += inc; a3 += inc; a4 += inc; a5 += inc; a6 += inc; a7 += inc;
+    }
+  } else {
+    double y0 = seed * 0.5, y1 = seed * 0.25, y2 = seed * 0.125, y3 = seed * 0.0625;
+#pragma unroll 4
+    for (int it = 0; it < iters; ++it) {
+      double v, m;
+      v = a0 - y0; m = a4 < a0 ? a4 : a0; m = m < a1 ? m : a1; a0 = m + v * v;
+      v = a1 - y1; m = a5 < a1 ? a5 : a1; m = m < a2 ? m : a2; a1 = m + v * v;
+      v = a2 - y2; m = a6 < a2 ? a6 : a2; m = m < a3 ? m : a3; a2 = m + v * v;
+      v = a3 - y3; m = a7 < a3 ? a7 : a3; m = m < a0 ? m : a0; a3 = m + v * v;
+    }
+  }
+  const unsigned long long c1 = clock64();
+  const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  out[gtid] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (gtid == 0) cyc[0] = c1 - c0;
+}
+
+}  // namespace wb

@@ -1,0 +1,604 @@
+// libwbcuda.so: C ABI (include/wb_cuda.h) + launch logic + multi-GPU row sharding.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false ...
+// -fmad=false is REQUIRED: the reference build contains no FMA, and every DP value is
+// reproduced bit for bit only if a*b+c is two roundings ("No FMA").
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/wb_cuda.h"
+#include "dispatch.cuh"
+#include "kernels.cuh"
+#include "prep.hpp"
+#include "argmin.cuh"
+
+namespace wb {
+
+static thread_local std::string g_err;
+static void set_err(const std::string& s) { g_err = s; }
+
+#define WB_CK(call)                                                                              \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess) {                                                                     \
+      char buf_[512];                                                                            \
+      snprintf(buf_, sizeof buf_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,           \
+               cudaGetErrorString(e_));                                                          \
+      set_err(buf_);                                                                             \
+      return 1;                                                                                  \
+    }                                                                                            \
+  } while (0)
+
+// Device buffers owned by one call on one device; freed (stream-ordered) on destruction.
+struct Workspace {
+  cudaStream_t stream;
+  std::vector<void*> bufs;
+  std::vector<std::vector<double>> host_keep;  // host staging that must outlive async copies
+  explicit Workspace(cudaStream_t s) : stream(s) {}
+  ~Workspace() { for (void* p : bufs) cudaFreeAsync(p, stream); }
+  template <class T> int alloc(T** p, size_t n) {
+    void* q = nullptr;
+    WB_CK(cudaMallocAsync(&q, std::max<size_t>(n, 1) * sizeof(T), stream));
+    bufs.push_back(q);
+    *p = (T*)q;
+    return 0;
+  }
+};
+
+struct DeviceInfo { int sms; int max_smem_optin; int cc_major; int cc_minor; };
+static int device_info(DeviceInfo* di) {
+  int dev = 0;
+  WB_CK(cudaGetDevice(&dev));
+  WB_CK(cudaDeviceGetAttribute(&di->sms, cudaDevAttrMultiProcessorCount, dev));
+  WB_CK(cudaDeviceGetAttribute(&di->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  WB_CK(cudaDeviceGetAttribute(&di->cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  WB_CK(cudaDeviceGetAttribute(&di->cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (di->cc_major != 10) {
+    set_err("wildboar_b200 requires an sm_100 (B200) device; there is no CPU or other-arch fallback");
+    return 1;
+  }
+  return 0;
+}
+
+// DP cells the reference evaluates per pair: sum_i (j_stop(i) - j_start(i)).
+static int64_t cells_per_pair(int Tx, int Ty, int R) {
+  Geom g = make_geom(Tx, Ty, R);
+  int64_t c = 0;
+  for (int i = 0; i < Tx; ++i) {
+    int js = std::max(0, i - g.a), je = std::min(Ty, i + g.max_len);
+    if (je > js) c += je - js;
+  }
+  return c;
+}
+
+constexpr int kStripW = 8;
+
+template <class M, int NT, int MINB, bool EA>
+static int launch_strip_cfg(const KArgs& a, const M& m, int nwarps, size_t smem, int sms, cudaStream_t st) {
+  auto kern = k_strip<M, kStripW, NT, MINB, EA>;
+  WB_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  WB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nwarps * 32, smem));
+  if (per_sm < 1) { set_err("strip kernel does not fit on an SM"); return 1; }
+  long long warps_total = (long long)sms * per_sm * nwarps;
+  long long grid = (long long)sms * per_sm;
+  if (a.ntasks < warps_total) grid = std::max<long long>(1, (a.ntasks + nwarps - 1) / nwarps);
+  kern<<<(unsigned)grid, nwarps * 32, smem, st>>>(a, m);
+  WB_CK(cudaGetLastError());
+  return 0;
+}
+
+// What one DP launch needs to know.
+struct DpCall {
+  int metric;
+  wb_params p;
+  const double* x; long long nx; int Tx;  // dense device arrays, ORIGINAL series
+  const double* y; long long ny; int Ty;
+  int mode;
+  double* out; long long ld;
+  double* out_m;       // optional (row-scan only)
+  const double* thr;   // optional raw-domain abandon thresholds per x row
+  int ea;              // eadistance() variants of R (ddtw EL:3308, edr EL:3833)
+  long long row0; int mirror;
+  bool need_rowmin;    // force the row-scan engine (exact replay needs row minima)
+  // prepared operands (filled by prepare_operands; reusable across chunked launches)
+  const double* px; const double* py; int ptx, pty;
+  const double* sx; const double* sy;
+  Tables tab;
+  int R;
+  bool degenerate;     // ddtw with min(T) < 3: every distance is 0 (EL:3270)
+};
+
+// Slope transforms, per-series scalars and lookup tables for one (x, y) operand pair.
+static int prepare_operands(Workspace& ws, DpCall& c) {
+  cudaStream_t st = ws.stream;
+  const int Tmin = std::min(c.Tx, c.Ty);
+  c.R = (int)compute_r(Tmin, c.p.r);
+  c.px = c.x; c.py = c.y; c.ptx = c.Tx; c.pty = c.Ty;
+  c.sx = c.sy = nullptr;
+  c.tab.weights = c.tab.tw = nullptr;
+  c.degenerate = false;
+  if (is_derivative(c.metric)) {
+    if (Tmin < 3) { c.degenerate = true; return 0; }
+    double *dx = nullptr, *dy = nullptr;
+    if (ws.alloc(&dx, (size_t)c.nx * (c.Tx - 2))) return 1;
+    k_slope<<<1024, 256, 0, st>>>(c.x, c.nx, c.Tx, dx);
+    if (c.y == c.x && c.ny == c.nx && c.Ty == c.Tx) dy = dx;
+    else {
+      if (ws.alloc(&dy, (size_t)c.ny * (c.Ty - 2))) return 1;
+      k_slope<<<1024, 256, 0, st>>>(c.y, c.ny, c.Ty, dy);
+    }
+    WB_CK(cudaGetLastError());
+    c.px = dx; c.py = dy; c.ptx = c.Tx - 2; c.pty = c.Ty - 2;
+    if (c.ea) c.R = (int)compute_r(std::min(c.ptx, c.pty), c.p.r);
+  }
+  if (c.metric == M_EDR && c.ea) c.R = (int)compute_r(c.Tx, c.p.r);
+  const int nmax = std::max(c.ptx, c.pty);
+  if (c.metric == M_WDTW || c.metric == M_WLCSS || c.metric == M_WDDTW || c.metric == M_TWE) {
+    ws.host_keep.push_back(c.metric == M_TWE ? make_tw(c.p.stiffness, nmax + 1) : make_weights(c.p.g, nmax));
+    std::vector<double>& h = ws.host_keep.back();
+    double* d = nullptr;
+    if (ws.alloc(&d, h.size())) return 1;
+    WB_CK(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (c.metric == M_TWE) c.tab.tw = d; else c.tab.weights = d;
+  }
+  if (c.metric == M_ERP || (c.metric == M_EDR && std::isnan(c.p.epsilon))) {
+    const int kind = c.metric == M_ERP ? 0 : 1;
+    double *sx = nullptr, *sy = nullptr;
+    if (ws.alloc(&sx, (size_t)c.nx)) return 1;
+    k_series_stat<<<(unsigned)((c.nx + 127) / 128), 128, 0, st>>>(c.px, c.nx, c.ptx, kind, c.p.g, sx);
+    if (c.py == c.px && c.ny == c.nx && c.pty == c.ptx) sy = sx;
+    else {
+      if (ws.alloc(&sy, (size_t)c.ny)) return 1;
+      k_series_stat<<<(unsigned)((c.ny + 127) / 128), 128, 0, st>>>(c.py, c.ny, c.pty, kind, c.p.g, sy);
+    }
+    WB_CK(cudaGetLastError());
+    c.sx = sx; c.sy = sy;
+  }
+  return 0;
+}
+
+// Launch the DP over rows [r0, r0+nrows) of the prepared x against columns [c0, c0+ncols) of
+// the prepared y.  out/out_m/thr are indexed relative to (r0, c0) / r0.
+static int launch_dp(Workspace& ws, const DeviceInfo& di, const DpCall& c, long long r0, long long nrows,
+                     long long c0, long long ncols, double* out, long long ld, double* out_m, const double* thr,
+                     wb_stats* stats) {
+  cudaStream_t st = ws.stream;
+  if (nrows <= 0 || ncols <= 0) return 0;
+  if (c.degenerate) {
+    if (c.mode == PM_PAIRED) WB_CK(cudaMemsetAsync(out, 0, sizeof(double) * nrows, st));
+    else WB_CK(cudaMemset2DAsync(out, ld * sizeof(double), 0, ncols * sizeof(double), nrows, st));
+    return 0;
+  }
+  KArgs a;
+  memset(&a, 0, sizeof a);
+  a.x = c.px + r0 * c.ptx; a.y = c.py + c0 * c.pty;
+  a.nx = nrows; a.ny = ncols; a.Tx = c.ptx; a.Ty = c.pty;
+  a.g = make_geom(c.ptx, c.pty, c.R);
+  a.sx = c.sx ? c.sx + r0 : nullptr; a.sy = c.sy ? c.sy + c0 : nullptr;
+  a.out = out; a.ld = ld; a.out_m = out_m; a.thr = thr;
+  a.mode = c.mode; a.row0 = c.row0 + r0 - c0; a.mirror = c.mirror;
+  a.nyb = (ncols + 31) / 32;
+  a.ntasks = (c.mode == PM_PAIRED) ? (nrows + 31) / 32 : nrows * a.nyb;
+  unsigned long long* counter = nullptr;
+  if (ws.alloc(&counter, 1)) return 1;
+  WB_CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+  a.counter = counter;
+
+  a.NS = strip_ring_slots(a.g);
+  const size_t per_warp = (size_t)a.NS * 32 * sizeof(double);
+  const size_t smem_cap = (size_t)di.max_smem_optin;
+  int engine = 0;
+  int rc = 0;
+  bool known = with_policy(c.metric, c.p, c.tab, [&](auto m) {
+    using M = decltype(m);
+    bool strip_ok = strip_supported<M>(a.g, kStripW) && per_warp <= smem_cap && !c.need_rowmin &&
+                    !(out_m != nullptr) && c.p.engine != 1;
+    if (thr && !M::kColumnMinBound) strip_ok = false;  // exact abandoning needs row minima
+    if (c.p.engine == 2 && !strip_ok) { set_err("strip engine forced but not applicable"); rc = 1; return; }
+    if (strip_ok) {
+      engine = 2;
+      int nw = (int)std::min<size_t>(8, smem_cap / per_warp);
+      const bool two = 2 * 8 * per_warp <= smem_cap;
+      if constexpr (M::kColumnMinBound) {
+        if (thr) {
+          rc = two ? launch_strip_cfg<M, 256, 2, true>(a, m, 8, 8 * per_warp, di.sms, st)
+                   : launch_strip_cfg<M, 256, 1, true>(a, m, nw, nw * per_warp, di.sms, st);
+          return;
+        }
+      }
+      rc = two ? launch_strip_cfg<M, 256, 2, false>(a, m, 8, 8 * per_warp, di.sms, st)
+               : launch_strip_cfg<M, 256, 1, false>(a, m, nw, nw * per_warp, di.sms, st);
+    } else {
+      engine = 1;
+      constexpr int NT = 128;
+      int per_sm = 0;
+      auto kern = k_rowscan<M, NT>;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, 0) != cudaSuccess || per_sm < 1) {
+        set_err("row-scan kernel occupancy query failed"); rc = 1; return;
+      }
+      per_sm = std::min(per_sm, 4);
+      long long grid = (long long)di.sms * per_sm;
+      long long need = (a.ntasks * 32 + NT - 1) / NT;
+      grid = std::max<long long>(1, std::min(grid, need));
+      a.srows = std::max(c.ptx, c.pty) + 1;
+      a.sstride = grid * NT;
+      double* scratch = nullptr;
+      if (ws.alloc(&scratch, (size_t)2 * a.srows * a.sstride)) { rc = 1; return; }
+      a.scratch = scratch;
+      kern<<<(unsigned)grid, NT, 0, st>>>(a, m);
+      if (cudaGetLastError() != cudaSuccess) { set_err("row-scan kernel launch failed"); rc = 1; }
+    }
+  });
+  if (!known) { set_err("unknown metric id"); return 1; }
+  if (rc) return rc;
+  if (stats) {
+    stats->engine = engine;
+    stats->launches += 1;
+    long long pairs = (c.mode == PM_PAIRED) ? nrows : nrows * ncols;
+    if (c.mode == PM_SELF) {
+      pairs = 0;
+      for (long long i = 0; i < nrows; ++i) {
+        long long ig = a.row0 + i;
+        pairs += std::max<long long>(0, ncols - 1 - ig);
+      }
+    }
+    stats->pairs += pairs;
+    stats->cells += pairs * cells_per_pair(c.ptx, c.pty, c.R);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Host-buffer drivers: stage, shard rows over devices, gather.
+// ------------------------------------------------------------------------------------------
+struct HostJob {
+  int kind;  // 0 pairwise, 1 self, 2 paired, 3 argmin
+  int metric; wb_params p;
+  const double* x; int64_t nx, Tx, xs;
+  const double* y; int64_t ny, Ty, ys;
+  double* out;
+  int64_t k; const double* lower_bound; int use_device_lb; int64_t* out_idx;
+};
+
+static int h2d_rows(double* dst, const double* src, int64_t rows, int64_t T, int64_t stride, cudaStream_t st) {
+  if (rows <= 0) return 0;
+  if (stride == T) WB_CK(cudaMemcpyAsync(dst, src, sizeof(double) * rows * T, cudaMemcpyHostToDevice, st));
+  else WB_CK(cudaMemcpy2DAsync(dst, sizeof(double) * T, src, sizeof(double) * stride, sizeof(double) * T, rows,
+                               cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+struct Timer {
+  cudaEvent_t a, b; cudaStream_t st; bool ok;
+  explicit Timer(cudaStream_t s) : st(s) { ok = cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess; }
+  ~Timer() { if (ok) { cudaEventDestroy(a); cudaEventDestroy(b); } }
+  void start() { if (ok) cudaEventRecord(a, st); }
+  void stop() { if (ok) cudaEventRecord(b, st); }
+  double ms() { float f = 0; if (ok && cudaEventSynchronize(b) == cudaSuccess) cudaEventElapsedTime(&f, a, b); return f; }
+};
+
+// rows [lo, hi) of the job on device `dev`
+static int device_worker(const HostJob& J, int dev, int64_t lo, int64_t hi, wb_stats* st_out) {
+  WB_CK(cudaSetDevice(dev));
+  DeviceInfo di;
+  if (device_info(&di)) return 1;
+  cudaStream_t st, cst;
+  WB_CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  WB_CK(cudaStreamCreateWithFlags(&cst, cudaStreamNonBlocking));
+  int rc = 0;
+  wb_stats stats;
+  memset(&stats, 0, sizeof stats);
+  {
+    Workspace ws(st);
+    Timer total(st);
+    total.start();
+    const int64_t rows = hi - lo;
+    double *dx = nullptr, *dy = nullptr;
+    do {
+      if (J.kind == 1) {
+        // self join: every device holds all of x (columns); its rows are [lo, hi)
+        if ((rc = ws.alloc(&dy, (size_t)J.nx * J.Tx))) break;
+        if ((rc = h2d_rows(dy, J.x, J.nx, J.Tx, J.xs, st))) break;
+        dx = dy + lo * J.Tx;
+      } else if (J.kind == 2) {
+        // paired: first operand is the USER's y (CD:1632-1647)
+        if ((rc = ws.alloc(&dx, (size_t)rows * J.Ty))) break;
+        if ((rc = ws.alloc(&dy, (size_t)rows * J.Tx))) break;
+        if ((rc = h2d_rows(dx, J.y + lo * J.ys, rows, J.Ty, J.ys, st))) break;
+        if ((rc = h2d_rows(dy, J.x + lo * J.xs, rows, J.Tx, J.xs, st))) break;
+      } else {
+        if ((rc = ws.alloc(&dx, (size_t)rows * J.Tx))) break;
+        if ((rc = ws.alloc(&dy, (size_t)J.ny * J.Ty))) break;
+        if ((rc = h2d_rows(dx, J.x + lo * J.xs, rows, J.Tx, J.xs, st))) break;
+        if ((rc = h2d_rows(dy, J.y, J.ny, J.Ty, J.ys, st))) break;
+      }
+      DpCall c;
+      memset(&c, 0, sizeof c);
+      c.metric = J.metric; c.p = J.p;
+      if (J.kind == 2) { c.x = dx; c.nx = rows; c.Tx = (int)J.Ty; c.y = dy; c.ny = rows; c.Ty = (int)J.Tx; c.mode = PM_PAIRED; }
+      else if (J.kind == 1) { c.x = dx; c.nx = rows; c.Tx = (int)J.Tx; c.y = dy; c.ny = J.nx; c.Ty = (int)J.Tx; c.mode = PM_SELF; c.row0 = lo; }
+      else { c.x = dx; c.nx = rows; c.Tx = (int)J.Tx; c.y = dy; c.ny = J.ny; c.Ty = (int)J.Ty; c.mode = PM_PAIRWISE; }
+
+      if (J.kind == 3) {
+        c.ea = 1;
+        if ((rc = prepare_operands(ws, c))) break;
+        ArgminIo io;
+        io.k = J.k; io.lower_bound = J.lower_bound ? J.lower_bound + lo * J.ny : nullptr; io.lb_ld = J.ny;
+        io.out_idx = J.out_idx + lo * J.k; io.out_dist = J.out + lo * J.k; io.use_device_lb = J.use_device_lb;
+        rc = run_argmin(ws, di, c, io, &stats,
+                        [&](long long r0, long long nr, long long c0, long long nc, double* o, long long ld, double* om,
+                            const double* thr, wb_stats* s) { return launch_dp(ws, di, c, r0, nr, c0, nc, o, ld, om, thr, s); });
+        if (rc) break;
+        WB_CK(cudaStreamSynchronize(st));
+        break;
+      }
+
+      if ((rc = prepare_operands(ws, c))) break;
+      if (J.kind == 2) {
+        double* dout = nullptr;
+        if ((rc = ws.alloc(&dout, (size_t)rows))) break;
+        Timer kt(st); kt.start();
+        if ((rc = launch_dp(ws, di, c, 0, rows, 0, rows, dout, 1, nullptr, nullptr, &stats))) break;
+        kt.stop();
+        WB_CK(cudaMemcpyAsync(J.out + lo, dout, sizeof(double) * rows, cudaMemcpyDeviceToHost, st));
+        WB_CK(cudaStreamSynchronize(st));
+        stats.kernel_ms += kt.ms();
+        break;
+      }
+      // pairwise / self: chunk the row block so result slabs stream back while the next chunk computes
+      const int64_t ncols = c.ny;
+      const size_t slab_budget = (size_t)256 << 20;
+      int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(rows, (int64_t)(slab_budget / (sizeof(double) * std::max<int64_t>(ncols, 1)))));
+      const int64_t nchunks = (rows + chunk - 1) / chunk;
+      double* dbuf[2] = {nullptr, nullptr};
+      if ((rc = ws.alloc(&dbuf[0], (size_t)chunk * ncols))) break;
+      if (nchunks > 1 && (rc = ws.alloc(&dbuf[1], (size_t)chunk * ncols))) break;
+      cudaEvent_t done[2], k0[2], k1[2];
+      for (int b = 0; b < 2; ++b) { cudaEventCreate(&done[b]); cudaEventCreate(&k0[b]); cudaEventCreate(&k1[b]); }
+      auto enqueue = [&](int64_t ci) -> int {
+        const int b = (int)(ci & 1);
+        const int64_t r0 = ci * chunk, nr = std::min(chunk, rows - r0);
+        if (J.kind == 1) WB_CK(cudaMemsetAsync(dbuf[b], 0, sizeof(double) * nr * ncols, st));
+        WB_CK(cudaEventRecord(k0[b], st));
+        if (launch_dp(ws, di, c, r0, nr, 0, ncols, dbuf[b], ncols, nullptr, nullptr, &stats)) return 1;
+        WB_CK(cudaEventRecord(k1[b], st));
+        WB_CK(cudaEventRecord(done[b], st));
+        return 0;
+      };
+      if ((rc = enqueue(0))) break;
+      for (int64_t ci = 0; ci < nchunks && !rc; ++ci) {
+        const int b = (int)(ci & 1);
+        const int64_t r0 = ci * chunk, nr = std::min(chunk, rows - r0);
+        if (ci + 1 < nchunks) {
+          // buffer (ci+1)&1 was drained by the copy of chunk ci-1 (synchronous for the host)
+          if ((rc = enqueue(ci + 1))) break;
+        }
+        if (cudaStreamWaitEvent(cst, done[b], 0) != cudaSuccess) { set_err("cudaStreamWaitEvent failed"); rc = 1; break; }
+        if (cudaMemcpyAsync(J.out + (lo + r0) * ncols, dbuf[b], sizeof(double) * nr * ncols, cudaMemcpyDeviceToHost, cst) != cudaSuccess ||
+            cudaStreamSynchronize(cst) != cudaSuccess) { set_err("device-to-host copy of the result slab failed"); rc = 1; break; }
+        float f = 0;
+        if (cudaEventElapsedTime(&f, k0[b], k1[b]) == cudaSuccess) stats.kernel_ms += f;
+      }
+      for (int b = 0; b < 2; ++b) { cudaEventDestroy(done[b]); cudaEventDestroy(k0[b]); cudaEventDestroy(k1[b]); }
+      if (rc) break;
+      WB_CK(cudaStreamSynchronize(st));
+    } while (0);
+    total.stop();
+    if (!rc) { cudaStreamSynchronize(st); stats.total_ms = total.ms(); }
+  }
+  cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  cudaStreamDestroy(cst);
+  if (st_out) *st_out = stats;
+  return rc;
+}
+
+// utils/_parallel.py:7-23: contiguous row blocks, the first (n % G) one row longer
+static void row_blocks(int64_t n, int G, std::vector<int64_t>& off) {
+  off.assign(G + 1, 0);
+  int64_t bs = n / G, ov = n % G;
+  for (int b = 0; b < G; ++b) off[b + 1] = off[b] + bs + (b < ov ? 1 : 0);
+}
+// self join: rows i cost (n-1-i) pairs; cut so every device gets ~equal pair counts
+static void tri_blocks(int64_t n, int G, std::vector<int64_t>& off) {
+  off.assign(G + 1, n);
+  off[0] = 0;
+  const double total = 0.5 * (double)n * (double)(n - 1);
+  int64_t i = 0;
+  double acc = 0;
+  for (int b = 1; b < G; ++b) {
+    const double target = total * b / G;
+    while (i < n && acc + (double)(n - 1 - i) <= target) { acc += (double)(n - 1 - i); ++i; }
+    off[b] = i;
+  }
+}
+
+static int run_host_job(const HostJob& J, const int* devices, int n_devices, wb_stats* stats) {
+  int ndev_avail = 0;
+  if (cudaGetDeviceCount(&ndev_avail) != cudaSuccess || ndev_avail < 1) {
+    set_err("no CUDA device available: wildboar_b200 has no CPU fallback");
+    return 1;
+  }
+  std::vector<int> devs;
+  if (devices && n_devices > 0) devs.assign(devices, devices + n_devices);
+  else devs.push_back(0);
+  for (int d : devs) if (d < 0 || d >= ndev_avail) { set_err("invalid device ordinal"); return 1; }
+  const int64_t n_work = J.nx;
+  int G = (int)std::min<int64_t>((int64_t)devs.size(), std::max<int64_t>(n_work, 1));
+  std::vector<int64_t> off;
+  if (J.kind == 1) tri_blocks(n_work, G, off); else row_blocks(n_work, G, off);
+  std::vector<wb_stats> sts(G);
+  std::vector<int> rcs(G, 0);
+  std::vector<std::string> errs(G);
+  if (G == 1) {
+    rcs[0] = device_worker(J, devs[0], off[0], off[1], &sts[0]);
+    errs[0] = g_err;
+  } else {
+    std::vector<std::thread> th;
+    for (int b = 0; b < G; ++b)
+      th.emplace_back([&, b]() { rcs[b] = device_worker(J, devs[b], off[b], off[b + 1], &sts[b]); errs[b] = g_err; });
+    for (auto& t : th) t.join();
+  }
+  for (int b = 0; b < G; ++b) if (rcs[b]) { set_err(errs[b]); return rcs[b]; }
+  if (J.kind == 1) {
+    // lower triangle = copy of the upper one (CD:1240-1246), blocked for cache friendliness
+    const int64_t n = J.nx, B = 64;
+    for (int64_t ib = 0; ib < n; ib += B)
+      for (int64_t jb = ib; jb < n; jb += B)
+        for (int64_t i = ib; i < std::min(ib + B, n); ++i)
+          for (int64_t j = std::max(jb, i + 1); j < std::min(jb + B, n); ++j) J.out[j * n + i] = J.out[i * n + j];
+  }
+  if (stats) {
+    memset(stats, 0, sizeof *stats);
+    for (int b = 0; b < G; ++b) {
+      stats->kernel_ms = std::max(stats->kernel_ms, sts[b].kernel_ms);
+      stats->total_ms = std::max(stats->total_ms, sts[b].total_ms);
+      stats->cells += sts[b].cells; stats->pairs += sts[b].pairs; stats->launches += sts[b].launches;
+      stats->engine = std::max(stats->engine, sts[b].engine);
+    }
+  }
+  return 0;
+}
+
+static int check_common(int metric, const wb_params* p, const void* x, int64_t n, int64_t T) {
+  if (!p || !x) { set_err("null argument"); return 1; }
+  if (metric < 0 || metric >= M_COUNT) { set_err("unknown metric id"); return 1; }
+  if (n < 1 || T < 1) { set_err("empty input"); return 1; }
+  if (T > (1 << 24)) { set_err("series too long"); return 1; }
+  if (!(p->r >= 0.0 && p->r <= 1.0)) { set_err("r must be in [0, 1]"); return 1; }
+  return 0;
+}
+
+}  // namespace wb
+
+using namespace wb;
+
+extern "C" {
+
+int wb_cuda_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char* wb_cuda_last_error(void) { return g_err.c_str(); }
+
+int wb_cuda_pairwise(int metric, const wb_params* params, const double* x, int64_t nx, int64_t Tx, int64_t x_stride,
+                     const double* y, int64_t ny, int64_t Ty, int64_t y_stride, double* out, const int* devices,
+                     int n_devices, wb_stats* stats) {
+  if (check_common(metric, params, x, nx, Tx) || check_common(metric, params, y, ny, Ty)) return 1;
+  if (!out) { set_err("null output"); return 1; }
+  if (metric == M_WDDTW && Tx > Ty) { set_err("wddtw requires len(x) <= len(y) (the reference overflows a buffer otherwise)"); return 1; }
+  HostJob J; memset(&J, 0, sizeof J);
+  J.kind = 0; J.metric = metric; J.p = *params; J.x = x; J.nx = nx; J.Tx = Tx; J.xs = x_stride;
+  J.y = y; J.ny = ny; J.Ty = Ty; J.ys = y_stride; J.out = out;
+  return run_host_job(J, devices, n_devices, stats);
+}
+
+int wb_cuda_pairwise_self(int metric, const wb_params* params, const double* x, int64_t n, int64_t T,
+                          int64_t x_stride, double* out, const int* devices, int n_devices, wb_stats* stats) {
+  if (check_common(metric, params, x, n, T)) return 1;
+  if (!out) { set_err("null output"); return 1; }
+  HostJob J; memset(&J, 0, sizeof J);
+  J.kind = 1; J.metric = metric; J.p = *params; J.x = x; J.nx = n; J.Tx = T; J.xs = x_stride;
+  J.y = x; J.ny = n; J.Ty = T; J.ys = x_stride; J.out = out;
+  return run_host_job(J, devices, n_devices, stats);
+}
+
+int wb_cuda_paired(int metric, const wb_params* params, const double* x, int64_t n, int64_t Tx, int64_t x_stride,
+                   const double* y, int64_t Ty, int64_t y_stride, double* out, const int* devices, int n_devices,
+                   wb_stats* stats) {
+  if (check_common(metric, params, x, n, Tx) || check_common(metric, params, y, n, Ty)) return 1;
+  if (!out) { set_err("null output"); return 1; }
+  if (metric == M_WDDTW && Ty > Tx) { set_err("wddtw (paired, operands swapped) requires len(y) <= len(x)"); return 1; }
+  HostJob J; memset(&J, 0, sizeof J);
+  J.kind = 2; J.metric = metric; J.p = *params; J.x = x; J.nx = n; J.Tx = Tx; J.xs = x_stride;
+  J.y = y; J.ny = n; J.Ty = Ty; J.ys = y_stride; J.out = out;
+  return run_host_job(J, devices, n_devices, stats);
+}
+
+int wb_cuda_argmin(int metric, const wb_params* params, const double* x, int64_t nx, int64_t Tx, int64_t x_stride,
+                   const double* y, int64_t ny, int64_t Ty, int64_t y_stride, int64_t k, const double* lower_bound,
+                   int use_device_lb, int64_t* out_idx, double* out_dist, const int* devices, int n_devices,
+                   wb_stats* stats) {
+  if (check_common(metric, params, x, nx, Tx) || check_common(metric, params, y, ny, Ty)) return 1;
+  if (!out_idx || !out_dist) { set_err("null output"); return 1; }
+  if (k < 1 || k > ny) { set_err("k must satisfy 1 <= k <= n_y"); return 1; }
+  if (metric == M_WDDTW && Tx > Ty) { set_err("wddtw requires len(x) <= len(y)"); return 1; }
+  HostJob J; memset(&J, 0, sizeof J);
+  J.kind = 3; J.metric = metric; J.p = *params; J.x = x; J.nx = nx; J.Tx = Tx; J.xs = x_stride;
+  J.y = y; J.ny = ny; J.Ty = Ty; J.ys = y_stride; J.out = out_dist; J.out_idx = out_idx; J.k = k;
+  J.lower_bound = lower_bound; J.use_device_lb = use_device_lb;
+  return run_host_job(J, devices, n_devices, stats);
+}
+
+int wb_cuda_pairwise_dev(int metric, const wb_params* params, const double* d_x, int64_t nx, int64_t Tx,
+                         const double* d_y, int64_t ny, int64_t Ty, double* d_out, void* stream, wb_stats* stats) {
+  if (check_common(metric, params, d_x, nx, Tx) || check_common(metric, params, d_y, ny, Ty)) return 1;
+  if (!d_out) { set_err("null output"); return 1; }
+  if (metric == M_WDDTW && Tx > Ty) { set_err("wddtw requires len(x) <= len(y)"); return 1; }
+  DeviceInfo di;
+  if (device_info(&di)) return 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  wb_stats local; memset(&local, 0, sizeof local);
+  int rc = 0;
+  double kms = 0;
+  {
+    Workspace ws(st);
+    DpCall c; memset(&c, 0, sizeof c);
+    c.metric = metric; c.p = *params; c.x = d_x; c.nx = nx; c.Tx = (int)Tx; c.y = d_y; c.ny = ny; c.Ty = (int)Ty;
+    c.mode = PM_PAIRWISE;
+    Timer kt(st);
+    rc = prepare_operands(ws, c);
+    if (!rc) {
+      kt.start();
+      rc = launch_dp(ws, di, c, 0, nx, 0, ny, d_out, ny, nullptr, nullptr, &local);
+      kt.stop();
+    }
+    if (!rc && stats) kms = kt.ms();
+  }
+  if (rc) return rc;
+  if (stats) { *stats = local; stats->kernel_ms = kms; stats->total_ms = kms; }
+  return 0;
+}
+
+int wb_cuda_fp64_peak(int mix, double* inst_per_s, double* sm_mhz_est) {
+  DeviceInfo di;
+  if (device_info(&di)) return 1;
+  const int threads = 256, per_sm = 8, iters = 1 << 15;
+  const long long grid = (long long)di.sms * per_sm;
+  double* out = nullptr; unsigned long long* cyc = nullptr;
+  WB_CK(cudaMalloc(&out, sizeof(double) * grid * threads));
+  WB_CK(cudaMalloc(&cyc, sizeof(unsigned long long)));
+  cudaEvent_t a, b;
+  WB_CK(cudaEventCreate(&a)); WB_CK(cudaEventCreate(&b));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    WB_CK(cudaEventRecord(a));
+    k_fp64_peak<<<(unsigned)grid, threads>>>(mix, iters, 1.0 + rep, out, cyc);
+    WB_CK(cudaEventRecord(b));
+    WB_CK(cudaEventSynchronize(b));
+    float ms = 0; WB_CK(cudaEventElapsedTime(&ms, a, b));
+    if (rep > 0) best = std::min(best, ms);
+  }
+  unsigned long long hc = 0;
+  WB_CK(cudaMemcpy(&hc, cyc, sizeof hc, cudaMemcpyDeviceToHost));
+  // FP64-pipe instructions per thread-iteration: mix 0: 8 DADD; mix 1: 4 cells x (DADD, DMUL, DADD, 2 DSETP)
+  const double per_iter = mix == 0 ? 8.0 : 20.0;
+  const double lane_inst = (double)grid * threads * (double)iters * per_iter;
+  if (inst_per_s) *inst_per_s = lane_inst / (best * 1e-3);
+  if (sm_mhz_est) *sm_mhz_est = (double)hc / (best * 1e-3) / 1e6;
+  cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out); cudaFree(cyc);
+  return 0;
+}
+
+}  // extern "C"
