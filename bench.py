@@ -47,10 +47,7 @@ def cells_per_pair(T, r):
     return T * (2 * R - 1) - R * (R - 1) if R <= T else T * T
 
 
-def row_block(n, nb, b):
-    bs, ov = divmod(n, nb)
-    lo = b * bs + min(b, ov)
-    return lo, lo + bs + (1 if b < ov else 0)
+from wildboar_b200.sharding import aggregate_throughput, max_over_ranks, row_block  # noqa: E402
 
 
 class ClockSampler:
@@ -181,8 +178,14 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOAD))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--profile-rows", type=int, default=0,
+                    help="PROFILING ONLY (ncu): shrink the x row count so ~40 kernel replays stay short; "
+                         "the JSON line is then marked and is not a bench value")
     args = ap.parse_args()
-    wl = WORKLOAD[args.workload]
+    wl = dict(WORKLOAD[args.workload])
+    if args.profile_rows > 0:
+        wl["nx"] = min(wl["nx"], args.profile_rows)
+        wl["desc"] += f" [PROFILING RUN: first {wl['nx']} x rows only]"
     if args.impl == "reference":
         run_reference_arm(args, wl, args.workload)
         return
@@ -274,14 +277,11 @@ def main():
     e2e_stats = wb.last_stats()
     assert res.shape == (nx, ny)
 
-    tms = torch.tensor([ms, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, kernel_ms = [float(v) for v in tms.tolist()]
+    ms, e2e_ms, kernel_ms = max_over_ranks([ms, e2e_s * 1e3, kernel_ms], device=dev)
 
     if rank == 0:
-        value = cells_total * args.steps / (ms * 1e-3) / 1e9
-        e2e_value = cells_total * e2e_steps / (e2e_ms * 1e-3) / 1e9
+        value = aggregate_throughput(cells_total, args.steps, ms) / 1e9
+        e2e_value = aggregate_throughput(cells_total, e2e_steps, e2e_ms) / 1e9
         ops = FP64_OPS_PER_CELL[metric]
         achieved = cells_rank * ops / (kernel_ms * 1e-3) / 1e9  # G FP64-pipe lane-instructions / s, this GPU
         nominal = 148 * 64 * 1.965  # G lane-inst/s at max boost

@@ -18,8 +18,14 @@ struct StripRunner {
     if (!strip_supported<M>(g, W)) { *ok = 0; return 0; }
     *ok = 1;
     std::vector<double> bnd((size_t)NS * bs + 8, -12345.0);
-    return abandon < INFINITY ? strip_pair<M, W, true>(g, m, x, y, bnd.data(), bs, NS, abandon)
-                              : strip_pair<M, W, false>(g, m, x, y, bnd.data(), bs, NS, abandon);
+    if (abandon < INFINITY) return strip_pair<M, W, true>(g, m, x, y, bnd.data(), bs, NS, abandon);
+    // exercise several in-thread wavefront depths
+    const double r2 = strip_pair<M, W, false, 2>(g, m, x, y, bnd.data(), bs, NS, abandon);
+    const double r1 = strip_pair<M, W, false, 1>(g, m, x, y, bnd.data(), bs, NS, abandon);
+    const double r4 = strip_pair<M, W, false, 4>(g, m, x, y, bnd.data(), bs, NS, abandon);
+    const double r3 = strip_pair<M, W, false, 3>(g, m, x, y, bnd.data(), bs, NS, abandon);
+    if (!(r1 == r2 && r2 == r4 && r3 == r2) && !(r1 != r1 && r2 != r2)) return -1e300;  // NR variants disagree
+    return r2;
   }
 };
 

@@ -69,7 +69,7 @@ WB_HD double sel_f64(bool p, double a, double b) {
 // `generic_row` (per-cell, warp-uniform predicates).  Full rows -- (2R-1-W+1)/(2R-1+W-1) of
 // all rows, 87 % for the headline shape -- take the predicate-free `fast path`, two rows per
 // iteration so that two independent left->right dependency chains are in flight per thread.
-template <class M, int W, bool EA>
+template <class M, int W, bool EA, int NR = 2>
 WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
                         const double* __restrict__ y, double* bnd, int bs, int NS, double abandon) {
   const int Tx = g.Tx, Ty = g.Ty;
@@ -156,45 +156,110 @@ WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
     int fb = imin2(i_hi, j0 + g.a);
     if (M::kMsmBand) fb -= 1;  // the generic row captures the stale-left value for the bottom triangle
 
-    while (i < fa && i <= i_hi) generic_row();
+    // Regular triangles (band edges cross the strip away from the matrix borders) are run as
+    // straight-line code with exactly the in-band cells of every row: no per-cell predicates.
+    const bool wide = !M::kMsmBand && wv == W && g.H >= 2 * W;
+    const bool reg_top = wide && i_lo >= 1 && i_lo == j0 - g.max_len + 1;
+    const bool reg_bot = wide && (j0 + g.a + W - 1 <= Tx - 1);
 
-    while (i + 1 <= fb) {
-      // ---- fast path: rows i and i+1, all W cells in band, no predicates ----
-      const double xa = xi;
-      const double xb = x[i + 1];
-      const double xnext = x[imin2(i + 2, Tx - 1)];
-      const int sl1 = (sl + 1 == NS) ? 0 : sl + 1;
-      const double la = bnd[sl * bs];
-      const double lb = bnd[sl1 * bs];
-      const typename M::Row ra = m.row(i, xa, xim);
-      const typename M::Row rb = m.row(i + 1, xb, xa);
-      double diag_a = Dg;
-      double diag_b = la;
-      double left_a = la, left_b = lb;
+    // One copy of every row routine; the hot two-row loop stays a tight inner loop.
+    for (;;) {
+      while (i >= fa && i + NR - 1 <= fb) {
+        // ---- fast path: rows i .. i+NR-1, all W cells in band, no predicates; NR independent
+        // left->right dependency chains (an in-thread anti-diagonal wavefront) ----
+        double xr[NR];
+        xr[0] = xi;
 #pragma unroll
-      for (int c = 0; c < W; ++c) {
-        const double up = prev[c];
-        const double da = m.cell(up, left_a, diag_a, ra, cols[c], i, j0 + c);
-        const double db = m.cell(da, left_b, diag_b, rb, cols[c], i + 1, j0 + c);
-        diag_a = up;
-        diag_b = da;
-        left_a = da;
-        left_b = db;
-        prev[c] = db;
+        for (int r = 1; r < NR; ++r) xr[r] = x[i + r];
+        const double xnext = x[imin2(i + NR, Tx - 1)];
+        int slr[NR];
+        slr[0] = sl;
+#pragma unroll
+        for (int r = 1; r < NR; ++r) slr[r] = (slr[r - 1] + 1 == NS) ? 0 : slr[r - 1] + 1;
+        double lft[NR], dg[NR];
+        typename M::Row rws[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          lft[r] = bnd[slr[r] * bs];
+          rws[r] = m.row(i + r, xr[r], r == 0 ? xim : xr[r - 1]);
+        }
+        dg[0] = Dg;
+#pragma unroll
+        for (int r = 1; r < NR; ++r) dg[r] = lft[r - 1];
+        Dg = lft[NR - 1];
+#pragma unroll
+        for (int c = 0; c < W; ++c) {
+          double v = prev[c];
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            const double d = m.cell(v, lft[r], dg[r], rws[r], cols[c], i + r, j0 + c);
+            dg[r] = v;
+            lft[r] = d;
+            v = d;
+          }
+          prev[c] = v;
+        }
+        // lft[r] now holds column W-1 of row i+r (the last strip's writes are never read; they
+        // are kept so the hot loop has no strip-dependent branch)
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          bnd[slr[r] * bs] = lft[r];
+          if (EA && M::kColumnMinBound) colmin = dmin2(colmin, lft[r]);
+        }
+        sl = (slr[NR - 1] + 1 == NS) ? 0 : slr[NR - 1] + 1;
+        xim = xr[NR - 1];
+        xi = xnext;
+        i += NR;
       }
-      // left_a / left_b now hold column W-1 of rows i / i+1 (the last strip's writes are
-      // never read; they are kept so the hot loop has no strip-dependent branch)
-      bnd[sl * bs] = left_a;
-      bnd[sl1 * bs] = left_b;
-      if (EA && M::kColumnMinBound) colmin = dmin2(colmin, dmin2(left_a, left_b));
-      Dg = lb;
-      sl = (sl1 + 1 == NS) ? 0 : sl1 + 1;
-      xim = xb;
-      xi = xnext;
-      i += 2;
+      if (i > i_hi) break;
+      if (reg_top && i == i_lo) {
+#pragma unroll
+        for (int t = 0; t < W - 1; ++t) {
+          const double xnext = x[imin2(i + 1, Tx - 1)];
+          double left = bnd[sl * bs];
+          double diag = Dg;
+          Dg = left;
+          const typename M::Row rw = m.row(i, xi, xim);
+#pragma unroll
+          for (int c = 0; c <= t; ++c) {
+            const double up = prev[c];
+            const double d = m.cell(up, left, diag, rw, cols[c], i, j0 + c);
+            prev[c] = d;
+            left = d;
+            diag = up;
+          }
+          sl = (sl + 1 == NS) ? 0 : sl + 1;
+          xim = xi;
+          xi = xnext;
+          ++i;
+        }
+      } else if (reg_bot && i == j0 + g.a + 1) {
+#pragma unroll
+        for (int t = 1; t < W; ++t) {
+          // row i = j0 + a + t: cells t..W-1; the cell left of the band reads the sentinel
+          const double xnext = x[imin2(i + 1, Tx - 1)];
+          const typename M::Row rw = m.row(i, xi, xim);
+          double left = m.lsent();
+          double diag = prev[t - 1];
+#pragma unroll
+          for (int c = t; c < W; ++c) {
+            const double up = prev[c];
+            const double d = m.cell(up, left, diag, rw, cols[c], i, j0 + c);
+            prev[c] = d;
+            left = d;
+            diag = up;
+          }
+          bnd[sl * bs] = left;
+          if (EA && M::kColumnMinBound) colmin = dmin2(colmin, left);
+          sl = (sl + 1 == NS) ? 0 : sl + 1;
+          xim = xi;
+          xi = xnext;
+          ++i;
+        }
+      } else {
+        generic_row();
+      }
     }
-
-    while (i <= i_hi) generic_row();
 
     if (!last_strip) {
       if (jl + g.a + 1 <= Tx - 1) bnd[sl * bs] = M::kMsmBand ? stale : m.lsent();

@@ -66,7 +66,7 @@ __device__ __forceinline__ long long next_task(unsigned long long* counter, int 
 }
 
 // ---- strip engine: thread per pair, boundary ring in shared memory [warp][slot][lane] ----
-template <class M, int W, int NT, int MINB, bool EA>
+template <class M, int W, int NT, int MINB, bool EA, int NR = 2>
 __global__ void __launch_bounds__(NT, MINB) k_strip(KArgs a, M m) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(NT, MINB) k_strip(KArgs a, M m) {
     pc.sy = a.sy ? a.sy[j] : 0.0;
     mm.begin_pair(pc);
     const double ab = EA ? a.thr[i] : WB_INF;
-    const double d = strip_pair<M, W, EA>(a.g, mm, a.x + i * a.Tx, a.y + j * a.Ty, bnd, 32, a.NS, ab);
+    const double d = strip_pair<M, W, EA, NR>(a.g, mm, a.x + i * a.Tx, a.y + j * a.Ty, bnd, 32, a.NS, ab);
     if (valid) {
       if (a.mode == PM_PAIRED) a.out[i] = d;
       else {
