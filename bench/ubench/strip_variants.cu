@@ -111,15 +111,14 @@ int main(int argc, char** argv) {
   int reps = argc > 5 ? atoi(argv[5]) : 2;
   int dev = 0, sms = 0; CK(cudaGetDevice(&dev)); CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   printf("SMs=%d  problem %d x %d, T=%d, r=%.3f\n", sms, nx, ny, T, rr);
-  for (int w : {1, 2, 4, 8}) {
+  if (argc <= 6) for (int w : {2, 4, 8}) {
     run_issue<0>("DADD", 8, sms, w);
     run_issue<1>("DADD+LOP(alu) 1:1", 16, sms, w);
     run_issue<2>("DADD+IMAD(fma) 1:1", 16, sms, w);
     run_issue<3>("DADD+LOP+FFMA 1:1:1", 24, sms, w);
     run_issue<6>("DADD+2LOP 1:2", 24, sms, w);
   }
-  run_issue<4>("LOP only", 8, sms, 8);
-  run_issue<5>("LOP+FFMA 1:1", 16, sms, 8);
+  if (argc <= 6) { run_issue<4>("LOP only", 8, sms, 8); run_issue<5>("LOP+FFMA 1:1", 16, sms, 8); }
 
   std::vector<double> hx((size_t)nx * T), hy((size_t)ny * T);
   unsigned s = 12345;
@@ -134,11 +133,12 @@ int main(int argc, char** argv) {
   int R = (int)compute_r(T, rr);
   DtwPolicy<false, false> m; m.w = nullptr; m.p = 0;
 #define V(W, NR, NW, MB) run_variant<DtwPolicy<false, false>, W, NR, NW, MB>(m, dx, dy, nx, ny, T, R, dout, counter, sms, reps);
-  V(8, 1, 8, 1) V(8, 2, 8, 1) V(8, 3, 8, 1) V(8, 4, 8, 1)
-  V(8, 2, 4, 1) V(8, 4, 4, 1) V(8, 2, 6, 1) V(8, 4, 6, 1)
-  V(4, 2, 8, 1) V(4, 4, 8, 1)
-  V(12, 2, 8, 1) V(12, 3, 8, 1) V(12, 4, 8, 1)
-  V(16, 1, 8, 1) V(16, 2, 8, 1) V(16, 3, 8, 1) V(16, 4, 8, 1)
+  int only_strip = argc > 6 ? atoi(argv[6]) : 0;
+  (void)only_strip;
+  V(8, 2, 8, 1) V(8, 4, 8, 1) V(8, 2, 8, 2) V(8, 4, 8, 2) V(8, 3, 8, 2)
+  V(4, 2, 8, 2) V(4, 4, 8, 2)
+  V(12, 4, 8, 1) V(16, 4, 8, 1) V(16, 2, 8, 1) V(16, 6, 8, 1) V(16, 8, 8, 1)
+  V(16, 4, 4, 1) V(16, 4, 6, 1)
   printf("done\n");
   return 0;
 }

@@ -72,6 +72,7 @@ extern "C" int hostsim_pair(int engine, int W, int metric, const wb_params* p, c
         case 3: r = StripRunner<3>::run(g, m, x, y, NS, bs, min_dist_raw, &ok); break;
         case 4: r = StripRunner<4>::run(g, m, x, y, NS, bs, min_dist_raw, &ok); break;
         case 8: r = StripRunner<8>::run(g, m, x, y, NS, bs, min_dist_raw, &ok); break;
+        case 12: r = StripRunner<12>::run(g, m, x, y, NS, bs, min_dist_raw, &ok); break;
         case 16: r = StripRunner<16>::run(g, m, x, y, NS, bs, min_dist_raw, &ok); break;
         default: ok = 0;
       }

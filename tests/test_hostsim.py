@@ -35,7 +35,7 @@ def test_engines_match_oracle(oracle, metric):
         x = np.cumsum(rng.standard_normal(Tx)); y = np.cumsum(rng.standard_normal(Ty))
         ref = oracle.pairwise(metric, x, y.reshape(1, -1), r=r)[0, 0]
         p = _params(oracle, metric, r=r)
-        for engine, W in [(1, 0), (2, 2), (2, 4), (2, 8), (2, 16)]:
+        for engine, W in [(1, 0), (2, 2), (2, 4), (2, 8), (2, 12), (2, 16)]:
             rc, v, _ = sim.pair(engine, W, mid, p, x, y, bs=int(rng.integers(1, 3)))
             if rc == 1:
                 continue  # geometry routed to the row-scan engine

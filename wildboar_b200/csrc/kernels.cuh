@@ -172,7 +172,10 @@ __global__ void __launch_bounds__(256) k_fp64_peak(int mix, int iters, double se
   if (mix == 0) {
 #pragma unroll 4
     for (int it = 0; it < iters; ++it) {
-      a0 += inc; a1 += inc; a2 += inc; a3 += inc; a4 += inc; a5 += inc; a6 += inc; a7 += inc;
+      // volatile so that the clock reads bracket the arithmetic
+      asm volatile("add.f64 %0, %0, %8; add.f64 %1, %1, %8; add.f64 %2, %2, %8; add.f64 %3, %3, %8;"
+                   "add.f64 %4, %4, %8; add.f64 %5, %5, %8; add.f64 %6, %6, %8; add.f64 %7, %7, %8;"
+                   : "+d"(a0), "+d"(a1), "+d"(a2), "+d"(a3), "+d"(a4), "+d"(a5), "+d"(a6), "+d"(a7) : "d"(inc));
     }
   } else {
     double y0 = seed * 0.5, y1 = seed * 0.25, y2 = seed * 0.125, y3 = seed * 0.0625;

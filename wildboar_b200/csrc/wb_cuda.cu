@@ -79,11 +79,18 @@ static int64_t cells_per_pair(int Tx, int Ty, int R) {
   return c;
 }
 
-constexpr int kStripW = 8;
+// Strip-kernel configurations (measured on B200, profiles/r01_variants.md):
+//   BIG   : W = 16 columns per strip, 4-row in-thread wavefront, <= 255 regs, one CTA of up to
+//           8 warps per SM (shared memory for the boundary rings is the occupancy limiter).
+//           Used when the band is tall enough for regular triangles (H >= 2W).
+//   SMALL : W = 8 (W = 4 for very narrow bands), 2-row wavefront, <= 128 regs, two CTAs of
+//           8 warps per SM.
+template <class M> struct BigW { static constexpr int value = 16; };
+template <> struct BigW<DtwPolicy<false, true>> { static constexpr int value = 12; };  // adtw: registers
 
-template <class M, int NT, int MINB, bool EA>
+template <class M, int W, int MINB, bool EA, int NR>
 static int launch_strip_cfg(const KArgs& a, const M& m, int nwarps, size_t smem, int sms, cudaStream_t st) {
-  auto kern = k_strip<M, kStripW, NT, MINB, EA>;
+  auto kern = k_strip<M, W, 256, MINB, EA, NR>;
   WB_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   WB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nwarps * 32, smem));
@@ -94,6 +101,24 @@ static int launch_strip_cfg(const KArgs& a, const M& m, int nwarps, size_t smem,
   kern<<<(unsigned)grid, nwarps * 32, smem, st>>>(a, m);
   WB_CK(cudaGetLastError());
   return 0;
+}
+
+template <class M, bool EA>
+static int launch_strip(const KArgs& a, const M& m, size_t smem_cap, int sms, cudaStream_t st, int* w_used) {
+  const size_t per_warp = (size_t)a.NS * 32 * sizeof(double);
+  constexpr int WB = BigW<M>::value;
+  if (a.g.H >= 2 * WB) {
+    const int nw = (int)std::max<size_t>(1, std::min<size_t>(8, smem_cap / per_warp));
+    *w_used = WB;
+    return launch_strip_cfg<M, WB, 1, EA, 4>(a, m, nw, nw * per_warp, sms, st);
+  }
+  const int nw = (int)std::max<size_t>(1, std::min<size_t>(8, smem_cap / per_warp));
+  if (a.g.H >= 16 || a.g.H < 8) {
+    *w_used = 8;
+    return launch_strip_cfg<M, 8, 2, EA, 2>(a, m, nw, nw * per_warp, sms, st);
+  }
+  *w_used = 4;
+  return launch_strip_cfg<M, 4, 2, EA, 2>(a, m, nw, nw * per_warp, sms, st);
 }
 
 // What one DP launch needs to know.
@@ -200,23 +225,17 @@ static int launch_dp(Workspace& ws, const DeviceInfo& di, const DpCall& c, long 
   int rc = 0;
   bool known = with_policy(c.metric, c.p, c.tab, [&](auto m) {
     using M = decltype(m);
-    bool strip_ok = strip_supported<M>(a.g, kStripW) && per_warp <= smem_cap && !c.need_rowmin &&
+    bool strip_ok = strip_supported<M>(a.g, 4) && per_warp <= smem_cap && !c.need_rowmin &&
                     !(out_m != nullptr) && c.p.engine != 1;
     if (thr && !M::kColumnMinBound) strip_ok = false;  // exact abandoning needs row minima
     if (c.p.engine == 2 && !strip_ok) { set_err("strip engine forced but not applicable"); rc = 1; return; }
     if (strip_ok) {
       engine = 2;
-      int nw = (int)std::min<size_t>(8, smem_cap / per_warp);
-      const bool two = 2 * 8 * per_warp <= smem_cap;
+      int w_used = 0;
       if constexpr (M::kColumnMinBound) {
-        if (thr) {
-          rc = two ? launch_strip_cfg<M, 256, 2, true>(a, m, 8, 8 * per_warp, di.sms, st)
-                   : launch_strip_cfg<M, 256, 1, true>(a, m, nw, nw * per_warp, di.sms, st);
-          return;
-        }
+        if (thr) { rc = launch_strip<M, true>(a, m, smem_cap, di.sms, st, &w_used); return; }
       }
-      rc = two ? launch_strip_cfg<M, 256, 2, false>(a, m, 8, 8 * per_warp, di.sms, st)
-               : launch_strip_cfg<M, 256, 1, false>(a, m, nw, nw * per_warp, di.sms, st);
+      rc = launch_strip<M, false>(a, m, smem_cap, di.sms, st, &w_used);
     } else {
       engine = 1;
       constexpr int NT = 128;
@@ -574,7 +593,7 @@ int wb_cuda_pairwise_dev(int metric, const wb_params* params, const double* d_x,
 int wb_cuda_fp64_peak(int mix, double* inst_per_s, double* sm_mhz_est) {
   DeviceInfo di;
   if (device_info(&di)) return 1;
-  const int threads = 256, per_sm = 8, iters = 1 << 15;
+  const int threads = 256, per_sm = 4, iters = 1 << 16;  // 32 warps per SM: one resident wave
   const long long grid = (long long)di.sms * per_sm;
   double* out = nullptr; unsigned long long* cyc = nullptr;
   WB_CK(cudaMalloc(&out, sizeof(double) * grid * threads));
