@@ -54,9 +54,23 @@ struct Workspace {
 };
 
 struct DeviceInfo { int sms; int max_smem_optin; int cc_major; int cc_minor; };
+// Keep stream-ordered allocations cached in the device's default pool between calls (the
+// default release threshold of 0 hands every buffer back to the OS at each synchronisation).
+static void retain_pool_memory(int dev) {
+  static std::atomic<unsigned long long> done{0};
+  if (dev < 0 || dev >= 64 || (done.load() >> dev) & 1ULL) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long thr = ~0ULL;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done.fetch_or(1ULL << dev);
+}
+
 static int device_info(DeviceInfo* di) {
   int dev = 0;
   WB_CK(cudaGetDevice(&dev));
+  retain_pool_memory(dev);
   WB_CK(cudaDeviceGetAttribute(&di->sms, cudaDevAttrMultiProcessorCount, dev));
   WB_CK(cudaDeviceGetAttribute(&di->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   WB_CK(cudaDeviceGetAttribute(&di->cc_major, cudaDevAttrComputeCapabilityMajor, dev));
@@ -375,7 +389,7 @@ static int device_worker(const HostJob& J, int dev, int64_t lo, int64_t hi, wb_s
       }
       // pairwise / self: chunk the row block so result slabs stream back while the next chunk computes
       const int64_t ncols = c.ny;
-      const size_t slab_budget = (size_t)256 << 20;
+      const size_t slab_budget = (size_t)48 << 20;  // small slabs: the un-overlapped tail copy stays short
       int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(rows, (int64_t)(slab_budget / (sizeof(double) * std::max<int64_t>(ncols, 1)))));
       const int64_t nchunks = (rows + chunk - 1) / chunk;
       double* dbuf[2] = {nullptr, nullptr};
