@@ -66,21 +66,22 @@ static void run_issue(const char* name, int ninst, int sms, int warps_per_smsp) 
 // ---------------- strip kernel variants ----------------
 struct Result { double ms; double gcups; double checksum; };
 
-template <class M, int W, int NR, int NWARPS, int MINB>
+template <class M, int W, int NR, int NWARPS, int MINB, bool GRING = false>
 static Result run_variant(const M& m, const double* dx, const double* dy, long long nx, long long ny, int T, int R,
                           double* dout, unsigned long long* counter, int sms, int reps) {
   KArgs a; memset(&a, 0, sizeof a);
   a.x = dx; a.y = dy; a.nx = nx; a.ny = ny; a.Tx = T; a.Ty = T; a.g = make_geom(T, T, R);
   a.NS = strip_ring_slots(a.g); a.out = dout; a.ld = ny; a.counter = counter; a.mode = PM_PAIRWISE;
   a.nyb = (ny + 31) / 32; a.ntasks = nx * a.nyb;
-  size_t smem = (size_t)NWARPS * a.NS * 32 * sizeof(double);
-  auto kern = k_strip<M, W, NWARPS * 32, MINB, false, NR>;
+  size_t smem = GRING ? 0 : (size_t)NWARPS * a.NS * 32 * sizeof(double);
+  auto kern = k_strip<M, W, NWARPS * 32, MINB, false, NR, GRING>;
   Result r{0, 0, 0};
-  if (smem > 232448) { r.ms = -1; return r; }
+  if (smem > 232448) { printf("strip W=%2d NR=%d warps/CTA=%d: does not fit in shared memory\n", W, NR, NWARPS); r.ms = -1; return r; }
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NWARPS * 32, smem));
   if (per_sm < 1) { r.ms = -2; return r; }
+  if (GRING) { if (per_sm > MINB) per_sm = MINB; CK(cudaMalloc(&a.gring, (size_t)sms * per_sm * NWARPS * a.NS * 32 * sizeof(double))); }
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   float best = 1e30f;
   for (int rep = 0; rep < reps + 1; ++rep) {
@@ -98,8 +99,9 @@ static Result run_variant(const M& m, const double* dx, const double* dy, long l
   CK(cudaMemcpy(h.data(), dout + (nx - 1) * ny, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
   for (double v : h) r.checksum += v;
   cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
-  printf("strip W=%2d NR=%d warps/CTA=%d CTAs/SM=%d regs=%3d smem=%6zu  %8.2f ms  %8.1f GCUPS  (%.1f%% of 3689 nominal)  chk=%.6f\n",
-         W, NR, NWARPS, per_sm, fa.numRegs, smem, r.ms, r.gcups, 100.0 * r.gcups * 5 / 18448.0, r.checksum);
+  if (GRING) cudaFree(a.gring);
+  printf("%s W=%2d NR=%d warps/CTA=%d CTAs/SM=%d regs=%3d smem=%6zu  %8.2f ms  %8.1f GCUPS  (%.1f%% of 3689 nominal)  chk=%.6f\n",
+         GRING ? "gring" : "strip", W, NR, NWARPS, per_sm, fa.numRegs, smem, r.ms, r.gcups, 100.0 * r.gcups * 5 / 18448.0, r.checksum);
   fflush(stdout);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return r;
@@ -135,10 +137,9 @@ int main(int argc, char** argv) {
 #define V(W, NR, NW, MB) run_variant<DtwPolicy<false, false>, W, NR, NW, MB>(m, dx, dy, nx, ny, T, R, dout, counter, sms, reps);
   int only_strip = argc > 6 ? atoi(argv[6]) : 0;
   (void)only_strip;
-  V(8, 2, 8, 1) V(8, 4, 8, 1) V(8, 2, 8, 2) V(8, 4, 8, 2) V(8, 3, 8, 2)
-  V(4, 2, 8, 2) V(4, 4, 8, 2)
-  V(12, 4, 8, 1) V(16, 4, 8, 1) V(16, 2, 8, 1) V(16, 6, 8, 1) V(16, 8, 8, 1)
-  V(16, 4, 4, 1) V(16, 4, 6, 1)
+#define G(W, NR, NW, MB) run_variant<DtwPolicy<false, false>, W, NR, NW, MB, true>(m, dx, dy, nx, ny, T, R, dout, counter, sms, reps);
+  V(16, 4, 8, 1) V(16, 4, 6, 1) V(16, 4, 2, 1) V(8, 2, 8, 2)
+  G(16, 4, 8, 1) G(16, 4, 9, 1) G(12, 4, 8, 1) G(12, 4, 10, 1) G(12, 4, 12, 1) G(8, 4, 8, 1) G(8, 4, 8, 2) G(8, 2, 8, 2) G(8, 4, 12, 1)
   printf("done\n");
   return 0;
 }

@@ -112,6 +112,10 @@ WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
     double stale = m.lsent();
     double colmin = WB_INF;
     int i = i_lo;
+    double pf[NR];
+    bool have_pf = false;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) pf[r] = 0.0;
 
     auto generic_row = [&]() {
       const double xnext = x[imin2(i + 1, Tx - 1)];  // prefetch next row's sample
@@ -180,8 +184,19 @@ WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
         typename M::Row rws[NR];
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-          lft[r] = bnd[slr[r] * bs];
+          lft[r] = have_pf ? pf[r] : bnd[slr[r] * bs];
           rws[r] = m.row(i + r, xr[r], r == 0 ? xim : xr[r - 1]);
+        }
+        // prefetch the boundary values of the NEXT NR rows (hides the ring's load latency when
+        // it lives in global memory; any slot is valid memory, unused values are discarded)
+        {
+          int sn = (slr[NR - 1] + 1 == NS) ? 0 : slr[NR - 1] + 1;
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            pf[r] = bnd[sn * bs];
+            sn = (sn + 1 == NS) ? 0 : sn + 1;
+          }
+          have_pf = true;
         }
         dg[0] = Dg;
 #pragma unroll
@@ -211,6 +226,7 @@ WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
         xi = xnext;
         i += NR;
       }
+      have_pf = false;
       if (i > i_hi) break;
       if (reg_top && i == i_lo) {
 #pragma unroll

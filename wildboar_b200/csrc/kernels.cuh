@@ -31,6 +31,7 @@ struct KArgs {
   int mode;
   long long row0;     // PM_SELF: global index of local x row 0 (row-sharded self join)
   int mirror;         // PM_SELF: also write out[j][i] (single-device full matrix)
+  double* gring;      // strip engine, GRING variant: boundary rings in global memory, [warp][slot][lane]
   double* scratch;    // row-scan engine: 2 rows per thread, interleaved
   long long sstride;  // = total threads
   int srows;          // elements per scratch row
@@ -66,12 +67,15 @@ __device__ __forceinline__ long long next_task(unsigned long long* counter, int 
 }
 
 // ---- strip engine: thread per pair, boundary ring in shared memory [warp][slot][lane] ----
-template <class M, int W, int NT, int MINB, bool EA, int NR = 2>
+template <class M, int W, int NT, int MINB, bool EA, int NR = 2, bool GRING = false>
 __global__ void __launch_bounds__(NT, MINB) k_strip(KArgs a, M m) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  double* bnd = smem + (size_t)warp * a.NS * 32 + lane;
+  // boundary ring of this warp's 32 pairs: shared memory, or (tall bands that would leave too
+  // few warps resident) L2-resident global memory
+  double* bnd = GRING ? a.gring + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * a.NS * 32 + lane
+                      : smem + (size_t)warp * a.NS * 32 + lane;
   for (;;) {
     const long long t = next_task(a.counter, lane);
     if (t >= a.ntasks) break;

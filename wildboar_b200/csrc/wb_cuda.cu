@@ -93,46 +93,62 @@ static int64_t cells_per_pair(int Tx, int Ty, int R) {
   return c;
 }
 
-// Strip-kernel configurations (measured on B200, profiles/r01_variants.md):
-//   BIG   : W = 16 columns per strip, 4-row in-thread wavefront, <= 255 regs, one CTA of up to
-//           8 warps per SM (shared memory for the boundary rings is the occupancy limiter).
-//           Used when the band is tall enough for regular triangles (H >= 2W).
-//   SMALL : W = 8 (W = 4 for very narrow bands), 2-row wavefront, <= 128 regs, two CTAs of
-//           8 warps per SM.
-template <class M> struct BigW { static constexpr int value = 16; };
-template <> struct BigW<DtwPolicy<false, true>> { static constexpr int value = 12; };  // adtw: registers
+// Strip-kernel configurations (measured on B200: profiles/r01_variants.md, r01_variants3.log).
+//   NARROW (H < 32)        : W = 8 (W = 4 for 8 <= H < 16), NR = 2, rings in SHARED memory, two CTAs
+//                            of 8 warps per SM (<= 128 regs).
+//   L2 (H >= 32, NS <= 220): rings in GLOBAL memory (L2 resident: 148 SMs x warps x NS x 256 B
+//                            stays under the 126 MB L2), W = WL, NR = 4, NWL warps per SM.
+//   TALL (NS > 220)        : rings in global memory, wider strips (W = WT: half the ring traffic
+//                            per cell), 8 warps per SM so the rings still mostly fit in L2.
+// Shared-memory rings cap cfg3 at 8 warps per SM (816 B per pair); the global ring lifts that
+// to 12 and is what makes T = 4096 bands (3.3 KB per pair) run at all.
+template <class M> struct StripCfg { static constexpr int WL = 8, NWL = 12, WT = 16; };
+template <> struct StripCfg<DtwPolicy<false, false>> { static constexpr int WL = 12, NWL = 12, WT = 16; };
+template <> struct StripCfg<LcssPolicy<false>> { static constexpr int WL = 12, NWL = 12, WT = 16; };
+template <> struct StripCfg<DtwPolicy<false, true>> { static constexpr int WL = 8, NWL = 12, WT = 12; };
+template <> struct StripCfg<TwePolicy> { static constexpr int WL = 8, NWL = 8, WT = 12; };
 
-template <class M, int W, int MINB, bool EA, int NR>
-static int launch_strip_cfg(const KArgs& a, const M& m, int nwarps, size_t smem, int sms, cudaStream_t st) {
-  auto kern = k_strip<M, W, 256, MINB, EA, NR>;
-  WB_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <class M, int W, int NT, int MINB, bool EA, int NR, bool GRING>
+static int launch_strip_cfg(Workspace& ws, KArgs a, const M& m, int nwarps, int sms, int* w_used) {
+  cudaStream_t st = ws.stream;
+  auto kern = k_strip<M, W, NT, MINB, EA, NR, GRING>;
+  const size_t per_warp = (size_t)a.NS * 32 * sizeof(double);
+  size_t smem = GRING ? 0 : (size_t)nwarps * per_warp;
+  if (!GRING) WB_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   WB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nwarps * 32, smem));
   if (per_sm < 1) { set_err("strip kernel does not fit on an SM"); return 1; }
-  long long warps_total = (long long)sms * per_sm * nwarps;
+  per_sm = std::min(per_sm, MINB);
   long long grid = (long long)sms * per_sm;
-  if (a.ntasks < warps_total) grid = std::max<long long>(1, (a.ntasks + nwarps - 1) / nwarps);
+  if (a.ntasks < grid * nwarps) grid = std::max<long long>(1, (a.ntasks + nwarps - 1) / nwarps);
+  if (GRING) {
+    double* ring = nullptr;
+    if (ws.alloc(&ring, (size_t)grid * nwarps * a.NS * 32)) return 1;
+    a.gring = ring;
+  }
+  *w_used = W;
   kern<<<(unsigned)grid, nwarps * 32, smem, st>>>(a, m);
   WB_CK(cudaGetLastError());
   return 0;
 }
 
 template <class M, bool EA>
-static int launch_strip(const KArgs& a, const M& m, size_t smem_cap, int sms, cudaStream_t st, int* w_used) {
+static int launch_strip(Workspace& ws, const KArgs& a, const M& m, size_t smem_cap, int sms, int* w_used) {
   const size_t per_warp = (size_t)a.NS * 32 * sizeof(double);
-  constexpr int WB = BigW<M>::value;
-  if (a.g.H >= 2 * WB) {
-    const int nw = (int)std::max<size_t>(1, std::min<size_t>(8, smem_cap / per_warp));
-    *w_used = WB;
-    return launch_strip_cfg<M, WB, 1, EA, 4>(a, m, nw, nw * per_warp, sms, st);
+  using C = StripCfg<M>;
+  if (a.g.H >= 32) {
+    // keep the global rings of one launch below ~8 GB whatever the series length
+    const size_t ring_budget = (size_t)8 << 30;
+    int cap = (int)std::max<size_t>(1, ring_budget / (per_warp * (size_t)sms));
+    if (a.NS <= 220 && a.g.H >= 2 * C::WL)
+      return launch_strip_cfg<M, C::WL, C::NWL * 32, 1, EA, 4, true>(ws, a, m, std::min(C::NWL, cap), sms, w_used);
+    if (a.g.H >= 2 * C::WT)
+      return launch_strip_cfg<M, C::WT, 256, 1, EA, 4, true>(ws, a, m, std::min(8, cap), sms, w_used);
+    return launch_strip_cfg<M, 8, 256, 2, EA, 2, true>(ws, a, m, std::min(8, cap), sms, w_used);
   }
   const int nw = (int)std::max<size_t>(1, std::min<size_t>(8, smem_cap / per_warp));
-  if (a.g.H >= 16 || a.g.H < 8) {
-    *w_used = 8;
-    return launch_strip_cfg<M, 8, 2, EA, 2>(a, m, nw, nw * per_warp, sms, st);
-  }
-  *w_used = 4;
-  return launch_strip_cfg<M, 4, 2, EA, 2>(a, m, nw, nw * per_warp, sms, st);
+  if (a.g.H >= 16 || a.g.H < 8) return launch_strip_cfg<M, 8, 256, 2, EA, 2, false>(ws, a, m, nw, sms, w_used);
+  return launch_strip_cfg<M, 4, 256, 2, EA, 2, false>(ws, a, m, nw, sms, w_used);
 }
 
 // What one DP launch needs to know.
@@ -239,7 +255,7 @@ static int launch_dp(Workspace& ws, const DeviceInfo& di, const DpCall& c, long 
   int rc = 0;
   bool known = with_policy(c.metric, c.p, c.tab, [&](auto m) {
     using M = decltype(m);
-    bool strip_ok = strip_supported<M>(a.g, 4) && per_warp <= smem_cap && !c.need_rowmin &&
+    bool strip_ok = strip_supported<M>(a.g, 4) && !c.need_rowmin &&
                     !(out_m != nullptr) && c.p.engine != 1;
     if (thr && !M::kColumnMinBound) strip_ok = false;  // exact abandoning needs row minima
     if (c.p.engine == 2 && !strip_ok) { set_err("strip engine forced but not applicable"); rc = 1; return; }
@@ -247,9 +263,9 @@ static int launch_dp(Workspace& ws, const DeviceInfo& di, const DpCall& c, long 
       engine = 2;
       int w_used = 0;
       if constexpr (M::kColumnMinBound) {
-        if (thr) { rc = launch_strip<M, true>(a, m, smem_cap, di.sms, st, &w_used); return; }
+        if (thr) { rc = launch_strip<M, true>(ws, a, m, smem_cap, di.sms, &w_used); return; }
       }
-      rc = launch_strip<M, false>(a, m, smem_cap, di.sms, st, &w_used);
+      rc = launch_strip<M, false>(ws, a, m, smem_cap, di.sms, &w_used);
     } else {
       engine = 1;
       constexpr int NT = 128;
