@@ -61,6 +61,8 @@ typedef struct wb_stats {
   int64_t pairs;        /* pairs evaluated                                               */
   int32_t launches;     /* kernels launched by this call                                 */
   int32_t engine;       /* engine used for the DP (1 row-scan, 2 strip)                  */
+  int64_t lb_kim_pruned;   /* argmin cascade: pairs pruned by LB_Kim                     */
+  int64_t lb_keogh_pruned; /* argmin cascade: pairs pruned by LB_Keogh (either direction)  */
 } wb_stats;
 
 int wb_cuda_device_count(void);

@@ -164,6 +164,30 @@ def test_argmin_self_join_and_lower_bound(W, oracle):
         _eq(idx, oi, "lb idx"); _eq(dist, od, "lb dist")
 
 
+@pytest.mark.parametrize("k", [1, 5])
+def test_argmin_device_cascade_is_exact(W, oracle, k, monkeypatch):
+    """Many small chunks force the LB_Kim -> LB_Keogh -> list-mode DP cascade; results must not move."""
+    monkeypatch.setenv("WILDBOAR_CUDA_ARGMIN_CHUNK", "64")
+    q, refs = random_walks(70, 128, 41), random_walks(1500, 128, 42)
+    refs[700] = q[3]; refs[20] = q[3]; refs[1499] = q[69]  # exact matches early, late and duplicated
+    oi, od = oracle.argmin("dtw", q, refs, k=k, r=0.1, n_jobs=0)
+    for lb in (True, False):
+        idx, dist = W.argmin_distance(q, refs, k=k, metric="dtw", metric_params={"r": 0.1}, return_distance=True,
+                                      device_lower_bound=lb)
+        _eq(idx, oi, f"cascade={lb} idx"); _eq(dist, od, f"cascade={lb} dist")
+        st = W.last_stats()
+        if lb:
+            assert st["lb_kim_pruned"] + st["lb_keogh_pruned"] > 0, st
+            assert st["pairs"] < 70 * 1500
+    # smooth series: LB_Keogh is tight, most pairs are pruned
+    t = np.linspace(0, 6.28, 128)
+    qs = np.sin(t)[None, :] * np.linspace(1, 2, 40)[:, None]
+    rs = np.sin(t + 0.05)[None, :] * np.linspace(0.5, 3, 900)[:, None]
+    idx, dist = W.argmin_distance(qs, rs, k=k, metric="dtw", metric_params={"r": 0.05}, return_distance=True)
+    oi, od = oracle.argmin("dtw", qs, rs, k=k, r=0.05, n_jobs=0)
+    _eq(idx, oi, "smooth idx"); _eq(dist, od, "smooth dist")
+
+
 def test_argmin_cfg4_shape_subset(W, oracle):
     """BASELINE configs[3] shape: T=256, r=0.05, k=1 -- 48 queries x 3000 references."""
     q, refs = random_walks(20000, 256, 3)[:48], random_walks(200000, 256, 4)[:3000]

@@ -17,6 +17,7 @@
 //     M > T(t) with the exact t.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include "dispatch.cuh"
 #include "kernels.cuh"
 
@@ -136,6 +137,162 @@ __global__ void k_fill(double* p, long long n, double v) {
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) p[e] = v;
 }
 
+// ------------------------------------------------------------------------------------------
+// On-device lower-bound cascade for dtw: LB_Kim (first/last point) ->
+// LB_Keogh(query, envelope(ref)) -> LB_Keogh(ref, envelope(query)) -> survivors go to the
+// early-abandoning DP.  Envelope half-width = R-1 (the band is |i-j| <= R-1), the tightest
+// valid one.  Pruning compares against the chunk-start threshold with a 1e-9 relative safety
+// margin, so rounding in the O(T) sums can never drop a pair the exact scan would accept; it
+// therefore NEVER changes the result (the replay only ever sees "pruned" = +INF = rejected).
+// ------------------------------------------------------------------------------------------
+// lower/upper[k] = min/max t[k-w .. k+w] (clipped); rows = series (queries)
+__global__ void k_envelope_rows(const double* __restrict__ x, long long n, int T, int w,
+                                double* __restrict__ lo, double* __restrict__ hi) {
+  const long long total = n * (long long)T;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long s = e / T;
+    const int k = (int)(e - s * T);
+    const double* p = x + s * T;
+    const int a = max(0, k - w), b = min(T - 1, k + w);
+    double l = p[a], h = p[a];
+    for (int q = a + 1; q <= b; ++q) { const double v = p[q]; l = fmin(l, v); h = fmax(h, v); }
+    lo[e] = l; hi[e] = h;
+  }
+}
+// same, but written TRANSPOSED ([t][series]) together with the transposed series, so that a
+// warp whose lanes are 32 consecutive references reads them coalesced
+__global__ void k_envelope_T(const double* __restrict__ y, long long n, int T, int w, double* __restrict__ yT,
+                             double* __restrict__ loT, double* __restrict__ hiT) {
+  const long long total = n * (long long)T;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(e / n);
+    const long long s = e - (long long)k * n;
+    const double* p = y + s * T;
+    const int a = max(0, k - w), b = min(T - 1, k + w);
+    double l = p[a], h = p[a];
+    for (int q = a + 1; q <= b; ++q) { const double v = p[q]; l = fmin(l, v); h = fmax(h, v); }
+    yT[e] = p[k]; loT[e] = l; hiT[e] = h;
+  }
+}
+
+struct LbArgs {
+  const double* x; const double* lox; const double* hix;   // (nq, T) row-major
+  const double* yT; const double* loyT; const double* hiyT;  // (T, ny) transposed
+  long long nq, ny, c0, nc; int T;
+  const double* tau;  // per query, distance domain
+  double* d; long long ld;  // chunk matrix: +INF = pruned, -1 = survivor (to be filled by the DP)
+  unsigned long long* n_kim; unsigned long long* n_keogh;  // pruning statistics
+};
+
+__global__ void __launch_bounds__(256) k_lb_prune(LbArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long nyb = (a.nc + 31) / 32;
+  const long long ntask = a.nq * nyb;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int T = a.T;
+  for (long long t = wid; t < ntask; t += nw) {
+    const long long i = t / nyb;
+    const long long jl = (t - i * nyb) * 32 + lane;
+    const bool valid = jl < a.nc;
+    const long long j = a.c0 + (valid ? jl : a.nc - 1);
+    const double tau = a.tau[i];
+    const double lim = isinf(tau) ? WB_INF : tau * tau * (1.0 + 1e-9);  // prune only if LB^2 > lim
+    const double* q = a.x + i * T;
+    bool pruned = false;
+    if (!isinf(lim)) {
+      // LB_Kim: every warping path contains (0,0) and (T-1,T-1)
+      const double d0 = q[0] - a.yT[j];
+      const double d1 = q[T - 1] - a.yT[(long long)(T - 1) * a.ny + j];
+      double lb = d0 * d0 + (T > 1 ? d1 * d1 : 0.0);
+      pruned = lb > lim;
+      if (pruned && valid) atomicAdd(a.n_kim, 1ULL);
+      if (!__all_sync(0xffffffffu, pruned)) {
+        // LB_Keogh, query against the reference's envelope
+        double s = 0.0;
+        const double* lo = a.loyT + j; const double* hi = a.hiyT + j;
+        for (int k = 0; k < T; ++k) {
+          const double v = q[k];
+          const double l = lo[(long long)k * a.ny], h = hi[(long long)k * a.ny];
+          const double e = v > h ? v - h : (v < l ? l - v : 0.0);
+          s += e * e;
+          if ((k & 31) == 31 && __all_sync(0xffffffffu, pruned || s > lim)) break;
+        }
+        bool p2 = pruned || s > lim;
+        if (!__all_sync(0xffffffffu, p2)) {
+          // LB_Keogh, reference against the query's envelope
+          double s2 = 0.0;
+          const double* ql = a.lox + i * T; const double* qh = a.hix + i * T;
+          const double* yy = a.yT + j;
+          for (int k = 0; k < T; ++k) {
+            const double v = yy[(long long)k * a.ny];
+            const double l = ql[k], h = qh[k];
+            const double e = v > h ? v - h : (v < l ? l - v : 0.0);
+            s2 += e * e;
+            if ((k & 31) == 31 && __all_sync(0xffffffffu, p2 || s2 > lim)) break;
+          }
+          p2 = p2 || s2 > lim;
+        }
+        if (p2 && !pruned && valid) atomicAdd(a.n_keogh, 1ULL);
+        pruned = p2;
+      }
+    }
+    if (valid) a.d[i * a.ld + jl] = pruned ? WB_INF : -1.0;
+  }
+}
+
+// survivors per query row -> exclusive scan -> (i, j) list sorted by (i, j)
+__global__ void __launch_bounds__(128) k_row_count(const double* __restrict__ d, long long nq, long long nc, long long ld,
+                                                   int* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long q = wid; q < nq; q += nw) {
+    int c = 0;
+    for (long long jj = 0; jj < nc; jj += 32) {
+      const long long j = jj + lane;
+      c += __popc(__ballot_sync(0xffffffffu, j < nc && d[q * ld + j] < 0.0));
+    }
+    if (lane == 0) counts[q] = c;
+  }
+}
+__global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ counts, long long nq, int* __restrict__ starts,
+                                                      int* __restrict__ total, unsigned long long* __restrict__ grand_total) {
+  __shared__ int part[1024];
+  const int tid = threadIdx.x;
+  const long long per = (nq + 1023) / 1024;
+  const long long lo = tid * per, hi = min(nq, lo + per);
+  int s = 0;
+  for (long long q = lo; q < hi; ++q) s += counts[q];
+  part[tid] = s;
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    for (int k = 0; k < 1024; ++k) { const int v = part[k]; part[k] = acc; acc += v; }
+    *total = acc;
+    atomicAdd(grand_total, (unsigned long long)acc);
+  }
+  __syncthreads();
+  int acc = part[tid];
+  for (long long q = lo; q < hi; ++q) { starts[q] = acc; acc += counts[q]; }
+}
+__global__ void __launch_bounds__(128) k_fill_list(const double* __restrict__ d, long long nq, long long nc, long long ld,
+                                                   const int* __restrict__ starts, int2* __restrict__ list) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long q = wid; q < nq; q += nw) {
+    int base = starts[q];
+    for (long long jj = 0; jj < nc; jj += 32) {
+      const long long j = jj + lane;
+      const bool sv = j < nc && d[q * ld + j] < 0.0;
+      const unsigned m = __ballot_sync(0xffffffffu, sv);
+      if (sv) list[base + __popc(m & ((1u << lane) - 1u))] = make_int2((int)q, (int)j);
+      base += __popc(m);
+    }
+  }
+}
+
 // LaunchFn(r0, nrows, c0, ncols, out, ld, out_m, thr, stats) -> int
 template <class WS, class DI, class Call, class LaunchFn>
 int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stats, LaunchFn launch) {
@@ -154,11 +311,31 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
   long long* hidx = nullptr; int* hn = nullptr;
   long long C = (4LL << 20) / std::max<long long>(nq, 1);
   C = std::max<long long>(32, std::min<long long>(4096, (C / 32) * 32));
+  if (const char* e = getenv("WILDBOAR_CUDA_ARGMIN_CHUNK")) {  // tuning / test knob: columns per chunk
+    const long long v = atoll(e);
+    if (v >= 32) C = (v / 32) * 32;
+  }
   C = std::min<long long>(C, ((ny + 31) / 32) * 32);
   if (ws.alloc(&tau, (size_t)nq) || ws.alloc(&thr, (size_t)nq) || ws.alloc(&hval, (size_t)nq * k) ||
       ws.alloc(&hidx, (size_t)nq * k) || ws.alloc(&hn, (size_t)nq) || ws.alloc(&dbuf, (size_t)nq * C)) return 1;
   if (!dtwfam && ws.alloc(&mbuf, (size_t)nq * C)) return 1;
   if (io.lower_bound && ws.alloc(&lbuf, (size_t)nq * C)) return 1;
+  // ---- optional on-device lower-bound cascade (dtw, equal lengths) ----
+  const bool cascade = io.use_device_lb && c.metric == M_DTW && c.ptx == c.pty && c.ptx >= 2 && !c.degenerate &&
+                       nq * C < 2000000000LL;
+  double *lox = nullptr, *hix = nullptr, *yT = nullptr, *loyT = nullptr, *hiyT = nullptr;
+  int *counts = nullptr, *starts = nullptr, *list_len = nullptr; int2* list = nullptr;
+  unsigned long long* lbstat = nullptr;  // [0] kim-pruned, [1] keogh-pruned, [2] survivors
+  if (cascade) {
+    const int T = c.ptx, w = std::max(c.R - 1, 0);
+    if (ws.alloc(&lox, (size_t)nq * T) || ws.alloc(&hix, (size_t)nq * T) || ws.alloc(&yT, (size_t)ny * T) ||
+        ws.alloc(&loyT, (size_t)ny * T) || ws.alloc(&hiyT, (size_t)ny * T) || ws.alloc(&counts, (size_t)nq) ||
+        ws.alloc(&starts, (size_t)nq) || ws.alloc(&list_len, 1) || ws.alloc(&list, (size_t)nq * C) ||
+        ws.alloc(&lbstat, 3)) return 1;
+    if (cudaMemsetAsync(lbstat, 0, 3 * sizeof(unsigned long long), st) != cudaSuccess) return 1;
+    k_envelope_rows<<<1024, 256, 0, st>>>(c.px, nq, T, w, lox, hix);
+    k_envelope_T<<<2048, 256, 0, st>>>(c.py, ny, T, w, yT, loyT, hiyT);
+  }
   k_fill<<<256, 256, 0, st>>>(tau, nq, WB_INF);
   if (cudaMemsetAsync(hval, 0, sizeof(double) * nq * k, st) != cudaSuccess ||
       cudaMemsetAsync(hidx, 0, sizeof(long long) * nq * k, st) != cudaSuccess ||
@@ -174,6 +351,21 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
     if (c.degenerate) {
       // ddtw with T < 3: eadistance() returns False for every pair (EL:3297-3298)
       k_fill<<<256, 256, 0, st>>>(dbuf, nq * C, WB_INF);
+    } else if (cascade && c0 > 0) {
+      // chunk 0 has no threshold yet (tau = INF): nothing can be pruned, run it densely
+      LbArgs la;
+      la.x = c.px; la.lox = lox; la.hix = hix; la.yT = yT; la.loyT = loyT; la.hiyT = hiyT;
+      la.nq = nq; la.ny = ny; la.c0 = c0; la.nc = nc; la.T = c.ptx; la.tau = tau; la.d = dbuf; la.ld = C;
+      la.n_kim = lbstat; la.n_keogh = lbstat + 1;
+      k_lb_prune<<<148 * 8, 256, 0, st>>>(la);
+      k_row_count<<<148 * 4, 128, 0, st>>>(dbuf, nq, nc, C, counts);
+      k_scan_counts<<<1, 1024, 0, st>>>(counts, nq, starts, list_len, lbstat + 2);
+      k_fill_list<<<148 * 4, 128, 0, st>>>(dbuf, nq, nc, C, starts, list);
+      c.mode = PM_LIST; c.list = list; c.list_len = list_len;
+      rc = launch(0, nq, c0, nc, dbuf, C, nullptr, thr, nullptr);
+      c.mode = PM_PAIRWISE; c.list = nullptr; c.list_len = nullptr;
+      if (stats) stats->launches += 5;
+      if (rc) break;
     } else {
       rc = launch(0, nq, c0, nc, dbuf, C, mbuf, (kind == TK_NONE || kind == TK_LCSS) ? nullptr : thr, stats);
       if (rc) break;
@@ -196,6 +388,17 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
         cudaStreamSynchronize(st) != cudaSuccess) rc = 1;
     float f = 0;
     if (!rc && stats && cudaEventElapsedTime(&f, e0, e1) == cudaSuccess) stats->kernel_ms += f;
+    if (!rc && stats && cascade) {
+      unsigned long long h[3] = {0, 0, 0};
+      if (cudaMemcpy(h, lbstat, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess) {
+        // pairs / cells = what actually went through the DP (dense first chunk + survivors)
+        const long long cpp = stats->pairs > 0 ? stats->cells / stats->pairs : 0;
+        stats->pairs += (long long)h[2];
+        stats->cells += (long long)h[2] * cpp;
+        stats->lb_kim_pruned = (long long)h[0];
+        stats->lb_keogh_pruned = (long long)h[1];
+      }
+    }
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return rc;

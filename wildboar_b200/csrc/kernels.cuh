@@ -10,6 +10,7 @@ enum PairMode : int {
   PM_PAIRWISE = 0,  // out[i][j] = d(x_i, y_j)                       (CD:1144-1205)
   PM_SELF = 1,      // j > i only, also written to out[j][i]          (CD:1208-1267)
   PM_PAIRED = 2,    // out[i] = d(x_i, y_i)  (caller already swapped)  (CD:1597-1652)
+  PM_LIST = 3,      // out[i][j] for the (i, j) of a device-resident survivor list (argmin cascade)
 };
 
 struct KArgs {
@@ -31,6 +32,8 @@ struct KArgs {
   int mode;
   long long row0;     // PM_SELF: global index of local x row 0 (row-sharded self join)
   int mirror;         // PM_SELF: also write out[j][i] (single-device full matrix)
+  const int2* list;   // PM_LIST: pairs to evaluate, sorted by (i, j)
+  const int* list_len;  // PM_LIST: number of pairs (device resident: no host round trip)
   double* gring;      // strip engine, GRING variant: boundary rings in global memory, [warp][slot][lane]
   double* scratch;    // row-scan engine: 2 rows per thread, interleaved
   long long sstride;  // = total threads
@@ -38,8 +41,21 @@ struct KArgs {
 };
 
 // One warp task = 32 consecutive pairs.  Returns false when the whole task is empty.
+__device__ __forceinline__ long long task_count(const KArgs& a) {
+  return a.mode == PM_LIST ? ((long long)__ldg(a.list_len) + 31) / 32 : a.ntasks;
+}
+
 __device__ __forceinline__ bool decode_task(const KArgs& a, long long t, int lane, long long& i, long long& j,
                                             bool& valid) {
+  if (a.mode == PM_LIST) {
+    const long long n = __ldg(a.list_len);
+    long long e = t * 32 + lane;
+    valid = e < n;
+    if (!valid) e = n - 1;
+    const int2 p = a.list[e];
+    i = p.x; j = p.y;
+    return true;
+  }
   if (a.mode == PM_PAIRED) {
     i = t * 32 + lane;
     valid = i < a.nx;
@@ -76,9 +92,10 @@ __global__ void __launch_bounds__(NT, MINB) k_strip(KArgs a, M m) {
   // few warps resident) L2-resident global memory
   double* bnd = GRING ? a.gring + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * a.NS * 32 + lane
                       : smem + (size_t)warp * a.NS * 32 + lane;
+  const long long ntasks = task_count(a);
   for (;;) {
     const long long t = next_task(a.counter, lane);
-    if (t >= a.ntasks) break;
+    if (t >= ntasks) break;
     long long i, j;
     bool valid;
     if (!decode_task(a, t, lane, i, j, valid)) continue;
@@ -107,9 +124,10 @@ __global__ void __launch_bounds__(NT) k_rowscan(KArgs a, M m) {
   const long long gtid = (long long)blockIdx.x * NT + threadIdx.x;
   double* b0 = a.scratch + gtid;
   double* b1 = a.scratch + (long long)a.srows * a.sstride + gtid;
+  const long long ntasks = task_count(a);
   for (;;) {
     const long long t = next_task(a.counter, lane);
-    if (t >= a.ntasks) break;
+    if (t >= ntasks) break;
     long long i, j;
     bool valid;
     if (!decode_task(a, t, lane, i, j, valid)) continue;

@@ -24,6 +24,7 @@
 #pragma once
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define WB_HD __host__ __device__ __forceinline__
@@ -239,21 +240,36 @@ struct MsmPolicy {
   WB_HD double diag0(int i) const { return i == 0 ? 0.0 : WB_INF; }
   WB_HD void begin_pair(const PairCtx&) {}
 
-  struct Row { double xi; float xf, xmf; };
-  struct Col { double yj; float yf, ymf; };
-  WB_HD Row row(int, double xi, double xim) const { Row r; r.xi = xi; r.xf = (float)xi; r.xmf = (float)xim; return r; }
-  WB_HD Col col(int, double yj, double yjm) const { Col c2; c2.yj = yj; c2.yf = (float)yj; c2.ymf = (float)yjm; return c2; }
+  // _msm_cost(x, y, z) = c + (x between y and z ? 0 : min(|x-y|, |x-z|)), differences in fp32.
+  // With a = x-y and b = x-z (fp32; the rounded differences keep the exact sign and are zero
+  // iff the operands are equal), "between" <=> a and b have opposite signs or one is zero, and
+  // in the zero case min(|a|,|b|) is 0 anyway.  So the extra cost is
+  //     signbit(a) != signbit(b) ? 0 : min(|a|, |b|)
+  // -- one xor + one select instead of four compares.  Per cell only ONE fp32 subtraction is
+  // new: for the "up" move a = X[i]-X[i-1] is a row constant and b = X[i]-Y[j]; for the
+  // "left" move a = Y[j]-X[i] = -b (negation is exact) and b = Y[j]-Y[j-1] is a column constant.
+  struct Row { double xi; float xf, dx; };   // dx = (float)X[i] - (float)X[i-1]
+  struct Col { double yj; float yf, dy; };   // dy = (float)Y[j] - (float)Y[j-1]
+  WB_HD Row row(int, double xi, double xim) const { Row r; r.xi = xi; r.xf = (float)xi; r.dx = r.xf - (float)xim; return r; }
+  WB_HD Col col(int, double yj, double yjm) const { Col c2; c2.yj = yj; c2.yf = (float)yj; c2.dy = c2.yf - (float)yjm; return c2; }
 
-  WB_HD double cost(float x, float y, float z) const {
-    bool between = (y <= x && x <= z) || (y >= x && x >= z);
-    float d1 = fabsf(x - y), d2 = fabsf(x - z);
-    float m = d1 < d2 ? d1 : d2;
-    return c + (between ? 0.0 : (double)m);
+  WB_HD static unsigned fbits(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    unsigned u; memcpy(&u, &f, 4); return u;
+#endif
+  }
+  WB_HD double extra(float a, float b) const {
+    const float m = fminf(fabsf(a), fabsf(b));
+    const bool opposite = ((fbits(a) ^ fbits(b)) >> 31) != 0u;
+    return c + (double)(opposite ? 0.0f : m);
   }
   WB_HD double cell(double up, double left, double diag, const Row& r, const Col& cl, int, int) const {
-    double a = diag + fabs(r.xi - cl.yj);
-    double b = up + cost(r.xf, r.xmf, cl.yf);
-    double d = left + cost(cl.yf, r.xf, cl.ymf);
+    const float xy = r.xf - cl.yf;                  // (float)X[i] - (float)Y[j]
+    const double a = diag + fabs(r.xi - cl.yj);
+    const double b = up + extra(r.dx, xy);          // _msm_cost(X[i], X[i-1], Y[j])
+    const double d = left + extra(-xy, cl.dy);      // _msm_cost(Y[j], X[i], Y[j-1])
     return dmin2(dmin2(a, b), d);
   }
   WB_HD double finish(double d, const Geom&) const { return d; }

@@ -164,6 +164,7 @@ struct DpCall {
   int ea;              // eadistance() variants of R (ddtw EL:3308, edr EL:3833)
   long long row0; int mirror;
   bool need_rowmin;    // force the row-scan engine (exact replay needs row minima)
+  const int2* list; const int* list_len;  // PM_LIST (argmin cascade): device-resident survivor list
   // prepared operands (filled by prepare_operands; reusable across chunked launches)
   const double* px; const double* py; int ptx, pty;
   const double* sx; const double* sy;
@@ -241,6 +242,7 @@ static int launch_dp(Workspace& ws, const DeviceInfo& di, const DpCall& c, long 
   a.sx = c.sx ? c.sx + r0 : nullptr; a.sy = c.sy ? c.sy + c0 : nullptr;
   a.out = out; a.ld = ld; a.out_m = out_m; a.thr = thr;
   a.mode = c.mode; a.row0 = c.row0 + r0 - c0; a.mirror = c.mirror;
+  a.list = c.list; a.list_len = c.list_len;
   a.nyb = (ncols + 31) / 32;
   a.ntasks = (c.mode == PM_PAIRED) ? (nrows + 31) / 32 : nrows * a.nyb;
   unsigned long long* counter = nullptr;
@@ -512,6 +514,7 @@ static int run_host_job(const HostJob& J, const int* devices, int n_devices, wb_
       stats->kernel_ms = std::max(stats->kernel_ms, sts[b].kernel_ms);
       stats->total_ms = std::max(stats->total_ms, sts[b].total_ms);
       stats->cells += sts[b].cells; stats->pairs += sts[b].pairs; stats->launches += sts[b].launches;
+      stats->lb_kim_pruned += sts[b].lb_kim_pruned; stats->lb_keogh_pruned += sts[b].lb_keogh_pruned;
       stats->engine = std::max(stats->engine, sts[b].engine);
     }
   }
