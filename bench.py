@@ -298,12 +298,13 @@ def main():
             "gpu_launches": int(args.steps * st["launches"]),
             "clocks": clocks,
             "roofline": {
-                "bound": "fp64_alu", "kernel": "k_strip<DtwPolicy,W=8>", "achieved": achieved, "peak": peak_inst / 1e9,
+                "bound": "fp64_alu", "kernel": "k_strip<DtwPolicy<0,0>, W=12, NT=384, NR=4, GRING> (12 warps/SM, L2-resident boundary rings)", "achieved": achieved, "peak": peak_inst / 1e9,
                 "unit": "G FP64-pipe lane-inst/s", "frac": achieved / (peak_inst / 1e9),
                 "peak_source": "measured in this run: wb_cuda_fp64_peak(mix=0), DADD issue rate, all SMs",
                 "ops_per_cell": ops, "kernel_ms": kernel_ms, "kernel_gcups": cells_rank / (kernel_ms * 1e-3) / 1e9,
                 "nominal_peak": nominal, "frac_of_nominal": achieved / nominal,
-                "dtw_mix_peak": peak_mix / 1e9, "sm_mhz_during_peak": sm_mhz_est,
+                "dtw_mix_peak": peak_mix / 1e9, "frac_of_dtw_mix_peak": achieved / (peak_mix / 1e9),
+                "dtw_mix_peak_note": "register-only loop of the same instruction mix (3 FP64 arith + 2x(DSETP+2 FSEL)): practical issue ceiling, profiles/r01_issue_model.md",
                 "traffic": None,
                 "hbm": {"algorithmic_bytes": int((nx + ny) * T * 8 + nx * ny * 8),
                         "achieved_gbs": ((nx + ny) * T * 8 + nx * ny * 8) / (kernel_ms * 1e-3) / 1e9,
