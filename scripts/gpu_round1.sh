@@ -15,3 +15,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --c
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_strip -s 3 -c 1 -f -o gpurun_out/prof_strip \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --e2e-steps 1 --profile-rows 512 > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out
+timeout 900 python scripts/bench_configs.py > gpurun_out/bench_configs.log 2>&1; echo "bench_configs rc=$?"
+tail -40 gpurun_out/bench_configs.log
