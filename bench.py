@@ -35,6 +35,13 @@ WORKLOAD = {
     "cfg1": dict(metric="dtw", r=0.1, nx=200, ny=200, T=150, desc="pairwise dtw r=0.1 200x150 vs 200x150 (configs[0])"),
     "cfg2": dict(metric="dtw", r=1.0, nx=5000, ny=5000, T=140, desc="pairwise dtw r=1.0 5000x140 vs copy (configs[1], one metric)"),
 }
+# per-metric variants of the cfg2 / cfg5 shapes (profiling and per-config evidence; not the driver's bench line)
+for _m in ("wdtw", "ddtw", "adtw", "msm", "twe", "erp", "lcss", "edr"):
+    WORKLOAD[f"cfg2_{_m}"] = dict(metric=_m, r=1.0, nx=5000, ny=5000, T=140,
+                                  desc=f"pairwise {_m} r=1.0 5000x140 vs copy (configs[1], one metric)")
+for _m in ("msm", "twe", "dtw"):
+    WORKLOAD[f"cfg5_{_m}"] = dict(metric=_m, r=0.05, nx=2000, ny=2000, T=4096,
+                                  desc=f"pairwise {_m} r=0.05 2000x4096 vs 2000x4096 (configs[4])")
 FP64_OPS_PER_CELL = {"dtw": 5, "ddtw": 5, "wdtw": 6, "adtw": 7, "lcss": 4, "erp": 6, "edr": 7, "msm": 8, "twe": 10}
 
 
@@ -42,9 +49,13 @@ def random_walks(n, T, seed):
     return np.cumsum(np.random.default_rng(seed).standard_normal((n, T)), axis=1)
 
 
-def cells_per_pair(T, r):
+def cells_per_pair(T, r, metric="dtw"):
+    """Reference cell count of one equal-length pair; ddtw runs on T-2 points with R from T."""
     R = max(int(np.floor(T * r)), 1)
-    return T * (2 * R - 1) - R * (R - 1) if R <= T else T * T
+    if metric in ("ddtw", "wddtw"):
+        T = T - 2
+    R = min(R, T)
+    return T * (2 * R - 1) - R * (R - 1)
 
 
 from wildboar_b200.sharding import aggregate_throughput, max_over_ranks, row_block  # noqa: E402
@@ -109,13 +120,13 @@ def cpu_reference_callable():
     from oracle import ref
     wd = ref.load()
     if wd is not None:
-        def fn(x, y, r, n_jobs):
-            return wd.pairwise_distance(x, y, metric="dtw", metric_params={"r": r}, n_jobs=n_jobs)
+        def fn(x, y, r, n_jobs, metric="dtw"):
+            return wd.pairwise_distance(x, y, metric=metric, metric_params={"r": r}, n_jobs=n_jobs)
         return "reference", fn
     from oracle import oracle as O
 
-    def fn(x, y, r, n_jobs):
-        return O.pairwise("dtw", x, y, r=r, n_jobs=n_jobs if n_jobs > 0 else 0)
+    def fn(x, y, r, n_jobs, metric="dtw"):
+        return O.pairwise(metric, x, y, r=r, n_jobs=n_jobs if n_jobs > 0 else 0)
     return "port", fn
 
 
@@ -125,11 +136,11 @@ def time_cpu_sample(wl, target_s=12.0, steps=1):
     cores = os.cpu_count() or 1
     x = random_walks(wl["nx"], wl["T"], 1)
     y = random_walks(wl["ny"], wl["T"], 2)
-    cpp = cells_per_pair(wl["T"], wl["r"])
+    cpp = cells_per_pair(wl["T"], wl["r"], wl["metric"])
     ny_s = min(wl["ny"], 1024)
     # warm-up / calibration (joblib thread start-up, page-in)
     nx_p = min(wl["nx"], max(cores, 8))
-    t0 = time.perf_counter(); fn(x[:nx_p], y[:ny_s], wl["r"], cores); fn(x[:nx_p], y[:ny_s], wl["r"], cores)
+    t0 = time.perf_counter(); fn(x[:nx_p], y[:ny_s], wl["r"], cores, wl["metric"]); fn(x[:nx_p], y[:ny_s], wl["r"], cores, wl["metric"])
     dt = (time.perf_counter() - t0) / 2
     rate = nx_p * ny_s * cpp / max(dt, 1e-6)
     nx_s = int(min(wl["nx"], max(cores, target_s * rate / (ny_s * cpp))))
@@ -137,7 +148,7 @@ def time_cpu_sample(wl, target_s=12.0, steps=1):
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        fn(x[:nx_s], y[:ny_s], wl["r"], cores)
+        fn(x[:nx_s], y[:ny_s], wl["r"], cores, wl["metric"])
         times.append(time.perf_counter() - t0)
     cells = nx_s * ny_s * cpp
     return {"kind": kind, "cores": cores, "times": times, "cells_per_step": cells,
@@ -221,7 +232,7 @@ def main():
     x_h = random_walks(wl["nx"], T, 1)[lo:hi].copy()
     y_h = random_walks(wl["ny"], T, 2)
     nx, ny = hi - lo, wl["ny"]
-    cpp = cells_per_pair(T, r)
+    cpp = cells_per_pair(T, r, metric)
     cells_rank = nx * ny * cpp
     cells_total = wl["nx"] * ny * cpp
 
@@ -298,7 +309,7 @@ def main():
             "gpu_launches": int(args.steps * st["launches"]),
             "clocks": clocks,
             "roofline": {
-                "bound": "fp64_alu", "kernel": "k_strip<DtwPolicy<0,0>, W=12, NT=384, NR=4, GRING> (12 warps/SM, L2-resident boundary rings)", "achieved": achieved, "peak": peak_inst / 1e9,
+                "bound": "fp64_alu", "kernel": _kernel_label(metric, st), "achieved": achieved, "peak": peak_inst / 1e9,
                 "unit": "G FP64-pipe lane-inst/s", "frac": achieved / (peak_inst / 1e9),
                 "peak_source": "measured in this run: wb_cuda_fp64_peak(mix=0), DADD issue rate, all SMs",
                 "ops_per_cell": ops, "kernel_ms": kernel_ms, "kernel_gcups": cells_rank / (kernel_ms * 1e-3) / 1e9,
@@ -322,6 +333,14 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _kernel_label(metric, st):
+    if st.get("engine") != 2:
+        return f"k_rowscan<{metric}>"
+    where = "L2-resident global boundary buffers" if st.get("strip_gring") else "shared-memory boundary buffers"
+    return (f"k_strip<{metric}, W={st.get('strip_w')}, NR={st.get('strip_nr')}, {st.get('strip_warps')} warps/CTA> "
+            f"(thread per pair, {where})")
 
 
 def _measured_hbm():

@@ -67,11 +67,11 @@ static void run_issue(const char* name, int ninst, int sms, int warps_per_smsp) 
 struct Result { double ms; double gcups; double checksum; };
 
 template <class M, int W, int NR, int NWARPS, int MINB, bool GRING = false>
-static Result run_variant(const M& m, const double* dx, const double* dy, long long nx, long long ny, int T, int R,
+static Result run_variant(const char* pname, int ops, const M& m, const double* dx, const double* dy, long long nx, long long ny, int T, int R,
                           double* dout, unsigned long long* counter, int sms, int reps) {
   KArgs a; memset(&a, 0, sizeof a);
   a.x = dx; a.y = dy; a.nx = nx; a.ny = ny; a.Tx = T; a.Ty = T; a.g = make_geom(T, T, R);
-  a.NS = strip_ring_slots(a.g); a.out = dout; a.ld = ny; a.counter = counter; a.mode = PM_PAIRWISE;
+  a.NS = strip_ring_slots(a.g, W); a.out = dout; a.ld = ny; a.counter = counter; a.mode = PM_PAIRWISE;
   a.nyb = (ny + 31) / 32; a.ntasks = nx * a.nyb;
   size_t smem = GRING ? 0 : (size_t)NWARPS * a.NS * 32 * sizeof(double);
   auto kern = k_strip<M, W, NWARPS * 32, MINB, false, NR, GRING>;
@@ -100,8 +100,8 @@ static Result run_variant(const M& m, const double* dx, const double* dy, long l
   for (double v : h) r.checksum += v;
   cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
   if (GRING) cudaFree(a.gring);
-  printf("%s W=%2d NR=%d warps/CTA=%d CTAs/SM=%d regs=%3d smem=%6zu  %8.2f ms  %8.1f GCUPS  (%.1f%% of 3689 nominal)  chk=%.6f\n",
-         GRING ? "gring" : "strip", W, NR, NWARPS, per_sm, fa.numRegs, smem, r.ms, r.gcups, 100.0 * r.gcups * 5 / 18448.0, r.checksum);
+  printf("%-5s %s W=%2d NR=%d warps/CTA=%d CTAs/SM=%d regs=%3d smem=%6zu  %8.2f ms  %8.1f GCUPS  (%.1f%% of FP64 peak, %d ops/cell)  chk=%.6f\n",
+         pname, GRING ? "gring" : "strip", W, NR, NWARPS, per_sm, fa.numRegs, smem, r.ms, r.gcups, 100.0 * r.gcups * ops / 18448.0, ops, r.checksum);
   fflush(stdout);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return r;
@@ -113,14 +113,14 @@ int main(int argc, char** argv) {
   int reps = argc > 5 ? atoi(argv[5]) : 2;
   int dev = 0, sms = 0; CK(cudaGetDevice(&dev)); CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   printf("SMs=%d  problem %d x %d, T=%d, r=%.3f\n", sms, nx, ny, T, rr);
-  if (argc <= 6) for (int w : {2, 4, 8}) {
+  if (argc <= 7) for (int w : {8}) {
     run_issue<0>("DADD", 8, sms, w);
     run_issue<1>("DADD+LOP(alu) 1:1", 16, sms, w);
     run_issue<2>("DADD+IMAD(fma) 1:1", 16, sms, w);
     run_issue<3>("DADD+LOP+FFMA 1:1:1", 24, sms, w);
     run_issue<6>("DADD+2LOP 1:2", 24, sms, w);
   }
-  if (argc <= 6) { run_issue<4>("LOP only", 8, sms, 8); run_issue<5>("LOP+FFMA 1:1", 16, sms, 8); }
+  if (argc <= 7) { run_issue<4>("LOP only", 8, sms, 8); run_issue<5>("LOP+FFMA 1:1", 16, sms, 8); }
 
   std::vector<double> hx((size_t)nx * T), hy((size_t)ny * T);
   unsigned s = 12345;
@@ -134,12 +134,37 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(dy, hy.data(), hy.size() * 8, cudaMemcpyHostToDevice));
   int R = (int)compute_r(T, rr);
   DtwPolicy<false, false> m; m.w = nullptr; m.p = 0;
-#define V(W, NR, NW, MB) run_variant<DtwPolicy<false, false>, W, NR, NW, MB>(m, dx, dy, nx, ny, T, R, dout, counter, sms, reps);
-  int only_strip = argc > 6 ? atoi(argv[6]) : 0;
-  (void)only_strip;
-#define G(W, NR, NW, MB) run_variant<DtwPolicy<false, false>, W, NR, NW, MB, true>(m, dx, dy, nx, ny, T, R, dout, counter, sms, reps);
-  V(16, 4, 8, 1) V(16, 4, 6, 1) V(16, 4, 2, 1) V(8, 2, 8, 2)
-  G(16, 4, 8, 1) G(16, 4, 9, 1) G(12, 4, 8, 1) G(12, 4, 10, 1) G(12, 4, 12, 1) G(8, 4, 8, 1) G(8, 4, 8, 2) G(8, 2, 8, 2) G(8, 4, 12, 1)
+  // tables for the weighted metrics / twe (signed, pointer to the centre)
+  std::vector<double> hw = make_weights(0.05, T), htw = make_tw(0.001, T + 1);
+  double *dw, *dtw;
+  CK(cudaMalloc(&dw, hw.size() * 8)); CK(cudaMalloc(&dtw, htw.size() * 8));
+  CK(cudaMemcpy(dw, hw.data(), hw.size() * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dtw, htw.data(), htw.size() * 8, cudaMemcpyHostToDevice));
+  DtwPolicy<true, false> mw; mw.w = dw + table_center(T); mw.p = 0;
+  DtwPolicy<false, true> ma; ma.w = nullptr; ma.p = 1.0;
+  LcssPolicy<false> ml; ml.w = nullptr; ml.eps = 1.0;
+  ErpPolicy me; me.g = 0; me.gx_sum = 0; me.gy_sum = 0;
+  EdrPolicy md; md.eps_param = 0.25; md.eps = 0.25;
+  MsmPolicy mm; mm.cf = 1.0f; mm.c = 1.0;
+  TwePolicy mt; mt.pen = 1.001; mt.tw = dtw + table_center(T + 1);
+  int set = argc > 6 ? atoi(argv[6]) : 0;
+#define RV(P, NAME, OPS, OBJ, W, NR, NW, MB, GR) run_variant<P, W, NR, NW, MB, GR>(NAME, OPS, OBJ, dx, dy, nx, ny, T, R, dout, counter, sms, reps);
+#define V(W, NR, NW, MB) RV(decltype(m), "dtw", 5, m, W, NR, NW, MB, false)
+#define G(W, NR, NW, MB) RV(decltype(m), "dtw", 5, m, W, NR, NW, MB, true)
+#define GP(W, NR, NW, MB) RV(decltype(mw), "wdtw", 6, mw, W, NR, NW, MB, true) RV(decltype(ma), "adtw", 7, ma, W, NR, NW, MB, true) \
+  RV(decltype(ml), "lcss", 4, ml, W, NR, NW, MB, true) RV(decltype(me), "erp", 6, me, W, NR, NW, MB, true) RV(decltype(md), "edr", 7, md, W, NR, NW, MB, true) \
+  RV(decltype(mm), "msm", 8, mm, W, NR, NW, MB, true) RV(decltype(mt), "twe", 10, mt, W, NR, NW, MB, true)
+#define GL(W, NR, NW, MB) RV(decltype(mm), "msm", 8, mm, W, NR, NW, MB, true) RV(decltype(mt), "twe", 10, mt, W, NR, NW, MB, true)
+  if (set == 0) {  // dtw, tall bands (cfg3 / cfg2 shapes)
+    G(12, 4, 12, 1) G(12, 6, 12, 1) G(12, 8, 12, 1) G(8, 2, 16, 1) G(8, 4, 16, 1) G(8, 6, 16, 1) G(8, 8, 16, 1)
+    G(10, 6, 14, 1) G(10, 5, 14, 1) G(14, 6, 10, 1) G(16, 6, 8, 1) G(6, 4, 20, 1) G(6, 6, 20, 1)
+  } else if (set == 1) {  // dtw, narrow bands (cfg1 / cfg4 shapes)
+    V(8, 2, 8, 2) V(8, 4, 8, 2) V(8, 6, 8, 2) V(8, 2, 16, 1) V(6, 2, 8, 2) V(6, 2, 10, 2) V(4, 2, 12, 2)
+  } else if (set == 2) {  // the other metrics, cfg2 shape
+    GP(8, 4, 12, 1) GP(8, 4, 16, 1) GP(8, 2, 16, 1) GP(12, 4, 12, 1) GP(12, 6, 12, 1) GP(8, 6, 12, 1)
+  } else {  // long series (cfg5 shape): msm / twe
+    GL(16, 4, 8, 1) GL(12, 4, 8, 1) GL(12, 4, 12, 1) GL(8, 4, 12, 1) GL(8, 4, 16, 1) GL(8, 2, 16, 1) GL(12, 6, 12, 1) GL(8, 4, 8, 2)
+  }
   printf("done\n");
   return 0;
 }

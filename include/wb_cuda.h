@@ -63,6 +63,10 @@ typedef struct wb_stats {
   int32_t engine;       /* engine used for the DP (1 row-scan, 2 strip)                  */
   int64_t lb_kim_pruned;   /* argmin cascade: pairs pruned by LB_Kim                     */
   int64_t lb_keogh_pruned; /* argmin cascade: pairs pruned by LB_Keogh (either direction)  */
+  int32_t strip_w;      /* strip engine, last launch: strip width W (columns held in registers) */
+  int32_t strip_nr;     /* rows per fast-path iteration (in-thread wavefront depth)            */
+  int32_t strip_warps;  /* warps per CTA                                                       */
+  int32_t strip_gring;  /* 1: boundary buffers in global memory (L2), 0: shared memory          */
 } wb_stats;
 
 int wb_cuda_device_count(void);

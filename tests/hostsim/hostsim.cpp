@@ -17,13 +17,13 @@ struct StripRunner {
   static double run(const Geom& g, const M& m, const double* x, const double* y, int NS, int bs, double abandon, int* ok) {
     if (!strip_supported<M>(g, W)) { *ok = 0; return 0; }
     *ok = 1;
-    std::vector<double> bnd((size_t)NS * bs + 8, -12345.0);
-    if (abandon < INFINITY) return strip_pair<M, W, true>(g, m, x, y, bnd.data(), bs, NS, abandon);
+    std::vector<double> bnd((size_t)NS * bs, -12345.0);
+    if (abandon < INFINITY) return strip_pair<M, W, true>(g, m, x, y, bnd.data(), bs, abandon);
     // exercise several in-thread wavefront depths
-    const double r2 = strip_pair<M, W, false, 2>(g, m, x, y, bnd.data(), bs, NS, abandon);
-    const double r1 = strip_pair<M, W, false, 1>(g, m, x, y, bnd.data(), bs, NS, abandon);
-    const double r4 = strip_pair<M, W, false, 4>(g, m, x, y, bnd.data(), bs, NS, abandon);
-    const double r3 = strip_pair<M, W, false, 3>(g, m, x, y, bnd.data(), bs, NS, abandon);
+    const double r2 = strip_pair<M, W, false, 2>(g, m, x, y, bnd.data(), bs, abandon);
+    const double r1 = strip_pair<M, W, false, 1>(g, m, x, y, bnd.data(), bs, abandon);
+    const double r4 = strip_pair<M, W, false, 4>(g, m, x, y, bnd.data(), bs, abandon);
+    const double r3 = strip_pair<M, W, false, 3>(g, m, x, y, bnd.data(), bs, abandon);
     if (!(r1 == r2 && r2 == r4 && r3 == r2) && !(r1 != r1 && r2 != r2)) return -1e300;  // NR variants disagree
     return r2;
   }
@@ -50,7 +50,7 @@ extern "C" int hostsim_pair(int engine, int W, int metric, const wb_params* p, c
   if (metric == M_WDTW || metric == M_WLCSS) w = make_weights(p->g, nmax);
   if (metric == M_WDDTW) w = make_weights(p->g, nmax);
   if (metric == M_TWE) tw = make_tw(p->stiffness, nmax + 1);
-  Tables t{w.data(), tw.data()};
+  Tables t{w.empty() ? nullptr : w.data() + table_center(nmax), tw.empty() ? nullptr : tw.data() + table_center(nmax + 1)};
   PairCtx pc{0, 0};
   if (metric == M_ERP) { pc.sx = seq_gap_sum(x, tx, p->g); pc.sy = seq_gap_sum(y, ty, p->g); }
   if (metric == M_EDR) { pc.sx = seq_std(x, tx); pc.sy = seq_std(y, ty); }
@@ -64,7 +64,7 @@ extern "C" int hostsim_pair(int engine, int W, int metric, const wb_params* p, c
       *out = rowscan_pair(g, m, x, y, b0.data(), b1.data(), (long long)bs, min_dist_raw, &mm);
       if (out_rowminmax) *out_rowminmax = mm;
     } else {
-      int NS = strip_ring_slots(g) + ns_extra;
+      int NS = strip_ring_slots(g, W) + ns_extra;
       int ok = 0;
       double r = 0;
       switch (W) {

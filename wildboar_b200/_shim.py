@@ -26,7 +26,8 @@ class WbParams(C.Structure):
 
 class WbStats(C.Structure):
     _fields_ = [("kernel_ms", C.c_double), ("total_ms", C.c_double), ("cells", C.c_int64), ("pairs", C.c_int64),
-                ("launches", C.c_int32), ("engine", C.c_int32), ("lb_kim_pruned", C.c_int64), ("lb_keogh_pruned", C.c_int64)]
+                ("launches", C.c_int32), ("engine", C.c_int32), ("lb_kim_pruned", C.c_int64), ("lb_keogh_pruned", C.c_int64),
+                ("strip_w", C.c_int32), ("strip_nr", C.c_int32), ("strip_warps", C.c_int32), ("strip_gring", C.c_int32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

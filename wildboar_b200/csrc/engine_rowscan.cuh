@@ -36,12 +36,12 @@ WB_HD double rowscan_pair(const Geom& g, const M& m, const double* __restrict__ 
     // the running sum cy (EL:1620-1622)
     typename M::Row r0 = m.row(0, x[0], 0.0);
     typename M::Col c0 = m.col(0, y[0], 0.0);
-    double v = m.cell(WB_INF, WB_INF, 0.0, r0, c0, 0, 0);
+    double v = m.cell(WB_INF, WB_INF, 0.0, r0, c0, m.dv(0, 0));
     prev[0] = v;
     int n0 = imin2(Ty, g.max_len + 1);
     for (int j = 1; j < n0; ++j) {
       typename M::Col cj = m.col(j, y[j], y[j - 1]);
-      v = m.cell(WB_INF, v, WB_INF, r0, cj, 0, j);
+      v = m.cell(WB_INF, v, WB_INF, r0, cj, m.dv(0, j));
       prev[(long long)j * bs] = v;
     }
     cy = prev[0];
@@ -62,7 +62,7 @@ WB_HD double rowscan_pair(const Geom& g, const M& m, const double* __restrict__ 
     double left, diag;
     if (M::kMsmBand) {
       typename M::Col c0 = m.col(0, y[0], 0.0);
-      cy = m.cell(cy, WB_INF, WB_INF, rw, c0, i, 0);  // up-branch only: cy[i-1] + cost(X[i],X[i-1],Y[0])
+      cy = m.cell(cy, WB_INF, WB_INF, rw, c0, m.dv(i, 0));  // up-branch only: cy[i-1] + cost(X[i],X[i-1],Y[0])
       cost[0] = cy;
       rowmin = cy;
       js = imax2(1, js);
@@ -83,7 +83,7 @@ WB_HD double rowscan_pair(const Geom& g, const M& m, const double* __restrict__ 
       const double yj = y[j];
       const double yjm = (j > 0) ? y[j - 1] : 0.0;
       const typename M::Col cj = m.col(j, yj, yjm);
-      const double d = m.cell(up, left, diag, rw, cj, i, j);
+      const double d = m.cell(up, left, diag, rw, cj, m.dv(i, j));
       cost[(long long)j * bs] = d;
       rowmin = dmin2(rowmin, d);
       left = d;

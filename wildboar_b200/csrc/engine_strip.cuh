@@ -43,9 +43,21 @@ inline bool strip_supported(const Geom& g, int W) {
   return true;
 }
 
-// Ring slots needed per pair: every in-band cell of a boundary column (H of them), plus the
-// left-sentinel slot that the producer strip appends below it; never more than the Tx rows.
-WB_HD int strip_ring_slots(const Geom& g) { return imax2(2, imin2(g.H + 1, g.Tx)); }
+// Boundary-buffer slots needed per pair.  The buffer between strip s and strip s+1 holds the
+// last column of strip s, D[i][jl], LINEARLY: slot(i) = i - (i_lo(s+1) - 1).  Strip s therefore
+// reads slot i - B_in and writes slot i - B_out with B_out - B_in = i_lo(s+1) - i_lo(s) >= 0:
+// writes trail reads inside the same buffer, no modulo arithmetic, and in the hot loop every
+// access is pointer + immediate.  Reads reach at most min(Tx, H + W - 1) slots past slot 0; the
+// fast path prefetches one NR-row group ahead (padding: NR <= 8 slots).
+WB_HD int strip_ring_slots(const Geom& g, int W) { return imin2(g.Tx, g.H + W - 1) + 1 + 8; }
+
+// first row of the strip that starts at column j0
+template <class M>
+WB_HD int strip_ilo(const Geom& g, int j0) {
+  int v = imax2(0, j0 - g.max_len + 1);
+  if (M::kMsmBand && j0 == g.max_len) v = 0;  // row 0 reaches one cell beyond the band (EL:1615-1617)
+  return v;
+}
 
 // Opaque select: keeps the compiler from turning a chain of register selects into a
 // dynamically indexed (local-memory) array access.
@@ -59,20 +71,22 @@ WB_HD double sel_f64(bool p, double a, double b) {
 #endif
 }
 
-// bnd: ring base for this pair; slot s lives at bnd[s * bs].
+// bnd: boundary buffer of this pair; slot s lives at bnd[s * bs] (BS > 0: compile-time stride).
 // abandon: early-abandon threshold on the RAW dp value (pre-finish); only honoured for
 //          policies whose column minima lower-bound the result (DTW family).  Returns +INF
 //          when abandoned.
 //
 // Rows of a strip fall in three phases: a top triangle (the band's upper edge crosses the
 // strip), FULL rows (all W cells in band) and a bottom triangle.  Triangle rows go through
-// `generic_row` (per-cell, warp-uniform predicates).  Full rows -- (2R-1-W+1)/(2R-1+W-1) of
-// all rows, 87 % for the headline shape -- take the predicate-free `fast path`, two rows per
-// iteration so that two independent left->right dependency chains are in flight per thread.
-template <class M, int W, bool EA, int NR = 2>
+// `generic_row` (per-cell, warp-uniform predicates) or, for regular triangles, straight-line
+// code.  Full rows -- (2R-1-W+1)/(2R-1+W-1) of all rows, 87 % for the headline shape -- take
+// the predicate-free `fast path`, NR rows per iteration so that NR independent left->right
+// dependency chains are in flight per thread.
+template <class M, int W, bool EA, int NR = 2, int BS = 0>
 WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
-                        const double* __restrict__ y, double* bnd, int bs, int NS, double abandon) {
+                        const double* __restrict__ y, double* bnd, int bs_rt, double abandon) {
   const int Tx = g.Tx, Ty = g.Ty;
+  const long long bs = BS > 0 ? BS : bs_rt;
   double result = 0.0;
   const double left0c = m.left0(1);
 
@@ -81,9 +95,13 @@ WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
     const bool last_strip = (j0 + W >= Ty);
     const bool first_strip = (j0 == 0);
     const int jl = j0 + wv - 1;
-    int i_lo = imax2(0, j0 - g.max_len + 1);
-    if (M::kMsmBand && j0 == g.max_len) i_lo = 0;
+    const int i_lo = strip_ilo<M>(g, j0);
     const int i_hi = imin2(Tx - 1, jl + g.a);
+    // read slot of row i: i - B_in (slot 0 = row i_lo - 1, the first diagonal); write slot: i - B_out
+    const int B_in = i_lo - 1;
+    const int B_out = last_strip ? B_in : strip_ilo<M>(g, j0 + W) - 1;
+    double* const rbase = bnd - (long long)B_in * bs;   // rbase[i * bs] = read slot of row i
+    double* const wbase = bnd - (long long)B_out * bs;  // wbase[i * bs] = write slot of row i
 
     typename M::Col cols[W];
 #pragma unroll
@@ -97,31 +115,25 @@ WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
 #pragma unroll
     for (int c = 0; c < W; ++c) prev[c] = m.usent();
 
-    int sl = i_lo % NS;
     double Dg;
     if (first_strip) {
       // virtual column -1: left0 is the same constant for every row and diag0(i) == left0(i-1)
-      // for i >= 1, so the first strip simply finds left0 in every ring slot it will read.
-      const int nfill = imin2(NS, i_hi + 2);
-      for (int s = 0; s < nfill; ++s) bnd[s * bs] = left0c;
+      // for i >= 1, so the first strip simply finds left0 in every slot it will read.
+      for (int s = 0; s <= i_hi + 1; ++s) bnd[s * bs] = left0c;
       Dg = m.diag0(0);
     } else if (i_lo == 0) Dg = m.prev_init();
-    else { int sp = (sl == 0) ? NS - 1 : sl - 1; Dg = bnd[sp * bs]; }
+    else Dg = bnd[0];
     double xi = x[i_lo];
     double xim = (M::kNeedPrevX && i_lo > 0) ? x[i_lo - 1] : 0.0;
     double stale = m.lsent();
     double colmin = WB_INF;
     int i = i_lo;
-    double pf[NR];
-    bool have_pf = false;
-#pragma unroll
-    for (int r = 0; r < NR; ++r) pf[r] = 0.0;
 
     auto generic_row = [&]() {
       const double xnext = x[imin2(i + 1, Tx - 1)];  // prefetch next row's sample
       const int js = row_js<M>(g, i), je = row_je<M>(g, i);
       const int clo = imax2(js - j0, 0), chi = imin2(je - j0, wv);
-      double left = bnd[sl * bs];
+      double left = rbase[i * bs];
       double diag = Dg;
       Dg = left;
       if (i == 0) {
@@ -137,19 +149,19 @@ WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
         if (M::kMsmBand && c == cst) stale_next = up;
         if (c >= clo && c < chi) {
           if (c > 0 && c == clo) left = M::kMsmBand ? stale : m.lsent();
-          const double d = m.cell(up, left, diag, rw, cols[c], i, j0 + c);
+          const double d = m.cell(up, left, diag, rw, cols[c], m.dv(i, j0 + c));
           prev[c] = d;
           left = d;
         }
         diag = up;
       }
       stale = stale_next;
-      if (chi == W) {
+      // (MSM's row 0 reaches one cell beyond the band; no later strip reads that value)
+      if (chi == W && (!M::kMsmBand || i >= B_out)) {
         const double b = prev[W - 1];
-        bnd[sl * bs] = b;
+        wbase[i * bs] = b;
         if (EA && M::kColumnMinBound) colmin = dmin2(colmin, b);
       }
-      sl = (sl + 1 == NS) ? 0 : sl + 1;
       xim = xi;
       xi = xnext;
       ++i;
@@ -166,85 +178,94 @@ WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
     const bool reg_top = wide && i_lo >= 1 && i_lo == j0 - g.max_len + 1;
     const bool reg_bot = wide && (j0 + g.a + W - 1 <= Tx - 1);
 
-    // One copy of every row routine; the hot two-row loop stays a tight inner loop.
+    // One copy of every row routine; the hot NR-row loop stays a tight inner loop.
     for (;;) {
-      while (i >= fa && i + NR - 1 <= fb) {
+      if (i >= fa && i + NR - 1 <= fb) {
         // ---- fast path: rows i .. i+NR-1, all W cells in band, no predicates; NR independent
-        // left->right dependency chains (an in-thread anti-diagonal wavefront) ----
-        double xr[NR];
-        xr[0] = xi;
+        // left->right dependency chains (an in-thread anti-diagonal wavefront).  All boundary
+        // and x accesses are pointer + immediate; the boundary values and x samples of the NEXT
+        // group are loaded one group ahead (hides the L1/L2 latency of the global rings).
+        double* rp = rbase + (long long)i * bs;
+        double* wp = wbase + (long long)i * bs;
+        const double* xp = x + i;
+        double pf[NR], xn[NR];
 #pragma unroll
-        for (int r = 1; r < NR; ++r) xr[r] = x[i + r];
-        const double xnext = x[imin2(i + NR, Tx - 1)];
-        int slr[NR];
-        slr[0] = sl;
+        for (int r = 0; r < NR; ++r) pf[r] = rp[r * bs];
+        xn[0] = xi;
 #pragma unroll
-        for (int r = 1; r < NR; ++r) slr[r] = (slr[r - 1] + 1 == NS) ? 0 : slr[r - 1] + 1;
-        double lft[NR], dg[NR];
-        typename M::Row rws[NR];
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          lft[r] = have_pf ? pf[r] : bnd[slr[r] * bs];
-          rws[r] = m.row(i + r, xr[r], r == 0 ? xim : xr[r - 1]);
-        }
-        // prefetch the boundary values of the NEXT NR rows (hides the ring's load latency when
-        // it lives in global memory; any slot is valid memory, unused values are discarded)
-        {
-          int sn = (slr[NR - 1] + 1 == NS) ? 0 : slr[NR - 1] + 1;
+        for (int r = 1; r < NR; ++r) xn[r] = xp[r];
+        do {
+          double xr[NR], lft[NR], dg[NR];
+          typename M::Row rws[NR];
 #pragma unroll
           for (int r = 0; r < NR; ++r) {
-            pf[r] = bnd[sn * bs];
-            sn = (sn + 1 == NS) ? 0 : sn + 1;
+            xr[r] = xn[r];
+            lft[r] = pf[r];
+            rws[r] = m.row(i + r, xr[r], r == 0 ? xim : xr[r - 1]);
           }
-          have_pf = true;
-        }
-        dg[0] = Dg;
-#pragma unroll
-        for (int r = 1; r < NR; ++r) dg[r] = lft[r - 1];
-        Dg = lft[NR - 1];
-#pragma unroll
-        for (int c = 0; c < W; ++c) {
-          double v = prev[c];
+          // next group's operands (the rows exist whenever the loop continues; otherwise the
+          // clamped x pointer / the padded buffer keep the loads in bounds and the values unused)
+          const double* xq = (i + 2 * NR <= Tx) ? xp + NR : xp;
 #pragma unroll
           for (int r = 0; r < NR; ++r) {
-            const double d = m.cell(v, lft[r], dg[r], rws[r], cols[c], i + r, j0 + c);
-            dg[r] = v;
-            lft[r] = d;
-            v = d;
+            pf[r] = rp[(NR + r) * bs];
+            xn[r] = xq[r];
           }
-          prev[c] = v;
-        }
-        // lft[r] now holds column W-1 of row i+r (the last strip's writes are never read; they
-        // are kept so the hot loop has no strip-dependent branch)
+          // per-diagonal values (weights / stiffness terms) of the group's W + NR - 1 diagonals:
+          // pointer + immediate loads from the signed tables, nothing for the other metrics
+          typename M::Dv dvs[W + NR - 1];
+          if (M::kHasDv) {
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-          bnd[slr[r] * bs] = lft[r];
-          if (EA && M::kColumnMinBound) colmin = dmin2(colmin, lft[r]);
-        }
-        sl = (slr[NR - 1] + 1 == NS) ? 0 : slr[NR - 1] + 1;
-        xim = xr[NR - 1];
-        xi = xnext;
-        i += NR;
+            for (int d = 0; d < W + NR - 1; ++d) dvs[d] = m.dv_diag(i - j0 + d - (W - 1));
+          }
+          dg[0] = Dg;
+#pragma unroll
+          for (int r = 1; r < NR; ++r) dg[r] = lft[r - 1];
+          Dg = lft[NR - 1];
+#pragma unroll
+          for (int c = 0; c < W; ++c) {
+            double v = prev[c];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+              const double d = m.cell(v, lft[r], dg[r], rws[r], cols[c], dvs[r - c + W - 1]);
+              dg[r] = v;
+              lft[r] = d;
+              v = d;
+            }
+            prev[c] = v;
+          }
+          // lft[r] now holds column W-1 of row i+r (the last strip's writes are never read; they
+          // are kept so the hot loop has no strip-dependent branch)
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            wp[r * bs] = lft[r];
+            if (EA && M::kColumnMinBound) colmin = dmin2(colmin, lft[r]);
+          }
+          xim = xr[NR - 1];
+          rp += NR * bs;
+          wp += NR * bs;
+          xp += NR;
+          i += NR;
+        } while (i + NR - 1 <= fb);
+        xi = x[imin2(i, Tx - 1)];
       }
-      have_pf = false;
       if (i > i_hi) break;
       if (reg_top && i == i_lo) {
 #pragma unroll
         for (int t = 0; t < W - 1; ++t) {
           const double xnext = x[imin2(i + 1, Tx - 1)];
-          double left = bnd[sl * bs];
+          double left = rbase[i * bs];
           double diag = Dg;
           Dg = left;
           const typename M::Row rw = m.row(i, xi, xim);
 #pragma unroll
           for (int c = 0; c <= t; ++c) {
             const double up = prev[c];
-            const double d = m.cell(up, left, diag, rw, cols[c], i, j0 + c);
+            const double d = m.cell(up, left, diag, rw, cols[c], m.dv(i, j0 + c));
             prev[c] = d;
             left = d;
             diag = up;
           }
-          sl = (sl + 1 == NS) ? 0 : sl + 1;
           xim = xi;
           xi = xnext;
           ++i;
@@ -260,14 +281,13 @@ WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
 #pragma unroll
           for (int c = t; c < W; ++c) {
             const double up = prev[c];
-            const double d = m.cell(up, left, diag, rw, cols[c], i, j0 + c);
+            const double d = m.cell(up, left, diag, rw, cols[c], m.dv(i, j0 + c));
             prev[c] = d;
             left = d;
             diag = up;
           }
-          bnd[sl * bs] = left;
+          wbase[i * bs] = left;
           if (EA && M::kColumnMinBound) colmin = dmin2(colmin, left);
-          sl = (sl + 1 == NS) ? 0 : sl + 1;
           xim = xi;
           xi = xnext;
           ++i;
@@ -278,7 +298,7 @@ WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
     }
 
     if (!last_strip) {
-      if (jl + g.a + 1 <= Tx - 1) bnd[sl * bs] = M::kMsmBand ? stale : m.lsent();
+      if (jl + g.a + 1 <= Tx - 1) wbase[(jl + g.a + 1) * bs] = M::kMsmBand ? stale : m.lsent();
       if (EA && M::kColumnMinBound && colmin > abandon) return WB_INF;
     } else {
 #pragma unroll

@@ -19,7 +19,7 @@ struct KArgs {
   long long nx, ny;
   int Tx, Ty;
   Geom g;
-  int NS;            // strip engine: ring slots per pair
+  int NS;            // strip engine: boundary-buffer slots per pair (strip_ring_slots(g, W))
   const double* sx;  // per-sample scalars of x (erp gap sums / edr std) or nullptr
   const double* sy;
   double* out;
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(NT, MINB) k_strip(KArgs a, M m) {
     pc.sy = a.sy ? a.sy[j] : 0.0;
     mm.begin_pair(pc);
     const double ab = EA ? a.thr[i] : WB_INF;
-    const double d = strip_pair<M, W, EA, NR>(a.g, mm, a.x + i * a.Tx, a.y + j * a.Ty, bnd, 32, a.NS, ab);
+    const double d = strip_pair<M, W, EA, NR, 32>(a.g, mm, a.x + i * a.Tx, a.y + j * a.Ty, bnd, 32, ab);
     if (valid) {
       if (a.mode == PM_PAIRED) a.out[i] = d;
       else {

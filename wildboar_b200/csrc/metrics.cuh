@@ -94,7 +94,7 @@ struct DtwPolicy {
   static constexpr bool kMsmBand = false;
   static constexpr bool kNeedPrevX = false;
   static constexpr bool kColumnMinBound = true;  // column minima lower-bound the result
-  const double* w;  // weights table (WEIGHTED), length >= max(Tx,Ty)
+  const double* w;  // WEIGHTED: CENTER of the signed weights table, w[d] = weight(|d|), d = i - j
   double p;         // penalty (AMERCING)
 
   WB_HD double prev_init() const { return WB_INF; }
@@ -110,14 +110,16 @@ struct DtwPolicy {
     Row r; r.xi = xi; r.p = (AMERCING && i > 0) ? p : 0.0; return r;
   }
   WB_HD Col col(int, double yj, double) const { Col c; c.yj = yj; return c; }
+  // per-diagonal value: the weight; row 0 uses w[max(j-1,0)] (EL:894-903 quirk)
+  struct Dv { double w; };
+  static constexpr bool kHasDv = WEIGHTED;
+  WB_HD Dv dv(int i, int j) const { Dv d; d.w = WEIGHTED ? ldg(w + ((i == 0) ? imax2(j - 1, 0) : (i - j))) : 1.0; return d; }
+  WB_HD Dv dv_diag(int d) const { Dv v; v.w = WEIGHTED ? ldg(w + d) : 1.0; return v; }  // rows >= 1
 
-  WB_HD double cell(double up, double left, double diag, const Row& r, const Col& c, int i, int j) const {
+  WB_HD double cell(double up, double left, double diag, const Row& r, const Col& c, const Dv& d) const {
     double v = r.xi - c.yj;
     double cost = v * v;
-    if (WEIGHTED) {
-      int k = (i == 0) ? imax2(j - 1, 0) : iabs1(i - j);
-      cost = cost * ldg(w + k);
-    }
+    if (WEIGHTED) cost = cost * d.w;
     if (AMERCING) { up = up + r.p; left = left + r.p; }
     return dmin2(dmin2(up, left), diag) + cost;
   }
@@ -132,7 +134,7 @@ struct LcssPolicy {
   static constexpr bool kMsmBand = false;
   static constexpr bool kNeedPrevX = false;
   static constexpr bool kColumnMinBound = false;
-  const double* w;
+  const double* w;  // WEIGHTED: center of the signed weights table
   double eps;
 
   WB_HD double prev_init() const { return 0.0; }
@@ -147,10 +149,15 @@ struct LcssPolicy {
   WB_HD Row row(int, double xi, double) const { Row r; r.xi = xi; return r; }
   WB_HD Col col(int, double yj, double) const { Col c; c.yj = yj; return c; }
 
-  WB_HD double cell(double up, double left, double diag, const Row& r, const Col& c, int i, int j) const {
+  struct Dv { double w; };
+  static constexpr bool kHasDv = WEIGHTED;
+  WB_HD Dv dv(int i, int j) const { return dv_diag(i - j); }
+  WB_HD Dv dv_diag(int d) const { Dv v; v.w = WEIGHTED ? ldg(w + d) : 1.0; return v; }
+
+  WB_HD double cell(double up, double left, double diag, const Row& r, const Col& c, const Dv& d) const {
     double v = fabs(r.xi - c.yj);
     double wv = 1.0;
-    if (WEIGHTED) wv = ldg(w + iabs1(i - j));
+    if (WEIGHTED) wv = d.w;
     double hit = wv + diag;
     double miss = dmax2(left, up);
     return (v <= eps) ? hit : miss;
@@ -180,7 +187,12 @@ struct ErpPolicy {
   WB_HD Row row(int, double xi, double) const { Row r; r.xi = xi; r.gx = fabs(xi - g); return r; }
   WB_HD Col col(int, double yj, double) const { Col c; c.yj = yj; c.gy = fabs(yj - g); return c; }
 
-  WB_HD double cell(double up, double left, double diag, const Row& r, const Col& c, int, int) const {
+  struct Dv {};
+  static constexpr bool kHasDv = false;
+  WB_HD Dv dv(int, int) const { return Dv(); }
+  WB_HD Dv dv_diag(int) const { return Dv(); }
+
+  WB_HD double cell(double up, double left, double diag, const Row& r, const Col& c, const Dv&) const {
     double v = fabs(r.xi - c.yj);
     return dmin2(diag + v, dmin2(up + r.gx, left + c.gy));
   }
@@ -211,7 +223,12 @@ struct EdrPolicy {
   WB_HD Row row(int, double xi, double) const { Row r; r.xi = xi; return r; }
   WB_HD Col col(int, double yj, double) const { Col c; c.yj = yj; return c; }
 
-  WB_HD double cell(double up, double left, double diag, const Row& r, const Col& c, int, int) const {
+  struct Dv {};
+  static constexpr bool kHasDv = false;
+  WB_HD Dv dv(int, int) const { return Dv(); }
+  WB_HD Dv dv_diag(int) const { return Dv(); }
+
+  WB_HD double cell(double up, double left, double diag, const Row& r, const Col& c, const Dv&) const {
     double v = fabs(r.xi - c.yj);
     double sub = diag + ((v < eps) ? 0.0 : 1.0);
     return dmin2(dmin2(sub, up + 1.0), left + 1.0);
@@ -260,16 +277,40 @@ struct MsmPolicy {
     unsigned u; memcpy(&u, &f, 4); return u;
 #endif
   }
+  // extra cost = c + (sign(a) != sign(b) ? 0 : min(|a|, |b|)).  NEG: the first operand is -a (the
+  // sign test is inverted instead of negating; a zero operand makes the minimum zero either way).
+  // Device: pinned with inline PTX to LOP3 (predicate out) + FMNMX + FSEL + one F2F -- left to
+  // the compiler the select migrates behind the conversion (two more 32-bit selects per call), and
+  // MSM is bound by exactly that pipe (profiles/r01c_ncu_msm_twe.md).
+  template <bool NEG>
   WB_HD double extra(float a, float b) const {
+#if defined(__CUDA_ARCH__)
+    float e;
+    if (NEG)
+      asm("{ .reg .pred p; .reg .b32 t; lop3.b32 t, %1, %2, 0x80000000, 0x28; setp.eq.u32 p, t, 0;"
+          " min.f32 %0, %3, %4; selp.f32 %0, 0f00000000, %0, p; }"
+          : "=f"(e) : "r"(fbits(a)), "r"(fbits(b)), "f"(fabsf(a)), "f"(fabsf(b)));
+    else
+      asm("{ .reg .pred p; .reg .b32 t; lop3.b32 t, %1, %2, 0x80000000, 0x28; setp.ne.u32 p, t, 0;"
+          " min.f32 %0, %3, %4; selp.f32 %0, 0f00000000, %0, p; }"
+          : "=f"(e) : "r"(fbits(a)), "r"(fbits(b)), "f"(fabsf(a)), "f"(fabsf(b)));
+    return c + (double)e;
+#else
     const float m = fminf(fabsf(a), fabsf(b));
-    const bool opposite = ((fbits(a) ^ fbits(b)) >> 31) != 0u;
+    const bool opposite = (((fbits(a) ^ fbits(b)) >> 31) != 0u) != NEG;
     return c + (double)(opposite ? 0.0f : m);
+#endif
   }
-  WB_HD double cell(double up, double left, double diag, const Row& r, const Col& cl, int, int) const {
+  struct Dv {};
+  static constexpr bool kHasDv = false;
+  WB_HD Dv dv(int, int) const { return Dv(); }
+  WB_HD Dv dv_diag(int) const { return Dv(); }
+
+  WB_HD double cell(double up, double left, double diag, const Row& r, const Col& cl, const Dv&) const {
     const float xy = r.xf - cl.yf;                  // (float)X[i] - (float)Y[j]
     const double a = diag + fabs(r.xi - cl.yj);
-    const double b = up + extra(r.dx, xy);          // _msm_cost(X[i], X[i-1], Y[j])
-    const double d = left + extra(-xy, cl.dy);      // _msm_cost(Y[j], X[i], Y[j-1])
+    const double b = up + extra<false>(r.dx, xy);   // _msm_cost(X[i], X[i-1], Y[j])
+    const double d = left + extra<true>(xy, cl.dy); // _msm_cost(Y[j], X[i], Y[j-1]): a = Y[j]-X[i] = -xy
     return dmin2(dmin2(a, b), d);
   }
   WB_HD double finish(double d, const Geom&) const { return d; }
@@ -284,7 +325,7 @@ struct TwePolicy {
   static constexpr bool kNeedPrevX = true;
   static constexpr bool kColumnMinBound = false;
   double pen;        // penalty + stiffness
-  const double* tw;  // tw[k] = (stiffness * 2) * k
+  const double* tw;  // CENTER of the signed table tw[d] = (stiffness * 2) * |d|, d = i - j
 
   WB_HD double prev_init() const { return WB_INF; }
   WB_HD double usent() const { return 0.0; }
@@ -298,10 +339,15 @@ struct TwePolicy {
   WB_HD Row row(int, double xi, double xim) const { Row r; r.xi = xi; r.xim = xim; r.dx = fabs(xim - xi); return r; }
   WB_HD Col col(int, double yj, double yjm) const { Col c; c.yj = yj; c.yjm = yjm; c.dy = fabs(yjm - yj); return c; }
 
-  WB_HD double cell(double up, double left, double diag, const Row& r, const Col& c, int i, int j) const {
+  struct Dv { double t; };
+  static constexpr bool kHasDv = true;
+  WB_HD Dv dv(int i, int j) const { return dv_diag(i - j); }
+  WB_HD Dv dv_diag(int d) const { Dv v; v.t = ldg(tw + d); return v; }
+
+  WB_HD double cell(double up, double left, double diag, const Row& r, const Col& c, const Dv& d) const {
     double del_x = (up + r.dx) + pen;
     double del_y = (left + c.dy) + pen;
-    double match = ((diag + fabs(r.xi - c.yj)) + fabs(r.xim - c.yjm)) + ldg(tw + iabs1(i - j));
+    double match = ((diag + fabs(r.xi - c.yj)) + fabs(r.xim - c.yjm)) + d.t;
     return dmin2(dmin2(del_x, del_y), match);
   }
   WB_HD double finish(double d, const Geom&) const { return d; }

@@ -12,17 +12,33 @@ inline int64_t compute_r(int64_t length, double r) {
   return (int64_t)std::fmax(std::floor((double)length * r), 1.0);
 }
 
+// Lookup tables indexed by the SIGNED diagonal offset d = i - j (so that the DP cell needs no
+// abs() and the strip engine's hot loop can address them as pointer + immediate):
+// t[center + d] = f(|d|) for |d| < n, with kTablePad zero entries on both sides -- the fast
+// path also evaluates the clipped columns of a partial last strip (results unused) and indexes up
+// to W-1 entries past the last meaningful one.  Kernels receive the pointer to the CENTER.
+constexpr int64_t kTablePad = 16;
+inline int64_t table_center(int64_t n) { return (n > 0 ? n : 0) + kTablePad; }
+
 // EL:3339-3341 (wdtw/wlcss: n = max(Tx,Ty)), EL:3418-3428 (wddtw: n = max(Tx,Ty) - 2)
 inline std::vector<double> make_weights(double g, int64_t n) {
-  std::vector<double> w((size_t)(n > 0 ? n : 0));
-  for (int64_t i = 0; i < n; i++) w[(size_t)i] = 1.0 / (1.0 + std::exp(-g * ((double)i - (double)n / 2.0)));
+  const int64_t c = table_center(n);
+  std::vector<double> w((size_t)(2 * c + 1), 0.0);
+  for (int64_t i = 0; i < n; i++) {
+    const double v = 1.0 / (1.0 + std::exp(-g * ((double)i - (double)n / 2.0)));
+    w[(size_t)(c + i)] = v; w[(size_t)(c - i)] = v;
+  }
   return w;
 }
 
 // EL:1813: stiffness * 2 * labs(i - j)
 inline std::vector<double> make_tw(double stiffness, int64_t n) {
-  std::vector<double> t((size_t)(n > 0 ? n : 0));
-  for (int64_t k = 0; k < n; k++) t[(size_t)k] = stiffness * 2 * (double)k;
+  const int64_t c = table_center(n);
+  std::vector<double> t((size_t)(2 * c + 1), 0.0);
+  for (int64_t k = 0; k < n; k++) {
+    const double v = stiffness * 2 * (double)k;
+    t[(size_t)(c + k)] = v; t[(size_t)(c - k)] = v;
+  }
   return t;
 }
 

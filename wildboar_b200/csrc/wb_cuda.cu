@@ -93,26 +93,27 @@ static int64_t cells_per_pair(int Tx, int Ty, int R) {
   return c;
 }
 
-// Strip-kernel configurations (measured on B200: profiles/r01_variants.md, r01_variants3.log).
-//   NARROW (H < 32)        : W = 8 (W = 4 for 8 <= H < 16), NR = 2, rings in SHARED memory, two CTAs
-//                            of 8 warps per SM (<= 128 regs).
-//   L2 (H >= 32, NS <= 220): rings in GLOBAL memory (L2 resident: 148 SMs x warps x NS x 256 B
-//                            stays under the 126 MB L2), W = WL, NR = 4, NWL warps per SM.
-//   TALL (NS > 220)        : rings in global memory, wider strips (W = WT: half the ring traffic
-//                            per cell), 8 warps per SM so the rings still mostly fit in L2.
-// Shared-memory rings cap cfg3 at 8 warps per SM (816 B per pair); the global ring lifts that
-// to 12 and is what makes T = 4096 bands (3.3 KB per pair) run at all.
-template <class M> struct StripCfg { static constexpr int WL = 8, NWL = 12, WT = 16; };
-template <> struct StripCfg<DtwPolicy<false, false>> { static constexpr int WL = 12, NWL = 12, WT = 16; };
-template <> struct StripCfg<LcssPolicy<false>> { static constexpr int WL = 12, NWL = 12, WT = 16; };
-template <> struct StripCfg<DtwPolicy<false, true>> { static constexpr int WL = 8, NWL = 12, WT = 12; };
-template <> struct StripCfg<TwePolicy> { static constexpr int WL = 8, NWL = 8, WT = 12; };
+// Strip-kernel configurations (measured on B200: profiles/r01c_variants.md).
+//   NARROW (H < 32)       : W = 8 (W = 4 for 8 <= H < 16), NR = 2, boundary buffers in SHARED memory,
+//                           two CTAs of 8 warps per SM.
+//   L2 (32 <= H <= 219)   : boundary buffers in GLOBAL memory (L2 resident: 148 SMs x warps x slots x
+//                           256 B stays well under the 126 MB L2), per-policy (W, NR, warps).
+//   TALL (H > 219)        : global buffers, W = 8, NR = 4, 16 warps per SM (the buffers no longer fit
+//                           in L2; more warps hide the extra latency).
+// Shared-memory buffers would cap cfg3 at 6-7 warps per SM (33 KB per warp); the global buffers
+// lift that to 12-16 and are what makes T = 4096 bands (110 KB per warp) run at all.
+template <class M> struct StripCfg { static constexpr int WL = 12, NRL = 6, NWL = 12; };
+template <> struct StripCfg<DtwPolicy<false, false>> { static constexpr int WL = 10, NRL = 6, NWL = 14; };
+template <> struct StripCfg<TwePolicy> { static constexpr int WL = 12, NRL = 4, NWL = 12; };
+template <> struct StripCfg<MsmPolicy> { static constexpr int WL = 8, NRL = 4, NWL = 16; };
 
 template <class M, int W, int NT, int MINB, bool EA, int NR, bool GRING>
-static int launch_strip_cfg(Workspace& ws, KArgs a, const M& m, int nwarps, int sms, int* w_used) {
+static int launch_strip_cfg(Workspace& ws, KArgs a, const M& m, int nwarps, int sms, size_t smem_cap, wb_stats* cfg) {
   cudaStream_t st = ws.stream;
   auto kern = k_strip<M, W, NT, MINB, EA, NR, GRING>;
+  a.NS = strip_ring_slots(a.g, W);
   const size_t per_warp = (size_t)a.NS * 32 * sizeof(double);
+  if (!GRING) nwarps = (int)std::max<size_t>(1, std::min<size_t>((size_t)nwarps, smem_cap / per_warp));
   size_t smem = GRING ? 0 : (size_t)nwarps * per_warp;
   if (!GRING) WB_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
@@ -126,29 +127,28 @@ static int launch_strip_cfg(Workspace& ws, KArgs a, const M& m, int nwarps, int 
     if (ws.alloc(&ring, (size_t)grid * nwarps * a.NS * 32)) return 1;
     a.gring = ring;
   }
-  *w_used = W;
+  if (cfg) { cfg->strip_w = W; cfg->strip_nr = NR; cfg->strip_warps = nwarps; cfg->strip_gring = GRING ? 1 : 0; }
   kern<<<(unsigned)grid, nwarps * 32, smem, st>>>(a, m);
   WB_CK(cudaGetLastError());
   return 0;
 }
 
 template <class M, bool EA>
-static int launch_strip(Workspace& ws, const KArgs& a, const M& m, size_t smem_cap, int sms, int* w_used) {
-  const size_t per_warp = (size_t)a.NS * 32 * sizeof(double);
+static int launch_strip(Workspace& ws, const KArgs& a, const M& m, size_t smem_cap, int sms, wb_stats* cfg) {
   using C = StripCfg<M>;
+  const size_t per_warp = (size_t)strip_ring_slots(a.g, 16) * 32 * sizeof(double);  // widest strips
   if (a.g.H >= 32) {
     // keep the global rings of one launch below ~8 GB whatever the series length
     const size_t ring_budget = (size_t)8 << 30;
     int cap = (int)std::max<size_t>(1, ring_budget / (per_warp * (size_t)sms));
-    if (a.NS <= 220 && a.g.H >= 2 * C::WL)
-      return launch_strip_cfg<M, C::WL, C::NWL * 32, 1, EA, 4, true>(ws, a, m, std::min(C::NWL, cap), sms, w_used);
-    if (a.g.H >= 2 * C::WT)
-      return launch_strip_cfg<M, C::WT, 256, 1, EA, 4, true>(ws, a, m, std::min(8, cap), sms, w_used);
-    return launch_strip_cfg<M, 8, 256, 2, EA, 2, true>(ws, a, m, std::min(8, cap), sms, w_used);
+    if (a.g.H <= 219 && a.g.H >= 2 * C::WL)
+      return launch_strip_cfg<M, C::WL, C::NWL * 32, 1, EA, C::NRL, true>(ws, a, m, std::min(C::NWL, cap), sms, smem_cap, cfg);
+    if (a.g.H > 219)
+      return launch_strip_cfg<M, 8, 512, 1, EA, 4, true>(ws, a, m, std::min(16, cap), sms, smem_cap, cfg);
+    return launch_strip_cfg<M, 8, 256, 2, EA, 2, true>(ws, a, m, std::min(8, cap), sms, smem_cap, cfg);
   }
-  const int nw = (int)std::max<size_t>(1, std::min<size_t>(8, smem_cap / per_warp));
-  if (a.g.H >= 16 || a.g.H < 8) return launch_strip_cfg<M, 8, 256, 2, EA, 2, false>(ws, a, m, nw, sms, w_used);
-  return launch_strip_cfg<M, 4, 256, 2, EA, 2, false>(ws, a, m, nw, sms, w_used);
+  if (a.g.H >= 16 || a.g.H < 8) return launch_strip_cfg<M, 8, 256, 2, EA, 2, false>(ws, a, m, 8, sms, smem_cap, cfg);
+  return launch_strip_cfg<M, 4, 256, 2, EA, 2, false>(ws, a, m, 8, sms, smem_cap, cfg);
 }
 
 // What one DP launch needs to know.
@@ -199,12 +199,14 @@ static int prepare_operands(Workspace& ws, DpCall& c) {
   if (c.metric == M_EDR && c.ea) c.R = (int)compute_r(c.Tx, c.p.r);
   const int nmax = std::max(c.ptx, c.pty);
   if (c.metric == M_WDTW || c.metric == M_WLCSS || c.metric == M_WDDTW || c.metric == M_TWE) {
-    ws.host_keep.push_back(c.metric == M_TWE ? make_tw(c.p.stiffness, nmax + 1) : make_weights(c.p.g, nmax));
+    // signed tables (index = i - j); kernels get the pointer to the centre entry
+    const int64_t tn = c.metric == M_TWE ? nmax + 1 : nmax;
+    ws.host_keep.push_back(c.metric == M_TWE ? make_tw(c.p.stiffness, tn) : make_weights(c.p.g, tn));
     std::vector<double>& h = ws.host_keep.back();
     double* d = nullptr;
     if (ws.alloc(&d, h.size())) return 1;
     WB_CK(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (c.metric == M_TWE) c.tab.tw = d; else c.tab.weights = d;
+    if (c.metric == M_TWE) c.tab.tw = d + table_center(tn); else c.tab.weights = d + table_center(tn);
   }
   if (c.metric == M_ERP || (c.metric == M_EDR && std::isnan(c.p.epsilon))) {
     const int kind = c.metric == M_ERP ? 0 : 1;
@@ -250,8 +252,6 @@ static int launch_dp(Workspace& ws, const DeviceInfo& di, const DpCall& c, long 
   WB_CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
   a.counter = counter;
 
-  a.NS = strip_ring_slots(a.g);
-  const size_t per_warp = (size_t)a.NS * 32 * sizeof(double);
   const size_t smem_cap = (size_t)di.max_smem_optin;
   int engine = 0;
   int rc = 0;
@@ -263,11 +263,10 @@ static int launch_dp(Workspace& ws, const DeviceInfo& di, const DpCall& c, long 
     if (c.p.engine == 2 && !strip_ok) { set_err("strip engine forced but not applicable"); rc = 1; return; }
     if (strip_ok) {
       engine = 2;
-      int w_used = 0;
       if constexpr (M::kColumnMinBound) {
-        if (thr) { rc = launch_strip<M, true>(ws, a, m, smem_cap, di.sms, &w_used); return; }
+        if (thr) { rc = launch_strip<M, true>(ws, a, m, smem_cap, di.sms, stats); return; }
       }
-      rc = launch_strip<M, false>(ws, a, m, smem_cap, di.sms, &w_used);
+      rc = launch_strip<M, false>(ws, a, m, smem_cap, di.sms, stats);
     } else {
       engine = 1;
       constexpr int NT = 128;
@@ -516,6 +515,7 @@ static int run_host_job(const HostJob& J, const int* devices, int n_devices, wb_
       stats->cells += sts[b].cells; stats->pairs += sts[b].pairs; stats->launches += sts[b].launches;
       stats->lb_kim_pruned += sts[b].lb_kim_pruned; stats->lb_keogh_pruned += sts[b].lb_keogh_pruned;
       stats->engine = std::max(stats->engine, sts[b].engine);
+      if (sts[b].strip_w) { stats->strip_w = sts[b].strip_w; stats->strip_nr = sts[b].strip_nr; stats->strip_warps = sts[b].strip_warps; stats->strip_gring = sts[b].strip_gring; }
     }
   }
   return 0;
