@@ -96,9 +96,9 @@ static int64_t cells_per_pair(int Tx, int Ty, int R) {
 // Strip-kernel configurations (measured on B200: profiles/r01c_variants.md).
 //   NARROW (H < 32)       : W = 8 (W = 4 for 8 <= H < 16), NR = 2, boundary buffers in SHARED memory,
 //                           two CTAs of 8 warps per SM.
-//   L2 (32 <= H <= 219)   : boundary buffers in GLOBAL memory (L2 resident: 148 SMs x warps x slots x
+//   L2 (H >= 32, <= 230 slots): boundary buffers in GLOBAL memory (L2 resident: 148 SMs x warps x slots x
 //                           256 B stays well under the 126 MB L2), per-policy (W, NR, warps).
-//   TALL (H > 219)        : global buffers, W = 8, NR = 4, 16 warps per SM (the buffers no longer fit
+//   TALL (> 230 slots)    : global buffers, W = 8, NR = 4, 16 warps per SM (the buffers no longer fit
 //                           in L2; more warps hide the extra latency).
 // Shared-memory buffers would cap cfg3 at 6-7 warps per SM (33 KB per warp); the global buffers
 // lift that to 12-16 and are what makes T = 4096 bands (110 KB per warp) run at all.
@@ -141,9 +141,10 @@ static int launch_strip(Workspace& ws, const KArgs& a, const M& m, size_t smem_c
     // keep the global rings of one launch below ~8 GB whatever the series length
     const size_t ring_budget = (size_t)8 << 30;
     int cap = (int)std::max<size_t>(1, ring_budget / (per_warp * (size_t)sms));
-    if (a.g.H <= 219 && a.g.H >= 2 * C::WL)
+    const bool fits_l2 = strip_ring_slots(a.g, C::WL) <= 230;  // slots are bounded by Tx as well as by H
+    if (fits_l2 && a.g.H >= 2 * C::WL)
       return launch_strip_cfg<M, C::WL, C::NWL * 32, 1, EA, C::NRL, true>(ws, a, m, std::min(C::NWL, cap), sms, smem_cap, cfg);
-    if (a.g.H > 219)
+    if (!fits_l2)
       return launch_strip_cfg<M, 8, 512, 1, EA, 4, true>(ws, a, m, std::min(16, cap), sms, smem_cap, cfg);
     return launch_strip_cfg<M, 8, 256, 2, EA, 2, true>(ws, a, m, std::min(8, cap), sms, smem_cap, cfg);
   }
