@@ -188,6 +188,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOAD))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"],
+                    help="fp64 = bit-exact mode (the driver's bench line); fp32 = the optional fp32 mode (extra evidence only)")
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--profile-rows", type=int, default=0,
                     help="PROFILING ONLY (ncu): shrink the x row count so ~40 kernel replays stay short; "
@@ -228,6 +230,8 @@ def main():
     metric, r, T = wl["metric"], wl["r"], wl["T"]
     mid = _shim.METRIC_IDS[metric]
     params = wb.check_metric(metric)(r=r)._params()
+    params.precision = 1 if args.precision == "fp32" else 0
+    wb.set_precision(args.precision)
     lo, hi = row_block(wl["nx"], world, rank)
     x_h = random_walks(wl["nx"], T, 1)[lo:hi].copy()
     y_h = random_walks(wl["ny"], T, 2)
@@ -296,22 +300,30 @@ def main():
         ops = FP64_OPS_PER_CELL[metric]
         achieved = cells_rank * ops / (kernel_ms * 1e-3) / 1e9  # G FP64-pipe lane-instructions / s, this GPU
         nominal = 148 * 64 * 1.965  # G lane-inst/s at max boost
+        if args.precision == "fp32":
+            # optional fp32 mode: 3 instructions per dtw cell (FADD, FMNMX3, FFMA) against the nominal
+            # FP32 issue rate 148 SMs x 128 lanes x 1.965 GHz (no in-run microbenchmark for this mode)
+            ops = 3 if metric in ("dtw", "ddtw") else ops
+            achieved = cells_rank * ops / (kernel_ms * 1e-3) / 1e9
+            nominal = 148 * 128 * 1.965
+            peak_inst = nominal * 1e9
         line = {
             "metric": "pairwise_elastic_distance_gcups", "value": value, "unit": "GCUPS", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64" if args.precision == "fp64" else "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "workload_id": args.workload, "cells_per_pair": cpp,
                        "pairs": wl["nx"] * ny, "sharding": f"x rows in {world} contiguous blocks, y replicated, no collective",
-                       "l2": "256 MB buffer written between timed iterations (L2 flush)", "mode": "fp64 bit-exact (-fmad=false)"},
+                       "l2": "256 MB buffer written between timed iterations (L2 flush)", "mode": "fp64 bit-exact (-fmad=false)" if args.precision == "fp64" else "optional fp32 mode (<= 1e-4 relative)"},
             "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": int((nx + ny) * T * 8),
                     "d2h_bytes_per_step": int(nx * ny * 8), "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "api": "wildboar_b200.pairwise_distance(numpy, numpy) -> numpy", "device_ms_last_call": e2e_stats["total_ms"]},
             "gpu_launches": int(args.steps * st["launches"]),
             "clocks": clocks,
             "roofline": {
-                "bound": "fp64_alu", "kernel": _kernel_label(metric, st), "achieved": achieved, "peak": peak_inst / 1e9,
+                "bound": "fp64_alu" if args.precision == "fp64" else "fp32_alu", "kernel": _kernel_label(metric, st), "achieved": achieved, "peak": peak_inst / 1e9,
                 "unit": "G FP64-pipe lane-inst/s", "frac": achieved / (peak_inst / 1e9),
-                "peak_source": "measured in this run: wb_cuda_fp64_peak(mix=0), DADD issue rate, all SMs",
+                "peak_source": ("measured in this run: wb_cuda_fp64_peak(mix=0), DADD issue rate, all SMs" if args.precision == "fp64"
+                                else "nominal FP32 issue rate 148 x 128 lanes x 1.965 GHz"),
                 "ops_per_cell": ops, "kernel_ms": kernel_ms, "kernel_gcups": cells_rank / (kernel_ms * 1e-3) / 1e9,
                 "nominal_peak": nominal, "frac_of_nominal": achieved / nominal,
                 "dtw_mix_peak": peak_mix / 1e9, "frac_of_dtw_mix_peak": achieved / (peak_mix / 1e9),

@@ -50,7 +50,8 @@ typedef struct wb_params {
   double penalty;   /* twe                                                         */
   double stiffness; /* twe                                                         */
   int32_t engine;   /* 0 auto, 1 force row-scan engine, 2 force strip engine       */
-  int32_t reserved;
+  int32_t precision; /* 0: fp64, bit-equal to the reference (default); 1: fp32 arithmetic (<= 1e-4 relative;
+                        lcss / wlcss / edr always run in fp64)                                         */
 } wb_params;
 
 /* timing / work counters of the last call (optional out-parameter) */

@@ -12,7 +12,7 @@ _ROOT = os.path.join(_HERE, "..", "..")
 
 class WbParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("r", "g", "p", "c", "epsilon", "penalty", "stiffness")] + [
-        ("engine", C.c_int32), ("reserved", C.c_int32)]
+        ("engine", C.c_int32), ("precision", C.c_int32)]
 
 
 def build(force=False):

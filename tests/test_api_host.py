@@ -77,3 +77,23 @@ def test_metric_objects_pickle(wb):
         m = cls()
         m2 = pickle.loads(pickle.dumps(m))
         assert type(m2) is cls and m2.__reduce__()[1] == m.__reduce__()[1] or name == "edr"
+
+
+def test_precision_switch(wb, monkeypatch):
+    """set_precision / WILDBOAR_CUDA_PRECISION stamp the C-ABI parameter block (no compute here)."""
+    from wildboar_b200 import _shim
+    p = wb.check_metric("dtw")(r=0.1)._params()
+    assert _shim.apply_engine_override(p).precision == 0
+    wb.set_precision("fp32")
+    try:
+        assert _shim.apply_engine_override(p).precision == 1 and wb.get_precision() == "fp32"
+    finally:
+        wb.set_precision(None)
+    monkeypatch.setenv("WILDBOAR_CUDA_PRECISION", "fp32")
+    assert _shim.apply_engine_override(p).precision == 1
+    monkeypatch.setenv("WILDBOAR_CUDA_PRECISION", "bf16")
+    import pytest
+    with pytest.raises(ValueError):
+        wb.get_precision()
+    with pytest.raises(ValueError):
+        wb.set_precision("fp16")

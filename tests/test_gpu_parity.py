@@ -230,3 +230,70 @@ def test_multi_gpu_row_sharding_is_transparent(W, oracle):
             _eq(i, oi, metric + " argmin idx"); _eq(d, od, metric + " argmin dist")
     finally:
         W.set_devices([0])
+
+
+# ---------------------------------------------------------------------------------------------
+# optional fp32 mode (north star: <= 1e-4 relative error against the reference's fp64 values)
+# ---------------------------------------------------------------------------------------------
+FP32_RTOL = 1e-4
+FP32_METRICS = ["dtw", "ddtw", "wdtw", "wddtw", "adtw", "erp", "msm", "twe"]
+
+
+@pytest.fixture
+def fp32(W):
+    W.set_precision("fp32")
+    yield W
+    W.set_precision(None)
+
+
+def _close32(got, want, what):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape and got.dtype == np.float64, what
+    err = np.abs(got - want) / np.maximum(np.abs(want), 1e-30)
+    err = np.where(want == 0, np.abs(got), err)
+    assert err.max() <= FP32_RTOL, (what, float(err.max()))
+    return float(err.max())
+
+
+@pytest.mark.parametrize("metric", FP32_METRICS)
+def test_fp32_mode_within_tolerance(fp32, oracle, metric):
+    """fp32 arithmetic, float64 in / float64 out: pairwise (both engines' geometries), singleton, paired."""
+    for (nx, ny, Tx, Ty, r) in [(48, 100, 140, 140, 1.0), (40, 70, 256, 256, 0.05), (30, 45, 50, 77, 0.2), (6, 40, 3, 9, 0.5)]:
+        if metric == "wddtw" and Tx > Ty:
+            continue
+        x, y = random_walks(nx, Tx, 11), random_walks(ny, Ty, 12)
+        _close32(fp32.pairwise_distance(x, y, metric=metric, metric_params={"r": r}),
+                 oracle.pairwise(metric, x, y, r=r, n_jobs=0), f"{metric} {Tx}x{Ty} r={r}")
+    X = random_walks(120, 140, 13)
+    _close32(fp32.pairwise_distance(X, metric=metric), oracle.pairwise(metric, X, None, n_jobs=0), metric + " singleton")
+    _close32(fp32.paired_distance(X[:60], X[60:], metric=metric), oracle.paired(metric, X[:60], X[60:], n_jobs=0), metric + " paired")
+    assert fp32.get_precision() == "fp32"
+
+
+def test_fp32_mode_cfg3_and_cfg5_shapes(fp32, oracle):
+    x, y = random_walks(10000, 512, 1)[:32], random_walks(10000, 512, 2)[:200]
+    _close32(fp32.pairwise_distance(x, y, metric="dtw", metric_params={"r": 0.1}), oracle.pairwise("dtw", x, y, r=0.1, n_jobs=0), "cfg3 fp32")
+    x, y = random_walks(2000, 4096, 1)[:4], random_walks(2000, 4096, 2)[:40]
+    for metric in ("msm", "twe"):
+        _close32(fp32.pairwise_distance(x, y, metric=metric, metric_params={"r": 0.05}),
+                 oracle.pairwise(metric, x, y, r=0.05, n_jobs=0), f"cfg5 {metric} fp32")
+
+
+@pytest.mark.parametrize("metric", ["lcss", "wlcss", "edr"])
+def test_fp32_mode_keeps_threshold_metrics_exact(fp32, oracle, metric):
+    """lcss / wlcss / edr are step functions of |x-y| vs eps: they stay in fp64 (bit-equal) in fp32 mode."""
+    x, y = random_walks(40, 90, 7), random_walks(70, 90, 8)
+    _eq(fp32.pairwise_distance(x, y, metric=metric, metric_params={"r": 0.3}), oracle.pairwise(metric, x, y, r=0.3, n_jobs=0), metric)
+
+
+def test_fp32_argmin_indices_on_separated_data(fp32, oracle):
+    """argmin in fp32 mode: distances within tolerance; indices equal wherever the fp64 margin between the
+    best and the runner-up exceeds the tolerance."""
+    q, refs = random_walks(64, 128, 21), random_walks(500, 128, 22)
+    idx, dist = fp32.argmin_distance(q, refs, k=1, metric="dtw", metric_params={"r": 0.1}, return_distance=True)
+    full = oracle.pairwise("dtw", q, refs, r=0.1, n_jobs=0)
+    srt = np.sort(full, axis=1)
+    clear = (srt[:, 1] - srt[:, 0]) > 4 * FP32_RTOL * srt[:, 1]
+    assert clear.sum() > 32
+    assert np.array_equal(idx[clear, 0], np.argmin(full, axis=1)[clear])
+    _close32(dist[:, 0], full[np.arange(len(q)), idx[:, 0]], "argmin fp32 distances")

@@ -14,9 +14,9 @@ from .distance import (  # noqa: F401
     paired_distance,
     pairwise_distance,
 )
-from ._shim import device_count, last_stats, library_path, set_devices  # noqa: F401
+from ._shim import device_count, get_precision, last_stats, library_path, set_devices, set_precision  # noqa: F401
 
 __all__ = [
     "pairwise_distance", "paired_distance", "argmin_distance", "check_metric",
-    "device_count", "set_devices", "last_stats", "library_path",
+    "device_count", "set_devices", "set_precision", "get_precision", "last_stats", "library_path",
 ]

@@ -21,7 +21,7 @@ METRIC_IDS = {
 
 class WbParams(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("r", "g", "p", "c", "epsilon", "penalty", "stiffness")] + [
-        ("engine", C.c_int32), ("reserved", C.c_int32)]
+        ("engine", C.c_int32), ("precision", C.c_int32)]
 
 
 class WbStats(C.Structure):
@@ -100,15 +100,38 @@ def _resolve_devices(work_cells):
     return [0]
 
 
+_precision = None
+
+
+def set_precision(precision):
+    """Arithmetic of the DP kernels: "fp64" (default: bit-equal to the reference) or "fp32"
+    (optional mode of the north star: <= 1e-4 relative error, about 3x the throughput; lcss, wlcss and
+    edr are step functions of a threshold test and always run in fp64).  None = take
+    WILDBOAR_CUDA_PRECISION from the environment (default fp64)."""
+    global _precision
+    if precision is not None and precision not in ("fp64", "fp32"):
+        raise ValueError("precision must be 'fp64', 'fp32' or None")
+    _precision = precision
+
+
+def get_precision():
+    p = _precision if _precision is not None else os.environ.get("WILDBOAR_CUDA_PRECISION", "fp64").strip().lower()
+    if p not in ("fp64", "fp32"):
+        raise ValueError("WILDBOAR_CUDA_PRECISION must be fp64 or fp32")
+    return p
+
+
 def last_stats():
     """wb_stats of the last call on this thread (dict) or None."""
     return getattr(_tls, "stats", None)
 
 
 def apply_engine_override(params):
-    """WILDBOAR_CUDA_ENGINE=rowscan|strip forces one DP engine (testing / cross-checks)."""
+    """WILDBOAR_CUDA_ENGINE=rowscan|strip forces one DP engine (testing / cross-checks); also
+    stamps the selected precision into the parameter block."""
     e = os.environ.get("WILDBOAR_CUDA_ENGINE", "").strip().lower()
     params.engine = {"rowscan": 1, "strip": 2}.get(e, 0)
+    params.precision = 1 if get_precision() == "fp32" else 0
     return params
 
 

@@ -5,14 +5,20 @@
 
 namespace wb {
 
-struct Tables {
-  const double* weights;  // wdtw / wddtw / wlcss
-  const double* tw;       // twe
+template <class F>
+struct TablesT {
+  const F* weights;  // wdtw / wddtw / wlcss (centre of the signed table)
+  const F* tw;       // twe (centre of the signed table)
 };
+using Tables = TablesT<double>;
+
+// metrics with an fp32 variant (lcss / wlcss / edr are step functions of a threshold test and
+// always run in double)
+inline bool has_fp32_variant(int metric) { return !(metric == M_LCSS || metric == M_WLCSS || metric == M_EDR); }
 
 // Calls f(policy) with the policy object for `metric`; returns false for an unknown id.
-template <class F>
-inline bool with_policy(int metric, const wb_params& p, const Tables& t, F&& f) {
+template <class Fn>
+inline bool with_policy(int metric, const wb_params& p, const Tables& t, Fn&& f) {
   switch (metric) {
     case M_DTW: case M_DDTW: { DtwPolicy<false, false> m; m.w = nullptr; m.p = 0; f(m); return true; }
     case M_WDTW: case M_WDDTW: { DtwPolicy<true, false> m; m.w = t.weights; m.p = 0; f(m); return true; }
@@ -23,6 +29,20 @@ inline bool with_policy(int metric, const wb_params& p, const Tables& t, F&& f) 
     case M_EDR: { EdrPolicy m; m.eps_param = p.epsilon; m.eps = p.epsilon; f(m); return true; }
     case M_MSM: { MsmPolicy m; m.cf = (float)p.c; m.c = (double)m.cf; f(m); return true; }
     case M_TWE: { TwePolicy m; m.pen = p.penalty + p.stiffness; m.tw = t.tw; f(m); return true; }
+  }
+  return false;
+}
+
+// fp32 mode: same policies instantiated for float
+template <class Fn>
+inline bool with_policy_f32(int metric, const wb_params& p, const TablesT<float>& t, Fn&& f) {
+  switch (metric) {
+    case M_DTW: case M_DDTW: { DtwPolicy<false, false, float> m; m.w = nullptr; m.p = 0; f(m); return true; }
+    case M_WDTW: case M_WDDTW: { DtwPolicy<true, false, float> m; m.w = t.weights; m.p = 0; f(m); return true; }
+    case M_ADTW: { DtwPolicy<false, true, float> m; m.w = nullptr; m.p = (float)p.p; f(m); return true; }
+    case M_ERP: { ErpPolicyT<float> m; m.g = (float)p.g; m.gx_sum = 0; m.gy_sum = 0; f(m); return true; }
+    case M_MSM: { MsmPolicyT<float> m; m.cf = (float)p.c; m.c = m.cf; f(m); return true; }
+    case M_TWE: { TwePolicyT<float> m; m.pen = (float)(p.penalty + p.stiffness); m.tw = t.tw; f(m); return true; }
   }
   return false;
 }

@@ -21,27 +21,28 @@ template <class M> struct EaFromRow1 { static constexpr bool value = M::kColumnM
 // min_dist: abandon when a checked row's minimum exceeds it (raw dp domain); WB_INF disables.
 // row_min_max (optional): max over checked rows of the row minimum (for replay).
 template <class M>
-WB_HD double rowscan_pair(const Geom& g, const M& m, const double* __restrict__ x,
-                          const double* __restrict__ y, double* b0, double* b1, long long bs,
-                          double min_dist, double* row_min_max) {
+WB_HD typename M::real rowscan_pair(const Geom& g, const M& m, const typename M::real* __restrict__ x,
+                                    const typename M::real* __restrict__ y, typename M::real* b0, typename M::real* b1,
+                                    long long bs, typename M::real min_dist, typename M::real* row_min_max) {
+  using F = typename M::real;
   const int Tx = g.Tx, Ty = g.Ty;
-  double* prev = b0;
-  double* cost = b1;
-  double mmax = -WB_INF;
+  F* prev = b0;
+  F* cost = b1;
+  F mmax = -Num<F>::inf();
   int i_first = 0;
-  double cy = 0.0;
+  F cy = F(0);
 
   if (M::kMsmBand) {
     // explicit first row incl. the one cell beyond the band (EL:1611-1617); first column is
     // the running sum cy (EL:1620-1622)
-    typename M::Row r0 = m.row(0, x[0], 0.0);
-    typename M::Col c0 = m.col(0, y[0], 0.0);
-    double v = m.cell(WB_INF, WB_INF, 0.0, r0, c0, m.dv(0, 0));
+    typename M::Row r0 = m.row(0, x[0], F(0));
+    typename M::Col c0 = m.col(0, y[0], F(0));
+    F v = m.cell(Num<F>::inf(), Num<F>::inf(), F(0), r0, c0, m.dv(0, 0));
     prev[0] = v;
     int n0 = imin2(Ty, g.max_len + 1);
     for (int j = 1; j < n0; ++j) {
       typename M::Col cj = m.col(j, y[j], y[j - 1]);
-      v = m.cell(WB_INF, v, WB_INF, r0, cj, m.dv(0, j));
+      v = m.cell(Num<F>::inf(), v, Num<F>::inf(), r0, cj, m.dv(0, j));
       prev[(long long)j * bs] = v;
     }
     cy = prev[0];
@@ -55,14 +56,14 @@ WB_HD double rowscan_pair(const Geom& g, const M& m, const double* __restrict__ 
   for (int i = i_first; i < Tx; ++i) {
     int js = imax2(0, i - g.a);
     const int je = imin2(Ty, i + g.max_len);
-    const double xi = x[i];
-    const double xim = (i > 0) ? x[i - 1] : 0.0;
+    const F xi = x[i];
+    const F xim = (i > 0) ? x[i - 1] : F(0);
     const typename M::Row rw = m.row(i, xi, xim);
-    double rowmin = WB_INF;
-    double left, diag;
+    F rowmin = Num<F>::inf();
+    F left, diag;
     if (M::kMsmBand) {
-      typename M::Col c0 = m.col(0, y[0], 0.0);
-      cy = m.cell(cy, WB_INF, WB_INF, rw, c0, m.dv(i, 0));  // up-branch only: cy[i-1] + cost(X[i],X[i-1],Y[0])
+      typename M::Col c0 = m.col(0, y[0], F(0));
+      cy = m.cell(cy, Num<F>::inf(), Num<F>::inf(), rw, c0, m.dv(i, 0));  // up-branch only: cy[i-1] + cost(X[i],X[i-1],Y[0])
       cost[0] = cy;
       rowmin = cy;
       js = imax2(1, js);
@@ -79,11 +80,11 @@ WB_HD double rowscan_pair(const Geom& g, const M& m, const double* __restrict__ 
       }
     }
     for (int j = js; j < je; ++j) {
-      const double up = prev[(long long)j * bs];
-      const double yj = y[j];
-      const double yjm = (j > 0) ? y[j - 1] : 0.0;
+      const F up = prev[(long long)j * bs];
+      const F yj = y[j];
+      const F yjm = (j > 0) ? y[j - 1] : F(0);
       const typename M::Col cj = m.col(j, yj, yjm);
-      const double d = m.cell(up, left, diag, rw, cj, m.dv(i, j));
+      const F d = m.cell(up, left, diag, rw, cj, m.dv(i, j));
       cost[(long long)j * bs] = d;
       rowmin = dmin2(rowmin, d);
       left = d;
@@ -91,10 +92,10 @@ WB_HD double rowscan_pair(const Geom& g, const M& m, const double* __restrict__ 
     }
     if (!(EaFromRow1<M>::value && i == 0)) {
       mmax = dmax2(mmax, rowmin);
-      if (rowmin > min_dist) { if (row_min_max) *row_min_max = mmax; return WB_INF; }
+      if (rowmin > min_dist) { if (row_min_max) *row_min_max = mmax; return Num<F>::inf(); }
     }
     if (je < Ty) cost[(long long)je * bs] = m.usent();
-    double* t = cost; cost = prev; prev = t;
+    F* t = cost; cost = prev; prev = t;
   }
   if (row_min_max) *row_min_max = mmax;
   return m.finish(prev[(long long)(Ty - 1) * bs], g);

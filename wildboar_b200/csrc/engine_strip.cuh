@@ -61,10 +61,19 @@ WB_HD int strip_ilo(const Geom& g, int j0) {
 
 // Opaque select: keeps the compiler from turning a chain of register selects into a
 // dynamically indexed (local-memory) array access.
-WB_HD double sel_f64(bool p, double a, double b) {
+WB_HD double sel_real(bool p, double a, double b) {
 #if defined(__CUDA_ARCH__)
   double r;
   asm("{ .reg .pred q; setp.ne.s32 q, %3, 0; selp.f64 %0, %1, %2, q; }" : "=d"(r) : "d"(a), "d"(b), "r"((int)p));
+  return r;
+#else
+  return p ? a : b;
+#endif
+}
+WB_HD float sel_real(bool p, float a, float b) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("{ .reg .pred q; setp.ne.s32 q, %3, 0; selp.f32 %0, %1, %2, q; }" : "=f"(r) : "f"(a), "f"(b), "r"((int)p));
   return r;
 #else
   return p ? a : b;
@@ -83,12 +92,14 @@ WB_HD double sel_f64(bool p, double a, double b) {
 // the predicate-free `fast path`, NR rows per iteration so that NR independent left->right
 // dependency chains are in flight per thread.
 template <class M, int W, bool EA, int NR = 2, int BS = 0>
-WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
-                        const double* __restrict__ y, double* bnd, int bs_rt, double abandon) {
+WB_HD typename M::real strip_pair(const Geom& g, const M& m, const typename M::real* __restrict__ x,
+                                  const typename M::real* __restrict__ y, typename M::real* bnd, int bs_rt,
+                                  typename M::real abandon) {
+  using F = typename M::real;  // F: bit-exact mode; float: fp32 mode
   const int Tx = g.Tx, Ty = g.Ty;
   const long long bs = BS > 0 ? BS : bs_rt;
-  double result = 0.0;
-  const double left0c = m.left0(1);
+  F result = F(0);
+  const F left0c = m.left0(1);
 
   for (int j0 = 0; j0 < Ty; j0 += W) {
     const int wv = imin2(W, Ty - j0);
@@ -100,22 +111,22 @@ WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
     // read slot of row i: i - B_in (slot 0 = row i_lo - 1, the first diagonal); write slot: i - B_out
     const int B_in = i_lo - 1;
     const int B_out = last_strip ? B_in : strip_ilo<M>(g, j0 + W) - 1;
-    double* const rbase = bnd - (long long)B_in * bs;   // rbase[i * bs] = read slot of row i
-    double* const wbase = bnd - (long long)B_out * bs;  // wbase[i * bs] = write slot of row i
+    F* const rbase = bnd - (long long)B_in * bs;   // rbase[i * bs] = read slot of row i
+    F* const wbase = bnd - (long long)B_out * bs;  // wbase[i * bs] = write slot of row i
 
     typename M::Col cols[W];
 #pragma unroll
     for (int c = 0; c < W; ++c) {
       int jj = imin2(j0 + c, Ty - 1);
-      double yj = y[jj];
-      double yjm = (jj > 0) ? y[jj - 1] : 0.0;
+      F yj = y[jj];
+      F yjm = (jj > 0) ? y[jj - 1] : F(0);
       cols[c] = m.col(jj, yj, yjm);
     }
-    double prev[W];
+    F prev[W];
 #pragma unroll
     for (int c = 0; c < W; ++c) prev[c] = m.usent();
 
-    double Dg;
+    F Dg;
     if (first_strip) {
       // virtual column -1: left0 is the same constant for every row and diag0(i) == left0(i-1)
       // for i >= 1, so the first strip simply finds left0 in every slot it will read.
@@ -123,18 +134,18 @@ WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
       Dg = m.diag0(0);
     } else if (i_lo == 0) Dg = m.prev_init();
     else Dg = bnd[0];
-    double xi = x[i_lo];
-    double xim = (M::kNeedPrevX && i_lo > 0) ? x[i_lo - 1] : 0.0;
-    double stale = m.lsent();
-    double colmin = WB_INF;
+    F xi = x[i_lo];
+    F xim = (M::kNeedPrevX && i_lo > 0) ? x[i_lo - 1] : F(0);
+    F stale = m.lsent();
+    F colmin = Num<F>::inf();
     int i = i_lo;
 
     auto generic_row = [&]() {
-      const double xnext = x[imin2(i + 1, Tx - 1)];  // prefetch next row's sample
+      const F xnext = x[imin2(i + 1, Tx - 1)];  // prefetch next row's sample
       const int js = row_js<M>(g, i), je = row_je<M>(g, i);
       const int clo = imax2(js - j0, 0), chi = imin2(je - j0, wv);
-      double left = rbase[i * bs];
-      double diag = Dg;
+      F left = rbase[i * bs];
+      F diag = Dg;
       Dg = left;
       if (i == 0) {
 #pragma unroll
@@ -142,14 +153,14 @@ WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
       }
       const typename M::Row rw = m.row(i, xi, xim);
       const int cst = M::kMsmBand ? (row_js<M>(g, i + 1) - 1 - j0) : -1;
-      double stale_next = stale;
+      F stale_next = stale;
 #pragma unroll
       for (int c = 0; c < W; ++c) {
-        const double up = prev[c];
+        const F up = prev[c];
         if (M::kMsmBand && c == cst) stale_next = up;
         if (c >= clo && c < chi) {
           if (c > 0 && c == clo) left = M::kMsmBand ? stale : m.lsent();
-          const double d = m.cell(up, left, diag, rw, cols[c], m.dv(i, j0 + c));
+          const F d = m.cell(up, left, diag, rw, cols[c], m.dv(i, j0 + c));
           prev[c] = d;
           left = d;
         }
@@ -158,7 +169,7 @@ WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
       stale = stale_next;
       // (MSM's row 0 reaches one cell beyond the band; no later strip reads that value)
       if (chi == W && (!M::kMsmBand || i >= B_out)) {
-        const double b = prev[W - 1];
+        const F b = prev[W - 1];
         wbase[i * bs] = b;
         if (EA && M::kColumnMinBound) colmin = dmin2(colmin, b);
       }
@@ -185,17 +196,17 @@ WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
         // left->right dependency chains (an in-thread anti-diagonal wavefront).  All boundary
         // and x accesses are pointer + immediate; the boundary values and x samples of the NEXT
         // group are loaded one group ahead (hides the L1/L2 latency of the global rings).
-        double* rp = rbase + (long long)i * bs;
-        double* wp = wbase + (long long)i * bs;
-        const double* xp = x + i;
-        double pf[NR], xn[NR];
+        F* rp = rbase + (long long)i * bs;
+        F* wp = wbase + (long long)i * bs;
+        const F* xp = x + i;
+        F pf[NR], xn[NR];
 #pragma unroll
         for (int r = 0; r < NR; ++r) pf[r] = rp[r * bs];
         xn[0] = xi;
 #pragma unroll
         for (int r = 1; r < NR; ++r) xn[r] = xp[r];
         do {
-          double xr[NR], lft[NR], dg[NR];
+          F xr[NR], lft[NR], dg[NR];
           typename M::Row rws[NR];
 #pragma unroll
           for (int r = 0; r < NR; ++r) {
@@ -205,7 +216,7 @@ WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
           }
           // next group's operands (the rows exist whenever the loop continues; otherwise the
           // clamped x pointer / the padded buffer keep the loads in bounds and the values unused)
-          const double* xq = (i + 2 * NR <= Tx) ? xp + NR : xp;
+          const F* xq = (i + 2 * NR <= Tx) ? xp + NR : xp;
 #pragma unroll
           for (int r = 0; r < NR; ++r) {
             pf[r] = rp[(NR + r) * bs];
@@ -224,10 +235,10 @@ WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
           Dg = lft[NR - 1];
 #pragma unroll
           for (int c = 0; c < W; ++c) {
-            double v = prev[c];
+            F v = prev[c];
 #pragma unroll
             for (int r = 0; r < NR; ++r) {
-              const double d = m.cell(v, lft[r], dg[r], rws[r], cols[c], dvs[r - c + W - 1]);
+              const F d = m.cell(v, lft[r], dg[r], rws[r], cols[c], dvs[r - c + W - 1]);
               dg[r] = v;
               lft[r] = d;
               v = d;
@@ -253,15 +264,15 @@ WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
       if (reg_top && i == i_lo) {
 #pragma unroll
         for (int t = 0; t < W - 1; ++t) {
-          const double xnext = x[imin2(i + 1, Tx - 1)];
-          double left = rbase[i * bs];
-          double diag = Dg;
+          const F xnext = x[imin2(i + 1, Tx - 1)];
+          F left = rbase[i * bs];
+          F diag = Dg;
           Dg = left;
           const typename M::Row rw = m.row(i, xi, xim);
 #pragma unroll
           for (int c = 0; c <= t; ++c) {
-            const double up = prev[c];
-            const double d = m.cell(up, left, diag, rw, cols[c], m.dv(i, j0 + c));
+            const F up = prev[c];
+            const F d = m.cell(up, left, diag, rw, cols[c], m.dv(i, j0 + c));
             prev[c] = d;
             left = d;
             diag = up;
@@ -274,14 +285,14 @@ WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
 #pragma unroll
         for (int t = 1; t < W; ++t) {
           // row i = j0 + a + t: cells t..W-1; the cell left of the band reads the sentinel
-          const double xnext = x[imin2(i + 1, Tx - 1)];
+          const F xnext = x[imin2(i + 1, Tx - 1)];
           const typename M::Row rw = m.row(i, xi, xim);
-          double left = m.lsent();
-          double diag = prev[t - 1];
+          F left = m.lsent();
+          F diag = prev[t - 1];
 #pragma unroll
           for (int c = t; c < W; ++c) {
-            const double up = prev[c];
-            const double d = m.cell(up, left, diag, rw, cols[c], m.dv(i, j0 + c));
+            const F up = prev[c];
+            const F d = m.cell(up, left, diag, rw, cols[c], m.dv(i, j0 + c));
             prev[c] = d;
             left = d;
             diag = up;
@@ -299,10 +310,10 @@ WB_HD double strip_pair(const Geom& g, const M& m, const double* __restrict__ x,
 
     if (!last_strip) {
       if (jl + g.a + 1 <= Tx - 1) wbase[(jl + g.a + 1) * bs] = M::kMsmBand ? stale : m.lsent();
-      if (EA && M::kColumnMinBound && colmin > abandon) return WB_INF;
+      if (EA && M::kColumnMinBound && colmin > abandon) return Num<F>::inf();
     } else {
 #pragma unroll
-      for (int c = 0; c < W; ++c) result = sel_f64(c == wv - 1, prev[c], result);
+      for (int c = 0; c < W; ++c) result = sel_real(c == wv - 1, prev[c], result);
     }
   }
   return m.finish(result, g);

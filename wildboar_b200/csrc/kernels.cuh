@@ -13,9 +13,12 @@ enum PairMode : int {
   PM_LIST = 3,      // out[i][j] for the (i, j) of a device-resident survivor list (argmin cascade)
 };
 
-struct KArgs {
-  const double* x;  // (nx, Tx) dense, first operand (rows of the DP)
-  const double* y;  // (ny, Ty) dense, second operand (columns of the DP)
+// F = arithmetic type of the DP (double: bit-exact mode, float: fp32 mode).  Results, per-series
+// scalars and thresholds cross the kernel boundary as doubles in both modes.
+template <class F>
+struct KArgsT {
+  const F* x;  // (nx, Tx) dense, first operand (rows of the DP)
+  const F* y;  // (ny, Ty) dense, second operand (columns of the DP)
   long long nx, ny;
   int Tx, Ty;
   Geom g;
@@ -34,18 +37,21 @@ struct KArgs {
   int mirror;         // PM_SELF: also write out[j][i] (single-device full matrix)
   const int2* list;   // PM_LIST: pairs to evaluate, sorted by (i, j)
   const int* list_len;  // PM_LIST: number of pairs (device resident: no host round trip)
-  double* gring;      // strip engine, GRING variant: boundary rings in global memory, [warp][slot][lane]
-  double* scratch;    // row-scan engine: 2 rows per thread, interleaved
+  F* gring;           // strip engine, GRING variant: boundary buffers in global memory, [warp][slot][lane]
+  F* scratch;         // row-scan engine: 2 rows per thread, interleaved
   long long sstride;  // = total threads
   int srows;          // elements per scratch row
 };
+using KArgs = KArgsT<double>;
 
 // One warp task = 32 consecutive pairs.  Returns false when the whole task is empty.
-__device__ __forceinline__ long long task_count(const KArgs& a) {
+template <class A>
+__device__ __forceinline__ long long task_count(const A& a) {
   return a.mode == PM_LIST ? ((long long)__ldg(a.list_len) + 31) / 32 : a.ntasks;
 }
 
-__device__ __forceinline__ bool decode_task(const KArgs& a, long long t, int lane, long long& i, long long& j,
+template <class A>
+__device__ __forceinline__ bool decode_task(const A& a, long long t, int lane, long long& i, long long& j,
                                             bool& valid) {
   if (a.mode == PM_LIST) {
     const long long n = __ldg(a.list_len);
@@ -84,14 +90,16 @@ __device__ __forceinline__ long long next_task(unsigned long long* counter, int 
 
 // ---- strip engine: thread per pair, boundary ring in shared memory [warp][slot][lane] ----
 template <class M, int W, int NT, int MINB, bool EA, int NR = 2, bool GRING = false>
-__global__ void __launch_bounds__(NT, MINB) k_strip(KArgs a, M m) {
-  extern __shared__ double smem[];
+__global__ void __launch_bounds__(NT, MINB) k_strip(KArgsT<typename M::real> a, M m) {
+  using F = typename M::real;
+  extern __shared__ double smem_raw[];
+  F* smem = reinterpret_cast<F*>(smem_raw);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  // boundary ring of this warp's 32 pairs: shared memory, or (tall bands that would leave too
+  // boundary buffers of this warp's 32 pairs: shared memory, or (tall bands that would leave too
   // few warps resident) L2-resident global memory
-  double* bnd = GRING ? a.gring + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * a.NS * 32 + lane
-                      : smem + (size_t)warp * a.NS * 32 + lane;
+  F* bnd = GRING ? a.gring + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * a.NS * 32 + lane
+                 : smem + (size_t)warp * a.NS * 32 + lane;
   const long long ntasks = task_count(a);
   for (;;) {
     const long long t = next_task(a.counter, lane);
@@ -104,8 +112,8 @@ __global__ void __launch_bounds__(NT, MINB) k_strip(KArgs a, M m) {
     pc.sx = a.sx ? a.sx[i] : 0.0;
     pc.sy = a.sy ? a.sy[j] : 0.0;
     mm.begin_pair(pc);
-    const double ab = EA ? a.thr[i] : WB_INF;
-    const double d = strip_pair<M, W, EA, NR, 32>(a.g, mm, a.x + i * a.Tx, a.y + j * a.Ty, bnd, 32, ab);
+    const F ab = EA ? (F)a.thr[i] : Num<F>::inf();
+    const double d = (double)strip_pair<M, W, EA, NR, 32>(a.g, mm, a.x + i * a.Tx, a.y + j * a.Ty, bnd, 32, ab);
     if (valid) {
       if (a.mode == PM_PAIRED) a.out[i] = d;
       else {
@@ -119,11 +127,12 @@ __global__ void __launch_bounds__(NT, MINB) k_strip(KArgs a, M m) {
 
 // ---- row-scan engine: thread per pair, two scratch rows per thread in global memory ----
 template <class M, int NT>
-__global__ void __launch_bounds__(NT) k_rowscan(KArgs a, M m) {
+__global__ void __launch_bounds__(NT) k_rowscan(KArgsT<typename M::real> a, M m) {
+  using F = typename M::real;
   const int lane = threadIdx.x & 31;
   const long long gtid = (long long)blockIdx.x * NT + threadIdx.x;
-  double* b0 = a.scratch + gtid;
-  double* b1 = a.scratch + (long long)a.srows * a.sstride + gtid;
+  F* b0 = a.scratch + gtid;
+  F* b1 = a.scratch + (long long)a.srows * a.sstride + gtid;
   const long long ntasks = task_count(a);
   for (;;) {
     const long long t = next_task(a.counter, lane);
@@ -136,14 +145,14 @@ __global__ void __launch_bounds__(NT) k_rowscan(KArgs a, M m) {
     pc.sx = a.sx ? a.sx[i] : 0.0;
     pc.sy = a.sy ? a.sy[j] : 0.0;
     mm.begin_pair(pc);
-    const double md = a.thr ? a.thr[i] : WB_INF;
-    double mmax = 0.0;
-    const double d = rowscan_pair<M>(a.g, mm, a.x + i * a.Tx, a.y + j * a.Ty, b0, b1, a.sstride, md, &mmax);
+    const F md = a.thr ? (F)a.thr[i] : Num<F>::inf();
+    F mmax = F(0);
+    const double d = (double)rowscan_pair<M>(a.g, mm, a.x + i * a.Tx, a.y + j * a.Ty, b0, b1, a.sstride, md, &mmax);
     if (valid) {
       if (a.mode == PM_PAIRED) a.out[i] = d;
       else {
         a.out[i * a.ld + j] = d;
-        if (a.out_m) a.out_m[i * a.ld + j] = mmax;
+        if (a.out_m) a.out_m[i * a.ld + j] = (double)mmax;
         if (a.mode == PM_SELF && a.mirror) a.out[j * a.ld + i] = d;
       }
     }
@@ -161,6 +170,12 @@ __global__ void k_slope(const double* __restrict__ q, long long n, int T, double
     const double* p = q + s * T + k;
     d[e] = ((p[1] - p[0]) + ((p[2] - p[0]) / 2)) / 2;
   }
+}
+
+// fp32 mode: operands are converted once per call
+__global__ void k_to_float(const double* __restrict__ src, long long n, float* __restrict__ dst) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    dst[e] = (float)src[e];
 }
 
 // kind 0: erp gap sum  sum_t |x[t] - g| (EL:1295-1303, sequential order)

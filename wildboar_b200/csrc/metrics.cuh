@@ -47,18 +47,35 @@ enum MetricId : int {
 
 WB_HD double dmin2(double a, double b) { return a < b ? a : b; }
 WB_HD double dmax2(double a, double b) { return a > b ? a : b; }
+// fp32 mode (optional, <= 1e-4 relative): native FMNMX / FMNMX3
+WB_HD float dmin2(float a, float b) { return fminf(a, b); }
+WB_HD float dmax2(float a, float b) { return fmaxf(a, b); }
 WB_HD int imin2(int a, int b) { return a < b ? a : b; }
 WB_HD int imax2(int a, int b) { return a > b ? a : b; }
 WB_HD int iabs1(int a) { return a < 0 ? -a : a; }
 
 // Read-only global load (table lookups that are uniform across a warp).
-WB_HD double ldg(const double* p) {
+template <class F>
+WB_HD F ldg(const F* p) {
 #if defined(__CUDA_ARCH__)
   return __ldg(p);
 #else
   return *p;
 #endif
 }
+
+// +infinity of the arithmetic type (F = double: the bit-exact mode; F = float: the fp32 mode)
+template <class F> struct Num;
+template <> struct Num<double> { WB_HD static double inf() { return WB_INF; } };
+template <> struct Num<float> {
+  WB_HD static float inf() {
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(0x7f800000);
+#else
+    return (float)INFINITY;
+#endif
+  }
+};
 
 // Band geometry shared by every metric (EL:890-891, 909-910 and the same expressions inlined
 // in the other kernels).  R = max(floor(min(Tx,Ty) * r), 1) is computed by the caller.
@@ -89,41 +106,47 @@ struct PairCtx {
 // WEIGHTED: cost is (v*v)*w[widx]; row 0 uses w[max(j-1,0)] (EL:894-903 quirk).
 // AMERCING: min(min(up+p, left+p), diag) + v*v, no penalty on row 0 (EL:966-971).
 // ------------------------------------------------------------------------------------------
-template <bool WEIGHTED, bool AMERCING>
+template <bool WEIGHTED, bool AMERCING, class F = double>
 struct DtwPolicy {
+  using real = F;
   static constexpr bool kMsmBand = false;
   static constexpr bool kNeedPrevX = false;
   static constexpr bool kColumnMinBound = true;  // column minima lower-bound the result
-  const double* w;  // WEIGHTED: CENTER of the signed weights table, w[d] = weight(|d|), d = i - j
-  double p;         // penalty (AMERCING)
+  const F* w;  // WEIGHTED: CENTER of the signed weights table, w[d] = weight(|d|), d = i - j
+  F p;         // penalty (AMERCING)
 
-  WB_HD double prev_init() const { return WB_INF; }
-  WB_HD double usent() const { return WB_INF; }
-  WB_HD double lsent() const { return WB_INF; }
-  WB_HD double left0(int) const { return WB_INF; }
-  WB_HD double diag0(int i) const { return i == 0 ? 0.0 : WB_INF; }
+  WB_HD F prev_init() const { return Num<F>::inf(); }
+  WB_HD F usent() const { return Num<F>::inf(); }
+  WB_HD F lsent() const { return Num<F>::inf(); }
+  WB_HD F left0(int) const { return Num<F>::inf(); }
+  WB_HD F diag0(int i) const { return i == 0 ? F(0) : Num<F>::inf(); }
   WB_HD void begin_pair(const PairCtx&) {}
 
-  struct Row { double xi; double p; };
-  struct Col { double yj; };
-  WB_HD Row row(int i, double xi, double) const {
-    Row r; r.xi = xi; r.p = (AMERCING && i > 0) ? p : 0.0; return r;
+  struct Row { F xi; F p; };
+  struct Col { F yj; };
+  WB_HD Row row(int i, F xi, F) const {
+    Row r; r.xi = xi; r.p = (AMERCING && i > 0) ? p : F(0); return r;
   }
-  WB_HD Col col(int, double yj, double) const { Col c; c.yj = yj; return c; }
+  WB_HD Col col(int, F yj, F) const { Col c; c.yj = yj; return c; }
   // per-diagonal value: the weight; row 0 uses w[max(j-1,0)] (EL:894-903 quirk)
-  struct Dv { double w; };
+  struct Dv { F w; };
   static constexpr bool kHasDv = WEIGHTED;
-  WB_HD Dv dv(int i, int j) const { Dv d; d.w = WEIGHTED ? ldg(w + ((i == 0) ? imax2(j - 1, 0) : (i - j))) : 1.0; return d; }
-  WB_HD Dv dv_diag(int d) const { Dv v; v.w = WEIGHTED ? ldg(w + d) : 1.0; return v; }  // rows >= 1
+  WB_HD Dv dv(int i, int j) const { Dv d; d.w = WEIGHTED ? ldg(w + ((i == 0) ? imax2(j - 1, 0) : (i - j))) : F(1); return d; }
+  WB_HD Dv dv_diag(int d) const { Dv v; v.w = WEIGHTED ? ldg(w + d) : F(1); return v; }  // rows >= 1
 
-  WB_HD double cell(double up, double left, double diag, const Row& r, const Col& c, const Dv& d) const {
-    double v = r.xi - c.yj;
-    double cost = v * v;
-    if (WEIGHTED) cost = cost * d.w;
+  WB_HD F cell(F up, F left, F diag, const Row& r, const Col& c, const Dv& d) const {
+    F v = r.xi - c.yj;
     if (AMERCING) { up = up + r.p; left = left + r.p; }
+    if (sizeof(F) == 4) {
+      // fp32 mode: FADD, FMNMX3, FFMA (contraction allowed: the mode's contract is 1e-4 relative)
+      const F m = dmin2(dmin2(up, left), diag);
+      return WEIGHTED ? (F)fmaf((float)(v * v), (float)d.w, (float)m) : (F)fmaf((float)v, (float)v, (float)m);
+    }
+    F cost = v * v;
+    if (WEIGHTED) cost = cost * d.w;
     return dmin2(dmin2(up, left), diag) + cost;
   }
-  WB_HD double finish(double d, const Geom&) const { return sqrt(d); }
+  WB_HD F finish(F d, const Geom&) const { return sqrt(d); }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -131,6 +154,7 @@ struct DtwPolicy {
 // ------------------------------------------------------------------------------------------
 template <bool WEIGHTED>
 struct LcssPolicy {
+  using real = double;  // no fp32 variant: the result is a step function of |x-y| <= eps
   static constexpr bool kMsmBand = false;
   static constexpr bool kNeedPrevX = false;
   static constexpr bool kColumnMinBound = false;
@@ -168,41 +192,44 @@ struct LcssPolicy {
 // ------------------------------------------------------------------------------------------
 // ERP.  EL:1273-1347.  sx/sy are the whole-series gap sums (sequential order).
 // ------------------------------------------------------------------------------------------
-struct ErpPolicy {
+template <class F = double>
+struct ErpPolicyT {
+  using real = F;
   static constexpr bool kMsmBand = false;
   static constexpr bool kNeedPrevX = false;
   static constexpr bool kColumnMinBound = false;
-  double g;
-  double gx_sum, gy_sum;
+  F g;
+  F gx_sum, gy_sum;
 
-  WB_HD double prev_init() const { return gy_sum; }
-  WB_HD double usent() const { return 0.0; }
-  WB_HD double lsent() const { return 0.0; }
-  WB_HD double left0(int) const { return gx_sum; }
-  WB_HD double diag0(int i) const { return i == 0 ? 0.0 : gx_sum; }
-  WB_HD void begin_pair(const PairCtx& pc) { gx_sum = pc.sx; gy_sum = pc.sy; }
+  WB_HD F prev_init() const { return gy_sum; }
+  WB_HD F usent() const { return F(0); }
+  WB_HD F lsent() const { return F(0); }
+  WB_HD F left0(int) const { return gx_sum; }
+  WB_HD F diag0(int i) const { return i == 0 ? F(0) : gx_sum; }
+  WB_HD void begin_pair(const PairCtx& pc) { gx_sum = (F)pc.sx; gy_sum = (F)pc.sy; }
 
-  struct Row { double xi, gx; };
-  struct Col { double yj, gy; };
-  WB_HD Row row(int, double xi, double) const { Row r; r.xi = xi; r.gx = fabs(xi - g); return r; }
-  WB_HD Col col(int, double yj, double) const { Col c; c.yj = yj; c.gy = fabs(yj - g); return c; }
+  struct Row { F xi, gx; };
+  struct Col { F yj, gy; };
+  WB_HD Row row(int, F xi, F) const { Row r; r.xi = xi; r.gx = fabs(xi - g); return r; }
+  WB_HD Col col(int, F yj, F) const { Col c; c.yj = yj; c.gy = fabs(yj - g); return c; }
 
   struct Dv {};
   static constexpr bool kHasDv = false;
   WB_HD Dv dv(int, int) const { return Dv(); }
   WB_HD Dv dv_diag(int) const { return Dv(); }
 
-  WB_HD double cell(double up, double left, double diag, const Row& r, const Col& c, const Dv&) const {
-    double v = fabs(r.xi - c.yj);
+  WB_HD F cell(F up, F left, F diag, const Row& r, const Col& c, const Dv&) const {
+    F v = fabs(r.xi - c.yj);
     return dmin2(diag + v, dmin2(up + r.gx, left + c.gy));
   }
-  WB_HD double finish(double d, const Geom&) const { return d; }
+  WB_HD F finish(F d, const Geom&) const { return d; }
 };
 
 // ------------------------------------------------------------------------------------------
 // EDR.  EL:1437-1497; eps < 0 on entry means "default": max(std_x, std_y) / 4 (EL:3762-3766).
 // ------------------------------------------------------------------------------------------
 struct EdrPolicy {
+  using real = double;  // no fp32 variant: the result is a step function of |x-y| < eps
   static constexpr bool kMsmBand = false;
   static constexpr bool kNeedPrevX = false;
   static constexpr bool kColumnMinBound = false;
@@ -243,18 +270,20 @@ struct EdrPolicy {
 // Band quirks (column 0 always evaluated, row 0 one cell wider, stale left) live in the engine
 // behind kMsmBand.
 // ------------------------------------------------------------------------------------------
-struct MsmPolicy {
+template <class F = double>
+struct MsmPolicyT {
+  using real = F;
   static constexpr bool kMsmBand = true;
   static constexpr bool kNeedPrevX = true;
   static constexpr bool kColumnMinBound = false;
-  double c;  // (double)(float)c
+  F c;  // (F)(float)c
   float cf;
 
-  WB_HD double prev_init() const { return WB_INF; }
-  WB_HD double usent() const { return 0.0; }
-  WB_HD double lsent() const { return 0.0; }  // only for bands the stale rule cannot reach
-  WB_HD double left0(int) const { return WB_INF; }
-  WB_HD double diag0(int i) const { return i == 0 ? 0.0 : WB_INF; }
+  WB_HD F prev_init() const { return Num<F>::inf(); }
+  WB_HD F usent() const { return F(0); }
+  WB_HD F lsent() const { return F(0); }  // only for bands the stale rule cannot reach
+  WB_HD F left0(int) const { return Num<F>::inf(); }
+  WB_HD F diag0(int i) const { return i == 0 ? F(0) : Num<F>::inf(); }
   WB_HD void begin_pair(const PairCtx&) {}
 
   // _msm_cost(x, y, z) = c + (x between y and z ? 0 : min(|x-y|, |x-z|)), differences in fp32.
@@ -265,10 +294,10 @@ struct MsmPolicy {
   // -- one xor + one select instead of four compares.  Per cell only ONE fp32 subtraction is
   // new: for the "up" move a = X[i]-X[i-1] is a row constant and b = X[i]-Y[j]; for the
   // "left" move a = Y[j]-X[i] = -b (negation is exact) and b = Y[j]-Y[j-1] is a column constant.
-  struct Row { double xi; float xf, dx; };   // dx = (float)X[i] - (float)X[i-1]
-  struct Col { double yj; float yf, dy; };   // dy = (float)Y[j] - (float)Y[j-1]
-  WB_HD Row row(int, double xi, double xim) const { Row r; r.xi = xi; r.xf = (float)xi; r.dx = r.xf - (float)xim; return r; }
-  WB_HD Col col(int, double yj, double yjm) const { Col c2; c2.yj = yj; c2.yf = (float)yj; c2.dy = c2.yf - (float)yjm; return c2; }
+  struct Row { F xi; float xf, dx; };   // dx = (float)X[i] - (float)X[i-1]
+  struct Col { F yj; float yf, dy; };   // dy = (float)Y[j] - (float)Y[j-1]
+  WB_HD Row row(int, F xi, F xim) const { Row r; r.xi = xi; r.xf = (float)xi; r.dx = r.xf - (float)xim; return r; }
+  WB_HD Col col(int, F yj, F yjm) const { Col c2; c2.yj = yj; c2.yf = (float)yj; c2.dy = c2.yf - (float)yjm; return c2; }
 
   WB_HD static unsigned fbits(float f) {
 #if defined(__CUDA_ARCH__)
@@ -283,7 +312,7 @@ struct MsmPolicy {
   // the compiler the select migrates behind the conversion (two more 32-bit selects per call), and
   // MSM is bound by exactly that pipe (profiles/r01c_ncu_msm_twe.md).
   template <bool NEG>
-  WB_HD double extra(float a, float b) const {
+  WB_HD F extra(float a, float b) const {
 #if defined(__CUDA_ARCH__)
     float e;
     if (NEG)
@@ -294,11 +323,11 @@ struct MsmPolicy {
       asm("{ .reg .pred p; .reg .b32 t; lop3.b32 t, %1, %2, 0x80000000, 0x28; setp.ne.u32 p, t, 0;"
           " min.f32 %0, %3, %4; selp.f32 %0, 0f00000000, %0, p; }"
           : "=f"(e) : "r"(fbits(a)), "r"(fbits(b)), "f"(fabsf(a)), "f"(fabsf(b)));
-    return c + (double)e;
+    return c + (F)e;
 #else
     const float m = fminf(fabsf(a), fabsf(b));
     const bool opposite = (((fbits(a) ^ fbits(b)) >> 31) != 0u) != NEG;
-    return c + (double)(opposite ? 0.0f : m);
+    return c + (F)(opposite ? 0.0f : m);
 #endif
   }
   struct Dv {};
@@ -306,51 +335,57 @@ struct MsmPolicy {
   WB_HD Dv dv(int, int) const { return Dv(); }
   WB_HD Dv dv_diag(int) const { return Dv(); }
 
-  WB_HD double cell(double up, double left, double diag, const Row& r, const Col& cl, const Dv&) const {
+  WB_HD F cell(F up, F left, F diag, const Row& r, const Col& cl, const Dv&) const {
     const float xy = r.xf - cl.yf;                  // (float)X[i] - (float)Y[j]
-    const double a = diag + fabs(r.xi - cl.yj);
-    const double b = up + extra<false>(r.dx, xy);   // _msm_cost(X[i], X[i-1], Y[j])
-    const double d = left + extra<true>(xy, cl.dy); // _msm_cost(Y[j], X[i], Y[j-1]): a = Y[j]-X[i] = -xy
+    const F a = diag + fabs(r.xi - cl.yj);
+    const F b = up + extra<false>(r.dx, xy);   // _msm_cost(X[i], X[i-1], Y[j])
+    const F d = left + extra<true>(xy, cl.dy); // _msm_cost(Y[j], X[i], Y[j-1]): a = Y[j]-X[i] = -xy
     return dmin2(dmin2(a, b), d);
   }
-  WB_HD double finish(double d, const Geom&) const { return d; }
+  WB_HD F finish(F d, const Geom&) const { return d; }
 };
 
 // ------------------------------------------------------------------------------------------
 // TWE.  EL:1733-1829.  Conventions X[-1] = Y[-1] = 0; pen = penalty + stiffness;
 // tw[k] = (stiffness*2)*k is a table so that no int->double conversion sits in the cell.
 // ------------------------------------------------------------------------------------------
-struct TwePolicy {
+template <class F = double>
+struct TwePolicyT {
+  using real = F;
   static constexpr bool kMsmBand = false;
   static constexpr bool kNeedPrevX = true;
   static constexpr bool kColumnMinBound = false;
-  double pen;        // penalty + stiffness
-  const double* tw;  // CENTER of the signed table tw[d] = (stiffness * 2) * |d|, d = i - j
+  F pen;        // penalty + stiffness
+  const F* tw;  // CENTER of the signed table tw[d] = (stiffness * 2) * |d|, d = i - j
 
-  WB_HD double prev_init() const { return WB_INF; }
-  WB_HD double usent() const { return 0.0; }
-  WB_HD double lsent() const { return 0.0; }
-  WB_HD double left0(int) const { return WB_INF; }
-  WB_HD double diag0(int i) const { return i == 0 ? 0.0 : WB_INF; }
+  WB_HD F prev_init() const { return Num<F>::inf(); }
+  WB_HD F usent() const { return F(0); }
+  WB_HD F lsent() const { return F(0); }
+  WB_HD F left0(int) const { return Num<F>::inf(); }
+  WB_HD F diag0(int i) const { return i == 0 ? F(0) : Num<F>::inf(); }
   WB_HD void begin_pair(const PairCtx&) {}
 
-  struct Row { double xi, xim, dx; };
-  struct Col { double yj, yjm, dy; };
-  WB_HD Row row(int, double xi, double xim) const { Row r; r.xi = xi; r.xim = xim; r.dx = fabs(xim - xi); return r; }
-  WB_HD Col col(int, double yj, double yjm) const { Col c; c.yj = yj; c.yjm = yjm; c.dy = fabs(yjm - yj); return c; }
+  struct Row { F xi, xim, dx; };
+  struct Col { F yj, yjm, dy; };
+  WB_HD Row row(int, F xi, F xim) const { Row r; r.xi = xi; r.xim = xim; r.dx = fabs(xim - xi); return r; }
+  WB_HD Col col(int, F yj, F yjm) const { Col c; c.yj = yj; c.yjm = yjm; c.dy = fabs(yjm - yj); return c; }
 
-  struct Dv { double t; };
+  struct Dv { F t; };
   static constexpr bool kHasDv = true;
   WB_HD Dv dv(int i, int j) const { return dv_diag(i - j); }
   WB_HD Dv dv_diag(int d) const { Dv v; v.t = ldg(tw + d); return v; }
 
-  WB_HD double cell(double up, double left, double diag, const Row& r, const Col& c, const Dv& d) const {
-    double del_x = (up + r.dx) + pen;
-    double del_y = (left + c.dy) + pen;
-    double match = ((diag + fabs(r.xi - c.yj)) + fabs(r.xim - c.yjm)) + d.t;
+  WB_HD F cell(F up, F left, F diag, const Row& r, const Col& c, const Dv& d) const {
+    F del_x = (up + r.dx) + pen;
+    F del_y = (left + c.dy) + pen;
+    F match = ((diag + fabs(r.xi - c.yj)) + fabs(r.xim - c.yjm)) + d.t;
     return dmin2(dmin2(del_x, del_y), match);
   }
-  WB_HD double finish(double d, const Geom&) const { return d; }
+  WB_HD F finish(F d, const Geom&) const { return d; }
 };
+
+using ErpPolicy = ErpPolicyT<double>;
+using MsmPolicy = MsmPolicyT<double>;
+using TwePolicy = TwePolicyT<double>;
 
 }  // namespace wb

@@ -42,6 +42,7 @@ struct Workspace {
   cudaStream_t stream;
   std::vector<void*> bufs;
   std::vector<std::vector<double>> host_keep;  // host staging that must outlive async copies
+  std::vector<std::vector<float>> host_keep_f;
   explicit Workspace(cudaStream_t s) : stream(s) {}
   ~Workspace() { for (void* p : bufs) cudaFreeAsync(p, stream); }
   template <class T> int alloc(T** p, size_t n) {
@@ -108,11 +109,12 @@ template <> struct StripCfg<TwePolicy> { static constexpr int WL = 12, NRL = 4, 
 template <> struct StripCfg<MsmPolicy> { static constexpr int WL = 8, NRL = 4, NWL = 16; };
 
 template <class M, int W, int NT, int MINB, bool EA, int NR, bool GRING>
-static int launch_strip_cfg(Workspace& ws, KArgs a, const M& m, int nwarps, int sms, size_t smem_cap, wb_stats* cfg) {
+static int launch_strip_cfg(Workspace& ws, KArgsT<typename M::real> a, const M& m, int nwarps, int sms, size_t smem_cap, wb_stats* cfg) {
+  using F = typename M::real;
   cudaStream_t st = ws.stream;
   auto kern = k_strip<M, W, NT, MINB, EA, NR, GRING>;
   a.NS = strip_ring_slots(a.g, W);
-  const size_t per_warp = (size_t)a.NS * 32 * sizeof(double);
+  const size_t per_warp = (size_t)a.NS * 32 * sizeof(F);
   if (!GRING) nwarps = (int)std::max<size_t>(1, std::min<size_t>((size_t)nwarps, smem_cap / per_warp));
   size_t smem = GRING ? 0 : (size_t)nwarps * per_warp;
   if (!GRING) WB_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -123,7 +125,7 @@ static int launch_strip_cfg(Workspace& ws, KArgs a, const M& m, int nwarps, int 
   long long grid = (long long)sms * per_sm;
   if (a.ntasks < grid * nwarps) grid = std::max<long long>(1, (a.ntasks + nwarps - 1) / nwarps);
   if (GRING) {
-    double* ring = nullptr;
+    F* ring = nullptr;
     if (ws.alloc(&ring, (size_t)grid * nwarps * a.NS * 32)) return 1;
     a.gring = ring;
   }
@@ -134,9 +136,9 @@ static int launch_strip_cfg(Workspace& ws, KArgs a, const M& m, int nwarps, int 
 }
 
 template <class M, bool EA>
-static int launch_strip(Workspace& ws, const KArgs& a, const M& m, size_t smem_cap, int sms, wb_stats* cfg) {
+static int launch_strip(Workspace& ws, const KArgsT<typename M::real>& a, const M& m, size_t smem_cap, int sms, wb_stats* cfg) {
   using C = StripCfg<M>;
-  const size_t per_warp = (size_t)strip_ring_slots(a.g, 16) * 32 * sizeof(double);  // widest strips
+  const size_t per_warp = (size_t)strip_ring_slots(a.g, 16) * 32 * sizeof(typename M::real);  // widest strips
   if (a.g.H >= 32) {
     // keep the global rings of one launch below ~8 GB whatever the series length
     const size_t ring_budget = (size_t)8 << 30;
@@ -170,6 +172,10 @@ struct DpCall {
   const double* px; const double* py; int ptx, pty;
   const double* sx; const double* sy;
   Tables tab;
+  // fp32 mode (optional; p.precision == 1 and the metric has a float variant): float copies
+  bool fp32;
+  const float* pxf; const float* pyf;
+  TablesT<float> tabf;
   int R;
   bool degenerate;     // ddtw with min(T) < 3: every distance is 0 (EL:3270)
 };
@@ -222,14 +228,39 @@ static int prepare_operands(Workspace& ws, DpCall& c) {
     WB_CK(cudaGetLastError());
     c.sx = sx; c.sy = sy;
   }
+  c.fp32 = c.p.precision == 1 && has_fp32_variant(c.metric);
+  c.pxf = c.pyf = nullptr; c.tabf.weights = c.tabf.tw = nullptr;
+  if (c.fp32) {
+    float *fx = nullptr, *fy = nullptr;
+    if (ws.alloc(&fx, (size_t)c.nx * c.ptx)) return 1;
+    k_to_float<<<1024, 256, 0, st>>>(c.px, c.nx * (long long)c.ptx, fx);
+    if (c.py == c.px && c.ny == c.nx && c.pty == c.ptx) fy = fx;
+    else {
+      if (ws.alloc(&fy, (size_t)c.ny * c.pty)) return 1;
+      k_to_float<<<1024, 256, 0, st>>>(c.py, c.ny * (long long)c.pty, fy);
+    }
+    WB_CK(cudaGetLastError());
+    c.pxf = fx; c.pyf = fy;
+    if (c.tab.weights || c.tab.tw) {
+      const std::vector<double>& h = ws.host_keep.back();
+      ws.host_keep_f.emplace_back(h.begin(), h.end());
+      std::vector<float>& hf = ws.host_keep_f.back();
+      float* d = nullptr;
+      if (ws.alloc(&d, hf.size())) return 1;
+      WB_CK(cudaMemcpyAsync(d, hf.data(), hf.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+      const int64_t tn = c.metric == M_TWE ? nmax + 1 : nmax;
+      if (c.metric == M_TWE) c.tabf.tw = d + table_center(tn); else c.tabf.weights = d + table_center(tn);
+    }
+  }
   return 0;
 }
 
 // Launch the DP over rows [r0, r0+nrows) of the prepared x against columns [c0, c0+ncols) of
 // the prepared y.  out/out_m/thr are indexed relative to (r0, c0) / r0.
-static int launch_dp(Workspace& ws, const DeviceInfo& di, const DpCall& c, long long r0, long long nrows,
-                     long long c0, long long ncols, double* out, long long ld, double* out_m, const double* thr,
-                     wb_stats* stats) {
+template <class F>
+static int launch_dp_t(Workspace& ws, const DeviceInfo& di, const DpCall& c, long long r0, long long nrows,
+                       long long c0, long long ncols, double* out, long long ld, double* out_m, const double* thr,
+                       wb_stats* stats) {
   cudaStream_t st = ws.stream;
   if (nrows <= 0 || ncols <= 0) return 0;
   if (c.degenerate) {
@@ -237,9 +268,11 @@ static int launch_dp(Workspace& ws, const DeviceInfo& di, const DpCall& c, long 
     else WB_CK(cudaMemset2DAsync(out, ld * sizeof(double), 0, ncols * sizeof(double), nrows, st));
     return 0;
   }
-  KArgs a;
+  constexpr bool kF32 = sizeof(F) == 4;
+  KArgsT<F> a;
   memset(&a, 0, sizeof a);
-  a.x = c.px + r0 * c.ptx; a.y = c.py + c0 * c.pty;
+  if constexpr (kF32) { a.x = c.pxf + r0 * c.ptx; a.y = c.pyf + c0 * c.pty; }
+  else { a.x = c.px + r0 * c.ptx; a.y = c.py + c0 * c.pty; }
   a.nx = nrows; a.ny = ncols; a.Tx = c.ptx; a.Ty = c.pty;
   a.g = make_geom(c.ptx, c.pty, c.R);
   a.sx = c.sx ? c.sx + r0 : nullptr; a.sy = c.sy ? c.sy + c0 : nullptr;
@@ -256,7 +289,7 @@ static int launch_dp(Workspace& ws, const DeviceInfo& di, const DpCall& c, long 
   const size_t smem_cap = (size_t)di.max_smem_optin;
   int engine = 0;
   int rc = 0;
-  bool known = with_policy(c.metric, c.p, c.tab, [&](auto m) {
+  auto body = [&](auto m) {
     using M = decltype(m);
     bool strip_ok = strip_supported<M>(a.g, 4) && !c.need_rowmin &&
                     !(out_m != nullptr) && c.p.engine != 1;
@@ -282,13 +315,16 @@ static int launch_dp(Workspace& ws, const DeviceInfo& di, const DpCall& c, long 
       grid = std::max<long long>(1, std::min(grid, need));
       a.srows = std::max(c.ptx, c.pty) + 1;
       a.sstride = grid * NT;
-      double* scratch = nullptr;
+      F* scratch = nullptr;
       if (ws.alloc(&scratch, (size_t)2 * a.srows * a.sstride)) { rc = 1; return; }
       a.scratch = scratch;
       kern<<<(unsigned)grid, NT, 0, st>>>(a, m);
       if (cudaGetLastError() != cudaSuccess) { set_err("row-scan kernel launch failed"); rc = 1; }
     }
-  });
+  };
+  bool known;
+  if constexpr (kF32) known = with_policy_f32(c.metric, c.p, c.tabf, body);
+  else known = with_policy(c.metric, c.p, c.tab, body);
   if (!known) { set_err("unknown metric id"); return 1; }
   if (rc) return rc;
   if (stats) {
@@ -306,6 +342,13 @@ static int launch_dp(Workspace& ws, const DeviceInfo& di, const DpCall& c, long 
     stats->cells += pairs * cells_per_pair(c.ptx, c.pty, c.R);
   }
   return 0;
+}
+
+static int launch_dp(Workspace& ws, const DeviceInfo& di, const DpCall& c, long long r0, long long nrows,
+                     long long c0, long long ncols, double* out, long long ld, double* out_m, const double* thr,
+                     wb_stats* stats) {
+  if (c.fp32) return launch_dp_t<float>(ws, di, c, r0, nrows, c0, ncols, out, ld, out_m, thr, stats);
+  return launch_dp_t<double>(ws, di, c, r0, nrows, c0, ncols, out, ld, out_m, thr, stats);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -528,6 +571,7 @@ static int check_common(int metric, const wb_params* p, const void* x, int64_t n
   if (n < 1 || T < 1) { set_err("empty input"); return 1; }
   if (T > (1 << 24)) { set_err("series too long"); return 1; }
   if (!(p->r >= 0.0 && p->r <= 1.0)) { set_err("r must be in [0, 1]"); return 1; }
+  if (p->precision != 0 && p->precision != 1) { set_err("precision must be 0 (fp64, bit-exact) or 1 (fp32)"); return 1; }
   return 0;
 }
 
