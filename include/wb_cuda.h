@@ -113,6 +113,23 @@ int wb_cuda_pairwise_dev(int metric, const wb_params *params,
                          const double *d_y, int64_t ny, int64_t Ty,
                          double *d_out, void *stream, wb_stats *stats);
 
+/* Lower-bound matrices of wildboar.distance.lb, host buffers, one device.
+ * out[i * nx + j] for query i (rows of q) and fitted sample j (rows of x); both (n, T) float64 with
+ * `*_stride` elements between consecutive samples.
+ *
+ * wb_cuda_lb_keogh replaces DtwKeoghLowerBound(r, kind).fit(x).transform(q), distance/lb.py:359-432
+ * (a Python double loop over _dtw_lb_keogh, _elastic.pyx:1095-1115): envelope half-width
+ * max(floor(T r), 1) (T - 1 when that equals T, lb.py:367-369), kind 0 = "both" (maximum of the two
+ * directions), 1 = "left" (query against the sample's envelope), 2 = "right".
+ * wb_cuda_lb_kim replaces DtwKimLowerBound().fit(x).transform(q), distance/lb.py:224-311 (sum of the
+ * squared first/last-three-point terms; the reference applies no square root). */
+int wb_cuda_lb_keogh(const double *q, int64_t nq, int64_t q_stride,
+                     const double *x, int64_t nx, int64_t x_stride, int64_t T,
+                     double r, int kind, double *out, int device, wb_stats *stats);
+int wb_cuda_lb_kim(const double *q, int64_t nq, int64_t q_stride,
+                   const double *x, int64_t nx, int64_t x_stride, int64_t T,
+                   double *out, int device, wb_stats *stats);
+
 /* Measured FP64 issue rate of the current device: runs a register-only DADD/DMUL chain on
  * every SM and returns FP64 warp-lane instructions per second (the ALU roofline denominator,
  * SURVEY 8d).  mix: 0 = DADD only, 1 = DTW cell mix (3 arithmetic + 2 compare/select). */

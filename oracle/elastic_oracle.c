@@ -615,3 +615,61 @@ double orc_lb_keogh_one(const double *q, const double *lower, const double *uppe
   }
   return sqrt(s);
 }
+
+/* distance/dtw.py:38-40 (_compute_warp_size) + LB:367-369 / LB:410-412: envelope half-width used by
+ * DtwKeoghLowerBound: max(floor(T * r), 1), and T - 1 when that equals T. */
+int64_t orc_lb_warp_size(int64_t T, double r) {
+  int64_t w = (int64_t)floor((double)T * r);
+  if (w < 1) w = 1;
+  if (w == T) w -= 1;
+  return w;
+}
+
+/* DtwKeoghLowerBound.fit(X).transform(Q), LB:359-432.  out[i * nx + j] for query i, fitted sample j.
+ * kind: 0 both (max of the two directions), 1 left (query against the sample's envelope),
+ * 2 right (sample against the query's envelope).  The disabled direction contributes -inf (LB:420-429). */
+int orc_lb_keogh_matrix(const double *q, int64_t nq, const double *x, int64_t nx, int64_t T, double r, int kind,
+                        double *out) {
+  const int64_t w = orc_lb_warp_size(T, r);
+  double *xl = (double *)malloc(sizeof(double) * (size_t)nx * T), *xu = (double *)malloc(sizeof(double) * (size_t)nx * T);
+  double *ql = (double *)malloc(sizeof(double) * T), *qu = (double *)malloc(sizeof(double) * T);
+  if (!xl || !xu || !ql || !qu) return 1;
+  for (int64_t j = 0; j < nx; j++) orc_envelope(x + j * T, T, w, xl + j * T, xu + j * T);   /* fit, LB:371-374 */
+  for (int64_t i = 0; i < nq; i++) {
+    if (kind == 0 || kind == 2) orc_envelope(q + i * T, T, w, ql, qu);                         /* LB:417-418 */
+    for (int64_t j = 0; j < nx; j++) {
+      double d1 = -INFINITY, d2 = -INFINITY;
+      if (kind == 0 || kind == 1) d1 = orc_lb_keogh_one(q + i * T, xl + j * T, xu + j * T, T);
+      if (kind == 0 || kind == 2) d2 = orc_lb_keogh_one(x + j * T, ql, qu, T);
+      out[i * nx + j] = d1 > d2 ? d1 : d2;                                                     /* LB:431 */
+    }
+  }
+  free(xl); free(xu); free(ql); free(qu);
+  return 0;
+}
+
+/* DtwKimLowerBound.fit(X).transform(Q), LB:224-311: first/last three points; the SUM of squared terms
+ * (the reference applies no sqrt).  x = fitted samples (columns of the result), y = queries. */
+static inline double kim_d(double a, double b) { double v = a - b; return v * v; }
+int orc_lb_kim_matrix(const double *q, int64_t nq, const double *x, int64_t nx, int64_t T, double *out) {
+  for (int64_t i = 0; i < nq; i++) {
+    const double *Y = q + i * T;
+    for (int64_t j = 0; j < nx; j++) {
+      const double *X = x + j * T;
+      const double x0 = X[0], x0_ = X[T - 1], y0 = Y[0], y0_ = Y[T - 1];
+      double d = kim_d(x0, y0) + kim_d(x0_, y0_);
+      if (T > 1) {
+        const double x1 = X[1], x1_ = X[T - 2], y1 = Y[1], y1_ = Y[T - 2];
+        d += dmin(kim_d(x1, y0), dmin(kim_d(x0, y1), kim_d(x1, y1)));
+        d += dmin(kim_d(x1_, y1), dmin(kim_d(x0_, y1_), kim_d(x1_, y1_)));
+        if (T > 2) {
+          const double x2 = X[2], x2_ = X[T - 3], y2 = Y[2], y2_ = Y[T - 3];
+          d += dmin(kim_d(x0, y2), dmin(kim_d(x1, y2), dmin(kim_d(x2, y2), dmin(kim_d(x2, y1), kim_d(x2, y0)))));
+          d += dmin(kim_d(x0_, y2_), dmin(kim_d(x1_, y2_), dmin(kim_d(x2_, y2_), dmin(kim_d(x2_, y1_), kim_d(x2_, y0_)))));
+        }
+      }
+      out[i * nx + j] = d;
+    }
+  }
+  return 0;
+}

@@ -60,6 +60,10 @@ def lib():
         _lib.orc_envelope.argtypes = [dp, i64, i64, dp, dp]
         _lib.orc_lb_keogh_one.argtypes = [dp, dp, dp, i64]
         _lib.orc_lb_keogh_one.restype = C.c_double
+        _lib.orc_lb_warp_size.argtypes = [i64, C.c_double]
+        _lib.orc_lb_warp_size.restype = i64
+        _lib.orc_lb_keogh_matrix.argtypes = [dp, i64, dp, i64, i64, C.c_double, C.c_int, dp]
+        _lib.orc_lb_kim_matrix.argtypes = [dp, i64, dp, i64, i64, dp]
         _lib.orc_compute_r.argtypes = [i64, C.c_double]
         _lib.orc_compute_r.restype = i64
         _lib.orc_std.argtypes = [dp, i64]
@@ -153,6 +157,33 @@ def envelope(t, w):
 def lb_keogh_one(q, lower, upper):
     q = np.ascontiguousarray(q, dtype=np.float64)
     return lib().orc_lb_keogh_one(_dp(q), _dp(np.ascontiguousarray(lower)), _dp(np.ascontiguousarray(upper)), len(q))
+
+
+LB_KINDS = {"both": 0, "left": 1, "right": 2}
+
+
+def lb_warp_size(T, r):
+    return lib().orc_lb_warp_size(int(T), float(r))
+
+
+def lb_keogh(q, x, r=1.0, kind="both"):
+    """DtwKeoghLowerBound(r, kind).fit(x).transform(q) -> (nq, nx), lb.py:359-432."""
+    q, x = _arr(q), _arr(x)
+    assert q.shape[1] == x.shape[1]
+    out = np.empty((q.shape[0], x.shape[0]))
+    rc = lib().orc_lb_keogh_matrix(_dp(q), q.shape[0], _dp(x), x.shape[0], x.shape[1], float(r), LB_KINDS[kind], _dp(out))
+    assert rc == 0
+    return out
+
+
+def lb_kim(q, x):
+    """DtwKimLowerBound().fit(x).transform(q) -> (nq, nx), lb.py:224-311."""
+    q, x = _arr(q), _arr(x)
+    assert q.shape[1] == x.shape[1]
+    out = np.empty((q.shape[0], x.shape[0]))
+    rc = lib().orc_lb_kim_matrix(_dp(q), q.shape[0], _dp(x), x.shape[0], x.shape[1], _dp(out))
+    assert rc == 0
+    return out
 
 
 def compute_r(n, r):

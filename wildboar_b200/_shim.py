@@ -69,6 +69,8 @@ def lib():
                                              DV, ci, SP]
                 L.wb_cuda_pairwise_dev.argtypes = [ci, PP, C.c_void_p, i64, i64, C.c_void_p, i64, i64, C.c_void_p,
                                                    C.c_void_p, SP]
+                L.wb_cuda_lb_keogh.argtypes = [_DP, i64, i64, _DP, i64, i64, i64, C.c_double, ci, _DP, ci, SP]
+                L.wb_cuda_lb_kim.argtypes = [_DP, i64, i64, _DP, i64, i64, i64, _DP, ci, SP]
                 L.wb_cuda_fp64_peak.argtypes = [ci, _DP, _DP]
                 _lib = L
     return _lib
@@ -210,6 +212,35 @@ def argmin(metric_id, params, x, y, k, lower_bound=None, use_device_lb=False):
                                 C.byref(st)))
     _tls.stats = st.as_dict()
     return idx.astype(np.intp, copy=False), dist
+
+
+def _first_device():
+    devs = _resolve_devices(0.0)
+    return devs[0] if devs else 0
+
+
+def lb_keogh(q, x, r, kind):
+    """(nq, nx) LB_Keogh matrix; kind 0 both / 1 left / 2 right (include/wb_cuda.h)."""
+    q, qp, nq, T, qs = _rows(q)
+    x, xp, nx, Tx, xs = _rows(x)
+    assert T == Tx
+    out = np.empty((nq, nx), dtype=np.float64)
+    st = WbStats()
+    _check(lib().wb_cuda_lb_keogh(qp, nq, qs, xp, nx, xs, T, float(r), int(kind), out.ctypes.data_as(_DP), _first_device(),
+                                  C.byref(st)))
+    _tls.stats = st.as_dict()
+    return out
+
+
+def lb_kim(q, x):
+    q, qp, nq, T, qs = _rows(q)
+    x, xp, nx, Tx, xs = _rows(x)
+    assert T == Tx
+    out = np.empty((nq, nx), dtype=np.float64)
+    st = WbStats()
+    _check(lib().wb_cuda_lb_kim(qp, nq, qs, xp, nx, xs, T, out.ctypes.data_as(_DP), _first_device(), C.byref(st)))
+    _tls.stats = st.as_dict()
+    return out
 
 
 def pairwise_dev(metric_id, params, x_ptr, nx, Tx, y_ptr, ny, Ty, out_ptr, stream=0, want_stats=True):

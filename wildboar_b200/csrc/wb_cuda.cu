@@ -19,6 +19,7 @@
 #include "kernels.cuh"
 #include "prep.hpp"
 #include "argmin.cuh"
+#include "lb.cuh"
 
 namespace wb {
 
@@ -565,6 +566,83 @@ static int run_host_job(const HostJob& J, const int* devices, int n_devices, wb_
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Lower-bound matrices (wildboar.distance.lb transformers), one device.
+// ------------------------------------------------------------------------------------------
+// distance/dtw.py:38-40 + LB:367-369: envelope half-width max(floor(T r), 1), T - 1 when that equals T
+static int lb_warp_size(int64_t T, double r) {
+  int64_t w = (int64_t)std::floor((double)T * r);
+  if (w < 1) w = 1;
+  if (w == T) w -= 1;
+  return (int)w;
+}
+
+// op 0: LB_Keogh (kind 0 both / 1 left / 2 right), op 1: LB_Kim
+static int run_lb(int op, const double* q, int64_t nq, int64_t qs, const double* x, int64_t nx, int64_t xs, int64_t T,
+                  double r, int kind, double* out, int device, wb_stats* stats) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { set_err("no CUDA device available: wildboar_b200 has no CPU fallback"); return 1; }
+  if (device < 0 || device >= ndev) { set_err("invalid device ordinal"); return 1; }
+  WB_CK(cudaSetDevice(device));
+  DeviceInfo di;
+  if (device_info(&di)) return 1;
+  cudaStream_t st;
+  WB_CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  int rc = 0;
+  wb_stats local; memset(&local, 0, sizeof local);
+  {
+    Workspace ws(st);
+    Timer total(st), kt(st);
+    total.start();
+    do {
+      double *dq = nullptr, *dx = nullptr;
+      if ((rc = ws.alloc(&dq, (size_t)nq * T)) || (rc = ws.alloc(&dx, (size_t)nx * T))) break;
+      if ((rc = h2d_rows(dq, q, nq, T, qs, st)) || (rc = h2d_rows(dx, x, nx, T, xs, st))) break;
+      // result slabs of <= 256 MB, double buffered like the pairwise driver
+      const int64_t chunk = std::max<int64_t>(kLbQB, std::min<int64_t>(nq, (((int64_t)256 << 20) / (8 * std::max<int64_t>(nx, 1))) / kLbQB * kLbQB));
+      double* dout = nullptr;
+      if ((rc = ws.alloc(&dout, (size_t)std::min<int64_t>(chunk, nq) * nx))) break;
+      double *qlo = nullptr, *qhi = nullptr, *xT = nullptr, *xloT = nullptr, *xhiT = nullptr;
+      kt.start();
+      if (op == 0) {
+        const int w = lb_warp_size(T, r);
+        if ((rc = ws.alloc(&qlo, (size_t)nq * T)) || (rc = ws.alloc(&qhi, (size_t)nq * T)) || (rc = ws.alloc(&xT, (size_t)nx * T)) ||
+            (rc = ws.alloc(&xloT, (size_t)nx * T)) || (rc = ws.alloc(&xhiT, (size_t)nx * T))) break;
+        k_envelope_rows<<<1024, 256, 0, st>>>(dq, nq, (int)T, w, qlo, qhi);           // LB:417-418
+        k_envelope_T<<<2048, 256, 0, st>>>(dx, nx, (int)T, w, xT, xloT, xhiT);        // fit, LB:371-374
+        WB_CK(cudaGetLastError());
+        local.launches += 2;
+      }
+      for (int64_t i0 = 0; i0 < nq && !rc; i0 += chunk) {
+        const int64_t ni = std::min(chunk, nq - i0);
+        if (op == 0) {
+          LbMatArgs a;
+          a.q = dq + i0 * T; a.qlo = qlo + i0 * T; a.qhi = qhi + i0 * T; a.xT = xT; a.xloT = xloT; a.xhiT = xhiT;
+          a.nq = ni; a.nx = nx; a.T = (int)T; a.out = dout; a.ld = nx;
+          const long long tasks = ((nx + kLbNT - 1) / kLbNT) * ((ni + kLbQB - 1) / kLbQB);
+          const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(tasks, (long long)di.sms * 8));
+          if (kind == 1) k_lb_keogh_matrix<true, false><<<grid, kLbNT, 0, st>>>(a);
+          else if (kind == 2) k_lb_keogh_matrix<false, true><<<grid, kLbNT, 0, st>>>(a);
+          else k_lb_keogh_matrix<true, true><<<grid, kLbNT, 0, st>>>(a);
+        } else {
+          k_lb_kim_matrix<<<(unsigned)std::min<long long>((ni * nx + 255) / 256, (long long)di.sms * 16), 256, 0, st>>>(dq + i0 * T, ni, dx, nx, (int)T, dout, nx);
+        }
+        if (cudaGetLastError() != cudaSuccess) { set_err("lower-bound kernel launch failed"); rc = 1; break; }
+        local.launches += 1;
+        if (cudaMemcpyAsync(out + i0 * nx, dout, sizeof(double) * ni * nx, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) { set_err("device-to-host copy of the lower-bound slab failed"); rc = 1; break; }
+      }
+      kt.stop();
+    } while (0);
+    total.stop();
+    if (!rc) { cudaStreamSynchronize(st); local.total_ms = total.ms(); local.kernel_ms = kt.ms(); local.pairs = nq * nx; local.cells = nq * nx * T; }
+  }
+  cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  if (stats) *stats = local;
+  return rc;
+}
+
 static int check_common(int metric, const wb_params* p, const void* x, int64_t n, int64_t T) {
   if (!p || !x) { set_err("null argument"); return 1; }
   if (metric < 0 || metric >= M_COUNT) { set_err("unknown metric id"); return 1; }
@@ -666,6 +744,22 @@ int wb_cuda_pairwise_dev(int metric, const wb_params* params, const double* d_x,
   if (rc) return rc;
   if (stats) { *stats = local; stats->kernel_ms = kms; stats->total_ms = kms; }
   return 0;
+}
+
+int wb_cuda_lb_keogh(const double* q, int64_t nq, int64_t q_stride, const double* x, int64_t nx, int64_t x_stride,
+                     int64_t T, double r, int kind, double* out, int device, wb_stats* stats) {
+  if (!q || !x || !out) { set_err("null argument"); return 1; }
+  if (nq < 1 || nx < 1 || T < 1) { set_err("empty input"); return 1; }
+  if (!(r >= 0.0 && r <= 1.0)) { set_err("r must be in [0, 1]"); return 1; }
+  if (kind < 0 || kind > 2) { set_err("kind must be 0 (both), 1 (left) or 2 (right)"); return 1; }
+  return run_lb(0, q, nq, q_stride, x, nx, x_stride, T, r, kind, out, device, stats);
+}
+
+int wb_cuda_lb_kim(const double* q, int64_t nq, int64_t q_stride, const double* x, int64_t nx, int64_t x_stride,
+                   int64_t T, double* out, int device, wb_stats* stats) {
+  if (!q || !x || !out) { set_err("null argument"); return 1; }
+  if (nq < 1 || nx < 1 || T < 1) { set_err("empty input"); return 1; }
+  return run_lb(1, q, nq, q_stride, x, nx, x_stride, T, 0.0, 0, out, device, stats);
 }
 
 int wb_cuda_fp64_peak(int mix, double* inst_per_s, double* sm_mhz_est) {
