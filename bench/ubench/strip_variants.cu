@@ -67,13 +67,15 @@ static void run_issue(const char* name, int ninst, int sms, int warps_per_smsp) 
 struct Result { double ms; double gcups; double checksum; };
 
 template <class M, int W, int NR, int NWARPS, int MINB, bool GRING = false>
-static Result run_variant(const char* pname, int ops, const M& m, const double* dx, const double* dy, long long nx, long long ny, int T, int R,
+static Result run_variant(const char* pname, int ops, const M& m, const void* dxv, const void* dyv, long long nx, long long ny, int T, int R,
                           double* dout, unsigned long long* counter, int sms, int reps) {
-  KArgs a; memset(&a, 0, sizeof a);
+  using F = typename M::real;
+  const F* dx = (const F*)dxv; const F* dy = (const F*)dyv;
+  KArgsT<F> a; memset(&a, 0, sizeof a);
   a.x = dx; a.y = dy; a.nx = nx; a.ny = ny; a.Tx = T; a.Ty = T; a.g = make_geom(T, T, R);
   a.NS = strip_ring_slots(a.g, W); a.out = dout; a.ld = ny; a.counter = counter; a.mode = PM_PAIRWISE;
   a.nyb = (ny + 31) / 32; a.ntasks = nx * a.nyb;
-  size_t smem = GRING ? 0 : (size_t)NWARPS * a.NS * 32 * sizeof(double);
+  size_t smem = GRING ? 0 : (size_t)NWARPS * a.NS * 32 * sizeof(F);
   auto kern = k_strip<M, W, NWARPS * 32, MINB, false, NR, GRING>;
   Result r{0, 0, 0};
   if (smem > 232448) { printf("strip W=%2d NR=%d warps/CTA=%d: does not fit in shared memory\n", W, NR, NWARPS); r.ms = -1; return r; }
@@ -81,7 +83,7 @@ static Result run_variant(const char* pname, int ops, const M& m, const double* 
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NWARPS * 32, smem));
   if (per_sm < 1) { r.ms = -2; return r; }
-  if (GRING) { if (per_sm > MINB) per_sm = MINB; CK(cudaMalloc(&a.gring, (size_t)sms * per_sm * NWARPS * a.NS * 32 * sizeof(double))); }
+  if (GRING) { if (per_sm > MINB) per_sm = MINB; CK(cudaMalloc(&a.gring, (size_t)sms * per_sm * NWARPS * a.NS * 32 * sizeof(F))); }
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   float best = 1e30f;
   for (int rep = 0; rep < reps + 1; ++rep) {
@@ -147,7 +149,21 @@ int main(int argc, char** argv) {
   EdrPolicy md; md.eps_param = 0.25; md.eps = 0.25;
   MsmPolicy mm; mm.cf = 1.0f; mm.c = 1.0;
   TwePolicy mt; mt.pen = 1.001; mt.tw = dtw + table_center(T + 1);
+  // fp32 mode: float copies of the operands and tables
+  std::vector<float> hxf(hx.begin(), hx.end()), hyf(hy.begin(), hy.end()), hwf(hw.begin(), hw.end()), htwf(htw.begin(), htw.end());
+  float *dxf, *dyf, *dwf, *dtwf;
+  CK(cudaMalloc(&dxf, hxf.size() * 4)); CK(cudaMalloc(&dyf, hyf.size() * 4)); CK(cudaMalloc(&dwf, hwf.size() * 4)); CK(cudaMalloc(&dtwf, htwf.size() * 4));
+  CK(cudaMemcpy(dxf, hxf.data(), hxf.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dyf, hyf.data(), hyf.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dwf, hwf.data(), hwf.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dtwf, htwf.data(), htwf.size() * 4, cudaMemcpyHostToDevice));
+  DtwPolicy<false, false, float> fm; fm.w = nullptr; fm.p = 0;
+  DtwPolicy<false, true, float> fa; fa.w = nullptr; fa.p = 1.0f;
+  MsmPolicyT<float> fmm; fmm.cf = 1.0f; fmm.c = 1.0f;
+  TwePolicyT<float> ft; ft.pen = 1.001f; ft.tw = dtwf + table_center(T + 1);
   int set = argc > 6 ? atoi(argv[6]) : 0;
+#define RVF(P, NAME, OPS, OBJ, W, NR, NW, MB, GR) run_variant<P, W, NR, NW, MB, GR>(NAME, OPS, OBJ, dxf, dyf, nx, ny, T, R, dout, counter, sms, reps);
+#define FG(W, NR, NW, MB) RVF(decltype(fm), "dtw32", 3, fm, W, NR, NW, MB, true)
+#define FV(W, NR, NW, MB) RVF(decltype(fm), "dtw32", 3, fm, W, NR, NW, MB, false)
+#define FO(W, NR, NW, MB) RVF(decltype(fa), "adtw32", 5, fa, W, NR, NW, MB, true) RVF(decltype(fmm), "msm32", 8, fmm, W, NR, NW, MB, true) RVF(decltype(ft), "twe32", 10, ft, W, NR, NW, MB, true)
 #define RV(P, NAME, OPS, OBJ, W, NR, NW, MB, GR) run_variant<P, W, NR, NW, MB, GR>(NAME, OPS, OBJ, dx, dy, nx, ny, T, R, dout, counter, sms, reps);
 #define V(W, NR, NW, MB) RV(decltype(m), "dtw", 5, m, W, NR, NW, MB, false)
 #define G(W, NR, NW, MB) RV(decltype(m), "dtw", 5, m, W, NR, NW, MB, true)
@@ -162,6 +178,13 @@ int main(int argc, char** argv) {
     V(8, 2, 8, 2) V(8, 4, 8, 2) V(8, 6, 8, 2) V(8, 2, 16, 1) V(6, 2, 8, 2) V(6, 2, 10, 2) V(4, 2, 12, 2)
   } else if (set == 2) {  // the other metrics, cfg2 shape
     GP(8, 4, 12, 1) GP(8, 4, 16, 1) GP(8, 2, 16, 1) GP(12, 4, 12, 1) GP(12, 6, 12, 1) GP(8, 6, 12, 1)
+  } else if (set == 4) {  // fp32 mode, dtw (tall bands: global buffers; also shared memory, which now fits more warps)
+    FG(12, 6, 12, 1) FG(12, 4, 16, 1) FG(16, 4, 16, 1) FG(16, 6, 16, 1) FG(16, 8, 16, 1) FG(24, 4, 12, 1) FG(24, 6, 12, 1) FG(16, 4, 24, 1) FG(16, 4, 12, 2) FG(32, 4, 8, 1) FG(20, 6, 16, 1)
+    FV(16, 4, 12, 1) FV(16, 6, 12, 1) FV(24, 4, 12, 1) FV(12, 6, 12, 1)
+  } else if (set == 5) {  // fp32 mode, narrow bands (shared memory)
+    FV(8, 2, 8, 2) FV(8, 4, 8, 2) FV(16, 4, 8, 2) FV(16, 2, 8, 2) FV(16, 4, 16, 1) FV(12, 4, 16, 1) FV(16, 4, 12, 2)
+  } else if (set == 6) {  // fp32 mode, other metrics
+    FO(12, 6, 12, 1) FO(16, 4, 16, 1) FO(16, 6, 16, 1) FO(24, 4, 12, 1) FO(8, 4, 16, 1)
   } else {  // long series (cfg5 shape): msm / twe
     GL(16, 4, 8, 1) GL(12, 4, 8, 1) GL(12, 4, 12, 1) GL(8, 4, 12, 1) GL(8, 4, 16, 1) GL(8, 2, 16, 1) GL(12, 6, 12, 1) GL(8, 4, 8, 2)
   }

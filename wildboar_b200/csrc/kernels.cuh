@@ -115,10 +115,12 @@ __global__ void __launch_bounds__(NT, MINB) k_strip(KArgsT<typename M::real> a, 
     const F ab = EA ? (F)a.thr[i] : Num<F>::inf();
     const double d = (double)strip_pair<M, W, EA, NR, 32>(a.g, mm, a.x + i * a.Tx, a.y + j * a.Ty, bnd, 32, ab);
     if (valid) {
-      if (a.mode == PM_PAIRED) a.out[i] = d;
+      // results are written once and never re-read by the kernel: streaming stores keep them from
+      // displacing the boundary buffers / y tiles in L2
+      if (a.mode == PM_PAIRED) __stcs(&a.out[i], d);
       else {
-        a.out[i * a.ld + j] = d;
-        if (a.mode == PM_SELF && a.mirror) a.out[j * a.ld + i] = d;
+        __stcs(&a.out[i * a.ld + j], d);
+        if (a.mode == PM_SELF && a.mirror) __stcs(&a.out[j * a.ld + i], d);
       }
     }
     __syncwarp();

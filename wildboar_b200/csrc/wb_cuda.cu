@@ -12,6 +12,7 @@
 #include <limits>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/wb_cuda.h"
@@ -95,6 +96,41 @@ static int64_t cells_per_pair(int Tx, int Ty, int R) {
   return c;
 }
 
+// The global boundary buffers are written once and read once one strip later; between the two, every other
+// warp's buffer traffic and the streaming result stores pass through L2.  Marking the buffer range as an
+// L2 PERSISTING access-policy window (misses: streaming) keeps the dirty lines from being evicted to HBM
+// before they are consumed (profiles/r01d_l2_persist.md).  WILDBOAR_CUDA_L2_PERSIST=0 disables it.
+static bool l2_persist_window(cudaStream_t st, void* base, size_t bytes) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("WILDBOAR_CUDA_L2_PERSIST"); enabled = (e && e[0] == '0') ? 0 : 1; }
+  if (!enabled) return false;
+  cudaStreamAttrValue attr;
+  memset(&attr, 0, sizeof attr);
+  if (base == nullptr || bytes == 0) {  // reset
+    attr.accessPolicyWindow.num_bytes = 0;
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+    return false;
+  }
+  int dev = 0, max_persist = 0, max_window = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+  cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+  if (max_persist <= 0 || max_window <= 0) return false;
+  static std::atomic<unsigned long long> limit_set{0};
+  if (dev < 64 && !((limit_set.load() >> dev) & 1ULL)) {
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+    limit_set.fetch_or(1ULL << dev);
+  }
+  const size_t win = std::min(bytes, (size_t)max_window);
+  attr.accessPolicyWindow.base_ptr = base;
+  attr.accessPolicyWindow.num_bytes = win;
+  attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)max_persist / (double)win);
+  attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) { cudaGetLastError(); return false; }
+  return true;
+}
+
 // Strip-kernel configurations (measured on B200: profiles/r01c_variants.md).
 //   NARROW (H < 32)       : W = 8 (W = 4 for 8 <= H < 16), NR = 2, boundary buffers in SHARED memory,
 //                           two CTAs of 8 warps per SM.
@@ -125,14 +161,18 @@ static int launch_strip_cfg(Workspace& ws, KArgsT<typename M::real> a, const M& 
   per_sm = std::min(per_sm, MINB);
   long long grid = (long long)sms * per_sm;
   if (a.ntasks < grid * nwarps) grid = std::max<long long>(1, (a.ntasks + nwarps - 1) / nwarps);
+  bool window_set = false;
   if (GRING) {
     F* ring = nullptr;
+    const size_t ring_bytes = (size_t)grid * nwarps * a.NS * 32 * sizeof(F);
     if (ws.alloc(&ring, (size_t)grid * nwarps * a.NS * 32)) return 1;
     a.gring = ring;
+    window_set = l2_persist_window(st, ring, ring_bytes);
   }
   if (cfg) { cfg->strip_w = W; cfg->strip_nr = NR; cfg->strip_warps = nwarps; cfg->strip_gring = GRING ? 1 : 0; }
   kern<<<(unsigned)grid, nwarps * 32, smem, st>>>(a, m);
   WB_CK(cudaGetLastError());
+  if (window_set) l2_persist_window(st, nullptr, 0);
   return 0;
 }
 
@@ -140,6 +180,22 @@ template <class M, bool EA>
 static int launch_strip(Workspace& ws, const KArgsT<typename M::real>& a, const M& m, size_t smem_cap, int sms, wb_stats* cfg) {
   using C = StripCfg<M>;
   const size_t per_warp = (size_t)strip_ring_slots(a.g, 16) * 32 * sizeof(typename M::real);  // widest strips
+  if constexpr (sizeof(typename M::real) == 4) {
+    // optional fp32 mode (profiles/r01d_variants_fp32.md): half-size boundary buffers -> shared memory holds
+    // 12 warps for cfg3-like bands; otherwise global buffers with wider strips
+    if (a.g.H >= 32) {
+      const size_t pw12 = (size_t)strip_ring_slots(a.g, 12) * 32 * sizeof(float);
+      const size_t pw16 = (size_t)strip_ring_slots(a.g, 16) * 32 * sizeof(float);
+      const size_t ring_budget = (size_t)8 << 30;
+      const int cap = (int)std::max<size_t>(1, ring_budget / (pw16 * (size_t)sms));
+      if (std::is_same<M, DtwPolicy<false, false, float>>::value && pw12 * 12 <= smem_cap && a.g.H >= 24)
+        return launch_strip_cfg<M, 12, 384, 1, EA, 6, false>(ws, a, m, 12, sms, smem_cap, cfg);
+      if (strip_ring_slots(a.g, 16) <= 230) return launch_strip_cfg<M, 16, 512, 1, EA, 6, true>(ws, a, m, std::min(16, cap), sms, smem_cap, cfg);
+      return launch_strip_cfg<M, 16, 512, 1, EA, 4, true>(ws, a, m, std::min(16, cap), sms, smem_cap, cfg);
+    }
+    if (a.g.H >= 16 || a.g.H < 8) return launch_strip_cfg<M, 8, 256, 2, EA, 2, false>(ws, a, m, 8, sms, smem_cap, cfg);
+    return launch_strip_cfg<M, 4, 256, 2, EA, 2, false>(ws, a, m, 8, sms, smem_cap, cfg);
+  }
   if (a.g.H >= 32) {
     // keep the global rings of one launch below ~8 GB whatever the series length
     const size_t ring_budget = (size_t)8 << 30;

@@ -26,18 +26,42 @@ def _wrap(orig, ours):
     return wrapper
 
 
+# callers that bind the three functions by name at import time: KNN / KMeans / KMedoids
+# (`distance/_neighbors.py:121-160, 262-283, 320-347`), MDS, silhouette, change-point segmentation, counterfactuals
+_CALLER_MODULES = (
+    "wildboar.distance._neighbors", "wildboar.distance._manifold", "wildboar.metrics._cluster", "wildboar.segment._base",
+    "wildboar.explain.counterfactual._nice", "wildboar.explain.counterfactual._nn", "wildboar.explain.counterfactual._proto",
+)
+
+
 def patch():
-    """Install the wrappers; returns the list of patched callables' qualified names."""
-    mods = [importlib.import_module("wildboar.distance"), importlib.import_module("wildboar.distance._distance")]
+    """Install the wrappers; returns the list of patched callables' qualified names.
+
+    Besides ``wildboar.distance`` and ``wildboar.distance._distance`` every already-imported (or known)
+    ``wildboar.*`` module that holds a reference to one of the three functions is re-pointed, so the
+    estimators built on them (KNeighborsClassifier, KMeans, KMedoids, MDS, silhouette ...) use the CUDA
+    path for elastic metrics without any change."""
+    import sys
+    base = importlib.import_module("wildboar.distance._distance")
+    importlib.import_module("wildboar.distance")
+    for m in _CALLER_MODULES:
+        try:
+            importlib.import_module(m)
+        except Exception:  # optional parts of wildboar that are not importable here
+            pass
+    originals = {name: getattr(base, name) for name in _NAMES}
+    originals = {n: getattr(f, "__wildboar_b200_original__", f) for n, f in originals.items()}
+    wrappers = {name: _wrap(originals[name], getattr(_d, name)) for name in _NAMES}
     done = []
-    for mod in mods:
+    for modname, mod in list(sys.modules.items()):
+        if mod is None or not (modname == "wildboar" or modname.startswith("wildboar.")):
+            continue
         for name in _NAMES:
-            cur = getattr(mod, name)
-            if hasattr(cur, "__wildboar_b200_original__"):
-                continue
-            _ORIG[(mod.__name__, name)] = cur
-            setattr(mod, name, _wrap(cur, getattr(_d, name)))
-            done.append(f"{mod.__name__}.{name}")
+            cur = getattr(mod, name, None)
+            if cur is originals[name]:
+                _ORIG[(modname, name)] = cur
+                setattr(mod, name, wrappers[name])
+                done.append(f"{modname}.{name}")
     return done
 
 
