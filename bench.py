@@ -328,7 +328,11 @@ def main():
                 "nominal_peak": nominal, "frac_of_nominal": achieved / nominal,
                 "dtw_mix_peak": peak_mix / 1e9, "frac_of_dtw_mix_peak": achieved / (peak_mix / 1e9),
                 "dtw_mix_peak_note": "register-only loop of the same instruction mix (3 FP64 arith + 2x(DSETP+2 FSEL)): practical issue ceiling, profiles/r01_issue_model.md",
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE full-size launch of this kernel, from the ncu capture of
+                # this very command line (profiles/r01e_traffic_full_cfg3.csv, profiles/r01d_l2_persist.md); ncu cannot run inside
+                # the timed bench, so the number is recorded here for the workload / device count it was measured on
+                "traffic": (16.68e9 if (args.workload == "cfg3" and world == 1 and args.precision == "fp64" and args.profile_rows == 0) else None),
+                "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                 "hbm": {"algorithmic_bytes": int((nx + ny) * T * 8 + nx * ny * 8),
                         "achieved_gbs": ((nx + ny) * T * 8 + nx * ny * 8) / (kernel_ms * 1e-3) / 1e9,
                         "peak_gbs": _measured_hbm()},

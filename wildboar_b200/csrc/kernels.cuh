@@ -69,8 +69,11 @@ __device__ __forceinline__ bool decode_task(const A& a, long long t, int lane, l
     j = i;
     return true;
   }
-  i = t / a.nyb;
-  long long jb = t - i * a.nyb;
+  // x row fastest: the ~2000 warps that are resident at any time then share ONE block of 32 y rows
+  // (L1/L2 resident, 128 KB) and differ in the x row (one broadcast load per DP row), instead of
+  // touching every y row at once (41 MB for cfg3, which the boundary buffers evict from L2)
+  const long long jb = t / a.nx;
+  i = t - jb * a.nx;
   j = jb * 32 + lane;
   valid = j < a.ny;
   if (!valid) j = a.ny - 1;
