@@ -22,6 +22,23 @@
 #define CELL_ARITH(d, up, dg, y) asm volatile("{ .reg .f64 v; sub.f64 v, %3, %4; mul.f64 v, v, v; add.f64 %0, %0, v; }" : "+d"(d) : "d"(up), "d"(dg), "d"(xx), "d"(y));
 #define CELL_INT1(d, up, dg, y) asm volatile("{ .reg .pred q; .reg .f64 v, m; .reg .b64 a, b, c; sub.f64 v, %3, %4; mov.b64 a, %1; mov.b64 b, %0; min.u64 c, a, b; mov.b64 m, c; setp.lt.f64 q, %2, m; selp.f64 m, %2, m, q; mul.f64 v, v, v; add.f64 %0, m, v; }" : "+d"(d) : "d"(up), "d"(dg), "d"(xx), "d"(y));
 
+
+// ---- select-pipe experiments: where do the four 32-bit selects of the two mins execute? ----
+// HYB: per min, low half via selp.b32 (ALU pipe), high half via a predicated IMAD (FMA-heavy pipe; `one` is an opaque runtime 1)
+#define CELL_HYB(d, up, dg, y) asm volatile("{ .reg .pred q; .reg .f64 v, m; .reg .b32 al, ah, bl, bh; sub.f64 v, %3, %4; setp.lt.f64 q, %1, %0; mov.b64 {al, ah}, %1; mov.b64 {bl, bh}, %0; selp.b32 bl, al, bl, q; @q mad.lo.u32 bh, ah, %5, 0; mov.b64 m, {bl, bh}; setp.lt.f64 q, %2, m; mov.b64 {al, ah}, %2; selp.b32 bl, al, bl, q; @q mad.lo.u32 bh, ah, %5, 0; mov.b64 m, {bl, bh}; mul.f64 v, v, v; add.f64 %0, m, v; }" : "+d"(d) : "d"(up), "d"(dg), "d"(xx), "d"(y), "r"(onei));
+// IMAD: all four selects as predicated IMADs
+#define CELL_IMAD(d, up, dg, y) asm volatile("{ .reg .pred q; .reg .f64 v, m; .reg .b32 al, ah, bl, bh; sub.f64 v, %3, %4; setp.lt.f64 q, %1, %0; mov.b64 {al, ah}, %1; mov.b64 {bl, bh}, %0; @q mad.lo.u32 bl, al, %5, 0; @q mad.lo.u32 bh, ah, %5, 0; mov.b64 m, {bl, bh}; setp.lt.f64 q, %2, m; mov.b64 {al, ah}, %2; @q mad.lo.u32 bl, al, %5, 0; @q mad.lo.u32 bh, ah, %5, 0; mov.b64 m, {bl, bh}; mul.f64 v, v, v; add.f64 %0, m, v; }" : "+d"(d) : "d"(up), "d"(dg), "d"(xx), "d"(y), "r"(onei));
+// PMOV: predicated mov.b32 (ptxas picks the pipe)
+#define CELL_PMOV(d, up, dg, y) asm volatile("{ .reg .pred q; .reg .f64 v, m; .reg .b32 al, ah, bl, bh; sub.f64 v, %3, %4; setp.lt.f64 q, %1, %0; mov.b64 {al, ah}, %1; mov.b64 {bl, bh}, %0; @q mov.b32 bl, al; @q mov.b32 bh, ah; mov.b64 m, {bl, bh}; setp.lt.f64 q, %2, m; mov.b64 {al, ah}, %2; @q mov.b32 bl, al; @q mov.b32 bh, ah; mov.b64 m, {bl, bh}; mul.f64 v, v, v; add.f64 %0, m, v; }" : "+d"(d) : "d"(up), "d"(dg), "d"(xx), "d"(y));
+// PADD: second min folded into two predicated DADDs (no selects for it): q ? dg + c : m + c
+#define CELL_PADD(d, up, dg, y) asm volatile("{ .reg .pred q; .reg .f64 v, m; sub.f64 v, %3, %4; setp.lt.f64 q, %1, %0; selp.f64 m, %1, %0, q; setp.lt.f64 q, %2, m; mul.f64 v, v, v; @q add.f64 %0, %2, v; @!q add.f64 %0, m, v; }" : "+d"(d) : "d"(up), "d"(dg), "d"(xx), "d"(y));
+// HYBPADD: first min hybrid (ALU + IMAD), second min as predicated DADDs
+#define CELL_HYBPADD(d, up, dg, y) asm volatile("{ .reg .pred q; .reg .f64 v, m; .reg .b32 al, ah, bl, bh; sub.f64 v, %3, %4; setp.lt.f64 q, %1, %0; mov.b64 {al, ah}, %1; mov.b64 {bl, bh}, %0; selp.b32 bl, al, bl, q; @q mad.lo.u32 bh, ah, %5, 0; mov.b64 m, {bl, bh}; setp.lt.f64 q, %2, m; mul.f64 v, v, v; @q add.f64 %0, %2, v; @!q add.f64 %0, m, v; }" : "+d"(d) : "d"(up), "d"(dg), "d"(xx), "d"(y), "r"(onei));
+// SHF: high half via funnel shift by 0 under predicate? (ALU) -- control: selp both halves but independent int regs not from FP64 results
+#define CELL_FSELONLY(d, up, dg, y) asm volatile("{ .reg .pred q; .reg .f64 v, m; sub.f64 v, %3, %4; setp.lt.f64 q, %1, %0; selp.f64 m, %1, %0, q; mul.f64 v, v, v; add.f64 %0, m, v; }" : "+d"(d) : "d"(up), "d"(dg), "d"(xx), "d"(y));
+// MIXSEL: low halves via selp.b32 (SEL), high halves via selp.f32 (FSEL): are they different pipes?
+#define CELL_MIXSEL(d, up, dg, y) asm volatile("{ .reg .pred q; .reg .f64 v, m; .reg .b32 al, bl; .reg .f32 ah, bh; sub.f64 v, %3, %4; setp.lt.f64 q, %1, %0; mov.b64 {al, ah}, %1; mov.b64 {bl, bh}, %0; selp.b32 bl, al, bl, q; selp.f32 bh, ah, bh, q; mov.b64 m, {bl, bh}; setp.lt.f64 q, %2, m; mov.b64 {al, ah}, %2; selp.b32 bl, al, bl, q; selp.f32 bh, ah, bh, q; mov.b64 m, {bl, bh}; mul.f64 v, v, v; add.f64 %0, m, v; }" : "+d"(d) : "d"(up), "d"(dg), "d"(xx), "d"(y));
+
 template <int MIX>
 __global__ void __launch_bounds__(256) k(int iters, double seed, double* out) {
   double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
@@ -30,6 +47,7 @@ __global__ void __launch_bounds__(256) k(int iters, double seed, double* out) {
   float f0 = 1, f1 = 2, f2 = 3, f3 = 4, f4 = 5, f5 = 6, f6 = 7, f7 = 8;
   const double inc = seed * 1e-9 + 1e-7, one = 1.0 + seed * 1e-12, xx = seed * 0.37;
   const int k = (int)blockIdx.x | 1;
+  const int onei = (iters > 0) ? 1 : (int)seed;
 #pragma unroll 1
   for (int it = 0; it < iters; ++it) {
     if (MIX == 0) { D(a0) D(a1) D(a2) D(a3) D(a4) D(a5) D(a6) D(a7) }
@@ -48,6 +66,13 @@ __global__ void __launch_bounds__(256) k(int iters, double seed, double* out) {
     if (MIX == 12) { CELL_NOSETP(a0, a4, a1, a5, j0) CELL_NOSETP(a1, a5, a2, a6, j1) CELL_NOSETP(a2, a6, a3, a7, j2) CELL_NOSETP(a3, a7, a0, a4, j3) CELL_NOSETP(a4, a0, a5, a1, j4) CELL_NOSETP(a5, a1, a6, a2, j5) CELL_NOSETP(a6, a2, a7, a3, j6) CELL_NOSETP(a7, a3, a4, a0, j7) }
     if (MIX == 13) { ALL8(CELL_ARITH) }
     if (MIX == 14) { ALL8(CELL_INT1) }
+    if (MIX == 15) { ALL8(CELL_HYB) }
+    if (MIX == 16) { ALL8(CELL_IMAD) }
+    if (MIX == 17) { ALL8(CELL_PMOV) }
+    if (MIX == 18) { ALL8(CELL_PADD) }
+    if (MIX == 19) { ALL8(CELL_HYBPADD) }
+    if (MIX == 20) { ALL8(CELL_FSELONLY) }
+    if (MIX == 21) { ALL8(CELL_MIXSEL) }
   }
   out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 + (double)(i0 + i1 + i2 + i3 + i4 + i5 + i6 + i7 + j0 + j1 + j2 + j3 + j4 + j5 + j6 + j7) + (double)(f0 + f1 + f2 + f3 + f4 + f5 + f6 + f7);
 }
@@ -89,6 +114,13 @@ int main() {
     run<12>("8 cells, 4 FSEL no DSETP", 64, 24, sms, w, clk);
     run<13>("8 cells, arithmetic only", 24, 24, sms, w, clk);
     run<14>("8 cells, 1 min.u64 + 1 DSETP min", 72, 32, sms, w, clk);
+    run<15>("8 cells, selects: SEL lo + IMAD hi", 72, 40, sms, w, clk);
+    run<16>("8 cells, selects: 4 pred IMAD", 72, 40, sms, w, clk);
+    run<17>("8 cells, selects: 4 pred MOV", 72, 40, sms, w, clk);
+    run<18>("8 cells, min2 as 2 pred DADD", 64, 48, sms, w, clk);
+    run<19>("8 cells, min1 SEL+IMAD, min2 pred DADD", 64, 48, sms, w, clk);
+    run<21>("8 cells, selects: SEL lo + FSEL hi", 72, 40, sms, w, clk);
+    run<20>("8 cells, one min only (DSETP+2FSEL)", 48, 32, sms, w, clk);
   }
   return 0;
 }
