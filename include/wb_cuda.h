@@ -92,6 +92,23 @@ int wb_cuda_paired(int metric, const wb_params *params,
                    const double *y, int64_t Ty, int64_t y_stride,
                    double *out, const int *devices, int n_devices, wb_stats *stats);
 
+/* Multivariate forms: x is (nx, n_dims, Tx) with `x_stride` elements between samples and
+ * `x_dim_stride` elements between the dimensions of one sample (the reference's TSArray,
+ * utils/__init__.pxd:4), y likewise; y == NULL selects the self join (_singleton_pairwise_distance).
+ * combine 0 = dim="mean": ONE (nx, ny) matrix, the per-dimension distances summed in dimension order and
+ * divided by n_dims on the device (bit-equal to np.mean(list, axis=0), _distance.py:1250-1253 / 1289-1292);
+ * combine 1 = dim="full": out is (n_dims, nx, ny).  The dimensions are uploaded once and the result crosses
+ * PCIe once.  Replaces the per-dimension Python loops of pairwise_distance (_distance.py:1245-1297) and
+ * paired_distance (_distance.py:1163-1169; out is (n,) or (n_dims, n); operands swapped as in wb_cuda_paired). */
+int wb_cuda_pairwise_nd(int metric, const wb_params *params,
+                        const double *x, int64_t nx, int64_t n_dims, int64_t Tx, int64_t x_stride, int64_t x_dim_stride,
+                        const double *y, int64_t ny, int64_t Ty, int64_t y_stride, int64_t y_dim_stride,
+                        int combine, double *out, const int *devices, int n_devices, wb_stats *stats);
+int wb_cuda_paired_nd(int metric, const wb_params *params,
+                      const double *x, int64_t n, int64_t n_dims, int64_t Tx, int64_t x_stride, int64_t x_dim_stride,
+                      const double *y, int64_t Ty, int64_t y_stride, int64_t y_dim_stride,
+                      int combine, double *out, const int *devices, int n_devices, wb_stats *stats);
+
 /* k nearest y for every x under the reference's sequential early-abandoning scan.
  * out_idx / out_dist: (nx, k) in the reference heap's array order (utils/_misc.pyx:62-107).
  * lower_bound: optional (nx, ny) matrix, pairs with lower_bound >= running threshold are

@@ -65,6 +65,10 @@ def lib():
                 L.wb_cuda_pairwise.argtypes = [ci, PP, _DP, i64, i64, i64, _DP, i64, i64, i64, _DP, DV, ci, SP]
                 L.wb_cuda_pairwise_self.argtypes = [ci, PP, _DP, i64, i64, i64, _DP, DV, ci, SP]
                 L.wb_cuda_paired.argtypes = [ci, PP, _DP, i64, i64, i64, _DP, i64, i64, _DP, DV, ci, SP]
+                L.wb_cuda_pairwise_nd.argtypes = [ci, PP, _DP, i64, i64, i64, i64, i64, _DP, i64, i64, i64, i64, ci, _DP, DV,
+                                                  ci, SP]
+                L.wb_cuda_paired_nd.argtypes = [ci, PP, _DP, i64, i64, i64, i64, i64, _DP, i64, i64, i64, ci, _DP, DV, ci,
+                                                SP]
                 L.wb_cuda_argmin.argtypes = [ci, PP, _DP, i64, i64, i64, _DP, i64, i64, i64, i64, _DP, ci, _IP, _DP,
                                              DV, ci, SP]
                 L.wb_cuda_pairwise_dev.argtypes = [ci, PP, C.c_void_p, i64, i64, C.c_void_p, i64, i64, C.c_void_p,
@@ -191,6 +195,57 @@ def paired(metric_id, params, x, y):
     dv, nd = _dev_array(_resolve_devices(_est_cells(n, Tx, Ty, params.r)))
     _check(lib().wb_cuda_paired(metric_id, C.byref(params), xp, n, Tx, xs, yp, Ty, ys, out.ctypes.data_as(_DP), dv, nd,
                                 C.byref(st)))
+    _tls.stats = st.as_dict()
+    return out
+
+
+def _samples(a):
+    """(array, pointer, n, n_dims, T, sample stride, dim stride) of a 3-D float64 TSArray (strides in elements)."""
+    assert a.dtype == np.float64 and a.ndim == 3
+    n, nd, T = a.shape
+    ok = (T <= 1 or a.strides[2] == 8) and a.strides[0] % 8 == 0 and a.strides[1] % 8 == 0
+    ss, ds = a.strides[0] // 8, a.strides[1] // 8
+    if not ok or (nd > 1 and ds < T) or (n > 1 and ss < T):
+        a = np.ascontiguousarray(a)
+        ss, ds = nd * T, T
+    if n == 1:
+        ss = max(ss, nd * T)
+    return a, a.ctypes.data_as(_DP), n, nd, T, ss, ds
+
+
+def pairwise_nd(metric_id, params, x, y, combine):
+    """Multivariate pairwise / self join; combine "mean" -> (nx, ny), "full" -> (n_dims, nx, ny)."""
+    apply_engine_override(params)
+    x, xp, nx, nd, Tx, xss, xds = _samples(x)
+    full = combine == "full"
+    st = WbStats()
+    if y is None:
+        out = np.empty((nd, nx, nx) if full else (nx, nx), dtype=np.float64)
+        dv, ndv = _dev_array(_resolve_devices(nd * _est_cells(nx * nx / 2, Tx, Tx, params.r)))
+        _check(lib().wb_cuda_pairwise_nd(metric_id, C.byref(params), xp, nx, nd, Tx, xss, xds, None, 0, 0, 0, 0,
+                                         1 if full else 0, out.ctypes.data_as(_DP), dv, ndv, C.byref(st)))
+    else:
+        y, yp, ny, ndy, Ty, yss, yds = _samples(y)
+        assert nd == ndy
+        out = np.empty((nd, nx, ny) if full else (nx, ny), dtype=np.float64)
+        dv, ndv = _dev_array(_resolve_devices(nd * _est_cells(nx * ny, Tx, Ty, params.r)))
+        _check(lib().wb_cuda_pairwise_nd(metric_id, C.byref(params), xp, nx, nd, Tx, xss, xds, yp, ny, Ty, yss, yds,
+                                         1 if full else 0, out.ctypes.data_as(_DP), dv, ndv, C.byref(st)))
+    _tls.stats = st.as_dict()
+    return out
+
+
+def paired_nd(metric_id, params, x, y, combine):
+    apply_engine_override(params)
+    x, xp, n, nd, Tx, xss, xds = _samples(x)
+    y, yp, ny, ndy, Ty, yss, yds = _samples(y)
+    assert n == ny and nd == ndy
+    full = combine == "full"
+    out = np.empty((nd, n) if full else (n,), dtype=np.float64)
+    st = WbStats()
+    dv, ndv = _dev_array(_resolve_devices(nd * _est_cells(n, Tx, Ty, params.r)))
+    _check(lib().wb_cuda_paired_nd(metric_id, C.byref(params), xp, n, nd, Tx, xss, xds, yp, Ty, yss, yds,
+                                   1 if full else 0, out.ctypes.data_as(_DP), dv, ndv, C.byref(st)))
     _tls.stats = st.as_dict()
     return out
 

@@ -41,6 +41,11 @@ struct KArgsT {
   F* scratch;         // row-scan engine: 2 rows per thread, interleaved
   long long sstride;  // = total threads
   int srows;          // elements per scratch row
+  // multivariate dim="mean" (DI:1289-1297, np.mean over the per-dimension matrices): the launches of
+  // dimensions 1.. ADD to the stored value (dimension order = numpy's reduction order along axis 0) and
+  // the last one divides by the number of dimensions
+  int acc;            // 1: out = out + d
+  double div;         // != 0: out = (...) / div
 };
 using KArgs = KArgsT<double>;
 
@@ -85,6 +90,14 @@ __device__ __forceinline__ bool decode_task(const A& a, long long t, int lane, l
   return true;
 }
 
+// dim="mean": sum the per-dimension distances in dimension order, divide after the last one
+template <class A>
+__device__ __forceinline__ double combine_dims(const A& a, const double* po, double d) {
+  if (a.acc) d = *po + d;
+  if (a.div != 0.0) d = d / a.div;
+  return d;
+}
+
 __device__ __forceinline__ long long next_task(unsigned long long* counter, int lane) {
   unsigned long long t = 0;
   if (lane == 0) t = atomicAdd(counter, 1ULL);
@@ -120,11 +133,10 @@ __global__ void __launch_bounds__(NT, MINB) k_strip(KArgsT<typename M::real> a, 
     if (valid) {
       // results are written once and never re-read by the kernel: streaming stores keep them from
       // displacing the boundary buffers / y tiles in L2
-      if (a.mode == PM_PAIRED) __stcs(&a.out[i], d);
-      else {
-        __stcs(&a.out[i * a.ld + j], d);
-        if (a.mode == PM_SELF && a.mirror) __stcs(&a.out[j * a.ld + i], d);
-      }
+      double* const po = a.mode == PM_PAIRED ? &a.out[i] : &a.out[i * a.ld + j];
+      const double r = combine_dims(a, po, d);
+      __stcs(po, r);
+      if (a.mode == PM_SELF && a.mirror) __stcs(&a.out[j * a.ld + i], r);
     }
     __syncwarp();
   }
@@ -154,11 +166,12 @@ __global__ void __launch_bounds__(NT) k_rowscan(KArgsT<typename M::real> a, M m)
     F mmax = F(0);
     const double d = (double)rowscan_pair<M>(a.g, mm, a.x + i * a.Tx, a.y + j * a.Ty, b0, b1, a.sstride, md, &mmax);
     if (valid) {
-      if (a.mode == PM_PAIRED) a.out[i] = d;
-      else {
-        a.out[i * a.ld + j] = d;
+      double* const po = a.mode == PM_PAIRED ? &a.out[i] : &a.out[i * a.ld + j];
+      const double r = combine_dims(a, po, d);
+      *po = r;
+      if (a.mode != PM_PAIRED) {
         if (a.out_m) a.out_m[i * a.ld + j] = (double)mmax;
-        if (a.mode == PM_SELF && a.mirror) a.out[j * a.ld + i] = d;
+        if (a.mode == PM_SELF && a.mirror) a.out[j * a.ld + i] = r;
       }
     }
     __syncwarp();

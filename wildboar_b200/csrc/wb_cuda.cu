@@ -238,6 +238,8 @@ struct DpCall {
   TablesT<float> tabf;
   int R;
   bool degenerate;     // ddtw with min(T) < 3: every distance is 0 (EL:3270)
+  // multivariate dim="mean": accumulate into / scale the stored value (kernels.cuh, combine_dims)
+  int acc; double div;
 };
 
 // Slope transforms, per-series scalars and lookup tables for one (x, y) operand pair.
@@ -324,6 +326,7 @@ static int launch_dp_t(Workspace& ws, const DeviceInfo& di, const DpCall& c, lon
   cudaStream_t st = ws.stream;
   if (nrows <= 0 || ncols <= 0) return 0;
   if (c.degenerate) {
+    if (c.acc) return 0;  // every dimension is degenerate alike: the zeros of dimension 0 stand (0 / n_dims == 0)
     if (c.mode == PM_PAIRED) WB_CK(cudaMemsetAsync(out, 0, sizeof(double) * nrows, st));
     else WB_CK(cudaMemset2DAsync(out, ld * sizeof(double), 0, ncols * sizeof(double), nrows, st));
     return 0;
@@ -339,6 +342,7 @@ static int launch_dp_t(Workspace& ws, const DeviceInfo& di, const DpCall& c, lon
   a.out = out; a.ld = ld; a.out_m = out_m; a.thr = thr;
   a.mode = c.mode; a.row0 = c.row0 + r0 - c0; a.mirror = c.mirror;
   a.list = c.list; a.list_len = c.list_len;
+  a.acc = c.acc; a.div = c.div;
   a.nyb = (ncols + 31) / 32;
   a.ntasks = (c.mode == PM_PAIRED) ? (nrows + 31) / 32 : nrows * a.nyb;
   unsigned long long* counter = nullptr;
@@ -421,6 +425,9 @@ struct HostJob {
   const double* y; int64_t ny, Ty, ys;
   double* out;
   int64_t k; const double* lower_bound; int use_device_lb; int64_t* out_idx;
+  // multivariate (pairwise / self / paired): n_dims >= 1 dimensions, `xds` / `yds` elements between the
+  // dimensions of one sample; combine 0 = "mean" (one matrix), 1 = "full" (n_dims matrices)  (DI:1289-1297)
+  int64_t nd, xds, yds; int combine;
 };
 
 static int h2d_rows(double* dst, const double* src, int64_t rows, int64_t T, int64_t stride, cudaStream_t st) {
@@ -456,31 +463,52 @@ static int device_worker(const HostJob& J, int dev, int64_t lo, int64_t hi, wb_s
     Timer total(st);
     total.start();
     const int64_t rows = hi - lo;
+    const int64_t nd = std::max<int64_t>(J.nd, 1);
     double *dx = nullptr, *dy = nullptr;
     do {
+      // operands are staged densely as (n_dims, samples, T)
+      int64_t xn = 0, xT = 0, yn = 0, yT = 0;  // samples / length of the staged first and second operand
       if (J.kind == 1) {
         // self join: every device holds all of x (columns); its rows are [lo, hi)
-        if ((rc = ws.alloc(&dy, (size_t)J.nx * J.Tx))) break;
-        if ((rc = h2d_rows(dy, J.x, J.nx, J.Tx, J.xs, st))) break;
-        dx = dy + lo * J.Tx;
+        yn = J.nx; yT = J.Tx; xn = J.nx; xT = J.Tx;
+        if ((rc = ws.alloc(&dy, (size_t)nd * J.nx * J.Tx))) break;
+        for (int64_t d = 0; d < nd && !rc; ++d) rc = h2d_rows(dy + d * J.nx * J.Tx, J.x + d * J.xds, J.nx, J.Tx, J.xs, st);
+        if (rc) break;
+        dx = dy;
       } else if (J.kind == 2) {
         // paired: first operand is the USER's y (CD:1632-1647)
-        if ((rc = ws.alloc(&dx, (size_t)rows * J.Ty))) break;
-        if ((rc = ws.alloc(&dy, (size_t)rows * J.Tx))) break;
-        if ((rc = h2d_rows(dx, J.y + lo * J.ys, rows, J.Ty, J.ys, st))) break;
-        if ((rc = h2d_rows(dy, J.x + lo * J.xs, rows, J.Tx, J.xs, st))) break;
+        xn = rows; xT = J.Ty; yn = rows; yT = J.Tx;
+        if ((rc = ws.alloc(&dx, (size_t)nd * rows * J.Ty))) break;
+        if ((rc = ws.alloc(&dy, (size_t)nd * rows * J.Tx))) break;
+        for (int64_t d = 0; d < nd && !rc; ++d) {
+          if ((rc = h2d_rows(dx + d * rows * J.Ty, J.y + d * J.yds + lo * J.ys, rows, J.Ty, J.ys, st))) break;
+          rc = h2d_rows(dy + d * rows * J.Tx, J.x + d * J.xds + lo * J.xs, rows, J.Tx, J.xs, st);
+        }
+        if (rc) break;
       } else {
-        if ((rc = ws.alloc(&dx, (size_t)rows * J.Tx))) break;
-        if ((rc = ws.alloc(&dy, (size_t)J.ny * J.Ty))) break;
-        if ((rc = h2d_rows(dx, J.x + lo * J.xs, rows, J.Tx, J.xs, st))) break;
-        if ((rc = h2d_rows(dy, J.y, J.ny, J.Ty, J.ys, st))) break;
+        xn = rows; xT = J.Tx; yn = J.ny; yT = J.Ty;
+        if ((rc = ws.alloc(&dx, (size_t)nd * rows * J.Tx))) break;
+        if ((rc = ws.alloc(&dy, (size_t)nd * J.ny * J.Ty))) break;
+        for (int64_t d = 0; d < nd && !rc; ++d) {
+          if ((rc = h2d_rows(dx + d * rows * J.Tx, J.x + d * J.xds + lo * J.xs, rows, J.Tx, J.xs, st))) break;
+          rc = h2d_rows(dy + d * J.ny * J.Ty, J.y + d * J.yds, J.ny, J.Ty, J.ys, st);
+        }
+        if (rc) break;
       }
-      DpCall c;
-      memset(&c, 0, sizeof c);
-      c.metric = J.metric; c.p = J.p;
-      if (J.kind == 2) { c.x = dx; c.nx = rows; c.Tx = (int)J.Ty; c.y = dy; c.ny = rows; c.Ty = (int)J.Tx; c.mode = PM_PAIRED; }
-      else if (J.kind == 1) { c.x = dx; c.nx = rows; c.Tx = (int)J.Tx; c.y = dy; c.ny = J.nx; c.Ty = (int)J.Tx; c.mode = PM_SELF; c.row0 = lo; }
-      else { c.x = dx; c.nx = rows; c.Tx = (int)J.Tx; c.y = dy; c.ny = J.ny; c.Ty = (int)J.Ty; c.mode = PM_PAIRWISE; }
+      // one prepared call per dimension (slopes, per-series scalars and tables are per dimension)
+      std::vector<DpCall> cs((size_t)nd);
+      for (int64_t d = 0; d < nd; ++d) {
+        DpCall& c = cs[(size_t)d];
+        memset(&c, 0, sizeof c);
+        c.metric = J.metric; c.p = J.p;
+        const double* xd = dx + d * xn * xT;
+        const double* yd = dy + d * yn * yT;
+        if (J.kind == 2) { c.x = xd; c.nx = rows; c.Tx = (int)xT; c.y = yd; c.ny = rows; c.Ty = (int)yT; c.mode = PM_PAIRED; }
+        else if (J.kind == 1) { c.x = xd + lo * J.Tx; c.nx = rows; c.Tx = (int)J.Tx; c.y = yd; c.ny = J.nx; c.Ty = (int)J.Tx; c.mode = PM_SELF; c.row0 = lo; }
+        else { c.x = xd; c.nx = rows; c.Tx = (int)J.Tx; c.y = yd; c.ny = J.ny; c.Ty = (int)J.Ty; c.mode = PM_PAIRWISE; }
+        if (nd > 1 && J.combine == 0) { c.acc = d > 0; c.div = (d == nd - 1) ? (double)nd : 0.0; }
+      }
+      DpCall& c = cs[0];
 
       if (J.kind == 3) {
         c.ea = 1;
@@ -496,16 +524,24 @@ static int device_worker(const HostJob& J, int dev, int64_t lo, int64_t hi, wb_s
         break;
       }
 
-      if ((rc = prepare_operands(ws, c))) break;
+      for (int64_t d = 0; d < nd && !rc; ++d) rc = prepare_operands(ws, cs[(size_t)d]);
+      if (rc) break;
+      // result matrices: 1 (single dimension / "mean") or n_dims ("full"); dimensions per matrix: n_dims or 1
+      const int64_t nmat = (nd > 1 && J.combine == 1) ? nd : 1;
+      const int64_t dpm = nd / nmat;
       if (J.kind == 2) {
         double* dout = nullptr;
         if ((rc = ws.alloc(&dout, (size_t)rows))) break;
-        Timer kt(st); kt.start();
-        if ((rc = launch_dp(ws, di, c, 0, rows, 0, rows, dout, 1, nullptr, nullptr, &stats))) break;
-        kt.stop();
-        WB_CK(cudaMemcpyAsync(J.out + lo, dout, sizeof(double) * rows, cudaMemcpyDeviceToHost, st));
-        WB_CK(cudaStreamSynchronize(st));
-        stats.kernel_ms += kt.ms();
+        for (int64_t mi = 0; mi < nmat && !rc; ++mi) {
+          Timer kt(st); kt.start();
+          for (int64_t d = mi * dpm; d < (mi + 1) * dpm && !rc; ++d)
+            rc = launch_dp(ws, di, cs[(size_t)d], 0, rows, 0, rows, dout, 1, nullptr, nullptr, &stats);
+          if (rc) break;
+          kt.stop();
+          WB_CK(cudaMemcpyAsync(J.out + mi * J.nx + lo, dout, sizeof(double) * rows, cudaMemcpyDeviceToHost, st));
+          WB_CK(cudaStreamSynchronize(st));
+          stats.kernel_ms += kt.ms();
+        }
         break;
       }
       // pairwise / self: chunk the row block so result slabs stream back while the next chunk computes
@@ -513,31 +549,35 @@ static int device_worker(const HostJob& J, int dev, int64_t lo, int64_t hi, wb_s
       const size_t slab_budget = (size_t)48 << 20;  // small slabs: the un-overlapped tail copy stays short
       int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(rows, (int64_t)(slab_budget / (sizeof(double) * std::max<int64_t>(ncols, 1)))));
       const int64_t nchunks = (rows + chunk - 1) / chunk;
+      const int64_t nunits = nchunks * nmat;  // streaming unit u = (matrix u / nchunks, row chunk u % nchunks)
       double* dbuf[2] = {nullptr, nullptr};
       if ((rc = ws.alloc(&dbuf[0], (size_t)chunk * ncols))) break;
-      if (nchunks > 1 && (rc = ws.alloc(&dbuf[1], (size_t)chunk * ncols))) break;
+      if (nunits > 1 && (rc = ws.alloc(&dbuf[1], (size_t)chunk * ncols))) break;
       cudaEvent_t done[2], k0[2], k1[2];
       for (int b = 0; b < 2; ++b) { cudaEventCreate(&done[b]); cudaEventCreate(&k0[b]); cudaEventCreate(&k1[b]); }
-      auto enqueue = [&](int64_t ci) -> int {
-        const int b = (int)(ci & 1);
+      auto enqueue = [&](int64_t u) -> int {
+        const int b = (int)(u & 1);
+        const int64_t mi = u / nchunks, ci = u % nchunks;
         const int64_t r0 = ci * chunk, nr = std::min(chunk, rows - r0);
         if (J.kind == 1) WB_CK(cudaMemsetAsync(dbuf[b], 0, sizeof(double) * nr * ncols, st));
         WB_CK(cudaEventRecord(k0[b], st));
-        if (launch_dp(ws, di, c, r0, nr, 0, ncols, dbuf[b], ncols, nullptr, nullptr, &stats)) return 1;
+        for (int64_t d = mi * dpm; d < (mi + 1) * dpm; ++d)
+          if (launch_dp(ws, di, cs[(size_t)d], r0, nr, 0, ncols, dbuf[b], ncols, nullptr, nullptr, &stats)) return 1;
         WB_CK(cudaEventRecord(k1[b], st));
         WB_CK(cudaEventRecord(done[b], st));
         return 0;
       };
       if ((rc = enqueue(0))) break;
-      for (int64_t ci = 0; ci < nchunks && !rc; ++ci) {
-        const int b = (int)(ci & 1);
+      for (int64_t u = 0; u < nunits && !rc; ++u) {
+        const int b = (int)(u & 1);
+        const int64_t mi = u / nchunks, ci = u % nchunks;
         const int64_t r0 = ci * chunk, nr = std::min(chunk, rows - r0);
-        if (ci + 1 < nchunks) {
-          // buffer (ci+1)&1 was drained by the copy of chunk ci-1 (synchronous for the host)
-          if ((rc = enqueue(ci + 1))) break;
+        if (u + 1 < nunits) {
+          // buffer (u+1)&1 was drained by the copy of unit u-1 (synchronous for the host)
+          if ((rc = enqueue(u + 1))) break;
         }
         if (cudaStreamWaitEvent(cst, done[b], 0) != cudaSuccess) { set_err("cudaStreamWaitEvent failed"); rc = 1; break; }
-        if (cudaMemcpyAsync(J.out + (lo + r0) * ncols, dbuf[b], sizeof(double) * nr * ncols, cudaMemcpyDeviceToHost, cst) != cudaSuccess ||
+        if (cudaMemcpyAsync(J.out + mi * J.nx * ncols + (lo + r0) * ncols, dbuf[b], sizeof(double) * nr * ncols, cudaMemcpyDeviceToHost, cst) != cudaSuccess ||
             cudaStreamSynchronize(cst) != cudaSuccess) { set_err("device-to-host copy of the result slab failed"); rc = 1; break; }
         float f = 0;
         if (cudaEventElapsedTime(&f, k0[b], k1[b]) == cudaSuccess) stats.kernel_ms += f;
@@ -606,10 +646,14 @@ static int run_host_job(const HostJob& J, const int* devices, int n_devices, wb_
   if (J.kind == 1) {
     // lower triangle = copy of the upper one (CD:1240-1246), blocked for cache friendliness
     const int64_t n = J.nx, B = 64;
-    for (int64_t ib = 0; ib < n; ib += B)
-      for (int64_t jb = ib; jb < n; jb += B)
-        for (int64_t i = ib; i < std::min(ib + B, n); ++i)
-          for (int64_t j = std::max(jb, i + 1); j < std::min(jb + B, n); ++j) J.out[j * n + i] = J.out[i * n + j];
+    const int64_t nmat = (J.nd > 1 && J.combine == 1) ? J.nd : 1;
+    for (int64_t mi = 0; mi < nmat; ++mi) {
+      double* o = J.out + mi * n * n;
+      for (int64_t ib = 0; ib < n; ib += B)
+        for (int64_t jb = ib; jb < n; jb += B)
+          for (int64_t i = ib; i < std::min(ib + B, n); ++i)
+            for (int64_t j = std::max(jb, i + 1); j < std::min(jb + B, n); ++j) o[j * n + i] = o[i * n + j];
+    }
   }
   if (stats) {
     memset(stats, 0, sizeof *stats);
@@ -757,6 +801,39 @@ int wb_cuda_paired(int metric, const wb_params* params, const double* x, int64_t
   HostJob J; memset(&J, 0, sizeof J);
   J.kind = 2; J.metric = metric; J.p = *params; J.x = x; J.nx = n; J.Tx = Tx; J.xs = x_stride;
   J.y = y; J.ny = n; J.Ty = Ty; J.ys = y_stride; J.out = out;
+  return run_host_job(J, devices, n_devices, stats);
+}
+
+static int check_nd(int64_t n_dims, int combine) {
+  if (n_dims < 1) { set_err("n_dims must be >= 1"); return 1; }
+  if (combine != 0 && combine != 1) { set_err("combine must be 0 (mean) or 1 (full)"); return 1; }
+  return 0;
+}
+
+int wb_cuda_pairwise_nd(int metric, const wb_params* params, const double* x, int64_t nx, int64_t n_dims, int64_t Tx,
+                        int64_t x_stride, int64_t x_dim_stride, const double* y, int64_t ny, int64_t Ty, int64_t y_stride,
+                        int64_t y_dim_stride, int combine, double* out, const int* devices, int n_devices, wb_stats* stats) {
+  if (check_common(metric, params, x, nx, Tx) || check_nd(n_dims, combine)) return 1;
+  if (y && check_common(metric, params, y, ny, Ty)) return 1;
+  if (!out) { set_err("null output"); return 1; }
+  if (y && metric == M_WDDTW && Tx > Ty) { set_err("wddtw requires len(x) <= len(y) (the reference overflows a buffer otherwise)"); return 1; }
+  HostJob J; memset(&J, 0, sizeof J);
+  J.metric = metric; J.p = *params; J.x = x; J.nx = nx; J.Tx = Tx; J.xs = x_stride; J.xds = x_dim_stride;
+  J.nd = n_dims; J.combine = combine; J.out = out;
+  if (y) { J.kind = 0; J.y = y; J.ny = ny; J.Ty = Ty; J.ys = y_stride; J.yds = y_dim_stride; }
+  else { J.kind = 1; J.y = x; J.ny = nx; J.Ty = Tx; J.ys = x_stride; J.yds = x_dim_stride; }
+  return run_host_job(J, devices, n_devices, stats);
+}
+
+int wb_cuda_paired_nd(int metric, const wb_params* params, const double* x, int64_t n, int64_t n_dims, int64_t Tx,
+                      int64_t x_stride, int64_t x_dim_stride, const double* y, int64_t Ty, int64_t y_stride,
+                      int64_t y_dim_stride, int combine, double* out, const int* devices, int n_devices, wb_stats* stats) {
+  if (check_common(metric, params, x, n, Tx) || check_common(metric, params, y, n, Ty) || check_nd(n_dims, combine)) return 1;
+  if (!out) { set_err("null output"); return 1; }
+  if (metric == M_WDDTW && Ty > Tx) { set_err("wddtw (paired, operands swapped) requires len(y) <= len(x)"); return 1; }
+  HostJob J; memset(&J, 0, sizeof J);
+  J.kind = 2; J.metric = metric; J.p = *params; J.x = x; J.nx = n; J.Tx = Tx; J.xs = x_stride; J.xds = x_dim_stride;
+  J.y = y; J.ny = n; J.Ty = Ty; J.ys = y_stride; J.yds = y_dim_stride; J.nd = n_dims; J.combine = combine; J.out = out;
   return run_host_job(J, devices, n_devices, stats);
 }
 

@@ -311,6 +311,8 @@ def pairwise_distance(x, y=None, *, dim="mean", metric="euclidean", metric_param
         if n_dims == 1 and dim == "mean":
             dim = 0
         dims, how = _dim_slices(x_, dim, n_dims)
+        if how is not None and n_dims > 1:  # all dimensions in ONE library call (combined on the device)
+            return _shim.pairwise_nd(m.metric_id, params, x_, None, how)
         return _combine([_shim.pairwise(m.metric_id, params, x_[:, d, :], None) for d in dims], how)
     x = check_array(x, allow_3d=True, ensure_2d=False, dtype=np.double)
     y = check_array(y, allow_3d=True, ensure_2d=False, dtype=np.double)
@@ -324,7 +326,10 @@ def pairwise_distance(x, y=None, *, dim="mean", metric="euclidean", metric_param
     if n_dims == 1 and dim == "mean":
         dim = 0
     dims, how = _dim_slices(x_, dim, n_dims)
-    distances = _combine([_shim.pairwise(m.metric_id, params, x_[:, d, :], y_[:, d, :]) for d in dims], how)
+    if how is not None and n_dims > 1:
+        distances = _shim.pairwise_nd(m.metric_id, params, x_, y_, how)
+    else:
+        distances = _combine([_shim.pairwise(m.metric_id, params, x_[:, d, :], y_[:, d, :]) for d in dims], how)
     return _format_return(distances, y.ndim, x.ndim)
 
 
@@ -353,7 +358,10 @@ def paired_distance(x, y, *, dim="mean", metric="euclidean", metric_params=None,
     x_ = _check_ts_array(x)
     y_ = _check_ts_array(y)
     dims, how = _dim_slices(x_, dim, n_dims)
-    distances = _combine([_shim.paired(m.metric_id, params, x_[:, d, :], y_[:, d, :]) for d in dims], how)
+    if how is not None and n_dims > 1:
+        distances = _shim.paired_nd(m.metric_id, params, x_, y_, how)
+    else:
+        distances = _combine([_shim.paired(m.metric_id, params, x_[:, d, :], y_[:, d, :]) for d in dims], how)
     return _format_return(distances, y.ndim, x.ndim)
 
 
