@@ -122,6 +122,23 @@ int wb_cuda_argmin(int metric, const wb_params *params,
                    int64_t *out_idx, double *out_dist,
                    const int *devices, int n_devices, wb_stats *stats);
 
+/* Device-resident fitted set: the estimators that call this path keep their training set
+ * `_fit_X` (distance/_neighbors.py:76, 239) and query it repeatedly (kneighbors :141-150, predict_proba
+ * :262-283, KMeans assign :320-347).  wb_cuda_fit uploads y (ny, n_dims, Ty) ONCE to every listed device;
+ * the *_fitted calls then move only the queries and the result.  They shard the query rows over the
+ * devices of the fitted set and otherwise behave exactly like wb_cuda_pairwise_nd / wb_cuda_argmin. */
+typedef struct wb_fitted wb_fitted;
+int wb_cuda_fit(const double *y, int64_t ny, int64_t n_dims, int64_t Ty, int64_t y_stride, int64_t y_dim_stride,
+                const int *devices, int n_devices, wb_fitted **out);
+void wb_cuda_fit_free(wb_fitted *fit);
+int wb_cuda_pairwise_fitted(int metric, const wb_params *params,
+                            const double *x, int64_t nx, int64_t n_dims, int64_t Tx, int64_t x_stride, int64_t x_dim_stride,
+                            const wb_fitted *fit, int combine, double *out, wb_stats *stats);
+int wb_cuda_argmin_fitted(int metric, const wb_params *params,
+                          const double *x, int64_t nx, int64_t Tx, int64_t x_stride,
+                          const wb_fitted *fit, int64_t k, const double *lower_bound, int use_device_lb,
+                          int64_t *out_idx, double *out_dist, wb_stats *stats);
+
 /* Device-resident variant of wb_cuda_pairwise: d_x (nx, Tx), d_y (ny, Ty), d_out (nx, ny) are
  * dense row-major DEVICE arrays on the current device.  Enqueues on `stream`; fills `stats`
  * (after synchronising the stream) when stats != NULL. */

@@ -4,6 +4,7 @@
 
 Writes tests/golden/next_golden.npz:
   nd|...   multivariate pairwise / self / paired with dim="mean" / "full" (_distance.py:1245-1297, 1163-1169)
+  nb|...   KNeighborsClassifier.predict_proba / predict and NearestNeighbors.kneighbors (distance/_neighbors.py:19-300)
 """
 import os
 import sys
@@ -30,12 +31,51 @@ def multivariate(wd, out):
             out[f"nd|{metric}|{dim}|paired"] = wd.paired_distance(x[:5], y, dim=dim, metric=metric, metric_params=mp)
 
 
+NB_CASES = [("dtw", {"r": 0.1}), ("wdtw", {"r": 0.3, "g": 0.1}), ("msm", {"r": 0.2}), ("erp", {"r": 0.2}),
+            ("lcss", {"r": 0.5, "epsilon": 0.7}), ("twe", {"r": 0.15}), ("edr", {"r": 0.3}), ("adtw", {"r": 0.1, "p": 0.5})]
+
+
+def neighbors(wd, out):
+    """KNeighborsClassifier / NearestNeighbors of the reference (distance/_neighbors.py) on seeded random walks."""
+    rng = np.random.default_rng(20261019)
+    X = np.cumsum(rng.standard_normal((60, 50)), axis=1)
+    y = rng.integers(0, 3, 60) * 2 + 1            # labels {1, 3, 5}
+    Q = np.cumsum(rng.standard_normal((25, 50)), axis=1)
+    X3 = np.cumsum(rng.standard_normal((40, 2, 30)), axis=2)
+    y3 = rng.integers(0, 2, 40)
+    Q3 = np.cumsum(rng.standard_normal((15, 2, 30)), axis=2)
+    for k, v in dict(X=X, y=y, Q=Q, X3=X3, y3=y3, Q3=Q3).items():
+        out[f"nb|{k}"] = v
+    for metric, mp in NB_CASES:
+        for k in (1, 3):
+            clf = wd.KNeighborsClassifier(n_neighbors=k, metric=metric, metric_params=mp).fit(X, y)
+            out[f"nb|{metric}|knn{k}|proba"] = clf.predict_proba(Q)
+            out[f"nb|{metric}|knn{k}|predict"] = clf.predict(Q)
+        nn = wd.NearestNeighbors(n_neighbors=4, metric=metric, metric_params=mp).fit(X)
+        d, i = nn.kneighbors(Q)
+        out[f"nb|{metric}|nn|dist"], out[f"nb|{metric}|nn|ind"] = d, i.astype(np.int64)
+        try:
+            d, i = nn.kneighbors()
+            out[f"nb|{metric}|nnself|dist"], out[f"nb|{metric}|nnself|ind"] = d, i.astype(np.int64)
+        except ValueError:  # the reference cannot drop the query itself when it is not among the k+1 (ties / abandoning)
+            out[f"nb|{metric}|nnself|raises"] = np.array(1)
+    for metric, mp in NB_CASES[:3]:
+        clf = wd.KNeighborsClassifier(n_neighbors=3, metric=metric, metric_params=mp).fit(X3, y3)
+        out[f"nb3|{metric}|knn3|proba"] = clf.predict_proba(Q3)
+        nn = wd.NearestNeighbors(n_neighbors=3, metric=metric, metric_params=mp).fit(X3)
+        d, i = nn.kneighbors(Q3)
+        out[f"nb3|{metric}|nn|dist"], out[f"nb3|{metric}|nn|ind"] = d, i.astype(np.int64)
+        d, i = nn.kneighbors()
+        out[f"nb3|{metric}|nnself|dist"], out[f"nb3|{metric}|nnself|ind"] = d, i.astype(np.int64)
+
+
 def main():
     wd = ref.load()
     if wd is None:
         raise SystemExit("oracle/_ref is not built; run oracle/build_ref.sh first")
     out = {}
     multivariate(wd, out)
+    neighbors(wd, out)
     path = os.path.join(HERE, "next_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")

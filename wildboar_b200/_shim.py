@@ -69,6 +69,11 @@ def lib():
                                                   ci, SP]
                 L.wb_cuda_paired_nd.argtypes = [ci, PP, _DP, i64, i64, i64, i64, i64, _DP, i64, i64, i64, ci, _DP, DV, ci,
                                                 SP]
+                L.wb_cuda_fit.argtypes = [_DP, i64, i64, i64, i64, i64, DV, ci, C.POINTER(C.c_void_p)]
+                L.wb_cuda_fit_free.argtypes = [C.c_void_p]
+                L.wb_cuda_fit_free.restype = None
+                L.wb_cuda_pairwise_fitted.argtypes = [ci, PP, _DP, i64, i64, i64, i64, i64, C.c_void_p, ci, _DP, SP]
+                L.wb_cuda_argmin_fitted.argtypes = [ci, PP, _DP, i64, i64, i64, C.c_void_p, i64, _DP, ci, _IP, _DP, SP]
                 L.wb_cuda_argmin.argtypes = [ci, PP, _DP, i64, i64, i64, _DP, i64, i64, i64, i64, _DP, ci, _IP, _DP,
                                              DV, ci, SP]
                 L.wb_cuda_pairwise_dev.argtypes = [ci, PP, C.c_void_p, i64, i64, C.c_void_p, i64, i64, C.c_void_p,
@@ -265,6 +270,64 @@ def argmin(metric_id, params, x, y, k, lower_bound=None, use_device_lb=False):
     _check(lib().wb_cuda_argmin(metric_id, C.byref(params), xp, nx, Tx, xs, yp, ny, Ty, ys, k, lbp,
                                 1 if use_device_lb else 0, idx.ctypes.data_as(_IP), dist.ctypes.data_as(_DP), dv, nd,
                                 C.byref(st)))
+    _tls.stats = st.as_dict()
+    return idx.astype(np.intp, copy=False), dist
+
+
+class FittedSet:
+    """A training set kept resident on the device(s) (wb_cuda_fit): estimators upload `_fit_X` once and
+    every later query moves only the queries and the result.  x: (n, n_dims, T) float64."""
+
+    def __init__(self, x, devices=None):
+        x, xp, n, nd, T, ss, ds = _samples(x)
+        self.shape = (n, nd, T)
+        devs = list(devices) if devices is not None else _resolve_devices(0.0 if _devices is not None else 1e30)
+        dv, ndv = _dev_array(devs)
+        h = C.c_void_p()
+        _check(lib().wb_cuda_fit(xp, n, nd, T, ss, ds, dv, ndv, C.byref(h)))
+        self._h = h
+        self.devices = devs
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h is not None and _lib is not None:
+            _lib.wb_cuda_fit_free(h)
+
+    __del__ = close
+
+    def _handle(self):
+        if self._h is None:
+            raise RuntimeError("the fitted set has been released")
+        return self._h
+
+
+def pairwise_fitted(metric_id, params, x, fitted, combine="mean"):
+    """x (nx, n_dims, Tx) against a FittedSet; (nx, n) or, combine="full", (n_dims, nx, n)."""
+    apply_engine_override(params)
+    x, xp, nx, nd, Tx, xss, xds = _samples(x)
+    full = combine == "full"
+    n = fitted.shape[0]
+    out = np.empty((nd, nx, n) if full else (nx, n), dtype=np.float64)
+    st = WbStats()
+    _check(lib().wb_cuda_pairwise_fitted(metric_id, C.byref(params), xp, nx, nd, Tx, xss, xds, fitted._handle(),
+                                         1 if full else 0, out.ctypes.data_as(_DP), C.byref(st)))
+    _tls.stats = st.as_dict()
+    return out
+
+
+def argmin_fitted(metric_id, params, x, fitted, k, lower_bound=None, use_device_lb=False):
+    apply_engine_override(params)
+    x, xp, nx, Tx, xs = _rows(x)
+    idx = np.zeros((nx, k), dtype=np.int64)
+    dist = np.zeros((nx, k), dtype=np.float64)
+    lbp = None
+    if lower_bound is not None:
+        lower_bound = np.ascontiguousarray(lower_bound, dtype=np.float64)
+        lbp = lower_bound.ctypes.data_as(_DP)
+    st = WbStats()
+    _check(lib().wb_cuda_argmin_fitted(metric_id, C.byref(params), xp, nx, Tx, xs, fitted._handle(), k, lbp,
+                                       1 if use_device_lb else 0, idx.ctypes.data_as(_IP), dist.ctypes.data_as(_DP),
+                                       C.byref(st)))
     _tls.stats = st.as_dict()
     return idx.astype(np.intp, copy=False), dist
 

@@ -418,6 +418,15 @@ static int launch_dp(Workspace& ws, const DeviceInfo& di, const DpCall& c, long 
 // ------------------------------------------------------------------------------------------
 // Host-buffer drivers: stage, shard rows over devices, gather.
 // ------------------------------------------------------------------------------------------
+}  // namespace wb
+// Device-resident fitted set (include/wb_cuda.h, wb_cuda_fit): a dense (n_dims, n, T) copy per device.
+struct wb_fitted {
+  int64_t n, nd, T;
+  std::vector<int> devs;
+  std::vector<double*> ptr;
+};
+namespace wb {
+
 struct HostJob {
   int kind;  // 0 pairwise, 1 self, 2 paired, 3 argmin
   int metric; wb_params p;
@@ -428,6 +437,7 @@ struct HostJob {
   // multivariate (pairwise / self / paired): n_dims >= 1 dimensions, `xds` / `yds` elements between the
   // dimensions of one sample; combine 0 = "mean" (one matrix), 1 = "full" (n_dims matrices)  (DI:1289-1297)
   int64_t nd, xds, yds; int combine;
+  const wb_fitted* fit;  // kinds 0 / 3: the second operand is already resident on the devices
 };
 
 static int h2d_rows(double* dst, const double* src, int64_t rows, int64_t T, int64_t stride, cudaStream_t st) {
@@ -488,10 +498,13 @@ static int device_worker(const HostJob& J, int dev, int64_t lo, int64_t hi, wb_s
       } else {
         xn = rows; xT = J.Tx; yn = J.ny; yT = J.Ty;
         if ((rc = ws.alloc(&dx, (size_t)nd * rows * J.Tx))) break;
-        if ((rc = ws.alloc(&dy, (size_t)nd * J.ny * J.Ty))) break;
+        if (J.fit) {
+          for (size_t q = 0; q < J.fit->devs.size(); ++q) if (J.fit->devs[q] == dev) dy = J.fit->ptr[q];
+          if (!dy) { set_err("the fitted set is not resident on this device"); rc = 1; break; }
+        } else if ((rc = ws.alloc(&dy, (size_t)nd * J.ny * J.Ty))) break;
         for (int64_t d = 0; d < nd && !rc; ++d) {
           if ((rc = h2d_rows(dx + d * rows * J.Tx, J.x + d * J.xds + lo * J.xs, rows, J.Tx, J.xs, st))) break;
-          rc = h2d_rows(dy + d * J.ny * J.Ty, J.y + d * J.yds, J.ny, J.Ty, J.ys, st);
+          if (!J.fit) rc = h2d_rows(dy + d * J.ny * J.Ty, J.y + d * J.yds, J.ny, J.Ty, J.ys, st);
         }
         if (rc) break;
       }
@@ -850,6 +863,73 @@ int wb_cuda_argmin(int metric, const wb_params* params, const double* x, int64_t
   J.y = y; J.ny = ny; J.Ty = Ty; J.ys = y_stride; J.out = out_dist; J.out_idx = out_idx; J.k = k;
   J.lower_bound = lower_bound; J.use_device_lb = use_device_lb;
   return run_host_job(J, devices, n_devices, stats);
+}
+
+int wb_cuda_fit(const double* y, int64_t ny, int64_t n_dims, int64_t Ty, int64_t y_stride, int64_t y_dim_stride,
+                const int* devices, int n_devices, wb_fitted** out) {
+  if (!y || !out) { set_err("null argument"); return 1; }
+  if (ny < 1 || Ty < 1 || n_dims < 1) { set_err("empty input"); return 1; }
+  int ndev_avail = 0;
+  if (cudaGetDeviceCount(&ndev_avail) != cudaSuccess || ndev_avail < 1) {
+    set_err("no CUDA device available: wildboar_b200 has no CPU fallback");
+    return 1;
+  }
+  wb_fitted* f = new wb_fitted;
+  f->n = ny; f->nd = n_dims; f->T = Ty;
+  if (devices && n_devices > 0) f->devs.assign(devices, devices + n_devices); else f->devs.push_back(0);
+  int rc = 0;
+  for (int d : f->devs) {
+    if (d < 0 || d >= ndev_avail) { set_err("invalid device ordinal"); rc = 1; break; }
+    DeviceInfo di;
+    double* p = nullptr;
+    if (cudaSetDevice(d) != cudaSuccess || device_info(&di)) { rc = 1; if (g_err.empty()) set_err("cudaSetDevice failed"); break; }
+    if (cudaMalloc(&p, sizeof(double) * (size_t)n_dims * ny * Ty) != cudaSuccess) { cudaGetLastError(); set_err("out of device memory for the fitted set"); rc = 1; break; }
+    f->ptr.push_back(p);
+    for (int64_t k = 0; k < n_dims && !rc; ++k) rc = h2d_rows(p + k * ny * Ty, y + k * y_dim_stride, ny, Ty, y_stride, 0);
+    if (!rc && cudaDeviceSynchronize() != cudaSuccess) { set_err("upload of the fitted set failed"); rc = 1; }
+    if (rc) break;
+  }
+  if (rc) { wb_cuda_fit_free(f); return rc; }
+  *out = f;
+  return 0;
+}
+
+void wb_cuda_fit_free(wb_fitted* f) {
+  if (!f) return;
+  for (size_t q = 0; q < f->ptr.size(); ++q) {
+    if (cudaSetDevice(f->devs[q]) == cudaSuccess) cudaFree(f->ptr[q]);
+  }
+  delete f;
+}
+
+int wb_cuda_pairwise_fitted(int metric, const wb_params* params, const double* x, int64_t nx, int64_t n_dims, int64_t Tx,
+                            int64_t x_stride, int64_t x_dim_stride, const wb_fitted* fit, int combine, double* out,
+                            wb_stats* stats) {
+  if (!fit) { set_err("null fitted set"); return 1; }
+  if (check_common(metric, params, x, nx, Tx) || check_nd(n_dims, combine)) return 1;
+  if (n_dims != fit->nd) { set_err("x and the fitted set must have the same number of dimensions"); return 1; }
+  if (!out) { set_err("null output"); return 1; }
+  if (metric == M_WDDTW && Tx > fit->T) { set_err("wddtw requires len(x) <= len(y)"); return 1; }
+  HostJob J; memset(&J, 0, sizeof J);
+  J.kind = 0; J.metric = metric; J.p = *params; J.x = x; J.nx = nx; J.Tx = Tx; J.xs = x_stride; J.xds = x_dim_stride;
+  J.ny = fit->n; J.Ty = fit->T; J.nd = n_dims; J.combine = combine; J.out = out; J.fit = fit;
+  return run_host_job(J, fit->devs.data(), (int)fit->devs.size(), stats);
+}
+
+int wb_cuda_argmin_fitted(int metric, const wb_params* params, const double* x, int64_t nx, int64_t Tx, int64_t x_stride,
+                          const wb_fitted* fit, int64_t k, const double* lower_bound, int use_device_lb, int64_t* out_idx,
+                          double* out_dist, wb_stats* stats) {
+  if (!fit) { set_err("null fitted set"); return 1; }
+  if (check_common(metric, params, x, nx, Tx)) return 1;
+  if (fit->nd != 1) { set_err("argmin needs a univariate fitted set"); return 1; }
+  if (!out_idx || !out_dist) { set_err("null output"); return 1; }
+  if (k < 1 || k > fit->n) { set_err("k must satisfy 1 <= k <= n_y"); return 1; }
+  if (metric == M_WDDTW && Tx > fit->T) { set_err("wddtw requires len(x) <= len(y)"); return 1; }
+  HostJob J; memset(&J, 0, sizeof J);
+  J.kind = 3; J.metric = metric; J.p = *params; J.x = x; J.nx = nx; J.Tx = Tx; J.xs = x_stride;
+  J.ny = fit->n; J.Ty = fit->T; J.out = out_dist; J.out_idx = out_idx; J.k = k;
+  J.lower_bound = lower_bound; J.use_device_lb = use_device_lb; J.fit = fit;
+  return run_host_job(J, fit->devs.data(), (int)fit->devs.size(), stats);
 }
 
 int wb_cuda_pairwise_dev(int metric, const wb_params* params, const double* d_x, int64_t nx, int64_t Tx,

@@ -1,0 +1,212 @@
+"""Nearest-neighbour estimators on the CUDA path, with the training set resident on the device.
+
+Mirrors ``wildboar.distance.NearestNeighbors`` / ``KNeighborsClassifier`` (reference:
+src/wildboar/distance/_neighbors.py:19-160 and :163-300): same constructor parameters, ``fit`` /
+``kneighbors`` / ``predict_proba`` / ``predict`` semantics, same neighbour sets, order and
+probabilities -- they come from the same ``argmin_distance`` (heap order, strict ``<`` ties) and
+``pairwise_distance(dim="mean")`` + ``np.argpartition`` calls as in the reference.
+
+B200-first difference: ``fit`` uploads ``_fit_X`` once (``wb_cuda_fit``); every later query moves only
+the queries and the result.  Elastic metrics only; there is no CPU fallback.
+"""
+import numbers
+
+import numpy as np
+
+from . import _shim
+from .distance import _METRICS, _check_ts_array, _make_metric, check_array
+
+try:  # sklearn is optional: it only contributes get_params / set_params / clone support
+    from sklearn.base import BaseEstimator as _SkBase
+except Exception:  # pragma: no cover
+    class _SkBase:  # minimal stand-in
+        def get_params(self, deep=True):
+            return {k: getattr(self, k) for k in self._param_names}
+
+        def set_params(self, **params):
+            for k, v in params.items():
+                if k not in self._param_names:
+                    raise ValueError(f"Invalid parameter {k!r} for estimator {type(self).__name__}.")
+                setattr(self, k, v)
+            return self
+
+try:
+    from sklearn.exceptions import NotFittedError as _NotFitted
+except Exception:  # pragma: no cover
+    class _NotFitted(ValueError, AttributeError):
+        pass
+
+__all__ = ["NearestNeighbors", "KNeighborsClassifier"]
+
+
+class _NeighborsBase(_SkBase):
+    _param_names = ("n_neighbors", "metric", "metric_params", "n_jobs")
+
+    def __init__(self, n_neighbors=5, *, metric="dtw", metric_params=None, n_jobs=None):
+        self.n_neighbors = n_neighbors
+        self.metric = metric
+        self.metric_params = metric_params
+        self.n_jobs = n_jobs
+
+    # _parameter_constraints of the reference (_neighbors.py:37-42, 188-193)
+    def _validate_params(self):
+        k = self.n_neighbors
+        if isinstance(k, bool) or not isinstance(k, numbers.Integral) or k < 1:
+            raise ValueError(
+                f"The 'n_neighbors' parameter of {type(self).__name__} must be an int in the range [1, inf). Got {k!r} instead."
+            )
+        if not (isinstance(self.metric, str) and self.metric in _METRICS):
+            raise ValueError(
+                f"The 'metric' parameter of {type(self).__name__} must be a str among {set(_METRICS)} "
+                f"(the elastic metrics; others are not accelerated). Got {self.metric!r} instead."
+            )
+        if self.metric_params is not None and not isinstance(self.metric_params, dict):
+            raise ValueError(
+                f"The 'metric_params' parameter of {type(self).__name__} must be an instance of 'dict' or None. "
+                f"Got {self.metric_params!r} instead."
+            )
+        if self.n_jobs is not None and (isinstance(self.n_jobs, bool) or not isinstance(self.n_jobs, numbers.Integral)):
+            raise ValueError(f"The 'n_jobs' parameter of {type(self).__name__} must be an int or None. Got {self.n_jobs!r} instead.")
+
+    def _fit_x(self, x):
+        self._validate_params()
+        x = check_array(x, allow_3d=True, dtype=float, input_name="x")
+        self.n_timesteps_in_ = x.shape[-1]
+        self.n_dims_in_ = x.shape[1] if x.ndim == 3 else 1
+        self._fit_X = x.copy()
+        self._release()
+        self._fitted = _shim.FittedSet(_check_ts_array(self._fit_X))  # resident until refit / release / gc
+        return x
+
+    def _release(self):
+        f = self.__dict__.pop("_fitted", None)
+        if f is not None:
+            f.close()
+
+    def release(self):
+        """Free the device copy of the training set (it is re-uploaded on the next query)."""
+        self._release()
+
+    def __getstate__(self):  # device handles do not pickle; the copy is re-created lazily
+        state = dict(self.__dict__)
+        state.pop("_fitted", None)
+        return state
+
+    def _check_is_fitted(self):
+        if not hasattr(self, "_fit_X"):
+            raise _NotFitted(
+                f"This {type(self).__name__} instance is not fitted yet. Call 'fit' with appropriate arguments before using this estimator."
+            )
+        if "_fitted" not in self.__dict__:
+            self._fitted = _shim.FittedSet(_check_ts_array(self._fit_X))
+
+    def _check_query(self, x):
+        x = check_array(x, allow_3d=True, dtype=float, input_name="x")
+        n_dims = x.shape[1] if x.ndim == 3 else 1
+        if n_dims != self.n_dims_in_:
+            raise ValueError(f"X has {n_dims} dimensions, but {type(self).__name__} is expecting {self.n_dims_in_} dimensions as input.")
+        if x.shape[-1] != self.n_timesteps_in_:
+            raise ValueError(f"X has {x.shape[-1]} timesteps, but {type(self).__name__} is expecting {self.n_timesteps_in_} timesteps as input.")
+        # "Treat a multivariate time series with a single dimension as a univariate time series" (_neighbors.py:112-115)
+        if x.ndim == 3 and x.shape[1] == 1:
+            x = x.reshape(x.shape[0], -1)
+        return x
+
+    # the two query forms of the reference, against the resident training set
+    def _pairwise_mean(self, x):
+        m = _make_metric(self.metric, self.metric_params)
+        return _shim.pairwise_fitted(m.metric_id, m._params(), _check_ts_array(x), self._fitted, "mean")
+
+    def _argmin(self, x, k, sorted_):
+        m = _make_metric(self.metric, self.metric_params)
+        k = min(k, self._fit_X.shape[0])
+        idx, dist = _shim.argmin_fitted(m.metric_id, m._params(), _check_ts_array(x)[:, 0, :], self._fitted, k,
+                                        use_device_lb=m.name == "dtw")
+        if sorted_:
+            order = np.argsort(dist, axis=1, kind="stable")
+            idx = np.take_along_axis(idx, order, axis=1)
+            dist = np.take_along_axis(dist, order, axis=1)
+        return idx, dist
+
+
+class NearestNeighbors(_NeighborsBase):
+    """Unsupervised neighbour searches (reference: _neighbors.py:19-160)."""
+
+    def fit(self, x, y=None):
+        self._fit_x(x)
+        return self
+
+    def kneighbors(self, x=None, n_neighbors=None, return_distance=True):
+        self._check_is_fitted()
+        if n_neighbors is None:
+            n_neighbors = self.n_neighbors
+        if x is not None:
+            query_is_train = False
+            x = self._check_query(x)
+        else:
+            query_is_train = True
+            x = self._fit_X
+            if x.ndim == 3 and x.shape[1] == 1:
+                x = x.reshape(x.shape[0], -1)
+
+        if x.ndim == 3:
+            dists = self._pairwise_mean(x)
+            if query_is_train:
+                np.fill_diagonal(dists, np.inf)
+            sample_range = np.arange(x.shape[0])[:, None]
+            neigh_ind = np.argpartition(dists, n_neighbors - 1, axis=1)[:, :n_neighbors]
+            neigh_dist = dists[sample_range, neigh_ind]
+            sort_inds = np.argsort(neigh_dist, axis=1)
+            neigh_ind = neigh_ind[sample_range, sort_inds]
+            if return_distance:
+                return neigh_dist[sample_range, sort_inds], neigh_ind
+            return neigh_ind
+
+        k = n_neighbors + 1 if query_is_train else n_neighbors
+        indices, distances = self._argmin(x, k, True)
+        if query_is_train:
+            mask = indices != np.arange(x.shape[0])[:, None]
+            indices = indices[mask].reshape(x.shape[0], -1)
+            distances = distances[mask].reshape(x.shape[0], -1)
+        if return_distance:
+            return distances, indices
+        return indices
+
+
+class KNeighborsClassifier(_NeighborsBase):
+    """k-nearest-neighbour classifier (reference: _neighbors.py:163-300)."""
+
+    def fit(self, x, y):
+        y = np.asarray(y)
+        if y.ndim != 1:
+            raise ValueError(f"y should be a 1d array, got an array of shape {y.shape} instead.")
+        if y.dtype.kind == "f" and not np.all(y == np.floor(y)):
+            raise ValueError("Unknown label type: continuous. Maybe you are trying to fit a classifier, which expects discrete classes on a regression target with continuous values.")
+        x = check_array(x, allow_3d=True, dtype=float, input_name="x")
+        if x.shape[0] != y.shape[0]:
+            raise ValueError(f"Found input variables with inconsistent numbers of samples: [{x.shape[0]}, {y.shape[0]}]")
+        self._fit_x(x)
+        self.classes_, self._y = np.unique(y, return_inverse=True)
+        return self
+
+    def predict_proba(self, x):
+        self._check_is_fitted()
+        x = self._check_query(x)
+        if x.ndim == 3:
+            dists = self._pairwise_mean(x)
+            closest = np.argpartition(dists, self.n_neighbors, axis=1)[:, : self.n_neighbors]
+        else:
+            closest, _ = self._argmin(x, self.n_neighbors, False)
+        preds = self._y[closest]
+        probs = np.empty((x.shape[0], len(self.classes_)), dtype=float)
+        for i in range(len(self.classes_)):
+            probs[:, i] = np.sum(preds == i, axis=1) / self.n_neighbors
+        return probs
+
+    def predict(self, x):
+        proba = np.argmax(self.predict_proba(x), axis=1)
+        return np.take(self.classes_, proba)
+
+    def score(self, x, y):
+        """Mean accuracy (sklearn.base.ClassifierMixin.score)."""
+        return float(np.mean(self.predict(x) == np.asarray(y)))
