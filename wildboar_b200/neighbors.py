@@ -150,9 +150,14 @@ class NearestNeighbors(_NeighborsBase):
                 x = x.reshape(x.shape[0], -1)
 
         if x.ndim == 3:
-            dists = self._pairwise_mean(x)
             if query_is_train:
+                # `pairwise_distance(x, self._fit_X)` with x IS _fit_X takes the reference's singleton form
+                # (upper triangle mirrored, _distance.py:1236-1264) -- it differs for the asymmetric metrics
+                m = _make_metric(self.metric, self.metric_params)
+                dists = _shim.pairwise_nd(m.metric_id, m._params(), _check_ts_array(x), None, "mean")
                 np.fill_diagonal(dists, np.inf)
+            else:
+                dists = self._pairwise_mean(x)
             sample_range = np.arange(x.shape[0])[:, None]
             neigh_ind = np.argpartition(dists, n_neighbors - 1, axis=1)[:, :n_neighbors]
             neigh_dist = dists[sample_range, neigh_ind]
