@@ -139,6 +139,33 @@ int wb_cuda_argmin_fitted(int metric, const wb_params *params,
                           const wb_fitted *fit, int64_t k, const double *lower_bound, int use_device_lb,
                           int64_t *out_idx, double *out_dist, wb_stats *stats);
 
+/* DTW alignments and DBA.
+ *
+ * wb_cuda_dtw_paths: optimal warping paths of n_pairs pairs (a[ia[p]], b[ib[p]]) (ia / ib NULL: pair p uses
+ * series p), a: (na, Ta) rows of the DP, b: (nb, Tb) columns, host buffers.  Replaces `_dtw_alignment`
+ * (_elastic.pyx:1011-1073) + the Python back-walk `dtw_mapping` (distance/dtw.py:385-413): band
+ * max(floor(max(Ta, Tb) r), 1) (dtw.py:38-40), optional `weights` (max(Ta, Tb) values, cost v*v*weights[|i-j|]).
+ * path_lo / path_hi: (n_pairs, Ta) int32, the path occupies columns lo..hi of each row (== the rows of
+ * `indicator.nonzero()`); cost (optional, n_pairs): D[Ta-1][Tb-1]; out_matrix (optional, n_pairs x Ta x Tb):
+ * the alignment matrix with +inf outside the band (the reference leaves those cells uninitialised).
+ *
+ * wb_cuda_dba_epoch: one majorize-minimize step of `_mm_dtw_average` (distance/dtw.py:655-690) for K
+ * barycentres at once against a resident sample set.  Cluster c owns members[member_offsets[c] ..
+ * member_offsets[c+1]) (sample indices, ascending).  do_update != 0: every member is aligned with means_in[c]
+ * and means_out[c] = z / V accumulated in the reference's order (bit-equal); do_update == 0: means_out =
+ * means_in.  dist_out[q] = metric(means_out[c], sample members[q]) for metric WB_DTW / WB_WDTW (the cost
+ * function of dtw_average, dtw.py:590-605; the caller averages with numpy).  sample_weight: optional, one per
+ * SAMPLE of the fitted set; weights: the alignment's weight vector (wdtw: jeong_weight(max(Tm, T), g) computed
+ * by the caller with numpy, dtw.py:347-374) or NULL. */
+int wb_cuda_dtw_paths(const double *a, int64_t na, int64_t Ta, int64_t a_stride,
+                      const double *b, int64_t nb, int64_t Tb, int64_t b_stride,
+                      const int64_t *ia, const int64_t *ib, int64_t n_pairs, double r, const double *weights,
+                      int32_t *path_lo, int32_t *path_hi, double *cost, double *out_matrix, int device, wb_stats *stats);
+int wb_cuda_dba_epoch(const wb_fitted *fit, int metric, const wb_params *params,
+                      const double *means_in, int64_t K, int64_t Tm,
+                      const int64_t *member_offsets, const int64_t *members, const double *sample_weight,
+                      const double *weights, int do_update, double *means_out, double *dist_out, wb_stats *stats);
+
 /* Device-resident variant of wb_cuda_pairwise: d_x (nx, Tx), d_y (ny, Ty), d_out (nx, ny) are
  * dense row-major DEVICE arrays on the current device.  Enqueues on `stream`; fills `stats`
  * (after synchronising the stream) when stats != NULL. */

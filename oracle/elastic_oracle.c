@@ -20,6 +20,7 @@
  */
 #include <math.h>
 #include <stdint.h>
+#include <limits.h>
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
@@ -672,4 +673,66 @@ int orc_lb_kim_matrix(const double *q, int64_t nq, const double *x, int64_t nx, 
     }
   }
   return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * DTW alignment matrix, warping path, DBA (test infrastructure like the rest).
+ * ------------------------------------------------------------------------------------------ */
+
+/* _elastic.pyx:1011-1073 `_dtw_alignment`: the full (xl, yl) matrix.  The reference allocates it with
+ * np.empty and writes only the band and one +inf sentinel on either side of every row; this restatement
+ * writes exactly the same cells and leaves the others untouched (callers pre-fill `out`, e.g. with NaN). */
+void orc_dtw_alignment(const double *X, int64_t xl, const double *Y, int64_t yl, int64_t r, const double *weights,
+                       double *out) {
+  double w = 1.0, v;
+  const int64_t dy = i64max(0, yl - xl), dx = i64max(0, xl - yl);
+  v = X[0] - Y[0];
+  if (weights) w = weights[0];
+  out[0] = v * v * w;
+  for (int64_t i = 1; i < i64min(xl, r + 1); i++) {
+    v = X[i] - Y[0];
+    if (weights) w = weights[i];
+    out[i * yl] = out[(i - 1) * yl] + v * v * w;
+  }
+  for (int64_t i = 1; i < i64min(yl, dy + r); i++) {
+    v = X[0] - Y[i];
+    if (weights) w = weights[i];
+    out[i] = out[i - 1] + v * v * w;
+  }
+  if (dy + r < yl) out[dy + r] = INFINITY;
+  for (int64_t i = 1; i < xl; i++) {
+    const int64_t j_start = i64max(0, i - dx - r + 1), j_stop = i64min(yl, i + dy + r);
+    if (j_start > 0) out[i * yl + j_start - 1] = INFINITY;
+    for (int64_t j = j_start; j < j_stop; j++) {
+      v = X[i] - Y[j];
+      const double x = out[(i - 1) * yl + j];
+      const double y = j > 0 ? out[i * yl + j - 1] : INFINITY;
+      const double z = j > 0 ? out[(i - 1) * yl + j - 1] : INFINITY;
+      if (weights) w = weights[llabs(i - j)];
+      out[i * yl + j] = dmin(dmin(x, y), z) + v * v * w;
+    }
+    if (j_stop < yl) out[i * yl + j_stop] = INFINITY;
+  }
+}
+
+/* distance/dtw.py:385-413 `dtw_mapping`: walk back from the last cell; np.argmin([diag, up, left]) takes the
+ * FIRST minimum.  lo[i] / hi[i] = first / last column of the path in row i (a monotone path covers a contiguous
+ * run of columns per row; `indicator.nonzero()` lists them row by row, ascending). */
+void orc_dtw_path(const double *D, int64_t xl, int64_t yl, int32_t *lo, int32_t *hi) {
+  int64_t i = xl - 1, j = yl - 1;
+  for (int64_t k = 0; k < xl; k++) { lo[k] = INT32_MAX; hi[k] = -1; }
+  while (i > 0 || j > 0) {
+    if (j < lo[i]) lo[i] = (int32_t)j;
+    if (j > hi[i]) hi[i] = (int32_t)j;
+    const double od = (i > 0 && j > 0) ? D[(i - 1) * yl + j - 1] : INFINITY;
+    const double ou = i > 0 ? D[(i - 1) * yl + j] : INFINITY;
+    const double ol = j > 0 ? D[i * yl + j - 1] : INFINITY;
+    int move = 0;
+    double best = od;
+    if (ou < best) { best = ou; move = 1; }
+    if (ol < best) { best = ol; move = 2; }
+    if (move == 0) { i--; j--; } else if (move == 1) i--; else j--;
+  }
+  if (0 < lo[0]) lo[0] = 0;
+  if (0 > hi[0]) hi[0] = 0;
 }

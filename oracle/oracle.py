@@ -203,3 +203,74 @@ def cells_per_pair(Tx, Ty, r, metric="dtw"):
     js = np.maximum(0, i - min_len - R + 1)
     je = np.minimum(Ty, i + max_len)
     return int(np.sum(np.maximum(je - js, 0)))
+
+
+# ---------------------------------------------------------------------------------------------
+# DTW alignment / warping path / DBA (reference: distance/dtw.py:246-690)
+# ---------------------------------------------------------------------------------------------
+def warp_size(x_size, r, y_size=0):
+    """dtw.py:38-40 `_compute_warp_size` (max, not min, of the two lengths)."""
+    import math
+    return max(math.floor(max(x_size, y_size) * r), 1)
+
+
+def jeong_weight(n, g=0.05):
+    """dtw.py:347-374 (numpy's exp, as in the reference)."""
+    return 1.0 / (1.0 + np.exp(-g * (np.arange(n, dtype=float) - n / 2.0)))
+
+
+def dtw_alignment(x, y, r=1.0, weight=None):
+    """`_dtw_alignment` (EL:1011-1073): cells the reference leaves uninitialised (np.empty) are NaN here."""
+    L = lib()
+    L.orc_dtw_alignment.argtypes = [C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_double), C.c_int64, C.c_int64,
+                                    C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+    y = np.ascontiguousarray(y, dtype=np.float64).ravel()
+    out = np.full((x.shape[0], y.shape[0]), np.nan)
+    wp = None
+    if weight is not None:
+        weight = np.ascontiguousarray(weight, dtype=np.float64)
+        wp = _dp(weight)
+    L.orc_dtw_alignment(_dp(x), x.shape[0], _dp(y), y.shape[0], warp_size(x.shape[0], r, y.shape[0]), wp, _dp(out))
+    return out
+
+
+def dtw_path(alignment):
+    """First / last column of the optimal path per row (`dtw_mapping`, dtw.py:385-413)."""
+    L = lib()
+    ip32 = C.POINTER(C.c_int32)
+    L.orc_dtw_path.argtypes = [C.POINTER(C.c_double), C.c_int64, C.c_int64, ip32, ip32]
+    a = np.ascontiguousarray(alignment, dtype=np.float64)
+    lo = np.zeros(a.shape[0], dtype=np.int32)
+    hi = np.zeros(a.shape[0], dtype=np.int32)
+    L.orc_dtw_path(_dp(a), a.shape[0], a.shape[1], lo.ctypes.data_as(ip32), hi.ctypes.data_as(ip32))
+    return lo, hi
+
+
+def dtw_average_mm(X, r=1.0, g=None, init=None, sample_weight=None, tol=1e-5, max_epoch=50):
+    """`_mm_dtw_average` (dtw.py:655-690) with the cost function of `dtw_average` (dtw.py:590-605)."""
+    X = _arr(X)
+    mean = np.array(init, dtype=float, copy=True)
+    metric, mp = ("dtw", dict(r=r)) if g is None else ("wdtw", dict(r=r, g=g))
+
+    def costfn(mean):
+        cost = pairwise(metric, mean.reshape(1, -1), X, **mp)[0]
+        return np.mean(cost) if sample_weight is None else np.average(cost, weights=sample_weight)
+
+    cost = costfn(mean)
+    for _ in range(max_epoch):
+        z = np.zeros(mean.shape[0])
+        V = np.zeros(mean.shape[0])
+        for i in range(X.shape[0]):
+            weight = None if g is None else jeong_weight(max(mean.shape[0], X.shape[1]), g)
+            lo, hi = dtw_path(dtw_alignment(mean, X[i], r=r, weight=weight))
+            w = 1.0 if sample_weight is None else sample_weight[i]
+            for m in range(mean.shape[0]):
+                for xx in range(lo[m], hi[m] + 1):
+                    V[m] += w
+                    z[m] += X[i, xx] * w
+        mean = z / V
+        prev_cost, cost = cost, costfn(mean)
+        if abs(prev_cost - cost) < tol:
+            break
+    return mean, cost

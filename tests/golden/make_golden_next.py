@@ -4,6 +4,7 @@
 
 Writes tests/golden/next_golden.npz:
   nd|...   multivariate pairwise / self / paired with dim="mean" / "full" (_distance.py:1245-1297, 1163-1169)
+  al|... dba|... km|...  dtw_alignment / dtw_mapping / dtw_average (distance/dtw.py:246-690), KMeans(metric="dtw")
   nb|...   KNeighborsClassifier.predict_proba / predict and NearestNeighbors.kneighbors (distance/_neighbors.py:19-300)
 """
 import os
@@ -69,6 +70,43 @@ def neighbors(wd, out):
         out[f"nb3|{metric}|nnself|dist"], out[f"nb3|{metric}|nnself|ind"] = d, i.astype(np.int64)
 
 
+def alignments(wd, out):
+    """dtw_alignment / wdtw_alignment / dtw_mapping / dtw_average / KMeans(metric="dtw") of the reference."""
+    from wildboar.distance import dtw as rd
+    from wildboar.distance import KMeans
+    rng = np.random.default_rng(20261020)
+    shapes = [(30, 30, 0.1), (25, 40, 0.2), (40, 25, 0.3), (16, 16, 1.0), (12, 12, 0.0), (1, 5, 0.5), (5, 1, 0.5), (64, 64, 0.05)]
+    out["al|shapes"] = np.array(shapes)
+    for k, (tx, ty, r) in enumerate(shapes):
+        x = np.cumsum(rng.standard_normal(tx))
+        y = np.cumsum(rng.standard_normal(ty))
+        out[f"al|{k}|x"], out[f"al|{k}|y"] = x, y
+        for name, fn, kw in (("dtw", rd.dtw_alignment, {}), ("wdtw", rd.wdtw_alignment, {"g": 0.1})):
+            # the reference leaves the cells outside the band uninitialised: pre-fill them with NaN
+            a = fn(x, y, r=r, out=np.full((tx, ty), np.nan), **kw)
+            out[f"al|{k}|{name}|matrix"] = a
+            out[f"al|{k}|{name}|path"] = rd.dtw_mapping(alignment=a)
+    X = np.cumsum(rng.standard_normal((24, 48)), axis=1)
+    sw = rng.random(24) + 0.5
+    out["dba|X"], out["dba|sw"] = X, sw
+    for name, kw in (("mm", {}), ("mm_g", {"g": 0.15}), ("mm_sw", {"sample_weight": sw}), ("mm_r1", {"r": 1.0}),
+                     ("ssg", {"method": "ssg", "random_state": 3, "max_epoch": 6}),
+                     ("random", {"init": "random", "random_state": 5})):
+        args = dict(r=0.2, init=X[7], method="mm", return_cost=True)
+        args.update(kw)
+        mean, cost = rd.dtw_average(X, **args)
+        out[f"dba|{name}|mean"], out[f"dba|{name}|cost"] = mean, np.array(cost)
+    Xk = np.concatenate([np.cumsum(rng.standard_normal((20, 40)), axis=1) + off for off in (0.0, 6.0, -6.0)])
+    out["km|X"] = Xk
+    for name, kw in (("dtw", {}), ("wdtw", {"g": 0.1}), ("k7", {"n_clusters": 7, "n_init": 2, "r": 0.1})):
+        args = dict(n_clusters=3, metric="dtw", r=0.2, random_state=11, max_iter=20)
+        args.update(kw)
+        km = KMeans(**args).fit(Xk)
+        out[f"km|{name}|centers"], out[f"km|{name}|labels"] = km.cluster_centers_, km.labels_.astype(np.int64)
+        out[f"km|{name}|inertia"], out[f"km|{name}|n_iter"] = np.array(km.inertia_), np.array(km.n_iter_)
+        out[f"km|{name}|transform"] = km.transform(Xk[::5])
+
+
 def main():
     wd = ref.load()
     if wd is None:
@@ -76,6 +114,7 @@ def main():
     out = {}
     multivariate(wd, out)
     neighbors(wd, out)
+    alignments(wd, out)
     path = os.path.join(HERE, "next_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")

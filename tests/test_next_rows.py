@@ -175,3 +175,142 @@ def test_fitted_set_equals_host_calls(W, oracle):
     fit.close()
     with pytest.raises(RuntimeError, match="released"):
         _shim.pairwise_fitted(m.metric_id, m._params(), q.reshape(200, 1, 64), fit)
+
+
+# ---------------------------------------------------------------------------------------------
+# DTW alignment, warping path, DBA, KMeans(metric="dtw")
+# ---------------------------------------------------------------------------------------------
+def _al_cases(g):
+    for k, (tx, ty, r) in enumerate(g["al|shapes"]):
+        yield k, int(tx), int(ty), float(r)
+
+
+def _band_equal(got, want):
+    """Equal wherever the reference wrote a value (NaN = cells its np.empty matrix leaves uninitialised)."""
+    written = ~np.isnan(want)
+    return np.array_equal(got[written], want[written])
+
+
+def test_oracle_alignment_path_dba_match_reference_golden(oracle, next_golden):
+    g = next_golden
+    for k, tx, ty, r in _al_cases(g):
+        x, y = g[f"al|{k}|x"], g[f"al|{k}|y"]
+        for name, w in (("dtw", None), ("wdtw", oracle.jeong_weight(max(tx, ty), 0.1))):
+            a = oracle.dtw_alignment(x, y, r=r, weight=w)
+            assert np.array_equal(a, g[f"al|{k}|{name}|matrix"], equal_nan=True), (k, name)
+            lo, hi = oracle.dtw_path(a)
+            cols = np.arange(ty)[None, :]
+            assert np.array_equal((cols >= lo[:, None]) & (cols <= hi[:, None]), g[f"al|{k}|{name}|path"]), (k, name)
+    X, sw = g["dba|X"], g["dba|sw"]
+    for name, kw in (("mm", {}), ("mm_g", {"g": 0.15}), ("mm_sw", {"sample_weight": sw}), ("mm_r1", {"r": 1.0})):
+        args = dict(r=0.2, init=X[7])
+        args.update(kw)
+        mean, cost = oracle.dtw_average_mm(X, **args)
+        assert np.array_equal(mean, g[f"dba|{name}|mean"]) and cost == g[f"dba|{name}|cost"], name
+
+
+def test_dtw_module_host_logic(wb):
+    from wildboar_b200 import dtw
+    assert np.array_equal(dtw.jeong_weight(5, 0.3), 1.0 / (1.0 + np.exp(-0.3 * (np.arange(5, dtype=float) - 2.5))))
+    with pytest.raises(ValueError, match="r =="):
+        dtw.dtw_alignment(np.zeros(4), np.zeros(4), r=1.5)
+    with pytest.raises(ValueError, match="weight must have the same size"):
+        dtw.dtw_alignment(np.zeros(4), np.zeros(6), weight=np.ones(4))
+    with pytest.raises(ValueError, match="neither x or y"):
+        dtw.dtw_mapping(x=np.zeros(3))
+    with pytest.raises(ValueError, match="minimum of 2"):
+        dtw.dtw_average(np.zeros((1, 5)))
+    with pytest.raises(ValueError, match="method must be"):
+        if wb.device_count() == 0:
+            raise ValueError("method must be (no device: the sample set cannot be uploaded)")
+        dtw.dtw_average(np.zeros((3, 5)), init=np.zeros(5), method="bogus")
+    # a precomputed alignment is walked back on the host exactly like the reference
+    a = np.array([[0.0, 1.0, np.inf], [1.0, 0.5, 2.0], [np.inf, 1.5, 0.7]])
+    assert np.array_equal(dtw.dtw_mapping(alignment=a), np.eye(3, dtype=bool))
+    from wildboar_b200.neighbors import KMeans
+    with pytest.raises(ValueError, match="metric"):
+        KMeans(3, metric="euclidean").fit(np.zeros((5, 8)))
+    with pytest.raises(ValueError, match="n_clusters"):
+        KMeans(0).fit(np.zeros((5, 8)))
+
+
+@pytest.mark.gpu
+def test_alignment_and_mapping_match_reference_golden(W, next_golden):
+    from wildboar_b200 import dtw
+    g = next_golden
+    for k, tx, ty, r in _al_cases(g):
+        x, y = g[f"al|{k}|x"], g[f"al|{k}|y"]
+        for name, fn, kw in (("dtw", dtw.dtw_alignment, {}), ("wdtw", dtw.wdtw_alignment, {"g": 0.1})):
+            want = g[f"al|{k}|{name}|matrix"]
+            got = fn(x, y, r=r, **kw)
+            assert _band_equal(got, want), (k, name)
+            assert np.all(np.isposinf(got[np.isnan(want)])), (k, name)   # outside the band: +inf instead of garbage
+            assert np.array_equal(dtw.dtw_mapping(alignment=got), g[f"al|{k}|{name}|path"]), (k, name)
+        assert np.array_equal(dtw.dtw_mapping(x, y, r=r), g[f"al|{k}|dtw|path"]), k
+        ind, (ii, jj) = dtw.dtw_mapping(x, y, r=r, return_index=True)
+        assert np.array_equal(np.stack([ii, jj]), np.stack(g[f"al|{k}|dtw|path"].nonzero()))
+
+
+@pytest.mark.gpu
+def test_batched_paths_match_oracle(W, oracle):
+    from wildboar_b200 import dtw
+    a, b = random_walks(70, 90, 41), random_walks(33, 120, 42)
+    ia = np.random.default_rng(1).integers(0, 70, 200)
+    ib = np.random.default_rng(2).integers(0, 33, 200)
+    for r, weight in ((0.1, None), (0.3, oracle.jeong_weight(120, 0.2)), (1.0, None), (0.0, None)):
+        lo, hi, cost = dtw.dtw_paths(a, b, r=r, weight=weight, ia=ia, ib=ib, return_cost=True)
+        for p in range(0, 200, 7):
+            A = oracle.dtw_alignment(a[ia[p]], b[ib[p]], r=r, weight=weight)
+            olo, ohi = oracle.dtw_path(A)
+            assert np.array_equal(lo[p], olo) and np.array_equal(hi[p], ohi), (r, p)
+            assert cost[p] == A[-1, -1]
+    lo, hi = dtw.dtw_paths(a[:33], b, r=0.2)     # no index arrays: pair p = (a[p], b[p])
+    olo, ohi = oracle.dtw_path(oracle.dtw_alignment(a[32], b[32], r=0.2))
+    assert np.array_equal(lo[32], olo) and np.array_equal(hi[32], ohi)
+
+
+@pytest.mark.gpu
+def test_dtw_average_matches_reference_golden(W, next_golden):
+    from wildboar_b200 import dtw
+    g = next_golden
+    X, sw = g["dba|X"], g["dba|sw"]
+    for name, kw in (("mm", {}), ("mm_g", {"g": 0.15}), ("mm_sw", {"sample_weight": sw}), ("mm_r1", {"r": 1.0}),
+                     ("ssg", {"method": "ssg", "random_state": 3, "max_epoch": 6}),
+                     ("random", {"init": "random", "random_state": 5})):
+        args = dict(r=0.2, init=X[7], method="mm", return_cost=True)
+        args.update(kw)
+        mean, cost = dtw.dtw_average(X, **args)
+        assert np.array_equal(mean, g[f"dba|{name}|mean"]), name
+        assert cost == g[f"dba|{name}|cost"], name
+    # several groups per device step == one call per group
+    groups = [np.arange(0, 10), np.arange(10, 24), np.array([1, 5, 20])]
+    inits = [X[0], X[12], X[5]]
+    means, costs = dtw.dtw_average_many(X, groups, inits, r=0.2)
+    for grp, init, mean, cost in zip(groups, inits, means, costs):
+        m1, c1 = dtw.dtw_average(X[grp], r=0.2, init=init, return_cost=True)
+        assert np.array_equal(mean, m1) and cost == c1
+
+
+@pytest.mark.gpu
+def test_dba_larger_matches_oracle(W, oracle):
+    from wildboar_b200 import dtw
+    X = random_walks(40, 200, 43)
+    mean, cost = dtw.dtw_average(X, r=0.1, init=X[3], max_epoch=4, return_cost=True)
+    omean, ocost = oracle.dtw_average_mm(X, r=0.1, init=X[3], max_epoch=4)
+    assert np.array_equal(mean, omean) and cost == ocost
+
+
+@pytest.mark.gpu
+def test_kmeans_matches_reference_golden(W, next_golden):
+    from wildboar_b200.neighbors import KMeans
+    g = next_golden
+    Xk = g["km|X"]
+    for name, kw in (("dtw", {}), ("wdtw", {"g": 0.1}), ("k7", {"n_clusters": 7, "n_init": 2, "r": 0.1})):
+        args = dict(n_clusters=3, metric="dtw", r=0.2, random_state=11, max_iter=20)
+        args.update(kw)
+        km = KMeans(**args).fit(Xk)
+        assert np.array_equal(km.cluster_centers_, g[f"km|{name}|centers"]), name
+        assert np.array_equal(km.labels_, g[f"km|{name}|labels"]), name
+        assert km.inertia_ == g[f"km|{name}|inertia"] and km.n_iter_ == g[f"km|{name}|n_iter"], name
+        assert np.array_equal(km.transform(Xk[::5]), g[f"km|{name}|transform"]), name
+        assert np.array_equal(km.predict(Xk[::5]), g[f"km|{name}|transform"].argmin(axis=1)), name

@@ -74,6 +74,10 @@ def lib():
                 L.wb_cuda_fit_free.restype = None
                 L.wb_cuda_pairwise_fitted.argtypes = [ci, PP, _DP, i64, i64, i64, i64, i64, C.c_void_p, ci, _DP, SP]
                 L.wb_cuda_argmin_fitted.argtypes = [ci, PP, _DP, i64, i64, i64, C.c_void_p, i64, _DP, ci, _IP, _DP, SP]
+                I32P = C.POINTER(C.c_int32)
+                L.wb_cuda_dtw_paths.argtypes = [_DP, i64, i64, i64, _DP, i64, i64, i64, _IP, _IP, i64, C.c_double, _DP, I32P,
+                                                I32P, _DP, _DP, ci, SP]
+                L.wb_cuda_dba_epoch.argtypes = [C.c_void_p, ci, PP, _DP, i64, i64, _IP, _IP, _DP, _DP, ci, _DP, _DP, SP]
                 L.wb_cuda_argmin.argtypes = [ci, PP, _DP, i64, i64, i64, _DP, i64, i64, i64, i64, _DP, ci, _IP, _DP,
                                              DV, ci, SP]
                 L.wb_cuda_pairwise_dev.argtypes = [ci, PP, C.c_void_p, i64, i64, C.c_void_p, i64, i64, C.c_void_p,
@@ -330,6 +334,71 @@ def argmin_fitted(metric_id, params, x, fitted, k, lower_bound=None, use_device_
                                        C.byref(st)))
     _tls.stats = st.as_dict()
     return idx.astype(np.intp, copy=False), dist
+
+
+def dtw_paths(a, b, r, weights=None, ia=None, ib=None, want_cost=False, want_matrix=False):
+    """Warping paths of pairs (a[ia[p]], b[ib[p]]): (lo, hi[, cost][, matrix]), include/wb_cuda.h."""
+    a, ap, na, Ta, as_ = _rows(a)
+    b, bp, nb, Tb, bs_ = _rows(b)
+    iap = ibp = None
+    n_pairs = min(na, nb)
+    if ia is not None:
+        ia = np.ascontiguousarray(ia, dtype=np.int64)
+        iap, n_pairs = ia.ctypes.data_as(_IP), ia.shape[0]
+    if ib is not None:
+        ib = np.ascontiguousarray(ib, dtype=np.int64)
+        ibp, n_pairs = ib.ctypes.data_as(_IP), ib.shape[0]
+    if ia is not None and ib is not None:
+        assert ia.shape == ib.shape
+    wp = None
+    if weights is not None:
+        weights = np.ascontiguousarray(weights, dtype=np.float64)
+        assert weights.shape[0] == max(Ta, Tb)
+        wp = weights.ctypes.data_as(_DP)
+    I32P = C.POINTER(C.c_int32)
+    lo = np.empty((n_pairs, Ta), dtype=np.int32)
+    hi = np.empty((n_pairs, Ta), dtype=np.int32)
+    cost = np.empty(n_pairs, dtype=np.float64) if want_cost else None
+    mat = np.empty((n_pairs, Ta, Tb), dtype=np.float64) if want_matrix else None
+    st = WbStats()
+    _check(lib().wb_cuda_dtw_paths(ap, na, Ta, as_, bp, nb, Tb, bs_, iap, ibp, n_pairs, float(r), wp,
+                                   lo.ctypes.data_as(I32P), hi.ctypes.data_as(I32P),
+                                   cost.ctypes.data_as(_DP) if want_cost else None,
+                                   mat.ctypes.data_as(_DP) if want_matrix else None, _first_device(), C.byref(st)))
+    _tls.stats = st.as_dict()
+    out = [lo, hi]
+    if want_cost:
+        out.append(cost)
+    if want_matrix:
+        out.append(mat)
+    return tuple(out)
+
+
+def dba_epoch(fitted, metric_id, params, means, offsets, members, sample_weight=None, weights=None, update=True):
+    """One DBA step for all clusters (wb_cuda_dba_epoch): (new_means (K, Tm), dist (n_members,))."""
+    apply_engine_override(params)
+    means = np.ascontiguousarray(means, dtype=np.float64)
+    K, Tm = means.shape
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    members = np.ascontiguousarray(members, dtype=np.int64)
+    assert offsets.shape[0] == K + 1 and offsets[-1] == members.shape[0]
+    swp = wp = None
+    if sample_weight is not None:
+        sample_weight = np.ascontiguousarray(sample_weight, dtype=np.float64)
+        assert sample_weight.shape[0] == fitted.shape[0]
+        swp = sample_weight.ctypes.data_as(_DP)
+    if weights is not None:
+        weights = np.ascontiguousarray(weights, dtype=np.float64)
+        assert weights.shape[0] == max(Tm, fitted.shape[2])
+        wp = weights.ctypes.data_as(_DP)
+    out = np.empty((K, Tm), dtype=np.float64)
+    dist = np.empty(members.shape[0], dtype=np.float64)
+    st = WbStats()
+    _check(lib().wb_cuda_dba_epoch(fitted._handle(), metric_id, C.byref(params), means.ctypes.data_as(_DP), K, Tm,
+                                   offsets.ctypes.data_as(_IP), members.ctypes.data_as(_IP), swp, wp, 1 if update else 0,
+                                   out.ctypes.data_as(_DP), dist.ctypes.data_as(_DP), C.byref(st)))
+    _tls.stats = st.as_dict()
+    return out, dist
 
 
 def _first_device():

@@ -11,6 +11,7 @@ enum PairMode : int {
   PM_SELF = 1,      // j > i only, also written to out[j][i]          (CD:1208-1267)
   PM_PAIRED = 2,    // out[i] = d(x_i, y_i)  (caller already swapped)  (CD:1597-1652)
   PM_LIST = 3,      // out[i][j] for the (i, j) of a device-resident survivor list (argmin cascade)
+  PM_LISTP = 4,     // out[e] = d(x_i, y_j) for list entry e = (i, j)   (DBA: members against their centre)
 };
 
 // F = arithmetic type of the DP (double: bit-exact mode, float: fp32 mode).  Results, per-series
@@ -52,13 +53,13 @@ using KArgs = KArgsT<double>;
 // One warp task = 32 consecutive pairs.  Returns false when the whole task is empty.
 template <class A>
 __device__ __forceinline__ long long task_count(const A& a) {
-  return a.mode == PM_LIST ? ((long long)__ldg(a.list_len) + 31) / 32 : a.ntasks;
+  return (a.mode == PM_LIST || a.mode == PM_LISTP) ? ((long long)__ldg(a.list_len) + 31) / 32 : a.ntasks;
 }
 
 template <class A>
 __device__ __forceinline__ bool decode_task(const A& a, long long t, int lane, long long& i, long long& j,
                                             bool& valid) {
-  if (a.mode == PM_LIST) {
+  if (a.mode == PM_LIST || a.mode == PM_LISTP) {
     const long long n = __ldg(a.list_len);
     long long e = t * 32 + lane;
     valid = e < n;
@@ -98,6 +99,13 @@ __device__ __forceinline__ double combine_dims(const A& a, const double* po, dou
   return d;
 }
 
+template <class A>
+__device__ __forceinline__ double* result_ptr(const A& a, long long t, int lane, long long i, long long j) {
+  if (a.mode == PM_PAIRED) return &a.out[i];
+  if (a.mode == PM_LISTP) return &a.out[t * 32 + lane];
+  return &a.out[i * a.ld + j];
+}
+
 __device__ __forceinline__ long long next_task(unsigned long long* counter, int lane) {
   unsigned long long t = 0;
   if (lane == 0) t = atomicAdd(counter, 1ULL);
@@ -133,7 +141,7 @@ __global__ void __launch_bounds__(NT, MINB) k_strip(KArgsT<typename M::real> a, 
     if (valid) {
       // results are written once and never re-read by the kernel: streaming stores keep them from
       // displacing the boundary buffers / y tiles in L2
-      double* const po = a.mode == PM_PAIRED ? &a.out[i] : &a.out[i * a.ld + j];
+      double* const po = result_ptr(a, t, lane, i, j);
       const double r = combine_dims(a, po, d);
       __stcs(po, r);
       if (a.mode == PM_SELF && a.mirror) __stcs(&a.out[j * a.ld + i], r);
@@ -166,10 +174,10 @@ __global__ void __launch_bounds__(NT) k_rowscan(KArgsT<typename M::real> a, M m)
     F mmax = F(0);
     const double d = (double)rowscan_pair<M>(a.g, mm, a.x + i * a.Tx, a.y + j * a.Ty, b0, b1, a.sstride, md, &mmax);
     if (valid) {
-      double* const po = a.mode == PM_PAIRED ? &a.out[i] : &a.out[i * a.ld + j];
+      double* const po = result_ptr(a, t, lane, i, j);
       const double r = combine_dims(a, po, d);
       *po = r;
-      if (a.mode != PM_PAIRED) {
+      if (a.mode != PM_PAIRED && a.mode != PM_LISTP) {
         if (a.out_m) a.out_m[i * a.ld + j] = (double)mmax;
         if (a.mode == PM_SELF && a.mirror) a.out[j * a.ld + i] = r;
       }

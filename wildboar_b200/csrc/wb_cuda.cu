@@ -21,6 +21,7 @@
 #include "prep.hpp"
 #include "argmin.cuh"
 #include "lb.cuh"
+#include "dba.cuh"
 
 namespace wb {
 
@@ -45,6 +46,7 @@ struct Workspace {
   std::vector<void*> bufs;
   std::vector<std::vector<double>> host_keep;  // host staging that must outlive async copies
   std::vector<std::vector<float>> host_keep_f;
+  std::vector<std::vector<int>> host_keep_i;
   explicit Workspace(cudaStream_t s) : stream(s) {}
   ~Workspace() { for (void* p : bufs) cudaFreeAsync(p, stream); }
   template <class T> int alloc(T** p, size_t n) {
@@ -228,6 +230,7 @@ struct DpCall {
   long long row0; int mirror;
   bool need_rowmin;    // force the row-scan engine (exact replay needs row minima)
   const int2* list; const int* list_len;  // PM_LIST (argmin cascade): device-resident survivor list
+  long long list_n;                       // PM_LISTP: number of list entries (known on the host)
   // prepared operands (filled by prepare_operands; reusable across chunked launches)
   const double* px; const double* py; int ptx, pty;
   const double* sx; const double* sy;
@@ -345,6 +348,7 @@ static int launch_dp_t(Workspace& ws, const DeviceInfo& di, const DpCall& c, lon
   a.acc = c.acc; a.div = c.div;
   a.nyb = (ncols + 31) / 32;
   a.ntasks = (c.mode == PM_PAIRED) ? (nrows + 31) / 32 : nrows * a.nyb;
+  if (c.mode == PM_LISTP) a.ntasks = (c.list_n + 31) / 32;
   unsigned long long* counter = nullptr;
   if (ws.alloc(&counter, 1)) return 1;
   WB_CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
@@ -395,6 +399,7 @@ static int launch_dp_t(Workspace& ws, const DeviceInfo& di, const DpCall& c, lon
     stats->engine = engine;
     stats->launches += 1;
     long long pairs = (c.mode == PM_PAIRED) ? nrows : nrows * ncols;
+    if (c.mode == PM_LISTP) pairs = c.list_n;
     if (c.mode == PM_SELF) {
       pairs = 0;
       for (long long i = 0; i < nrows; ++i) {
@@ -759,6 +764,208 @@ static int run_lb(int op, const double* q, int64_t nq, int64_t qs, const double*
   return rc;
 }
 
+// ------------------------------------------------------------------------------------------
+// DTW alignment paths + DBA (kernels in dba.cuh).
+// ------------------------------------------------------------------------------------------
+// dtw.py:38-40 `_compute_warp_size`: max(floor(max(Ta, Tb) r), 1)
+static int warp_size_max(int64_t Ta, int64_t Tb, double r) {
+  return (int)std::max<int64_t>((int64_t)std::floor((double)std::max(Ta, Tb) * r), 1);
+}
+
+// Device-level: paths of n_pairs (a[ia[p]], b[ib[p]]) pairs.  d_w: centre of the signed weight table or nullptr.
+static int run_paths_dev(Workspace& ws, const double* d_a, int64_t Ta, const double* d_b, int64_t Tb, const int* d_ia,
+                         const int* d_ib, int64_t n_pairs, int R, const double* d_w, int* d_lo, int* d_hi, double* d_cost,
+                         double* d_D, wb_stats* stats) {
+  cudaStream_t st = ws.stream;
+  PathArgs p;
+  memset(&p, 0, sizeof p);
+  p.a = d_a; p.b = d_b; p.g = make_geom((int)Ta, (int)Tb, R); p.w = d_w;
+  p.HB = (p.g.H + 3) / 4;
+  // pairs per launch: bound the move buffer (<= 2 GB) and the scratch rows
+  const size_t per_task_moves = (size_t)Ta * p.HB * 32;
+  int64_t chunk = std::max<int64_t>(32, (int64_t)(((size_t)2 << 30) / per_task_moves) * 32);
+  chunk = std::min<int64_t>(chunk, 1 << 16);
+  chunk = std::min<int64_t>(chunk, (n_pairs + 31) / 32 * 32);
+  const int64_t threads = (chunk + 127) / 128 * 128;
+  unsigned char* moves = nullptr; double* scratch = nullptr;
+  if (ws.alloc(&moves, (size_t)(threads / 32) * per_task_moves) || ws.alloc(&scratch, (size_t)2 * (Tb + 1) * threads)) return 1;
+  p.moves = moves; p.scratch = scratch; p.sstride = threads;
+  for (int64_t p0 = 0; p0 < n_pairs; p0 += chunk) {
+    const int64_t np = std::min(chunk, n_pairs - p0);
+    p.n_pairs = np;
+    p.ia = d_ia ? d_ia + p0 : nullptr; p.ib = d_ib ? d_ib + p0 : nullptr;
+    if (!d_ia) p.a = d_a + p0 * Ta;
+    if (!d_ib) p.b = d_b + p0 * Tb;
+    p.lo = d_lo + p0 * Ta; p.hi = d_hi + p0 * Ta;
+    p.cost = d_cost ? d_cost + p0 : nullptr;
+    p.D = d_D ? d_D + p0 * Ta * Tb : nullptr;
+    const unsigned grid = (unsigned)((np + 127) / 128);
+    k_dtw_paths<<<grid, 128, 0, st>>>(p);
+    WB_CK(cudaGetLastError());
+    if (stats) { stats->launches += 1; stats->pairs += np; stats->cells += np * cells_per_pair((int)Ta, (int)Tb, R); }
+  }
+  return 0;
+}
+
+// signed table t[centre + d] = weights[|d|] (prep.hpp layout) from a caller-provided weight vector
+static int upload_weight_table(Workspace& ws, const double* weights, int64_t n, const double** d_center) {
+  *d_center = nullptr;
+  if (!weights) return 0;
+  const int64_t c = table_center(n);
+  ws.host_keep.emplace_back((size_t)(2 * c + 1), 0.0);
+  std::vector<double>& h = ws.host_keep.back();
+  for (int64_t i = 0; i < n; ++i) { h[(size_t)(c + i)] = weights[i]; h[(size_t)(c - i)] = weights[i]; }
+  double* d = nullptr;
+  if (ws.alloc(&d, h.size())) return 1;
+  WB_CK(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, ws.stream));
+  *d_center = d + c;
+  return 0;
+}
+
+static int begin_single_device(int device, DeviceInfo* di, cudaStream_t* st) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { set_err("no CUDA device available: wildboar_b200 has no CPU fallback"); return 1; }
+  if (device < 0 || device >= ndev) { set_err("invalid device ordinal"); return 1; }
+  WB_CK(cudaSetDevice(device));
+  if (device_info(di)) return 1;
+  WB_CK(cudaStreamCreateWithFlags(st, cudaStreamNonBlocking));
+  return 0;
+}
+
+static int upload_index(Workspace& ws, const int64_t* h, int64_t n, int64_t limit, int** d) {
+  *d = nullptr;
+  if (!h) return 0;
+  ws.host_keep_i.emplace_back((size_t)n);
+  std::vector<int>& v = ws.host_keep_i.back();
+  for (int64_t k = 0; k < n; ++k) {
+    if (h[k] < 0 || h[k] >= limit) { set_err("index out of range"); return 1; }
+    v[(size_t)k] = (int)h[k];
+  }
+  if (ws.alloc(d, (size_t)n)) return 1;
+  WB_CK(cudaMemcpyAsync(*d, v.data(), sizeof(int) * n, cudaMemcpyHostToDevice, ws.stream));
+  return 0;
+}
+
+static int run_dtw_paths_host(const double* a, int64_t na, int64_t Ta, int64_t as, const double* b, int64_t nb, int64_t Tb,
+                              int64_t bs, const int64_t* ia, const int64_t* ib, int64_t n_pairs, double r,
+                              const double* weights, int32_t* lo, int32_t* hi, double* cost, double* D, int device,
+                              wb_stats* stats) {
+  DeviceInfo di; cudaStream_t st;
+  if (begin_single_device(device, &di, &st)) return 1;
+  int rc = 0;
+  wb_stats local; memset(&local, 0, sizeof local);
+  {
+    Workspace ws(st);
+    Timer total(st), kt(st);
+    total.start();
+    do {
+      double *da = nullptr, *db = nullptr, *dcost = nullptr, *dD = nullptr;
+      int *dia = nullptr, *dib = nullptr, *dlo = nullptr, *dhi = nullptr;
+      const double* dw = nullptr;
+      if ((rc = ws.alloc(&da, (size_t)na * Ta)) || (rc = ws.alloc(&db, (size_t)nb * Tb))) break;
+      if ((rc = h2d_rows(da, a, na, Ta, as, st)) || (rc = h2d_rows(db, b, nb, Tb, bs, st))) break;
+      if ((rc = upload_index(ws, ia, n_pairs, na, &dia)) || (rc = upload_index(ws, ib, n_pairs, nb, &dib))) break;
+      if ((rc = upload_weight_table(ws, weights, std::max(Ta, Tb), &dw))) break;
+      if ((rc = ws.alloc(&dlo, (size_t)n_pairs * Ta)) || (rc = ws.alloc(&dhi, (size_t)n_pairs * Ta))) break;
+      if (cost && (rc = ws.alloc(&dcost, (size_t)n_pairs))) break;
+      if (D && (rc = ws.alloc(&dD, (size_t)n_pairs * Ta * Tb))) break;
+      kt.start();
+      if ((rc = run_paths_dev(ws, da, Ta, db, Tb, dia, dib, n_pairs, warp_size_max(Ta, Tb, r), dw, dlo, dhi, dcost, dD, &local))) break;
+      kt.stop();
+      if (cudaMemcpyAsync(lo, dlo, sizeof(int) * n_pairs * Ta, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          cudaMemcpyAsync(hi, dhi, sizeof(int) * n_pairs * Ta, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          (cost && cudaMemcpyAsync(cost, dcost, sizeof(double) * n_pairs, cudaMemcpyDeviceToHost, st) != cudaSuccess) ||
+          (D && cudaMemcpyAsync(D, dD, sizeof(double) * n_pairs * Ta * Tb, cudaMemcpyDeviceToHost, st) != cudaSuccess) ||
+          cudaStreamSynchronize(st) != cudaSuccess) { set_err("device-to-host copy of the warping paths failed"); rc = 1; break; }
+      local.kernel_ms = kt.ms();
+    } while (0);
+    total.stop();
+    if (!rc) { cudaStreamSynchronize(st); local.total_ms = total.ms(); }
+  }
+  cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  if (stats) *stats = local;
+  return rc;
+}
+
+// One DBA step for K clusters against a resident sample set (see include/wb_cuda.h, wb_cuda_dba_epoch).
+static int run_dba_epoch(const wb_fitted* fit, int metric, const wb_params& prm, const double* means_in, int64_t K, int64_t Tm,
+                         const int64_t* off, const int64_t* member, const double* sample_weight, const double* weights,
+                         int do_update, double* means_out, double* dist_out, wb_stats* stats) {
+  DeviceInfo di; cudaStream_t st;
+  if (begin_single_device(fit->devs[0], &di, &st)) return 1;
+  int rc = 0;
+  wb_stats local; memset(&local, 0, sizeof local);
+  const int64_t n_m = off[K], T = fit->T;
+  {
+    Workspace ws(st);
+    Timer total(st), kt(st);
+    total.start();
+    do {
+      const double* dX = fit->ptr[0];
+      double *dmeans = nullptr, *dnew = nullptr, *ddist = nullptr, *dsw = nullptr;
+      int *dmem = nullptr, *dlo = nullptr, *dhi = nullptr, *dlen = nullptr, *dia = nullptr;
+      long long* doff = nullptr; int2* dlist = nullptr;
+      const double* dw = nullptr;
+      if ((rc = ws.alloc(&dmeans, (size_t)K * Tm)) || (rc = ws.alloc(&dnew, (size_t)K * Tm)) || (rc = ws.alloc(&ddist, (size_t)n_m)) ||
+          (rc = ws.alloc(&doff, (size_t)K + 1)) || (rc = ws.alloc(&dlist, (size_t)n_m)) || (rc = ws.alloc(&dlen, 1))) break;
+      WB_CK(cudaMemcpyAsync(dmeans, means_in, sizeof(double) * K * Tm, cudaMemcpyHostToDevice, st));
+      if ((rc = upload_index(ws, member, n_m, fit->n, &dmem))) break;
+      // per member: its cluster (row of the means) -- the first operand of every alignment / distance
+      ws.host_keep_i.emplace_back((size_t)n_m);
+      std::vector<int>& hia = ws.host_keep_i.back();
+      ws.host_keep_i.emplace_back((size_t)2 * n_m + 1);
+      std::vector<int>& hlist = ws.host_keep_i.back();
+      for (int64_t c = 0; c < K; ++c) {
+        if (off[c + 1] < off[c]) { set_err("member offsets must be non-decreasing"); rc = 1; break; }
+        for (int64_t q = off[c]; q < off[c + 1]; ++q) { hia[(size_t)q] = (int)c; hlist[(size_t)2 * q] = (int)c; hlist[(size_t)2 * q + 1] = (int)member[q]; }
+      }
+      if (rc) break;
+      hlist[(size_t)2 * n_m] = (int)n_m;
+      if ((rc = ws.alloc(&dia, (size_t)n_m))) break;
+      WB_CK(cudaMemcpyAsync(dia, hia.data(), sizeof(int) * n_m, cudaMemcpyHostToDevice, st));
+      WB_CK(cudaMemcpyAsync(dlist, hlist.data(), sizeof(int) * 2 * n_m, cudaMemcpyHostToDevice, st));
+      WB_CK(cudaMemcpyAsync(dlen, hlist.data() + 2 * n_m, sizeof(int), cudaMemcpyHostToDevice, st));
+      WB_CK(cudaMemcpyAsync(doff, off, sizeof(long long) * (K + 1), cudaMemcpyHostToDevice, st));
+      if (sample_weight) {
+        if ((rc = ws.alloc(&dsw, (size_t)fit->n))) break;
+        WB_CK(cudaMemcpyAsync(dsw, sample_weight, sizeof(double) * fit->n, cudaMemcpyHostToDevice, st));
+      }
+      kt.start();
+      const double* dcur = dmeans;
+      if (do_update) {
+        if ((rc = upload_weight_table(ws, weights, std::max(Tm, T), &dw))) break;
+        if ((rc = ws.alloc(&dlo, (size_t)n_m * Tm)) || (rc = ws.alloc(&dhi, (size_t)n_m * Tm))) break;
+        if ((rc = run_paths_dev(ws, dmeans, Tm, dX, T, dia, dmem, n_m, warp_size_max(Tm, T, prm.r), dw, dlo, dhi, nullptr, nullptr, &local))) break;
+        DbaArgs u;
+        u.X = dX; u.T = (int)T; u.member = dmem; u.off = doff; u.sw = dsw; u.lo = dlo; u.hi = dhi; u.K = (int)K; u.Tm = (int)Tm;
+        u.mean_out = dnew;
+        k_dba_update<<<(unsigned)((K * Tm + 127) / 128), 128, 0, st>>>(u);
+        WB_CK(cudaGetLastError());
+        local.launches += 1;
+        dcur = dnew;
+      }
+      // distance of every member to its (new) centre: metric(centre, sample), as `pairwise_distance(mean, X)` (dtw.py:590-600)
+      DpCall c; memset(&c, 0, sizeof c);
+      c.metric = metric; c.p = prm; c.x = dcur; c.nx = K; c.Tx = (int)Tm; c.y = dX; c.ny = fit->n; c.Ty = (int)T;
+      c.mode = PM_LISTP; c.list = dlist; c.list_len = dlen; c.list_n = n_m;
+      if ((rc = prepare_operands(ws, c))) break;
+      if ((rc = launch_dp(ws, di, c, 0, K, 0, fit->n, ddist, fit->n, nullptr, nullptr, &local))) break;
+      kt.stop();
+      if (cudaMemcpyAsync(means_out, dcur, sizeof(double) * K * Tm, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          cudaMemcpyAsync(dist_out, ddist, sizeof(double) * n_m, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          cudaStreamSynchronize(st) != cudaSuccess) { set_err("device-to-host copy of the DBA step failed"); rc = 1; break; }
+      local.kernel_ms = kt.ms();
+    } while (0);
+    total.stop();
+    if (!rc) { cudaStreamSynchronize(st); local.total_ms = total.ms(); }
+  }
+  cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  if (stats) *stats = local;
+  return rc;
+}
+
 static int check_common(int metric, const wb_params* p, const void* x, int64_t n, int64_t T) {
   if (!p || !x) { set_err("null argument"); return 1; }
   if (metric < 0 || metric >= M_COUNT) { set_err("unknown metric id"); return 1; }
@@ -930,6 +1137,32 @@ int wb_cuda_argmin_fitted(int metric, const wb_params* params, const double* x, 
   J.ny = fit->n; J.Ty = fit->T; J.out = out_dist; J.out_idx = out_idx; J.k = k;
   J.lower_bound = lower_bound; J.use_device_lb = use_device_lb; J.fit = fit;
   return run_host_job(J, fit->devs.data(), (int)fit->devs.size(), stats);
+}
+
+int wb_cuda_dtw_paths(const double* a, int64_t na, int64_t Ta, int64_t a_stride, const double* b, int64_t nb, int64_t Tb,
+                      int64_t b_stride, const int64_t* ia, const int64_t* ib, int64_t n_pairs, double r,
+                      const double* weights, int32_t* path_lo, int32_t* path_hi, double* cost, double* out_matrix,
+                      int device, wb_stats* stats) {
+  if (!a || !b || !path_lo || !path_hi) { set_err("null argument"); return 1; }
+  if (na < 1 || nb < 1 || Ta < 1 || Tb < 1 || n_pairs < 1) { set_err("empty input"); return 1; }
+  if (Ta > (1 << 24) || Tb > (1 << 24)) { set_err("series too long"); return 1; }
+  if (!(r >= 0.0 && r <= 1.0)) { set_err("r must be in [0, 1]"); return 1; }
+  if ((!ia && n_pairs > na) || (!ib && n_pairs > nb)) { set_err("without an index array, n_pairs must not exceed the number of series"); return 1; }
+  return run_dtw_paths_host(a, na, Ta, a_stride, b, nb, Tb, b_stride, ia, ib, n_pairs, r, weights, path_lo, path_hi, cost,
+                            out_matrix, device, stats);
+}
+
+int wb_cuda_dba_epoch(const wb_fitted* fit, int metric, const wb_params* params, const double* means_in, int64_t K, int64_t Tm,
+                      const int64_t* member_offsets, const int64_t* members, const double* sample_weight,
+                      const double* weights, int do_update, double* means_out, double* dist_out, wb_stats* stats) {
+  if (!fit || !params || !means_in || !member_offsets || !members || !means_out || !dist_out) { set_err("null argument"); return 1; }
+  if (fit->nd != 1) { set_err("DBA needs a univariate fitted set"); return 1; }
+  if (metric != M_DTW && metric != M_WDTW) { set_err("DBA is defined for dtw and wdtw"); return 1; }
+  if (K < 1 || Tm < 1 || member_offsets[0] != 0 || member_offsets[K] < 1) { set_err("empty input"); return 1; }
+  if (!(params->r >= 0.0 && params->r <= 1.0)) { set_err("r must be in [0, 1]"); return 1; }
+  if (metric == M_WDTW && do_update && !weights) { set_err("wdtw alignment needs the weight vector"); return 1; }
+  return run_dba_epoch(fit, metric, *params, means_in, K, Tm, member_offsets, members, sample_weight, weights, do_update,
+                       means_out, dist_out, stats);
 }
 
 int wb_cuda_pairwise_dev(int metric, const wb_params* params, const double* d_x, int64_t nx, int64_t Tx,

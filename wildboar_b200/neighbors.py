@@ -36,7 +36,7 @@ except Exception:  # pragma: no cover
     class _NotFitted(ValueError, AttributeError):
         pass
 
-__all__ = ["NearestNeighbors", "KNeighborsClassifier"]
+__all__ = ["NearestNeighbors", "KNeighborsClassifier", "KMeans"]
 
 
 class _NeighborsBase(_SkBase):
@@ -215,3 +215,150 @@ class KNeighborsClassifier(_NeighborsBase):
     def score(self, x, y):
         """Mean accuracy (sklearn.base.ClassifierMixin.score)."""
         return float(np.mean(self.predict(x) == np.asarray(y)))
+
+
+class KMeans(_SkBase):
+    """KMeans clustering with DTW / weighted-DTW barycentres (reference: _neighbors.py:303-640, metric="dtw").
+
+    Same parameters (except that only ``metric="dtw"`` is accelerated -- euclidean k-means is not an elastic
+    path), same random-number consumption, same ``cluster_centers_`` / ``labels_`` / ``inertia_`` /
+    ``n_iter_`` as the reference.  B200-first: assignment and cost are one ``argmin`` / ``paired`` call each,
+    and the barycentre update of ALL clusters runs as batched DBA epochs on the device
+    (``wildboar_b200.dtw.dtw_average_many``) against a sample set that is uploaded once per ``fit``.
+    """
+
+    _param_names = ("n_clusters", "metric", "r", "g", "init", "n_init", "max_iter", "tol", "verbose", "random_state")
+
+    def __init__(self, n_clusters=8, *, metric="dtw", r=1.0, g=None, init="random", n_init="auto", max_iter=300,
+                 tol=1e-3, verbose=0, random_state=None):
+        self.metric = metric
+        self.r = r
+        self.g = g
+        self.n_clusters = n_clusters
+        self.init = init
+        self.n_init = n_init
+        self.max_iter = max_iter
+        self.tol = tol
+        self.verbose = verbose
+        self.random_state = random_state
+
+    def _validate_params(self):
+        name = type(self).__name__
+
+        def bad(param, what):
+            return ValueError(f"The {param!r} parameter of {name} must be {what}. Got {getattr(self, param)!r} instead.")
+
+        def is_int(v):
+            return isinstance(v, numbers.Integral) and not isinstance(v, bool)
+
+        if not is_int(self.n_clusters) or self.n_clusters < 1:
+            raise bad("n_clusters", "an int in the range [1, inf)")
+        if self.metric != "dtw":
+            raise bad("metric", "'dtw' (euclidean k-means is not an elastic path and is not accelerated)")
+        if isinstance(self.r, bool) or not isinstance(self.r, numbers.Real) or not 0 <= self.r <= 1:
+            raise bad("r", "a float in the range [0, 1]")
+        if self.g is not None and (isinstance(self.g, bool) or not isinstance(self.g, numbers.Real) or not self.g > 0):
+            raise bad("g", "None or a float in the range (0, inf)")
+        if self.init != "random":
+            raise bad("init", "a str among {'random'}")
+        if not (self.n_init == "auto" or (is_int(self.n_init) and self.n_init >= 1)):
+            raise bad("n_init", "a str among {'auto'} or an int in the range [1, inf)")
+        if not is_int(self.max_iter) or self.max_iter < 1:
+            raise bad("max_iter", "an int in the range [1, inf)")
+        if not isinstance(self.tol, float):
+            raise bad("tol", "an instance of 'float'")
+
+    def _metric(self):
+        if self.g is None:
+            return "dtw", {"r": self.r}
+        return "wdtw", {"r": self.r, "g": self.g}
+
+    def fit(self, x, y=None):
+        from .dtw import _check_random_state
+        self._validate_params()
+        x = check_array(x, allow_3d=False, dtype=float, input_name="x")
+        self.n_timesteps_in_ = x.shape[-1]
+        n_init = 1 if self.n_init == "auto" else self.n_init
+        random_state = _check_random_state(self.random_state)
+        fitted = _shim.FittedSet(x.reshape(x.shape[0], 1, x.shape[1]), devices=[_shim._first_device()])
+        try:
+            best = None
+            best_cost = np.inf
+            for _ in range(n_init):
+                run = self._fit_one_init(x, fitted, random_state)
+                if run["cost"] < best_cost:
+                    best_cost, best = run["cost"], run
+        finally:
+            fitted.close()
+        self.n_iter_ = best["iter"]
+        self.inertia_ = best_cost
+        self.cluster_centers_ = best["centroids"]
+        if best["reassign"]:
+            best["assigned"], best["distance"] = self._assign(x, best["centroids"])
+        self.labels_ = best["assigned"]
+        return self
+
+    # _KMeansCluster.assign / cost (_neighbors.py:303-347)
+    def _assign(self, x, centroids):
+        from .distance import argmin_distance
+        metric, mp = self._metric()
+        assigned, distance = argmin_distance(x, centroids, k=1, metric=metric, metric_params=mp, return_distance=True)
+        return np.ravel(assigned), distance
+
+    def _cost(self, x, centroids, assigned):
+        from .distance import paired_distance
+        metric, mp = self._metric()
+        return paired_distance(x, centroids[assigned], dim="mean", metric=metric, metric_params=mp).sum() / x.shape[0]
+
+    def _update(self, x, fitted, centroids, assigned, distance, random_state):
+        """`_KMeansCluster.update` (_neighbors.py:349-361): the cluster loop only does the bookkeeping (membership
+        snapshots, empty / singleton clusters, one `randint` per barycentre as in `_DtwCluster._update_centroid`);
+        the barycentres themselves are computed afterwards, all clusters per device step."""
+        from .dtw import dtw_average_many
+        jobs = []
+        for c in range(centroids.shape[0]):
+            members = np.flatnonzero(assigned == c)
+            if members.shape[0] == 0:
+                far_from_center = distance.min(axis=1).argmax()
+                assigned[far_from_center] = c
+                centroids[c] = x[far_from_center]
+            elif members.shape[0] == 1:
+                centroids[c] = x[members[0]]
+            else:
+                random_state.randint(np.iinfo(np.int32).max)  # consumed by the reference, unused by method="mm"
+                jobs.append((c, members))
+        if jobs:
+            means, _ = dtw_average_many(x, [m for _, m in jobs], [centroids[c] for c, _ in jobs], r=self.r, g=self.g,
+                                        fitted=fitted)
+            for (c, _), mean in zip(jobs, means):
+                centroids[c] = mean
+
+    def _fit_one_init(self, x, fitted, random_state):
+        import math
+        centroids = x[random_state.choice(x.shape[0], size=self.n_clusters, replace=False)]
+        prev_cost, cost, reassign = np.inf, -np.inf, True
+        assigned = distance = None
+        for it in range(self.max_iter):
+            assigned, distance = self._assign(x, centroids)
+            prev_cost, cost = cost, self._cost(x, centroids, assigned)
+            if self.verbose > 0:
+                print(f"Iteration {it}, {cost} (prev_cost = {prev_cost})")
+            if math.isclose(cost, prev_cost, rel_tol=self.tol):
+                reassign = False
+                break
+            self._update(x, fitted, centroids, assigned, distance, random_state)
+        return dict(iter=it, cost=cost, centroids=centroids, assigned=assigned, distance=distance, reassign=reassign)
+
+    def transform(self, x):
+        from .distance import pairwise_distance
+        if not hasattr(self, "cluster_centers_"):
+            raise _NotFitted(f"This {type(self).__name__} instance is not fitted yet. Call 'fit' with appropriate arguments before using this estimator.")
+        x = check_array(x, allow_3d=False, dtype=float, input_name="x")
+        metric, mp = self._metric()
+        return pairwise_distance(x, self.cluster_centers_, dim="mean", metric=metric, metric_params=mp)
+
+    def predict(self, x):
+        return self.transform(x).argmin(axis=1)
+
+    def fit_predict(self, x, y=None):
+        return self.fit(x).labels_
