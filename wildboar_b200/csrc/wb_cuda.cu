@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <limits>
 #include <string>
 #include <thread>
@@ -44,9 +45,10 @@ static void set_err(const std::string& s) { g_err = s; }
 struct Workspace {
   cudaStream_t stream;
   std::vector<void*> bufs;
-  std::vector<std::vector<double>> host_keep;  // host staging that must outlive async copies
-  std::vector<std::vector<float>> host_keep_f;
-  std::vector<std::vector<int>> host_keep_i;
+  // host staging that must outlive async copies (deque: references stay valid across later emplace_back calls)
+  std::deque<std::vector<double>> host_keep;
+  std::deque<std::vector<float>> host_keep_f;
+  std::deque<std::vector<int>> host_keep_i;
   explicit Workspace(cudaStream_t s) : stream(s) {}
   ~Workspace() { for (void* p : bufs) cudaFreeAsync(p, stream); }
   template <class T> int alloc(T** p, size_t n) {
@@ -773,7 +775,7 @@ static int warp_size_max(int64_t Ta, int64_t Tb, double r) {
 }
 
 // Device-level: paths of n_pairs (a[ia[p]], b[ib[p]]) pairs.  d_w: centre of the signed weight table or nullptr.
-static int run_paths_dev(Workspace& ws, const double* d_a, int64_t Ta, const double* d_b, int64_t Tb, const int* d_ia,
+static int run_paths_dev(Workspace& ws, int di_smem_cap, int di_sms, const double* d_a, int64_t Ta, const double* d_b, int64_t Tb, const int* d_ia,
                          const int* d_ib, int64_t n_pairs, int R, const double* d_w, int* d_lo, int* d_hi, double* d_cost,
                          double* d_D, wb_stats* stats) {
   cudaStream_t st = ws.stream;
@@ -781,14 +783,24 @@ static int run_paths_dev(Workspace& ws, const double* d_a, int64_t Ta, const dou
   memset(&p, 0, sizeof p);
   p.a = d_a; p.b = d_b; p.g = make_geom((int)Ta, (int)Tb, R); p.w = d_w;
   p.HB = (p.g.H + 3) / 4;
-  // pairs per launch: bound the move buffer (<= 2 GB) and the scratch rows
+  // threads per CTA: the band row (H + 1 slots per thread) lives in shared memory when it fits
+  const size_t row_bytes = (size_t)(p.g.H + 1) * sizeof(double);
+  // few pairs: small CTAs spread the warps over all SMs (each warp then has an L1 and a scheduler to itself)
+  int nt = 128;
+  while (nt > 32 && (row_bytes * nt > (size_t)200 * 1024 || (n_pairs + nt - 1) / nt < di_sms)) nt >>= 1;
+  const bool smem_ok = row_bytes * nt <= (size_t)di_smem_cap;
+  const size_t smem = smem_ok ? row_bytes * nt : 0;
+  if (!smem_ok) nt = 128;
+  if (smem_ok) WB_CK(cudaFuncSetAttribute(k_dtw_paths<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // pairs per launch: bound the move buffer (<= 2 GB) and the fallback scratch
   const size_t per_task_moves = (size_t)Ta * p.HB * 32;
   int64_t chunk = std::max<int64_t>(32, (int64_t)(((size_t)2 << 30) / per_task_moves) * 32);
   chunk = std::min<int64_t>(chunk, 1 << 16);
   chunk = std::min<int64_t>(chunk, (n_pairs + 31) / 32 * 32);
-  const int64_t threads = (chunk + 127) / 128 * 128;
+  const int64_t threads = (chunk + nt - 1) / nt * nt;
   unsigned char* moves = nullptr; double* scratch = nullptr;
-  if (ws.alloc(&moves, (size_t)(threads / 32) * per_task_moves) || ws.alloc(&scratch, (size_t)2 * (Tb + 1) * threads)) return 1;
+  if (ws.alloc(&moves, (size_t)(threads / 32) * per_task_moves)) return 1;
+  if (!smem_ok && ws.alloc(&scratch, (size_t)(p.g.H + 1) * threads)) return 1;
   p.moves = moves; p.scratch = scratch; p.sstride = threads;
   for (int64_t p0 = 0; p0 < n_pairs; p0 += chunk) {
     const int64_t np = std::min(chunk, n_pairs - p0);
@@ -799,8 +811,9 @@ static int run_paths_dev(Workspace& ws, const double* d_a, int64_t Ta, const dou
     p.lo = d_lo + p0 * Ta; p.hi = d_hi + p0 * Ta;
     p.cost = d_cost ? d_cost + p0 : nullptr;
     p.D = d_D ? d_D + p0 * Ta * Tb : nullptr;
-    const unsigned grid = (unsigned)((np + 127) / 128);
-    k_dtw_paths<<<grid, 128, 0, st>>>(p);
+    const unsigned grid = (unsigned)((np + nt - 1) / nt);
+    if (smem_ok) k_dtw_paths<true><<<grid, nt, smem, st>>>(p);
+    else k_dtw_paths<false><<<grid, nt, 0, st>>>(p);
     WB_CK(cudaGetLastError());
     if (stats) { stats->launches += 1; stats->pairs += np; stats->cells += np * cells_per_pair((int)Ta, (int)Tb, R); }
   }
@@ -870,7 +883,7 @@ static int run_dtw_paths_host(const double* a, int64_t na, int64_t Ta, int64_t a
       if (cost && (rc = ws.alloc(&dcost, (size_t)n_pairs))) break;
       if (D && (rc = ws.alloc(&dD, (size_t)n_pairs * Ta * Tb))) break;
       kt.start();
-      if ((rc = run_paths_dev(ws, da, Ta, db, Tb, dia, dib, n_pairs, warp_size_max(Ta, Tb, r), dw, dlo, dhi, dcost, dD, &local))) break;
+      if ((rc = run_paths_dev(ws, di.max_smem_optin, di.sms, da, Ta, db, Tb, dia, dib, n_pairs, warp_size_max(Ta, Tb, r), dw, dlo, dhi, dcost, dD, &local))) break;
       kt.stop();
       if (cudaMemcpyAsync(lo, dlo, sizeof(int) * n_pairs * Ta, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
           cudaMemcpyAsync(hi, dhi, sizeof(int) * n_pairs * Ta, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
@@ -936,11 +949,11 @@ static int run_dba_epoch(const wb_fitted* fit, int metric, const wb_params& prm,
       if (do_update) {
         if ((rc = upload_weight_table(ws, weights, std::max(Tm, T), &dw))) break;
         if ((rc = ws.alloc(&dlo, (size_t)n_m * Tm)) || (rc = ws.alloc(&dhi, (size_t)n_m * Tm))) break;
-        if ((rc = run_paths_dev(ws, dmeans, Tm, dX, T, dia, dmem, n_m, warp_size_max(Tm, T, prm.r), dw, dlo, dhi, nullptr, nullptr, &local))) break;
+        if ((rc = run_paths_dev(ws, di.max_smem_optin, di.sms, dmeans, Tm, dX, T, dia, dmem, n_m, warp_size_max(Tm, T, prm.r), dw, dlo, dhi, nullptr, nullptr, &local))) break;
         DbaArgs u;
         u.X = dX; u.T = (int)T; u.member = dmem; u.off = doff; u.sw = dsw; u.lo = dlo; u.hi = dhi; u.K = (int)K; u.Tm = (int)Tm;
         u.mean_out = dnew;
-        k_dba_update<<<(unsigned)((K * Tm + 127) / 128), 128, 0, st>>>(u);
+        k_dba_update<<<(unsigned)((K * Tm + 31) / 32), 32, 0, st>>>(u);
         WB_CK(cudaGetLastError());
         local.launches += 1;
         dcur = dnew;
@@ -1090,10 +1103,17 @@ int wb_cuda_fit(const double* y, int64_t ny, int64_t n_dims, int64_t Ty, int64_t
     DeviceInfo di;
     double* p = nullptr;
     if (cudaSetDevice(d) != cudaSuccess || device_info(&di)) { rc = 1; if (g_err.empty()) set_err("cudaSetDevice failed"); break; }
-    if (cudaMalloc(&p, sizeof(double) * (size_t)n_dims * ny * Ty) != cudaSuccess) { cudaGetLastError(); set_err("out of device memory for the fitted set"); rc = 1; break; }
+    // stream-ordered allocation from the device's retained pool (device_info): cudaMalloc / cudaFree cost up to
+    // hundreds of ms next to a large retained pool, which would dominate short estimator calls
+    cudaStream_t st;
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { set_err("cudaStreamCreate failed"); rc = 1; break; }
+    if (cudaMallocAsync((void**)&p, sizeof(double) * (size_t)n_dims * ny * Ty, st) != cudaSuccess) {
+      cudaGetLastError(); cudaStreamDestroy(st); set_err("out of device memory for the fitted set"); rc = 1; break;
+    }
     f->ptr.push_back(p);
-    for (int64_t k = 0; k < n_dims && !rc; ++k) rc = h2d_rows(p + k * ny * Ty, y + k * y_dim_stride, ny, Ty, y_stride, 0);
-    if (!rc && cudaDeviceSynchronize() != cudaSuccess) { set_err("upload of the fitted set failed"); rc = 1; }
+    for (int64_t k = 0; k < n_dims && !rc; ++k) rc = h2d_rows(p + k * ny * Ty, y + k * y_dim_stride, ny, Ty, y_stride, st);
+    if (!rc && cudaStreamSynchronize(st) != cudaSuccess) { set_err("upload of the fitted set failed"); rc = 1; }
+    cudaStreamDestroy(st);
     if (rc) break;
   }
   if (rc) { wb_cuda_fit_free(f); return rc; }
@@ -1104,7 +1124,8 @@ int wb_cuda_fit(const double* y, int64_t ny, int64_t n_dims, int64_t Ty, int64_t
 void wb_cuda_fit_free(wb_fitted* f) {
   if (!f) return;
   for (size_t q = 0; q < f->ptr.size(); ++q) {
-    if (cudaSetDevice(f->devs[q]) == cudaSuccess) cudaFree(f->ptr[q]);
+    // every library call synchronises before it returns, so no work is pending on the set
+    if (cudaSetDevice(f->devs[q]) == cudaSuccess) { cudaFreeAsync(f->ptr[q], 0); }
   }
   delete f;
 }
