@@ -178,6 +178,8 @@ int main(int argc, char** argv) {
     V(8, 2, 8, 2) V(8, 4, 8, 2) V(8, 6, 8, 2) V(8, 2, 16, 1) V(6, 2, 8, 2) V(6, 2, 10, 2) V(4, 2, 12, 2)
   } else if (set == 2) {  // the other metrics, cfg2 shape
     GP(8, 4, 12, 1) GP(8, 4, 16, 1) GP(8, 2, 16, 1) GP(12, 4, 12, 1) GP(12, 6, 12, 1) GP(8, 6, 12, 1)
+  } else if (set == 7) {  // more (W, NR, warps) points for the non-dtw metrics
+    GP(10, 6, 14, 1) GP(10, 4, 14, 1) GP(8, 6, 16, 1) GP(10, 6, 12, 1) GP(12, 4, 14, 1) GP(6, 6, 20, 1)
   } else if (set == 4) {  // fp32 mode, dtw (tall bands: global buffers; also shared memory, which now fits more warps)
     FG(12, 6, 12, 1) FG(12, 4, 16, 1) FG(16, 4, 16, 1) FG(16, 6, 16, 1) FG(16, 8, 16, 1) FG(24, 4, 12, 1) FG(24, 6, 12, 1) FG(16, 4, 24, 1) FG(16, 4, 12, 2) FG(32, 4, 8, 1) FG(20, 6, 16, 1)
     FV(16, 4, 12, 1) FV(16, 6, 12, 1) FV(24, 4, 12, 1) FV(12, 6, 12, 1)
@@ -187,6 +189,7 @@ int main(int argc, char** argv) {
     FO(12, 6, 12, 1) FO(16, 4, 16, 1) FO(16, 6, 16, 1) FO(24, 4, 12, 1) FO(8, 4, 16, 1)
   } else {  // long series (cfg5 shape): msm / twe
     GL(16, 4, 8, 1) GL(12, 4, 8, 1) GL(12, 4, 12, 1) GL(8, 4, 12, 1) GL(8, 4, 16, 1) GL(8, 2, 16, 1) GL(12, 6, 12, 1) GL(8, 4, 8, 2)
+    GL(10, 4, 14, 1) GL(10, 6, 14, 1) GL(8, 6, 16, 1) GL(12, 4, 14, 1)
   }
   printf("done\n");
   return 0;

@@ -114,13 +114,19 @@ WB_HD typename M::real strip_pair(const Geom& g, const M& m, const typename M::r
     F* const rbase = bnd - (long long)B_in * bs;   // rbase[i * bs] = read slot of row i
     F* const wbase = bnd - (long long)B_out * bs;  // wbase[i * bs] = write slot of row i
 
+    // y[j-1] of column c is the y[j] of column c-1 (one register, and the metrics' |x[i-1] - y[j-1]| terms become
+    // common subexpressions of the neighbouring cell's |x[i] - y[j]|); columns clipped by the matrix border repeat
+    // y[Ty-1] -- their cells are never used
     typename M::Col cols[W];
+    {
+      F yprev = (j0 > 0) ? y[j0 - 1] : F(0);
 #pragma unroll
-    for (int c = 0; c < W; ++c) {
-      int jj = imin2(j0 + c, Ty - 1);
-      F yj = y[jj];
-      F yjm = (jj > 0) ? y[jj - 1] : F(0);
-      cols[c] = m.col(jj, yj, yjm);
+      for (int c = 0; c < W; ++c) {
+        const int jj = imin2(j0 + c, Ty - 1);
+        const F yj = y[jj];
+        cols[c] = m.col(jj, yj, yprev);
+        yprev = yj;
+      }
     }
     F prev[W];
 #pragma unroll

@@ -147,10 +147,12 @@ static bool l2_persist_window(cudaStream_t st, void* base, size_t bytes) {
 //                           in L2; more warps hide the extra latency).
 // Shared-memory buffers would cap cfg3 at 6-7 warps per SM (33 KB per warp); the global buffers
 // lift that to 12-16 and are what makes T = 4096 bands (110 KB per warp) run at all.
-template <class M> struct StripCfg { static constexpr int WL = 12, NRL = 6, NWL = 12; };
-template <> struct StripCfg<DtwPolicy<false, false>> { static constexpr int WL = 10, NRL = 6, NWL = 14; };
-template <> struct StripCfg<TwePolicy> { static constexpr int WL = 12, NRL = 4, NWL = 12; };
-template <> struct StripCfg<MsmPolicy> { static constexpr int WL = 8, NRL = 4, NWL = 16; };
+// (W, NR, warps) per policy from the sweep of profiles/r01h_variants_metrics.md: W = 10, NR = 6 everywhere; 14 warps at
+// 128 registers, or 12 warps at 168 registers for the cells that need the registers (twe, msm, edr).
+template <class M> struct StripCfg { static constexpr int WL = 10, NRL = 6, NWL = 14; };
+template <> struct StripCfg<TwePolicy> { static constexpr int WL = 10, NRL = 6, NWL = 12; };
+template <> struct StripCfg<MsmPolicy> { static constexpr int WL = 10, NRL = 6, NWL = 12; };
+template <> struct StripCfg<EdrPolicy> { static constexpr int WL = 10, NRL = 6, NWL = 12; };
 
 template <class M, int W, int NT, int MINB, bool EA, int NR, bool GRING>
 static int launch_strip_cfg(Workspace& ws, KArgsT<typename M::real> a, const M& m, int nwarps, int sms, size_t smem_cap, wb_stats* cfg) {
