@@ -74,7 +74,7 @@ static Result run_variant(const char* pname, int ops, const M& m, const void* dx
   KArgsT<F> a; memset(&a, 0, sizeof a);
   a.x = dx; a.y = dy; a.nx = nx; a.ny = ny; a.Tx = T; a.Ty = T; a.g = make_geom(T, T, R);
   a.NS = strip_ring_slots(a.g, W); a.out = dout; a.ld = ny; a.counter = counter; a.mode = PM_PAIRWISE;
-  a.nyb = (ny + 31) / 32; a.ntasks = nx * a.nyb;
+  a.nyb = (ny + 31) / 32; a.ntasks = nx * a.nyb; a.ys = T;
   size_t smem = GRING ? 0 : (size_t)NWARPS * a.NS * 32 * sizeof(F);
   auto kern = k_strip<M, W, NWARPS * 32, MINB, false, NR, GRING>;
   Result r{0, 0, 0};

@@ -166,6 +166,23 @@ int wb_cuda_dba_epoch(const wb_fitted *fit, int metric, const wb_params *params,
                       const int64_t *member_offsets, const int64_t *members, const double *sample_weight,
                       const double *weights, int do_update, double *means_out, double *dist_out, wb_stats *stats);
 
+/* Subsequence search for the DTW family: for every subsequence k (s[s_offsets[k] .. s_offsets[k+1]),
+ * length m_k <= T) and sample i, the minimum over the sliding windows w = 0 .. T - m_k of
+ * metric(subsequence, x[i][w : w + m_k]) and the FIRST window that attains it.  Replaces
+ * `_pairwise_subsequence_distance` / `_paired_subsequence_distance` (_cdistance.pyx:1018-1062) over
+ * Dtw / WeightedDtw / AmercingDtw / DerivativeDtw / WeightedDerivativeDtw SubsequenceMetric (_elastic.pyx:2206-2615,
+ * dtw_subsequence_distance :622-660, adtw :701-740, ddtw :780-815): band from the subsequence length
+ * (_compute_r(m_k, r)), comparison in the squared-cost domain, sqrt of the minimum; wdtw / wddtw weights span the
+ * SERIES length (T, T - 2).  The reference abandons windows early against the running minimum, which never changes
+ * the result for these metrics; the device evaluates every window (all windows of all samples are the `y` operand of
+ * ONE pairwise launch per subsequence, addressed with stride 1).
+ * paired == 0: out_dist / out_idx are (nx, n_s); paired != 0 (n_s == nx): subsequence i against sample i, (nx). */
+int wb_cuda_subsequence(int metric, const wb_params *params,
+                        const double *s, const int64_t *s_offsets, int64_t n_s,
+                        const double *x, int64_t nx, int64_t T, int64_t x_stride,
+                        int paired, double *out_dist, int64_t *out_idx,
+                        const int *devices, int n_devices, wb_stats *stats);
+
 /* Device-resident variant of wb_cuda_pairwise: d_x (nx, Tx), d_y (ny, Ty), d_out (nx, ny) are
  * dense row-major DEVICE arrays on the current device.  Enqueues on `stream`; fills `stats`
  * (after synchronising the stream) when stats != NULL. */

@@ -736,3 +736,51 @@ void orc_dtw_path(const double *D, int64_t xl, int64_t yl, int32_t *lo, int32_t 
   if (0 < lo[0]) lo[0] = 0;
   if (0 > hi[0]) hi[0] = 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * subsequence search, DTW family (test infrastructure).
+ * dtw_subsequence_distance EL:622-660, adtw_subsequence_distance EL:701-740, ddtw_subsequence_distance EL:780-815,
+ * with the per-class conventions of EL:2206-2615: r = _compute_r(s_len, r) from the ORIGINAL subsequence length;
+ * wdtw weights over n_timestep (EL:2370-2372), wddtw over n_timestep - 2 (EL:2540-2543); early abandoning against
+ * the running minimum, strict `<` (first best window).  Returns sqrt(min) and the window start in *index
+ * (left untouched -- as in the reference -- when nothing is accepted or ddtw sees s_len < 3).
+ * ------------------------------------------------------------------------------------------ */
+double orc_subsequence_distance(int metric, const orc_params *p, const double *S, int64_t s_len, const double *T,
+                                int64_t t_len, int64_t *index) {
+  const int deriv = (metric == ORC_DDTW || metric == ORC_WDDTW);
+  const int64_t r = orc_compute_r(s_len, p->r);
+  double *cost = (double *)malloc(sizeof(double) * (size_t)(t_len + 1));
+  double *cost_prev = (double *)malloc(sizeof(double) * (size_t)(t_len + 1));
+  double *weights = NULL, *S_buffer = NULL, *T_buffer = NULL;
+  double min_dist = INFINITY, dist;
+  const int64_t length = t_len - s_len + 1;
+  if (metric == ORC_WDTW) {
+    weights = (double *)malloc(sizeof(double) * (size_t)t_len);
+    orc_weights(p->g, t_len, weights);
+  } else if (metric == ORC_WDDTW) {
+    weights = (double *)malloc(sizeof(double) * (size_t)t_len);
+    if (t_len - 2 > 0) orc_weights(p->g, t_len - 2, weights);
+  }
+  if (deriv) {
+    if (s_len < 3) { free(cost); free(cost_prev); free(weights); return 0; }
+    S_buffer = (double *)malloc(sizeof(double) * (size_t)t_len);
+    T_buffer = (double *)malloc(sizeof(double) * (size_t)t_len);
+    orc_average_slope(S, s_len, S_buffer);
+  }
+  for (int64_t i = 0; i < length; i++) {
+    if (deriv) {
+      orc_average_slope(T + i, s_len, T_buffer);
+      dist = dtw_distance(S_buffer, s_len - 2, T_buffer, s_len - 2, r, cost, cost_prev, weights, min_dist);
+    } else if (metric == ORC_ADTW) {
+      dist = adtw_distance(S, s_len, T + i, s_len, r, cost, cost_prev, p->p, min_dist);
+    } else {
+      dist = dtw_distance(S, s_len, T + i, s_len, r, cost, cost_prev, weights, min_dist);
+    }
+    if (dist < min_dist) {
+      if (index) *index = i;
+      min_dist = dist;
+    }
+  }
+  free(cost); free(cost_prev); free(weights); free(S_buffer); free(T_buffer);
+  return sqrt(min_dist);
+}

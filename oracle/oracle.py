@@ -274,3 +274,26 @@ def dtw_average_mm(X, r=1.0, g=None, init=None, sample_weight=None, tol=1e-5, ma
         if abs(prev_cost - cost) < tol:
             break
     return mean, cost
+
+
+# ---------------------------------------------------------------------------------------------
+# subsequence search, DTW family (reference: _distance.py:543-729, _elastic.pyx:622-815, 2206-2615)
+# ---------------------------------------------------------------------------------------------
+def pairwise_subsequence(metric, subsequences, x, **params):
+    """(dist, idx) of shape (n_samples, n_subsequences): minimum over the sliding windows, first best window."""
+    L = lib()
+    L.orc_subsequence_distance.argtypes = [C.c_int, C.POINTER(Params), C.POINTER(C.c_double), C.c_int64,
+                                           C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_int64)]
+    L.orc_subsequence_distance.restype = C.c_double
+    x = _arr(x)
+    p = make_params(metric, **params)
+    dist = np.empty((x.shape[0], len(subsequences)))
+    idx = np.zeros((x.shape[0], len(subsequences)), dtype=np.int64)
+    for k, s in enumerate(subsequences):
+        s = np.ascontiguousarray(s, dtype=np.float64)
+        for i in range(x.shape[0]):
+            j = C.c_int64(0)
+            dist[i, k] = L.orc_subsequence_distance(METRIC_IDS[metric], C.byref(p), _dp(s), s.shape[0], _dp(x[i]), x.shape[1],
+                                                    C.byref(j))
+            idx[i, k] = j.value
+    return dist, idx

@@ -5,6 +5,7 @@
 Writes tests/golden/next_golden.npz:
   nd|...   multivariate pairwise / self / paired with dim="mean" / "full" (_distance.py:1245-1297, 1163-1169)
   al|... dba|... km|...  dtw_alignment / dtw_mapping / dtw_average (distance/dtw.py:246-690), KMeans(metric="dtw")
+  ss|...   pairwise / paired_subsequence_distance, DTW family (_distance.py:543-729)
   nb|...   KNeighborsClassifier.predict_proba / predict and NearestNeighbors.kneighbors (distance/_neighbors.py:19-300)
 """
 import os
@@ -107,6 +108,29 @@ def alignments(wd, out):
         out[f"km|{name}|transform"] = km.transform(Xk[::5])
 
 
+SS_CASES = [("dtw", {"r": 0.1}), ("dtw", {"r": 1.0}), ("wdtw", {"r": 0.3, "g": 0.1}), ("adtw", {"r": 0.2, "p": 0.5}),
+            ("ddtw", {"r": 0.2}), ("wddtw", {"r": 0.5, "g": 0.2})]
+SS_LENGTHS = (12, 30, 5, 3, 80, 1, 2)
+
+
+def subsequences(wd, out):
+    """pairwise / paired_subsequence_distance of the reference for the DTW-family subsequence metrics."""
+    rng = np.random.default_rng(20261021)
+    X = np.cumsum(rng.standard_normal((9, 80)), axis=1)
+    subs = [np.cumsum(rng.standard_normal(m)) for m in SS_LENGTHS]
+    out["ss|X"] = X
+    for k, s in enumerate(subs):
+        out[f"ss|s{k}"] = s
+    for ci, (metric, mp) in enumerate(SS_CASES):
+        keep = [k for k, s in enumerate(subs) if not (metric in ("ddtw", "wddtw") and len(s) < 3)]  # index unspecified there
+        ss = [subs[k] for k in keep]
+        d, i = wd.pairwise_subsequence_distance(ss, X, metric=metric, metric_params=mp, return_index=True)
+        out[f"ss|{ci}|keep"], out[f"ss|{ci}|dist"], out[f"ss|{ci}|idx"] = np.array(keep), d, i.astype(np.int64)
+        paired = [subs[keep[q % len(keep)]] for q in range(X.shape[0])]
+        d, i = wd.paired_subsequence_distance(paired, X, metric=metric, metric_params=mp, return_index=True)
+        out[f"ss|{ci}|paired_dist"], out[f"ss|{ci}|paired_idx"] = d, i.astype(np.int64)
+
+
 def main():
     wd = ref.load()
     if wd is None:
@@ -115,6 +139,7 @@ def main():
     multivariate(wd, out)
     neighbors(wd, out)
     alignments(wd, out)
+    subsequences(wd, out)
     path = os.path.join(HERE, "next_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")

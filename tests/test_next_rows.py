@@ -314,3 +314,84 @@ def test_kmeans_matches_reference_golden(W, next_golden):
         assert km.inertia_ == g[f"km|{name}|inertia"] and km.n_iter_ == g[f"km|{name}|n_iter"], name
         assert np.array_equal(km.transform(Xk[::5]), g[f"km|{name}|transform"]), name
         assert np.array_equal(km.predict(Xk[::5]), g[f"km|{name}|transform"].argmin(axis=1)), name
+
+
+# ---------------------------------------------------------------------------------------------
+# subsequence search, DTW family
+# ---------------------------------------------------------------------------------------------
+SS_CASES = [("dtw", {"r": 0.1}), ("dtw", {"r": 1.0}), ("wdtw", {"r": 0.3, "g": 0.1}), ("adtw", {"r": 0.2, "p": 0.5}),
+            ("ddtw", {"r": 0.2}), ("wddtw", {"r": 0.5, "g": 0.2})]
+
+
+def _ss_inputs(g, ci):
+    keep = g[f"ss|{ci}|keep"]
+    return g["ss|X"], [g[f"ss|s{k}"] for k in keep]
+
+
+def test_oracle_subsequence_matches_reference_golden(oracle, next_golden):
+    g = next_golden
+    for ci, (metric, mp) in enumerate(SS_CASES):
+        X, ss = _ss_inputs(g, ci)
+        d, i = oracle.pairwise_subsequence(metric, ss, X, **mp)
+        assert np.array_equal(d, g[f"ss|{ci}|dist"]) and np.array_equal(i, g[f"ss|{ci}|idx"]), (metric, mp)
+
+
+def test_subsequence_host_logic(wb):
+    x = np.zeros((3, 10))
+    with pytest.raises(ValueError, match="cannot be empty"):
+        wb.pairwise_subsequence_distance([], x, metric="dtw")
+    with pytest.raises(ValueError, match="Invalid subsequnce shape"):
+        wb.pairwise_subsequence_distance([np.zeros(11)], x, metric="dtw")
+    with pytest.raises(ValueError, match="unsupported metric"):
+        wb.pairwise_subsequence_distance([np.zeros(4)], x, metric="euclidean")
+    with pytest.raises(ValueError, match="scaled"):
+        wb.pairwise_subsequence_distance([np.zeros(4)], x, metric="dtw", scale=True)
+    with pytest.raises(ValueError, match="must be the same"):
+        wb.paired_subsequence_distance([np.zeros(4)], x, metric="dtw")
+    with pytest.raises(ValueError, match="dim must be"):
+        wb.pairwise_subsequence_distance([np.zeros(4)], x, dim=1, metric="dtw")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ci", range(len(SS_CASES)))
+def test_subsequence_matches_reference_golden(W, next_golden, ci):
+    g = next_golden
+    metric, mp = SS_CASES[ci]
+    X, ss = _ss_inputs(g, ci)
+    d, i = W.pairwise_subsequence_distance(ss, X, metric=metric, metric_params=mp, return_index=True)
+    assert np.array_equal(d, g[f"ss|{ci}|dist"]) and np.array_equal(i, g[f"ss|{ci}|idx"])
+    assert np.array_equal(W.pairwise_subsequence_distance(ss, X, metric=metric, metric_params=mp), g[f"ss|{ci}|dist"])
+    paired = [ss[q % len(ss)] for q in range(X.shape[0])]
+    d, i = W.paired_subsequence_distance(paired, X, metric=metric, metric_params=mp, return_index=True)
+    assert np.array_equal(d, g[f"ss|{ci}|paired_dist"]) and np.array_equal(i, g[f"ss|{ci}|paired_idx"])
+    # return shapes (_format_return): one subsequence -> (n_samples,), 1-D x -> (n_subsequences,), both -> scalar
+    assert W.pairwise_subsequence_distance(ss[0], X, metric=metric, metric_params=mp).shape == (X.shape[0],)
+    assert W.pairwise_subsequence_distance(ss, X[0], metric=metric, metric_params=mp).shape == (len(ss),)
+    assert isinstance(W.pairwise_subsequence_distance(ss[0], X[0], metric=metric, metric_params=mp), float)
+
+
+@pytest.mark.gpu
+def test_subsequence_larger_matches_oracle(W, oracle):
+    """Longer series (strip engine, several warp tasks per sample), ties (repeated motif -> first window wins),
+    3-D input with dim, two devices if present."""
+    rng = np.random.default_rng(9)
+    X = np.cumsum(rng.standard_normal((40, 600)), axis=1)
+    motif = X[3, 100:164].copy()
+    X[3, 300:364] = motif                                    # the same window twice: index 100 must win
+    subs = [motif, X[7, 500:600].copy(), np.cumsum(rng.standard_normal(200))]
+    for metric, mp in (("dtw", {"r": 0.1}), ("wdtw", {"r": 0.2, "g": 0.05}), ("ddtw", {"r": 0.1}), ("adtw", {"r": 0.05, "p": 2.0})):
+        d, i = W.pairwise_subsequence_distance(subs, X, metric=metric, metric_params=mp, return_index=True)
+        od, oi = oracle.pairwise_subsequence(metric, subs, X, **mp)
+        assert np.array_equal(d, od) and np.array_equal(i, oi), metric
+    d, i = W.pairwise_subsequence_distance(subs, X, metric="dtw", metric_params={"r": 0.1}, return_index=True)
+    assert d[3, 0] == 0.0 and i[3, 0] == 100 and d[7, 1] == 0.0 and i[7, 1] == 500
+    X3 = np.stack([X, X[::-1]], axis=1)
+    d1 = W.pairwise_subsequence_distance(subs, X3, dim=1, metric="dtw", metric_params={"r": 0.1})
+    assert np.array_equal(d1, d[::-1])
+    if W.device_count() >= 2:
+        W.set_devices([0, 1])
+        try:
+            d2, i2 = W.pairwise_subsequence_distance(subs, X, metric="dtw", metric_params={"r": 0.1}, return_index=True)
+        finally:
+            W.set_devices([0])
+        assert np.array_equal(d2, d) and np.array_equal(i2, i)

@@ -14,9 +14,11 @@ from .distance import (  # noqa: F401
     paired_distance,
     pairwise_distance,
 )
+from .subsequence import paired_subsequence_distance, pairwise_subsequence_distance  # noqa: F401
 from ._shim import device_count, get_precision, last_stats, library_path, set_devices, set_precision  # noqa: F401
 
 __all__ = [
     "pairwise_distance", "paired_distance", "argmin_distance", "check_metric",
+    "pairwise_subsequence_distance", "paired_subsequence_distance",
     "device_count", "set_devices", "set_precision", "get_precision", "last_stats", "library_path",
 ]

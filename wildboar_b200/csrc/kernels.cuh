@@ -47,6 +47,7 @@ struct KArgsT {
   // the last one divides by the number of dimensions
   int acc;            // 1: out = out + d
   double div;         // != 0: out = (...) / div
+  long long ys;       // elements between consecutive y series (Ty for dense rows; 1 = every sliding window of one long buffer)
 };
 using KArgs = KArgsT<double>;
 
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(NT, MINB) k_strip(KArgsT<typename M::real> a, 
     pc.sy = a.sy ? a.sy[j] : 0.0;
     mm.begin_pair(pc);
     const F ab = EA ? (F)a.thr[i] : Num<F>::inf();
-    const double d = (double)strip_pair<M, W, EA, NR, 32>(a.g, mm, a.x + i * a.Tx, a.y + j * a.Ty, bnd, 32, ab);
+    const double d = (double)strip_pair<M, W, EA, NR, 32>(a.g, mm, a.x + i * a.Tx, a.y + j * a.ys, bnd, 32, ab);
     if (valid) {
       // results are written once and never re-read by the kernel: streaming stores keep them from
       // displacing the boundary buffers / y tiles in L2
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(NT) k_rowscan(KArgsT<typename M::real> a, M m)
     mm.begin_pair(pc);
     const F md = a.thr ? (F)a.thr[i] : Num<F>::inf();
     F mmax = F(0);
-    const double d = (double)rowscan_pair<M>(a.g, mm, a.x + i * a.Tx, a.y + j * a.Ty, b0, b1, a.sstride, md, &mmax);
+    const double d = (double)rowscan_pair<M>(a.g, mm, a.x + i * a.Tx, a.y + j * a.ys, b0, b1, a.sstride, md, &mmax);
     if (valid) {
       double* const po = result_ptr(a, t, lane, i, j);
       const double r = combine_dims(a, po, d);
@@ -221,6 +222,35 @@ __global__ void k_series_stat(const double* __restrict__ x, long long n, int T, 
     const double mean = ex / (double)T;
     ex2 = ex2 / (double)T - mean * mean;
     out[s] = ex2 > 1e-13 ? sqrt(ex2) : 0.0;
+  }
+}
+
+// ---- subsequence search: first minimum over the windows of every sample (EL:622-660: `dist < min_dist`, strict) ----
+// raw: DP values of ALL windows of the flat (n, T) buffer, window w of sample i at raw[i * T + w]; only w < nw are
+// windows of sample i (the rest straddle two samples).  One warp per sample.
+__global__ void __launch_bounds__(128) k_window_min(const double* __restrict__ raw, long long n, int T, int nw,
+                                                    double* __restrict__ out_dist, long long* __restrict__ out_idx,
+                                                    long long ld, int apply_sqrt) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const double* p = raw + i * T;
+  double best = WB_INF;
+  int bidx = 0x7fffffff;
+  for (int w = lane; w < nw; w += 32) {
+    const double v = p[w];
+    if (v < best) { best = v; bidx = w; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    if (ov < best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+  }
+  if (lane == 0) {
+    // every window +inf (cannot happen for finite input): the reference leaves the index untouched; report 0
+    out_dist[i * ld] = apply_sqrt ? sqrt(best) : best;
+    out_idx[i * ld] = bidx == 0x7fffffff ? 0 : bidx;
   }
 }
 

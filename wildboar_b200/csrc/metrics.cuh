@@ -84,6 +84,8 @@ struct Geom {
   int max_len;  // max(0, Ty-Tx) + R
   int a;        // min_len + R - 1, min_len = max(0, Tx-Ty): row i starts at max(0, i - a)
   int H;        // band height of a column: a + max_len
+  int raw;      // 1: DTW-family policies return the squared-cost DP value without the final sqrt (subsequence search
+                //    compares in that domain, EL:622-660)
 };
 
 WB_HD Geom make_geom(int Tx, int Ty, int R) {
@@ -92,6 +94,7 @@ WB_HD Geom make_geom(int Tx, int Ty, int R) {
   g.max_len = imax2(0, Ty - Tx) + R;
   g.a = imax2(0, Tx - Ty) + R - 1;
   g.H = g.a + g.max_len;
+  g.raw = 0;
   return g;
 }
 
@@ -146,7 +149,7 @@ struct DtwPolicy {
     if (WEIGHTED) cost = cost * d.w;
     return dmin2(dmin2(up, left), diag) + cost;
   }
-  WB_HD F finish(F d, const Geom&) const { return sqrt(d); }
+  WB_HD F finish(F d, const Geom& g) const { return g.raw ? d : sqrt(d); }
 };
 
 // ------------------------------------------------------------------------------------------

@@ -149,10 +149,11 @@ static bool l2_persist_window(cudaStream_t st, void* base, size_t bytes) {
 // lift that to 12-16 and are what makes T = 4096 bands (110 KB per warp) run at all.
 // (W, NR, warps) per policy from the sweep of profiles/r01h_variants_metrics.md: W = 10, NR = 6 everywhere; 14 warps at
 // 128 registers, or 12 warps at 168 registers for the cells that need the registers (twe, msm, edr).
-template <class M> struct StripCfg { static constexpr int WL = 10, NRL = 6, NWL = 14; };
-template <> struct StripCfg<TwePolicy> { static constexpr int WL = 10, NRL = 6, NWL = 12; };
-template <> struct StripCfg<MsmPolicy> { static constexpr int WL = 10, NRL = 6, NWL = 12; };
-template <> struct StripCfg<EdrPolicy> { static constexpr int WL = 10, NRL = 6, NWL = 12; };
+// TALL bands (T = 4096 sweep, profiles/r01h_variants_cfg5_filled.log): twe W = 12, NR = 6, 12 warps; msm W = 8, NR = 4, 12 warps.
+template <class M> struct StripCfg { static constexpr int WL = 10, NRL = 6, NWL = 14, WT = 8, NRT = 4, NWT = 16; };
+template <> struct StripCfg<TwePolicy> { static constexpr int WL = 10, NRL = 6, NWL = 12, WT = 12, NRT = 6, NWT = 12; };
+template <> struct StripCfg<MsmPolicy> { static constexpr int WL = 10, NRL = 6, NWL = 12, WT = 8, NRT = 4, NWT = 12; };
+template <> struct StripCfg<EdrPolicy> { static constexpr int WL = 10, NRL = 6, NWL = 12, WT = 8, NRT = 4, NWT = 16; };
 
 template <class M, int W, int NT, int MINB, bool EA, int NR, bool GRING>
 static int launch_strip_cfg(Workspace& ws, KArgsT<typename M::real> a, const M& m, int nwarps, int sms, size_t smem_cap, wb_stats* cfg) {
@@ -213,7 +214,7 @@ static int launch_strip(Workspace& ws, const KArgsT<typename M::real>& a, const 
     if (fits_l2 && a.g.H >= 2 * C::WL)
       return launch_strip_cfg<M, C::WL, C::NWL * 32, 1, EA, C::NRL, true>(ws, a, m, std::min(C::NWL, cap), sms, smem_cap, cfg);
     if (!fits_l2)
-      return launch_strip_cfg<M, 8, 512, 1, EA, 4, true>(ws, a, m, std::min(16, cap), sms, smem_cap, cfg);
+      return launch_strip_cfg<M, C::WT, C::NWT * 32, 1, EA, C::NRT, true>(ws, a, m, std::min(C::NWT, cap), sms, smem_cap, cfg);
     return launch_strip_cfg<M, 8, 256, 2, EA, 2, true>(ws, a, m, std::min(8, cap), sms, smem_cap, cfg);
   }
   if (a.g.H >= 16 || a.g.H < 8) return launch_strip_cfg<M, 8, 256, 2, EA, 2, false>(ws, a, m, 8, sms, smem_cap, cfg);
@@ -247,6 +248,8 @@ struct DpCall {
   bool degenerate;     // ddtw with min(T) < 3: every distance is 0 (EL:3270)
   // multivariate dim="mean": accumulate into / scale the stored value (kernels.cuh, combine_dims)
   int acc; double div;
+  // subsequence search: y series start every `ys` elements (0: dense rows), raw = no final sqrt
+  long long ys; int raw;
 };
 
 // Slope transforms, per-series scalars and lookup tables for one (x, y) operand pair.
@@ -341,10 +344,13 @@ static int launch_dp_t(Workspace& ws, const DeviceInfo& di, const DpCall& c, lon
   constexpr bool kF32 = sizeof(F) == 4;
   KArgsT<F> a;
   memset(&a, 0, sizeof a);
-  if constexpr (kF32) { a.x = c.pxf + r0 * c.ptx; a.y = c.pyf + c0 * c.pty; }
-  else { a.x = c.px + r0 * c.ptx; a.y = c.py + c0 * c.pty; }
+  const long long ystep = c.ys > 0 ? c.ys : c.pty;
+  if constexpr (kF32) { a.x = c.pxf + r0 * c.ptx; a.y = c.pyf + c0 * ystep; }
+  else { a.x = c.px + r0 * c.ptx; a.y = c.py + c0 * ystep; }
   a.nx = nrows; a.ny = ncols; a.Tx = c.ptx; a.Ty = c.pty;
   a.g = make_geom(c.ptx, c.pty, c.R);
+  a.g.raw = c.raw;
+  a.ys = c.ys > 0 ? c.ys : c.pty;
   a.sx = c.sx ? c.sx + r0 : nullptr; a.sy = c.sy ? c.sy + c0 : nullptr;
   a.out = out; a.ld = ld; a.out_m = out_m; a.thr = thr;
   a.mode = c.mode; a.row0 = c.row0 + r0 - c0; a.mirror = c.mirror;
@@ -981,6 +987,151 @@ static int run_dba_epoch(const wb_fitted* fit, int metric, const wb_params& prm,
   return rc;
 }
 
+// ------------------------------------------------------------------------------------------
+// Subsequence search, DTW family: min over the sliding windows of every sample.
+// ------------------------------------------------------------------------------------------
+struct SubseqJob {
+  int metric; wb_params p;
+  const double* s; const int64_t* soff; int64_t ns;   // subsequences, concatenated
+  const double* x; int64_t nx, T, xs;
+  int paired;
+  double* out_dist; int64_t* out_idx;                  // (nx, ns) or, paired, (nx)
+};
+
+// samples [lo, hi) on device `dev`
+static int subseq_worker(const SubseqJob& J, int dev, int64_t lo, int64_t hi, wb_stats* st_out) {
+  DeviceInfo di; cudaStream_t st;
+  if (begin_single_device(dev, &di, &st)) return 1;
+  int rc = 0;
+  wb_stats stats; memset(&stats, 0, sizeof stats);
+  {
+    Workspace ws(st);
+    Timer total(st), kt(st);
+    total.start();
+    const int64_t rows = hi - lo;
+    const bool deriv = is_derivative(J.metric);
+    const bool weighted = J.metric == M_WDTW || J.metric == M_WDDTW;
+    const int64_t Tp = deriv ? J.T - 2 : J.T;  // length of the (prepared) samples
+    do {
+      double *dx = nullptr, *dxp = nullptr, *ds = nullptr, *draw = nullptr, *ddist = nullptr;
+      long long* didx = nullptr;
+      if ((rc = ws.alloc(&dx, (size_t)rows * J.T)) || (rc = h2d_rows(dx, J.x + lo * J.xs, rows, J.T, J.xs, st))) break;
+      dxp = dx;
+      if (deriv && Tp >= 1) {
+        // the derivative of a window is the window of the derivative (average_slope is local, EL:3220-3225)
+        if ((rc = ws.alloc(&dxp, (size_t)rows * Tp))) break;
+        k_slope<<<1024, 256, 0, st>>>(dx, rows, (int)J.T, dxp);
+        WB_CK(cudaGetLastError());
+      }
+      // subsequences (derivative metrics: their slopes), concatenated
+      const int64_t stot = J.soff[J.ns];
+      ws.host_keep.emplace_back((size_t)std::max<int64_t>(stot, 1));
+      std::vector<double>& hs = ws.host_keep.back();
+      std::vector<int64_t> poff((size_t)J.ns + 1, 0);  // offsets of the prepared subsequences
+      for (int64_t k = 0; k < J.ns; ++k) {
+        const int64_t m = J.soff[k + 1] - J.soff[k];
+        const int64_t mp = deriv ? std::max<int64_t>(m - 2, 0) : m;
+        if (deriv) { if (m >= 3) average_slope(J.s + J.soff[k], m, hs.data() + poff[(size_t)k]); }
+        else memcpy(hs.data() + poff[(size_t)k], J.s + J.soff[k], sizeof(double) * m);
+        poff[(size_t)k + 1] = poff[(size_t)k] + mp;
+      }
+      if ((rc = ws.alloc(&ds, hs.size()))) break;
+      WB_CK(cudaMemcpyAsync(ds, hs.data(), sizeof(double) * hs.size(), cudaMemcpyHostToDevice, st));
+      // weights: one table over the SERIES length (EL:2370-2372 wdtw: T; EL:2540-2543 wddtw: T - 2), libm exp
+      const double* dw = nullptr;
+      if (weighted) {
+        const int64_t wn = deriv ? J.T - 2 : J.T;
+        ws.host_keep.push_back(make_weights(J.p.g, wn));
+        std::vector<double>& h = ws.host_keep.back();
+        double* d = nullptr;
+        if ((rc = ws.alloc(&d, h.size()))) break;
+        WB_CK(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        dw = d + table_center(wn);
+      }
+      const int64_t nout = J.paired ? rows : rows * J.ns;
+      if ((rc = ws.alloc(&draw, (size_t)rows * std::max<int64_t>(Tp, 1))) || (rc = ws.alloc(&ddist, (size_t)nout)) ||
+          (rc = ws.alloc(&didx, (size_t)nout))) break;
+      WB_CK(cudaMemsetAsync(ddist, 0, sizeof(double) * nout, st));
+      WB_CK(cudaMemsetAsync(didx, 0, sizeof(long long) * nout, st));
+      kt.start();
+      // the DP policy on prepared data: ddtw -> dtw, wddtw -> wdtw
+      const int dp_metric = J.metric == M_DDTW ? M_DTW : (J.metric == M_WDDTW ? M_WDTW : J.metric);
+      for (int64_t k = 0; k < J.ns && !rc; ++k) {
+        const int64_t m = J.soff[k + 1] - J.soff[k];
+        const int64_t mp = poff[(size_t)k + 1] - poff[(size_t)k];
+        if (deriv && m < 3) continue;  // EL:793-794: distance 0 (index unspecified in the reference; 0 here)
+        const int64_t nw = Tp - mp + 1;  // windows per sample
+        // paired: subsequence k against sample k only; else against every sample of the block
+        const int64_t r0 = J.paired ? k - lo : 0, nr = J.paired ? 1 : rows;
+        if (J.paired && (k < lo || k >= hi)) continue;
+        DpCall c; memset(&c, 0, sizeof c);
+        c.metric = dp_metric; c.p = J.p; c.mode = PM_PAIRWISE;
+        c.px = ds + poff[(size_t)k]; c.nx = 1; c.ptx = (int)mp;
+        c.py = dxp + r0 * Tp; c.pty = (int)mp; c.ys = 1; c.ny = nr * Tp - mp + 1;
+        c.R = (int)compute_r(m, J.p.r);  // from the ORIGINAL subsequence length (EL:2253, 2480)
+        c.raw = 1;
+        c.tab.weights = dw;
+        if ((rc = launch_dp(ws, di, c, 0, 1, 0, c.ny, draw, c.ny, nullptr, nullptr, &stats))) break;
+        double* od = J.paired ? ddist + r0 : ddist + k;
+        long long* oi = J.paired ? didx + r0 : didx + k;
+        k_window_min<<<(unsigned)((nr * 32 + 127) / 128), 128, 0, st>>>(draw, nr, (int)Tp, (int)nw, od, oi, J.paired ? 1 : J.ns, 1);
+        WB_CK(cudaGetLastError());
+        stats.launches += 1;
+      }
+      if (rc) break;
+      kt.stop();
+      // gather: pairwise rows are contiguous (rows, ns); paired entries are contiguous (rows)
+      double* hd = J.paired ? J.out_dist + lo : J.out_dist + lo * J.ns;
+      int64_t* hi_ = J.paired ? J.out_idx + lo : J.out_idx + lo * J.ns;
+      if (cudaMemcpyAsync(hd, ddist, sizeof(double) * nout, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          cudaMemcpyAsync(hi_, didx, sizeof(long long) * nout, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          cudaStreamSynchronize(st) != cudaSuccess) { set_err("device-to-host copy of the subsequence distances failed"); rc = 1; break; }
+      stats.kernel_ms = kt.ms();
+    } while (0);
+    total.stop();
+    if (!rc) { cudaStreamSynchronize(st); stats.total_ms = total.ms(); }
+  }
+  cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  if (st_out) *st_out = stats;
+  return rc;
+}
+
+static int run_subsequence(const SubseqJob& J, const int* devices, int n_devices, wb_stats* stats) {
+  int ndev_avail = 0;
+  if (cudaGetDeviceCount(&ndev_avail) != cudaSuccess || ndev_avail < 1) {
+    set_err("no CUDA device available: wildboar_b200 has no CPU fallback");
+    return 1;
+  }
+  std::vector<int> devs;
+  if (devices && n_devices > 0) devs.assign(devices, devices + n_devices); else devs.push_back(0);
+  for (int d : devs) if (d < 0 || d >= ndev_avail) { set_err("invalid device ordinal"); return 1; }
+  const int G = (int)std::min<int64_t>((int64_t)devs.size(), std::max<int64_t>(J.nx, 1));
+  std::vector<int64_t> off;
+  row_blocks(J.nx, G, off);
+  std::vector<wb_stats> sts((size_t)G);
+  std::vector<int> rcs((size_t)G, 0);
+  std::vector<std::string> errs((size_t)G);
+  if (G == 1) { rcs[0] = subseq_worker(J, devs[0], off[0], off[1], &sts[0]); errs[0] = g_err; }
+  else {
+    std::vector<std::thread> th;
+    for (int b = 0; b < G; ++b)
+      th.emplace_back([&, b]() { rcs[(size_t)b] = subseq_worker(J, devs[(size_t)b], off[(size_t)b], off[(size_t)b + 1], &sts[(size_t)b]); errs[(size_t)b] = g_err; });
+    for (auto& t : th) t.join();
+  }
+  for (int b = 0; b < G; ++b) if (rcs[(size_t)b]) { set_err(errs[(size_t)b]); return rcs[(size_t)b]; }
+  if (stats) {
+    memset(stats, 0, sizeof *stats);
+    for (int b = 0; b < G; ++b) {
+      stats->kernel_ms = std::max(stats->kernel_ms, sts[(size_t)b].kernel_ms);
+      stats->total_ms = std::max(stats->total_ms, sts[(size_t)b].total_ms);
+      stats->cells += sts[(size_t)b].cells; stats->pairs += sts[(size_t)b].pairs; stats->launches += sts[(size_t)b].launches;
+      stats->engine = std::max(stats->engine, sts[(size_t)b].engine);
+    }
+  }
+  return 0;
+}
+
 static int check_common(int metric, const wb_params* p, const void* x, int64_t n, int64_t T) {
   if (!p || !x) { set_err("null argument"); return 1; }
   if (metric < 0 || metric >= M_COUNT) { set_err("unknown metric id"); return 1; }
@@ -1186,6 +1337,25 @@ int wb_cuda_dba_epoch(const wb_fitted* fit, int metric, const wb_params* params,
   if (metric == M_WDTW && do_update && !weights) { set_err("wdtw alignment needs the weight vector"); return 1; }
   return run_dba_epoch(fit, metric, *params, means_in, K, Tm, member_offsets, members, sample_weight, weights, do_update,
                        means_out, dist_out, stats);
+}
+
+int wb_cuda_subsequence(int metric, const wb_params* params, const double* s, const int64_t* s_offsets, int64_t n_s,
+                        const double* x, int64_t nx, int64_t T, int64_t x_stride, int paired, double* out_dist,
+                        int64_t* out_idx, const int* devices, int n_devices, wb_stats* stats) {
+  if (check_common(metric, params, x, nx, T)) return 1;
+  if (!s || !s_offsets || !out_dist || !out_idx) { set_err("null argument"); return 1; }
+  if (!is_dtw_family(metric)) { set_err("subsequence search is implemented for the DTW family (dtw, wdtw, adtw, ddtw, wddtw)"); return 1; }
+  if (params->precision != 0) { set_err("subsequence search runs in fp64"); return 1; }
+  if (n_s < 1 || s_offsets[0] != 0) { set_err("empty input"); return 1; }
+  if (paired && n_s != nx) { set_err("paired subsequence search needs one subsequence per sample"); return 1; }
+  for (int64_t k = 0; k < n_s; ++k) {
+    const int64_t m = s_offsets[k + 1] - s_offsets[k];
+    if (m < 1 || m > T) { set_err("every subsequence needs 1 <= length <= n_timestep"); return 1; }
+  }
+  SubseqJob J;
+  J.metric = metric; J.p = *params; J.s = s; J.soff = s_offsets; J.ns = n_s; J.x = x; J.nx = nx; J.T = T; J.xs = x_stride;
+  J.paired = paired ? 1 : 0; J.out_dist = out_dist; J.out_idx = out_idx;
+  return run_subsequence(J, devices, n_devices, stats);
 }
 
 int wb_cuda_pairwise_dev(int metric, const wb_params* params, const double* d_x, int64_t nx, int64_t Tx,
