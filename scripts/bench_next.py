@@ -142,6 +142,26 @@ def main():
                    ref_bit_equal=bool(np.array_equal(rmean, omean) and rcost == ocost))
     emit(**row)
 
+    # ---- 8f-4: subsequence search (shapelet distances), DTW family ----
+    n, T, ns, m = (300, 256, 8, 48) if QUICK else (2000, 512, 64, 64)
+    Xs = rw(n, T, 8)
+    rng = np.random.default_rng(9)
+    shp = [Xs[rng.integers(0, n), o:o + m].copy() for o in rng.integers(0, T - m, ns)]
+    for metric, mp in (("dtw", {"r": 0.1}), ("wdtw", {"r": 0.1, "g": 0.05})):
+        t_ss, (d, i) = timed(lambda: wb.pairwise_subsequence_distance(shp, Xs, metric=metric, metric_params=mp, return_index=True))
+        st = wb.last_stats()
+        row = dict(row="8f-4 pairwise_subsequence_distance", metric=metric, shape=f"{ns} subsequences x {m} vs {n} samples x {T}, r={mp['r']}",
+                   windows=n * (T - m + 1) * ns, cells=st["cells"], e2e_ms=round(t_ss * 1e3, 1), kernel_ms=round(st["kernel_ms"], 1),
+                   kernel_gcups=round(st["cells"] / (st["kernel_ms"] * 1e-3) / 1e9, 1), launches=st["launches"])
+        if wd is not None:
+            nss, nxs = (4, 48) if QUICK else (8, 128)
+            t_ref, (rd_, ri_) = timed(lambda: wd.pairwise_subsequence_distance(shp[:nss], Xs[:nxs], metric=metric, metric_params=mp,
+                                                                             return_index=True, n_jobs=NCPU), reps=1)
+            row.update(ref_sample=f"{nss} subsequences vs {nxs} samples, n_jobs={NCPU} (early abandoning)", ref_ms=round(t_ref * 1e3, 1),
+                       ref_windows_per_s=round(nss * nxs * (T - m + 1) / t_ref), windows_per_s=round(n * (T - m + 1) * ns / t_ss),
+                       ref_cores=NCPU, ref_bit_equal=bool(np.array_equal(rd_, d[:nxs, :nss]) and np.array_equal(ri_, i[:nxs, :nss])))
+        emit(**row)
+
     # ---- 8f-1: KMeans(metric="dtw") ----
     n, T, K = (300, 128, 4) if QUICK else (2000, 256, 8)
     Xk = np.concatenate([rw(n // K, T, 10 + c) + 8.0 * c for c in range(K)])
