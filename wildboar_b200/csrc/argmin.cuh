@@ -145,28 +145,46 @@ __global__ void k_fill(double* p, long long n, double v) {
 // margin, so rounding in the O(T) sums can never drop a pair the exact scan would accept; it
 // therefore NEVER changes the result (the replay only ever sees "pruned" = +INF = rejected).
 // ------------------------------------------------------------------------------------------
-// lower/upper[k] = min/max t[k-w .. k+w] (clipped); rows = series (queries)
-__global__ void k_envelope_rows(const double* __restrict__ x, long long n, int T, int w,
-                                double* __restrict__ lo, double* __restrict__ hi) {
+// Time order of the lower-bound sums.  Summing the time steps in natural order makes the early exit wait for
+// the part of the series where the excess over the envelope happens to be (for random walks: the end).  The
+// cascade therefore visits time step perm[p] = (p * stride) mod T at position p, with stride ~ 0.618 T coprime
+// to T (a golden-ratio sequence: every prefix is spread evenly over the series), and all arrays it reads are
+// stored in that order.  Only the pruning decision depends on these sums (1e-9 safety margin), never a result.
+inline int lb_time_stride(int T) {
+  if (T <= 2) return 1;
+  int s = (int)(0.6180339887498949 * T);
+  if (s < 1) s = 1;
+  auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
+  while (s > 1 && gcd(s, T) != 1) --s;
+  return s;
+}
+
+// lower/upper[p] = min/max t[k-w .. k+w] (clipped) at k = perm[p]; rows = series (queries); xp = the series in
+// the same order
+__global__ void k_envelope_rows(const double* __restrict__ x, long long n, int T, int w, int stride,
+                                double* __restrict__ xp, double* __restrict__ lo, double* __restrict__ hi) {
   const long long total = n * (long long)T;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const long long s = e / T;
-    const int k = (int)(e - s * T);
+    const int pos = (int)(e - s * T);
+    const int k = (int)(((long long)pos * stride) % T);
     const double* p = x + s * T;
     const int a = max(0, k - w), b = min(T - 1, k + w);
     double l = p[a], h = p[a];
     for (int q = a + 1; q <= b; ++q) { const double v = p[q]; l = fmin(l, v); h = fmax(h, v); }
+    if (xp) xp[e] = p[k];
     lo[e] = l; hi[e] = h;
   }
 }
-// same, but written TRANSPOSED ([t][series]) together with the transposed series, so that a
+// same, but written TRANSPOSED ([position][series]) together with the transposed series, so that a
 // warp whose lanes are 32 consecutive references reads them coalesced
-__global__ void k_envelope_T(const double* __restrict__ y, long long n, int T, int w, double* __restrict__ yT,
+__global__ void k_envelope_T(const double* __restrict__ y, long long n, int T, int w, int stride, double* __restrict__ yT,
                              double* __restrict__ loT, double* __restrict__ hiT) {
   const long long total = n * (long long)T;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(e / n);
-    const long long s = e - (long long)k * n;
+    const int pos = (int)(e / n);
+    const long long s = e - (long long)pos * n;
+    const int k = (int)(((long long)pos * stride) % T);
     const double* p = y + s * T;
     const int a = max(0, k - w), b = min(T - 1, k + w);
     double l = p[a], h = p[a];
@@ -175,9 +193,57 @@ __global__ void k_envelope_T(const double* __restrict__ y, long long n, int T, i
   }
 }
 
+// Cascade operands, all fp32 and rounded OUTWARD so that every LB_Keogh term computed from them (with round-down
+// arithmetic) is a rigorous lower bound of the exact fp64 term for ANY data: a larger envelope and a value interval
+// [v_down, v_up] can only shrink the excess over the envelope.  fp32 because the prune kernel is instruction bound:
+// 2 FADD + FMNMX + FFMA per direction and time step instead of 7 FP64-pipe instructions + 4 selects.
+//   references: envT[pos][j] = (lower_down, upper_up), yvT[pos][j] = (y_down, y_up); y0 / yL: first / last sample (fp64, LB_Kim)
+//   queries   : qf[i][pos]   = (x_down, x_up, lower_down, upper_up)
+// pos = position in the permuted time order (time step (pos * stride) mod T).
+__global__ void k_envelope_casc(const double* __restrict__ y, long long n, int T, int w, int stride, float2* __restrict__ envT,
+                                float2* __restrict__ yvT, double* __restrict__ y0, double* __restrict__ yL) {
+  const long long total = n * (long long)T;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int pos = (int)(e / n);
+    const long long s = e - (long long)pos * n;
+    const int k = (int)(((long long)pos * stride) % T);
+    const double* p = y + s * T;
+    const int a = max(0, k - w), b = min(T - 1, k + w);
+    double l = p[a], h = p[a];
+    for (int q = a + 1; q <= b; ++q) { const double v = p[q]; l = fmin(l, v); h = fmax(h, v); }
+    envT[e] = make_float2(__double2float_rd(l), __double2float_ru(h));
+    yvT[e] = make_float2(__double2float_rd(p[k]), __double2float_ru(p[k]));
+    if (pos == 0) { y0[s] = p[0]; yL[s] = p[T - 1]; }
+  }
+}
+__global__ void k_query_casc(const double* __restrict__ x, long long n, int T, int w, int stride, float4* __restrict__ qf) {
+  const long long total = n * (long long)T;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long s = e / T;
+    const int pos = (int)(e - s * T);
+    const int k = (int)(((long long)pos * stride) % T);
+    const double* p = x + s * T;
+    const int a = max(0, k - w), b = min(T - 1, k + w);
+    double l = p[a], h = p[a];
+    for (int q = a + 1; q <= b; ++q) { const double v = p[q]; l = fmin(l, v); h = fmax(h, v); }
+    qf[e] = make_float4(__double2float_rd(p[k]), __double2float_ru(p[k]), __double2float_rd(l), __double2float_ru(h));
+  }
+}
+
+#ifndef WB_LB_STRAGGLERS
+#define WB_LB_STRAGGLERS 2
+#endif
+#ifndef WB_LB_STRAGGLER_AFTER
+#define WB_LB_STRAGGLER_AFTER 63
+#endif
+constexpr int kLbStragglers = WB_LB_STRAGGLERS, kLbStragglerAfter = WB_LB_STRAGGLER_AFTER;
+
 struct LbArgs {
-  const double* x; const double* lox; const double* hix;   // (nq, T) row-major
-  const double* yT; const double* loyT; const double* hiyT;  // (T, ny) transposed
+  const double* x;     // (nq, T) queries, natural order (LB_Kim reads the first / last sample)
+  const float4* qf;    // (nq, T) (x_down, x_up, lower_down, upper_up), permuted time order
+  const float2* envT;  // (T, ny) (lower_down, upper_up) of the references, rows in the same order
+  const float2* yvT;   // (T, ny) (y_down, y_up)
+  const double* y0; const double* yL;  // (ny) first / last sample of the references
   long long nq, ny, c0, nc; int T;
   const double* tau;  // per query, distance domain
   double* d; long long ld;  // chunk matrix: +INF = pruned, -1 = survivor (to be filled by the DP)
@@ -191,6 +257,7 @@ __global__ void __launch_bounds__(256) k_lb_prune(LbArgs a) {
   const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
   const int T = a.T;
+  unsigned long long c_kim = 0, c_keogh = 0;  // per-warp statistics (lane 0), one atomic per warp at the end
   for (long long t = wid; t < ntask; t += nw) {
     const long long i = t / nyb;
     const long long jl = (t - i * nyb) * 32 + lane;
@@ -202,42 +269,58 @@ __global__ void __launch_bounds__(256) k_lb_prune(LbArgs a) {
     bool pruned = false;
     if (!isinf(lim)) {
       // LB_Kim: every warping path contains (0,0) and (T-1,T-1)
-      const double d0 = q[0] - a.yT[j];
-      const double d1 = q[T - 1] - a.yT[(long long)(T - 1) * a.ny + j];
+      const double d0 = q[0] - a.y0[j];
+      const double d1 = q[T - 1] - a.yL[j];
       double lb = d0 * d0 + (T > 1 ? d1 * d1 : 0.0);
       pruned = lb > lim;
-      if (pruned && valid) atomicAdd(a.n_kim, 1ULL);
+      c_kim += __popc(__ballot_sync(0xffffffffu, pruned && valid));
+      bool p2 = pruned;
       if (!__all_sync(0xffffffffu, pruned)) {
-        // LB_Keogh, query against the reference's envelope
-        double s = 0.0;
-        const double* lo = a.loyT + j; const double* hi = a.hiyT + j;
-        for (int k = 0; k < T; ++k) {
-          const double v = q[k];
-          const double l = lo[(long long)k * a.ny], h = hi[(long long)k * a.ny];
-          const double e = v > h ? v - h : (v < l ? l - v : 0.0);
-          s += e * e;
-          if ((k & 31) == 31 && __all_sync(0xffffffffu, pruned || s > lim)) break;
+        // LB_Keogh in BOTH directions at once (time steps in the permuted order): s1 = query against the reference's
+        // envelope, s2 = reference against the query's envelope, in round-down fp32 on outward-rounded operands (rigorous
+        // lower bounds of the fp64 sums).  A lane is pruned as soon as EITHER sum exceeds the limit, so the warp leaves
+        // at max over lanes of min(k1, k2) instead of running direction 1 to the end for every lane that only direction
+        // 2 can prune (ncu: 4800 instructions per warp task before, 80 % of the warps ran all T steps of direction 1).
+        const float limf = __double2float_ru(lim);
+        float s1 = 0.0f, s2 = 0.0f;
+        const float2* env = a.envT + j;
+        const float2* yv = a.yvT + j;
+        const float4* qf = a.qf + i * T;
+        const long long ny = a.ny;
+        // one time step: excess of the query sample over the reference envelope (>= 0 parts of x - upper and lower - x)
+        // and of the reference sample over the query envelope
+        auto step = [&](const float2 lh, const float2 yy, const float4 qq) {
+          const float e1 = fmaxf(fmaxf(__fsub_rd(qq.x, lh.y), __fsub_rd(lh.x, qq.y)), 0.0f);
+          s1 = __fmaf_rd(e1, e1, s1);
+          const float e2 = fmaxf(fmaxf(__fsub_rd(yy.x, qq.w), __fsub_rd(qq.z, yy.y)), 0.0f);
+          s2 = __fmaf_rd(e2, e2, s2);
+        };
+        int k = 0;
+        // blocks of 8 steps (pointer increments, all 24 loads of a block issued up front), then one warp vote: leave
+        // when every lane is pruned -- or when only a straggler or two are left after a good part of the series:
+        // finishing their sums would keep the whole warp busy, handing them to the (early-abandoning) DP is cheaper.
+        // Pruning is optional, so this cannot change a result.
+        for (; k + 8 <= T; k += 8) {
+          float2 lh[8], yy[8]; float4 qq[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { lh[u] = env[u * ny]; yy[u] = yv[u * ny]; qq[u] = qf[k + u]; }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) step(lh[u], yy[u], qq[u]);
+          env += 8 * ny; yv += 8 * ny;
+          const int alive = __popc(__ballot_sync(0xffffffffu, !(pruned || s1 > limf || s2 > limf)));
+          if (alive == 0 || (alive <= kLbStragglers && k + 7 >= kLbStragglerAfter)) { k = T; break; }
         }
-        bool p2 = pruned || s > lim;
-        if (!__all_sync(0xffffffffu, p2)) {
-          // LB_Keogh, reference against the query's envelope
-          double s2 = 0.0;
-          const double* ql = a.lox + i * T; const double* qh = a.hix + i * T;
-          const double* yy = a.yT + j;
-          for (int k = 0; k < T; ++k) {
-            const double v = yy[(long long)k * a.ny];
-            const double l = ql[k], h = qh[k];
-            const double e = v > h ? v - h : (v < l ? l - v : 0.0);
-            s2 += e * e;
-            if ((k & 31) == 31 && __all_sync(0xffffffffu, p2 || s2 > lim)) break;
-          }
-          p2 = p2 || s2 > lim;
-        }
-        if (p2 && !pruned && valid) atomicAdd(a.n_keogh, 1ULL);
+        for (; k < T; ++k) { step(*env, *yv, qf[k]); env += ny; yv += ny; }
+        p2 = pruned || s1 > limf || s2 > limf;
+        c_keogh += __popc(__ballot_sync(0xffffffffu, p2 && !pruned && valid));
         pruned = p2;
       }
     }
     if (valid) a.d[i * a.ld + jl] = pruned ? WB_INF : -1.0;
+  }
+  if (lane == 0) {
+    if (c_kim) atomicAdd(a.n_kim, c_kim);
+    if (c_keogh) atomicAdd(a.n_keogh, c_keogh);
   }
 }
 
@@ -323,18 +406,20 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
   // ---- optional on-device lower-bound cascade (dtw, equal lengths) ----
   const bool cascade = io.use_device_lb && c.metric == M_DTW && c.ptx == c.pty && c.ptx >= 2 && !c.degenerate &&
                        nq * C < 2000000000LL;
-  double *lox = nullptr, *hix = nullptr, *yT = nullptr, *loyT = nullptr, *hiyT = nullptr;
+  float4* qf = nullptr; float2 *envT = nullptr, *yvT = nullptr;
+  double *y0 = nullptr, *yL = nullptr;
   int *counts = nullptr, *starts = nullptr, *list_len = nullptr; int2* list = nullptr;
   unsigned long long* lbstat = nullptr;  // [0] kim-pruned, [1] keogh-pruned, [2] survivors
   if (cascade) {
     const int T = c.ptx, w = std::max(c.R - 1, 0);
-    if (ws.alloc(&lox, (size_t)nq * T) || ws.alloc(&hix, (size_t)nq * T) || ws.alloc(&yT, (size_t)ny * T) ||
-        ws.alloc(&loyT, (size_t)ny * T) || ws.alloc(&hiyT, (size_t)ny * T) || ws.alloc(&counts, (size_t)nq) ||
+    if (ws.alloc(&qf, (size_t)nq * T) || ws.alloc(&envT, (size_t)ny * T) || ws.alloc(&yvT, (size_t)ny * T) ||
+        ws.alloc(&y0, (size_t)ny) || ws.alloc(&yL, (size_t)ny) || ws.alloc(&counts, (size_t)nq) ||
         ws.alloc(&starts, (size_t)nq) || ws.alloc(&list_len, 1) || ws.alloc(&list, (size_t)nq * C) ||
         ws.alloc(&lbstat, 3)) return 1;
     if (cudaMemsetAsync(lbstat, 0, 3 * sizeof(unsigned long long), st) != cudaSuccess) return 1;
-    k_envelope_rows<<<1024, 256, 0, st>>>(c.px, nq, T, w, lox, hix);
-    k_envelope_T<<<2048, 256, 0, st>>>(c.py, ny, T, w, yT, loyT, hiyT);
+    const int stride = lb_time_stride(T);
+    k_query_casc<<<1024, 256, 0, st>>>(c.px, nq, T, w, stride, qf);
+    k_envelope_casc<<<2048, 256, 0, st>>>(c.py, ny, T, w, stride, envT, yvT, y0, yL);
   }
   k_fill<<<256, 256, 0, st>>>(tau, nq, WB_INF);
   if (cudaMemsetAsync(hval, 0, sizeof(double) * nq * k, st) != cudaSuccess ||
@@ -354,7 +439,7 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
     } else if (cascade && c0 > 0) {
       // chunk 0 has no threshold yet (tau = INF): nothing can be pruned, run it densely
       LbArgs la;
-      la.x = c.px; la.lox = lox; la.hix = hix; la.yT = yT; la.loyT = loyT; la.hiyT = hiyT;
+      la.x = c.px; la.qf = qf; la.envT = envT; la.yvT = yvT; la.y0 = y0; la.yL = yL;
       la.nq = nq; la.ny = ny; la.c0 = c0; la.nc = nc; la.T = c.ptx; la.tau = tau; la.d = dbuf; la.ld = C;
       la.n_kim = lbstat; la.n_keogh = lbstat + 1;
       k_lb_prune<<<148 * 8, 256, 0, st>>>(la);

@@ -739,8 +739,8 @@ static int run_lb(int op, const double* q, int64_t nq, int64_t qs, const double*
         const int w = lb_warp_size(T, r);
         if ((rc = ws.alloc(&qlo, (size_t)nq * T)) || (rc = ws.alloc(&qhi, (size_t)nq * T)) || (rc = ws.alloc(&xT, (size_t)nx * T)) ||
             (rc = ws.alloc(&xloT, (size_t)nx * T)) || (rc = ws.alloc(&xhiT, (size_t)nx * T))) break;
-        k_envelope_rows<<<1024, 256, 0, st>>>(dq, nq, (int)T, w, qlo, qhi);           // LB:417-418
-        k_envelope_T<<<2048, 256, 0, st>>>(dx, nx, (int)T, w, xT, xloT, xhiT);        // fit, LB:371-374
+        k_envelope_rows<<<1024, 256, 0, st>>>(dq, nq, (int)T, w, 1, nullptr, qlo, qhi);  // LB:417-418 (natural time order)
+        k_envelope_T<<<2048, 256, 0, st>>>(dx, nx, (int)T, w, 1, xT, xloT, xhiT);     // fit, LB:371-374
         WB_CK(cudaGetLastError());
         local.launches += 2;
       }
