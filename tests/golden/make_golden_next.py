@@ -5,6 +5,7 @@
 Writes tests/golden/next_golden.npz:
   nd|...   multivariate pairwise / self / paired with dim="mean" / "full" (_distance.py:1245-1297, 1163-1169)
   al|... dba|... km|...  dtw_alignment / dtw_mapping / dtw_average (distance/dtw.py:246-690), KMeans(metric="dtw")
+  ee|...   ElasticEnsembleClassifier (ensemble/_elastic.py): cross-validation scores, chosen parameters, probabilities
   ss|...   pairwise / paired_subsequence_distance, DTW family (_distance.py:543-729)
   nb|...   KNeighborsClassifier.predict_proba / predict and NearestNeighbors.kneighbors (distance/_neighbors.py:19-300)
 """
@@ -131,6 +132,29 @@ def subsequences(wd, out):
         out[f"ss|{ci}|paired_dist"], out[f"ss|{ci}|paired_idx"] = d, i.astype(np.int64)
 
 
+def ensembles(wd, out):
+    """ElasticEnsembleClassifier of the reference (ensemble/_elastic.py): scores, chosen parameters, probabilities."""
+    from wildboar.ensemble import ElasticEnsembleClassifier
+    rng = np.random.default_rng(20261022)
+    X = np.concatenate([np.cumsum(rng.standard_normal((18, 36)), axis=1) + off for off in (0.0, 1.5, -1.5)])
+    y = np.repeat([2, 5, 9], 18)
+    perm = rng.permutation(54)
+    X, y = X[perm], y[perm]
+    Q = np.cumsum(rng.standard_normal((12, 36)), axis=1)
+    out["ee|X"], out["ee|y"], out["ee|Q"] = X, y, Q
+    for name, kw in (("auto_k1", dict(n_neighbors=1, metric="auto")),
+                     ("custom_k3", dict(n_neighbors=3, metric={"dtw": {"min_r": 0.1, "max_r": 0.3, "num_r": 3},
+                                                                 "msm": {"min_c": 0.1, "max_c": 10, "num_c": 4},
+                                                                 "lcss": {"min_r": 0.0, "max_r": 0.25, "num_r": 2,
+                                                                          "min_epsilon": 0.3, "max_epsilon": 1.2, "num_epsilon": 2}}))):
+        clf = ElasticEnsembleClassifier(**kw).fit(X, y)
+        out[f"ee|{name}|scores"] = np.array([s for _, s in clf.scores_])
+        out[f"ee|{name}|metrics"] = np.array([m for m, _ in clf.scores_])
+        out[f"ee|{name}|params"] = np.array(repr([{k: float(v) for k, v in e.metric_params.items()} for e in clf.estimators_]))
+        out[f"ee|{name}|proba"] = clf.predict_proba(Q)
+        out[f"ee|{name}|predict"] = clf.predict(Q)
+
+
 def main():
     wd = ref.load()
     if wd is None:
@@ -140,6 +164,7 @@ def main():
     neighbors(wd, out)
     alignments(wd, out)
     subsequences(wd, out)
+    ensembles(wd, out)
     path = os.path.join(HERE, "next_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")

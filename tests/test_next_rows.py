@@ -395,3 +395,57 @@ def test_subsequence_larger_matches_oracle(W, oracle):
         finally:
             W.set_devices([0])
         assert np.array_equal(d2, d) and np.array_equal(i2, i)
+
+
+# ---------------------------------------------------------------------------------------------
+# ElasticEnsembleClassifier (leave-one-out grid search as one argmin call per candidate)
+# ---------------------------------------------------------------------------------------------
+def test_ensemble_host_logic(wb):
+    from wildboar_b200.ensemble import ElasticEnsembleClassifier, make_parameter_grid
+    grid = make_parameter_grid({"min_r": 0.1, "max_r": 0.3, "num_r": 3, "min_p": 1, "max_p": 4, "num_p": 2})
+    assert [sorted(g) for g in grid] == [["p", "r"]] * 6 and grid[0] == {"r": 0.1, "p": 1.0} and grid[-1] == {"r": 0.3, "p": 4.0}
+    assert make_parameter_grid(None) == [{}]
+    with pytest.raises(ValueError, match="must be prefixed"):
+        make_parameter_grid({"r": 1})
+    with pytest.raises(ValueError, match="maximum value is missing"):
+        make_parameter_grid({"min_r": 0.1})
+    with pytest.raises(ValueError, match="too few labels"):
+        ElasticEnsembleClassifier().fit(np.zeros((4, 8)), [1, 1, 1, 1])
+    with pytest.raises(ValueError, match="non-elastic"):
+        ElasticEnsembleClassifier(metric="all").fit(np.zeros((4, 8)), [0, 1, 0, 1])
+    with pytest.raises(ValueError, match="is not supported"):
+        ElasticEnsembleClassifier(metric={"euclidean": None}).fit(np.zeros((4, 8)), [0, 1, 0, 1])
+
+
+@pytest.mark.gpu
+def test_ensemble_matches_reference_golden(W, next_golden):
+    import ast
+    from wildboar_b200.ensemble import ElasticEnsembleClassifier
+    g = next_golden
+    X, y, Q = g["ee|X"], g["ee|y"], g["ee|Q"]
+    for name, kw in (("auto_k1", dict(n_neighbors=1, metric="auto")),
+                     ("custom_k3", dict(n_neighbors=3, metric={"dtw": {"min_r": 0.1, "max_r": 0.3, "num_r": 3},
+                                                                 "msm": {"min_c": 0.1, "max_c": 10, "num_c": 4},
+                                                                 "lcss": {"min_r": 0.0, "max_r": 0.25, "num_r": 2,
+                                                                          "min_epsilon": 0.3, "max_epsilon": 1.2, "num_epsilon": 2}}))):
+        clf = ElasticEnsembleClassifier(**kw).fit(X, y)
+        assert [m for m, _ in clf.scores_] == list(g[f"ee|{name}|metrics"]), name
+        assert np.array_equal(np.array([s for _, s in clf.scores_]), g[f"ee|{name}|scores"]), name
+        want_params = ast.literal_eval(str(g[f"ee|{name}|params"]))
+        assert [{k: float(v) for k, v in e.metric_params.items()} for e in clf.estimators_] == want_params, name
+        assert np.array_equal(clf.predict_proba(Q), g[f"ee|{name}|proba"]), name
+        assert np.array_equal(clf.predict(Q), g[f"ee|{name}|predict"]), name
+
+
+@pytest.mark.gpu
+def test_loo_mask_equals_fold_by_fold(W, oracle):
+    """The +inf diagonal lower bound reproduces the fold-by-fold scans (here: the oracle on each fold), also for the
+    metrics whose early abandoning makes argmin differ from pairwise + top-k (lcss, erp)."""
+    from wildboar_b200.ensemble import _loo_neighbors
+    X = random_walks(30, 40, 51)
+    for metric, mp in (("lcss", {"r": 0.2, "epsilon": 0.5}), ("erp", {"r": 0.1}), ("dtw", {"r": 0.1}), ("twe", {"r": 0.3})):
+        got = _loo_neighbors(X, metric, mp, 3)
+        for i in (0, 7, 29):
+            others = np.delete(np.arange(30), i)
+            oi, _ = oracle.argmin(metric, X[i:i + 1], X[others], k=3, **mp)
+            assert np.array_equal(got[i], others[oi[0]]), (metric, i)
