@@ -162,6 +162,27 @@ def main():
                        ref_cores=NCPU, ref_bit_equal=bool(np.array_equal(rd_, d[:nxs, :nss]) and np.array_equal(ri_, i[:nxs, :nss])))
         emit(**row)
 
+    # ---- 8f-1: ElasticEnsembleClassifier.fit (leave-one-out grid search over 9 metrics, 74 candidates) ----
+    from wildboar_b200.ensemble import ElasticEnsembleClassifier
+    n, T = (60, 64) if QUICK else (400, 128)
+    Xe = np.concatenate([rw(n // 2, T, 21), rw(n // 2, T, 22) + 2.0])
+    ye = np.repeat([0, 1], n // 2)
+    t_ee, clf = timed(lambda: ElasticEnsembleClassifier(n_neighbors=1, metric="auto").fit(Xe, ye), reps=1)
+    row = dict(row="8f-1 ElasticEnsembleClassifier(metric=auto).fit", shape=f"{n} samples x {T}, 9 metrics, 74 candidates, leave-one-out",
+               e2e_ms=round(t_ee * 1e3, 1), folds=n * 74, best=[(m, round(float(s_), 4)) for m, s_ in clf.scores_][:3])
+    if wd is not None:
+        from wildboar.ensemble import ElasticEnsembleClassifier as RefEE
+        ns = 30 if QUICK else 60
+        sel = np.r_[0:ns // 2, n // 2:n // 2 + ns // 2]
+        t_ref, rclf = timed(lambda: RefEE(n_neighbors=1, metric="auto", n_jobs=NCPU).fit(Xe[sel], ye[sel]), reps=1)
+        t_our, oclf = timed(lambda: ElasticEnsembleClassifier(n_neighbors=1, metric="auto").fit(Xe[sel], ye[sel]), reps=1)
+        row.update(ref_sample=f"{ns} samples (reference: GridSearchCV + LeaveOneOut, n_jobs={NCPU})", ref_ms=round(t_ref * 1e3, 1),
+                   ours_same_sample_ms=round(t_our * 1e3, 1), ref_cores=NCPU,
+                   ref_equal=bool([m for m, _ in rclf.scores_] == [m for m, _ in oclf.scores_] and
+                                  np.array_equal([s_ for _, s_ in rclf.scores_], [s_ for _, s_ in oclf.scores_]) and
+                                  np.array_equal(rclf.predict_proba(Xe[::7]), oclf.predict_proba(Xe[::7]))))
+    emit(**row)
+
     # ---- 8f-1: KMeans(metric="dtw") ----
     n, T, K = (300, 128, 4) if QUICK else (2000, 256, 8)
     Xk = np.concatenate([rw(n // K, T, 10 + c) + 8.0 * c for c in range(K)])
