@@ -28,7 +28,8 @@ def timed(fn, reps=2):
 def main():
     n = wb.device_count()
     rows = []
-    for devs in ([0], list(range(n))) if n > 1 else ([0],):
+    all_only = "--all-only" in sys.argv
+    for devs in (([0], list(range(n))) if not all_only else (list(range(n)),)) if n > 1 else ([0],):
         wb.set_devices(devs)
         g = len(devs)
         x, y = rw(10000, 512, 1), rw(10000, 512, 2)
