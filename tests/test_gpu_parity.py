@@ -188,6 +188,25 @@ def test_argmin_device_cascade_is_exact(W, oracle, k, monkeypatch):
     _eq(idx, oi, "smooth idx"); _eq(dist, od, "smooth dist")
 
 
+def test_argmin_cascade_odd_lengths_offsets_and_near_ties(W, oracle, monkeypatch):
+    """The cascade's fp32 sums are rigorous lower bounds whatever the data looks like: odd lengths (tail of the 8-step
+    blocks, time permutation with gcd handling), huge offsets (fp32 envelopes become loose, never wrong), tiny values,
+    references that differ from the query by one ulp-sized step (distances right at the running threshold)."""
+    monkeypatch.setenv("WILDBOAR_CUDA_ARGMIN_CHUNK", "32")
+    rng = np.random.default_rng(77)
+    for T, r in ((131, 0.1), (37, 0.3), (9, 0.5), (5, 1.0), (3, 0.1), (2, 1.0), (96, 0.02)):
+        for scale, offset in ((1.0, 0.0), (1.0, 1e7), (1e-30, 0.0), (1e6, -3e9)):
+            q = np.cumsum(rng.standard_normal((13, T)), axis=1) * scale + offset
+            refs = np.cumsum(rng.standard_normal((330, T)), axis=1) * scale + offset
+            refs[5] = q[2]
+            refs[200] = np.nextafter(q[2], np.inf)          # almost the same series again, later in the scan
+            refs[300] = q[7] + scale * 1e-9
+            for k in (1, 4):
+                idx, dist = W.argmin_distance(q, refs, k=k, metric="dtw", metric_params={"r": r}, return_distance=True)
+                oi, od = oracle.argmin("dtw", q, refs, k=k, r=r, n_jobs=0)
+                _eq(idx, oi, f"T={T} scale={scale} offset={offset} k={k} idx"); _eq(dist, od, f"T={T} scale={scale} offset={offset} k={k} dist")
+
+
 def test_argmin_cfg4_shape_subset(W, oracle):
     """BASELINE configs[3] shape: T=256, r=0.05, k=1 -- 48 queries x 3000 references."""
     q, refs = random_walks(20000, 256, 3)[:48], random_walks(200000, 256, 4)[:3000]

@@ -28,6 +28,26 @@ def _is_end_of_series(a):
     return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64) == _EOS_BITS
 
 
+_POOL = None
+
+
+def _sum_is_finite(array):
+    """isfinite(sum(array)); large contiguous arrays are summed in slices on a few threads (numpy releases the GIL)."""
+    global _POOL
+    with np.errstate(over="ignore", invalid="ignore"):
+        if array.size < (1 << 22) or not array.flags.c_contiguous:
+            return bool(np.isfinite(array.sum()))
+        if _POOL is None:
+            import os
+            from concurrent.futures import ThreadPoolExecutor
+            _POOL = ThreadPoolExecutor(max_workers=max(1, min(8, os.cpu_count() or 1)))
+        flat = array.reshape(-1)
+        n = _POOL._max_workers
+        step = -(-flat.shape[0] // n)
+        parts = list(_POOL.map(lambda k: flat[k * step:(k + 1) * step].sum(), range(n)))
+        return bool(np.isfinite(np.sum(parts)))
+
+
 def check_array(array, *, allow_3d=False, ensure_2d=True, ensure_ts_array=False, dtype=float, input_name=""):
     """Numeric, finite, equal-length time series array (subset of utils/validation.py:404)."""
     try:
@@ -55,9 +75,7 @@ def check_array(array, *, allow_3d=False, ensure_2d=True, ensure_ts_array=False,
     # one pass over the data in the common case (as sklearn's _assert_all_finite does): a finite sum means that
     # every element is finite; only otherwise look for what is wrong.  (Two boolean passes over a 400 MB
     # reference set cost more than the whole device side of a nearest-neighbour query.)
-    with np.errstate(over="ignore", invalid="ignore"):
-        all_finite = bool(np.isfinite(array.sum()))
-    if not all_finite:
+    if not _sum_is_finite(array):
         padded = input_name + " " if input_name else ""
         if np.isnan(array).any():
             if _is_end_of_series(array).any():
