@@ -176,11 +176,17 @@ int wb_cuda_dba_epoch(const wb_fitted *fit, int metric, const wb_params *params,
  * SERIES length (T, T - 2).  The reference abandons windows early against the running minimum, which never changes
  * the result for these metrics; the device evaluates every window (all windows of all samples are the `y` operand of
  * ONE pairwise launch per subsequence, addressed with stride 1).
- * paired == 0: out_dist / out_idx are (nx, n_s); paired != 0 (n_s == nx): subsequence i against sample i, (nx). */
+ * paired == 0: out_dist / out_idx are (nx, n_s); paired != 0 (n_s == nx): subsequence i against sample i, (nx).
+ * scaled != 0 (metric WB_DTW): `scaled_dtw`, the UCR-suite search of ScaledDtwSubsequenceMetric (_elastic.pyx:1928-2060,
+ * scaled_dtw_subsequence_distance :353-482, inner_scaled_dtw_subsequence_distance :263-345): `s` holds the subsequences
+ * already z-normalised by the caller ((s - mean) / std with numpy's mean / std, _cdistance.pyx:453-467), every window is
+ * normalised with its running mean / std in the reference's summation order, band |i - j| <= _compute_warp_width(m, r)
+ * (_elastic.pyx:1917-1921).  The reference's LB_Kim / LB_Keogh cascade and its cumulative-bound abandoning only skip
+ * windows that cannot become the minimum; the device evaluates every window exactly. */
 int wb_cuda_subsequence(int metric, const wb_params *params,
                         const double *s, const int64_t *s_offsets, int64_t n_s,
                         const double *x, int64_t nx, int64_t T, int64_t x_stride,
-                        int paired, double *out_dist, int64_t *out_idx,
+                        int paired, int scaled, double *out_dist, int64_t *out_idx,
                         const int *devices, int n_devices, wb_stats *stats);
 
 /* Device-resident variant of wb_cuda_pairwise: d_x (nx, Tx), d_y (ny, Ty), d_out (nx, ny) are

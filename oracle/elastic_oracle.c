@@ -784,3 +784,84 @@ double orc_subsequence_distance(int metric, const orc_params *p, const double *S
   free(cost); free(cost_prev); free(weights); free(S_buffer); free(T_buffer);
   return sqrt(min_dist);
 }
+
+static inline double sq_dist(double x, double y) { const double s = x - y; return s * s; }
+
+/* EL:158-225 `constant_lower_bound` (LB_Kim over the first / last three points of the z-normalised series), term by
+ * term as written there -- including the third term, which lists dist(t_y1, s_y1) twice and never dist(t_y1, s_y0):
+ * the value can therefore EXCEED the DTW distance, and since the scan skips a window when it is >= the running minimum
+ * (EL:413), it is part of the observable result and has to be reproduced.  The staged early returns of the reference
+ * return a partial sum that is already >= best_dist; the terms are non-negative, so "skipped" <=> full sum >= best_dist. */
+static double ucr_lb_kim(const double *S, double s_mean, double s_std, const double *T, double t_mean, double t_std,
+                         int64_t length) {
+  if (t_std == 0) return 0;
+  const double t_x0 = (T[0] - t_mean) / t_std, t_y0 = (T[length - 1] - t_mean) / t_std;
+  const double s_x0 = (S[0] - s_mean) / s_std, s_y0 = (S[length - 1] - s_mean) / s_std;
+  double min_dist = sq_dist(t_x0, s_x0) + sq_dist(t_y0, s_y0);
+  const double t_x1 = (T[1] - t_mean) / t_std, s_x1 = (S[1] - s_mean) / s_std;
+  min_dist += dmin(dmin(sq_dist(t_x1, s_x0), sq_dist(t_x0, s_x1)), sq_dist(t_x1, s_x1));
+  const double t_y1 = (T[length - 2] - t_mean) / t_std, s_y1 = (S[length - 2] - s_mean) / s_std;
+  min_dist += dmin(dmin(sq_dist(t_y1, s_y1), sq_dist(t_y0, s_y1)), sq_dist(t_y1, s_y1));
+  const double t_x2 = (T[2] - t_mean) / t_std, s_x2 = (S[2] - s_mean) / s_std;
+  min_dist += dmin(dmin(sq_dist(t_x0, s_x2), dmin(dmin(sq_dist(t_x1, s_x2), sq_dist(t_x2, s_x2)), sq_dist(t_x2, s_x1))),
+                   sq_dist(t_x2, s_x0));
+  const double t_y2 = (T[length - 3] - t_mean) / t_std, s_y2 = (S[length - 3] - s_mean) / s_std;
+  min_dist += dmin(dmin(sq_dist(t_y0, s_y2), dmin(dmin(sq_dist(t_y1, s_y2), sq_dist(t_y2, s_y2)), sq_dist(t_y2, s_y1))),
+                   sq_dist(t_y2, s_y0));
+  return min_dist;
+}
+
+/* scaled_dtw (UCR suite) subsequence search, ScaledDtwSubsequenceMetric EL:1928-2060.
+ * Follows scaled_dtw_subsequence_distance EL:353-482 for the window statistics (running ex / ex2, the oldest sample
+ * subtracted again, std = 1 when the variance is not positive) and the selection rule (`dist < min_dist`, first best
+ * window, sqrt of the minimum), and inner_scaled_dtw_subsequence_distance EL:263-345 for the DP (band |i - j| <= r with
+ * r = _compute_warp_width(s_len, r) EL:1917-1921, v = (S[i] - s_mean) / s_std - (X[j] - mean) / std).  The LB_Kim
+ * prefilter IS restated (ucr_lb_kim above: it is not a valid bound and changes results); the LB_Keogh bounds and the
+ * cumulative-bound abandoning (EL:424-470, 333-334) are valid lower bounds that only skip or cut short windows whose
+ * distance cannot be below the running minimum, and are not restated.  s_std == 0 is passed as 1 by the caller
+ * (_cdistance.pyx:370).  Needs s_len >= 3 (the reference reads S[1], S[2] unconditionally). */
+double orc_scaled_dtw_subsequence(const double *S, int64_t s_len, double s_mean, double s_std, const double *T,
+                                  int64_t t_len, double rfrac, int64_t *index) {
+  const int64_t r = (rfrac == 1.0) ? s_len - 1 : (int64_t)floor((double)s_len * rfrac);
+  double *cost = (double *)malloc(sizeof(double) * (size_t)(2 * r + 2));
+  double *cost_prev = (double *)malloc(sizeof(double) * (size_t)(2 * r + 2));
+  double ex = 0, ex2 = 0, min_dist = INFINITY;
+  for (int64_t t = 0; t < t_len; t++) {
+    const double cur = T[t];
+    ex += cur;
+    ex2 += cur * cur;
+    if (t >= s_len - 1) {
+      const int64_t I = t - (s_len - 1);
+      const double *X = T + I;
+      const double mean = ex / (double)s_len;
+      const double tmp = ex2 / (double)s_len - mean * mean;
+      const double std = tmp > 0 ? sqrt(tmp) : 1.0;
+      if (!(ucr_lb_kim(S, s_mean, s_std, X, mean, std, s_len) < min_dist)) { ex -= X[0]; ex2 -= X[0] * X[0]; continue; }
+      double *c = cost, *cp = cost_prev;
+      int64_t k = 0;
+      for (int64_t i = 0; i < 2 * r + 1; i++) { c[i] = INFINITY; cp[i] = INFINITY; }
+      for (int64_t i = 0; i < s_len; i++) {
+        k = i64max(0, r - i);
+        for (int64_t j = i64max(0, i - r); j < i64min(s_len, i + r + 1); j++) {
+          double v = (S[i] - s_mean) / s_std;
+          v -= (X[j] - mean) / std;
+          if (i == 0 && j == 0) c[k] = v * v;
+          else {
+            const double y = (j - 1 < 0 || k - 1 < 0) ? INFINITY : c[k - 1];
+            const double x = (i - 1 < 0 || k + 1 > 2 * r) ? INFINITY : cp[k + 1];
+            const double z = (i - 1 < 0 || j - 1 < 0) ? INFINITY : cp[k];
+            c[k] = dmin(dmin(x, y), z) + v * v;
+          }
+          k++;
+        }
+        double *tswap = c; c = cp; cp = tswap;
+      }
+      const double dist = cp[k - 1];
+      if (dist < min_dist) { if (index) *index = I; min_dist = dist; }
+      ex -= X[0];
+      ex2 -= X[0] * X[0];
+    }
+  }
+  free(cost); free(cost_prev);
+  return sqrt(min_dist);
+}

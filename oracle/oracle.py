@@ -297,3 +297,26 @@ def pairwise_subsequence(metric, subsequences, x, **params):
                                                     C.byref(j))
             idx[i, k] = j.value
     return dist, idx
+
+
+def pairwise_scaled_dtw_subsequence(subsequences, x, r=1.0):
+    """scaled_dtw subsequence search (ScaledDtwSubsequenceMetric, EL:1928-2060): (dist, idx), (n_samples, n_subsequences)."""
+    L = lib()
+    L.orc_scaled_dtw_subsequence.argtypes = [C.POINTER(C.c_double), C.c_int64, C.c_double, C.c_double, C.POINTER(C.c_double),
+                                             C.c_int64, C.c_double, C.POINTER(C.c_int64)]
+    L.orc_scaled_dtw_subsequence.restype = C.c_double
+    x = _arr(x)
+    dist = np.empty((x.shape[0], len(subsequences)))
+    idx = np.zeros((x.shape[0], len(subsequences)), dtype=np.int64)
+    for k, s in enumerate(subsequences):
+        s = np.ascontiguousarray(s, dtype=np.float64)
+        mean, std = np.mean(s), np.std(s)      # _cdistance.pyx:453-467 (EPSILON = 1e-13), :370
+        if std <= 1e-13:
+            std = 0.0
+        std = std if std != 0 else 1.0
+        for i in range(x.shape[0]):
+            j = C.c_int64(0)
+            dist[i, k] = L.orc_scaled_dtw_subsequence(_dp(s), s.shape[0], float(mean), float(std), _dp(x[i]), x.shape[1], float(r),
+                                                      C.byref(j))
+            idx[i, k] = j.value
+    return dist, idx

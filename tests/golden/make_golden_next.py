@@ -130,6 +130,21 @@ def subsequences(wd, out):
         paired = [subs[keep[q % len(keep)]] for q in range(X.shape[0])]
         d, i = wd.paired_subsequence_distance(paired, X, metric=metric, metric_params=mp, return_index=True)
         out[f"ss|{ci}|paired_dist"], out[f"ss|{ci}|paired_idx"] = d, i.astype(np.int64)
+    # scaled_dtw (UCR suite): subsequences of >= 3 samples, none constant (all windows tie at sqrt(m) there and the
+    # reference's bounds break the tie at rounding level)
+    Xs = np.cumsum(rng.standard_normal((11, 120)), axis=1)
+    ssubs = [np.cumsum(rng.standard_normal(m)) for m in (3, 4, 5, 6, 17, 40, 120, 64)]
+    ssubs.append(Xs[4, 20:52].copy() * 3.0 + 7.0)          # a scaled, shifted copy of a window: distance 0
+    out["ssc|X"] = Xs
+    for k, s in enumerate(ssubs):
+        out[f"ssc|s{k}"] = s
+    out["ssc|n"] = np.array(len(ssubs))
+    for r in (0.0, 0.05, 0.1, 0.3, 1.0):
+        d, i = wd.pairwise_subsequence_distance(ssubs, Xs, metric="scaled_dtw", metric_params={"r": r}, return_index=True)
+        out[f"ssc|{r}|dist"], out[f"ssc|{r}|idx"] = d, i.astype(np.int64)
+    d, i = wd.paired_subsequence_distance([ssubs[q % len(ssubs)] for q in range(11)], Xs, metric="dtw", scale=True,
+                                          metric_params={"r": 0.1}, return_index=True)
+    out["ssc|paired_dist"], out["ssc|paired_idx"] = d, i.astype(np.int64)
 
 
 def ensembles(wd, out):

@@ -449,3 +449,44 @@ def test_loo_mask_equals_fold_by_fold(W, oracle):
             others = np.delete(np.arange(30), i)
             oi, _ = oracle.argmin(metric, X[i:i + 1], X[others], k=3, **mp)
             assert np.array_equal(got[i], others[oi[0]]), (metric, i)
+
+
+def _ssc_inputs(g):
+    return g["ssc|X"], [g[f"ssc|s{k}"] for k in range(int(g["ssc|n"]))]
+
+
+def test_oracle_scaled_dtw_subsequence_matches_reference_golden(oracle, next_golden):
+    g = next_golden
+    X, ss = _ssc_inputs(g)
+    for r in (0.0, 0.05, 0.1, 0.3, 1.0):
+        d, i = oracle.pairwise_scaled_dtw_subsequence(ss, X, r=r)
+        assert np.array_equal(d, g[f"ssc|{r}|dist"]) and np.array_equal(i, g[f"ssc|{r}|idx"]), r
+
+
+@pytest.mark.gpu
+def test_scaled_dtw_subsequence_matches_reference_golden(W, next_golden):
+    g = next_golden
+    X, ss = _ssc_inputs(g)
+    for r in (0.0, 0.05, 0.1, 0.3, 1.0):
+        d, i = W.pairwise_subsequence_distance(ss, X, metric="scaled_dtw", metric_params={"r": r}, return_index=True)
+        assert np.array_equal(d, g[f"ssc|{r}|dist"]) and np.array_equal(i, g[f"ssc|{r}|idx"]), r
+    d, i = W.paired_subsequence_distance([ss[q % len(ss)] for q in range(X.shape[0])], X, metric="dtw", scale=True,
+                                         metric_params={"r": 0.1}, return_index=True)
+    assert np.array_equal(d, g["ssc|paired_dist"]) and np.array_equal(i, g["ssc|paired_idx"])
+    with pytest.raises(ValueError, match="at least 3 samples"):
+        W.pairwise_subsequence_distance([np.zeros(2)], X, metric="scaled_dtw")
+    with pytest.raises(ValueError, match="not accelerated"):
+        W.pairwise_subsequence_distance([np.zeros(5)], X, metric="scaled_msm")
+
+
+@pytest.mark.gpu
+def test_scaled_dtw_subsequence_larger_matches_oracle(W, oracle):
+    """Longer series / subsequences; the oracle restates the scan including the reference's (invalid) LB_Kim prefilter."""
+    rng = np.random.default_rng(19)
+    X = np.cumsum(rng.standard_normal((25, 400)), axis=1)
+    subs = [np.cumsum(rng.standard_normal(m)) for m in (7, 33, 128, 300)] + [X[9, 111:175].copy() * 0.5 - 3.0]
+    for r in (0.02, 0.1, 1.0):
+        d, i = W.pairwise_subsequence_distance(subs, X, metric="scaled_dtw", metric_params={"r": r}, return_index=True)
+        od, oi = oracle.pairwise_scaled_dtw_subsequence(subs, X, r=r)
+        assert np.array_equal(d, od) and np.array_equal(i, oi), r
+    assert abs(d[9, 4]) < 1e-6 and i[9, 4] == 111

@@ -29,6 +29,7 @@ inline bool with_policy(int metric, const wb_params& p, const Tables& t, Fn&& f)
     case M_EDR: { EdrPolicy m; m.eps_param = p.epsilon; m.eps = p.epsilon; f(m); return true; }
     case M_MSM: { MsmPolicy m; m.cf = (float)p.c; m.c = (double)m.cf; f(m); return true; }
     case M_TWE: { TwePolicy m; m.pen = p.penalty + p.stiffness; m.tw = t.tw; f(m); return true; }
+    case M_SCALED_DTW: { ScaledDtwPolicy m; m.w = nullptr; m.p = 0; m.mean = 0; m.stdv = 1; f(m); return true; }
   }
   return false;
 }

@@ -26,6 +26,7 @@ struct KArgsT {
   int NS;            // strip engine: boundary-buffer slots per pair (strip_ring_slots(g, W))
   const double* sx;  // per-sample scalars of x (erp gap sums / edr std) or nullptr
   const double* sy;
+  const double* sy2; // second per-sample scalar of y (scaled dtw: window std) or nullptr
   double* out;
   long long ld;       // out[i * ld + j]
   double* out_m;      // optional: max over checked rows of the row minimum (row-scan engine)
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(NT, MINB) k_strip(KArgsT<typename M::real> a, 
     PairCtx pc;
     pc.sx = a.sx ? a.sx[i] : 0.0;
     pc.sy = a.sy ? a.sy[j] : 0.0;
+    pc.sy2 = a.sy2 ? a.sy2[j] : 0.0;
     mm.begin_pair(pc);
     const F ab = EA ? (F)a.thr[i] : Num<F>::inf();
     const double d = (double)strip_pair<M, W, EA, NR, 32>(a.g, mm, a.x + i * a.Tx, a.y + j * a.ys, bnd, 32, ab);
@@ -170,6 +172,7 @@ __global__ void __launch_bounds__(NT) k_rowscan(KArgsT<typename M::real> a, M m)
     PairCtx pc;
     pc.sx = a.sx ? a.sx[i] : 0.0;
     pc.sy = a.sy ? a.sy[j] : 0.0;
+    pc.sy2 = a.sy2 ? a.sy2[j] : 0.0;
     mm.begin_pair(pc);
     const F md = a.thr ? (F)a.thr[i] : Num<F>::inf();
     F mmax = F(0);
@@ -223,6 +226,69 @@ __global__ void k_series_stat(const double* __restrict__ x, long long n, int T, 
     ex2 = ex2 / (double)T - mean * mean;
     out[s] = ex2 > 1e-13 ? sqrt(ex2) : 0.0;
   }
+}
+
+// ---- scaled subsequence search: running window statistics of every sample, in the reference's order (EL:375-401,
+// 472-474: ex / ex2 accumulate sample by sample and the oldest sample is subtracted again) ----
+// mean[i * T + w], stdv[i * T + w] for the windows w = 0 .. T - m of sample i; one thread per sample.
+__global__ void k_window_stats(const double* __restrict__ x, long long n, int T, int m, double* __restrict__ mean,
+                               double* __restrict__ stdv) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* p = x + i * T;
+  double ex = 0.0, ex2 = 0.0;
+  for (int t = 0; t < T; ++t) {
+    const double v = p[t];
+    ex += v;
+    ex2 += v * v;
+    if (t >= m - 1) {
+      const int w = t - (m - 1);
+      const double mu = ex / (double)m;
+      const double tmp = ex2 / (double)m - mu * mu;
+      mean[i * T + w] = mu;
+      stdv[i * T + w] = tmp > 0 ? sqrt(tmp) : 1.0;
+      const double old = p[w];
+      ex -= old;
+      ex2 -= old * old;
+    }
+  }
+}
+
+// LB_Kim of the UCR-suite scan, `constant_lower_bound` EL:158-225, for every window of every sample (same layout as the
+// DP values: entry i * T + w).  Term by term as the reference writes it -- its third term lists dist(t_y1, s_y1) twice
+// and never dist(t_y1, s_y0), so the value can exceed the DTW distance; the scan skips a window when it is >= the running
+// minimum (EL:413), which makes it part of the observable result.  sn = z-normalised subsequence (m >= 3 values).
+__global__ void k_ucr_kim(const double* __restrict__ x, long long n, int T, int m, const double* __restrict__ sn,
+                          const double* __restrict__ mean, const double* __restrict__ stdv, double* __restrict__ lb) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nw = T - m + 1;
+  if (e >= n * (long long)nw) return;
+  const long long i = e / nw;
+  const int w = (int)(e - i * nw);
+  const double* t = x + i * T + w;
+  const double mu = mean[i * T + w], sd = stdv[i * T + w];
+  auto d2 = [](double a, double b) { const double q = a - b; return q * q; };
+  const double t_x0 = (t[0] - mu) / sd, t_y0 = (t[m - 1] - mu) / sd;
+  const double s_x0 = sn[0], s_y0 = sn[m - 1];
+  double v = d2(t_x0, s_x0) + d2(t_y0, s_y0);
+  const double t_x1 = (t[1] - mu) / sd, s_x1 = sn[1];
+  v += dmin2(dmin2(d2(t_x1, s_x0), d2(t_x0, s_x1)), d2(t_x1, s_x1));
+  const double t_y1 = (t[m - 2] - mu) / sd, s_y1 = sn[m - 2];
+  v += dmin2(dmin2(d2(t_y1, s_y1), d2(t_y0, s_y1)), d2(t_y1, s_y1));
+  const double t_x2 = (t[2] - mu) / sd, s_x2 = sn[2];
+  v += dmin2(dmin2(d2(t_x0, s_x2), dmin2(dmin2(d2(t_x1, s_x2), d2(t_x2, s_x2)), d2(t_x2, s_x1))), d2(t_x2, s_x0));
+  const double t_y2 = (t[m - 3] - mu) / sd, s_y2 = sn[m - 3];
+  v += dmin2(dmin2(d2(t_y0, s_y2), dmin2(dmin2(d2(t_y1, s_y2), d2(t_y2, s_y2)), d2(t_y2, s_y1))), d2(t_y2, s_y0));
+  lb[i * T + w] = v;
+}
+
+// scaled subsequence search: (raw minimum, window) of the replayed scan -> (sqrt, index)
+__global__ void k_finish_scan(const double* __restrict__ hval, const long long* __restrict__ hidx, long long n,
+                              double* __restrict__ out_dist, long long* __restrict__ out_idx, long long ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out_dist[i * ld] = sqrt(hval[i]);
+  out_idx[i * ld] = hidx[i];
 }
 
 // ---- subsequence search: first minimum over the windows of every sample (EL:622-660: `dist < min_dist`, strict) ----

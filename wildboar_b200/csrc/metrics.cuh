@@ -36,7 +36,8 @@ namespace wb {
 
 enum MetricId : int {
   M_DTW = 0, M_WDTW = 1, M_DDTW = 2, M_ADTW = 3, M_LCSS = 4, M_ERP = 5,
-  M_EDR = 6, M_MSM = 7, M_TWE = 8, M_WDDTW = 9, M_WLCSS = 10, M_COUNT = 11
+  M_EDR = 6, M_MSM = 7, M_TWE = 8, M_WDDTW = 9, M_WLCSS = 10, M_COUNT = 11,
+  M_SCALED_DTW = 100  // internal: scaled_dtw subsequence search (not a pairwise metric of the public enum)
 };
 
 #if defined(__CUDA_ARCH__)
@@ -101,7 +102,8 @@ WB_HD Geom make_geom(int Tx, int Ty, int R) {
 // Per-pair scalars a metric may need (computed by small prologue kernels / the host).
 struct PairCtx {
   double sx;  // erp: sum |x - g|   edr: std(x)
-  double sy;  // erp: sum |y - g|   edr: std(y)
+  double sy;  // erp: sum |y - g|   edr: std(y)      scaled dtw: mean of the window
+  double sy2; //                                      scaled dtw: std of the window
 };
 
 // ------------------------------------------------------------------------------------------
@@ -150,6 +152,17 @@ struct DtwPolicy {
     return dmin2(dmin2(up, left), diag) + cost;
   }
   WB_HD F finish(F d, const Geom& g) const { return g.raw ? d : sqrt(d); }
+};
+
+// ------------------------------------------------------------------------------------------
+// Scaled (z-normalised) DTW of the UCR-suite subsequence search, `inner_scaled_dtw_subsequence_distance` EL:263-345:
+// v = (S[i] - s_mean) / s_std - (X[j] - mean) / std.  The first operand arrives already normalised; the second
+// operand's samples are normalised when a strip loads its columns, with the window's running mean / std (EL:390-401).
+// ------------------------------------------------------------------------------------------
+struct ScaledDtwPolicy : DtwPolicy<false, false, double> {
+  double mean, stdv;
+  WB_HD void begin_pair(const PairCtx& pc) { mean = pc.sy; stdv = pc.sy2; }
+  WB_HD Col col(int, double yj, double) const { Col c; c.yj = (yj - mean) / stdv; return c; }
 };
 
 // ------------------------------------------------------------------------------------------

@@ -238,7 +238,7 @@ struct DpCall {
   long long list_n;                       // PM_LISTP: number of list entries (known on the host)
   // prepared operands (filled by prepare_operands; reusable across chunked launches)
   const double* px; const double* py; int ptx, pty;
-  const double* sx; const double* sy;
+  const double* sx; const double* sy; const double* sy2;
   Tables tab;
   // fp32 mode (optional; p.precision == 1 and the metric has a float variant): float copies
   bool fp32;
@@ -351,7 +351,7 @@ static int launch_dp_t(Workspace& ws, const DeviceInfo& di, const DpCall& c, lon
   a.g = make_geom(c.ptx, c.pty, c.R);
   a.g.raw = c.raw;
   a.ys = c.ys > 0 ? c.ys : c.pty;
-  a.sx = c.sx ? c.sx + r0 : nullptr; a.sy = c.sy ? c.sy + c0 : nullptr;
+  a.sx = c.sx ? c.sx + r0 : nullptr; a.sy = c.sy ? c.sy + c0 : nullptr; a.sy2 = c.sy2 ? c.sy2 + c0 : nullptr;
   a.out = out; a.ld = ld; a.out_m = out_m; a.thr = thr;
   a.mode = c.mode; a.row0 = c.row0 + r0 - c0; a.mirror = c.mirror;
   a.list = c.list; a.list_len = c.list_len;
@@ -995,8 +995,14 @@ struct SubseqJob {
   const double* s; const int64_t* soff; int64_t ns;   // subsequences, concatenated
   const double* x; int64_t nx, T, xs;
   int paired;
+  int scaled;                                          // 1: scaled_dtw (UCR suite): s is already z-normalised
   double* out_dist; int64_t* out_idx;                  // (nx, ns) or, paired, (nx)
 };
+
+// EL:1917-1921 `_compute_warp_width` (the UCR-suite band |i - j| <= width; 0 = diagonal only)
+static int64_t compute_warp_width(int64_t length, double r) {
+  return r == 1.0 ? length - 1 : (int64_t)std::floor((double)length * r);
+}
 
 // samples [lo, hi) on device `dev`
 static int subseq_worker(const SubseqJob& J, int dev, int64_t lo, int64_t hi, wb_stats* st_out) {
@@ -1048,6 +1054,13 @@ static int subseq_worker(const SubseqJob& J, int dev, int64_t lo, int64_t hi, wb
         WB_CK(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, st));
         dw = d + table_center(wn);
       }
+      // scaled_dtw: running mean / std of every window, recomputed when the subsequence length changes
+      double *dmean = nullptr, *dstd = nullptr, *dkim = nullptr, *tau = nullptr, *hval = nullptr;
+      long long* hidx = nullptr; int* hn = nullptr;
+      int64_t stats_m = -1;
+      if (J.scaled && ((rc = ws.alloc(&dmean, (size_t)rows * Tp)) || (rc = ws.alloc(&dstd, (size_t)rows * Tp)) ||
+                       (rc = ws.alloc(&dkim, (size_t)rows * Tp)) || (rc = ws.alloc(&tau, (size_t)rows)) ||
+                       (rc = ws.alloc(&hval, (size_t)rows)) || (rc = ws.alloc(&hidx, (size_t)rows)) || (rc = ws.alloc(&hn, (size_t)rows)))) break;
       const int64_t nout = J.paired ? rows : rows * J.ns;
       if ((rc = ws.alloc(&draw, (size_t)rows * std::max<int64_t>(Tp, 1))) || (rc = ws.alloc(&ddist, (size_t)nout)) ||
           (rc = ws.alloc(&didx, (size_t)nout))) break;
@@ -1055,7 +1068,7 @@ static int subseq_worker(const SubseqJob& J, int dev, int64_t lo, int64_t hi, wb
       WB_CK(cudaMemsetAsync(didx, 0, sizeof(long long) * nout, st));
       kt.start();
       // the DP policy on prepared data: ddtw -> dtw, wddtw -> wdtw
-      const int dp_metric = J.metric == M_DDTW ? M_DTW : (J.metric == M_WDDTW ? M_WDTW : J.metric);
+      const int dp_metric = J.scaled ? (int)M_SCALED_DTW : (J.metric == M_DDTW ? M_DTW : (J.metric == M_WDDTW ? M_WDTW : J.metric));
       for (int64_t k = 0; k < J.ns && !rc; ++k) {
         const int64_t m = J.soff[k + 1] - J.soff[k];
         const int64_t mp = poff[(size_t)k + 1] - poff[(size_t)k];
@@ -1064,16 +1077,43 @@ static int subseq_worker(const SubseqJob& J, int dev, int64_t lo, int64_t hi, wb
         // paired: subsequence k against sample k only; else against every sample of the block
         const int64_t r0 = J.paired ? k - lo : 0, nr = J.paired ? 1 : rows;
         if (J.paired && (k < lo || k >= hi)) continue;
+        if (J.scaled && m != stats_m) {
+          k_window_stats<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(dxp, rows, (int)Tp, (int)m, dmean, dstd);
+          WB_CK(cudaGetLastError());
+          stats.launches += 1;
+          stats_m = m;
+        }
         DpCall c; memset(&c, 0, sizeof c);
         c.metric = dp_metric; c.p = J.p; c.mode = PM_PAIRWISE;
         c.px = ds + poff[(size_t)k]; c.nx = 1; c.ptx = (int)mp;
         c.py = dxp + r0 * Tp; c.pty = (int)mp; c.ys = 1; c.ny = nr * Tp - mp + 1;
         c.R = (int)compute_r(m, J.p.r);  // from the ORIGINAL subsequence length (EL:2253, 2480)
+        if (J.scaled) {
+          c.R = (int)compute_warp_width(m, J.p.r) + 1;  // band |i - j| <= warp width (EL:2033, 283-292)
+          c.sy = dmean + r0 * Tp; c.sy2 = dstd + r0 * Tp;
+        }
         c.raw = 1;
         c.tab.weights = dw;
         if ((rc = launch_dp(ws, di, c, 0, 1, 0, c.ny, draw, c.ny, nullptr, nullptr, &stats))) break;
         double* od = J.paired ? ddist + r0 : ddist + k;
         long long* oi = J.paired ? didx + r0 : didx + k;
+        if (J.scaled) {
+          // the reference's scan, replayed exactly: windows in order, running minimum t, a window is skipped when its
+          // LB_Kim value is >= t (EL:413) and accepted iff its distance is < t (EL:471) -- all in the squared-cost domain
+          const long long npair = nr * nw;
+          k_ucr_kim<<<(unsigned)((npair + 255) / 256), 256, 0, st>>>(dxp + r0 * Tp, nr, (int)Tp, (int)m, ds + poff[(size_t)k],
+                                                                      dmean + r0 * Tp, dstd + r0 * Tp, dkim);
+          k_fill<<<64, 256, 0, st>>>(tau, nr, WB_INF);
+          WB_CK(cudaMemsetAsync(hn, 0, sizeof(int) * nr, st));
+          ReplayArgs ra;
+          ra.d = draw; ra.m = nullptr; ra.lb = dkim; ra.ld = Tp; ra.nq = nr; ra.c0 = 0; ra.ncols = nw;
+          ra.k = 1; ra.kind = TK_NONE; ra.scale = 1.0; ra.tau = tau; ra.hidx = hidx; ra.hval = hval; ra.hn = hn;
+          k_replay<<<(unsigned)std::max<long long>(1, std::min<long long>((nr + 3) / 4, 148 * 16)), 128, 0, st>>>(ra);
+          k_finish_scan<<<(unsigned)((nr + 127) / 128), 128, 0, st>>>(hval, hidx, nr, od, oi, J.paired ? 1 : J.ns);
+          WB_CK(cudaGetLastError());
+          stats.launches += 4;
+          continue;
+        }
         k_window_min<<<(unsigned)((nr * 32 + 127) / 128), 128, 0, st>>>(draw, nr, (int)Tp, (int)nw, od, oi, J.paired ? 1 : J.ns, 1);
         WB_CK(cudaGetLastError());
         stats.launches += 1;
@@ -1340,7 +1380,7 @@ int wb_cuda_dba_epoch(const wb_fitted* fit, int metric, const wb_params* params,
 }
 
 int wb_cuda_subsequence(int metric, const wb_params* params, const double* s, const int64_t* s_offsets, int64_t n_s,
-                        const double* x, int64_t nx, int64_t T, int64_t x_stride, int paired, double* out_dist,
+                        const double* x, int64_t nx, int64_t T, int64_t x_stride, int paired, int scaled, double* out_dist,
                         int64_t* out_idx, const int* devices, int n_devices, wb_stats* stats) {
   if (check_common(metric, params, x, nx, T)) return 1;
   if (!s || !s_offsets || !out_dist || !out_idx) { set_err("null argument"); return 1; }
@@ -1348,13 +1388,16 @@ int wb_cuda_subsequence(int metric, const wb_params* params, const double* s, co
   if (params->precision != 0) { set_err("subsequence search runs in fp64"); return 1; }
   if (n_s < 1 || s_offsets[0] != 0) { set_err("empty input"); return 1; }
   if (paired && n_s != nx) { set_err("paired subsequence search needs one subsequence per sample"); return 1; }
+  if (scaled && metric != M_DTW) { set_err("the scaled (z-normalised) subsequence search is implemented for dtw"); return 1; }
+  if (scaled) for (int64_t k = 0; k < n_s; ++k)
+    if (s_offsets[k + 1] - s_offsets[k] < 3) { set_err("scaled_dtw needs subsequences of at least 3 samples (the reference's LB_Kim reads S[1], S[2])"); return 1; }
   for (int64_t k = 0; k < n_s; ++k) {
     const int64_t m = s_offsets[k + 1] - s_offsets[k];
     if (m < 1 || m > T) { set_err("every subsequence needs 1 <= length <= n_timestep"); return 1; }
   }
   SubseqJob J;
   J.metric = metric; J.p = *params; J.s = s; J.soff = s_offsets; J.ns = n_s; J.x = x; J.nx = nx; J.T = T; J.xs = x_stride;
-  J.paired = paired ? 1 : 0; J.out_dist = out_dist; J.out_idx = out_idx;
+  J.paired = paired ? 1 : 0; J.scaled = scaled ? 1 : 0; J.out_dist = out_dist; J.out_idx = out_idx;
   return run_subsequence(J, devices, n_devices, stats);
 }
 

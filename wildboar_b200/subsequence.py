@@ -2,12 +2,14 @@
 
 Mirrors ``wildboar.distance.pairwise_subsequence_distance`` and ``paired_subsequence_distance``
 (reference: src/wildboar/distance/_distance.py:543-636, 639-729) for ``metric`` in {dtw, wdtw, adtw, ddtw, wddtw}
-with ``scale=False``: same arguments, return shapes (``_format_return``), index of the FIRST best window.
+with ``scale=False`` and for ``scaled_dtw`` (= ``metric="dtw", scale=True``: the z-normalised UCR-suite search):
+same arguments, return shapes (``_format_return``), index of the FIRST best window.
 
 B200-first: instead of one early-abandoning scan per (sample, subsequence) pair, all sliding windows of all
 samples are the second operand of one pairwise DP launch per subsequence (windows addressed with stride 1, so a
 warp's 32 consecutive windows read consecutive addresses), followed by a first-minimum reduction per sample.
-The scaled (z-normalised, UCR-suite) and the non-DTW subsequence metrics are not covered; there is no CPU fallback.
+``scaled_dtw`` additionally replays the reference's scan exactly (its LB_Kim prefilter is not a valid bound and decides
+which window wins).  The other scaled and the non-DTW subsequence metrics are not covered; there is no CPU fallback.
 """
 import numbers
 
@@ -43,15 +45,32 @@ def _validate_subsequence(y):
     return y
 
 
+_EPSILON = 1e-13  # _cdistance.pxd EPSILON
+
+
 def _check_subsequence_metric(metric, scale):
+    """Returns (metric name of the DP, scaled?)  (_distance.py:208-228 `_infer_scaled_metric`, :263-300)."""
     if callable(metric):
         raise ValueError("callable subsequence metrics are not accelerated; use wildboar.distance for them")
-    if scale or (isinstance(metric, str) and metric.startswith("scaled_")):
-        raise ValueError("scaled subsequence metrics are not accelerated (SURVEY 8f-4, next); use wildboar.distance for them")
+    if scale and isinstance(metric, str) and not metric.startswith("scaled_"):
+        metric = "scaled_" + metric
+    if metric == "scaled_dtw":
+        return "dtw", True
+    if isinstance(metric, str) and metric.startswith("scaled_"):
+        raise ValueError(f"the scaled subsequence metric {metric!r} is not accelerated (only scaled_dtw); use wildboar.distance for it")
     if metric not in _SUBSEQUENCE_METRICS:
         raise ValueError(
-            "unsupported metric '{}', 'metric' must be a str among {}".format(metric, set(_SUBSEQUENCE_METRICS))
+            "unsupported metric '{}', 'metric' must be a str among {}".format(metric, set(_SUBSEQUENCE_METRICS) | {"scaled_dtw"})
         )
+    return metric, False
+
+
+def _z_normalise(s):
+    """ScaledSubsequenceMetric.from_array (_cdistance.pyx:453-467) + the std passed on (:283-298)."""
+    mean, std = np.mean(s), np.std(s)
+    if std <= _EPSILON:
+        std = 0.0
+    return (s - mean) / (std if std != 0 else 1.0)
 
 
 def _prepare(y, x, dim, metric, metric_params, scale):
@@ -62,12 +81,16 @@ def _prepare(y, x, dim, metric, metric_params, scale):
             raise ValueError("Invalid subsequnce shape (%d > %d)" % (s.shape[0], x.shape[-1]))
         if s.ndim != 1 or s.shape[0] < 1 or not np.all(np.isfinite(s)):
             raise ValueError("every subsequence must be a non-empty, finite 1-D array")
-    _check_subsequence_metric(metric, scale)
+    metric, scaled = _check_subsequence_metric(metric, scale)
     m = _make_metric(metric, metric_params)
     x_ = _check_ts_array(x)
     if isinstance(dim, bool) or not isinstance(dim, numbers.Integral) or not 0 <= dim < x_.shape[1]:
         raise ValueError("The parameter dim must be 0 <= dim < n_dims")
-    return y, x, x_[:, int(dim), :], m
+    if scaled:
+        if any(s.shape[0] < 3 for s in y):
+            raise ValueError("scaled_dtw needs subsequences of at least 3 samples (the reference reads S[1], S[2] unconditionally)")
+        y = [_z_normalise(s) for s in y]
+    return y, x, x_[:, int(dim), :], m, scaled
 
 
 def pairwise_subsequence_distance(y, x, *, dim=0, metric="dtw", metric_params=None, scale=False, return_index=False,
@@ -77,8 +100,8 @@ def pairwise_subsequence_distance(y, x, *, dim=0, metric="dtw", metric_params=No
     Returns an array of shape (n_samples, n_subsequences) (squeezed like the reference) and, with
     ``return_index``, the start of the first best-matching window.
     """
-    y, x, xd, m = _prepare(y, x, dim, metric, metric_params, scale)
-    min_dist, min_ind = _shim.subsequence(m.metric_id, m._params(), y, xd, paired=False)
+    y, x, xd, m, scaled = _prepare(y, x, dim, metric, metric_params, scale)
+    min_dist, min_ind = _shim.subsequence(m.metric_id, m._params(), y, xd, paired=False, scaled=scaled)
     if return_index:
         return _format_return(min_dist, len(y), x.ndim), _format_return(min_ind, len(y), x.ndim)
     return _format_return(min_dist, len(y), x.ndim)
@@ -87,13 +110,13 @@ def pairwise_subsequence_distance(y, x, *, dim=0, metric="dtw", metric_params=No
 def paired_subsequence_distance(y, x, *, dim=0, metric="dtw", metric_params=None, scale=False, return_index=False,
                                 n_jobs=None):
     """Minimum distance between the i:th subsequence and the i:th sample (_distance.py:639-729)."""
-    y, x, xd, m = _prepare(y, x, dim, metric, metric_params, scale)
+    y, x, xd, m, scaled = _prepare(y, x, dim, metric, metric_params, scale)
     n_samples = x.shape[0] if x.ndim > 1 else 1
     if len(y) != n_samples:
         raise ValueError(
             "The number of subsequences and samples must be the same, got %d subsequences and %d samples." % (len(y), n_samples)
         )
-    min_dist, min_ind = _shim.subsequence(m.metric_id, m._params(), y, xd, paired=True)
+    min_dist, min_ind = _shim.subsequence(m.metric_id, m._params(), y, xd, paired=True, scaled=scaled)
     if return_index:
         return _format_return(min_dist, len(y), x.ndim), _format_return(min_ind, len(y), x.ndim)
     return _format_return(min_dist, len(y), x.ndim)
