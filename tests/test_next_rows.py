@@ -344,8 +344,10 @@ def test_subsequence_host_logic(wb):
         wb.pairwise_subsequence_distance([np.zeros(11)], x, metric="dtw")
     with pytest.raises(ValueError, match="unsupported metric"):
         wb.pairwise_subsequence_distance([np.zeros(4)], x, metric="euclidean")
-    with pytest.raises(ValueError, match="scaled"):
-        wb.pairwise_subsequence_distance([np.zeros(4)], x, metric="dtw", scale=True)
+    with pytest.raises(ValueError, match="not accelerated"):
+        wb.pairwise_subsequence_distance([np.zeros(4)], x, metric="msm", scale=True)
+    with pytest.raises(ValueError, match="at least 3 samples"):
+        wb.pairwise_subsequence_distance([np.zeros(2)], x, metric="dtw", scale=True)
     with pytest.raises(ValueError, match="must be the same"):
         wb.paired_subsequence_distance([np.zeros(4)], x, metric="dtw")
     with pytest.raises(ValueError, match="dim must be"):
