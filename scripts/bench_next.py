@@ -147,7 +147,7 @@ def main():
     Xs = rw(n, T, 8)
     rng = np.random.default_rng(9)
     shp = [Xs[rng.integers(0, n), o:o + m].copy() for o in rng.integers(0, T - m, ns)]
-    for metric, mp in (("dtw", {"r": 0.1}), ("wdtw", {"r": 0.1, "g": 0.05})):
+    for metric, mp in (("dtw", {"r": 0.1}), ("wdtw", {"r": 0.1, "g": 0.05}), ("scaled_dtw", {"r": 0.1})):
         t_ss, (d, i) = timed(lambda: wb.pairwise_subsequence_distance(shp, Xs, metric=metric, metric_params=mp, return_index=True))
         st = wb.last_stats()
         row = dict(row="8f-4 pairwise_subsequence_distance", metric=metric, shape=f"{ns} subsequences x {m} vs {n} samples x {T}, r={mp['r']}",
