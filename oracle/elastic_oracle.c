@@ -738,7 +738,11 @@ void orc_dtw_path(const double *D, int64_t xl, int64_t yl, int32_t *lo, int32_t 
 }
 
 /* ------------------------------------------------------------------------------------------
- * subsequence search, DTW family (test infrastructure).
+ * subsequence search, DTW family + lcss / erp / edr / msm / twe (test infrastructure).
+ * lcss_subsequence_distance EL:1186-1224, erp EL:1350-1388, edr EL:1500-1536 (epsilon resolved by the caller: NaN means
+ * s_std / 4, EL:2762-2765), msm EL:1650-1686, twe EL:1832-1869: the window's *_distance() is early-abandoned against the
+ * running minimum -- for these metrics that CHANGES which windows are accepted (row minima are not monotone), so the scan
+ * order is part of the result; they return the minimum itself (no sqrt).
  * dtw_subsequence_distance EL:622-660, adtw_subsequence_distance EL:701-740, ddtw_subsequence_distance EL:780-815,
  * with the per-class conventions of EL:2206-2615: r = _compute_r(s_len, r) from the ORIGINAL subsequence length;
  * wdtw weights over n_timestep (EL:2370-2372), wddtw over n_timestep - 2 (EL:2540-2543); early abandoning against
@@ -752,8 +756,11 @@ double orc_subsequence_distance(int metric, const orc_params *p, const double *S
   double *cost = (double *)malloc(sizeof(double) * (size_t)(t_len + 1));
   double *cost_prev = (double *)malloc(sizeof(double) * (size_t)(t_len + 1));
   double *weights = NULL, *S_buffer = NULL, *T_buffer = NULL;
+  double *gX = (double *)malloc(sizeof(double) * (size_t)(t_len + 1));
+  double *gY = (double *)malloc(sizeof(double) * (size_t)(t_len + 1));
   double min_dist = INFINITY, dist;
   const int64_t length = t_len - s_len + 1;
+  const int squared = !(metric == ORC_LCSS || metric == ORC_ERP || metric == ORC_EDR || metric == ORC_MSM || metric == ORC_TWE);
   if (metric == ORC_WDTW) {
     weights = (double *)malloc(sizeof(double) * (size_t)t_len);
     orc_weights(p->g, t_len, weights);
@@ -762,7 +769,7 @@ double orc_subsequence_distance(int metric, const orc_params *p, const double *S
     if (t_len - 2 > 0) orc_weights(p->g, t_len - 2, weights);
   }
   if (deriv) {
-    if (s_len < 3) { free(cost); free(cost_prev); free(weights); return 0; }
+    if (s_len < 3) { free(cost); free(cost_prev); free(weights); free(gX); free(gY); return 0; }
     S_buffer = (double *)malloc(sizeof(double) * (size_t)t_len);
     T_buffer = (double *)malloc(sizeof(double) * (size_t)t_len);
     orc_average_slope(S, s_len, S_buffer);
@@ -773,6 +780,17 @@ double orc_subsequence_distance(int metric, const orc_params *p, const double *S
       dist = dtw_distance(S_buffer, s_len - 2, T_buffer, s_len - 2, r, cost, cost_prev, weights, min_dist);
     } else if (metric == ORC_ADTW) {
       dist = adtw_distance(S, s_len, T + i, s_len, r, cost, cost_prev, p->p, min_dist);
+    } else if (metric == ORC_LCSS) { /* EL:1186-1224; threshold s_len - min_dist * s_len (min(s_len, t_len) = s_len) */
+      dist = lcss_distance(S, s_len, T + i, s_len, r, p->epsilon, cost, cost_prev, NULL,
+                           isinf(min_dist) ? min_dist : (double)i64min(s_len, t_len) - min_dist * (double)i64min(s_len, t_len));
+    } else if (metric == ORC_ERP) { /* EL:1350-1388 */
+      dist = erp_distance(S, s_len, T + i, s_len, r, p->g, gX, gY, cost, cost_prev, min_dist);
+    } else if (metric == ORC_EDR) { /* EL:1500-1536: threshold min_dist * max(s_len, t_len) -- the SERIES length */
+      dist = edr_distance(S, s_len, T + i, s_len, r, p->epsilon, cost, cost_prev, min_dist * (double)i64max(s_len, t_len));
+    } else if (metric == ORC_MSM) { /* EL:1650-1686 */
+      dist = msm_distance(S, s_len, T + i, s_len, r, p->c, cost, cost_prev, gX, min_dist);
+    } else if (metric == ORC_TWE) { /* EL:1832-1869 */
+      dist = twe_distance(S, s_len, T + i, s_len, r, p->penalty, p->stiffness, cost, cost_prev, min_dist);
     } else {
       dist = dtw_distance(S, s_len, T + i, s_len, r, cost, cost_prev, weights, min_dist);
     }
@@ -781,8 +799,8 @@ double orc_subsequence_distance(int metric, const orc_params *p, const double *S
       min_dist = dist;
     }
   }
-  free(cost); free(cost_prev); free(weights); free(S_buffer); free(T_buffer);
-  return sqrt(min_dist);
+  free(cost); free(cost_prev); free(weights); free(S_buffer); free(T_buffer); free(gX); free(gY);
+  return squared ? sqrt(min_dist) : min_dist;
 }
 
 static inline double sq_dist(double x, double y) { const double s = x - y; return s * s; }
@@ -864,4 +882,104 @@ double orc_scaled_dtw_subsequence(const double *S, int64_t s_len, double s_mean,
   }
   free(cost); free(cost_prev);
   return sqrt(min_dist);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * the generic scaled subsequence metrics `scaled_<metric>` = ScaledSubsequenceMetricWrap(Metric),
+ * CD:470-551 (`_distance`): the subsequence is z-normalised with (s_mean, s_std) handed in by the caller
+ * (np.mean / np.std, std <= 1e-13 -> 0 -> 1.0, CD:453-467, 283-298), every window with the running IncStats
+ * (ST:45-93: Welford add / remove, variance < 1e-13 -> 0 -> std 1), then `wrap._eadistance(s_buffer, window, &min_dist)`
+ * decides (strict <, early abandoning against the running minimum).  `wrap.reset(X, X)` sizes the weight vectors from the
+ * SERIES length (wdtw EL:3334-3341: t_len; wddtw EL:3415-3428: t_len - 2).  EDR's default epsilon comes from
+ * fast_mean_std of the two normalised buffers (EL:3856-3861).  ddtw / wddtw with s_len < 3: nothing is accepted (EL:3297).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { double mean, n_samples, sum_square, sum; } inc_stats;
+static void inc_add(inc_stats *s, double w, double v) {
+  s->n_samples += w;
+  double next_m = s->mean + (v - s->mean) / s->n_samples;
+  s->sum_square += (v - s->mean) * (v - next_m);
+  s->mean = next_m;
+  s->sum += w * v;
+}
+static void inc_remove(inc_stats *s, double w, double v) {
+  if (s->n_samples == 1.0) { s->n_samples = 0.0; s->mean = 0.0; s->sum_square = 0.0; }
+  else {
+    double old_m = (s->n_samples * s->mean - v) / (s->n_samples - w);
+    s->sum_square -= (v - s->mean) * (v - old_m);
+    s->mean = old_m;
+    s->n_samples -= w;
+  }
+  s->sum -= w * v;
+}
+static double inc_variance(const inc_stats *s) {
+  if (s->n_samples <= 1) return 0;
+  double var = s->sum_square / s->n_samples;
+  if (var < 1e-13) var = 0.0;
+  return var;
+}
+
+/* mean / std of every window as the wrap computes them (exported for tests of the device statistics kernel) */
+void orc_inc_window_stats(const double *x, int64_t t_len, int64_t s_len, double *mean, double *std) {
+  inc_stats st = {0, 0, 0, 0};
+  for (int64_t i = 0; i < s_len - 1; i++) inc_add(&st, 1.0, x[i]);
+  for (int64_t i = 0; i < t_len - s_len + 1; i++) {
+    inc_add(&st, 1.0, x[i + s_len - 1]);
+    double sd = inc_variance(&st);
+    sd = (sd == 0.0) ? 1.0 : sqrt(sd);
+    mean[i] = st.mean; std[i] = sd;
+    inc_remove(&st, 1.0, x[i]);
+  }
+}
+
+double orc_scaled_subsequence_distance(int metric, const orc_params *p, const double *S, int64_t s_len, double s_mean,
+                                       double s_std, const double *T, int64_t t_len, int64_t *index) {
+  const int deriv = (metric == ORC_DDTW || metric == ORC_WDDTW);
+  size_t n = (size_t)(t_len + 2);
+  double *cost = (double *)malloc(sizeof(double) * n), *cost_prev = (double *)malloc(sizeof(double) * n);
+  double *sb = (double *)malloc(sizeof(double) * n), *xb = (double *)malloc(sizeof(double) * n);
+  double *a1 = (double *)malloc(sizeof(double) * n), *a2 = (double *)malloc(sizeof(double) * n);
+  double *weights = NULL, *mean = (double *)malloc(sizeof(double) * n), *std = (double *)malloc(sizeof(double) * n);
+  if (metric == ORC_WDTW) { weights = (double *)malloc(sizeof(double) * n); orc_weights(p->g, t_len, weights); }
+  if (metric == ORC_WDDTW) { weights = (double *)malloc(sizeof(double) * n); if (t_len - 2 > 0) orc_weights(p->g, t_len - 2, weights); }
+  double min_dist = INFINITY;
+  for (int64_t i = 0; i < s_len; i++) sb[i] = (S[i] - s_mean) / s_std;
+  orc_inc_window_stats(T, t_len, s_len, mean, std);
+  for (int64_t i = 0; i < t_len - s_len + 1; i++) {
+    for (int64_t j = 0; j < s_len; j++) xb[j] = (T[i + j] - mean[i]) / std[i];
+    double dist;
+    int64_t r = orc_compute_r(s_len, p->r);
+    switch (metric) {
+      case ORC_DTW: case ORC_WDTW:
+        dist = sqrt(dtw_distance(sb, s_len, xb, s_len, r, cost, cost_prev, weights, min_dist * min_dist)); break;
+      case ORC_ADTW:
+        dist = sqrt(adtw_distance(sb, s_len, xb, s_len, r, cost, cost_prev, p->p, min_dist * min_dist)); break;
+      case ORC_DDTW: case ORC_WDDTW:
+        if (s_len < 3) continue;
+        orc_average_slope(sb, s_len, a1); orc_average_slope(xb, s_len, a2);
+        dist = sqrt(dtw_distance(a1, s_len - 2, a2, s_len - 2, orc_compute_r(s_len - 2, p->r), cost, cost_prev, weights,
+                                 min_dist * min_dist));
+        break;
+      case ORC_LCSS:
+        dist = lcss_distance(sb, s_len, xb, s_len, r, p->epsilon, cost, cost_prev, NULL,
+                             isinf(min_dist) ? INFINITY : (double)s_len - min_dist * (double)s_len);
+        break;
+      case ORC_ERP:
+        dist = erp_distance(sb, s_len, xb, s_len, r, p->g, a1, a2, cost, cost_prev, min_dist); break;
+      case ORC_EDR: {
+        double eps = p->epsilon;
+        if (isnan(eps)) eps = dmax(orc_std(sb, s_len), orc_std(xb, s_len)) / 4.0;
+        dist = edr_distance(sb, s_len, xb, s_len, r, eps, cost, cost_prev, min_dist * (double)s_len);
+        break;
+      }
+      case ORC_MSM:
+        dist = msm_distance(sb, s_len, xb, s_len, r, p->c, cost, cost_prev, a1, min_dist); break;
+      case ORC_TWE:
+        dist = twe_distance(sb, s_len, xb, s_len, r, p->penalty, p->stiffness, cost, cost_prev, min_dist); break;
+      default: dist = NAN;
+    }
+    if (dist < min_dist) { min_dist = dist; if (index) *index = i; }
+  }
+  (void)deriv;
+  free(cost); free(cost_prev); free(sb); free(xb); free(a1); free(a2); free(weights); free(mean); free(std);
+  return min_dist;
 }

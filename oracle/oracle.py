@@ -289,14 +289,59 @@ def pairwise_subsequence(metric, subsequences, x, **params):
     p = make_params(metric, **params)
     dist = np.empty((x.shape[0], len(subsequences)))
     idx = np.zeros((x.shape[0], len(subsequences)), dtype=np.int64)
+    eps_auto = metric == "edr" and np.isnan(p.epsilon)
     for k, s in enumerate(subsequences):
         s = np.ascontiguousarray(s, dtype=np.float64)
+        if eps_auto:  # EdrSubsequenceMetric._distance EL:2762-2765: s_std / 4 with the subsequence's own std
+            p.epsilon = _subsequence_mean_std(s)[1] / 4.0
         for i in range(x.shape[0]):
             j = C.c_int64(0)
             dist[i, k] = L.orc_subsequence_distance(METRIC_IDS[metric], C.byref(p), _dp(s), s.shape[0], _dp(x[i]), x.shape[1],
                                                     C.byref(j))
             idx[i, k] = j.value
     return dist, idx
+
+
+def _subsequence_mean_std(s):
+    """ScaledSubsequenceMetric.from_array (_cdistance.pyx:453-467) + `std if std != 0 else 1.0` (:283-298)."""
+    mean, std = np.mean(s), np.std(s)
+    if std <= 1e-13:
+        std = 0.0
+    return float(mean), float(std if std != 0 else 1.0)
+
+
+def pairwise_scaled_subsequence(metric, subsequences, x, **params):
+    """`scaled_<metric>` = ScaledSubsequenceMetricWrap(Metric) (_cdistance.pyx:470-551): (dist, idx), (n_samples, n_subsequences)."""
+    L = lib()
+    L.orc_scaled_subsequence_distance.argtypes = [C.c_int, C.POINTER(Params), C.POINTER(C.c_double), C.c_int64, C.c_double,
+                                                  C.c_double, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_int64)]
+    L.orc_scaled_subsequence_distance.restype = C.c_double
+    x = _arr(x)
+    p = make_params(metric, **params)
+    dist = np.empty((x.shape[0], len(subsequences)))
+    idx = np.zeros((x.shape[0], len(subsequences)), dtype=np.int64)
+    for k, s in enumerate(subsequences):
+        s = np.ascontiguousarray(s, dtype=np.float64)
+        mean, std = _subsequence_mean_std(s)
+        for i in range(x.shape[0]):
+            j = C.c_int64(0)
+            dist[i, k] = L.orc_scaled_subsequence_distance(METRIC_IDS[metric], C.byref(p), _dp(s), s.shape[0], mean, std,
+                                                           _dp(x[i]), x.shape[1], C.byref(j))
+            idx[i, k] = j.value
+    return dist, idx
+
+
+def inc_window_stats(x, m):
+    """(mean, std) of every window of length m of the 1-D series x as ScaledSubsequenceMetricWrap computes them."""
+    L = lib()
+    dp = C.POINTER(C.c_double)
+    L.orc_inc_window_stats.argtypes = [dp, C.c_int64, C.c_int64, dp, dp]
+    L.orc_inc_window_stats.restype = None
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    nw = x.shape[0] - m + 1
+    mean, std = np.empty(nw), np.empty(nw)
+    L.orc_inc_window_stats(_dp(x), x.shape[0], m, _dp(mean), _dp(std))
+    return mean, std
 
 
 def pairwise_scaled_dtw_subsequence(subsequences, x, r=1.0):
