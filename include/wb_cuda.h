@@ -166,27 +166,42 @@ int wb_cuda_dba_epoch(const wb_fitted *fit, int metric, const wb_params *params,
                       const int64_t *member_offsets, const int64_t *members, const double *sample_weight,
                       const double *weights, int do_update, double *means_out, double *dist_out, wb_stats *stats);
 
-/* Subsequence search for the DTW family: for every subsequence k (s[s_offsets[k] .. s_offsets[k+1]),
+/* Subsequence search with the elastic metrics: for every subsequence k (s[s_offsets[k] .. s_offsets[k+1]),
  * length m_k <= T) and sample i, the minimum over the sliding windows w = 0 .. T - m_k of
- * metric(subsequence, x[i][w : w + m_k]) and the FIRST window that attains it.  Replaces
- * `_pairwise_subsequence_distance` / `_paired_subsequence_distance` (_cdistance.pyx:1018-1062) over
- * Dtw / WeightedDtw / AmercingDtw / DerivativeDtw / WeightedDerivativeDtw SubsequenceMetric (_elastic.pyx:2206-2615,
- * dtw_subsequence_distance :622-660, adtw :701-740, ddtw :780-815): band from the subsequence length
- * (_compute_r(m_k, r)), comparison in the squared-cost domain, sqrt of the minimum; wdtw / wddtw weights span the
+ * metric(subsequence, x[i][w : w + m_k]) and the FIRST window that attains it under the reference's scan.  Replaces
+ * `_pairwise_subsequence_distance` / `_paired_subsequence_distance` (_cdistance.pyx:1018-1062) over the elastic
+ * SubsequenceMetric classes of _distance.py:143-178.
+ * paired == 0: out_dist / out_idx are (nx, n_s); paired != 0 (n_s == nx): subsequence i against sample i, (nx).
+ *
+ * scaled == 0, DTW family (Dtw / WeightedDtw / AmercingDtw / DerivativeDtw / WeightedDerivativeDtw SubsequenceMetric,
+ * _elastic.pyx:2206-2615; dtw_subsequence_distance :622-660, adtw :701-740, ddtw :780-815): band from the subsequence
+ * length (_compute_r(m_k, r)), comparison in the squared-cost domain, sqrt of the minimum; wdtw / wddtw weights span the
  * SERIES length (T, T - 2).  The reference abandons windows early against the running minimum, which never changes
  * the result for these metrics; the device evaluates every window (all windows of all samples are the `y` operand of
- * ONE pairwise launch per subsequence, addressed with stride 1).
- * paired == 0: out_dist / out_idx are (nx, n_s); paired != 0 (n_s == nx): subsequence i against sample i, (nx).
- * scaled != 0 (metric WB_DTW): `scaled_dtw`, the UCR-suite search of ScaledDtwSubsequenceMetric (_elastic.pyx:1928-2060,
+ * ONE pairwise launch per subsequence, addressed with stride 1) and takes the first minimum.
+ *
+ * scaled == 0, lcss / erp / edr / msm / twe (Lcss / Erp / Edr / Msm / Twe SubsequenceMetric, _elastic.pyx:2616-3124;
+ * *_subsequence_distance :1186, :1350, :1500, :1650, :1832): here the early abandoning against the running minimum DOES
+ * decide which windows are accepted (row minima are not monotone; lcss compares a similarity with a distance bound,
+ * edr scales the bound with the SERIES length), so the scan is replayed exactly: one DP launch records every window's
+ * distance and the maximum of its row minima, one warp per sample then walks the windows in order.  edr's default epsilon
+ * (params->epsilon NaN) is std / 4 of each subsequence: pass it in s_epsilon (n_s values, computed by the caller with numpy
+ * as ScaledSubsequenceMetric.from_array does, _cdistance.pyx:453-467); s_epsilon is ignored otherwise and may be NULL.
+ *
+ * scaled != 0, metric WB_DTW: `scaled_dtw`, the UCR-suite search of ScaledDtwSubsequenceMetric (_elastic.pyx:1928-2060,
  * scaled_dtw_subsequence_distance :353-482, inner_scaled_dtw_subsequence_distance :263-345): `s` holds the subsequences
  * already z-normalised by the caller ((s - mean) / std with numpy's mean / std, _cdistance.pyx:453-467), every window is
  * normalised with its running mean / std in the reference's summation order, band |i - j| <= _compute_warp_width(m, r)
- * (_elastic.pyx:1917-1921).  The reference's LB_Kim / LB_Keogh cascade and its cumulative-bound abandoning only skip
- * windows that cannot become the minimum; the device evaluates every window exactly. */
+ * (_elastic.pyx:1917-1921); the reference's LB_Kim prefilter is part of the observable result and is replayed.
+ *
+ * scaled != 0, any other metric: `scaled_<metric>` = ScaledSubsequenceMetricWrap(Metric) (_cdistance.pyx:470-551): `s`
+ * z-normalised by the caller as above, every window z-normalised with the reference's running IncStats
+ * (utils/_stats.pyx:45-93), then Metric._eadistance() against the running minimum -- replayed exactly as above (weights
+ * of wdtw / wddtw over T / T - 2 as wrap.reset(X, X) sizes them; edr's default epsilon from the two normalised buffers). */
 int wb_cuda_subsequence(int metric, const wb_params *params,
                         const double *s, const int64_t *s_offsets, int64_t n_s,
                         const double *x, int64_t nx, int64_t T, int64_t x_stride,
-                        int paired, int scaled, double *out_dist, int64_t *out_idx,
+                        int paired, int scaled, const double *s_epsilon, double *out_dist, int64_t *out_idx,
                         const int *devices, int n_devices, wb_stats *stats);
 
 /* Device-resident variant of wb_cuda_pairwise: d_x (nx, Tx), d_y (ny, Ty), d_out (nx, ny) are

@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Measurement of SURVEY 8f-4 (second half) on ONE GPU: subsequence search with the metrics whose scan is replayed
+(lcss / erp / edr / msm / twe and the generic scaled_<metric> wraps), the UNMODIFIED reference (oracle/_ref) timed beside
+it on the box's host cores on a stated, bounded sample of the same workload.  One JSON line per metric.
+
+  python scripts/bench_scan.py [--quick] [--no-ref]
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import wildboar_b200 as wb  # noqa: E402
+
+QUICK = "--quick" in sys.argv
+NO_REF = "--no-ref" in sys.argv
+NCPU = os.cpu_count() or 1
+
+
+def timed(fn, reps=2):
+    fn()
+    best = 1e30
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out = fn()
+        best = min(best, time.perf_counter() - t0)
+    return best, out
+
+
+def main():
+    wb.set_devices([0])
+    wd = None
+    if not NO_REF:
+        from oracle import ref
+        wd = ref.load()
+    n, T, ns, m = (300, 256, 8, 48) if QUICK else (2000, 512, 64, 64)
+    Xs = np.cumsum(np.random.default_rng(8).standard_normal((n, T)), axis=-1)
+    rng = np.random.default_rng(9)
+    shp = [Xs[rng.integers(0, n), o:o + m].copy() for o in rng.integers(0, T - m, ns)]
+    cases = [("msm", {"r": 0.1}), ("twe", {"r": 0.1}), ("erp", {"r": 0.1}), ("lcss", {"r": 0.1}), ("edr", {"r": 0.1}),
+             ("scaled_msm", {"r": 0.1}), ("scaled_twe", {"r": 0.1}), ("scaled_adtw", {"r": 0.1}), ("scaled_ddtw", {"r": 0.1})]
+    for metric, mp in cases:
+        t_ss, (d, i) = timed(lambda: wb.pairwise_subsequence_distance(shp, Xs, metric=metric, metric_params=mp, return_index=True))
+        st = wb.last_stats()
+        row = dict(row="8f-4 pairwise_subsequence_distance (replayed scan)", metric=metric,
+                   shape=f"{ns} subsequences x {m} vs {n} samples x {T}, r={mp['r']}", windows=n * (T - m + 1) * ns,
+                   cells=st["cells"], e2e_ms=round(t_ss * 1e3, 1), kernel_ms=round(st["kernel_ms"], 1),
+                   kernel_gcups=round(st["cells"] / (st["kernel_ms"] * 1e-3) / 1e9, 1), launches=st["launches"], engine=st["engine"],
+                   windows_per_s=round(n * (T - m + 1) * ns / t_ss))
+        if wd is not None:
+            nss, nxs = (4, 48) if QUICK else (8, 128)
+            t_ref, (rd_, ri_) = timed(lambda: wd.pairwise_subsequence_distance(shp[:nss], Xs[:nxs], metric=metric, metric_params=mp,
+                                                                             return_index=True, n_jobs=NCPU), reps=1)
+            row.update(ref_sample=f"{nss} subsequences vs {nxs} samples, n_jobs={NCPU} (early abandoning)", ref_ms=round(t_ref * 1e3, 1),
+                       ref_windows_per_s=round(nss * nxs * (T - m + 1) / t_ref), ref_cores=NCPU,
+                       ref_bit_equal=bool(np.array_equal(rd_, d[:nxs, :nss]) and np.array_equal(ri_, i[:nxs, :nss])))
+        print(json.dumps(row), flush=True)
+
+
+if __name__ == "__main__":
+    main()

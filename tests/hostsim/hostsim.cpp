@@ -82,3 +82,8 @@ extern "C" int hostsim_pair(int engine, int W, int metric, const wb_params* p, c
   if (!known) return 2;
   return rc;
 }
+
+// window statistics of the generic scaled subsequence metrics (metrics.cuh inc_window_stats_one == the body of k_inc_window_stats)
+extern "C" void hostsim_inc_window_stats(const double* x, int64_t T, int64_t m, double* mean, double* stdv) {
+  inc_window_stats_one(x, (int)T, (int)m, mean, stdv);
+}

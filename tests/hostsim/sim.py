@@ -47,3 +47,16 @@ def pair(engine, W, metric_id, params, x, y, ea=0, min_dist_raw=float("inf"), ns
     rc = lib().hostsim_pair(engine, W, metric_id, C.byref(params), x.ctypes.data_as(dp), len(x), y.ctypes.data_as(dp),
                             len(y), ea, min_dist_raw, ns_extra, bs, C.byref(out), C.byref(mm))
     return rc, out.value, mm.value
+
+
+def inc_window_stats(x, m):
+    """(mean, std) of every length-m window of the 1-D series x through the device code path compiled for the host."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    nw = len(x) - m + 1
+    mean, std = np.empty(nw), np.empty(nw)
+    dp = C.POINTER(C.c_double)
+    f = lib().hostsim_inc_window_stats
+    f.argtypes = [dp, C.c_int64, C.c_int64, dp, dp]
+    f.restype = None
+    f(x.ctypes.data_as(dp), len(x), m, mean.ctypes.data_as(dp), std.ctypes.data_as(dp))
+    return mean, std

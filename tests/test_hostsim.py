@@ -93,3 +93,90 @@ def test_strip_abandon_is_safe(oracle):
             assert v == d
         else:
             assert v == d or np.isinf(v)
+
+
+def _replay_first(d, M, kind, scale):
+    """k = 1 replay of k_replay (argmin.cuh): accept iff d < t and not M > T(t); returns (t, index)."""
+    t, idx = np.inf, 0
+    for w in range(len(d)):
+        if not d[w] < t:
+            continue
+        if M is not None:
+            if kind == "ident":
+                T = t
+            elif kind == "lcss":
+                T = np.inf if np.isinf(t) else scale - t * scale
+            elif kind == "scale":
+                T = t * scale
+            else:
+                T = t * t
+            if M[w] > T:
+                continue
+        t, idx = d[w], w
+    return t, idx
+
+
+_SCAN_CASES = [("lcss", {"r": 0.2, "epsilon": 0.6}), ("lcss", {}), ("erp", {"r": 0.1, "g": 0.3}), ("erp", {}),
+               ("edr", {"r": 0.25, "epsilon": 0.5}), ("edr", {}), ("msm", {"r": 0.15, "c": 0.4}), ("msm", {}),
+               ("twe", {"r": 0.2, "penalty": 0.4, "stiffness": 0.05}), ("twe", {})]
+
+
+@pytest.mark.parametrize("metric,mp", _SCAN_CASES)
+def test_subsequence_scan_scheme_matches_oracle(oracle, metric, mp):
+    """The device scheme of subseq_scan_worker (wb_cuda.cu) -- every window's (d, M) from the row-scan engine without
+    abandoning, then the k = 1 replay with the metric's threshold transform -- reproduces the reference's
+    early-abandoning scan for lcss / erp / edr / msm / twe (the oracle is pinned to the reference)."""
+    rng = np.random.default_rng(11)
+    mid = oracle.METRIC_IDS[metric]
+    T = 48
+    X = np.cumsum(rng.standard_normal((4, T)), axis=1)
+    subs = [np.cumsum(rng.standard_normal(m)) for m in (1, 2, 7, 16, 31, 48)]
+    od, oi = oracle.pairwise_subsequence(metric, subs, X, **mp)
+    for k, s in enumerate(subs):
+        m = len(s)
+        kw = dict(mp)
+        if metric == "edr" and "epsilon" not in kw:
+            kw["epsilon"] = oracle._subsequence_mean_std(s)[1] / 4.0
+        p = _params(oracle, metric, **kw)
+        kind, scale = {"lcss": ("lcss", float(m)), "edr": ("scale", float(T))}.get(metric, ("ident", 1.0))
+        for i in range(len(X)):
+            d, M = [], []
+            for w in range(T - m + 1):
+                rc, dv, mv = sim.pair(1, 0, mid, p, s, X[i, w:w + m])
+                assert rc == 0
+                d.append(dv); M.append(mv)
+            t, idx = _replay_first(d, M, kind, scale)
+            assert t == od[i, k] and idx == oi[i, k], (metric, m, i, t, od[i, k], idx, oi[i, k])
+
+
+@pytest.mark.parametrize("metric,mp", _SCAN_CASES + [("adtw", {"r": 0.2, "p": 0.3}), ("ddtw", {"r": 0.3}), ("adtw", {})])
+def test_scaled_subsequence_scan_scheme_matches_oracle(oracle, metric, mp):
+    """Same for scaled_<metric> (ScaledSubsequenceMetricWrap): windows z-normalised with the device's IncStats loop."""
+    rng = np.random.default_rng(12)
+    mid = oracle.METRIC_IDS[metric]
+    T = 40
+    X = np.cumsum(rng.standard_normal((3, T)), axis=1)
+    X[2, 10:22] = X[2, 10]  # constant stretch: windows with zero variance (std -> 1)
+    subs = [np.cumsum(rng.standard_normal(m)) for m in (1, 3, 9, 20, 40)]
+    od, oi = oracle.pairwise_scaled_subsequence(metric, subs, X, **mp)
+    p = _params(oracle, metric, **mp)
+    dtwfam = metric in ("adtw", "ddtw")
+    for k, s in enumerate(subs):
+        m = len(s)
+        mean, std = oracle._subsequence_mean_std(s)
+        sn = (s - mean) / std
+        kind, scale = {"lcss": ("lcss", float(m)), "edr": ("scale", float(m))}.get(metric, ("ident", 1.0))
+        for i in range(len(X)):
+            wm, ws = sim.inc_window_stats(X[i], m)
+            om, os_ = oracle.inc_window_stats(X[i], m)
+            assert np.array_equal(wm, om) and np.array_equal(ws, os_)
+            if metric == "ddtw" and m < 3:
+                assert np.isinf(od[i, k])
+                continue
+            d, M = [], []
+            for w in range(T - m + 1):
+                rc, dv, mv = sim.pair(1, 0, mid, p, sn, (X[i, w:w + m] - wm[w]) / ws[w], ea=1)
+                assert rc == 0
+                d.append(dv); M.append(mv)
+            t, idx = _replay_first(d, None if dtwfam else M, kind, scale)
+            assert t == od[i, k] and idx == oi[i, k], (metric, m, i, t, od[i, k], idx, oi[i, k])

@@ -344,8 +344,10 @@ def test_subsequence_host_logic(wb):
         wb.pairwise_subsequence_distance([np.zeros(11)], x, metric="dtw")
     with pytest.raises(ValueError, match="unsupported metric"):
         wb.pairwise_subsequence_distance([np.zeros(4)], x, metric="euclidean")
-    with pytest.raises(ValueError, match="not accelerated"):
-        wb.pairwise_subsequence_distance([np.zeros(4)], x, metric="msm", scale=True)
+    with pytest.raises(ValueError, match="unsupported metric"):
+        wb.pairwise_subsequence_distance([np.zeros(4)], x, metric="manhattan", scale=True)
+    with pytest.raises(ValueError, match="unsupported metric"):
+        wb.pairwise_subsequence_distance([np.zeros(4)], x, metric="scaled_wlcss")
     with pytest.raises(ValueError, match="at least 3 samples"):
         wb.pairwise_subsequence_distance([np.zeros(2)], x, metric="dtw", scale=True)
     with pytest.raises(ValueError, match="must be the same"):
@@ -477,8 +479,8 @@ def test_scaled_dtw_subsequence_matches_reference_golden(W, next_golden):
     assert np.array_equal(d, g["ssc|paired_dist"]) and np.array_equal(i, g["ssc|paired_idx"])
     with pytest.raises(ValueError, match="at least 3 samples"):
         W.pairwise_subsequence_distance([np.zeros(2)], X, metric="scaled_dtw")
-    with pytest.raises(ValueError, match="not accelerated"):
-        W.pairwise_subsequence_distance([np.zeros(5)], X, metric="scaled_msm")
+    with pytest.raises(ValueError, match="unsupported metric"):
+        W.pairwise_subsequence_distance([np.zeros(5)], X, metric="scaled_euclidean")
 
 
 @pytest.mark.gpu

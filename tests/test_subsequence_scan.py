@@ -1,0 +1,171 @@
+"""SURVEY 8f-4, second half: subsequence search with lcss / erp / edr / msm / twe and the generic scaled_<metric>
+metrics (ScaledSubsequenceMetricWrap), where the reference's early abandoning decides which window is reported.
+
+CPU tests pin the oracle restatement to golden vectors generated from the unmodified reference
+(tests/golden/make_golden_scan.py); `-m gpu` tests compare the CUDA path (public API -> ctypes -> C ABI) with those
+vectors and, at larger sizes, with the oracle -- bit for bit, distances and window indices.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+from make_golden_scan import SC_CASES, SW_CASES  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def scan_golden():
+    with np.load(os.path.join(ROOT, "tests", "golden", "scan_golden.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope="module")
+def W(wb):
+    assert wb.device_count() >= 1, "no CUDA device: the product has no CPU fallback"
+    wb.set_devices([0])
+    return wb
+
+
+def _inputs(g, tag, ci):
+    keep = g[f"{tag}|{ci}|keep"]
+    return g["X"], [g[f"s{k}"] for k in keep]
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU: oracle == reference
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ci", range(len(SC_CASES)))
+def test_oracle_scan_matches_reference_golden(oracle, scan_golden, ci):
+    metric, mp = SC_CASES[ci]
+    X, ss = _inputs(scan_golden, "sc", ci)
+    d, i = oracle.pairwise_subsequence(metric, ss, X, **mp)
+    assert np.array_equal(d, scan_golden[f"sc|{ci}|dist"]) and np.array_equal(i, scan_golden[f"sc|{ci}|idx"])
+
+
+@pytest.mark.parametrize("ci", range(len(SW_CASES)))
+def test_oracle_scaled_wrap_matches_reference_golden(oracle, scan_golden, ci):
+    metric, mp = SW_CASES[ci]
+    X, ss = _inputs(scan_golden, "sw", ci)
+    d, i = oracle.pairwise_scaled_subsequence(metric, ss, X, **mp)
+    assert np.array_equal(d, scan_golden[f"sw|{ci}|dist"]) and np.array_equal(i, scan_golden[f"sw|{ci}|idx"])
+
+
+def test_abandoning_decides_the_result(oracle, scan_golden):
+    """Why the scan has to be replayed: for these metrics the reference's answer is NOT the plain minimum over the windows."""
+    X = scan_golden["X"]
+    differs = 0
+    for ci, (metric, mp) in enumerate(SC_CASES):
+        _, ss = _inputs(scan_golden, "sc", ci)
+        for k, s in enumerate(ss):
+            m = len(s)
+            kw = dict(mp)
+            if metric == "edr" and "epsilon" not in kw:
+                kw["epsilon"] = oracle._subsequence_mean_std(s)[1] / 4.0
+            for i in range(X.shape[0]):
+                wins = np.stack([X[i, w:w + m] for w in range(X.shape[1] - m + 1)])
+                plain = oracle.pairwise(metric, s, wins, **kw)[0].min()
+                differs += plain != scan_golden[f"sc|{ci}|dist"][i, k]
+    assert differs > 0
+
+
+def test_scan_host_logic(wb):
+    x = np.zeros((3, 10))
+    for metric in ("lcss", "erp", "edr", "msm", "twe", "scaled_adtw", "scaled_twe", "scaled_edr"):
+        with pytest.raises(ValueError, match="Invalid subsequnce shape"):
+            wb.pairwise_subsequence_distance([np.zeros(11)], x, metric=metric)
+    with pytest.raises(TypeError):
+        wb.pairwise_subsequence_distance([np.zeros(4)], x, metric="msm", metric_params={"penalty": 1.0})
+    with pytest.raises(ValueError):
+        wb.pairwise_subsequence_distance([np.zeros(4)], x, metric="scaled_lcss", metric_params={"epsilon": -1.0})
+    from wildboar_b200.subsequence import _check_subsequence_metric
+    assert _check_subsequence_metric("msm", True) == ("msm", True)
+    assert _check_subsequence_metric("scaled_twe", False) == ("twe", True)
+    assert _check_subsequence_metric("edr", False) == ("edr", False)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU
+# ---------------------------------------------------------------------------------------------
+def _check_golden(W, g, tag, ci, metric, mp, name):
+    X, ss = _inputs(g, tag, ci)
+    d, i = W.pairwise_subsequence_distance(ss, X, metric=name, metric_params=mp, return_index=True)
+    bad = np.argwhere((d != g[f"{tag}|{ci}|dist"]) | (i != g[f"{tag}|{ci}|idx"]))
+    assert len(bad) == 0, (name, mp, bad[:4], d[tuple(bad[0])], g[f"{tag}|{ci}|dist"][tuple(bad[0])], i[tuple(bad[0])],
+                           g[f"{tag}|{ci}|idx"][tuple(bad[0])])
+    paired = [ss[q % len(ss)] for q in range(X.shape[0])]
+    d, i = W.paired_subsequence_distance(paired, X, metric=name, metric_params=mp, return_index=True)
+    assert np.array_equal(d, g[f"{tag}|{ci}|paired_dist"]) and np.array_equal(i, g[f"{tag}|{ci}|paired_idx"]), (name, mp)
+    assert W.pairwise_subsequence_distance(ss[0], X, metric=name, metric_params=mp).shape == (X.shape[0],)
+    assert isinstance(W.pairwise_subsequence_distance(ss[0], X[0], metric=name, metric_params=mp), float)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ci", range(len(SC_CASES)))
+def test_scan_matches_reference_golden(W, scan_golden, ci):
+    metric, mp = SC_CASES[ci]
+    _check_golden(W, scan_golden, "sc", ci, metric, mp, metric)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ci", range(len(SW_CASES)))
+def test_scaled_wrap_matches_reference_golden(W, scan_golden, ci):
+    metric, mp = SW_CASES[ci]
+    _check_golden(W, scan_golden, "sw", ci, metric, mp, "scaled_" + metric)
+    if ci == 0:  # scale=True selects the scaled metric like the reference's _infer_scaled_metric
+        X, ss = _inputs(scan_golden, "sw", ci)
+        d = W.pairwise_subsequence_distance(ss, X, metric=metric, scale=True, metric_params=mp)
+        assert np.array_equal(d, scan_golden[f"sw|{ci}|dist"])
+
+
+@pytest.mark.gpu
+def test_scan_larger_matches_oracle(W, oracle):
+    """Longer series (several warp tasks per sample, several samples per replay block), a repeated motif (first window wins),
+    more than one pass over the samples for the materialised scaled windows, two devices if present."""
+    rng = np.random.default_rng(23)
+    X = np.cumsum(rng.standard_normal((37, 300)), axis=1)
+    motif = X[3, 50:90].copy()
+    X[3, 200:240] = motif
+    subs = [motif, np.cumsum(rng.standard_normal(100)), X[11, 260:300].copy(), np.cumsum(rng.standard_normal(9))]
+    for metric, mp in (("lcss", {"r": 0.1, "epsilon": 0.8}), ("erp", {"r": 0.1}), ("edr", {"r": 0.1}), ("msm", {"r": 0.1}),
+                       ("twe", {"r": 0.1})):
+        d, i = W.pairwise_subsequence_distance(subs, X, metric=metric, metric_params=mp, return_index=True)
+        od, oi = oracle.pairwise_subsequence(metric, subs, X, **mp)
+        assert np.array_equal(d, od) and np.array_equal(i, oi), metric
+        if metric != "lcss":
+            assert d[3, 0] == 0.0 and i[3, 0] == 50 and d[11, 2] == 0.0 and i[11, 2] == 260
+    os.environ["WILDBOAR_CUDA_SCAN_WINDOW_BUDGET"] = str(300 * 100 * 5)  # forces several passes over the 37 samples
+    try:
+        for metric, mp in (("adtw", {"r": 0.1, "p": 0.2}), ("wdtw", {"r": 0.1}), ("ddtw", {"r": 0.1}), ("wddtw", {"r": 0.2}),
+                           ("lcss", {"r": 0.1, "epsilon": 0.3}), ("erp", {"r": 0.1}), ("edr", {"r": 0.1}), ("msm", {"r": 0.1}),
+                           ("twe", {"r": 0.1})):
+            d, i = W.pairwise_subsequence_distance(subs, X, metric="scaled_" + metric, metric_params=mp, return_index=True)
+            od, oi = oracle.pairwise_scaled_subsequence(metric, subs, X, **mp)
+            assert np.array_equal(d, od) and np.array_equal(i, oi), metric
+    finally:
+        del os.environ["WILDBOAR_CUDA_SCAN_WINDOW_BUDGET"]
+    if W.device_count() >= 2:
+        W.set_devices([0, 1])
+        try:
+            d2, i2 = W.pairwise_subsequence_distance(subs, X, metric="scaled_msm", metric_params={"r": 0.1}, return_index=True)
+        finally:
+            W.set_devices([0])
+        od, oi = oracle.pairwise_scaled_subsequence("msm", subs, X, r=0.1)
+        assert np.array_equal(d2, od) and np.array_equal(i2, oi)
+
+
+@pytest.mark.gpu
+def test_scan_negative_adtw_penalty(W, oracle):
+    """adtw with a negative penalty: row minima may decrease, so the abandoning of the scan matters here too."""
+    rng = np.random.default_rng(5)
+    X = np.cumsum(rng.standard_normal((6, 80)), axis=1)
+    subs = [np.cumsum(rng.standard_normal(m)) for m in (10, 25)]
+    mp = {"r": 0.3, "p": -0.05}
+    d, i = W.pairwise_subsequence_distance(subs, X, metric="adtw", metric_params=mp, return_index=True)
+    od, oi = oracle.pairwise_subsequence("adtw", subs, X, **mp)
+    assert np.array_equal(d, od, equal_nan=True) and np.array_equal(i, oi)
+    d, i = W.pairwise_subsequence_distance(subs, X, metric="scaled_adtw", metric_params=mp, return_index=True)
+    od, oi = oracle.pairwise_scaled_subsequence("adtw", subs, X, **mp)
+    assert np.array_equal(d, od, equal_nan=True) and np.array_equal(i, oi)

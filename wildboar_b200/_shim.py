@@ -78,7 +78,7 @@ def lib():
                 L.wb_cuda_dtw_paths.argtypes = [_DP, i64, i64, i64, _DP, i64, i64, i64, _IP, _IP, i64, C.c_double, _DP, I32P,
                                                 I32P, _DP, _DP, ci, SP]
                 L.wb_cuda_dba_epoch.argtypes = [C.c_void_p, ci, PP, _DP, i64, i64, _IP, _IP, _DP, _DP, ci, _DP, _DP, SP]
-                L.wb_cuda_subsequence.argtypes = [ci, PP, _DP, _IP, i64, _DP, i64, i64, i64, ci, ci, _DP, _IP, DV, ci, SP]
+                L.wb_cuda_subsequence.argtypes = [ci, PP, _DP, _IP, i64, _DP, i64, i64, i64, ci, ci, _DP, _DP, _IP, DV, ci, SP]
                 L.wb_cuda_argmin.argtypes = [ci, PP, _DP, i64, i64, i64, _DP, i64, i64, i64, i64, _DP, ci, _IP, _DP,
                                              DV, ci, SP]
                 L.wb_cuda_pairwise_dev.argtypes = [ci, PP, C.c_void_p, i64, i64, C.c_void_p, i64, i64, C.c_void_p,
@@ -402,9 +402,10 @@ def dba_epoch(fitted, metric_id, params, means, offsets, members, sample_weight=
     return out, dist
 
 
-def subsequence(metric_id, params, subsequences, x, paired=False, scaled=False):
+def subsequence(metric_id, params, subsequences, x, paired=False, scaled=False, s_epsilon=None):
     """Minimum sliding-window distance and first best window of every (sample, subsequence) pair
-    (wb_cuda_subsequence): (dist, idx) of shape (nx, n_s) or, paired, (nx,)."""
+    (wb_cuda_subsequence): (dist, idx) of shape (nx, n_s) or, paired, (nx,).  s_epsilon: edr's per-subsequence default
+    epsilon (std / 4) or None."""
     apply_engine_override(params)
     params.precision = 0
     x, xp, nx, T, xs = _rows(x)
@@ -418,8 +419,14 @@ def subsequence(metric_id, params, subsequences, x, paired=False, scaled=False):
     st = WbStats()
     cells = float(nx) * T * sum(_est_cells(1, int(m), int(m), params.r) for m in lens) / (nx if paired else 1)
     dv, nd = _dev_array(_resolve_devices(cells))
+    eps = None
+    if s_epsilon is not None:
+        eps = np.ascontiguousarray(s_epsilon, dtype=np.float64)
+        if eps.shape != (len(subsequences),):
+            raise ValueError("s_epsilon needs one value per subsequence")
     _check(lib().wb_cuda_subsequence(metric_id, C.byref(params), flat.ctypes.data_as(_DP), offsets.ctypes.data_as(_IP),
-                                     len(subsequences), xp, nx, T, xs, 1 if paired else 0, 1 if scaled else 0, dist.ctypes.data_as(_DP),
+                                     len(subsequences), xp, nx, T, xs, 1 if paired else 0, 1 if scaled else 0,
+                                     eps.ctypes.data_as(_DP) if eps is not None else None, dist.ctypes.data_as(_DP),
                                      idx.ctypes.data_as(_IP), dv, nd, C.byref(st)))
     _tls.stats = st.as_dict()
     return dist, idx.astype(np.intp, copy=False)

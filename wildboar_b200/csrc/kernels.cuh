@@ -210,11 +210,12 @@ __global__ void k_to_float(const double* __restrict__ src, long long n, float* _
 
 // kind 0: erp gap sum  sum_t |x[t] - g| (EL:1295-1303, sequential order)
 // kind 1: std of the series (utils/_stats.pyx:22-42: sequential sums, threshold 1e-13)
+// stride: elements between consecutive series (T for dense rows; 1 = every sliding window of a flat buffer)
 __global__ void k_series_stat(const double* __restrict__ x, long long n, int T, int kind, double g,
-                              double* __restrict__ out) {
+                              double* __restrict__ out, long long stride) {
   const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
-  const double* p = x + s * T;
+  const double* p = x + s * stride;
   if (kind == 0) {
     double acc = 0;
     for (int t = 0; t < T; ++t) acc += fabs(p[t] - g);
@@ -282,13 +283,38 @@ __global__ void k_ucr_kim(const double* __restrict__ x, long long n, int T, int 
   lb[i * T + w] = v;
 }
 
-// scaled subsequence search: (raw minimum, window) of the replayed scan -> (sqrt, index)
+// subsequence search: (minimum, window) of the replayed scan -> (sqrt when the scan ran in the squared-cost domain, index)
 __global__ void k_finish_scan(const double* __restrict__ hval, const long long* __restrict__ hidx, long long n,
-                              double* __restrict__ out_dist, long long* __restrict__ out_idx, long long ld) {
+                              double* __restrict__ out_dist, long long* __restrict__ out_idx, long long ld, int apply_sqrt) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  out_dist[i * ld] = sqrt(hval[i]);
+  out_dist[i * ld] = apply_sqrt ? sqrt(hval[i]) : hval[i];
   out_idx[i * ld] = hidx[i];
+}
+
+// ---- generic scaled subsequence metrics (ScaledSubsequenceMetricWrap, CD:470-551) ----
+// Window statistics with the reference's IncStats (utils/_stats.pyx:45-93: Welford add / remove in scan order, variance
+// below 1e-13 -> 0 -> std 1).  mean[i * nw + w], stdv[i * nw + w], nw = T - m + 1; one thread per sample.
+__global__ void k_inc_window_stats(const double* __restrict__ x, long long n, int T, int m, double* __restrict__ mean,
+                                   double* __restrict__ stdv) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long nw = T - m + 1;
+  inc_window_stats_one(x + i * T, T, m, mean + i * nw, stdv + i * nw);
+}
+
+// out[(i * nw + w) * m + j] = (x[i * T + w + j] - mean) / std: the z-normalised windows as dense rows (CD:526-527)
+__global__ void k_normalise_windows(const double* __restrict__ x, long long n, int T, int m, const double* __restrict__ mean,
+                                    const double* __restrict__ stdv, double* __restrict__ out) {
+  const int nw = T - m + 1;
+  const long long total = n * (long long)nw * m;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long win = e / m;
+    const int j = (int)(e - win * m);
+    const long long i = win / nw;
+    const int w = (int)(win - i * nw);
+    out[e] = (x[i * T + w + j] - mean[win]) / stdv[win];
+  }
 }
 
 // ---- subsequence search: first minimum over the windows of every sample (EL:622-660: `dist < min_dist`, strict) ----

@@ -165,6 +165,36 @@ struct ScaledDtwPolicy : DtwPolicy<false, false, double> {
   WB_HD Col col(int, double yj, double) const { Col c; c.yj = (yj - mean) / stdv; return c; }
 };
 
+// Window statistics of the generic scaled subsequence metrics (ScaledSubsequenceMetricWrap._distance, CD:505-531) with the
+// reference's IncStats (utils/_stats.pyx:45-93): Welford add of the newest sample, mean / variance of the window
+// (variance below 1e-13 -> 0 -> std 1; fewer than two samples -> std 1), Welford removal of the oldest sample -- in scan
+// order, so every rounding matches.  mean[w], stdv[w] for the windows w = 0 .. T - m of one series p[0 .. T).
+WB_HD void inc_window_stats_one(const double* p, int T, int m, double* mean, double* stdv) {
+  double mu = 0.0, ns = 0.0, ss = 0.0;
+  for (int t = 0; t < T; ++t) {
+    const double v = p[t];
+    ns += 1.0;
+    const double next_m = mu + (v - mu) / ns;
+    ss += (v - mu) * (v - next_m);
+    mu = next_m;
+    if (t >= m - 1) {
+      const int w = t - (m - 1);
+      double var = 0.0;
+      if (!(ns <= 1)) { var = ss / ns; if (var < 1e-13) var = 0.0; }
+      mean[w] = mu;
+      stdv[w] = var == 0.0 ? 1.0 : sqrt(var);
+      const double old = p[w];
+      if (ns == 1.0) { ns = 0.0; mu = 0.0; ss = 0.0; }
+      else {
+        const double old_m = (ns * mu - old) / (ns - 1.0);
+        ss -= (old - mu) * (old - old_m);
+        mu = old_m;
+        ns -= 1.0;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // LCSS / WLCSS.  EL:1118-1183; result 1 - s / min(Tx,Ty).
 // ------------------------------------------------------------------------------------------

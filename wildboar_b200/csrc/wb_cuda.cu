@@ -291,11 +291,11 @@ static int prepare_operands(Workspace& ws, DpCall& c) {
     const int kind = c.metric == M_ERP ? 0 : 1;
     double *sx = nullptr, *sy = nullptr;
     if (ws.alloc(&sx, (size_t)c.nx)) return 1;
-    k_series_stat<<<(unsigned)((c.nx + 127) / 128), 128, 0, st>>>(c.px, c.nx, c.ptx, kind, c.p.g, sx);
+    k_series_stat<<<(unsigned)((c.nx + 127) / 128), 128, 0, st>>>(c.px, c.nx, c.ptx, kind, c.p.g, sx, c.ptx);
     if (c.py == c.px && c.ny == c.nx && c.pty == c.ptx) sy = sx;
     else {
       if (ws.alloc(&sy, (size_t)c.ny)) return 1;
-      k_series_stat<<<(unsigned)((c.ny + 127) / 128), 128, 0, st>>>(c.py, c.ny, c.pty, kind, c.p.g, sy);
+      k_series_stat<<<(unsigned)((c.ny + 127) / 128), 128, 0, st>>>(c.py, c.ny, c.pty, kind, c.p.g, sy, c.pty);
     }
     WB_CK(cudaGetLastError());
     c.sx = sx; c.sy = sy;
@@ -995,7 +995,8 @@ struct SubseqJob {
   const double* s; const int64_t* soff; int64_t ns;   // subsequences, concatenated
   const double* x; int64_t nx, T, xs;
   int paired;
-  int scaled;                                          // 1: scaled_dtw (UCR suite): s is already z-normalised
+  int scaled;                                          // 1: scaled_<metric>: s is already z-normalised (dtw: UCR suite)
+  const double* s_eps;                                 // edr, unscaled: epsilon per subsequence (or nullptr)
   double* out_dist; int64_t* out_idx;                  // (nx, ns) or, paired, (nx)
 };
 
@@ -1109,7 +1110,7 @@ static int subseq_worker(const SubseqJob& J, int dev, int64_t lo, int64_t hi, wb
           ra.d = draw; ra.m = nullptr; ra.lb = dkim; ra.ld = Tp; ra.nq = nr; ra.c0 = 0; ra.ncols = nw;
           ra.k = 1; ra.kind = TK_NONE; ra.scale = 1.0; ra.tau = tau; ra.hidx = hidx; ra.hval = hval; ra.hn = hn;
           k_replay<<<(unsigned)std::max<long long>(1, std::min<long long>((nr + 3) / 4, 148 * 16)), 128, 0, st>>>(ra);
-          k_finish_scan<<<(unsigned)((nr + 127) / 128), 128, 0, st>>>(hval, hidx, nr, od, oi, J.paired ? 1 : J.ns);
+          k_finish_scan<<<(unsigned)((nr + 127) / 128), 128, 0, st>>>(hval, hidx, nr, od, oi, J.paired ? 1 : J.ns, 1);
           WB_CK(cudaGetLastError());
           stats.launches += 4;
           continue;
@@ -1121,6 +1122,161 @@ static int subseq_worker(const SubseqJob& J, int dev, int64_t lo, int64_t hi, wb
       if (rc) break;
       kt.stop();
       // gather: pairwise rows are contiguous (rows, ns); paired entries are contiguous (rows)
+      double* hd = J.paired ? J.out_dist + lo : J.out_dist + lo * J.ns;
+      int64_t* hi_ = J.paired ? J.out_idx + lo : J.out_idx + lo * J.ns;
+      if (cudaMemcpyAsync(hd, ddist, sizeof(double) * nout, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          cudaMemcpyAsync(hi_, didx, sizeof(long long) * nout, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          cudaStreamSynchronize(st) != cudaSuccess) { set_err("device-to-host copy of the subsequence distances failed"); rc = 1; break; }
+      stats.kernel_ms = kt.ms();
+    } while (0);
+    total.stop();
+    if (!rc) { cudaStreamSynchronize(st); stats.total_ms = total.ms(); }
+  }
+  cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  if (st_out) *st_out = stats;
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// Subsequence search as an exact replay of the reference's scan (second half):
+//   * lcss / erp / edr / msm / twe SubsequenceMetric (EL:2616-3124; *_subsequence_distance EL:1186, 1350, 1500, 1650, 1832):
+//     every window's *_distance() is early-abandoned against the running minimum, and for these metrics the abandoning
+//     decides which windows are accepted (row minima are not monotone);
+//   * scaled_<metric> = ScaledSubsequenceMetricWrap(Metric) (CD:470-551) for adtw, wdtw, ddtw, wddtw, lcss, erp, edr, msm,
+//     twe: windows z-normalised with the running IncStats, then Metric._eadistance() against the running minimum.
+// Device scheme (the one argmin uses, argmin.cuh): ONE DP launch per subsequence evaluates all windows of all samples of
+// the block without abandoning and records, per window, the distance d and M = max over the checked rows of the row
+// minimum; k_replay (one warp per sample) then walks the windows in order with the exact rule "accept iff d < t and
+// not M > T(t)" (T = the metric's threshold transform).  Unscaled windows are addressed in place (stride 1); scaled
+// windows are materialised z-normalised as dense rows, a bounded number of samples at a time.
+// ------------------------------------------------------------------------------------------
+static bool subseq_uses_scan(const SubseqJob& J) {
+  if (J.scaled) return J.metric != M_DTW;
+  return !is_dtw_family(J.metric) || (J.metric == M_ADTW && J.p.p < 0);
+}
+
+static int subseq_scan_worker(const SubseqJob& J, int dev, int64_t lo, int64_t hi, wb_stats* st_out) {
+  DeviceInfo di; cudaStream_t st;
+  if (begin_single_device(dev, &di, &st)) return 1;
+  int rc = 0;
+  wb_stats stats; memset(&stats, 0, sizeof stats);
+  {
+    Workspace ws(st);
+    Timer total(st), kt(st);
+    total.start();
+    const int64_t rows = hi - lo, T = J.T;
+    const bool dtwfam = is_dtw_family(J.metric);
+    const bool deriv = is_derivative(J.metric);
+    const bool want_m = !dtwfam || (J.metric == M_ADTW && J.p.p < 0);
+    do {
+      double *dx = nullptr, *ds = nullptr, *ddist = nullptr, *tau = nullptr, *hval = nullptr;
+      long long *didx = nullptr, *hidx = nullptr; int* hn = nullptr;
+      if ((rc = ws.alloc(&dx, (size_t)rows * T)) || (rc = h2d_rows(dx, J.x + lo * J.xs, rows, T, J.xs, st))) break;
+      const int64_t stot = J.soff[J.ns];
+      if ((rc = ws.alloc(&ds, (size_t)std::max<int64_t>(stot, 1)))) break;
+      WB_CK(cudaMemcpyAsync(ds, J.s, sizeof(double) * stot, cudaMemcpyHostToDevice, st));
+      // tables over the SERIES length: wdtw / wddtw weights (wrap.reset(X, X): EL:3334-3341 T, EL:3415-3428 T - 2, libm exp);
+      // twe's 2 * stiffness * |i - j| does not depend on the length
+      const double *dw = nullptr, *dtw = nullptr;
+      if (J.metric == M_WDTW || J.metric == M_WDDTW || J.metric == M_TWE) {
+        const int64_t tn = J.metric == M_TWE ? T + 1 : (deriv ? T - 2 : T);
+        ws.host_keep.push_back(J.metric == M_TWE ? make_tw(J.p.stiffness, tn) : make_weights(J.p.g, tn));
+        std::vector<double>& h = ws.host_keep.back();
+        double* d = nullptr;
+        if ((rc = ws.alloc(&d, h.size()))) break;
+        WB_CK(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        (J.metric == M_TWE ? dtw : dw) = d + table_center(tn);
+      }
+      const int64_t nout = J.paired ? rows : rows * J.ns;
+      if ((rc = ws.alloc(&ddist, (size_t)nout)) || (rc = ws.alloc(&didx, (size_t)nout)) || (rc = ws.alloc(&tau, (size_t)rows)) ||
+          (rc = ws.alloc(&hval, (size_t)rows)) || (rc = ws.alloc(&hidx, (size_t)rows)) || (rc = ws.alloc(&hn, (size_t)rows))) break;
+      WB_CK(cudaMemsetAsync(ddist, 0, sizeof(double) * nout, st));
+      WB_CK(cudaMemsetAsync(didx, 0, sizeof(long long) * nout, st));
+      kt.start();
+      for (int64_t k = 0; k < J.ns && !rc; ++k) {
+        const int64_t m = J.soff[k + 1] - J.soff[k];
+        const int64_t nw = T - m + 1;  // windows per sample
+        if (J.paired && (k < lo || k >= hi)) continue;
+        const int64_t b0 = J.paired ? k - lo : 0, bn = J.paired ? 1 : rows;
+        // replay rule of the metric: T(t) handed to the DP by *_subsequence_distance (unscaled) / _eadistance (scaled)
+        int kind = TK_IDENT; double scale = 1.0;
+        if (dtwfam) kind = J.scaled ? TK_SQUARE : TK_IDENT;  // unscaled adtw scans in the squared-cost domain (EL:701-740)
+        else if (J.metric == M_LCSS) { kind = TK_LCSS; scale = (double)m; }                      // EL:1213-1215, 3526-3528
+        else if (J.metric == M_EDR) { kind = TK_SCALE; scale = (double)(J.scaled ? m : T); }     // EL:3875 / EL:1523 (series length)
+        // samples per pass: the materialised windows of the scaled metrics stay below ~256 MB
+        int64_t step = bn;
+        if (J.scaled) {
+          int64_t budget = (int64_t)32 << 20;  // doubles
+          if (const char* e = getenv("WILDBOAR_CUDA_SCAN_WINDOW_BUDGET")) { const long long v = atoll(e); if (v > 0) budget = v; }  // test knob
+          step = std::max<int64_t>(1, std::min<int64_t>(bn, budget / std::max<int64_t>(nw * m, 1)));
+        }
+        for (int64_t q0 = 0; q0 < bn && !rc; q0 += step) {
+          const int64_t r0 = b0 + q0, nr = std::min(step, bn - q0);
+          double* od = J.paired ? ddist + r0 : ddist + r0 * J.ns + k;
+          long long* oi = J.paired ? didx + r0 : didx + r0 * J.ns + k;
+          const long long ldo = J.paired ? 1 : J.ns;
+          k_fill<<<64, 256, 0, st>>>(tau, nr, WB_INF);
+          k_fill<<<64, 256, 0, st>>>(hval, nr, WB_INF);
+          WB_CK(cudaMemsetAsync(hidx, 0, sizeof(long long) * nr, st));
+          WB_CK(cudaMemsetAsync(hn, 0, sizeof(int) * nr, st));
+          if (deriv && m < 3) {
+            // EL:3297-3298: _eadistance() accepts nothing -> the minimum stays +inf (index left at 0)
+            k_finish_scan<<<(unsigned)((nr + 127) / 128), 128, 0, st>>>(hval, hidx, nr, od, oi, ldo, 0);
+            WB_CK(cudaGetLastError());
+            continue;
+          }
+          Workspace it(st);  // buffers of this pass (returned to the pool, stream-ordered, at the end of the pass)
+          DpCall c; memset(&c, 0, sizeof c);
+          c.metric = J.metric; c.p = J.p; c.mode = PM_PAIRWISE;
+          if (J.metric == M_EDR && !J.scaled && J.s_eps) c.p.epsilon = J.s_eps[k];
+          long long ld;
+          if (J.scaled) {
+            double *mean = nullptr, *stdv = nullptr, *wn = nullptr;
+            if ((rc = it.alloc(&mean, (size_t)(nr * nw))) || (rc = it.alloc(&stdv, (size_t)(nr * nw))) ||
+                (rc = it.alloc(&wn, (size_t)(nr * nw * m)))) break;
+            k_inc_window_stats<<<(unsigned)((nr + 63) / 64), 64, 0, st>>>(dx + r0 * T, nr, (int)T, (int)m, mean, stdv);
+            k_normalise_windows<<<148 * 8, 256, 0, st>>>(dx + r0 * T, nr, (int)T, (int)m, mean, stdv, wn);
+            WB_CK(cudaGetLastError());
+            stats.launches += 2;
+            c.x = ds + J.soff[k]; c.nx = 1; c.Tx = (int)m;
+            c.y = wn; c.ny = nr * nw; c.Ty = (int)m;
+            c.ea = 1;  // _eadistance: ddtw band from the derivative length (EL:3308)
+            if ((rc = prepare_operands(it, c))) break;
+            if (dw) c.tab.weights = dw;
+            ld = nw;
+          } else {
+            c.px = ds + J.soff[k]; c.nx = 1; c.ptx = (int)m;
+            c.py = dx + r0 * T; c.pty = (int)m; c.ys = 1; c.ny = nr * T - m + 1;
+            c.R = (int)compute_r(m, J.p.r);
+            c.tab.tw = dtw;
+            c.raw = dtwfam ? 1 : 0;
+            if (J.metric == M_ERP) {
+              double *sx = nullptr, *sy = nullptr;
+              if ((rc = it.alloc(&sx, 1)) || (rc = it.alloc(&sy, (size_t)c.ny))) break;
+              k_series_stat<<<1, 32, 0, st>>>(c.px, 1, (int)m, 0, J.p.g, sx, m);
+              k_series_stat<<<(unsigned)((c.ny + 127) / 128), 128, 0, st>>>(c.py, c.ny, (int)m, 0, J.p.g, sy, 1);
+              WB_CK(cudaGetLastError());
+              stats.launches += 2;
+              c.sx = sx; c.sy = sy;
+            }
+            ld = T;
+          }
+          double *draw = nullptr, *mraw = nullptr;
+          if ((rc = it.alloc(&draw, (size_t)(nr * ld))) || (want_m && (rc = it.alloc(&mraw, (size_t)(nr * ld))))) break;
+          if ((rc = launch_dp(it, di, c, 0, 1, 0, c.ny, draw, c.ny, mraw, nullptr, &stats))) break;
+          ReplayArgs ra;
+          ra.d = draw; ra.m = mraw; ra.lb = nullptr; ra.ld = ld; ra.nq = nr; ra.c0 = 0; ra.ncols = nw;
+          ra.k = 1; ra.kind = kind; ra.scale = scale; ra.tau = tau; ra.hidx = hidx; ra.hval = hval; ra.hn = hn;
+          k_replay<<<(unsigned)std::max<long long>(1, std::min<long long>((nr + 3) / 4, 148 * 16)), 128, 0, st>>>(ra);
+          k_finish_scan<<<(unsigned)((nr + 127) / 128), 128, 0, st>>>(hval, hidx, nr, od, oi, ldo, (!J.scaled && dtwfam) ? 1 : 0);
+          WB_CK(cudaGetLastError());
+          stats.launches += 2;
+          for (auto& v : it.host_keep) ws.host_keep.push_back(std::move(v));  // staging of async copies outlives the pass
+        }
+      }
+      if (rc) break;
+      kt.stop();
       double* hd = J.paired ? J.out_dist + lo : J.out_dist + lo * J.ns;
       int64_t* hi_ = J.paired ? J.out_idx + lo : J.out_idx + lo * J.ns;
       if (cudaMemcpyAsync(hd, ddist, sizeof(double) * nout, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
@@ -1152,11 +1308,12 @@ static int run_subsequence(const SubseqJob& J, const int* devices, int n_devices
   std::vector<wb_stats> sts((size_t)G);
   std::vector<int> rcs((size_t)G, 0);
   std::vector<std::string> errs((size_t)G);
-  if (G == 1) { rcs[0] = subseq_worker(J, devs[0], off[0], off[1], &sts[0]); errs[0] = g_err; }
+  const auto worker = subseq_uses_scan(J) ? subseq_scan_worker : subseq_worker;
+  if (G == 1) { rcs[0] = worker(J, devs[0], off[0], off[1], &sts[0]); errs[0] = g_err; }
   else {
     std::vector<std::thread> th;
     for (int b = 0; b < G; ++b)
-      th.emplace_back([&, b]() { rcs[(size_t)b] = subseq_worker(J, devs[(size_t)b], off[(size_t)b], off[(size_t)b + 1], &sts[(size_t)b]); errs[(size_t)b] = g_err; });
+      th.emplace_back([&, b]() { rcs[(size_t)b] = worker(J, devs[(size_t)b], off[(size_t)b], off[(size_t)b + 1], &sts[(size_t)b]); errs[(size_t)b] = g_err; });
     for (auto& t : th) t.join();
   }
   for (int b = 0; b < G; ++b) if (rcs[(size_t)b]) { set_err(errs[(size_t)b]); return rcs[(size_t)b]; }
@@ -1380,24 +1537,32 @@ int wb_cuda_dba_epoch(const wb_fitted* fit, int metric, const wb_params* params,
 }
 
 int wb_cuda_subsequence(int metric, const wb_params* params, const double* s, const int64_t* s_offsets, int64_t n_s,
-                        const double* x, int64_t nx, int64_t T, int64_t x_stride, int paired, int scaled, double* out_dist,
-                        int64_t* out_idx, const int* devices, int n_devices, wb_stats* stats) {
+                        const double* x, int64_t nx, int64_t T, int64_t x_stride, int paired, int scaled,
+                        const double* s_epsilon, double* out_dist, int64_t* out_idx, const int* devices, int n_devices,
+                        wb_stats* stats) {
   if (check_common(metric, params, x, nx, T)) return 1;
   if (!s || !s_offsets || !out_dist || !out_idx) { set_err("null argument"); return 1; }
-  if (!is_dtw_family(metric)) { set_err("subsequence search is implemented for the DTW family (dtw, wdtw, adtw, ddtw, wddtw)"); return 1; }
+  if (metric == M_WLCSS) { set_err("wlcss has no subsequence metric in the reference (_distance.py:143-178)"); return 1; }
   if (params->precision != 0) { set_err("subsequence search runs in fp64"); return 1; }
   if (n_s < 1 || s_offsets[0] != 0) { set_err("empty input"); return 1; }
   if (paired && n_s != nx) { set_err("paired subsequence search needs one subsequence per sample"); return 1; }
-  if (scaled && metric != M_DTW) { set_err("the scaled (z-normalised) subsequence search is implemented for dtw"); return 1; }
-  if (scaled) for (int64_t k = 0; k < n_s; ++k)
+  if (scaled && metric == M_DTW) for (int64_t k = 0; k < n_s; ++k)
     if (s_offsets[k + 1] - s_offsets[k] < 3) { set_err("scaled_dtw needs subsequences of at least 3 samples (the reference's LB_Kim reads S[1], S[2])"); return 1; }
   for (int64_t k = 0; k < n_s; ++k) {
     const int64_t m = s_offsets[k + 1] - s_offsets[k];
     if (m < 1 || m > T) { set_err("every subsequence needs 1 <= length <= n_timestep"); return 1; }
   }
+  if (metric == M_EDR && !scaled) {
+    // EdrSubsequenceMetric._distance (EL:2762-2765): the default epsilon is s_std / 4 of each subsequence, which the caller
+    // computes with numpy exactly as ScaledSubsequenceMetric.from_array does (CD:453-467)
+    if (std::isnan(params->epsilon) && !s_epsilon) { set_err("edr subsequence search with the default epsilon needs s_epsilon (std / 4 per subsequence)"); return 1; }
+    if (s_epsilon) for (int64_t k = 0; k < n_s; ++k)
+      if (!(s_epsilon[k] > 0.0)) { set_err("s_epsilon must be positive"); return 1; }
+  }
   SubseqJob J;
   J.metric = metric; J.p = *params; J.s = s; J.soff = s_offsets; J.ns = n_s; J.x = x; J.nx = nx; J.T = T; J.xs = x_stride;
-  J.paired = paired ? 1 : 0; J.scaled = scaled ? 1 : 0; J.out_dist = out_dist; J.out_idx = out_idx;
+  J.paired = paired ? 1 : 0; J.scaled = scaled ? 1 : 0; J.s_eps = (metric == M_EDR && !scaled) ? s_epsilon : nullptr;
+  J.out_dist = out_dist; J.out_idx = out_idx;
   return run_subsequence(J, devices, n_devices, stats);
 }
 

@@ -1,15 +1,18 @@
-"""Subsequence search with the DTW-family metrics on the CUDA path.
+"""Subsequence search with the elastic metrics on the CUDA path.
 
 Mirrors ``wildboar.distance.pairwise_subsequence_distance`` and ``paired_subsequence_distance``
-(reference: src/wildboar/distance/_distance.py:543-636, 639-729) for ``metric`` in {dtw, wdtw, adtw, ddtw, wddtw}
-with ``scale=False`` and for ``scaled_dtw`` (= ``metric="dtw", scale=True``: the z-normalised UCR-suite search):
-same arguments, return shapes (``_format_return``), index of the FIRST best window.
+(reference: src/wildboar/distance/_distance.py:543-636, 639-729) for every ELASTIC entry of the reference's
+``_SUBSEQUENCE_METRICS`` (_distance.py:143-178): ``dtw, wdtw, adtw, ddtw, wddtw, lcss, erp, edr, msm, twe`` and their
+``scaled_`` forms (``scale=True``; ``scaled_dtw`` is the UCR-suite search, the others ScaledSubsequenceMetricWrap):
+same arguments, return shapes (``_format_return``), index of the first best window under the reference's scan.
 
 B200-first: instead of one early-abandoning scan per (sample, subsequence) pair, all sliding windows of all
-samples are the second operand of one pairwise DP launch per subsequence (windows addressed with stride 1, so a
-warp's 32 consecutive windows read consecutive addresses), followed by a first-minimum reduction per sample.
-``scaled_dtw`` additionally replays the reference's scan exactly (its LB_Kim prefilter is not a valid bound and decides
-which window wins).  The other scaled and the non-DTW subsequence metrics are not covered; there is no CPU fallback.
+samples are the second operand of one pairwise DP launch per subsequence (unscaled windows addressed in place with
+stride 1, so a warp's 32 consecutive windows read consecutive addresses; scaled windows z-normalised on the device),
+followed by a first-minimum reduction per sample -- or, where the reference's early abandoning decides the result
+(lcss / erp / edr / msm / twe and every scaled metric), by an exact replay of its scan (one warp per sample).
+The non-elastic subsequence metrics (euclidean, manhattan, mass, ...) are not part of this path; there is no CPU
+fallback.
 """
 import numbers
 
@@ -20,7 +23,7 @@ from .distance import _check_ts_array, _format_return, _make_metric, check_array
 
 __all__ = ["pairwise_subsequence_distance", "paired_subsequence_distance"]
 
-_SUBSEQUENCE_METRICS = ("dtw", "wdtw", "adtw", "ddtw", "wddtw")
+_SUBSEQUENCE_METRICS = ("dtw", "wdtw", "adtw", "ddtw", "wddtw", "lcss", "erp", "edr", "msm", "twe")
 
 
 def _is_arraylike(e):
@@ -54,23 +57,28 @@ def _check_subsequence_metric(metric, scale):
         raise ValueError("callable subsequence metrics are not accelerated; use wildboar.distance for them")
     if scale and isinstance(metric, str) and not metric.startswith("scaled_"):
         metric = "scaled_" + metric
-    if metric == "scaled_dtw":
-        return "dtw", True
-    if isinstance(metric, str) and metric.startswith("scaled_"):
-        raise ValueError(f"the scaled subsequence metric {metric!r} is not accelerated (only scaled_dtw); use wildboar.distance for it")
-    if metric not in _SUBSEQUENCE_METRICS:
+    scaled = isinstance(metric, str) and metric.startswith("scaled_")
+    base = metric[len("scaled_"):] if scaled else metric
+    if base not in _SUBSEQUENCE_METRICS:
         raise ValueError(
-            "unsupported metric '{}', 'metric' must be a str among {}".format(metric, set(_SUBSEQUENCE_METRICS) | {"scaled_dtw"})
+            "unsupported metric '{}', 'metric' must be a str among {}".format(
+                metric, set(_SUBSEQUENCE_METRICS) | {"scaled_" + b for b in _SUBSEQUENCE_METRICS})
         )
-    return metric, False
+    return base, scaled
 
 
-def _z_normalise(s):
-    """ScaledSubsequenceMetric.from_array (_cdistance.pyx:453-467) + the std passed on (:283-298)."""
+def _mean_std(s):
+    """ScaledSubsequenceMetric.from_array (_cdistance.pyx:453-467) + `std if std != 0 else 1.0` (:283-298)."""
     mean, std = np.mean(s), np.std(s)
     if std <= _EPSILON:
         std = 0.0
-    return (s - mean) / (std if std != 0 else 1.0)
+    return mean, (std if std != 0 else 1.0)
+
+
+def _z_normalise(s):
+    """The subsequence as the scaled metrics see it: (s - mean) / std (_elastic.pyx:2145-2166, _cdistance.pyx:505-509)."""
+    mean, std = _mean_std(s)
+    return (s - mean) / std
 
 
 def _prepare(y, x, dim, metric, metric_params, scale):
@@ -86,11 +94,15 @@ def _prepare(y, x, dim, metric, metric_params, scale):
     x_ = _check_ts_array(x)
     if isinstance(dim, bool) or not isinstance(dim, numbers.Integral) or not 0 <= dim < x_.shape[1]:
         raise ValueError("The parameter dim must be 0 <= dim < n_dims")
+    s_eps = None
+    if metric == "edr" and not scaled and np.isnan(m._params().epsilon):
+        # EdrSubsequenceMetric._distance (_elastic.pyx:2762-2765): epsilon = s_std / 4 of each subsequence
+        s_eps = np.array([_mean_std(s)[1] / 4.0 for s in y], dtype=np.double)
     if scaled:
-        if any(s.shape[0] < 3 for s in y):
+        if metric == "dtw" and any(s.shape[0] < 3 for s in y):
             raise ValueError("scaled_dtw needs subsequences of at least 3 samples (the reference reads S[1], S[2] unconditionally)")
         y = [_z_normalise(s) for s in y]
-    return y, x, x_[:, int(dim), :], m, scaled
+    return y, x, x_[:, int(dim), :], m, scaled, s_eps
 
 
 def pairwise_subsequence_distance(y, x, *, dim=0, metric="dtw", metric_params=None, scale=False, return_index=False,
@@ -100,8 +112,8 @@ def pairwise_subsequence_distance(y, x, *, dim=0, metric="dtw", metric_params=No
     Returns an array of shape (n_samples, n_subsequences) (squeezed like the reference) and, with
     ``return_index``, the start of the first best-matching window.
     """
-    y, x, xd, m, scaled = _prepare(y, x, dim, metric, metric_params, scale)
-    min_dist, min_ind = _shim.subsequence(m.metric_id, m._params(), y, xd, paired=False, scaled=scaled)
+    y, x, xd, m, scaled, s_eps = _prepare(y, x, dim, metric, metric_params, scale)
+    min_dist, min_ind = _shim.subsequence(m.metric_id, m._params(), y, xd, paired=False, scaled=scaled, s_epsilon=s_eps)
     if return_index:
         return _format_return(min_dist, len(y), x.ndim), _format_return(min_ind, len(y), x.ndim)
     return _format_return(min_dist, len(y), x.ndim)
@@ -110,13 +122,13 @@ def pairwise_subsequence_distance(y, x, *, dim=0, metric="dtw", metric_params=No
 def paired_subsequence_distance(y, x, *, dim=0, metric="dtw", metric_params=None, scale=False, return_index=False,
                                 n_jobs=None):
     """Minimum distance between the i:th subsequence and the i:th sample (_distance.py:639-729)."""
-    y, x, xd, m, scaled = _prepare(y, x, dim, metric, metric_params, scale)
+    y, x, xd, m, scaled, s_eps = _prepare(y, x, dim, metric, metric_params, scale)
     n_samples = x.shape[0] if x.ndim > 1 else 1
     if len(y) != n_samples:
         raise ValueError(
             "The number of subsequences and samples must be the same, got %d subsequences and %d samples." % (len(y), n_samples)
         )
-    min_dist, min_ind = _shim.subsequence(m.metric_id, m._params(), y, xd, paired=True, scaled=scaled)
+    min_dist, min_ind = _shim.subsequence(m.metric_id, m._params(), y, xd, paired=True, scaled=scaled, s_epsilon=s_eps)
     if return_index:
         return _format_return(min_dist, len(y), x.ndim), _format_return(min_ind, len(y), x.ndim)
     return _format_return(min_dist, len(y), x.ndim)
