@@ -983,3 +983,127 @@ double orc_scaled_subsequence_distance(int metric, const orc_params *p, const do
   free(cost); free(cost_prev); free(sb); free(xb); free(a1); free(a2); free(weights); free(mean); free(std);
   return min_dist;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * `_matches` / `_distance_profile` of the elastic subsequence metrics -- subsequence_match,
+ * paired_subsequence_match and distance_profile of _distance.py:732-1080, 1477-1600 end here (CD:338-372: the profile is
+ * `_matches` with threshold = +inf).  out[w] = distance of window w when the reference reports it as a match under
+ * `threshold`, NaN otherwise; returns the number of matches.  Rules restated:
+ *   unscaled dtw / wdtw / adtw / ddtw / wddtw (*_subsequence_matches EL:658-700, 737-779, 821-868): the DP runs against
+ *     threshold^2, match iff dist <= threshold^2, reported sqrt(dist);
+ *   unscaled lcss / erp / edr / msm / twe (EL:1227-1270, 1391-1434, 1539-1580, 1689-1730, 1872-1914): the DP is abandoned
+ *     against s_len - threshold * s_len (lcss, +inf stays +inf), threshold * max(s_len, t_len) (edr), threshold (others);
+ *     match iff dist <= threshold;
+ *   scaled_dtw (scaled_dtw_matches EL:485-619): windows with LB_Kim >= threshold^2 are skipped (that bound is not valid,
+ *     see ucr_lb_kim), match iff dist <= threshold^2, sqrt; the LB_Keogh bounds / cumulative abandoning are valid and are
+ *     not restated;
+ *   scaled_<metric> wraps (ScaledSubsequenceMetricWrap._matches CD:553-606): Metric._eadistance with *min_dist =
+ *     threshold, i.e. match iff dist < threshold (STRICT).
+ * ------------------------------------------------------------------------------------------ */
+int64_t orc_subsequence_matches(int metric, const orc_params *p, const double *S, int64_t s_len, double s_mean, double s_std,
+                                const double *T, int64_t t_len, int scaled, double threshold, double *out) {
+  const int64_t nw = t_len - s_len + 1;
+  int64_t n_matches = 0;
+  size_t n = (size_t)(t_len + 2);
+  for (int64_t w = 0; w < nw; w++) out[w] = NAN;
+  if (scaled && metric == ORC_DTW) {
+    const int64_t r = orc_compute_warp_width(s_len, p->r);
+    double *cost = (double *)malloc(sizeof(double) * (size_t)(2 * r + 2));
+    double *cost_prev = (double *)malloc(sizeof(double) * (size_t)(2 * r + 2));
+    const double thr = threshold * threshold;
+    double ex = 0, ex2 = 0;
+    for (int64_t t = 0; t < t_len; t++) {
+      const double cur = T[t];
+      ex += cur; ex2 += cur * cur;
+      if (t < s_len - 1) continue;
+      const int64_t I = t - (s_len - 1);
+      const double *X = T + I;
+      const double mean = ex / (double)s_len;
+      const double tmp = ex2 / (double)s_len - mean * mean;
+      const double std = tmp > 0 ? sqrt(tmp) : 1.0;
+      ex -= X[0]; ex2 -= X[0] * X[0];
+      if (!(ucr_lb_kim(S, s_mean, s_std, X, mean, std, s_len) < thr)) continue;
+      double *c = cost, *cp = cost_prev;
+      int64_t k = 0;
+      for (int64_t i = 0; i < 2 * r + 1; i++) { c[i] = INFINITY; cp[i] = INFINITY; }
+      for (int64_t i = 0; i < s_len; i++) {
+        k = i64max(0, r - i);
+        for (int64_t j = i64max(0, i - r); j < i64min(s_len, i + r + 1); j++) {
+          double v = (S[i] - s_mean) / s_std;
+          v -= (X[j] - mean) / std;
+          if (i == 0 && j == 0) c[k] = v * v;
+          else {
+            const double y = (j - 1 < 0 || k - 1 < 0) ? INFINITY : c[k - 1];
+            const double x = (i - 1 < 0 || k + 1 > 2 * r) ? INFINITY : cp[k + 1];
+            const double z = (i - 1 < 0 || j - 1 < 0) ? INFINITY : cp[k];
+            c[k] = dmin(dmin(x, y), z) + v * v;
+          }
+          k++;
+        }
+        double *tswap = c; c = cp; cp = tswap;
+      }
+      const double dist = cp[k - 1];
+      if (dist <= thr) { out[I] = sqrt(dist); n_matches++; }
+    }
+    free(cost); free(cost_prev);
+    return n_matches;
+  }
+  const int deriv = (metric == ORC_DDTW || metric == ORC_WDDTW);
+  double *cost = (double *)malloc(sizeof(double) * n), *cost_prev = (double *)malloc(sizeof(double) * n);
+  double *sb = (double *)malloc(sizeof(double) * n), *xb = (double *)malloc(sizeof(double) * n);
+  double *a1 = (double *)malloc(sizeof(double) * n), *a2 = (double *)malloc(sizeof(double) * n);
+  double *weights = NULL, *mean = (double *)malloc(sizeof(double) * n), *std = (double *)malloc(sizeof(double) * n);
+  if (metric == ORC_WDTW) { weights = (double *)malloc(sizeof(double) * n); orc_weights(p->g, t_len, weights); }
+  if (metric == ORC_WDDTW) { weights = (double *)malloc(sizeof(double) * n); if (t_len - 2 > 0) orc_weights(p->g, t_len - 2, weights); }
+  if (scaled) {
+    for (int64_t i = 0; i < s_len; i++) sb[i] = (S[i] - s_mean) / s_std;
+    orc_inc_window_stats(T, t_len, s_len, mean, std);
+  } else {
+    memcpy(sb, S, sizeof(double) * (size_t)s_len);
+  }
+  if (deriv && s_len >= 3) orc_average_slope(sb, s_len, a1);
+  const int64_t r = orc_compute_r(s_len, p->r);
+  for (int64_t i = 0; i < nw; i++) {
+    const double *X = T + i;
+    if (scaled) { for (int64_t j = 0; j < s_len; j++) xb[j] = (T[i + j] - mean[i]) / std[i]; X = xb; }
+    double dist, thr = threshold;
+    int sq = 0;
+    switch (metric) {
+      case ORC_DTW: case ORC_WDTW:
+        sq = 1; thr = threshold * threshold;
+        dist = dtw_distance(sb, s_len, X, s_len, r, cost, cost_prev, weights, thr); break;
+      case ORC_ADTW:
+        sq = 1; thr = threshold * threshold;
+        dist = adtw_distance(sb, s_len, X, s_len, r, cost, cost_prev, p->p, thr); break;
+      case ORC_DDTW: case ORC_WDDTW:
+        if (s_len < 3) continue; /* EL:843-844 (no matches) / EL:3297 (nothing accepted) */
+        sq = 1; thr = threshold * threshold;
+        orc_average_slope(X, s_len, a2);
+        dist = dtw_distance(a1, s_len - 2, a2, s_len - 2, scaled ? orc_compute_r(s_len - 2, p->r) : r, cost, cost_prev, weights, thr);
+        break;
+      case ORC_LCSS:
+        dist = lcss_distance(sb, s_len, X, s_len, r, p->epsilon, cost, cost_prev, NULL,
+                             isinf(threshold) ? INFINITY : (double)s_len - threshold * (double)s_len);
+        break;
+      case ORC_ERP:
+        dist = erp_distance(sb, s_len, X, s_len, r, p->g, a1, a2, cost, cost_prev, threshold); break;
+      case ORC_EDR: {
+        double eps = p->epsilon;
+        if (isnan(eps)) eps = dmax(orc_std(sb, s_len), orc_std(X, s_len)) / 4.0; /* scaled wrap only; unscaled: resolved by the caller */
+        dist = edr_distance(sb, s_len, X, s_len, r, eps, cost, cost_prev, threshold * (double)(scaled ? s_len : i64max(s_len, t_len)));
+        break;
+      }
+      case ORC_MSM:
+        dist = msm_distance(sb, s_len, X, s_len, r, p->c, cost, cost_prev, a2, threshold); break;
+      case ORC_TWE:
+        dist = twe_distance(sb, s_len, X, s_len, r, p->penalty, p->stiffness, cost, cost_prev, threshold); break;
+      default: dist = NAN;
+    }
+    if (scaled) {
+      if (sq) dist = sqrt(dist);
+      if (dist < threshold) { out[i] = dist; n_matches++; }
+    } else if (dist <= thr) { out[i] = sq ? sqrt(dist) : dist; n_matches++; }
+  }
+  free(cost); free(cost_prev); free(sb); free(xb); free(a1); free(a2); free(weights); free(mean); free(std);
+  return n_matches;
+}

@@ -365,3 +365,31 @@ def pairwise_scaled_dtw_subsequence(subsequences, x, r=1.0):
                                                       C.byref(j))
             idx[i, k] = j.value
     return dist, idx
+
+
+def subsequence_matches(metric, s, x, threshold=float("inf"), scaled=False, mean_std=None, **params):
+    """Dense form of SubsequenceMetric._matches for ONE subsequence against every sample of x (or, with s 2-D, the i:th
+    subsequence against the i:th sample): (n_samples, n_windows), the window's distance where the reference reports a
+    match under `threshold`, NaN elsewhere.  mean_std: (mean, std) the reference hands to the metric (default: the
+    from_array values, _cdistance.pyx:453-467); edr's default epsilon (unscaled) is std / 4 of it."""
+    L = lib()
+    dp = C.POINTER(C.c_double)
+    L.orc_subsequence_matches.argtypes = [C.c_int, C.POINTER(Params), dp, C.c_int64, C.c_double, C.c_double, dp, C.c_int64,
+                                          C.c_int, C.c_double, dp]
+    L.orc_subsequence_matches.restype = C.c_int64
+    x = _arr(x)
+    s = np.ascontiguousarray(s, dtype=np.float64)
+    subs = [s] * x.shape[0] if s.ndim == 1 else list(s)
+    assert len(subs) == x.shape[0]
+    p = make_params(metric, **params)
+    eps_auto = metric == "edr" and np.isnan(p.epsilon) and not scaled
+    m = subs[0].shape[0]
+    out = np.empty((x.shape[0], x.shape[1] - m + 1))
+    for i, si in enumerate(subs):
+        si = np.ascontiguousarray(si)
+        mean, std = _subsequence_mean_std(si) if mean_std is None else mean_std(si)
+        if eps_auto:
+            p.epsilon = std / 4.0
+        L.orc_subsequence_matches(METRIC_IDS[metric], C.byref(p), _dp(si), m, mean, std, _dp(x[i]), x.shape[1],
+                                  1 if scaled else 0, float(threshold), _dp(out[i]))
+    return out
