@@ -204,6 +204,25 @@ int wb_cuda_subsequence(int metric, const wb_params *params,
                         int paired, int scaled, const double *s_epsilon, double *out_dist, int64_t *out_idx,
                         const int *devices, int n_devices, wb_stats *stats);
 
+/* Subsequence matches / distance profile: the dense form of SubsequenceMetric._matches
+ * (_cdistance.pyx:311-372; the *_subsequence_matches of _elastic.pyx:658-700, 737-779, 821-868, 1227-1270, 1391-1434,
+ * 1539-1580, 1689-1730, 1872-1914, scaled_dtw_matches :485-619, ScaledSubsequenceMetricWrap._matches _cdistance.pyx:553-606).
+ * Replaces the per-sample loops of `_subsequence_match` / `_paired_subsequence_match` (_cdistance.pyx:1065-1141) and
+ * `_distance_profile` (_cdistance.pyx:1655-1725, = _matches with threshold +inf).
+ * s: (n_s, m) dense; n_s == 1: the one subsequence against every sample, n_s == nx: subsequence i against sample i.
+ * out: (nx, T - m + 1); out[i][w] = distance of window w of sample i where the reference reports a match under
+ * `threshold` (+inf: every window, the distance profile), NaN elsewhere.  Match rules as in the reference: unscaled
+ * metrics `dist <= threshold` (DTW family in the squared-cost domain), the scaled wraps `dist < threshold`; a window whose
+ * DP the reference abandons against the threshold (lcss: m - threshold m, edr: threshold max(m, T) resp. threshold m) is
+ * not a match; scaled_dtw skips windows whose (invalid) LB_Kim is >= threshold^2.  scaled / s_epsilon as in
+ * wb_cuda_subsequence (the caller z-normalises s and resolves edr's default epsilon from the statistics the reference
+ * uses on that path: numpy's for subsequence_match, sequential sums for distance_profile, _cdistance.pyx:167-185). */
+int wb_cuda_subsequence_profile(int metric, const wb_params *params,
+                                const double *s, int64_t n_s, int64_t m,
+                                const double *x, int64_t nx, int64_t T, int64_t x_stride,
+                                int scaled, const double *s_epsilon, double threshold, double *out,
+                                const int *devices, int n_devices, wb_stats *stats);
+
 /* Device-resident variant of wb_cuda_pairwise: d_x (nx, Tx), d_y (ny, Ty), d_out (nx, ny) are
  * dense row-major DEVICE arrays on the current device.  Enqueues on `stream`; fills `stats`
  * (after synchronising the stream) when stats != NULL. */

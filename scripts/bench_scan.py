@@ -59,6 +59,33 @@ def main():
                        ref_windows_per_s=round(nss * nxs * (T - m + 1) / t_ref), ref_cores=NCPU,
                        ref_bit_equal=bool(np.array_equal(rd_, d[:nxs, :nss]) and np.array_equal(ri_, i[:nxs, :nss])))
         print(json.dumps(row), flush=True)
+    # ---- distance_profile / subsequence_match: every window's distance, one list-mode launch per pass ----
+    Y = np.stack([Xs[(q + 1) % n, (q * 7) % (T - m):(q * 7) % (T - m) + m] for q in range(n)])
+    for metric, mp in (("dtw", {"r": 0.1}), ("scaled_dtw", {"r": 0.1}), ("msm", {"r": 0.1}), ("scaled_twe", {"r": 0.1})):
+        t_dp, dp = timed(lambda: wb.distance_profile(Y, Xs, metric=metric, metric_params=mp))
+        st = wb.last_stats()
+        row = dict(row="8f-4 distance_profile", metric=metric, shape=f"{n} subsequences x {m} paired with {n} samples x {T}, r={mp['r']}",
+                   windows=n * (T - m + 1), cells=st["cells"], e2e_ms=round(t_dp * 1e3, 1), kernel_ms=round(st["kernel_ms"], 1),
+                   kernel_gcups=round(st["cells"] / (st["kernel_ms"] * 1e-3) / 1e9, 1), launches=st["launches"], engine=st["engine"],
+                   windows_per_s=round(n * (T - m + 1) / t_dp))
+        if wd is not None:
+            nxs = 64 if QUICK else 256
+            t_ref, rdp = timed(lambda: wd.distance_profile(Y[:nxs], Xs[:nxs], metric=metric, metric_params=mp, n_jobs=NCPU), reps=1)
+            row.update(ref_sample=f"{nxs} pairs, n_jobs={NCPU}", ref_ms=round(t_ref * 1e3, 1), ref_windows_per_s=round(nxs * (T - m + 1) / t_ref),
+                       ref_cores=NCPU, ref_bit_equal=bool(np.array_equal(rdp, dp[:nxs])))
+        print(json.dumps(row), flush=True)
+    thr = float(np.quantile(dp, 0.01))
+    t_sm, (mi, md) = timed(lambda: wb.subsequence_match(shp[0], Xs, threshold=thr, metric="scaled_twe", metric_params={"r": 0.1}, return_distance=True))
+    row = dict(row="8f-4 subsequence_match", metric="scaled_twe", shape=f"1 subsequence x {m} vs {n} samples x {T}, threshold = 1 % quantile",
+               e2e_ms=round(t_sm * 1e3, 1), kernel_ms=round(wb.last_stats()["kernel_ms"], 1), matches=int(sum(0 if a is None else len(a) for a in mi)))
+    if wd is not None:
+        nxs = 64 if QUICK else 256
+        t_ref, (ri, rd) = timed(lambda: wd.subsequence_match(shp[0], Xs[:nxs], threshold=thr, metric="scaled_twe", metric_params={"r": 0.1},
+                                                           return_distance=True), reps=1)
+        same = all((a is None and b is None) or (a is not None and b is not None and np.array_equal(a, b)) for a, b in zip(ri, mi[:nxs])) and \
+            all((a is None and b is None) or (a is not None and b is not None and np.array_equal(a, b)) for a, b in zip(rd, md[:nxs]))
+        row.update(ref_sample=f"{nxs} samples (1 core: the reference's match loop is serial)", ref_ms=round(t_ref * 1e3, 1), ref_bit_equal=bool(same))
+    print(json.dumps(row), flush=True)
 
 
 if __name__ == "__main__":

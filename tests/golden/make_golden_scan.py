@@ -7,6 +7,8 @@ Writes tests/golden/scan_golden.npz:
            _elastic.pyx:2616-3124) -- the metrics whose early abandoning decides which window wins
   sw|...   the same calls for the generic scaled metrics scaled_<metric> = ScaledSubsequenceMetricWrap(Metric)
            (_cdistance.pyx:470-551) over adtw, wdtw, ddtw, wddtw, lcss, erp, edr, msm, twe
+  sm|...   subsequence_match / paired_subsequence_match (_distance.py:732-1080) and distance_profile (:1477-1600) for
+           every elastic subsequence metric, unscaled and scaled; jagged results padded with -1 / NaN
 """
 import os
 import sys
@@ -25,6 +27,53 @@ SW_CASES = [("adtw", {"r": 0.2, "p": 0.5}), ("wdtw", {"r": 0.3, "g": 0.1}), ("dd
             ("edr", {"r": 0.3, "epsilon": 0.8}), ("msm", {"r": 0.15, "c": 0.3}), ("twe", {"r": 0.2, "penalty": 0.5, "stiffness": 0.05}),
             ("msm", {}), ("lcss", {})]
 LENGTHS = (12, 30, 5, 3, 72, 1, 2, 41)
+
+
+SM_CASES = [("dtw", {"r": 0.1}), ("wdtw", {"r": 0.3, "g": 0.1}), ("adtw", {"r": 0.2, "p": 0.5}), ("ddtw", {"r": 0.2}),
+            ("wddtw", {"r": 0.5, "g": 0.2}), ("lcss", {"r": 0.2, "epsilon": 0.5}), ("erp", {"r": 0.1, "g": 0.4}), ("edr", {"r": 0.25}),
+            ("edr", {"r": 0.3, "epsilon": 0.8}), ("msm", {"r": 0.15, "c": 0.3}), ("twe", {"r": 0.2, "penalty": 0.5, "stiffness": 0.05})]
+SM_SUBS = (0, 1, 3)   # lengths 12, 30, 3
+
+
+def pad(lst, fill, dtype):
+    """Jagged per-sample results (None = no match) -> (n_samples, K) padded."""
+    lst = [np.array([], dtype=dtype) if a is None else np.atleast_1d(a) for a in lst]
+    K = max(1, max(len(a) for a in lst))
+    out = np.full((len(lst), K), fill, dtype=dtype)
+    for i, a in enumerate(lst):
+        out[i, :len(a)] = a
+    return out
+
+
+def matches(wd, out, X, subs):
+    n = X.shape[0]
+    for prefix in ("", "scaled_"):
+        for ci, (metric, mp) in enumerate(SM_CASES):
+            name = prefix + metric
+            for k in SM_SUBS:
+                s = subs[k]
+                key = f"sm|{name}|{ci}|{k}"
+                full_i, full_d = wd.subsequence_match(s, X, max_matches=10**9, metric=name, metric_params=mp, return_distance=True)
+                dists = np.concatenate([d for d in full_d if d is not None])
+                for ti, thr in enumerate((float(np.median(dists)), float(np.quantile(dists, 0.1)))):
+                    i_, d_ = wd.subsequence_match(s, X, threshold=thr, metric=name, metric_params=mp, return_distance=True)
+                    out[f"{key}|thr{ti}"] = np.array(thr)
+                    out[f"{key}|thr{ti}|idx"], out[f"{key}|thr{ti}|dist"] = pad(i_, -1, np.int64), pad(d_, np.nan, float)
+                # API-level forms: the 10 best, "auto", exclusion zone + max_matches, per-sample thresholds
+                i_, d_ = wd.subsequence_match(s, X, metric=name, metric_params=mp, return_distance=True)
+                out[f"{key}|top|idx"], out[f"{key}|top|dist"] = pad(i_, -1, np.int64), pad(d_, np.nan, float)
+                i_, d_ = wd.subsequence_match(s, X, threshold="auto", metric=name, metric_params=mp, return_distance=True)
+                out[f"{key}|auto|idx"], out[f"{key}|auto|dist"] = pad(i_, -1, np.int64), pad(d_, np.nan, float)
+                i_, d_ = wd.subsequence_match(s, X, threshold=float(np.median(dists)), exclude=0.5, max_matches=4, metric=name,
+                                              metric_params=mp, return_distance=True)
+                out[f"{key}|excl|idx"], out[f"{key}|excl|dist"] = pad(i_, -1, np.int64), pad(d_, np.nan, float)
+            # paired: subsequence q (mixed lengths) against sample q
+            paired = [subs[SM_SUBS[q % len(SM_SUBS)]] for q in range(n)]
+            i_, d_ = wd.paired_subsequence_match(paired, X, metric=name, metric_params=mp, return_distance=True, max_matches=5)
+            out[f"sm|{name}|{ci}|paired|idx"], out[f"sm|{name}|{ci}|paired|dist"] = pad(i_, -1, np.int64), pad(d_, np.nan, float)
+            # distance profile: subsequence q = a window of sample (q + 1) % n, length 15
+            Y = np.stack([X[(q + 1) % n, 7 + q:22 + q] for q in range(n)])
+            out[f"sm|{name}|{ci}|profile"] = wd.distance_profile(Y, X, metric=name, metric_params=mp)
 
 
 def main():
@@ -50,6 +99,7 @@ def main():
             paired = [ss[q % len(ss)] for q in range(X.shape[0])]
             d, i = wd.paired_subsequence_distance(paired, X, metric=prefix + metric, metric_params=mp, return_index=True)
             out[f"{tag}|{ci}|paired_dist"], out[f"{tag}|{ci}|paired_idx"] = d, i.astype(np.int64)
+    matches(wd, out, X, subs)
     path = os.path.join(HERE, "scan_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")

@@ -169,3 +169,146 @@ def test_scan_negative_adtw_penalty(W, oracle):
     d, i = W.pairwise_subsequence_distance(subs, X, metric="scaled_adtw", metric_params=mp, return_index=True)
     od, oi = oracle.pairwise_scaled_subsequence("adtw", subs, X, **mp)
     assert np.array_equal(d, od, equal_nan=True) and np.array_equal(i, oi)
+
+
+# ---------------------------------------------------------------------------------------------
+# subsequence_match / paired_subsequence_match / distance_profile
+# ---------------------------------------------------------------------------------------------
+from make_golden_scan import SM_CASES, SM_SUBS, pad  # noqa: E402
+
+
+def _same(a, b):
+    return a.shape == b.shape and np.array_equal(a, b, equal_nan=True)
+
+
+def _dense_from_padded(idx, dist, nw):
+    out = np.full((idx.shape[0], nw), np.nan)
+    for i in range(idx.shape[0]):
+        sel = idx[i] >= 0
+        out[i, idx[i][sel]] = dist[i][sel]
+    return out
+
+
+def _view_mean_std(s):
+    ex, ex2 = np.cumsum(s)[-1], np.cumsum(s * s)[-1]
+    mean = ex / len(s)
+    var = ex2 / len(s) - mean * mean
+    return float(mean), float(np.sqrt(var) if var > 1e-13 else 0.0)
+
+
+@pytest.mark.parametrize("scaled", [False, True])
+@pytest.mark.parametrize("ci", range(len(SM_CASES)))
+def test_oracle_matches_and_profile_match_reference_golden(oracle, scan_golden, ci, scaled):
+    g = scan_golden
+    metric, mp = SM_CASES[ci]
+    name = ("scaled_" if scaled else "") + metric
+    X = g["X"]
+    for k in SM_SUBS:
+        s = g[f"s{k}"]
+        for ti in range(2):
+            key = f"sm|{name}|{ci}|{k}|thr{ti}"
+            want = _dense_from_padded(g[key + "|idx"], g[key + "|dist"], X.shape[1] - len(s) + 1)
+            got = oracle.subsequence_matches(metric, s, X, float(g[key]), scaled, **mp)
+            assert _same(got, want), (name, k, ti)
+    n = X.shape[0]
+    Y = np.stack([X[(q + 1) % n, 7 + q:22 + q] for q in range(n)])
+    got = oracle.subsequence_matches(metric, Y, X, np.inf, scaled, mean_std=_view_mean_std, **mp)
+    assert _same(got, g[f"sm|{name}|{ci}|profile"]), name
+
+
+def test_match_host_logic(wb):
+    x = np.zeros((3, 10))
+    with pytest.raises(ValueError, match="single subsequence"):
+        wb.subsequence_match([np.zeros(3), np.zeros(3)], x, metric="dtw")
+    with pytest.raises(ValueError, match="Invalid subsequnce shape"):
+        wb.subsequence_match(np.zeros(11), x, metric="msm")
+    with pytest.raises(TypeError, match="threshold must be"):
+        wb.subsequence_match(np.zeros(4), x, threshold=object(), metric="dtw")
+    with pytest.raises(ValueError, match="must match the number of samples"):
+        wb.subsequence_match(np.zeros(4), x, threshold=[1.0, 2.0], metric="dtw")
+    with pytest.raises(ValueError, match="unsupported metric"):
+        wb.subsequence_match(np.zeros(4), x, threshold=1.0, metric="euclidean")
+    with pytest.raises(ValueError, match="must be the same"):
+        wb.paired_subsequence_match([np.zeros(4)], x, metric="dtw")
+    with pytest.raises(ValueError, match="dilation=1, padding=0"):
+        wb.distance_profile(np.zeros(3), x, dilation=2, metric="dtw")
+    with pytest.raises(ValueError, match="larger than input"):
+        wb.distance_profile(np.zeros((3, 11)), x, metric="dtw")
+    with pytest.raises(ValueError, match="same number of samples"):
+        wb.distance_profile(np.zeros((2, 4)), x, metric="dtw")
+    from wildboar_b200.subsequence import _keep_nontrivial, _rows_to_matches
+    idx, dist = _rows_to_matches(np.array([[np.nan, 1.0, 0.5, np.nan], [np.nan] * 4]))
+    assert np.array_equal(idx[0], [1, 2]) and np.array_equal(dist[0], [1.0, 0.5]) and idx[1] is None and dist[1] is None
+    keep = _keep_nontrivial(2)(0, np.array([0, 1, 2, 5]), np.array([0.3, 0.1, 0.2, 0.9]))
+    assert np.array_equal(keep, [False, True, False, True])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scaled", [False, True])
+@pytest.mark.parametrize("ci", range(len(SM_CASES)))
+def test_subsequence_match_and_profile_match_reference_golden(W, scan_golden, ci, scaled):
+    g = scan_golden
+    metric, mp = SM_CASES[ci]
+    name = ("scaled_" if scaled else "") + metric
+    X = g["X"]
+    n = X.shape[0]
+    for k in SM_SUBS:
+        s = g[f"s{k}"]
+        key = f"sm|{name}|{ci}|{k}"
+        for ti in range(2):
+            i_, d_ = W.subsequence_match(s, X, threshold=float(g[f"{key}|thr{ti}"]), metric=name, metric_params=mp, return_distance=True)
+            assert _same(pad(i_, -1, np.int64), g[f"{key}|thr{ti}|idx"]) and _same(pad(d_, np.nan, float), g[f"{key}|thr{ti}|dist"]), (name, k, ti)
+        i_, d_ = W.subsequence_match(s, X, metric=name, metric_params=mp, return_distance=True)
+        assert _same(pad(i_, -1, np.int64), g[f"{key}|top|idx"]) and _same(pad(d_, np.nan, float), g[f"{key}|top|dist"]), (name, k, "top")
+        i_, d_ = W.subsequence_match(s, X, threshold="auto", metric=name, metric_params=mp, return_distance=True)
+        assert _same(pad(i_, -1, np.int64), g[f"{key}|auto|idx"]) and _same(pad(d_, np.nan, float), g[f"{key}|auto|dist"]), (name, k, "auto")
+        thr = float(g[f"{key}|thr0"])
+        i_, d_ = W.subsequence_match(s, X, threshold=thr, exclude=0.5, max_matches=4, metric=name, metric_params=mp, return_distance=True)
+        assert _same(pad(i_, -1, np.int64), g[f"{key}|excl|idx"]) and _same(pad(d_, np.nan, float), g[f"{key}|excl|dist"]), (name, k, "excl")
+    paired = [g[f"s{SM_SUBS[q % len(SM_SUBS)]}"] for q in range(n)]
+    i_, d_ = W.paired_subsequence_match(paired, X, metric=name, metric_params=mp, return_distance=True, max_matches=5)
+    assert _same(pad(i_, -1, np.int64), g[f"sm|{name}|{ci}|paired|idx"]) and _same(pad(d_, np.nan, float), g[f"sm|{name}|{ci}|paired|dist"]), name
+    Y = np.stack([X[(q + 1) % n, 7 + q:22 + q] for q in range(n)])
+    assert _same(W.distance_profile(Y, X, metric=name, metric_params=mp), g[f"sm|{name}|{ci}|profile"]), name
+    # scale=True spelling and the single-series forms
+    if scaled:
+        assert _same(W.distance_profile(Y, X, metric=metric, scale=True, metric_params=mp), g[f"sm|{name}|{ci}|profile"])
+    assert W.distance_profile(Y[0], X[0], metric=name, metric_params=mp).shape == (X.shape[1] - 15 + 1,)
+
+
+@pytest.mark.gpu
+def test_profile_larger_matches_oracle(W, oracle):
+    """Longer series, several passes over the samples (scaled windows), per-sample thresholds, two devices if present."""
+    rng = np.random.default_rng(31)
+    X = np.cumsum(rng.standard_normal((33, 260)), axis=1)
+    s = X[5, 40:100].copy()
+    os.environ["WILDBOAR_CUDA_SCAN_WINDOW_BUDGET"] = str(201 * 60 * 7)
+    try:
+        for metric, mp in (("dtw", {"r": 0.1}), ("ddtw", {"r": 0.1}), ("msm", {"r": 0.1}), ("twe", {"r": 0.05}), ("lcss", {"r": 0.1, "epsilon": 0.4}),
+                           ("erp", {"r": 0.1}), ("edr", {"r": 0.1})):
+            for scaled in (False, True):
+                name = ("scaled_" if scaled else "") + metric
+                full = oracle.subsequence_matches(metric, s, X, np.inf, scaled, **mp)
+                thr = float(np.nanquantile(full, 0.2))
+                want = oracle.subsequence_matches(metric, s, X, thr, scaled, **mp)
+                i_, d_ = W.subsequence_match(s, X, threshold=thr, metric=name, metric_params=mp, return_distance=True)
+                got = _dense_from_padded(pad(i_, -1, np.int64), pad(d_, np.nan, float), full.shape[1])
+                assert _same(got, want), name
+                Y = np.stack([X[(q + 3) % 33, q:q + 60] for q in range(33)])
+                want = oracle.subsequence_matches(metric, Y, X, np.inf, scaled, mean_std=_view_mean_std, **mp)
+                assert _same(W.distance_profile(Y, X, metric=name, metric_params=mp), want), name
+    finally:
+        del os.environ["WILDBOAR_CUDA_SCAN_WINDOW_BUDGET"]
+    thr = np.linspace(2.0, 12.0, 33)
+    i_, d_ = W.subsequence_match(s, X, threshold=thr, metric="dtw", metric_params={"r": 0.1}, return_distance=True)
+    full = oracle.subsequence_matches("dtw", s, X, np.inf, False, r=0.1)
+    want = np.where(full <= thr[:, None], full, np.nan)
+    assert _same(_dense_from_padded(pad(i_, -1, np.int64), pad(d_, np.nan, float), full.shape[1]), want)
+    assert i_[5][np.argmin(d_[5])] == 40 and d_[5].min() == 0.0
+    if W.device_count() >= 2:
+        W.set_devices([0, 1])
+        try:
+            dp2 = W.distance_profile(np.stack([s] * 33), X, metric="scaled_msm", metric_params={"r": 0.1})
+        finally:
+            W.set_devices([0])
+        assert _same(dp2, oracle.subsequence_matches("msm", np.stack([s] * 33), X, np.inf, True, mean_std=_view_mean_std, r=0.1))

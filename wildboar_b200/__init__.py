@@ -2,7 +2,9 @@
 
 Public surface (mirrors ``wildboar.distance``; reference: src/wildboar/distance/_distance.py):
 
-    pairwise_distance, paired_distance, argmin_distance, check_metric
+    pairwise_distance, paired_distance, argmin_distance, check_metric,
+    pairwise_subsequence_distance, paired_subsequence_distance, subsequence_match, paired_subsequence_match,
+    distance_profile (elastic subsequence metrics)
 
 The compute path is ``libwbcuda.so`` (hand-written CUDA, include/wb_cuda.h).  There is no CPU
 fallback: without the library or without a B200 the calls raise.
@@ -14,11 +16,18 @@ from .distance import (  # noqa: F401
     paired_distance,
     pairwise_distance,
 )
-from .subsequence import paired_subsequence_distance, pairwise_subsequence_distance  # noqa: F401
+from .subsequence import (  # noqa: F401
+    distance_profile,
+    paired_subsequence_distance,
+    paired_subsequence_match,
+    pairwise_subsequence_distance,
+    subsequence_match,
+)
 from ._shim import device_count, get_precision, last_stats, library_path, set_devices, set_precision  # noqa: F401
 
 __all__ = [
     "pairwise_distance", "paired_distance", "argmin_distance", "check_metric",
-    "pairwise_subsequence_distance", "paired_subsequence_distance",
+    "pairwise_subsequence_distance", "paired_subsequence_distance", "subsequence_match", "paired_subsequence_match",
+    "distance_profile",
     "device_count", "set_devices", "set_precision", "get_precision", "last_stats", "library_path",
 ]

@@ -78,6 +78,7 @@ def lib():
                 L.wb_cuda_dtw_paths.argtypes = [_DP, i64, i64, i64, _DP, i64, i64, i64, _IP, _IP, i64, C.c_double, _DP, I32P,
                                                 I32P, _DP, _DP, ci, SP]
                 L.wb_cuda_dba_epoch.argtypes = [C.c_void_p, ci, PP, _DP, i64, i64, _IP, _IP, _DP, _DP, ci, _DP, _DP, SP]
+                L.wb_cuda_subsequence_profile.argtypes = [ci, PP, _DP, i64, i64, _DP, i64, i64, i64, ci, _DP, C.c_double, _DP, DV, ci, SP]
                 L.wb_cuda_subsequence.argtypes = [ci, PP, _DP, _IP, i64, _DP, i64, i64, i64, ci, ci, _DP, _DP, _IP, DV, ci, SP]
                 L.wb_cuda_argmin.argtypes = [ci, PP, _DP, i64, i64, i64, _DP, i64, i64, i64, i64, _DP, ci, _IP, _DP,
                                              DV, ci, SP]
@@ -430,6 +431,30 @@ def subsequence(metric_id, params, subsequences, x, paired=False, scaled=False, 
                                      idx.ctypes.data_as(_IP), dv, nd, C.byref(st)))
     _tls.stats = st.as_dict()
     return dist, idx.astype(np.intp, copy=False)
+
+
+def subsequence_profile(metric_id, params, s, x, scaled=False, s_epsilon=None, threshold=float("inf")):
+    """Dense matches / distance profile (wb_cuda_subsequence_profile): s is (m,) (against every sample) or (nx, m)
+    (paired); returns (nx, T - m + 1) with NaN where the reference reports no match under `threshold`."""
+    apply_engine_override(params)
+    params.precision = 0
+    x, xp, nx, T, xs = _rows(x)
+    s = np.ascontiguousarray(np.atleast_2d(np.asarray(s, dtype=np.float64)))
+    n_s, m = s.shape
+    out = np.empty((nx, T - m + 1), dtype=np.float64)
+    st = WbStats()
+    eps = None
+    if s_epsilon is not None:
+        eps = np.ascontiguousarray(np.atleast_1d(s_epsilon), dtype=np.float64)
+        if eps.shape != (n_s,):
+            raise ValueError("s_epsilon needs one value per subsequence")
+    cells = float(nx) * (T - m + 1) * _est_cells(1, int(m), int(m), params.r)
+    dv, nd = _dev_array(_resolve_devices(cells))
+    _check(lib().wb_cuda_subsequence_profile(metric_id, C.byref(params), s.ctypes.data_as(_DP), n_s, m, xp, nx, T, xs,
+                                             1 if scaled else 0, eps.ctypes.data_as(_DP) if eps is not None else None,
+                                             float(threshold), out.ctypes.data_as(_DP), dv, nd, C.byref(st)))
+    _tls.stats = st.as_dict()
+    return out
 
 
 def _first_device():

@@ -184,6 +184,8 @@ __global__ void __launch_bounds__(NT) k_rowscan(KArgsT<typename M::real> a, M m)
       if (a.mode != PM_PAIRED && a.mode != PM_LISTP) {
         if (a.out_m) a.out_m[i * a.ld + j] = (double)mmax;
         if (a.mode == PM_SELF && a.mirror) a.out[j * a.ld + i] = r;
+      } else if (a.mode == PM_LISTP && a.out_m) {
+        a.out_m[t * 32 + lane] = (double)mmax;  // one entry per list element, like the distances
       }
     }
     __syncwarp();
@@ -260,12 +262,14 @@ __global__ void k_window_stats(const double* __restrict__ x, long long n, int T,
 // and never dist(t_y1, s_y0), so the value can exceed the DTW distance; the scan skips a window when it is >= the running
 // minimum (EL:413), which makes it part of the observable result.  sn = z-normalised subsequence (m >= 3 values).
 __global__ void k_ucr_kim(const double* __restrict__ x, long long n, int T, int m, const double* __restrict__ sn,
-                          const double* __restrict__ mean, const double* __restrict__ stdv, double* __restrict__ lb) {
+                          const double* __restrict__ mean, const double* __restrict__ stdv, double* __restrict__ lb,
+                          long long sn_stride = 0) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int nw = T - m + 1;
   if (e >= n * (long long)nw) return;
   const long long i = e / nw;
   const int w = (int)(e - i * nw);
+  sn += i * sn_stride;  // 0: one subsequence for every sample; m: subsequence i for sample i
   const double* t = x + i * T + w;
   const double mu = mean[i * T + w], sd = stdv[i * T + w];
   auto d2 = [](double a, double b) { const double q = a - b; return q * q; };
@@ -314,6 +318,30 @@ __global__ void k_normalise_windows(const double* __restrict__ x, long long n, i
     const long long i = win / nw;
     const int w = (int)(win - i * nw);
     out[e] = (x[i * T + w + j] - mean[win]) / stdv[win];
+  }
+}
+
+// ---- subsequence matches / distance profile (SubsequenceMetric._matches, CD:311-372 and the *_subsequence_matches of EL) ----
+// pair list of one pass: entry e = i * nw + w pairs subsequence (paired ? sub0 + i : 0) with window w of sample i, whose
+// first element sits at y[i * ystride + w] (flat series, stride-1 windows) or row i * nw + w (ystride == nw: dense rows)
+__global__ void k_profile_list(int2* __restrict__ list, long long n, int nw, long long ystride, int sub0, int paired) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e / nw;
+    const int w = (int)(e - i * nw);
+    list[e] = make_int2(paired ? sub0 + (int)i : 0, (int)(i * ystride + w));
+  }
+}
+// out[e] = the window's distance when the reference reports it, NaN otherwise: d <= thr_d (strict: d < thr_d), not abandoned
+// (M > thr_m), not skipped by scaled_dtw's LB_Kim prefilter (kim >= thr_d; kim laid out [i * ldk + w]).
+__global__ void k_profile_select(const double* __restrict__ d, const double* __restrict__ mm, const double* __restrict__ kim,
+                                 long long n, int nw, long long ldk, double thr_d, double thr_m, int strict, int apply_sqrt,
+                                 double* __restrict__ out) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const double v = d[e];
+    bool ok = strict ? (v < thr_d) : (v <= thr_d);
+    if (ok && mm) ok = !(mm[e] > thr_m);
+    if (ok && kim) { const long long i = e / nw; ok = kim[i * ldk + (e - i * nw)] < thr_d; }
+    out[e] = ok ? (apply_sqrt ? sqrt(v) : v) : __longlong_as_double(0x7ff8000000000000LL);
   }
 }
 

@@ -1293,6 +1293,205 @@ static int subseq_scan_worker(const SubseqJob& J, int dev, int64_t lo, int64_t h
   return rc;
 }
 
+// ------------------------------------------------------------------------------------------
+// Subsequence matches / distance profile: the dense form of SubsequenceMetric._matches -- for ONE
+// subsequence against every sample (subsequence_match) or subsequence i against sample i (paired_subsequence_match,
+// distance_profile), out[i][w] = distance of window w where the reference reports it under `threshold`, NaN elsewhere.
+// Every (sample, window) pair of a pass is one entry of a pair list (PM_LISTP): one DP launch, one selection kernel.
+// ------------------------------------------------------------------------------------------
+struct ProfileJob {
+  int metric; wb_params p;
+  const double* s; int64_t ns, m;      // ns == 1 or ns == nx (paired), dense (ns, m); scaled: z-normalised by the caller
+  const double* x; int64_t nx, T, xs;
+  int scaled; const double* s_eps;     // edr, unscaled, default epsilon: std / 4 per subsequence
+  double threshold;
+  double* out;                         // (nx, T - m + 1)
+};
+
+static int subseq_profile_worker(const ProfileJob& J, int dev, int64_t lo, int64_t hi, wb_stats* st_out) {
+  DeviceInfo di; cudaStream_t st;
+  if (begin_single_device(dev, &di, &st)) return 1;
+  int rc = 0;
+  wb_stats stats; memset(&stats, 0, sizeof stats);
+  {
+    Workspace ws(st);
+    Timer total(st), kt(st);
+    total.start();
+    const int64_t rows = hi - lo, T = J.T, m = J.m, nw = T - m + 1;
+    const bool paired = J.ns > 1;
+    const int64_t nsub = paired ? rows : 1;
+    const bool dtwfam = is_dtw_family(J.metric);
+    const bool deriv = is_derivative(J.metric);
+    const bool ucr = J.scaled && J.metric == M_DTW;
+    const bool wrap = J.scaled && !ucr;
+    const bool want_m = !dtwfam || (J.metric == M_ADTW && J.p.p < 0);
+    const double thr = J.threshold;
+    do {
+      double *dx = nullptr, *ds = nullptr, *dout = nullptr;
+      if ((rc = ws.alloc(&dx, (size_t)rows * T)) || (rc = h2d_rows(dx, J.x + lo * J.xs, rows, T, J.xs, st))) break;
+      if ((rc = ws.alloc(&ds, (size_t)(nsub * m))) || (rc = ws.alloc(&dout, (size_t)(rows * nw)))) break;
+      WB_CK(cudaMemcpyAsync(ds, J.s + (paired ? lo * m : 0), sizeof(double) * nsub * m, cudaMemcpyHostToDevice, st));
+      kt.start();
+      if (deriv && m < 3) {
+        // EL:843-844 (ddtw_subsequence_matches returns no match), EL:3297 (the wrap's _eadistance accepts nothing)
+        k_fill<<<256, 256, 0, st>>>(dout, rows * nw, __builtin_nan(""));
+        WB_CK(cudaGetLastError());
+      } else {
+        // unscaled derivative metrics: the derivative of a window is the window of the derivative (EL:3220-3225)
+        const int64_t Tp = (deriv && !wrap) ? T - 2 : T, mp = (deriv && !wrap) ? m - 2 : m;
+        double *dxp = dx, *dsp = ds;
+        if (deriv && !wrap) {
+          if ((rc = ws.alloc(&dxp, (size_t)rows * Tp)) || (rc = ws.alloc(&dsp, (size_t)(nsub * mp)))) break;
+          k_slope<<<1024, 256, 0, st>>>(dx, rows, (int)T, dxp);
+          k_slope<<<256, 256, 0, st>>>(ds, nsub, (int)m, dsp);
+          WB_CK(cudaGetLastError());
+        }
+        const double *dw = nullptr, *dtw = nullptr;
+        if (J.metric == M_WDTW || J.metric == M_WDDTW || J.metric == M_TWE) {
+          const int64_t tn = J.metric == M_TWE ? T + 1 : (deriv ? T - 2 : T);
+          ws.host_keep.push_back(J.metric == M_TWE ? make_tw(J.p.stiffness, tn) : make_weights(J.p.g, tn));
+          std::vector<double>& h = ws.host_keep.back();
+          double* d = nullptr;
+          if ((rc = ws.alloc(&d, h.size()))) break;
+          WB_CK(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+          (J.metric == M_TWE ? dtw : dw) = d + table_center(tn);
+        }
+        // thresholds: what the DP is abandoned against (thr_m, compared with M) and what the distance is compared with
+        double thr_d = thr, thr_m = thr; int strict = wrap ? 1 : 0, apply_sqrt = 0;
+        if (dtwfam) {
+          thr_m = thr * thr;
+          if (!wrap) { thr_d = thr * thr; apply_sqrt = 1; }  // unscaled + scaled_dtw: squared-cost domain, sqrt of a match
+        } else if (J.metric == M_LCSS) thr_m = std::isinf(thr) ? thr : (double)m - thr * (double)m;
+        else if (J.metric == M_EDR) thr_m = thr * (double)(wrap ? m : T);
+        // unscaled edr with the default epsilon: the policy takes max(sx, sy) / 4 with sx = 4 * (std / 4), sy = 0
+        double* edr_sx = nullptr;
+        if (J.metric == M_EDR && !wrap && std::isnan(J.p.epsilon)) {
+          ws.host_keep.emplace_back((size_t)nsub);
+          std::vector<double>& h = ws.host_keep.back();
+          for (int64_t k = 0; k < nsub; ++k) h[(size_t)k] = J.s_eps[paired ? lo + k : 0] * 4.0;
+          if ((rc = ws.alloc(&edr_sx, (size_t)nsub))) break;
+          WB_CK(cudaMemcpyAsync(edr_sx, h.data(), sizeof(double) * nsub, cudaMemcpyHostToDevice, st));
+        }
+        int64_t step = std::max<int64_t>(1, std::min<int64_t>(rows, ((int64_t)1 << 28) / std::max<int64_t>(nw, 1)));
+        if (wrap) {
+          int64_t budget = (int64_t)32 << 20;  // doubles of materialised windows per pass
+          if (const char* e = getenv("WILDBOAR_CUDA_SCAN_WINDOW_BUDGET")) { const long long v = atoll(e); if (v > 0) budget = v; }
+          step = std::max<int64_t>(1, std::min<int64_t>(step, budget / std::max<int64_t>(nw * m, 1)));
+        }
+        for (int64_t r0 = 0; r0 < rows && !rc; r0 += step) {
+          const int64_t nr = std::min(step, rows - r0);
+          const long long n = nr * nw;
+          Workspace it(st);
+          int2* list = nullptr; int* dlen = nullptr;
+          double *draw = nullptr, *mraw = nullptr, *dkim = nullptr;
+          if ((rc = it.alloc(&list, (size_t)n)) || (rc = it.alloc(&dlen, 1)) || (rc = it.alloc(&draw, (size_t)n)) ||
+              (want_m && (rc = it.alloc(&mraw, (size_t)n)))) break;
+          const int n32 = (int)n;
+          WB_CK(cudaMemcpyAsync(dlen, &n32, sizeof(int), cudaMemcpyHostToDevice, st));
+          DpCall c; memset(&c, 0, sizeof c);
+          c.metric = J.metric; c.p = J.p; c.mode = PM_LISTP; c.list = list; c.list_len = dlen; c.list_n = n;
+          long long ystride, ldk = 0;
+          if (wrap) {
+            double *mean = nullptr, *stdv = nullptr, *wn = nullptr;
+            if ((rc = it.alloc(&mean, (size_t)n)) || (rc = it.alloc(&stdv, (size_t)n)) || (rc = it.alloc(&wn, (size_t)(n * m)))) break;
+            k_inc_window_stats<<<(unsigned)((nr + 63) / 64), 64, 0, st>>>(dx + r0 * T, nr, (int)T, (int)m, mean, stdv);
+            k_normalise_windows<<<148 * 8, 256, 0, st>>>(dx + r0 * T, nr, (int)T, (int)m, mean, stdv, wn);
+            WB_CK(cudaGetLastError());
+            stats.launches += 2;
+            c.x = ds; c.nx = nsub; c.Tx = (int)m; c.y = wn; c.ny = n; c.Ty = (int)m; c.ea = 1;
+            if ((rc = prepare_operands(it, c))) break;
+            if (dw) c.tab.weights = dw;
+            ystride = nw;
+          } else if (ucr) {
+            double *mean = nullptr, *stdv = nullptr;
+            if ((rc = it.alloc(&mean, (size_t)(nr * T))) || (rc = it.alloc(&stdv, (size_t)(nr * T))) || (rc = it.alloc(&dkim, (size_t)(nr * T)))) break;
+            k_window_stats<<<(unsigned)((nr + 127) / 128), 128, 0, st>>>(dx + r0 * T, nr, (int)T, (int)m, mean, stdv);
+            k_ucr_kim<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dx + r0 * T, nr, (int)T, (int)m, ds + (paired ? r0 * m : 0), mean, stdv, dkim,
+                                                                   paired ? m : 0);
+            WB_CK(cudaGetLastError());
+            stats.launches += 2;
+            c.metric = M_SCALED_DTW;
+            c.px = ds; c.nx = nsub; c.ptx = (int)m; c.py = dx + r0 * T; c.pty = (int)m; c.ys = 1; c.ny = nr * T - m + 1;
+            c.R = (int)compute_warp_width(m, J.p.r) + 1; c.sy = mean; c.sy2 = stdv; c.raw = 1;
+            ystride = T; ldk = T;
+          } else {
+            c.metric = J.metric == M_DDTW ? M_DTW : (J.metric == M_WDDTW ? M_WDTW : J.metric);  // the DP on prepared data
+            c.px = dsp; c.nx = nsub; c.ptx = (int)mp; c.py = dxp + r0 * Tp; c.pty = (int)mp; c.ys = 1; c.ny = nr * Tp - mp + 1;
+            c.R = (int)compute_r(m, J.p.r);  // from the ORIGINAL subsequence length (EL:2253, 2480)
+            c.tab.weights = dw; c.tab.tw = dtw; c.raw = dtwfam ? 1 : 0;
+            if (J.metric == M_ERP) {
+              double *sx = nullptr, *sy = nullptr;
+              if ((rc = it.alloc(&sx, (size_t)nsub)) || (rc = it.alloc(&sy, (size_t)c.ny))) break;
+              k_series_stat<<<(unsigned)((nsub + 127) / 128), 128, 0, st>>>(c.px, nsub, (int)m, 0, J.p.g, sx, m);
+              k_series_stat<<<(unsigned)((c.ny + 127) / 128), 128, 0, st>>>(c.py, c.ny, (int)m, 0, J.p.g, sy, 1);
+              WB_CK(cudaGetLastError());
+              stats.launches += 2;
+              c.sx = sx; c.sy = sy;
+            }
+            if (edr_sx) c.sx = edr_sx;
+            ystride = Tp;
+          }
+          k_profile_list<<<148 * 4, 256, 0, st>>>(list, n, (int)nw, ystride, (int)r0, paired ? 1 : 0);
+          WB_CK(cudaGetLastError());
+          if ((rc = launch_dp(it, di, c, 0, c.nx, 0, c.ny, draw, 0, mraw, nullptr, &stats))) break;
+          k_profile_select<<<148 * 4, 256, 0, st>>>(draw, mraw, dkim, n, (int)nw, ldk, thr_d, thr_m, strict, apply_sqrt, dout + r0 * nw);
+          WB_CK(cudaGetLastError());
+          stats.launches += 2;
+          for (auto& v : it.host_keep) ws.host_keep.push_back(std::move(v));
+        }
+        if (rc) break;
+      }
+      kt.stop();
+      if (cudaMemcpyAsync(J.out + lo * nw, dout, sizeof(double) * rows * nw, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          cudaStreamSynchronize(st) != cudaSuccess) { set_err("device-to-host copy of the distance profile failed"); rc = 1; break; }
+      stats.kernel_ms = kt.ms();
+    } while (0);
+    total.stop();
+    if (!rc) { cudaStreamSynchronize(st); stats.total_ms = total.ms(); }
+  }
+  cudaStreamSynchronize(st);
+  cudaStreamDestroy(st);
+  if (st_out) *st_out = stats;
+  return rc;
+}
+
+// rows of x in contiguous blocks over the devices, one host thread per device
+template <class Worker>
+static int run_row_sharded(int64_t nx, const int* devices, int n_devices, wb_stats* stats, Worker worker) {
+  int ndev_avail = 0;
+  if (cudaGetDeviceCount(&ndev_avail) != cudaSuccess || ndev_avail < 1) {
+    set_err("no CUDA device available: wildboar_b200 has no CPU fallback");
+    return 1;
+  }
+  std::vector<int> devs;
+  if (devices && n_devices > 0) devs.assign(devices, devices + n_devices); else devs.push_back(0);
+  for (int d : devs) if (d < 0 || d >= ndev_avail) { set_err("invalid device ordinal"); return 1; }
+  const int G = (int)std::min<int64_t>((int64_t)devs.size(), std::max<int64_t>(nx, 1));
+  std::vector<int64_t> off;
+  row_blocks(nx, G, off);
+  std::vector<wb_stats> sts((size_t)G);
+  std::vector<int> rcs((size_t)G, 0);
+  std::vector<std::string> errs((size_t)G);
+  if (G == 1) { rcs[0] = worker(devs[0], off[0], off[1], &sts[0]); errs[0] = g_err; }
+  else {
+    std::vector<std::thread> th;
+    for (int b = 0; b < G; ++b)
+      th.emplace_back([&, b]() { rcs[(size_t)b] = worker(devs[(size_t)b], off[(size_t)b], off[(size_t)b + 1], &sts[(size_t)b]); errs[(size_t)b] = g_err; });
+    for (auto& t : th) t.join();
+  }
+  for (int b = 0; b < G; ++b) if (rcs[(size_t)b]) { set_err(errs[(size_t)b]); return rcs[(size_t)b]; }
+  if (stats) {
+    memset(stats, 0, sizeof *stats);
+    for (int b = 0; b < G; ++b) {
+      stats->kernel_ms = std::max(stats->kernel_ms, sts[(size_t)b].kernel_ms);
+      stats->total_ms = std::max(stats->total_ms, sts[(size_t)b].total_ms);
+      stats->cells += sts[(size_t)b].cells; stats->pairs += sts[(size_t)b].pairs; stats->launches += sts[(size_t)b].launches;
+      stats->engine = std::max(stats->engine, sts[(size_t)b].engine);
+    }
+  }
+  return 0;
+}
+
 static int run_subsequence(const SubseqJob& J, const int* devices, int n_devices, wb_stats* stats) {
   int ndev_avail = 0;
   if (cudaGetDeviceCount(&ndev_avail) != cudaSuccess || ndev_avail < 1) {
@@ -1564,6 +1763,28 @@ int wb_cuda_subsequence(int metric, const wb_params* params, const double* s, co
   J.paired = paired ? 1 : 0; J.scaled = scaled ? 1 : 0; J.s_eps = (metric == M_EDR && !scaled) ? s_epsilon : nullptr;
   J.out_dist = out_dist; J.out_idx = out_idx;
   return run_subsequence(J, devices, n_devices, stats);
+}
+
+int wb_cuda_subsequence_profile(int metric, const wb_params* params, const double* s, int64_t n_s, int64_t m,
+                                const double* x, int64_t nx, int64_t T, int64_t x_stride, int scaled, const double* s_epsilon,
+                                double threshold, double* out, const int* devices, int n_devices, wb_stats* stats) {
+  if (check_common(metric, params, x, nx, T)) return 1;
+  if (!s || !out) { set_err("null argument"); return 1; }
+  if (metric == M_WLCSS) { set_err("wlcss has no subsequence metric in the reference (_distance.py:143-178)"); return 1; }
+  if (params->precision != 0) { set_err("subsequence search runs in fp64"); return 1; }
+  if (n_s != 1 && n_s != nx) { set_err("the profile needs one subsequence, or one per sample"); return 1; }
+  if (m < 1 || m > T) { set_err("the subsequence needs 1 <= length <= n_timestep"); return 1; }
+  if (scaled && metric == M_DTW && m < 3) { set_err("scaled_dtw needs subsequences of at least 3 samples (the reference's LB_Kim reads S[1], S[2])"); return 1; }
+  if (std::isnan(threshold)) { set_err("threshold must not be NaN"); return 1; }
+  if (metric == M_EDR && !scaled && std::isnan(params->epsilon)) {
+    if (!s_epsilon) { set_err("edr with the default epsilon needs s_epsilon (std / 4 per subsequence)"); return 1; }
+    for (int64_t k = 0; k < n_s; ++k) if (!(s_epsilon[k] >= 0.0)) { set_err("s_epsilon must not be negative"); return 1; }
+  }
+  wb::ProfileJob J;
+  J.metric = metric; J.p = *params; J.s = s; J.ns = n_s; J.m = m; J.x = x; J.nx = nx; J.T = T; J.xs = x_stride;
+  J.scaled = scaled ? 1 : 0; J.s_eps = s_epsilon; J.threshold = threshold; J.out = out;
+  return run_row_sharded(nx, devices, n_devices, stats,
+                         [&](int dev, int64_t lo, int64_t hi, wb_stats* st) { return subseq_profile_worker(J, dev, lo, hi, st); });
 }
 
 int wb_cuda_pairwise_dev(int metric, const wb_params* params, const double* d_x, int64_t nx, int64_t Tx,

@@ -14,14 +14,17 @@ followed by a first-minimum reduction per sample -- or, where the reference's ea
 The non-elastic subsequence metrics (euclidean, manhattan, mass, ...) are not part of this path; there is no CPU
 fallback.
 """
+import math
 import numbers
+import warnings
 
 import numpy as np
 
 from . import _shim
 from .distance import _check_ts_array, _format_return, _make_metric, check_array
 
-__all__ = ["pairwise_subsequence_distance", "paired_subsequence_distance"]
+__all__ = ["pairwise_subsequence_distance", "paired_subsequence_distance", "subsequence_match",
+           "paired_subsequence_match", "distance_profile"]
 
 _SUBSEQUENCE_METRICS = ("dtw", "wdtw", "adtw", "ddtw", "wddtw", "lcss", "erp", "edr", "msm", "twe")
 
@@ -132,3 +135,252 @@ def paired_subsequence_distance(y, x, *, dim=0, metric="dtw", metric_params=None
     if return_index:
         return _format_return(min_dist, len(y), x.ndim), _format_return(min_ind, len(y), x.ndim)
     return _format_return(min_dist, len(y), x.ndim)
+
+
+# ---------------------------------------------------------------------------------------------
+# subsequence_match / paired_subsequence_match / distance_profile (_distance.py:732-1080, 1477-1600)
+# ---------------------------------------------------------------------------------------------
+def _std_below_mean(mult):
+    """_distance.py:310-333: max(mean - mult * std, min)."""
+    def f(d):
+        return max(np.mean(d) - mult * np.std(d), np.min(d))
+    return f
+
+
+_THRESHOLD = {"auto": _std_below_mean(2.0)}
+
+
+def _jagged(lst):
+    arr = np.empty(len(lst), dtype=object)
+    arr[:] = lst
+    return arr
+
+
+def _rows_to_matches(dense):
+    """(n_samples, n_windows) with NaN = no match  ->  per-sample (indices, distances) arrays, None where nothing matched
+    (`_new_match_array` / `_new_distance_array`, _cdistance.pyx:936-953; matches in window order)."""
+    indices, distances = [], []
+    for row in dense:
+        idx = np.flatnonzero(~np.isnan(row))
+        if idx.size == 0:
+            indices.append(None)
+            distances.append(None)
+        else:
+            indices.append(idx.astype(np.intp))
+            distances.append(row[idx])
+    return indices, distances
+
+
+def _filter(indices, distances, keep):
+    out_i, out_d = [], []
+    for sample, (index, distance) in enumerate(zip(indices, distances)):
+        if index is None:
+            out_i.append(None)
+            out_d.append(None)
+        else:
+            sel = keep(sample, index, distance)
+            out_i.append(index[sel])
+            out_d.append(distance[sel])
+    return out_i, out_d
+
+
+def _keep_nontrivial(exclude):
+    """_exclude_trivial_matches (_distance.py:400-443): best matches first, drop those within `exclude` of a kept one."""
+    def keep(_, index, distance):
+        order = np.argsort(distance)
+        sel = np.zeros(order.size, dtype=bool)
+        kept = []
+        for o in order:
+            if not any(index[o] - exclude < e < index[o] + exclude for e in kept):
+                kept.append(index[o])
+                sel[o] = True
+        return sel
+    return keep
+
+
+def _resolve_threshold(threshold, max_matches, n_samples, allow_array):
+    """threshold / max_matches defaults and the post-filter of the match functions (_distance.py:848-893, 1033-1055)."""
+    if threshold is None:
+        threshold = np.inf
+        if max_matches is None:
+            max_matches = 10
+    max_dist = None
+    if callable(threshold) or isinstance(threshold, str):
+        if isinstance(threshold, str):
+            if threshold not in _THRESHOLD:
+                raise ValueError("threshold must be one of %s, got %r" % (set(_THRESHOLD), threshold))
+            fn = _THRESHOLD[threshold]
+        else:
+            fn = threshold
+
+        def max_dist(_, d):
+            return d <= fn(d)
+        threshold = np.inf
+    elif allow_array and _is_arraylike(threshold):
+        arr = np.asarray(threshold)
+        if len(arr) != n_samples:
+            raise ValueError(f"threshold array length ({len(arr)}) must match the number of samples ({n_samples})")
+
+        def max_dist(i, d):
+            return d <= arr[i]
+        threshold = np.inf
+    elif not isinstance(threshold, numbers.Real):
+        raise TypeError("threshold must be str, callable%s or float, not %s"
+                        % (", array-like" if allow_array else "", type(threshold).__qualname__))
+    return float(threshold), max_matches, max_dist
+
+
+def _profile(subs, xd, metric, m, scaled, threshold, mean_std):
+    """Dense matches of subs ((m,) or (n, m)) against the samples xd through the C ABI."""
+    sub2 = np.atleast_2d(subs)
+    s_eps = None
+    if metric == "edr" and not scaled and np.isnan(m._params().epsilon):
+        s_eps = np.array([mean_std(s)[1] / 4.0 for s in sub2], dtype=np.double)
+    if scaled:
+        if metric == "dtw" and sub2.shape[1] < 3:
+            raise ValueError("scaled_dtw needs subsequences of at least 3 samples (the reference reads S[1], S[2] unconditionally)")
+        normed = []
+        for s in sub2:
+            mean, std = mean_std(s)
+            if std == 0:
+                raise ValueError("constant subsequence: the reference divides by its zero standard deviation on this path")
+            normed.append((s - mean) / std)
+        sub2 = np.array(normed)
+    return _shim.subsequence_profile(m.metric_id, m._params(), sub2, xd, scaled=scaled, s_epsilon=s_eps, threshold=threshold)
+
+
+def _from_array_mean_std(s):
+    mean, std = _mean_std(s)
+    return mean, std
+
+
+def _view_mean_std(s):
+    """_ts_view_update_statistics (_cdistance.pyx:167-185): sequential sums; the std is handed on as is (0 when the variance
+    is <= 1e-13) by _DistanceProfile (_cdistance.pyx:1686-1697)."""
+    ex = np.cumsum(s)[-1]
+    ex2 = np.cumsum(s * s)[-1]
+    mean = ex / s.shape[0]
+    var = ex2 / s.shape[0] - mean * mean
+    return mean, (np.sqrt(var) if var > _EPSILON else 0.0)
+
+
+def subsequence_match(y, x, threshold=None, *, dim=0, metric="dtw", metric_params=None, scale=False, max_matches=None,
+                      exclude=None, return_distance=False, n_jobs=None):
+    """Start indices (and distances) of the windows of every sample that match the subsequence (_distance.py:732-924).
+
+    Same threshold forms (None -> the 10 best, float, "auto", callable, per-sample array), ``exclude`` and ``max_matches``
+    post-filters and return shapes as the reference; the per-window distances come from ONE device launch over all
+    windows of all samples (wb_cuda_subsequence_profile).  ``dim`` may select any dimension (the reference only accepts 0).
+    """
+    y = _validate_subsequence(y)
+    if len(y) > 1:
+        raise ValueError("A single subsequence expected, got %d" % len(y))
+    y = y[0]
+    x = check_array(x, allow_3d=True, ensure_2d=False, dtype=np.double)
+    if y.shape[0] > x.shape[-1]:
+        raise ValueError("Invalid subsequnce shape (%d > %d)" % (y.shape[0], x.shape[-1]))
+    metric, scaled = _check_subsequence_metric(metric, scale)
+    m = _make_metric(metric, metric_params)
+    x_ = _check_ts_array(x)
+    if isinstance(dim, bool) or not isinstance(dim, numbers.Integral) or not 0 <= dim < x_.shape[1]:
+        raise ValueError("The parameter dim must be 0 <= dim < n_dims")
+    if n_jobs is not None:
+        warnings.warn("n_jobs is not yet supported.", UserWarning)
+    n_samples = x.shape[0] if x.ndim > 1 else 1
+    threshold, max_matches, max_dist = _resolve_threshold(threshold, max_matches, n_samples, allow_array=True)
+    if exclude is not None and (isinstance(exclude, bool) or not isinstance(exclude, (numbers.Integral, numbers.Real))):
+        raise TypeError("exclude must be an int or a float, got %s" % type(exclude).__qualname__)
+    if exclude is not None and exclude < 0:
+        raise ValueError("exclude == %r, must be >= 0." % (exclude,))
+    if exclude is not None and not isinstance(exclude, numbers.Integral):
+        exclude = math.ceil(y.size * exclude)
+    dense = _profile(y, x_[:, int(dim), :], metric, m, scaled, threshold, _from_array_mean_std)
+    indices, distances = _rows_to_matches(dense)
+    if max_dist is not None:
+        indices, distances = _filter(indices, distances, lambda i, _, d: max_dist(i, d))
+    if exclude:
+        indices, distances = _filter(indices, distances, _keep_nontrivial(exclude))
+    if max_matches:
+        indices, distances = _filter(indices, distances, lambda _, __, d: np.argsort(d)[:max_matches])
+    indices = _format_return(_jagged(indices), len(y), x.ndim)
+    if indices.size == 1:
+        indices = indices.item()
+    if return_distance:
+        distances = _format_return(_jagged(distances), len(y), x.ndim)
+        if distances.size == 1:
+            distances = distances.item()
+        return indices, distances
+    return indices
+
+
+def paired_subsequence_match(y, x, threshold=None, *, dim=0, metric="dtw", metric_params=None, scale=False, max_matches=None,
+                             return_distance=False, n_jobs=None):
+    """Matches of the i:th subsequence in the i:th sample (_distance.py:927-1080); subsequences of equal length share one
+    device launch."""
+    y = _validate_subsequence(y)
+    x = check_array(x, allow_3d=True, ensure_2d=False, dtype=np.double)
+    n_samples = x.shape[0] if x.ndim > 1 else 1
+    if len(y) != n_samples:
+        raise ValueError("The number of subsequences and samples must be the same, got %d subsequences and %d samples."
+                         % (len(y), n_samples))
+    for s in y:
+        if s.shape[0] > x.shape[-1]:
+            raise ValueError("invalid subsequnce shape (%d > %d)" % (s.shape[0], x.shape[-1]))
+    metric, scaled = _check_subsequence_metric(metric, scale)
+    m = _make_metric(metric, metric_params)
+    x_ = _check_ts_array(x)
+    if isinstance(dim, bool) or not isinstance(dim, numbers.Integral) or not 0 <= dim < x_.shape[1]:
+        raise ValueError("The parameter dim must be 0 <= dim < n_dims")
+    if n_jobs is not None:
+        warnings.warn("n_jobs is not yet supported.", UserWarning)
+    threshold, max_matches, max_dist = _resolve_threshold(threshold, max_matches, n_samples, allow_array=False)
+    xd = x_[:, int(dim), :]
+    indices, distances = [None] * n_samples, [None] * n_samples
+    lengths = np.array([s.shape[0] for s in y])
+    for length in np.unique(lengths):
+        sel = np.flatnonzero(lengths == length)
+        dense = _profile(np.array([y[q] for q in sel]), np.ascontiguousarray(xd[sel]), metric, m, scaled, threshold,
+                         _from_array_mean_std)
+        gi, gd = _rows_to_matches(dense)
+        for q, a, b in zip(sel, gi, gd):
+            indices[q], distances[q] = a, b
+    if max_dist is not None:
+        indices, distances = _filter(indices, distances, lambda i, _, d: max_dist(i, d))
+    if max_matches:
+        indices, distances = _filter(indices, distances, lambda _, __, d: np.argsort(d)[:max_matches])
+    indices = _format_return(_jagged(indices), len(y), x.ndim)
+    if indices.size == 1:
+        indices = indices.reshape(1)
+    if return_distance:
+        distances = _format_return(_jagged(distances), len(y), x.ndim)
+        if distances.size == 1:
+            distances = distances.reshape(1)
+        return indices, distances
+    return indices
+
+
+def distance_profile(y, x, *, dilation=1, padding=0, dim=0, metric="dtw", metric_params=None, scale=False, n_jobs=None):
+    """Distance of the i:th subsequence to every window of the i:th sample (_distance.py:1477-1600, the
+    ``dilation=1, padding=0`` branch that ends in ``_distance_profile``, _cdistance.pyx:1655-1725).
+
+    The dilated / padded branch (``_dilated_distance_profile``) is not part of the CUDA path and raises."""
+    if dilation != 1 or padding != 0:
+        raise ValueError("wildboar_b200.distance_profile covers dilation=1, padding=0; use wildboar.distance for the dilated form")
+    y = np.squeeze(check_array(y, dtype=np.double, ensure_2d=False))
+    x = np.squeeze(check_array(x, allow_3d=True, ensure_2d=False, dtype=np.double))
+    if x.ndim == 1 and y.ndim != 1:
+        x = np.broadcast_to(x, shape=(y.shape[0], x.shape[0]))
+    if y.ndim == 1 and x.ndim != 1:
+        y = np.broadcast_to(y, shape=(x.shape[0], y.shape[0]))
+    x_ = _check_ts_array(x)
+    y_ = _check_ts_array(y)
+    if y_.shape[2] > x_.shape[2]:
+        raise ValueError("subsequence in y is larger than input in x.")
+    if y_.shape[0] != x_.shape[0]:
+        raise ValueError("y and x must have the same number of samples.")
+    if isinstance(dim, bool) or not isinstance(dim, numbers.Integral) or dim < 0 or dim >= x_.shape[1]:
+        raise ValueError(f"The parameter dim must be dim ({dim}) < n_dims ({x_.shape[1]})")
+    metric, scaled = _check_subsequence_metric(metric, scale)
+    m = _make_metric(metric, metric_params)
+    dp = _profile(np.ascontiguousarray(y_[:, 0, :]), x_[:, int(dim), :], metric, m, scaled, np.inf, _view_mean_std)
+    return np.squeeze(dp)
