@@ -223,6 +223,20 @@ int wb_cuda_subsequence_profile(int metric, const wb_params *params,
                                 int scaled, const double *s_epsilon, double threshold, double *out,
                                 const int *devices, int n_devices, wb_stats *stats);
 
+/* The k closest windows of sample i to subsequence i.  Replaces `_argmin_subsequence_distance`
+ * (_cdistance.pyx:1380-1600: `_ArgminSubsequenceDistance` for scaled == 0, `_ScaledArgminSubsequenceDistance` otherwise), the
+ * driver behind argmin_subsequence_distance (_distance.py:1636-1790): per sample a sequential scan of the windows with
+ * Metric._eadistance against the running bound (+inf until the k-heap is full, then its maximum, utils/_misc.pyx:62-107).
+ * s: (nx, m) dense; scaled != 0: s already z-normalised by the caller with fast_mean_std (utils/_stats.pyx:22-42, std 0 -> 1)
+ * and every window z-normalised on the device with the running IncStats; wdtw / wddtw weights over T / T - 2.
+ * out_idx / out_dist: (nx, k) in the heap's array order.  Same device scheme as the profile (all windows of all samples in
+ * one DP launch) followed by the exact replay of the scan, one warp per sample. */
+int wb_cuda_subsequence_argmin(int metric, const wb_params *params,
+                               const double *s, int64_t n_s, int64_t m,
+                               const double *x, int64_t nx, int64_t T, int64_t x_stride,
+                               int scaled, int64_t k, int64_t *out_idx, double *out_dist,
+                               const int *devices, int n_devices, wb_stats *stats);
+
 /* Device-resident variant of wb_cuda_pairwise: d_x (nx, Tx), d_y (ny, Ty), d_out (nx, ny) are
  * dense row-major DEVICE arrays on the current device.  Enqueues on `stream`; fills `stats`
  * (after synchronising the stream) when stats != NULL. */

@@ -931,57 +931,98 @@ void orc_inc_window_stats(const double *x, int64_t t_len, int64_t s_len, double 
   }
 }
 
+/* Metric._eadistance(sb, xb) of two equal-length buffers against the running bound md (EL:3188-3213, 3289-3320, 3376-3401,
+ * 3508-3536, 3638-3665, 3847-3881, 3953-3979, 4053-4079): the value the reference compares with md (sqrt domain for the DTW
+ * family); *valid = 0 for ddtw / wddtw below three samples (returns False).  weights: over the series length (reset(X, X)). */
+typedef struct { double *cost, *cost_prev, *a1, *a2, *weights; } ea_scratch;
+static double ea_eval(int metric, const orc_params *p, const double *sb, const double *xb, int64_t s_len, double md,
+                      ea_scratch *w, int *valid) {
+  const int64_t r = orc_compute_r(s_len, p->r);
+  *valid = 1;
+  switch (metric) {
+    case ORC_DTW: case ORC_WDTW:
+      return sqrt(dtw_distance(sb, s_len, xb, s_len, r, w->cost, w->cost_prev, w->weights, md * md));
+    case ORC_ADTW:
+      return sqrt(adtw_distance(sb, s_len, xb, s_len, r, w->cost, w->cost_prev, p->p, md * md));
+    case ORC_DDTW: case ORC_WDDTW:
+      if (s_len < 3) { *valid = 0; return 0; }
+      orc_average_slope(sb, s_len, w->a1); orc_average_slope(xb, s_len, w->a2);
+      return sqrt(dtw_distance(w->a1, s_len - 2, w->a2, s_len - 2, orc_compute_r(s_len - 2, p->r), w->cost, w->cost_prev,
+                               w->weights, md * md));
+    case ORC_LCSS: case ORC_WLCSS:
+      return lcss_distance(sb, s_len, xb, s_len, r, p->epsilon, w->cost, w->cost_prev, metric == ORC_WLCSS ? w->weights : NULL,
+                           isinf(md) ? INFINITY : (double)s_len - md * (double)s_len);
+    case ORC_ERP:
+      return erp_distance(sb, s_len, xb, s_len, r, p->g, w->a1, w->a2, w->cost, w->cost_prev, md);
+    case ORC_EDR: {
+      double eps = p->epsilon;
+      if (isnan(eps)) eps = dmax(orc_std(sb, s_len), orc_std(xb, s_len)) / 4.0;
+      return edr_distance(sb, s_len, xb, s_len, r, eps, w->cost, w->cost_prev, md * (double)s_len);
+    }
+    case ORC_MSM:
+      return msm_distance(sb, s_len, xb, s_len, r, p->c, w->cost, w->cost_prev, w->a1, md);
+    case ORC_TWE:
+      return twe_distance(sb, s_len, xb, s_len, r, p->penalty, p->stiffness, w->cost, w->cost_prev, md);
+  }
+  *valid = 0;
+  return NAN;
+}
+static void ea_scratch_init(ea_scratch *w, int metric, const orc_params *p, int64_t t_len) {
+  size_t n = (size_t)(t_len + 2);
+  w->cost = (double *)malloc(sizeof(double) * n); w->cost_prev = (double *)malloc(sizeof(double) * n);
+  w->a1 = (double *)malloc(sizeof(double) * n); w->a2 = (double *)malloc(sizeof(double) * n);
+  w->weights = NULL;
+  if (metric == ORC_WDTW || metric == ORC_WLCSS) { w->weights = (double *)malloc(sizeof(double) * n); orc_weights(p->g, t_len, w->weights); }
+  if (metric == ORC_WDDTW) { w->weights = (double *)malloc(sizeof(double) * n); if (t_len - 2 > 0) orc_weights(p->g, t_len - 2, w->weights); }
+}
+static void ea_scratch_free(ea_scratch *w) { free(w->cost); free(w->cost_prev); free(w->a1); free(w->a2); free(w->weights); }
+
+/* k = 1: ScaledSubsequenceMetricWrap._distance (CD:494-551).  k >= 1 with out_idx / out_dist: the paired scans of
+ * argmin_subsequence_distance, `_ArgminSubsequenceDistance` (scaled == 0, raw buffers) and `_ScaledArgminSubsequenceDistance`
+ * (scaled != 0) CD:1380-1548: the running bound is the heap maximum once the k-heap is full (MI:62-107), the result the heap
+ * array (heap order; entries >= *n_found are whatever calloc left: the reference reads uninitialised memory there). */
+static double subsequence_ea_scan(int metric, const orc_params *p, const double *S, int64_t s_len, double s_mean,
+                                  double s_std, const double *T, int64_t t_len, int scaled, int64_t k, int64_t *out_idx,
+                                  double *out_dist, int64_t *n_found, int64_t *index) {
+  size_t n = (size_t)(t_len + 2);
+  ea_scratch w; ea_scratch_init(&w, metric, p, t_len);
+  double *sb = (double *)malloc(sizeof(double) * n), *xb = (double *)malloc(sizeof(double) * n);
+  double *mean = (double *)malloc(sizeof(double) * n), *std = (double *)malloc(sizeof(double) * n);
+  orc_heap hp; hp.h = (heap_el *)calloc((size_t)k, sizeof(heap_el)); hp.n = 0; hp.cap = k;
+  double min_dist = INFINITY;
+  if (scaled) {
+    for (int64_t i = 0; i < s_len; i++) sb[i] = (S[i] - s_mean) / s_std;
+    orc_inc_window_stats(T, t_len, s_len, mean, std);
+  } else memcpy(sb, S, sizeof(double) * (size_t)s_len);
+  for (int64_t i = 0; i < t_len - s_len + 1; i++) {
+    const double *X = T + i;
+    if (scaled) { for (int64_t j = 0; j < s_len; j++) xb[j] = (T[i + j] - mean[i]) / std[i]; X = xb; }
+    int valid;
+    const double dist = ea_eval(metric, p, sb, X, s_len, min_dist, &w, &valid);
+    if (valid && dist < min_dist) {
+      heap_push(&hp, i, dist);
+      if (index) *index = i;
+      if (k == 1) min_dist = dist;
+    }
+    if (k > 1 || !valid) min_dist = (hp.n == hp.cap) ? hp.h[0].value : INFINITY;
+  }
+  for (int64_t j = 0; j < k && out_idx; j++) { out_idx[j] = hp.h[j].index; out_dist[j] = hp.h[j].value; }
+  if (n_found) *n_found = hp.n;
+  const double best = (k == 1 && hp.n == 1) ? hp.h[0].value : min_dist;
+  free(sb); free(xb); free(mean); free(std); free(hp.h); ea_scratch_free(&w);
+  return best;
+}
+
 double orc_scaled_subsequence_distance(int metric, const orc_params *p, const double *S, int64_t s_len, double s_mean,
                                        double s_std, const double *T, int64_t t_len, int64_t *index) {
-  const int deriv = (metric == ORC_DDTW || metric == ORC_WDDTW);
-  size_t n = (size_t)(t_len + 2);
-  double *cost = (double *)malloc(sizeof(double) * n), *cost_prev = (double *)malloc(sizeof(double) * n);
-  double *sb = (double *)malloc(sizeof(double) * n), *xb = (double *)malloc(sizeof(double) * n);
-  double *a1 = (double *)malloc(sizeof(double) * n), *a2 = (double *)malloc(sizeof(double) * n);
-  double *weights = NULL, *mean = (double *)malloc(sizeof(double) * n), *std = (double *)malloc(sizeof(double) * n);
-  if (metric == ORC_WDTW) { weights = (double *)malloc(sizeof(double) * n); orc_weights(p->g, t_len, weights); }
-  if (metric == ORC_WDDTW) { weights = (double *)malloc(sizeof(double) * n); if (t_len - 2 > 0) orc_weights(p->g, t_len - 2, weights); }
-  double min_dist = INFINITY;
-  for (int64_t i = 0; i < s_len; i++) sb[i] = (S[i] - s_mean) / s_std;
-  orc_inc_window_stats(T, t_len, s_len, mean, std);
-  for (int64_t i = 0; i < t_len - s_len + 1; i++) {
-    for (int64_t j = 0; j < s_len; j++) xb[j] = (T[i + j] - mean[i]) / std[i];
-    double dist;
-    int64_t r = orc_compute_r(s_len, p->r);
-    switch (metric) {
-      case ORC_DTW: case ORC_WDTW:
-        dist = sqrt(dtw_distance(sb, s_len, xb, s_len, r, cost, cost_prev, weights, min_dist * min_dist)); break;
-      case ORC_ADTW:
-        dist = sqrt(adtw_distance(sb, s_len, xb, s_len, r, cost, cost_prev, p->p, min_dist * min_dist)); break;
-      case ORC_DDTW: case ORC_WDDTW:
-        if (s_len < 3) continue;
-        orc_average_slope(sb, s_len, a1); orc_average_slope(xb, s_len, a2);
-        dist = sqrt(dtw_distance(a1, s_len - 2, a2, s_len - 2, orc_compute_r(s_len - 2, p->r), cost, cost_prev, weights,
-                                 min_dist * min_dist));
-        break;
-      case ORC_LCSS:
-        dist = lcss_distance(sb, s_len, xb, s_len, r, p->epsilon, cost, cost_prev, NULL,
-                             isinf(min_dist) ? INFINITY : (double)s_len - min_dist * (double)s_len);
-        break;
-      case ORC_ERP:
-        dist = erp_distance(sb, s_len, xb, s_len, r, p->g, a1, a2, cost, cost_prev, min_dist); break;
-      case ORC_EDR: {
-        double eps = p->epsilon;
-        if (isnan(eps)) eps = dmax(orc_std(sb, s_len), orc_std(xb, s_len)) / 4.0;
-        dist = edr_distance(sb, s_len, xb, s_len, r, eps, cost, cost_prev, min_dist * (double)s_len);
-        break;
-      }
-      case ORC_MSM:
-        dist = msm_distance(sb, s_len, xb, s_len, r, p->c, cost, cost_prev, a1, min_dist); break;
-      case ORC_TWE:
-        dist = twe_distance(sb, s_len, xb, s_len, r, p->penalty, p->stiffness, cost, cost_prev, min_dist); break;
-      default: dist = NAN;
-    }
-    if (dist < min_dist) { min_dist = dist; if (index) *index = i; }
-  }
-  (void)deriv;
-  free(cost); free(cost_prev); free(sb); free(xb); free(a1); free(a2); free(weights); free(mean); free(std);
-  return min_dist;
+  return subsequence_ea_scan(metric, p, S, s_len, s_mean, s_std, T, t_len, 1, 1, NULL, NULL, NULL, index);
+}
+
+int64_t orc_argmin_subsequence(int metric, const orc_params *p, const double *S, int64_t s_len, double s_mean, double s_std,
+                               const double *T, int64_t t_len, int scaled, int64_t k, int64_t *out_idx, double *out_dist) {
+  int64_t n_found = 0;
+  subsequence_ea_scan(metric, p, S, s_len, s_mean, s_std, T, t_len, scaled, k, out_idx, out_dist, &n_found, NULL);
+  return n_found;
 }
 
 /* ------------------------------------------------------------------------------------------

@@ -74,6 +74,19 @@ def main():
             row.update(ref_sample=f"{nxs} pairs, n_jobs={NCPU}", ref_ms=round(t_ref * 1e3, 1), ref_windows_per_s=round(nxs * (T - m + 1) / t_ref),
                        ref_cores=NCPU, ref_bit_equal=bool(np.array_equal(rdp, dp[:nxs])))
         print(json.dumps(row), flush=True)
+    for metric, mp, scale in (("dtw", {"r": 0.1}, False), ("msm", {"r": 0.1}, True)):
+        t_as, (ai, ad) = timed(lambda: wb.argmin_subsequence_distance(Y, Xs, k=5, metric=metric, metric_params=mp, scale=scale, return_distance=True))
+        st = wb.last_stats()
+        row = dict(row="8f-4 argmin_subsequence_distance k=5", metric=("scaled_" if scale else "") + metric,
+                   shape=f"{n} subsequences x {m} paired with {n} samples x {T}, r={mp['r']}", e2e_ms=round(t_as * 1e3, 1),
+                   kernel_ms=round(st["kernel_ms"], 1), launches=st["launches"], windows_per_s=round(n * (T - m + 1) / t_as))
+        if wd is not None:
+            nxs = 64 if QUICK else 256
+            t_ref, (ri, rd) = timed(lambda: wd.argmin_subsequence_distance(Y[:nxs], Xs[:nxs], k=5, metric=metric, metric_params=mp, scale=scale,
+                                                                         return_distance=True, n_jobs=NCPU), reps=1)
+            row.update(ref_sample=f"{nxs} pairs, n_jobs={NCPU}", ref_ms=round(t_ref * 1e3, 1), ref_windows_per_s=round(nxs * (T - m + 1) / t_ref),
+                       ref_cores=NCPU, ref_bit_equal=bool(np.array_equal(ri, ai[:nxs]) and np.array_equal(rd, ad[:nxs])))
+        print(json.dumps(row), flush=True)
     thr = float(np.quantile(dp, 0.01))
     t_sm, (mi, md) = timed(lambda: wb.subsequence_match(shp[0], Xs, threshold=thr, metric="scaled_twe", metric_params={"r": 0.1}, return_distance=True))
     row = dict(row="8f-4 subsequence_match", metric="scaled_twe", shape=f"1 subsequence x {m} vs {n} samples x {T}, threshold = 1 % quantile",

@@ -9,6 +9,7 @@ Writes tests/golden/scan_golden.npz:
            (_cdistance.pyx:470-551) over adtw, wdtw, ddtw, wddtw, lcss, erp, edr, msm, twe
   sm|...   subsequence_match / paired_subsequence_match (_distance.py:732-1080) and distance_profile (:1477-1600) for
            every elastic subsequence metric, unscaled and scaled; jagged results padded with -1 / NaN
+  as|...   argmin_subsequence_distance (_distance.py:1636-1790), k in {1, 4}, scale in {False, True}
 """
 import os
 import sys
@@ -33,6 +34,7 @@ SM_CASES = [("dtw", {"r": 0.1}), ("wdtw", {"r": 0.3, "g": 0.1}), ("adtw", {"r": 
             ("wddtw", {"r": 0.5, "g": 0.2}), ("lcss", {"r": 0.2, "epsilon": 0.5}), ("erp", {"r": 0.1, "g": 0.4}), ("edr", {"r": 0.25}),
             ("edr", {"r": 0.3, "epsilon": 0.8}), ("msm", {"r": 0.15, "c": 0.3}), ("twe", {"r": 0.2, "penalty": 0.5, "stiffness": 0.05})]
 SM_SUBS = (0, 1, 3)   # lengths 12, 30, 3
+AS_CASES = SM_CASES
 
 
 def pad(lst, fill, dtype):
@@ -100,6 +102,16 @@ def main():
             d, i = wd.paired_subsequence_distance(paired, X, metric=prefix + metric, metric_params=mp, return_index=True)
             out[f"{tag}|{ci}|paired_dist"], out[f"{tag}|{ci}|paired_idx"] = d, i.astype(np.int64)
     matches(wd, out, X, subs)
+    n = X.shape[0]
+    Y = np.stack([X[(q + 1) % n, 7 + q:22 + q] for q in range(n)])
+    ragged = [subs[SM_SUBS[q % len(SM_SUBS)]] for q in range(n)]
+    for ci, (metric, mp) in enumerate(AS_CASES):
+        for scale in (False, True):
+            for k in (1, 4):
+                i_, d_ = wd.argmin_subsequence_distance(Y, X, k=k, metric=metric, metric_params=mp, scale=scale, return_distance=True)
+                out[f"as|{ci}|{int(scale)}|{k}|idx"], out[f"as|{ci}|{int(scale)}|{k}|dist"] = i_.astype(np.int64), d_
+            i_, d_ = wd.argmin_subsequence_distance(ragged, X, k=3, metric=metric, metric_params=mp, scale=scale, return_distance=True)
+            out[f"as|{ci}|{int(scale)}|ragged|idx"], out[f"as|{ci}|{int(scale)}|ragged|dist"] = i_.astype(np.int64), d_
     path = os.path.join(HERE, "scan_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")

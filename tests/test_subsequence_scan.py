@@ -312,3 +312,76 @@ def test_profile_larger_matches_oracle(W, oracle):
         finally:
             W.set_devices([0])
         assert _same(dp2, oracle.subsequence_matches("msm", np.stack([s] * 33), X, np.inf, True, mean_std=_view_mean_std, r=0.1))
+
+
+# ---------------------------------------------------------------------------------------------
+# argmin_subsequence_distance
+# ---------------------------------------------------------------------------------------------
+from make_golden_scan import AS_CASES  # noqa: E402
+
+
+def _as_inputs(g):
+    X = g["X"]
+    n = X.shape[0]
+    Y = np.stack([X[(q + 1) % n, 7 + q:22 + q] for q in range(n)])
+    ragged = [g[f"s{SM_SUBS[q % len(SM_SUBS)]}"] for q in range(n)]
+    return X, Y, ragged
+
+
+@pytest.mark.parametrize("ci", range(len(AS_CASES)))
+def test_oracle_argmin_subsequence_matches_reference_golden(oracle, scan_golden, ci):
+    g = scan_golden
+    metric, mp = AS_CASES[ci]
+    X, Y, ragged = _as_inputs(g)
+    for scale in (False, True):
+        for k in (1, 4):
+            i_, d_ = oracle.argmin_subsequence(metric, list(Y), X, k=k, scaled=scale, **mp)
+            assert np.array_equal(i_, g[f"as|{ci}|{int(scale)}|{k}|idx"]) and np.array_equal(d_, g[f"as|{ci}|{int(scale)}|{k}|dist"]), (metric, scale, k)
+        i_, d_ = oracle.argmin_subsequence(metric, ragged, X, k=3, scaled=scale, **mp)
+        assert np.array_equal(i_, g[f"as|{ci}|{int(scale)}|ragged|idx"]) and np.array_equal(d_, g[f"as|{ci}|{int(scale)}|ragged|dist"])
+
+
+def test_argmin_subsequence_host_logic(wb):
+    x = np.zeros((3, 10))
+    with pytest.raises(ValueError, match="same number of samples"):
+        wb.argmin_subsequence_distance(np.zeros((2, 4)), x, metric="dtw")
+    with pytest.raises(ValueError, match="longest subsequence"):
+        wb.argmin_subsequence_distance(np.zeros((3, 11)), x, metric="dtw")
+    with pytest.raises(ValueError, match="k must be less"):
+        wb.argmin_subsequence_distance(np.zeros((3, 4)), x, k=8, metric="dtw")
+    with pytest.raises(ValueError, match="1d-array"):
+        wb.argmin_subsequence_distance([np.zeros((2, 2))] * 3, x, metric="dtw")
+    with pytest.raises(ValueError):
+        wb.argmin_subsequence_distance(np.zeros((3, 4)), x, metric="euclidean")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ci", range(len(AS_CASES)))
+def test_argmin_subsequence_matches_reference_golden(W, scan_golden, ci):
+    g = scan_golden
+    metric, mp = AS_CASES[ci]
+    X, Y, ragged = _as_inputs(g)
+    for scale in (False, True):
+        for k in (1, 4):
+            i_, d_ = W.argmin_subsequence_distance(Y, X, k=k, metric=metric, metric_params=mp, scale=scale, return_distance=True)
+            assert np.array_equal(i_, g[f"as|{ci}|{int(scale)}|{k}|idx"]) and np.array_equal(d_, g[f"as|{ci}|{int(scale)}|{k}|dist"]), (metric, scale, k)
+        i_, d_ = W.argmin_subsequence_distance(ragged, X, k=3, metric=metric, metric_params=mp, scale=scale, return_distance=True)
+        assert np.array_equal(i_, g[f"as|{ci}|{int(scale)}|ragged|idx"]) and np.array_equal(d_, g[f"as|{ci}|{int(scale)}|ragged|dist"])
+    assert np.array_equal(W.argmin_subsequence_distance(Y, X, k=4, metric="scaled_" + metric, metric_params=mp), g[f"as|{ci}|1|4|idx"])
+
+
+@pytest.mark.gpu
+def test_argmin_subsequence_larger_matches_oracle(W, oracle):
+    rng = np.random.default_rng(41)
+    X = np.cumsum(rng.standard_normal((45, 240)), axis=1)
+    Y = np.stack([X[(q + 2) % 45, q:q + 50] for q in range(45)])
+    os.environ["WILDBOAR_CUDA_SCAN_WINDOW_BUDGET"] = str(191 * 50 * 9)
+    try:
+        for metric, mp in (("dtw", {"r": 0.1}), ("ddtw", {"r": 0.1}), ("msm", {"r": 0.1}), ("twe", {"r": 0.05}), ("erp", {"r": 0.1}),
+                           ("edr", {"r": 0.1}), ("lcss", {"r": 0.1, "epsilon": 0.4})):
+            for scale in (False, True):
+                i_, d_ = W.argmin_subsequence_distance(Y, X, k=5, metric=metric, metric_params=mp, scale=scale, return_distance=True)
+                oi, od = oracle.argmin_subsequence(metric, list(Y), X, k=5, scaled=scale, **mp)
+                assert np.array_equal(i_, oi) and np.array_equal(d_, od), (metric, scale)
+    finally:
+        del os.environ["WILDBOAR_CUDA_SCAN_WINDOW_BUDGET"]

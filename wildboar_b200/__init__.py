@@ -17,6 +17,7 @@ from .distance import (  # noqa: F401
     pairwise_distance,
 )
 from .subsequence import (  # noqa: F401
+    argmin_subsequence_distance,
     distance_profile,
     paired_subsequence_distance,
     paired_subsequence_match,
@@ -28,6 +29,6 @@ from ._shim import device_count, get_precision, last_stats, library_path, set_de
 __all__ = [
     "pairwise_distance", "paired_distance", "argmin_distance", "check_metric",
     "pairwise_subsequence_distance", "paired_subsequence_distance", "subsequence_match", "paired_subsequence_match",
-    "distance_profile",
+    "distance_profile", "argmin_subsequence_distance",
     "device_count", "set_devices", "set_precision", "get_precision", "last_stats", "library_path",
 ]

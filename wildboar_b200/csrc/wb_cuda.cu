@@ -1306,6 +1306,9 @@ struct ProfileJob {
   int scaled; const double* s_eps;     // edr, unscaled, default epsilon: std / 4 per subsequence
   double threshold;
   double* out;                         // (nx, T - m + 1)
+  // argmin_subsequence_distance (argmin_k > 0, paired): the k closest windows under the sequential scan with
+  // Metric._eadistance (CD:1380-1548) instead of the dense profile; windows raw (scaled == 0) or z-normalised
+  int64_t argmin_k; int64_t* out_idx; double* out_dist;  // (nx, k), heap order
 };
 
 static int subseq_profile_worker(const ProfileJob& J, int dev, int64_t lo, int64_t hi, wb_stats* st_out) {
@@ -1322,17 +1325,29 @@ static int subseq_profile_worker(const ProfileJob& J, int dev, int64_t lo, int64
     const int64_t nsub = paired ? rows : 1;
     const bool dtwfam = is_dtw_family(J.metric);
     const bool deriv = is_derivative(J.metric);
-    const bool ucr = J.scaled && J.metric == M_DTW;
-    const bool wrap = J.scaled && !ucr;
+    const int64_t K = J.argmin_k;
+    const bool ucr = J.scaled && J.metric == M_DTW && K == 0;
+    const bool wrap = (J.scaled && !ucr) || K > 0;   // Metric._eadistance on materialised windows
+    const bool identity = K > 0 && !J.scaled;        // ... which are the raw windows (mean 0, std 1: (x - 0) / 1 == x)
     const bool want_m = !dtwfam || (J.metric == M_ADTW && J.p.p < 0);
     const double thr = J.threshold;
     do {
       double *dx = nullptr, *ds = nullptr, *dout = nullptr;
       if ((rc = ws.alloc(&dx, (size_t)rows * T)) || (rc = h2d_rows(dx, J.x + lo * J.xs, rows, T, J.xs, st))) break;
-      if ((rc = ws.alloc(&ds, (size_t)(nsub * m))) || (rc = ws.alloc(&dout, (size_t)(rows * nw)))) break;
+      if ((rc = ws.alloc(&ds, (size_t)(nsub * m))) || (K == 0 && (rc = ws.alloc(&dout, (size_t)(rows * nw))))) break;
       WB_CK(cudaMemcpyAsync(ds, J.s + (paired ? lo * m : 0), sizeof(double) * nsub * m, cudaMemcpyHostToDevice, st));
+      double *tau = nullptr, *hval = nullptr; long long* hidx = nullptr; int* hn = nullptr;
+      if (K > 0) {
+        if ((rc = ws.alloc(&tau, (size_t)rows)) || (rc = ws.alloc(&hn, (size_t)rows)) || (rc = ws.alloc(&hval, (size_t)(rows * K))) ||
+            (rc = ws.alloc(&hidx, (size_t)(rows * K)))) break;
+        k_fill<<<64, 256, 0, st>>>(tau, rows, WB_INF);
+        WB_CK(cudaMemsetAsync(hn, 0, sizeof(int) * rows, st));
+        WB_CK(cudaMemsetAsync(hval, 0, sizeof(double) * rows * K, st));
+        WB_CK(cudaMemsetAsync(hidx, 0, sizeof(long long) * rows * K, st));
+      }
       kt.start();
       if (deriv && m < 3) {
+        if (K > 0) { /* EL:3297: nothing is ever accepted; the reference returns uninitialised memory, we return zeros */ } else
         // EL:843-844 (ddtw_subsequence_matches returns no match), EL:3297 (the wrap's _eadistance accepts nothing)
         k_fill<<<256, 256, 0, st>>>(dout, rows * nw, __builtin_nan(""));
         WB_CK(cudaGetLastError());
@@ -1347,7 +1362,7 @@ static int subseq_profile_worker(const ProfileJob& J, int dev, int64_t lo, int64
           WB_CK(cudaGetLastError());
         }
         const double *dw = nullptr, *dtw = nullptr;
-        if (J.metric == M_WDTW || J.metric == M_WDDTW || J.metric == M_TWE) {
+        if (J.metric == M_WDTW || J.metric == M_WDDTW || J.metric == M_WLCSS || J.metric == M_TWE) {  // wlcss: argmin mode only
           const int64_t tn = J.metric == M_TWE ? T + 1 : (deriv ? T - 2 : T);
           ws.host_keep.push_back(J.metric == M_TWE ? make_tw(J.p.stiffness, tn) : make_weights(J.p.g, tn));
           std::vector<double>& h = ws.host_keep.back();
@@ -1394,7 +1409,8 @@ static int subseq_profile_worker(const ProfileJob& J, int dev, int64_t lo, int64
           if (wrap) {
             double *mean = nullptr, *stdv = nullptr, *wn = nullptr;
             if ((rc = it.alloc(&mean, (size_t)n)) || (rc = it.alloc(&stdv, (size_t)n)) || (rc = it.alloc(&wn, (size_t)(n * m)))) break;
-            k_inc_window_stats<<<(unsigned)((nr + 63) / 64), 64, 0, st>>>(dx + r0 * T, nr, (int)T, (int)m, mean, stdv);
+            if (identity) { k_fill<<<256, 256, 0, st>>>(mean, n, 0.0); k_fill<<<256, 256, 0, st>>>(stdv, n, 1.0); }
+            else k_inc_window_stats<<<(unsigned)((nr + 63) / 64), 64, 0, st>>>(dx + r0 * T, nr, (int)T, (int)m, mean, stdv);
             k_normalise_windows<<<148 * 8, 256, 0, st>>>(dx + r0 * T, nr, (int)T, (int)m, mean, stdv, wn);
             WB_CK(cudaGetLastError());
             stats.launches += 2;
@@ -1434,7 +1450,16 @@ static int subseq_profile_worker(const ProfileJob& J, int dev, int64_t lo, int64
           k_profile_list<<<148 * 4, 256, 0, st>>>(list, n, (int)nw, ystride, (int)r0, paired ? 1 : 0);
           WB_CK(cudaGetLastError());
           if ((rc = launch_dp(it, di, c, 0, c.nx, 0, c.ny, draw, 0, mraw, nullptr, &stats))) break;
-          k_profile_select<<<148 * 4, 256, 0, st>>>(draw, mraw, dkim, n, (int)nw, ldk, thr_d, thr_m, strict, apply_sqrt, dout + r0 * nw);
+          if (K > 0) {
+            ReplayArgs ra;
+            ra.d = draw; ra.m = mraw; ra.lb = nullptr; ra.ld = nw; ra.nq = nr; ra.c0 = 0; ra.ncols = nw; ra.k = (int)K;
+            const bool lcss = J.metric == M_LCSS || J.metric == M_WLCSS;
+            ra.kind = dtwfam ? TK_SQUARE : (lcss ? TK_LCSS : (J.metric == M_EDR ? TK_SCALE : TK_IDENT));
+            ra.scale = (lcss || J.metric == M_EDR) ? (double)m : 1.0;
+            ra.tau = tau + r0; ra.hidx = hidx + r0 * K; ra.hval = hval + r0 * K; ra.hn = hn + r0;
+            k_replay<<<(unsigned)std::max<long long>(1, std::min<long long>((nr + 3) / 4, 148 * 16)), 128, 0, st>>>(ra);
+          } else
+            k_profile_select<<<148 * 4, 256, 0, st>>>(draw, mraw, dkim, n, (int)nw, ldk, thr_d, thr_m, strict, apply_sqrt, dout + r0 * nw);
           WB_CK(cudaGetLastError());
           stats.launches += 2;
           for (auto& v : it.host_keep) ws.host_keep.push_back(std::move(v));
@@ -1442,7 +1467,11 @@ static int subseq_profile_worker(const ProfileJob& J, int dev, int64_t lo, int64
         if (rc) break;
       }
       kt.stop();
-      if (cudaMemcpyAsync(J.out + lo * nw, dout, sizeof(double) * rows * nw, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+      if (K > 0) {
+        if (cudaMemcpyAsync(J.out_idx + lo * K, hidx, sizeof(long long) * rows * K, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(J.out_dist + lo * K, hval, sizeof(double) * rows * K, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) { set_err("device-to-host copy of the closest windows failed"); rc = 1; break; }
+      } else if (cudaMemcpyAsync(J.out + lo * nw, dout, sizeof(double) * rows * nw, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
           cudaStreamSynchronize(st) != cudaSuccess) { set_err("device-to-host copy of the distance profile failed"); rc = 1; break; }
       stats.kernel_ms = kt.ms();
     } while (0);
@@ -1783,6 +1812,25 @@ int wb_cuda_subsequence_profile(int metric, const wb_params* params, const doubl
   wb::ProfileJob J;
   J.metric = metric; J.p = *params; J.s = s; J.ns = n_s; J.m = m; J.x = x; J.nx = nx; J.T = T; J.xs = x_stride;
   J.scaled = scaled ? 1 : 0; J.s_eps = s_epsilon; J.threshold = threshold; J.out = out;
+  J.argmin_k = 0; J.out_idx = nullptr; J.out_dist = nullptr;
+  return run_row_sharded(nx, devices, n_devices, stats,
+                         [&](int dev, int64_t lo, int64_t hi, wb_stats* st) { return subseq_profile_worker(J, dev, lo, hi, st); });
+}
+
+int wb_cuda_subsequence_argmin(int metric, const wb_params* params, const double* s, int64_t n_s, int64_t m,
+                               const double* x, int64_t nx, int64_t T, int64_t x_stride, int scaled, int64_t k,
+                               int64_t* out_idx, double* out_dist, const int* devices, int n_devices, wb_stats* stats) {
+  if (check_common(metric, params, x, nx, T)) return 1;
+  if (!s || !out_idx || !out_dist) { set_err("null argument"); return 1; }
+  if (params->precision != 0) { set_err("subsequence search runs in fp64"); return 1; }
+  if (metric == M_WLCSS) { set_err("wlcss is not a subsequence metric of the reference (_distance.py:143-178, 1602-1614)"); return 1; }
+  if (n_s != nx) { set_err("argmin_subsequence_distance pairs subsequence i with sample i"); return 1; }
+  if (m < 1 || m > T) { set_err("the subsequence needs 1 <= length <= n_timestep"); return 1; }
+  if (k < 1 || k > T - m + 1) { set_err("k must be in [1, n_timestep - m + 1]"); return 1; }
+  wb::ProfileJob J;
+  J.metric = metric; J.p = *params; J.s = s; J.ns = n_s; J.m = m; J.x = x; J.nx = nx; J.T = T; J.xs = x_stride;
+  J.scaled = scaled ? 1 : 0; J.s_eps = nullptr; J.threshold = WB_INF; J.out = nullptr;
+  J.argmin_k = k; J.out_idx = out_idx; J.out_dist = out_dist;
   return run_row_sharded(nx, devices, n_devices, stats,
                          [&](int dev, int64_t lo, int64_t hi, wb_stats* st) { return subseq_profile_worker(J, dev, lo, hi, st); });
 }

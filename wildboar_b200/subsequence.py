@@ -24,7 +24,7 @@ from . import _shim
 from .distance import _check_ts_array, _format_return, _make_metric, check_array
 
 __all__ = ["pairwise_subsequence_distance", "paired_subsequence_distance", "subsequence_match",
-           "paired_subsequence_match", "distance_profile"]
+           "paired_subsequence_match", "distance_profile", "argmin_subsequence_distance"]
 
 _SUBSEQUENCE_METRICS = ("dtw", "wdtw", "adtw", "ddtw", "wddtw", "lcss", "erp", "edr", "msm", "twe")
 
@@ -384,3 +384,68 @@ def distance_profile(y, x, *, dilation=1, padding=0, dim=0, metric="dtw", metric
     m = _make_metric(metric, metric_params)
     dp = _profile(np.ascontiguousarray(y_[:, 0, :]), x_[:, int(dim), :], metric, m, scaled, np.inf, _view_mean_std)
     return np.squeeze(dp)
+
+
+def _seq_mean_std(s):
+    """fast_mean_std (utils/_stats.pyx:22-42) as `_ScaledArgminSubsequenceDistance` uses it (_cdistance.pyx:1504-1506): sequential
+    sums, std 0 (variance <= 1e-13) replaced by 1."""
+    mean, std = _view_mean_std(s)
+    return mean, (std if std != 0.0 else 1.0)
+
+
+def argmin_subsequence_distance(y, x, *, dim=0, k=1, metric="dtw", metric_params=None, scale=False, return_distance=False,
+                                n_jobs=None):
+    """Start indices (and distances) of the ``k`` windows of the i:th sample closest to the i:th subsequence
+    (_distance.py:1636-1790): (n_samples, k) arrays in the reference's heap order.  ``metric`` is any elastic entry of
+    ``_METRICS`` (``scaled_`` prefix or ``scale=True`` for the z-normalised scan); subsequences of equal length share one
+    device launch."""
+    if isinstance(k, bool) or not isinstance(k, numbers.Integral) or k < 1:
+        raise ValueError("k must be an int >= 1")
+    x = np.asarray(x)
+    if isinstance(y, np.ndarray) and y.dtype == float:
+        y = check_array(y, allow_3d=False, dtype=np.double)
+        subs = [np.ascontiguousarray(s) for s in np.atleast_2d(y)]
+    else:
+        subs = []
+        for s in y:
+            s = np.asarray(s, dtype=np.double)
+            if s.ndim > 1:
+                raise ValueError("shapelet must be 1d-array")
+            subs.append(s)
+    if x.ndim == 1:
+        x = np.broadcast_to(x, shape=(len(subs), x.shape[0]))
+    x = check_array(x, allow_3d=True, dtype=np.double)
+    x_ = _check_ts_array(x)
+    max_len = max(s.shape[0] for s in subs)
+    if not max_len <= x_.shape[2]:
+        raise ValueError("the longest subsequence must be shorter than samples.")
+    if len(subs) != x_.shape[0]:
+        raise ValueError("both arrays must have the same number of samples.")
+    if isinstance(dim, bool) or not isinstance(dim, numbers.Integral) or dim < 0 or dim >= x_.shape[1]:
+        raise ValueError(f"The parameter dim must be dim ({dim}) < n_dims ({x_.shape[1]})")
+    if not k <= (x_.shape[2] - max_len + 1):
+        raise ValueError("k must be less x.shape[-1] - y.shape[-1] + 1.")
+    if callable(metric):
+        raise ValueError("callable metrics are not accelerated; use wildboar.distance for them")
+    scaled = (isinstance(metric, str) and metric.startswith("scaled_")) or bool(scale)
+    if isinstance(metric, str) and metric.startswith("scaled_"):
+        metric = metric[7:]
+    if metric not in _SUBSEQUENCE_METRICS:
+        raise ValueError("unsupported metric '{}', 'metric' must be a str among {}".format(
+            metric, set(_SUBSEQUENCE_METRICS) | {"scaled_" + b for b in _SUBSEQUENCE_METRICS}))
+    m = _make_metric(metric, metric_params)
+    xd = x_[:, int(dim), :]
+    indices = np.empty((len(subs), k), dtype=np.intp)
+    distances = np.empty((len(subs), k), dtype=np.double)
+    lengths = np.array([s.shape[0] for s in subs])
+    for length in np.unique(lengths):
+        sel = np.flatnonzero(lengths == length)
+        group = np.array([subs[q] for q in sel])
+        if scaled:
+            stats = [_seq_mean_std(s) for s in group]
+            group = np.array([(s - mean) / std for s, (mean, std) in zip(group, stats)])
+        gi, gd = _shim.subsequence_argmin(m.metric_id, m._params(), group, np.ascontiguousarray(xd[sel]), k, scaled=scaled)
+        indices[sel], distances[sel] = gi, gd
+    if return_distance:
+        return indices, distances
+    return indices
