@@ -58,6 +58,21 @@ struct Workspace {
     *p = (T*)q;
     return 0;
   }
+  // Engine scratch (row-scan rows, global boundary rings): ONE buffer reused by every DP launch of this workspace -- the
+  // launches of a workspace are serialised on its stream, and chunked callers (argmin, subsequence scans) launch hundreds
+  // of times, so a fresh buffer per launch would pile up gigabytes until the call ends.  Grows, never shrinks.
+  void* scratch = nullptr; size_t scratch_bytes = 0;
+  template <class T> int scratch_get(T** p, size_t n) {
+    const size_t need = std::max<size_t>(n, 1) * sizeof(T);
+    if (need > scratch_bytes) {
+      void* q = nullptr;
+      WB_CK(cudaMallocAsync(&q, need, stream));
+      bufs.push_back(q);  // the previous, smaller one stays alive until destruction (kernels in flight may still use it)
+      scratch = q; scratch_bytes = need;
+    }
+    *p = (T*)scratch;
+    return 0;
+  }
 };
 
 struct DeviceInfo { int sms; int max_smem_optin; int cc_major; int cc_minor; };
@@ -175,7 +190,7 @@ static int launch_strip_cfg(Workspace& ws, KArgsT<typename M::real> a, const M& 
   if (GRING) {
     F* ring = nullptr;
     const size_t ring_bytes = (size_t)grid * nwarps * a.NS * 32 * sizeof(F);
-    if (ws.alloc(&ring, (size_t)grid * nwarps * a.NS * 32)) return 1;
+    if (ws.scratch_get(&ring, (size_t)grid * nwarps * a.NS * 32)) return 1;
     a.gring = ring;
     window_set = l2_persist_window(st, ring, ring_bytes);
   }
@@ -394,7 +409,7 @@ static int launch_dp_t(Workspace& ws, const DeviceInfo& di, const DpCall& c, lon
       a.srows = std::max(c.ptx, c.pty) + 1;
       a.sstride = grid * NT;
       F* scratch = nullptr;
-      if (ws.alloc(&scratch, (size_t)2 * a.srows * a.sstride)) { rc = 1; return; }
+      if (ws.scratch_get(&scratch, (size_t)2 * a.srows * a.sstride)) { rc = 1; return; }
       a.scratch = scratch;
       kern<<<(unsigned)grid, NT, 0, st>>>(a, m);
       if (cudaGetLastError() != cudaSuccess) { set_err("row-scan kernel launch failed"); rc = 1; }
@@ -1387,7 +1402,8 @@ static int subseq_profile_worker(const ProfileJob& J, int dev, int64_t lo, int64
           if ((rc = ws.alloc(&edr_sx, (size_t)nsub))) break;
           WB_CK(cudaMemcpyAsync(edr_sx, h.data(), sizeof(double) * nsub, cudaMemcpyHostToDevice, st));
         }
-        int64_t step = std::max<int64_t>(1, std::min<int64_t>(rows, ((int64_t)1 << 28) / std::max<int64_t>(nw, 1)));
+        // pair-list entries are int2: at most 2^28 windows per pass and window offsets (i * T + w) below 2^31
+        int64_t step = std::max<int64_t>(1, std::min<int64_t>(rows, std::min<int64_t>(((int64_t)1 << 28) / std::max<int64_t>(nw, 1), ((int64_t)1 << 31) / T - 1)));
         if (wrap) {
           int64_t budget = (int64_t)32 << 20;  // doubles of materialised windows per pass
           if (const char* e = getenv("WILDBOAR_CUDA_SCAN_WINDOW_BUDGET")) { const long long v = atoll(e); if (v > 0) budget = v; }
