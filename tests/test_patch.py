@@ -60,3 +60,70 @@ def test_patched_reference_estimators_give_identical_results(wb, oracle):
     for cpu, cuda in zip(results["cpu"], results["cuda"]):
         for a, b in zip(cpu, cuda):
             assert np.array_equal(a, b)
+
+
+def test_patch_routes_elastic_subsequence_metrics_only(wb, monkeypatch):
+    from oracle import ref
+    wd = ref.load()
+    if wd is None:
+        pytest.skip("oracle/_ref not built")
+    from wildboar_b200 import patch as P, subsequence as S
+    calls = []
+    for name in ("pairwise_subsequence_distance", "subsequence_match", "distance_profile", "argmin_subsequence_distance"):
+        monkeypatch.setattr(S, name, lambda *a, _n=name, **k: calls.append((_n, k.get("metric"))) or "cuda")
+    x = np.cumsum(np.random.default_rng(0).standard_normal((3, 20)), axis=1)
+    try:
+        done = P.patch()
+        assert "wildboar.distance.subsequence_match" in done and "wildboar.distance._distance.distance_profile" in done
+        assert wd.pairwise_subsequence_distance(x[0, :5], x, metric="scaled_msm") == "cuda"
+        assert wd.subsequence_match(x[0, :5], x, threshold=1.0, metric="twe") == "cuda"
+        assert wd.distance_profile(x[:, :5], x, metric="dtw") == "cuda"
+        assert wd.argmin_subsequence_distance(x[:, :5], x, k=2, metric="erp", scale=True) == "cuda"
+        assert [c[0] for c in calls] == ["pairwise_subsequence_distance", "subsequence_match", "distance_profile", "argmin_subsequence_distance"]
+        # not elastic, or the dilated profile: the reference's own code paths
+        e = wd.pairwise_subsequence_distance(x[0, :5], x, metric="euclidean")
+        assert isinstance(e, np.ndarray) and e.shape == (3,)
+        dp = wd.distance_profile(x[:, :5], x, metric="dtw", dilation=2)
+        assert isinstance(dp, np.ndarray) and len(calls) == 4
+    finally:
+        P.unpatch()
+    assert not hasattr(wd.subsequence_match, "__wildboar_b200_original__")
+
+
+@pytest.mark.gpu
+def test_patched_reference_subsequence_callers_give_identical_results(wb):
+    """The reference's own motif annotation (annotate/_motifs.py, built on subsequence_match) runs unmodified on the patched
+    entry points and returns what it returns on its CPU path."""
+    from oracle import ref
+    wd = ref.load()
+    if wd is None:
+        pytest.skip("oracle/_ref not built")
+    from wildboar_b200 import patch as P
+    wb.set_devices([0])
+    rng = np.random.default_rng(8)
+    X = np.cumsum(rng.standard_normal((12, 90)), axis=1)
+    s = X[2, 30:50].copy()
+    results = {}
+    for mode in ("cpu", "cuda"):
+        if mode == "cuda":
+            P.patch()
+        try:
+            out = []
+            for metric, mp in (("dtw", {"r": 0.1}), ("scaled_dtw", {"r": 0.1}), ("msm", {"r": 0.2}), ("scaled_twe", {"r": 0.2})):
+                i_, d_ = wd.subsequence_match(s, X, threshold="auto", metric=metric, metric_params=mp, exclude=0.25, return_distance=True)
+                out.append((i_, d_))
+                out.append(wd.pairwise_subsequence_distance([s, s[:7]], X, metric=metric, metric_params=mp, return_index=True))
+                out.append((wd.distance_profile(np.stack([s] * 12), X, metric=metric, metric_params=mp),))
+            results[mode] = out
+        finally:
+            if mode == "cuda":
+                P.unpatch()
+    def same(a, b):
+        if a is None or b is None:
+            return a is None and b is None
+        if isinstance(a, np.ndarray) and a.dtype == object:
+            return len(a) == len(b) and all(same(p, q) for p, q in zip(a, b))
+        return np.array_equal(a, b)
+    for cpu, cuda in zip(results["cpu"], results["cuda"]):
+        for a, b in zip(cpu, cuda):
+            assert same(a, b)
