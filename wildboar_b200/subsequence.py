@@ -231,37 +231,40 @@ def _resolve_threshold(threshold, max_matches, n_samples, allow_array):
 
 
 def _profile(subs, xd, metric, m, scaled, threshold, mean_std):
-    """Dense matches of subs ((m,) or (n, m)) against the samples xd through the C ABI."""
-    sub2 = np.atleast_2d(subs)
+    """Dense matches of subs ((m,) or (n, m)) against the samples xd through the C ABI.  mean_std: row-wise statistics of
+    a C-contiguous (n, m) array -> (mean, std) arrays, the ones the reference uses on the calling path."""
+    sub2 = np.ascontiguousarray(np.atleast_2d(subs), dtype=np.double)
     s_eps = None
     if metric == "edr" and not scaled and np.isnan(m._params().epsilon):
-        s_eps = np.array([mean_std(s)[1] / 4.0 for s in sub2], dtype=np.double)
+        s_eps = mean_std(sub2)[1] / 4.0
     if scaled:
         if metric == "dtw" and sub2.shape[1] < 3:
             raise ValueError("scaled_dtw needs subsequences of at least 3 samples (the reference reads S[1], S[2] unconditionally)")
-        normed = []
-        for s in sub2:
-            mean, std = mean_std(s)
-            if std == 0:
-                raise ValueError("constant subsequence: the reference divides by its zero standard deviation on this path")
-            normed.append((s - mean) / std)
-        sub2 = np.array(normed)
+        mean, std = mean_std(sub2)
+        if np.any(std == 0):
+            raise ValueError("constant subsequence: the reference divides by its zero standard deviation on this path")
+        sub2 = (sub2 - mean[:, None]) / std[:, None]
     return _shim.subsequence_profile(m.metric_id, m._params(), sub2, xd, scaled=scaled, s_epsilon=s_eps, threshold=threshold)
 
 
-def _from_array_mean_std(s):
-    mean, std = _mean_std(s)
-    return mean, std
+def _from_array_mean_std(a):
+    """Row-wise ScaledSubsequenceMetric.from_array (_cdistance.pyx:453-467) + `std if std != 0 else 1.0` (:283-298); numpy's
+    reductions over the contiguous last axis are the 1-D reductions of every row."""
+    mean, std = np.mean(a, axis=1), np.std(a, axis=1)
+    std = np.where(std <= _EPSILON, 0.0, std)
+    return mean, np.where(std != 0, std, 1.0)
 
 
-def _view_mean_std(s):
-    """_ts_view_update_statistics (_cdistance.pyx:167-185): sequential sums; the std is handed on as is (0 when the variance
-    is <= 1e-13) by _DistanceProfile (_cdistance.pyx:1686-1697)."""
-    ex = np.cumsum(s)[-1]
-    ex2 = np.cumsum(s * s)[-1]
-    mean = ex / s.shape[0]
-    var = ex2 / s.shape[0] - mean * mean
-    return mean, (np.sqrt(var) if var > _EPSILON else 0.0)
+def _view_mean_std(a):
+    """Row-wise _ts_view_update_statistics (_cdistance.pyx:167-185): sequential sums (cumsum accumulates in order); the std
+    is handed on as is (0 when the variance is <= 1e-13) by _DistanceProfile (_cdistance.pyx:1686-1697)."""
+    a = np.atleast_2d(a)
+    n = a.shape[1]
+    ex = np.cumsum(a, axis=1)[:, -1]
+    ex2 = np.cumsum(a * a, axis=1)[:, -1]
+    mean = ex / n
+    var = ex2 / n - mean * mean
+    return mean, np.where(var > _EPSILON, np.sqrt(np.where(var > 0, var, 0.0)), 0.0)
 
 
 def subsequence_match(y, x, threshold=None, *, dim=0, metric="dtw", metric_params=None, scale=False, max_matches=None,
@@ -386,11 +389,11 @@ def distance_profile(y, x, *, dilation=1, padding=0, dim=0, metric="dtw", metric
     return np.squeeze(dp)
 
 
-def _seq_mean_std(s):
-    """fast_mean_std (utils/_stats.pyx:22-42) as `_ScaledArgminSubsequenceDistance` uses it (_cdistance.pyx:1504-1506): sequential
-    sums, std 0 (variance <= 1e-13) replaced by 1."""
-    mean, std = _view_mean_std(s)
-    return mean, (std if std != 0.0 else 1.0)
+def _seq_mean_std(a):
+    """Row-wise fast_mean_std (utils/_stats.pyx:22-42) as `_ScaledArgminSubsequenceDistance` uses it (_cdistance.pyx:1504-1506):
+    sequential sums, std 0 (variance <= 1e-13) replaced by 1."""
+    mean, std = _view_mean_std(a)
+    return mean, np.where(std != 0.0, std, 1.0)
 
 
 def argmin_subsequence_distance(y, x, *, dim=0, k=1, metric="dtw", metric_params=None, scale=False, return_distance=False,
@@ -440,10 +443,10 @@ def argmin_subsequence_distance(y, x, *, dim=0, k=1, metric="dtw", metric_params
     lengths = np.array([s.shape[0] for s in subs])
     for length in np.unique(lengths):
         sel = np.flatnonzero(lengths == length)
-        group = np.array([subs[q] for q in sel])
+        group = np.ascontiguousarray(np.array([subs[q] for q in sel]), dtype=np.double)
         if scaled:
-            stats = [_seq_mean_std(s) for s in group]
-            group = np.array([(s - mean) / std for s, (mean, std) in zip(group, stats)])
+            mean, std = _seq_mean_std(group)
+            group = (group - mean[:, None]) / std[:, None]
         gi, gd = _shim.subsequence_argmin(m.metric_id, m._params(), group, np.ascontiguousarray(xd[sel]), k, scaled=scaled)
         indices[sel], distances[sel] = gi, gd
     if return_distance:
