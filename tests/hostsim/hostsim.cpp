@@ -7,6 +7,7 @@
 #include "../../wildboar_b200/csrc/dispatch.cuh"
 #include "../../wildboar_b200/csrc/engine_rowscan.cuh"
 #include "../../wildboar_b200/csrc/engine_strip.cuh"
+#include "../../wildboar_b200/csrc/engine_band.cuh"
 #include "../../wildboar_b200/csrc/prep.hpp"
 
 using namespace wb;
@@ -58,7 +59,19 @@ extern "C" int hostsim_pair(int engine, int W, int metric, const wb_params* p, c
   int rc = 0;
   bool known = with_policy(metric, *p, t, [&](auto m) {
     m.begin_pair(pc);
-    if (engine == 1) {
+    if (engine == 3) {
+      // band-register engine, HB = W
+      using MM = decltype(m);
+      double mm = 0;
+      bool ok = true;
+      switch (W) {
+        case 8: if ((ok = band_supported<MM>(g, 8))) *out = band_pair<MM, 8>(g, m, x, y, min_dist_raw, &mm); break;
+        case 16: if ((ok = band_supported<MM>(g, 16))) *out = band_pair<MM, 16>(g, m, x, y, min_dist_raw, &mm); break;
+        case 32: if ((ok = band_supported<MM>(g, 32))) *out = band_pair<MM, 32>(g, m, x, y, min_dist_raw, &mm); break;
+        default: ok = false;
+      }
+      if (!ok) rc = 1; else if (out_rowminmax) *out_rowminmax = mm;
+    } else if (engine == 1) {
       std::vector<double> b0((size_t)(nmax + 1) * bs, -777.0), b1((size_t)(nmax + 1) * bs, -888.0);
       double mm = 0;
       *out = rowscan_pair(g, m, x, y, b0.data(), b1.data(), (long long)bs, min_dist_raw, &mm);

@@ -18,7 +18,7 @@ class WbParams(C.Structure):
 def build(force=False):
     srcs = [os.path.join(_HERE, "hostsim.cpp")] + [
         os.path.join(_ROOT, "wildboar_b200", "csrc", f)
-        for f in ("metrics.cuh", "engine_strip.cuh", "engine_rowscan.cuh", "dispatch.cuh", "prep.hpp")]
+        for f in ("metrics.cuh", "engine_strip.cuh", "engine_rowscan.cuh", "engine_band.cuh", "dispatch.cuh", "prep.hpp")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared",
                                "-Wno-unknown-pragmas", "-o", _SO, srcs[0]])

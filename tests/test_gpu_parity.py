@@ -98,6 +98,27 @@ def test_engines_agree_on_device(W, oracle, metric, monkeypatch):
         assert last_stats()["engine"] == {"rowscan": 1, "strip": 2}[eng]
 
 
+@pytest.mark.parametrize("metric", METRICS)
+def test_band_engine_matches_oracle(W, oracle, metric, monkeypatch):
+    """The band-register engine (narrow bands, equal lengths) forced for pairwise / paired, and selected automatically behind
+    argmin (row minima): H = 7 (HB 8), H = 15 (HB 16), H = 27 (HB 32); all engines agree with the oracle."""
+    from wildboar_b200 import last_stats
+    for T, r in ((40, 0.1), (80, 0.1), (140, 0.1)):
+        x, y = random_walks(33, T, 21), random_walks(70, T, 22)
+        want = oracle.pairwise(metric, x, y, r=r, n_jobs=0)
+        for eng in ("band", "rowscan"):
+            monkeypatch.setenv("WILDBOAR_CUDA_ENGINE", eng)
+            _eq(W.pairwise_distance(x, y, metric=metric, metric_params={"r": r}), want, f"{metric} {eng} T={T}")
+            assert last_stats()["engine"] == {"band": 3, "rowscan": 1}[eng]
+        monkeypatch.delenv("WILDBOAR_CUDA_ENGINE")
+        oi, od = oracle.argmin(metric, x, y, k=3, r=r)
+        gi, gd = W.argmin_distance(x, y, k=3, metric=metric, metric_params={"r": r}, return_distance=True)
+        _eq(gi, oi, f"{metric} argmin idx T={T}")
+        _eq(gd, od, f"{metric} argmin dist T={T}")
+        if metric in ("lcss", "erp", "edr", "msm", "twe", "wlcss"):
+            assert last_stats()["engine"] == 3
+
+
 def test_edge_shapes(W, oracle):
     for metric in ("dtw", "msm", "edr", "lcss", "twe", "erp"):
         for (nx, ny, Tx, Ty) in [(1, 1, 1, 1), (3, 2, 1, 5), (2, 3, 5, 1), (1, 65, 2, 2), (31, 1, 3, 3), (2, 33, 17, 17)]:

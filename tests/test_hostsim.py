@@ -180,3 +180,38 @@ def test_scaled_subsequence_scan_scheme_matches_oracle(oracle, metric, mp):
                 d.append(dv); M.append(mv)
             t, idx = _replay_first(d, None if dtwfam else M, kind, scale)
             assert t == od[i, k] and idx == oi[i, k], (metric, m, i, t, od[i, k], idx, oi[i, k])
+
+
+@pytest.mark.parametrize("metric", METRICS)
+def test_band_engine_matches_rowscan_and_oracle(oracle, metric):
+    """The band-register engine (engine_band.cuh: previous band row in registers) returns the row-scan engine's value AND
+    its row-minimum maximum, bit for bit, with and without abandoning, for every metric and every narrow-band geometry."""
+    rng = np.random.default_rng(100 + hash(metric) % 1000)
+    mid = oracle.METRIC_IDS[metric]
+    checked = abandoned = 0
+    for trial in range(120):
+        T = int(rng.integers(2, 70)) if trial % 3 else int(rng.integers(2, 12))
+        r = float(rng.choice([0, 0.02, 0.05, 0.1, 0.15, 0.2, 0.3, 0.5, 1.0]))
+        x = np.cumsum(rng.standard_normal(T)); y = np.cumsum(rng.standard_normal(T))
+        if trial % 7 == 0:
+            y = x + 0.05 * rng.standard_normal(T)
+        p = _params(oracle, metric, r=r)
+        for ea in (0, 1):
+            rc1, v1, m1 = sim.pair(1, 0, mid, p, x, y, ea=ea)
+            assert rc1 == 0
+            for HB in (8, 16, 32):
+                rc, v, mm = sim.pair(3, HB, mid, p, x, y, ea=ea)
+                if rc == 1:
+                    continue  # band too wide for HB (or MSM with R = 1): row-scan territory
+                assert rc == 0 and v == v1 and mm == m1, (metric, T, r, HB, ea, v, v1, mm, m1)
+                checked += 1
+                if ea == 0:
+                    assert v == oracle.pairwise(metric, x, y.reshape(1, -1), r=r)[0, 0]
+                # abandoning against a bound around the row-minimum maximum: same decision, same M at the exit
+                for f in (0.5, 0.999999, 1.0, 1.5):
+                    thr = m1 * f if np.isfinite(m1) and m1 != 0 else f - 0.75
+                    rca, va, ma = sim.pair(1, 0, mid, p, x, y, ea=ea, min_dist_raw=thr)
+                    rcb, vb, mb = sim.pair(3, HB, mid, p, x, y, ea=ea, min_dist_raw=thr)
+                    assert rcb == 0 and ((va == vb) or (np.isnan(va) and np.isnan(vb))) and ma == mb, (metric, T, r, HB, thr, va, vb, ma, mb)
+                    abandoned += np.isinf(vb) and not np.isinf(v1)
+    assert checked > 100 and abandoned > 10

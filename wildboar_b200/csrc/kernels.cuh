@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include "engine_rowscan.cuh"
 #include "engine_strip.cuh"
+#include "engine_band.cuh"
 
 namespace wb {
 
@@ -186,6 +187,42 @@ __global__ void __launch_bounds__(NT) k_rowscan(KArgsT<typename M::real> a, M m)
         if (a.mode == PM_SELF && a.mirror) a.out[j * a.ld + i] = r;
       } else if (a.mode == PM_LISTP && a.out_m) {
         a.out_m[t * 32 + lane] = (double)mmax;  // one entry per list element, like the distances
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---- band-register engine: thread per pair, the previous band row in HB registers (equal lengths, H <= HB) ----
+template <class M, int HB, int NT>
+__global__ void __launch_bounds__(NT) k_band(KArgsT<typename M::real> a, M m) {
+  using F = typename M::real;
+  const int lane = threadIdx.x & 31;
+  const long long ntasks = task_count(a);
+  for (;;) {
+    const long long t = next_task(a.counter, lane);
+    if (t >= ntasks) break;
+    long long i, j;
+    bool valid;
+    if (!decode_task(a, t, lane, i, j, valid)) continue;
+    M mm = m;
+    PairCtx pc;
+    pc.sx = a.sx ? a.sx[i] : 0.0;
+    pc.sy = a.sy ? a.sy[j] : 0.0;
+    pc.sy2 = a.sy2 ? a.sy2[j] : 0.0;
+    mm.begin_pair(pc);
+    const F md = a.thr ? (F)a.thr[i] : Num<F>::inf();
+    F mmax = F(0);
+    const double d = (double)band_pair<M, HB>(a.g, mm, a.x + i * a.Tx, a.y + j * a.ys, md, &mmax);
+    if (valid) {
+      double* const po = result_ptr(a, t, lane, i, j);
+      const double r = combine_dims(a, po, d);
+      *po = r;
+      if (a.mode != PM_PAIRED && a.mode != PM_LISTP) {
+        if (a.out_m) a.out_m[i * a.ld + j] = (double)mmax;
+        if (a.mode == PM_SELF && a.mirror) a.out[j * a.ld + i] = r;
+      } else if (a.mode == PM_LISTP && a.out_m) {
+        a.out_m[t * 32 + lane] = (double)mmax;
       }
     }
     __syncwarp();

@@ -385,7 +385,7 @@ static int launch_dp_t(Workspace& ws, const DeviceInfo& di, const DpCall& c, lon
   auto body = [&](auto m) {
     using M = decltype(m);
     bool strip_ok = strip_supported<M>(a.g, 4) && !c.need_rowmin &&
-                    !(out_m != nullptr) && c.p.engine != 1;
+                    !(out_m != nullptr) && c.p.engine != 1 && c.p.engine != 3;
     if (thr && !M::kColumnMinBound) strip_ok = false;  // exact abandoning needs row minima
     if (c.p.engine == 2 && !strip_ok) { set_err("strip engine forced but not applicable"); rc = 1; return; }
     if (strip_ok) {
@@ -394,7 +394,26 @@ static int launch_dp_t(Workspace& ws, const DeviceInfo& di, const DpCall& c, lon
         if (thr) { rc = launch_strip<M, true>(ws, a, m, smem_cap, di.sms, stats); return; }
       }
       rc = launch_strip<M, false>(ws, a, m, smem_cap, di.sms, stats);
+    } else if (!kF32 && c.p.engine != 1 && band_supported<M>(a.g, 32)) {
+      // rows in order + row minima, narrow band, equal lengths: the band lives in registers (engine_band.cuh)
+      engine = 3;
+      constexpr int NT = 128;
+      auto go = [&](auto kern) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, 0) != cudaSuccess || per_sm < 1) {
+          set_err("band kernel occupancy query failed"); rc = 1; return;
+        }
+        long long grid = (long long)di.sms * per_sm;
+        const long long need = (a.ntasks * 32 + NT - 1) / NT;
+        grid = std::max<long long>(1, std::min(grid, need));
+        kern<<<(unsigned)grid, NT, 0, st>>>(a, m);
+        if (cudaGetLastError() != cudaSuccess) { set_err("band kernel launch failed"); rc = 1; }
+      };
+      if (a.g.H <= 8) go(k_band<M, 8, NT>);
+      else if (a.g.H <= 16) go(k_band<M, 16, NT>);
+      else go(k_band<M, 32, NT>);
     } else {
+      if (c.p.engine == 3) { set_err("band engine forced but not applicable"); rc = 1; return; }
       engine = 1;
       constexpr int NT = 128;
       int per_sm = 0;
