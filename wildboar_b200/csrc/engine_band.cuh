@@ -32,11 +32,18 @@ inline bool band_supported(const Geom& g, int HB) {
 
 // min_dist: abandon when a checked row's minimum exceeds it (raw dp domain); +inf disables.
 // row_min_max (optional): max over checked rows of the row minimum (for the exact replay).
-template <class M, int HB>
+// YS: element stride of y (1: a plain series; 32: interleaved in groups of 32 series, kernels.cuh `KArgs::yil`).
+template <class M, int HB, int YS = 1>
 WB_HD typename M::real band_pair(const Geom& g, const M& m, const typename M::real* __restrict__ x,
-                                 const typename M::real* __restrict__ y, typename M::real min_dist,
+                                 const typename M::real* __restrict__ yp, typename M::real min_dist,
                                  typename M::real* row_min_max) {
   using F = typename M::real;
+  struct YView {
+    const F* p;
+    WB_HD F operator[](int t) const { return p[(long long)t * YS]; }
+    WB_HD YView operator+(int t) const { return YView{p + (long long)t * YS}; }
+  };
+  const YView y{yp};
   const int T = g.Tx, a = g.a, H = g.H, R = g.max_len;
   F P[HB];
 #pragma unroll
@@ -71,7 +78,7 @@ WB_HD typename M::real band_pair(const Geom& g, const M& m, const typename M::re
     const F xi = x[i];
     const F xim = (i > 0) ? x[i - 1] : F(0);
     const typename M::Row rw = m.row(i, xi, xim);
-    const F* const yb = y + (i - a);           // y[j] = yb[k]
+    const YView yb = y + (i - a);              // y[j] = yb[k]
     int klo = imax2(0, a - i);                  // first band coordinate inside the matrix (column 0 when i <= a)
     const int khi = imin2(H, T - i + a);        // one past the last
     // what the previous row left one cell past its band: prev_init above row 0, the sentinel otherwise (MSM row 1: the

@@ -20,11 +20,15 @@ template <class M> struct EaFromRow1 { static constexpr bool value = M::kColumnM
 // b0/b1: scratch rows, element j at b[j * bs]; each needs max(Tx,Ty)+1 elements.
 // min_dist: abandon when a checked row's minimum exceeds it (raw dp domain); WB_INF disables.
 // row_min_max (optional): max over checked rows of the row minimum (for replay).
-template <class M>
+// YS: element stride of y (1: a plain series; 32: series interleaved in groups of 32 so that a warp's lanes read
+// consecutive addresses, kernels.cuh `KArgs::yil`)
+template <class M, int YS = 1>
 WB_HD typename M::real rowscan_pair(const Geom& g, const M& m, const typename M::real* __restrict__ x,
-                                    const typename M::real* __restrict__ y, typename M::real* b0, typename M::real* b1,
+                                    const typename M::real* __restrict__ yp, typename M::real* b0, typename M::real* b1,
                                     long long bs, typename M::real min_dist, typename M::real* row_min_max) {
   using F = typename M::real;
+  struct YView { const F* p; WB_HD F operator[](int t) const { return p[(long long)t * YS]; } };
+  const YView y{yp};
   const int Tx = g.Tx, Ty = g.Ty;
   F* prev = b0;
   F* cost = b1;

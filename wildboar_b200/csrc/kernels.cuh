@@ -50,6 +50,9 @@ struct KArgsT {
   int acc;            // 1: out = out + d
   double div;         // != 0: out = (...) / div
   long long ys;       // elements between consecutive y series (Ty for dense rows; 1 = every sliding window of one long buffer)
+  int yil;            // 1: y is interleaved in groups of 32 series (k_interleave32): element t of series j sits at
+                      //    ((j >> 5) * Ty + t) * 32 + (j & 31), so the 32 lanes of a warp task read consecutive addresses
+                      //    (row-scan and band kernels; dense rows of many short series are uncoalesced otherwise)
 };
 using KArgs = KArgsT<double>;
 
@@ -177,7 +180,9 @@ __global__ void __launch_bounds__(NT) k_rowscan(KArgsT<typename M::real> a, M m)
     mm.begin_pair(pc);
     const F md = a.thr ? (F)a.thr[i] : Num<F>::inf();
     F mmax = F(0);
-    const double d = (double)rowscan_pair<M>(a.g, mm, a.x + i * a.Tx, a.y + j * a.ys, b0, b1, a.sstride, md, &mmax);
+    const double d = a.yil ? (double)rowscan_pair<M, 32>(a.g, mm, a.x + i * a.Tx, a.y + (j >> 5) * (32LL * a.Ty) + (j & 31), b0, b1,
+                                                         a.sstride, md, &mmax)
+                           : (double)rowscan_pair<M>(a.g, mm, a.x + i * a.Tx, a.y + j * a.ys, b0, b1, a.sstride, md, &mmax);
     if (valid) {
       double* const po = result_ptr(a, t, lane, i, j);
       const double r = combine_dims(a, po, d);
@@ -213,7 +218,8 @@ __global__ void __launch_bounds__(NT) k_band(KArgsT<typename M::real> a, M m) {
     mm.begin_pair(pc);
     const F md = a.thr ? (F)a.thr[i] : Num<F>::inf();
     F mmax = F(0);
-    const double d = (double)band_pair<M, HB>(a.g, mm, a.x + i * a.Tx, a.y + j * a.ys, md, &mmax);
+    const double d = a.yil ? (double)band_pair<M, HB, 32>(a.g, mm, a.x + i * a.Tx, a.y + (j >> 5) * (32LL * a.Ty) + (j & 31), md, &mmax)
+                           : (double)band_pair<M, HB>(a.g, mm, a.x + i * a.Tx, a.y + j * a.ys, md, &mmax);
     if (valid) {
       double* const po = result_ptr(a, t, lane, i, j);
       const double r = combine_dims(a, po, d);
@@ -342,6 +348,19 @@ __global__ void k_inc_window_stats(const double* __restrict__ x, long long n, in
   if (i >= n) return;
   const long long nw = T - m + 1;
   inc_window_stats_one(x + i * T, T, m, mean + i * nw, stdv + i * nw);
+}
+
+// dst[((e >> 5) * T + t) * 32 + (e & 31)] = src[e * T + t]: n dense series -> groups of 32 interleaved series (KArgs::yil)
+__global__ void k_interleave32(const double* __restrict__ src, long long n, int T, double* __restrict__ dst) {
+  const long long total = n * (long long)T;
+  for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
+    // o enumerates the DESTINATION order within a group so that the stores coalesce: o = (g * T + t) * 32 + l
+    const long long g = o / (32LL * T);
+    const long long r = o - g * 32LL * T;
+    const int t = (int)(r >> 5), l = (int)(r & 31);
+    const long long e = g * 32 + l;
+    if (e < n) dst[o] = src[e * T + t];
+  }
 }
 
 // out[(i * nw + w) * m + j] = (x[i * T + w + j] - mean) / std: the z-normalised windows as dense rows (CD:526-527)

@@ -265,6 +265,9 @@ struct DpCall {
   int acc; double div;
   // subsequence search: y series start every `ys` elements (0: dense rows), raw = no final sqrt
   long long ys; int raw;
+  // optional copy of the prepared y, interleaved in groups of 32 series (k_interleave32): used by the row-scan and band
+  // kernels (one thread per series of a warp task -> coalesced loads); the strip kernels keep reading `py`
+  const double* pyi;
 };
 
 // Slope transforms, per-series scalars and lookup tables for one (x, y) operand pair.
@@ -342,6 +345,20 @@ static int prepare_operands(Workspace& ws, DpCall& c) {
   return 0;
 }
 
+// Dense prepared y rows -> groups of 32 interleaved series for the thread-per-series kernels that walk their series row
+// by row (row-scan, band): many short dense rows are otherwise read with one 32-byte sector per lane and load.
+static int interleave_y(Workspace& ws, DpCall& c) {
+  c.pyi = nullptr;
+  if (c.degenerate || c.fp32 || c.ys != 0 || c.ny < 32 || c.pty < 1) return 0;
+  double* d = nullptr;
+  const long long groups = (c.ny + 31) / 32;
+  if (ws.alloc(&d, (size_t)(groups * 32 * c.pty))) return 1;
+  k_interleave32<<<148 * 8, 256, 0, ws.stream>>>(c.py, c.ny, c.pty, d);
+  WB_CK(cudaGetLastError());
+  c.pyi = d;
+  return 0;
+}
+
 // Launch the DP over rows [r0, r0+nrows) of the prepared x against columns [c0, c0+ncols) of
 // the prepared y.  out/out_m/thr are indexed relative to (r0, c0) / r0.
 template <class F>
@@ -372,6 +389,7 @@ static int launch_dp_t(Workspace& ws, const DeviceInfo& di, const DpCall& c, lon
   a.list = c.list; a.list_len = c.list_len;
   a.acc = c.acc; a.div = c.div;
   a.nyb = (ncols + 31) / 32;
+  a.yil = 0;
   a.ntasks = (c.mode == PM_PAIRED) ? (nrows + 31) / 32 : nrows * a.nyb;
   if (c.mode == PM_LISTP) a.ntasks = (c.list_n + 31) / 32;
   unsigned long long* counter = nullptr;
@@ -388,6 +406,9 @@ static int launch_dp_t(Workspace& ws, const DeviceInfo& di, const DpCall& c, lon
                     !(out_m != nullptr) && c.p.engine != 1 && c.p.engine != 3;
     if (thr && !M::kColumnMinBound) strip_ok = false;  // exact abandoning needs row minima
     if (c.p.engine == 2 && !strip_ok) { set_err("strip engine forced but not applicable"); rc = 1; return; }
+    if constexpr (!kF32) {
+      if (!strip_ok && c.pyi && c0 == 0 && c.ys == 0) { a.y = c.pyi; a.yil = 1; }
+    }
     if (strip_ok) {
       engine = 2;
       if constexpr (M::kColumnMinBound) {
@@ -1278,6 +1299,7 @@ static int subseq_scan_worker(const SubseqJob& J, int dev, int64_t lo, int64_t h
             c.ea = 1;  // _eadistance: ddtw band from the derivative length (EL:3308)
             if ((rc = prepare_operands(it, c))) break;
             if (dw) c.tab.weights = dw;
+            if (want_m && (rc = interleave_y(it, c))) break;
             ld = nw;
           } else {
             c.px = ds + J.soff[k]; c.nx = 1; c.ptx = (int)m;
@@ -1452,6 +1474,7 @@ static int subseq_profile_worker(const ProfileJob& J, int dev, int64_t lo, int64
             c.x = ds; c.nx = nsub; c.Tx = (int)m; c.y = wn; c.ny = n; c.Ty = (int)m; c.ea = 1;
             if ((rc = prepare_operands(it, c))) break;
             if (dw) c.tab.weights = dw;
+            if (want_m && (rc = interleave_y(it, c))) break;
             ystride = nw;
           } else if (ucr) {
             double *mean = nullptr, *stdv = nullptr;
