@@ -352,7 +352,7 @@ __global__ void k_inc_window_stats(const double* __restrict__ x, long long n, in
 
 // dst[((e >> 5) * T + t) * 32 + (e & 31)] = src[e * T + t]: n dense series -> groups of 32 interleaved series (KArgs::yil)
 __global__ void k_interleave32(const double* __restrict__ src, long long n, int T, double* __restrict__ dst) {
-  const long long total = n * (long long)T;
+  const long long total = ((n + 31) / 32) * 32LL * T;  // the last group is padded (its missing series are never read)
   for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
     // o enumerates the DESTINATION order within a group so that the stores coalesce: o = (g * T + t) * 32 + l
     const long long g = o / (32LL * T);
