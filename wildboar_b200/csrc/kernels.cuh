@@ -158,7 +158,9 @@ __global__ void __launch_bounds__(NT, MINB) k_strip(KArgsT<typename M::real> a, 
 }
 
 // ---- row-scan engine: thread per pair, two scratch rows per thread in global memory ----
-template <class M, int NT>
+// YS = 32: y interleaved in groups of 32 series (KArgs::yil); a separate instantiation so that the plain kernel keeps its
+// register budget
+template <class M, int NT, int YS = 1>
 __global__ void __launch_bounds__(NT) k_rowscan(KArgsT<typename M::real> a, M m) {
   using F = typename M::real;
   const int lane = threadIdx.x & 31;
@@ -180,9 +182,8 @@ __global__ void __launch_bounds__(NT) k_rowscan(KArgsT<typename M::real> a, M m)
     mm.begin_pair(pc);
     const F md = a.thr ? (F)a.thr[i] : Num<F>::inf();
     F mmax = F(0);
-    const double d = a.yil ? (double)rowscan_pair<M, 32>(a.g, mm, a.x + i * a.Tx, a.y + (j >> 5) * (32LL * a.Ty) + (j & 31), b0, b1,
-                                                         a.sstride, md, &mmax)
-                           : (double)rowscan_pair<M>(a.g, mm, a.x + i * a.Tx, a.y + j * a.ys, b0, b1, a.sstride, md, &mmax);
+    const F* const yp = (YS == 32) ? a.y + (j >> 5) * (32LL * a.Ty) + (j & 31) : a.y + j * a.ys;
+    const double d = (double)rowscan_pair<M, YS>(a.g, mm, a.x + i * a.Tx, yp, b0, b1, a.sstride, md, &mmax);
     if (valid) {
       double* const po = result_ptr(a, t, lane, i, j);
       const double r = combine_dims(a, po, d);
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(NT) k_rowscan(KArgsT<typename M::real> a, M m)
 }
 
 // ---- band-register engine: thread per pair, the previous band row in HB registers (equal lengths, H <= HB) ----
-template <class M, int HB, int NT>
+template <class M, int HB, int NT, int YS = 1>
 __global__ void __launch_bounds__(NT) k_band(KArgsT<typename M::real> a, M m) {
   using F = typename M::real;
   const int lane = threadIdx.x & 31;
@@ -218,8 +219,8 @@ __global__ void __launch_bounds__(NT) k_band(KArgsT<typename M::real> a, M m) {
     mm.begin_pair(pc);
     const F md = a.thr ? (F)a.thr[i] : Num<F>::inf();
     F mmax = F(0);
-    const double d = a.yil ? (double)band_pair<M, HB, 32>(a.g, mm, a.x + i * a.Tx, a.y + (j >> 5) * (32LL * a.Ty) + (j & 31), md, &mmax)
-                           : (double)band_pair<M, HB>(a.g, mm, a.x + i * a.Tx, a.y + j * a.ys, md, &mmax);
+    const F* const yp = (YS == 32) ? a.y + (j >> 5) * (32LL * a.Ty) + (j & 31) : a.y + j * a.ys;
+    const double d = (double)band_pair<M, HB, YS>(a.g, mm, a.x + i * a.Tx, yp, md, &mmax);
     if (valid) {
       double* const po = result_ptr(a, t, lane, i, j);
       const double r = combine_dims(a, po, d);

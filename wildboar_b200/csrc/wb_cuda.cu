@@ -430,7 +430,13 @@ static int launch_dp_t(Workspace& ws, const DeviceInfo& di, const DpCall& c, lon
         kern<<<(unsigned)grid, NT, 0, st>>>(a, m);
         if (cudaGetLastError() != cudaSuccess) { set_err("band kernel launch failed"); rc = 1; }
       };
-      if (a.g.H <= 8) go(k_band<M, 8, NT>);
+      if (a.yil) {
+        if constexpr (!kF32) {
+          if (a.g.H <= 8) go(k_band<M, 8, NT, 32>);
+          else if (a.g.H <= 16) go(k_band<M, 16, NT, 32>);
+          else go(k_band<M, 32, NT, 32>);
+        }
+      } else if (a.g.H <= 8) go(k_band<M, 8, NT>);
       else if (a.g.H <= 16) go(k_band<M, 16, NT>);
       else go(k_band<M, 32, NT>);
     } else {
@@ -451,7 +457,11 @@ static int launch_dp_t(Workspace& ws, const DeviceInfo& di, const DpCall& c, lon
       F* scratch = nullptr;
       if (ws.scratch_get(&scratch, (size_t)2 * a.srows * a.sstride)) { rc = 1; return; }
       a.scratch = scratch;
-      kern<<<(unsigned)grid, NT, 0, st>>>(a, m);
+      bool launched = false;
+      if constexpr (!kF32) {
+        if (a.yil) { k_rowscan<M, NT, 32><<<(unsigned)grid, NT, 0, st>>>(a, m); launched = true; }
+      }
+      if (!launched) kern<<<(unsigned)grid, NT, 0, st>>>(a, m);
       if (cudaGetLastError() != cudaSuccess) { set_err("row-scan kernel launch failed"); rc = 1; }
     }
   };
