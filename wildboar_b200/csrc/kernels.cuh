@@ -340,6 +340,18 @@ __global__ void k_finish_scan(const double* __restrict__ hval, const long long* 
   out_idx[i * ld] = hidx[i];
 }
 
+// grouped form: query q = g * nr + i (subsequence g of the launch, sample i of the pass) -> out[i * ld + ks[g]]
+__global__ void k_finish_scan_group(const double* __restrict__ hval, const long long* __restrict__ hidx, long long nr, long long ng,
+                                    const int* __restrict__ ks, double* __restrict__ out_dist, long long* __restrict__ out_idx,
+                                    long long ld, int apply_sqrt) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nr * ng) return;
+  const long long g = q / nr, i = q - g * nr;
+  const long long o = i * ld + ks[g];
+  out_dist[o] = apply_sqrt ? sqrt(hval[q]) : hval[q];
+  out_idx[o] = hidx[q];
+}
+
 // ---- generic scaled subsequence metrics (ScaledSubsequenceMetricWrap, CD:470-551) ----
 // Window statistics with the reference's IncStats (utils/_stats.pyx:45-93: Welford add / remove in scan order, variance
 // below 1e-13 -> 0 -> std 1).  mean[i * nw + w], stdv[i * nw + w], nw = T - m + 1; one thread per sample.

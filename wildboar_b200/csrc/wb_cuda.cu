@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <deque>
+#include <map>
 #include <limits>
 #include <string>
 #include <thread>
@@ -1235,12 +1236,9 @@ static int subseq_scan_worker(const SubseqJob& J, int dev, int64_t lo, int64_t h
     const bool deriv = is_derivative(J.metric);
     const bool want_m = !dtwfam || (J.metric == M_ADTW && J.p.p < 0);
     do {
-      double *dx = nullptr, *ds = nullptr, *ddist = nullptr, *tau = nullptr, *hval = nullptr;
-      long long *didx = nullptr, *hidx = nullptr; int* hn = nullptr;
+      double *dx = nullptr, *ddist = nullptr;
+      long long* didx = nullptr;
       if ((rc = ws.alloc(&dx, (size_t)rows * T)) || (rc = h2d_rows(dx, J.x + lo * J.xs, rows, T, J.xs, st))) break;
-      const int64_t stot = J.soff[J.ns];
-      if ((rc = ws.alloc(&ds, (size_t)std::max<int64_t>(stot, 1)))) break;
-      WB_CK(cudaMemcpyAsync(ds, J.s, sizeof(double) * stot, cudaMemcpyHostToDevice, st));
       // tables over the SERIES length: wdtw / wddtw weights (wrap.reset(X, X): EL:3334-3341 T, EL:3415-3428 T - 2, libm exp);
       // twe's 2 * stiffness * |i - j| does not depend on the length
       const double *dw = nullptr, *dtw = nullptr;
@@ -1254,91 +1252,149 @@ static int subseq_scan_worker(const SubseqJob& J, int dev, int64_t lo, int64_t h
         (J.metric == M_TWE ? dtw : dw) = d + table_center(tn);
       }
       const int64_t nout = J.paired ? rows : rows * J.ns;
-      if ((rc = ws.alloc(&ddist, (size_t)nout)) || (rc = ws.alloc(&didx, (size_t)nout)) || (rc = ws.alloc(&tau, (size_t)rows)) ||
-          (rc = ws.alloc(&hval, (size_t)rows)) || (rc = ws.alloc(&hidx, (size_t)rows)) || (rc = ws.alloc(&hn, (size_t)rows))) break;
+      if ((rc = ws.alloc(&ddist, (size_t)nout)) || (rc = ws.alloc(&didx, (size_t)nout))) break;
       WB_CK(cudaMemsetAsync(ddist, 0, sizeof(double) * nout, st));
       WB_CK(cudaMemsetAsync(didx, 0, sizeof(long long) * nout, st));
+      // Work units: (subsequences of ONE length, sample range).  Unpaired: every length group against all samples of the block
+      // -- the group is the x operand of one DP launch (its rows share every block of 32 windows, the window statistics and
+      // the z-normalised windows are computed once per length, not once per subsequence); paired: subsequence k against
+      // sample k only.
+      struct Unit { std::vector<int64_t> ks; int64_t b0, bn; };
+      std::vector<Unit> units;
+      if (J.paired) {
+        for (int64_t k = lo; k < hi; ++k) units.push_back(Unit{{k}, k - lo, 1});
+      } else {
+        std::map<int64_t, size_t> by_len;
+        for (int64_t k = 0; k < J.ns; ++k) {
+          const int64_t m = J.soff[k + 1] - J.soff[k];
+          auto itl = by_len.find(m);
+          if (itl == by_len.end()) { by_len[m] = units.size(); units.push_back(Unit{{k}, 0, rows}); }
+          else units[itl->second].ks.push_back(k);
+        }
+      }
       kt.start();
-      for (int64_t k = 0; k < J.ns && !rc; ++k) {
-        const int64_t m = J.soff[k + 1] - J.soff[k];
+      for (size_t u = 0; u < units.size() && !rc; ++u) {
+        const Unit& U = units[u];
+        const int64_t m = J.soff[U.ks[0] + 1] - J.soff[U.ks[0]];
         const int64_t nw = T - m + 1;  // windows per sample
-        if (J.paired && (k < lo || k >= hi)) continue;
-        const int64_t b0 = J.paired ? k - lo : 0, bn = J.paired ? 1 : rows;
+        const int64_t G = (int64_t)U.ks.size();
         // replay rule of the metric: T(t) handed to the DP by *_subsequence_distance (unscaled) / _eadistance (scaled)
         int kind = TK_IDENT; double scale = 1.0;
         if (dtwfam) kind = J.scaled ? TK_SQUARE : TK_IDENT;  // unscaled adtw scans in the squared-cost domain (EL:701-740)
         else if (J.metric == M_LCSS) { kind = TK_LCSS; scale = (double)m; }                      // EL:1213-1215, 3526-3528
         else if (J.metric == M_EDR) { kind = TK_SCALE; scale = (double)(J.scaled ? m : T); }     // EL:3875 / EL:1523 (series length)
-        // samples per pass: the materialised windows of the scaled metrics stay below ~256 MB
-        int64_t step = bn;
+        const long long ld = J.scaled ? nw : T;  // distance entries per sample (unscaled: incl. the windows that straddle two samples)
+        // samples per pass: the materialised windows of the scaled metrics stay below ~256 MB; subsequences per launch: at
+        // most 2^26 (sample, window, subsequence) entries
+        int64_t step = U.bn;
         if (J.scaled) {
           int64_t budget = (int64_t)32 << 20;  // doubles
           if (const char* e = getenv("WILDBOAR_CUDA_SCAN_WINDOW_BUDGET")) { const long long v = atoll(e); if (v > 0) budget = v; }  // test knob
-          step = std::max<int64_t>(1, std::min<int64_t>(bn, budget / std::max<int64_t>(nw * m, 1)));
+          step = std::max<int64_t>(1, std::min<int64_t>(U.bn, budget / std::max<int64_t>(nw * m, 1)));
         }
-        for (int64_t q0 = 0; q0 < bn && !rc; q0 += step) {
-          const int64_t r0 = b0 + q0, nr = std::min(step, bn - q0);
-          double* od = J.paired ? ddist + r0 : ddist + r0 * J.ns + k;
-          long long* oi = J.paired ? didx + r0 : didx + r0 * J.ns + k;
-          const long long ldo = J.paired ? 1 : J.ns;
-          k_fill<<<64, 256, 0, st>>>(tau, nr, WB_INF);
-          k_fill<<<64, 256, 0, st>>>(hval, nr, WB_INF);
-          WB_CK(cudaMemsetAsync(hidx, 0, sizeof(long long) * nr, st));
-          WB_CK(cudaMemsetAsync(hn, 0, sizeof(int) * nr, st));
-          if (deriv && m < 3) {
-            // EL:3297-3298: _eadistance() accepts nothing -> the minimum stays +inf (index left at 0)
-            k_finish_scan<<<(unsigned)((nr + 127) / 128), 128, 0, st>>>(hval, hidx, nr, od, oi, ldo, 0);
-            WB_CK(cudaGetLastError());
-            continue;
-          }
-          Workspace it(st);  // buffers of this pass (returned to the pool, stream-ordered, at the end of the pass)
-          DpCall c; memset(&c, 0, sizeof c);
-          c.metric = J.metric; c.p = J.p; c.mode = PM_PAIRWISE;
-          if (J.metric == M_EDR && !J.scaled && J.s_eps) c.p.epsilon = J.s_eps[k];
-          long long ld;
-          if (J.scaled) {
-            double *mean = nullptr, *stdv = nullptr, *wn = nullptr;
-            if ((rc = it.alloc(&mean, (size_t)(nr * nw))) || (rc = it.alloc(&stdv, (size_t)(nr * nw))) ||
-                (rc = it.alloc(&wn, (size_t)(nr * nw * m)))) break;
+        // the group's subsequences as dense rows (G, m)
+        Workspace uw(st);
+        double* dsg = nullptr;
+        if ((rc = uw.alloc(&dsg, (size_t)(G * m)))) break;
+        {
+          ws.host_keep.emplace_back((size_t)(G * m));
+          std::vector<double>& h = ws.host_keep.back();
+          for (int64_t g = 0; g < G; ++g) memcpy(h.data() + g * m, J.s + J.soff[U.ks[(size_t)g]], sizeof(double) * m);
+          WB_CK(cudaMemcpyAsync(dsg, h.data(), sizeof(double) * G * m, cudaMemcpyHostToDevice, st));
+        }
+        // unscaled edr with per-subsequence epsilons: the policy takes max(sx, sy) / 4 with sx = 4 * epsilon, sy = 0
+        double* edr_sx = nullptr;
+        const bool edr_eps = J.metric == M_EDR && !J.scaled && J.s_eps && std::isnan(J.p.epsilon);
+        if (edr_eps) {
+          ws.host_keep.emplace_back((size_t)G);
+          std::vector<double>& h = ws.host_keep.back();
+          for (int64_t g = 0; g < G; ++g) h[(size_t)g] = J.s_eps[U.ks[(size_t)g]] * 4.0;
+          if ((rc = uw.alloc(&edr_sx, (size_t)G))) break;
+          WB_CK(cudaMemcpyAsync(edr_sx, h.data(), sizeof(double) * G, cudaMemcpyHostToDevice, st));
+        }
+        // where query (g, i) of a launch goes: out[(r0 + i) * ns + ks[g]] (paired: out[r0 + i])
+        int* dks = nullptr;
+        {
+          ws.host_keep_i.emplace_back((size_t)G);
+          std::vector<int>& h = ws.host_keep_i.back();
+          for (int64_t g = 0; g < G; ++g) h[(size_t)g] = J.paired ? 0 : (int)U.ks[(size_t)g];
+          if ((rc = uw.alloc(&dks, (size_t)G))) break;
+          WB_CK(cudaMemcpyAsync(dks, h.data(), sizeof(int) * G, cudaMemcpyHostToDevice, st));
+        }
+        const long long ldo = J.paired ? 1 : J.ns;
+        for (int64_t q0 = 0; q0 < U.bn && !rc; q0 += step) {
+          const int64_t r0 = U.b0 + q0, nr = std::min(step, U.bn - q0);
+          const int64_t gstep = std::max<int64_t>(1, std::min<int64_t>(G, ((int64_t)1 << 26) / std::max<int64_t>(nr * ld, 1)));
+          Workspace pw(st);  // buffers of this pass
+          double *mean = nullptr, *stdv = nullptr, *wn = nullptr;
+          if (J.scaled && !(deriv && m < 3)) {
+            if ((rc = pw.alloc(&mean, (size_t)(nr * nw))) || (rc = pw.alloc(&stdv, (size_t)(nr * nw))) ||
+                (rc = pw.alloc(&wn, (size_t)(nr * nw * m)))) break;
             k_inc_window_stats<<<(unsigned)((nr + 63) / 64), 64, 0, st>>>(dx + r0 * T, nr, (int)T, (int)m, mean, stdv);
             k_normalise_windows<<<148 * 8, 256, 0, st>>>(dx + r0 * T, nr, (int)T, (int)m, mean, stdv, wn);
             WB_CK(cudaGetLastError());
             stats.launches += 2;
-            c.x = ds + J.soff[k]; c.nx = 1; c.Tx = (int)m;
-            c.y = wn; c.ny = nr * nw; c.Ty = (int)m;
-            c.ea = 1;  // _eadistance: ddtw band from the derivative length (EL:3308)
-            if ((rc = prepare_operands(it, c))) break;
-            if (dw) c.tab.weights = dw;
-            if (want_m && (rc = interleave_y(it, c))) break;
-            ld = nw;
-          } else {
-            c.px = ds + J.soff[k]; c.nx = 1; c.ptx = (int)m;
-            c.py = dx + r0 * T; c.pty = (int)m; c.ys = 1; c.ny = nr * T - m + 1;
-            c.R = (int)compute_r(m, J.p.r);
-            c.tab.tw = dtw;
-            c.raw = dtwfam ? 1 : 0;
-            if (J.metric == M_ERP) {
-              double *sx = nullptr, *sy = nullptr;
-              if ((rc = it.alloc(&sx, 1)) || (rc = it.alloc(&sy, (size_t)c.ny))) break;
-              k_series_stat<<<1, 32, 0, st>>>(c.px, 1, (int)m, 0, J.p.g, sx, m);
-              k_series_stat<<<(unsigned)((c.ny + 127) / 128), 128, 0, st>>>(c.py, c.ny, (int)m, 0, J.p.g, sy, 1);
-              WB_CK(cudaGetLastError());
-              stats.launches += 2;
-              c.sx = sx; c.sy = sy;
-            }
-            ld = T;
           }
-          double *draw = nullptr, *mraw = nullptr;
-          if ((rc = it.alloc(&draw, (size_t)(nr * ld))) || (want_m && (rc = it.alloc(&mraw, (size_t)(nr * ld))))) break;
-          if ((rc = launch_dp(it, di, c, 0, 1, 0, c.ny, draw, c.ny, mraw, nullptr, &stats))) break;
-          ReplayArgs ra;
-          ra.d = draw; ra.m = mraw; ra.lb = nullptr; ra.ld = ld; ra.nq = nr; ra.c0 = 0; ra.ncols = nw;
-          ra.k = 1; ra.kind = kind; ra.scale = scale; ra.tau = tau; ra.hidx = hidx; ra.hval = hval; ra.hn = hn;
-          k_replay<<<(unsigned)std::max<long long>(1, std::min<long long>((nr + 3) / 4, 148 * 16)), 128, 0, st>>>(ra);
-          k_finish_scan<<<(unsigned)((nr + 127) / 128), 128, 0, st>>>(hval, hidx, nr, od, oi, ldo, (!J.scaled && dtwfam) ? 1 : 0);
-          WB_CK(cudaGetLastError());
-          stats.launches += 2;
-          for (auto& v : it.host_keep) ws.host_keep.push_back(std::move(v));  // staging of async copies outlives the pass
+          for (int64_t g0 = 0; g0 < G && !rc; g0 += gstep) {
+            const int64_t gc = std::min(gstep, G - g0);
+            const long long nq = gc * nr;  // replay queries: (subsequence g, sample i) -> row g * nr + i of the distance buffer
+            Workspace it(st);
+            double *tau = nullptr, *hval = nullptr; long long* hidx = nullptr; int* hn = nullptr;
+            if ((rc = it.alloc(&tau, (size_t)nq)) || (rc = it.alloc(&hval, (size_t)nq)) || (rc = it.alloc(&hidx, (size_t)nq)) ||
+                (rc = it.alloc(&hn, (size_t)nq))) break;
+            k_fill<<<64, 256, 0, st>>>(tau, nq, WB_INF);
+            k_fill<<<64, 256, 0, st>>>(hval, nq, WB_INF);
+            WB_CK(cudaMemsetAsync(hidx, 0, sizeof(long long) * nq, st));
+            WB_CK(cudaMemsetAsync(hn, 0, sizeof(int) * nq, st));
+            double* od = J.paired ? ddist + r0 : ddist + r0 * J.ns;
+            long long* oi = J.paired ? didx + r0 : didx + r0 * J.ns;
+            if (deriv && m < 3) {
+              // EL:3297-3298: _eadistance() accepts nothing -> the minimum stays +inf (index left at 0)
+              k_finish_scan_group<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(hval, hidx, nr, gc, dks + g0, od, oi, ldo, 0);
+              WB_CK(cudaGetLastError());
+              continue;
+            }
+            DpCall c; memset(&c, 0, sizeof c);
+            c.metric = J.metric; c.p = J.p; c.mode = PM_PAIRWISE;
+            if (edr_eps) c.p.epsilon = std::nan("");
+            if (J.scaled) {
+              c.x = dsg + g0 * m; c.nx = gc; c.Tx = (int)m;
+              c.y = wn; c.ny = nr * nw; c.Ty = (int)m;
+              c.ea = 1;  // _eadistance: ddtw band from the derivative length (EL:3308)
+              if ((rc = prepare_operands(it, c))) break;
+              if (dw) c.tab.weights = dw;
+              if (want_m && (rc = interleave_y(it, c))) break;
+            } else {
+              c.px = dsg + g0 * m; c.nx = gc; c.ptx = (int)m;
+              c.py = dx + r0 * T; c.pty = (int)m; c.ys = 1; c.ny = nr * T - m + 1;
+              c.R = (int)compute_r(m, J.p.r);
+              c.tab.tw = dtw;
+              c.raw = dtwfam ? 1 : 0;
+              if (J.metric == M_ERP) {
+                double *sx = nullptr, *sy = nullptr;
+                if ((rc = it.alloc(&sx, (size_t)gc)) || (rc = it.alloc(&sy, (size_t)c.ny))) break;
+                k_series_stat<<<(unsigned)((gc + 127) / 128), 128, 0, st>>>(c.px, gc, (int)m, 0, J.p.g, sx, m);
+                k_series_stat<<<(unsigned)((c.ny + 127) / 128), 128, 0, st>>>(c.py, c.ny, (int)m, 0, J.p.g, sy, 1);
+                WB_CK(cudaGetLastError());
+                stats.launches += 2;
+                c.sx = sx; c.sy = sy;
+              }
+              if (edr_eps) c.sx = edr_sx + g0;
+            }
+            const long long ldd = nr * ld;  // distance entries per subsequence
+            double *draw = nullptr, *mraw = nullptr;
+            if ((rc = it.alloc(&draw, (size_t)(gc * ldd))) || (want_m && (rc = it.alloc(&mraw, (size_t)(gc * ldd))))) break;
+            if ((rc = launch_dp(it, di, c, 0, gc, 0, c.ny, draw, ldd, mraw, nullptr, &stats))) break;
+            ReplayArgs ra;
+            ra.d = draw; ra.m = mraw; ra.lb = nullptr; ra.ld = ld; ra.nq = nq; ra.c0 = 0; ra.ncols = nw;
+            ra.k = 1; ra.kind = kind; ra.scale = scale; ra.tau = tau; ra.hidx = hidx; ra.hval = hval; ra.hn = hn;
+            k_replay<<<(unsigned)std::max<long long>(1, std::min<long long>((nq + 3) / 4, 148 * 16)), 128, 0, st>>>(ra);
+            k_finish_scan_group<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(hval, hidx, nr, gc, dks + g0, od, oi, ldo,
+                                                                               (!J.scaled && dtwfam) ? 1 : 0);
+            WB_CK(cudaGetLastError());
+            stats.launches += 2;
+            for (auto& v : it.host_keep) ws.host_keep.push_back(std::move(v));  // staging of async copies outlives the pass
+          }
         }
       }
       if (rc) break;
