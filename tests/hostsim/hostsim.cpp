@@ -100,3 +100,20 @@ extern "C" int hostsim_pair(int engine, int W, int metric, const wb_params* p, c
 extern "C" void hostsim_inc_window_stats(const double* x, int64_t T, int64_t m, double* mean, double* stdv) {
   inc_window_stats_one(x, (int)T, (int)m, mean, stdv);
 }
+
+// interleaved series layout (metrics.cuh): emulate k_interleave32 on the host and read every series back the way the
+// YS = 32 kernels do (base + 32 * t).  Returns the number of mismatches.
+extern "C" long long hostsim_interleave_roundtrip(const double* src, long long n, int T) {
+  std::vector<double> dst((size_t)interleave32_size(n, T), -1.0);
+  for (long long o = 0; o < (long long)dst.size(); ++o) {
+    long long e; int t;
+    interleave32_source(o, T, &e, &t);
+    if (e < n) dst[(size_t)o] = src[e * T + t];
+  }
+  long long bad = 0;
+  for (long long e = 0; e < n; ++e) {
+    const double* yp = dst.data() + interleave32_base(e, T);
+    for (int t = 0; t < T; ++t) bad += (yp[32LL * t] != src[e * T + t]) + (dst[(size_t)interleave32_index(e, t, T)] != src[e * T + t]);
+  }
+  return bad;
+}

@@ -60,3 +60,12 @@ def inc_window_stats(x, m):
     f.restype = None
     f(x.ctypes.data_as(dp), len(x), m, mean.ctypes.data_as(dp), std.ctypes.data_as(dp))
     return mean, std
+
+
+def interleave_roundtrip(a):
+    """Mismatches after interleaving the rows of `a` 32 at a time and reading them back as the YS = 32 kernels do."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    f = lib().hostsim_interleave_roundtrip
+    f.argtypes = [C.POINTER(C.c_double), C.c_longlong, C.c_int]
+    f.restype = C.c_longlong
+    return int(f(a.ctypes.data_as(C.POINTER(C.c_double)), a.shape[0], a.shape[1]))

@@ -215,3 +215,10 @@ def test_band_engine_matches_rowscan_and_oracle(oracle, metric):
                     assert rcb == 0 and ((va == vb) or (np.isnan(va) and np.isnan(vb))) and ma == mb, (metric, T, r, HB, thr, va, vb, ma, mb)
                     abandoned += np.isinf(vb) and not np.isinf(v1)
     assert checked > 100 and abandoned > 10
+
+
+def test_interleaved_layout_roundtrip():
+    """k_interleave32's index map (incl. the padded last group) and the base + 32 t walk of the YS = 32 kernels."""
+    rng = np.random.default_rng(2)
+    for n, T in ((1, 1), (31, 5), (32, 5), (33, 5), (40, 7), (64, 3), (1000, 13), (97, 64)):
+        assert sim.interleave_roundtrip(rng.standard_normal((n, T))) == 0, (n, T)

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(NT) k_rowscan(KArgsT<typename M::real> a, M m)
     mm.begin_pair(pc);
     const F md = a.thr ? (F)a.thr[i] : Num<F>::inf();
     F mmax = F(0);
-    const F* const yp = (YS == 32) ? a.y + (j >> 5) * (32LL * a.Ty) + (j & 31) : a.y + j * a.ys;
+    const F* const yp = (YS == 32) ? a.y + interleave32_base(j, a.Ty) : a.y + j * a.ys;
     const double d = (double)rowscan_pair<M, YS>(a.g, mm, a.x + i * a.Tx, yp, b0, b1, a.sstride, md, &mmax);
     if (valid) {
       double* const po = result_ptr(a, t, lane, i, j);
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(NT) k_band(KArgsT<typename M::real> a, M m) {
     mm.begin_pair(pc);
     const F md = a.thr ? (F)a.thr[i] : Num<F>::inf();
     F mmax = F(0);
-    const F* const yp = (YS == 32) ? a.y + (j >> 5) * (32LL * a.Ty) + (j & 31) : a.y + j * a.ys;
+    const F* const yp = (YS == 32) ? a.y + interleave32_base(j, a.Ty) : a.y + j * a.ys;
     const double d = (double)band_pair<M, HB, YS>(a.g, mm, a.x + i * a.Tx, yp, md, &mmax);
     if (valid) {
       double* const po = result_ptr(a, t, lane, i, j);
@@ -365,13 +365,10 @@ __global__ void k_inc_window_stats(const double* __restrict__ x, long long n, in
 
 // dst[((e >> 5) * T + t) * 32 + (e & 31)] = src[e * T + t]: n dense series -> groups of 32 interleaved series (KArgs::yil)
 __global__ void k_interleave32(const double* __restrict__ src, long long n, int T, double* __restrict__ dst) {
-  const long long total = ((n + 31) / 32) * 32LL * T;  // the last group is padded (its missing series are never read)
+  const long long total = interleave32_size(n, T);  // the last group is padded (its missing series are never read)
   for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (long long)gridDim.x * blockDim.x) {
-    // o enumerates the DESTINATION order within a group so that the stores coalesce: o = (g * T + t) * 32 + l
-    const long long g = o / (32LL * T);
-    const long long r = o - g * 32LL * T;
-    const int t = (int)(r >> 5), l = (int)(r & 31);
-    const long long e = g * 32 + l;
+    long long e; int t;
+    interleave32_source(o, T, &e, &t);
     if (e < n) dst[o] = src[e * T + t];
   }
 }

@@ -195,6 +195,21 @@ WB_HD void inc_window_stats_one(const double* p, int T, int m, double* mean, dou
   }
 }
 
+// Interleaved series layout (KArgs::yil, k_interleave32): n series of length T regrouped 32 at a time so that element t of
+// the 32 series of a group is contiguous.  Element t of series e sits at interleave32_index(e, t, T); a thread that owns
+// series e walks it from interleave32_base(e, T) with an element stride of 32; the buffer holds interleave32_size(n, T)
+// elements (the last group is padded).
+WB_HD long long interleave32_base(long long e, int T) { return (e >> 5) * (32LL * T) + (e & 31); }
+WB_HD long long interleave32_index(long long e, int t, int T) { return interleave32_base(e, T) + 32LL * t; }
+WB_HD long long interleave32_size(long long n, int T) { return ((n + 31) / 32) * 32LL * T; }
+// inverse, used by the copy kernel (which enumerates destination offsets so that its stores coalesce)
+WB_HD void interleave32_source(long long o, int T, long long* e, int* t) {
+  const long long g = o / (32LL * T);
+  const long long r = o - g * 32LL * T;
+  *t = (int)(r >> 5);
+  *e = g * 32 + (r & 31);
+}
+
 // ------------------------------------------------------------------------------------------
 // LCSS / WLCSS.  EL:1118-1183; result 1 - s / min(Tx,Ty).
 // ------------------------------------------------------------------------------------------

@@ -352,8 +352,7 @@ static int interleave_y(Workspace& ws, DpCall& c) {
   c.pyi = nullptr;
   if (c.degenerate || c.fp32 || c.ys != 0 || c.ny < 32 || c.pty < 1) return 0;
   double* d = nullptr;
-  const long long groups = (c.ny + 31) / 32;
-  if (ws.alloc(&d, (size_t)(groups * 32 * c.pty))) return 1;
+  if (ws.alloc(&d, (size_t)interleave32_size(c.ny, c.pty))) return 1;
   k_interleave32<<<148 * 8, 256, 0, ws.stream>>>(c.py, c.ny, c.pty, d);
   WB_CK(cudaGetLastError());
   c.pyi = d;
