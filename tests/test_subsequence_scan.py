@@ -385,3 +385,40 @@ def test_argmin_subsequence_larger_matches_oracle(W, oracle):
                 assert np.array_equal(i_, oi) and np.array_equal(d_, od), (metric, scale)
     finally:
         del os.environ["WILDBOAR_CUDA_SCAN_WINDOW_BUDGET"]
+
+
+@pytest.mark.gpu
+def test_subsequence_family_edge_shapes(W, oracle):
+    """One window (m == T), one sample, m == 1, 3-D input with dim (strided rows), float32 / integer input, many lengths at once."""
+    rng = np.random.default_rng(77)
+    X3 = np.cumsum(rng.standard_normal((5, 3, 30)), axis=2)
+    X = np.ascontiguousarray(X3[:, 1, :])
+    full = [x.copy() for x in X]                       # m == T: a single window per sample
+    for metric, mp in (("msm", {"r": 0.2}), ("scaled_twe", {"r": 0.2}), ("dtw", {"r": 0.2}), ("scaled_erp", {"r": 0.2})):
+        scaled = metric.startswith("scaled_")
+        base = metric[7:] if scaled else metric
+        odist = oracle.pairwise_scaled_subsequence if scaled else oracle.pairwise_subsequence
+        d, i = W.pairwise_subsequence_distance(full, X3, dim=1, metric=metric, metric_params=mp, return_index=True)
+        od, oi = odist(base, full, X, **mp)
+        assert np.array_equal(d, od) and np.array_equal(i, oi) and np.all(i == 0), metric
+        # one sample, subsequences of every length 1 .. T in one call (one DP launch per length group)
+        subs = [X[2, :m].copy() for m in range(1 if base != "dtw" or not scaled else 3, 31)]
+        d, i = W.pairwise_subsequence_distance(subs, X[0], metric=metric, metric_params=mp, return_index=True)
+        od, oi = odist(base, subs, X[:1], **mp)
+        assert np.array_equal(d, od[0]) and np.array_equal(i, oi[0]), metric
+        # profile / matches / argmin with a single window
+        dp = W.distance_profile(X, X3, dim=1, metric=metric, metric_params=mp)
+        want = oracle.subsequence_matches(base, X, X, np.inf, scaled, mean_std=_view_mean_std, **mp)
+        assert _same(np.atleast_1d(dp), want[:, 0]), metric
+        ai, ad = W.argmin_subsequence_distance(X[:, :29], X3, dim=1, k=2, metric=base, scale=scaled, metric_params=mp, return_distance=True)
+        oi2, od2 = oracle.argmin_subsequence(base, list(X[:, :29]), X, k=2, scaled=scaled, **mp)
+        assert np.array_equal(ai, oi2) and np.array_equal(ad, od2), metric
+    # float32 and integer inputs are converted like the reference converts them (check_array(dtype=float))
+    Xi = np.round(X * 4).astype(np.int64)
+    d = W.pairwise_subsequence_distance([Xi[0, 3:12]], Xi, metric="edr", metric_params={"r": 0.3})
+    assert np.array_equal(d, oracle.pairwise_subsequence("edr", [Xi[0, 3:12].astype(float)], Xi.astype(float), r=0.3)[0][:, 0])
+    Xf = X.astype(np.float32)
+    d = W.pairwise_subsequence_distance([Xf[0, 3:12]], Xf, metric="lcss", metric_params={"r": 0.3})
+    assert np.array_equal(d, oracle.pairwise_subsequence("lcss", [Xf[0, 3:12].astype(float)], Xf.astype(float), r=0.3)[0][:, 0])
+    with pytest.raises(ValueError):
+        W.pairwise_subsequence_distance([np.array([1.0, np.nan, 2.0])], X, metric="msm")

@@ -32,6 +32,8 @@ struct KArgsT {
   long long ld;       // out[i * ld + j]
   double* out_m;      // optional: max over checked rows of the row minimum (row-scan engine)
   const double* thr;  // optional per-x-row early-abandon threshold, RAW dp domain
+  long long thr_ld;   // thr_div > 0 (row-scan / band kernels): the threshold of pair (i, j) is thr[i * thr_ld + j / thr_div] --
+  long long thr_div;  //   one per (x row, group of thr_div consecutive y series), e.g. per (subsequence, sample) in a scan
   unsigned long long* counter;  // persistent-grid work counter (zeroed before launch)
   long long ntasks;   // warp tasks
   long long nyb;      // ceil(ny / 32)
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(NT) k_rowscan(KArgsT<typename M::real> a, M m)
     pc.sy = a.sy ? a.sy[j] : 0.0;
     pc.sy2 = a.sy2 ? a.sy2[j] : 0.0;
     mm.begin_pair(pc);
-    const F md = a.thr ? (F)a.thr[i] : Num<F>::inf();
+    const F md = a.thr ? (F)a.thr[a.thr_div > 0 ? i * a.thr_ld + j / a.thr_div : i] : Num<F>::inf();
     F mmax = F(0);
     const F* const yp = (YS == 32) ? a.y + interleave32_base(j, a.Ty) : a.y + j * a.ys;
     const double d = (double)rowscan_pair<M, YS>(a.g, mm, a.x + i * a.Tx, yp, b0, b1, a.sstride, md, &mmax);
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(NT) k_band(KArgsT<typename M::real> a, M m) {
     pc.sy = a.sy ? a.sy[j] : 0.0;
     pc.sy2 = a.sy2 ? a.sy2[j] : 0.0;
     mm.begin_pair(pc);
-    const F md = a.thr ? (F)a.thr[i] : Num<F>::inf();
+    const F md = a.thr ? (F)a.thr[a.thr_div > 0 ? i * a.thr_ld + j / a.thr_div : i] : Num<F>::inf();
     F mmax = F(0);
     const F* const yp = (YS == 32) ? a.y + interleave32_base(j, a.Ty) : a.y + j * a.ys;
     const double d = (double)band_pair<M, HB, YS>(a.g, mm, a.x + i * a.Tx, yp, md, &mmax);
@@ -395,6 +397,16 @@ __global__ void k_profile_list(int2* __restrict__ list, long long n, int nw, lon
     const long long i = e / nw;
     const int w = (int)(e - i * nw);
     list[e] = make_int2(paired ? sub0 + (int)i : 0, (int)(i * ystride + w));
+  }
+}
+// pair list of the first c1 windows of every (subsequence g, sample i) query of a scan pass: entry e = (g * nr + i) * c1 + w
+// pairs subsequence g with window w of sample i, whose first element sits at y[i * ystride + w]
+__global__ void k_scan_head_list(int2* __restrict__ list, long long n, long long nr, int c1, long long ystride) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const long long q = e / c1;
+    const int w = (int)(e - q * c1);
+    const long long g = q / nr, i = q - g * nr;
+    list[e] = make_int2((int)g, (int)(i * ystride + w));
   }
 }
 // out[e] = the window's distance when the reference reports it, NaN otherwise: d <= thr_d (strict: d < thr_d), not abandoned

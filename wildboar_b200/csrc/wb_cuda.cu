@@ -247,6 +247,7 @@ struct DpCall {
   double* out; long long ld;
   double* out_m;       // optional (row-scan only)
   const double* thr;   // optional raw-domain abandon thresholds per x row
+  long long thr_ld, thr_div;  // thr_div > 0: thresholds per (x row, group of thr_div consecutive y series), KArgs::thr_ld / thr_div
   int ea;              // eadistance() variants of R (ddtw EL:3308, edr EL:3833)
   long long row0; int mirror;
   bool need_rowmin;    // force the row-scan engine (exact replay needs row minima)
@@ -385,6 +386,7 @@ static int launch_dp_t(Workspace& ws, const DeviceInfo& di, const DpCall& c, lon
   a.ys = c.ys > 0 ? c.ys : c.pty;
   a.sx = c.sx ? c.sx + r0 : nullptr; a.sy = c.sy ? c.sy + c0 : nullptr; a.sy2 = c.sy2 ? c.sy2 + c0 : nullptr;
   a.out = out; a.ld = ld; a.out_m = out_m; a.thr = thr;
+  a.thr_ld = c.thr_ld; a.thr_div = thr ? c.thr_div : 0;
   a.mode = c.mode; a.row0 = c.row0 + r0 - c0; a.mirror = c.mirror;
   a.list = c.list; a.list_len = c.list_len;
   a.acc = c.acc; a.div = c.div;
@@ -405,6 +407,7 @@ static int launch_dp_t(Workspace& ws, const DeviceInfo& di, const DpCall& c, lon
     bool strip_ok = strip_supported<M>(a.g, 4) && !c.need_rowmin &&
                     !(out_m != nullptr) && c.p.engine != 1 && c.p.engine != 3;
     if (thr && !M::kColumnMinBound) strip_ok = false;  // exact abandoning needs row minima
+    if (thr && c.thr_div > 0) strip_ok = false;        // per-(row, y group) thresholds: row-scan / band kernels only
     if (c.p.engine == 2 && !strip_ok) { set_err("strip engine forced but not applicable"); rc = 1; return; }
     if constexpr (!kF32) {
       if (!strip_ok && c.pyi && c0 == 0 && c.ys == 0) { a.y = c.pyi; a.yil = 1; }
@@ -1383,11 +1386,40 @@ static int subseq_scan_worker(const SubseqJob& J, int dev, int64_t lo, int64_t h
             const long long ldd = nr * ld;  // distance entries per subsequence
             double *draw = nullptr, *mraw = nullptr;
             if ((rc = it.alloc(&draw, (size_t)(gc * ldd))) || (want_m && (rc = it.alloc(&mraw, (size_t)(gc * ldd))))) break;
-            if ((rc = launch_dp(it, di, c, 0, gc, 0, c.ny, draw, ldd, mraw, nullptr, &stats))) break;
             ReplayArgs ra;
-            ra.d = draw; ra.m = mraw; ra.lb = nullptr; ra.ld = ld; ra.nq = nq; ra.c0 = 0; ra.ncols = nw;
-            ra.k = 1; ra.kind = kind; ra.scale = scale; ra.tau = tau; ra.hidx = hidx; ra.hval = hval; ra.hn = hn;
-            k_replay<<<(unsigned)std::max<long long>(1, std::min<long long>((nq + 3) / 4, 148 * 16)), 128, 0, st>>>(ra);
+            ra.lb = nullptr; ra.nq = nq; ra.k = 1; ra.kind = kind; ra.scale = scale;
+            ra.tau = tau; ra.hidx = hidx; ra.hval = hval; ra.hn = hn;
+            const unsigned rgrid = (unsigned)std::max<long long>(1, std::min<long long>((nq + 3) / 4, 148 * 16));
+            // Early abandoning, as the reference's scan has it: the first `head` windows of every query are evaluated and
+            // replayed first; their running minimum t1 bounds every later running minimum from above, so the main launch
+            // may abandon a window as soon as a row minimum exceeds T(t1) -- the reference (bound T(t) <= T(t1)) abandons
+            // that window too.  Only where T is monotone in t (not lcss) and row minima are available (not the strip path).
+            long long head = 0;
+            const double* thr = nullptr;
+            if (want_m && kind != TK_LCSS && kind != TK_NONE && nw >= 128 && !getenv("WILDBOAR_CUDA_SCAN_NO_ABANDON")) {
+              head = 32;
+              const long long n1 = nq * head;
+              int2* list = nullptr; int* dlen = nullptr; double *d1 = nullptr, *m1 = nullptr, *thr_w = nullptr;
+              if ((rc = it.alloc(&list, (size_t)n1)) || (rc = it.alloc(&dlen, 1)) || (rc = it.alloc(&d1, (size_t)n1)) ||
+                  (rc = it.alloc(&m1, (size_t)n1)) || (rc = it.alloc(&thr_w, (size_t)nq))) break;
+              const int n32 = (int)n1;
+              WB_CK(cudaMemcpyAsync(dlen, &n32, sizeof(int), cudaMemcpyHostToDevice, st));
+              k_scan_head_list<<<148 * 4, 256, 0, st>>>(list, n1, nr, (int)head, ld);
+              WB_CK(cudaGetLastError());
+              DpCall ch = c;
+              ch.mode = PM_LISTP; ch.list = list; ch.list_len = dlen; ch.list_n = n1;
+              if ((rc = launch_dp(it, di, ch, 0, gc, 0, c.ny, d1, 0, m1, nullptr, &stats))) break;
+              ra.d = d1; ra.m = m1; ra.ld = head; ra.c0 = 0; ra.ncols = head;
+              k_replay<<<rgrid, 128, 0, st>>>(ra);
+              k_thr_raw<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(tau, nq, kind, scale, thr_w);
+              WB_CK(cudaGetLastError());
+              stats.launches += 3;
+              thr = thr_w;
+              c.thr_ld = nr; c.thr_div = ld;
+            }
+            if ((rc = launch_dp(it, di, c, 0, gc, 0, c.ny, draw, ldd, mraw, thr, &stats))) break;
+            ra.d = draw + head; ra.m = mraw ? mraw + head : nullptr; ra.ld = ld; ra.c0 = head; ra.ncols = nw - head;
+            k_replay<<<rgrid, 128, 0, st>>>(ra);
             k_finish_scan_group<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(hval, hidx, nr, gc, dks + g0, od, oi, ldo,
                                                                                (!J.scaled && dtwfam) ? 1 : 0);
             WB_CK(cudaGetLastError());
