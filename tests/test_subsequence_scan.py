@@ -146,6 +146,18 @@ def test_scan_larger_matches_oracle(W, oracle):
             assert np.array_equal(d, od) and np.array_equal(i, oi), metric
     finally:
         del os.environ["WILDBOAR_CUDA_SCAN_WINDOW_BUDGET"]
+    # the head-then-abandon scheme forced on for every metric that has row minima (default: msm / twe / erp unscaled only) and off
+    for flag in ("1", "0"):
+        os.environ["WILDBOAR_CUDA_SCAN_ABANDON"] = flag
+        try:
+            for name, metric, mp, scaled in (("edr", "edr", {"r": 0.1}, False), ("scaled_msm", "msm", {"r": 0.1}, True),
+                                             ("scaled_edr", "edr", {"r": 0.2}, True), ("twe", "twe", {"r": 0.1}, False),
+                                             ("scaled_erp", "erp", {"r": 0.1}, True)):
+                d, i = W.pairwise_subsequence_distance(subs, X, metric=name, metric_params=mp, return_index=True)
+                od, oi = (oracle.pairwise_scaled_subsequence if scaled else oracle.pairwise_subsequence)(metric, subs, X, **mp)
+                assert np.array_equal(d, od) and np.array_equal(i, oi), (name, flag)
+        finally:
+            del os.environ["WILDBOAR_CUDA_SCAN_ABANDON"]
     if W.device_count() >= 2:
         W.set_devices([0, 1])
         try:

@@ -1393,10 +1393,15 @@ static int subseq_scan_worker(const SubseqJob& J, int dev, int64_t lo, int64_t h
             // Early abandoning, as the reference's scan has it: the first `head` windows of every query are evaluated and
             // replayed first; their running minimum t1 bounds every later running minimum from above, so the main launch
             // may abandon a window as soon as a row minimum exceeds T(t1) -- the reference (bound T(t) <= T(t1)) abandons
-            // that window too.  Only where T is monotone in t (not lcss) and row minima are available (not the strip path).
+            // that window too.  Needs T monotone in t (not lcss) and row minima (not the strip path); used where it pays:
+            // the unscaled metrics with T(t) = t (msm, twe, erp: 2x fewer cells on random walks).  edr's bound t * T is far
+            // above any row minimum of an m-row window, and z-normalised windows are too alike for the head to bound much
+            // (measured: +6 % time), so those run the single launch.  WILDBOAR_CUDA_SCAN_ABANDON=0 / 1 forces it off / on.
             long long head = 0;
             const double* thr = nullptr;
-            if (want_m && kind != TK_LCSS && kind != TK_NONE && nw >= 128 && !getenv("WILDBOAR_CUDA_SCAN_NO_ABANDON")) {
+            bool abandon = !J.scaled && kind == TK_IDENT;
+            if (const char* e = getenv("WILDBOAR_CUDA_SCAN_ABANDON")) abandon = atoi(e) != 0;
+            if (abandon && want_m && kind != TK_LCSS && kind != TK_NONE && nw >= 128) {
               head = 32;
               const long long n1 = nq * head;
               int2* list = nullptr; int* dlen = nullptr; double *d1 = nullptr, *m1 = nullptr, *thr_w = nullptr;
