@@ -222,3 +222,41 @@ def test_interleaved_layout_roundtrip():
     rng = np.random.default_rng(2)
     for n, T in ((1, 1), (31, 5), (32, 5), (33, 5), (40, 7), (64, 3), (1000, 13), (97, 64)):
         assert sim.interleave_roundtrip(rng.standard_normal((n, T))) == 0, (n, T)
+
+
+@pytest.mark.parametrize("metric,mp", [c for c in _SCAN_CASES if c[0] in ("erp", "msm", "twe", "edr")])
+def test_subsequence_scan_with_head_then_abandon_matches_oracle(oracle, metric, mp):
+    """The abandoning scheme of subseq_scan_worker: a head of windows evaluated fully and replayed, every later window
+    abandoned against T(running minimum of the head) -- through the band engine's own abandon test -- and replayed with the
+    carried-over state.  Must equal the reference's scan (whose bound is never larger)."""
+    rng = np.random.default_rng(13)
+    mid = oracle.METRIC_IDS[metric]
+    T, head = 60, 5
+    X = np.cumsum(rng.standard_normal((4, T)), axis=1)
+    subs = [np.cumsum(rng.standard_normal(m)) for m in (6, 13, 24)] + [X[1, 20:32].copy()]
+    od, oi = oracle.pairwise_subsequence(metric, subs, X, **mp)
+    abandoned = 0
+    for k, s in enumerate(subs):
+        m = len(s)
+        kw = dict(mp)
+        if metric == "edr" and "epsilon" not in kw:
+            kw["epsilon"] = oracle._subsequence_mean_std(s)[1] / 4.0
+        p = _params(oracle, metric, **kw)
+        scale = float(T) if metric == "edr" else 1.0
+        for i in range(len(X)):
+            nw = T - m + 1
+            d, M = [], []
+            for w in range(head):
+                rc, dv, mv = sim.pair(1, 0, mid, p, s, X[i, w:w + m])
+                d.append(dv); M.append(mv)
+            t1, _ = _replay_first(d, M, "scale" if metric == "edr" else "ident", scale)
+            for w in range(head, nw):
+                rc, dv, mv = sim.pair(3, 32, mid, p, s, X[i, w:w + m], min_dist_raw=t1 * scale)
+                if rc == 1:  # band too wide for the band engine: the row-scan engine abandons the same way
+                    rc, dv, mv = sim.pair(1, 0, mid, p, s, X[i, w:w + m], min_dist_raw=t1 * scale)
+                assert rc == 0
+                abandoned += np.isinf(dv)
+                d.append(dv); M.append(mv)
+            t, idx = _replay_first(d, M, "scale" if metric == "edr" else "ident", scale)
+            assert t == od[i, k] and idx == oi[i, k], (metric, m, i, t, od[i, k], idx, oi[i, k])
+    assert abandoned > 0 or metric == "edr"
