@@ -32,7 +32,7 @@ struct KArgsT {
   long long ld;       // out[i * ld + j]
   double* out_m;      // optional: max over checked rows of the row minimum (row-scan engine)
   const double* thr;  // optional per-x-row early-abandon threshold, RAW dp domain
-  long long thr_ld;   // thr_div > 0 (row-scan / band kernels): the threshold of pair (i, j) is thr[i * thr_ld + j / thr_div] --
+  long long thr_ld;   // thr_div > 0: the threshold of pair (i, j) is thr[i * thr_ld + j / thr_div] --
   long long thr_div;  //   one per (x row, group of thr_div consecutive y series), e.g. per (subsequence, sample) in a scan
   unsigned long long* counter;  // persistent-grid work counter (zeroed before launch)
   long long ntasks;   // warp tasks
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(NT, MINB) k_strip(KArgsT<typename M::real> a, 
     pc.sy = a.sy ? a.sy[j] : 0.0;
     pc.sy2 = a.sy2 ? a.sy2[j] : 0.0;
     mm.begin_pair(pc);
-    const F ab = EA ? (F)a.thr[i] : Num<F>::inf();
+    const F ab = EA ? (F)a.thr[a.thr_div > 0 ? i * a.thr_ld + j / a.thr_div : i] : Num<F>::inf();
     const double d = (double)strip_pair<M, W, EA, NR, 32>(a.g, mm, a.x + i * a.Tx, a.y + j * a.ys, bnd, 32, ab);
     if (valid) {
       // results are written once and never re-read by the kernel: streaming stores keep them from

@@ -407,7 +407,6 @@ static int launch_dp_t(Workspace& ws, const DeviceInfo& di, const DpCall& c, lon
     bool strip_ok = strip_supported<M>(a.g, 4) && !c.need_rowmin &&
                     !(out_m != nullptr) && c.p.engine != 1 && c.p.engine != 3;
     if (thr && !M::kColumnMinBound) strip_ok = false;  // exact abandoning needs row minima
-    if (thr && c.thr_div > 0) strip_ok = false;        // per-(row, y group) thresholds: row-scan / band kernels only
     if (c.p.engine == 2 && !strip_ok) { set_err("strip engine forced but not applicable"); rc = 1; return; }
     if constexpr (!kF32) {
       if (!strip_ok && c.pyi && c0 == 0 && c.ys == 0) { a.y = c.pyi; a.yil = 1; }
@@ -1135,6 +1134,11 @@ static int subseq_worker(const SubseqJob& J, int dev, int64_t lo, int64_t hi, wb
           (rc = ws.alloc(&didx, (size_t)nout))) break;
       WB_CK(cudaMemsetAsync(ddist, 0, sizeof(double) * nout, st));
       WB_CK(cudaMemsetAsync(didx, 0, sizeof(long long) * nout, st));
+      // head-then-abandon (unscaled scans): pair list / distances of the first 32 windows of every sample, their minimum
+      const bool head_ok = !J.scaled && !getenv("WILDBOAR_CUDA_SCAN_NO_ABANDON");
+      int2* hlist = nullptr; int* hdlen = nullptr; double *hd1 = nullptr, *hthr = nullptr; long long* hidx_tmp = nullptr;
+      if (head_ok && ((rc = ws.alloc(&hlist, (size_t)rows * 32)) || (rc = ws.alloc(&hdlen, 1)) || (rc = ws.alloc(&hd1, (size_t)rows * 32)) ||
+                      (rc = ws.alloc(&hthr, (size_t)rows)) || (rc = ws.alloc(&hidx_tmp, (size_t)rows)))) break;
       kt.start();
       // the DP policy on prepared data: ddtw -> dtw, wddtw -> wdtw
       const int dp_metric = J.scaled ? (int)M_SCALED_DTW : (J.metric == M_DDTW ? M_DTW : (J.metric == M_WDDTW ? M_WDTW : J.metric));
@@ -1163,7 +1167,26 @@ static int subseq_worker(const SubseqJob& J, int dev, int64_t lo, int64_t hi, wb
         }
         c.raw = 1;
         c.tab.weights = dw;
-        if ((rc = launch_dp(ws, di, c, 0, 1, 0, c.ny, draw, c.ny, nullptr, nullptr, &stats))) break;
+        // Early abandoning as in the reference's scan (EL:622-660 hands the running minimum to dtw_distance): the first 32
+        // windows of every sample are evaluated first (pair list), their minimum t1 can only be undercut, so the main launch
+        // abandons a window once a column minimum of its band exceeds t1 (strip engine, EA) -- such a window cannot be the
+        // (first) minimum; ties with t1 are not abandoned (strict >), so the first-minimum rule still sees them.
+        const double* thr = nullptr;
+        if (head_ok && nw >= 128) {
+          const long long n1 = nr * 32;
+          const int n32 = (int)n1;
+          WB_CK(cudaMemcpyAsync(hdlen, &n32, sizeof(int), cudaMemcpyHostToDevice, st));
+          k_scan_head_list<<<148 * 4, 256, 0, st>>>(hlist, n1, nr, 32, Tp);
+          WB_CK(cudaGetLastError());
+          DpCall ch = c;
+          ch.mode = PM_LISTP; ch.list = hlist; ch.list_len = hdlen; ch.list_n = n1;
+          if ((rc = launch_dp(ws, di, ch, 0, 1, 0, c.ny, hd1, 0, nullptr, nullptr, &stats))) break;
+          k_window_min<<<(unsigned)((nr * 32 + 127) / 128), 128, 0, st>>>(hd1, nr, 32, 32, hthr, hidx_tmp, 1, 0);
+          WB_CK(cudaGetLastError());
+          stats.launches += 2;
+          thr = hthr; c.thr_ld = 0; c.thr_div = Tp;
+        }
+        if ((rc = launch_dp(ws, di, c, 0, 1, 0, c.ny, draw, c.ny, nullptr, thr, &stats))) break;
         double* od = J.paired ? ddist + r0 : ddist + k;
         long long* oi = J.paired ? didx + r0 : didx + k;
         if (J.scaled) {
