@@ -434,3 +434,42 @@ def test_subsequence_family_edge_shapes(W, oracle):
     assert np.array_equal(d, oracle.pairwise_subsequence("lcss", [Xf[0, 3:12].astype(float)], Xf.astype(float), r=0.3)[0][:, 0])
     with pytest.raises(ValueError):
         W.pairwise_subsequence_distance([np.array([1.0, np.nan, 2.0])], X, metric="msm")
+
+
+def test_match_post_filters_equal_the_reference_helpers(wb):
+    """CPU: the jagged-list post-filters of subsequence_match (exclusion zone, max_matches, threshold functions) against the
+    reference's own helpers (_distance.py:376-511) on random match lists, None entries included."""
+    from oracle import ref
+    if ref.load() is None:
+        pytest.skip("oracle/_ref not built")
+    from wildboar.distance import _distance as RD
+    from wildboar_b200 import subsequence as S
+    rng = np.random.default_rng(3)
+
+    def same(a, b):
+        return len(a) == len(b) and all((p is None and q is None) or (p is not None and q is not None and np.array_equal(p, q))
+                                        for p, q in zip(a, b))
+    for trial in range(40):
+        idx, dist = [], []
+        for _ in range(6):
+            n = int(rng.integers(0, 15))
+            if n == 0:
+                idx.append(None); dist.append(None)
+            else:
+                idx.append(np.sort(rng.choice(60, n, replace=False)).astype(np.intp))
+                dist.append(np.round(rng.random(n), 1))          # ties on purpose
+        ex = int(rng.integers(1, 9))
+        ri, rd = RD._exclude_trivial_matches(idx, dist, ex)
+        oi, od_ = S._filter(idx, dist, S._keep_nontrivial(ex))
+        assert same(ri, oi) and same(rd, od_)
+        mm = int(rng.integers(1, 7))
+        ri, rd = RD._filter_by_max_matches(idx, dist, mm)
+        oi, od_ = S._filter(idx, dist, lambda _, __, d: np.argsort(d)[:mm])
+        assert same(ri, oi) and same(rd, od_)
+        fn = RD._THRESHOLD["auto"]
+        ri, rd = RD._filter_by_max_dist(idx, dist, lambda _, d: d <= fn(d))
+        thr, _, max_dist = S._resolve_threshold("auto", None, 6, allow_array=True)
+        oi, od_ = S._filter(idx, dist, lambda i, _, d: max_dist(i, d))
+        assert np.isinf(thr) and same(ri, oi) and same(rd, od_)
+    assert S._resolve_threshold(None, None, 3, True)[:2] == (np.inf, 10)
+    assert S._resolve_threshold(0.5, None, 3, True) == (0.5, None, None)
