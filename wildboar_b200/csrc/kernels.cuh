@@ -426,9 +426,11 @@ __global__ void k_profile_select(const double* __restrict__ d, const double* __r
 // ---- subsequence search: first minimum over the windows of every sample (EL:622-660: `dist < min_dist`, strict) ----
 // raw: DP values of ALL windows of the flat (n, T) buffer, window w of sample i at raw[i * T + w]; only w < nw are
 // windows of sample i (the rest straddle two samples).  One warp per sample.
+// ks != nullptr (grouped launch): row i = g * nr + s is sample s of the group's subsequence g and goes to out[s * ld + ks[g]].
 __global__ void __launch_bounds__(128) k_window_min(const double* __restrict__ raw, long long n, int T, int nw,
                                                     double* __restrict__ out_dist, long long* __restrict__ out_idx,
-                                                    long long ld, int apply_sqrt) {
+                                                    long long ld, int apply_sqrt, const int* __restrict__ ks = nullptr,
+                                                    long long nr = 0) {
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (i >= n) return;
@@ -447,8 +449,10 @@ __global__ void __launch_bounds__(128) k_window_min(const double* __restrict__ r
   }
   if (lane == 0) {
     // every window +inf (cannot happen for finite input): the reference leaves the index untouched; report 0
-    out_dist[i * ld] = apply_sqrt ? sqrt(best) : best;
-    out_idx[i * ld] = bidx == 0x7fffffff ? 0 : bidx;
+    long long o = i * ld;
+    if (ks) { const long long g = i / nr; o = (i - g * nr) * ld + ks[g]; }
+    out_dist[o] = apply_sqrt ? sqrt(best) : best;
+    out_idx[o] = bidx == 0x7fffffff ? 0 : bidx;
   }
 }
 

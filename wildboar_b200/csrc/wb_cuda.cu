@@ -1142,7 +1142,73 @@ static int subseq_worker(const SubseqJob& J, int dev, int64_t lo, int64_t hi, wb
       kt.start();
       // the DP policy on prepared data: ddtw -> dtw, wddtw -> wdtw
       const int dp_metric = J.scaled ? (int)M_SCALED_DTW : (J.metric == M_DDTW ? M_DTW : (J.metric == M_WDDTW ? M_WDTW : J.metric));
-      for (int64_t k = 0; k < J.ns && !rc; ++k) {
+      // Unpaired, unscaled: subsequences of one length are the x rows of ONE launch (they share every block of 32 windows, the
+      // head thresholds are per (subsequence, sample)); the per-subsequence loop below serves paired calls and scaled_dtw.
+      const bool grouped = !J.scaled && !J.paired;
+      if (grouped) {
+        std::map<int64_t, std::vector<int64_t>> groups;
+        for (int64_t k = 0; k < J.ns; ++k) {
+          const int64_t m = J.soff[k + 1] - J.soff[k];
+          if (deriv && m < 3) continue;  // EL:793-794: distance 0 (index unspecified in the reference; 0 here)
+          groups[m].push_back(k);
+        }
+        for (auto& kv : groups) {
+          if (rc) break;
+          const int64_t m = kv.first;
+          const std::vector<int64_t>& ks = kv.second;
+          const int64_t G = (int64_t)ks.size(), mp = deriv ? m - 2 : m, nw = Tp - mp + 1, nr = rows;
+          const long long ldd = nr * Tp;
+          const int64_t gstep = std::max<int64_t>(1, std::min<int64_t>(G, ((int64_t)1 << 26) / std::max<long long>(ldd, 1)));
+          for (int64_t g0 = 0; g0 < G && !rc; g0 += gstep) {
+            const int64_t gc = std::min(gstep, G - g0);
+            Workspace it(st);
+            double *dsg = nullptr, *dgraw = nullptr; int* dks = nullptr;
+            if ((rc = it.alloc(&dsg, (size_t)(gc * mp))) || (rc = it.alloc(&dks, (size_t)gc)) || (rc = it.alloc(&dgraw, (size_t)(gc * ldd)))) break;
+            ws.host_keep.emplace_back((size_t)(gc * mp));
+            std::vector<double>& hg = ws.host_keep.back();
+            ws.host_keep_i.emplace_back((size_t)gc);
+            std::vector<int>& hk = ws.host_keep_i.back();
+            for (int64_t g = 0; g < gc; ++g) {
+              const int64_t k = ks[(size_t)(g0 + g)];
+              memcpy(hg.data() + g * mp, hs.data() + poff[(size_t)k], sizeof(double) * mp);
+              hk[(size_t)g] = (int)k;
+            }
+            WB_CK(cudaMemcpyAsync(dsg, hg.data(), sizeof(double) * gc * mp, cudaMemcpyHostToDevice, st));
+            WB_CK(cudaMemcpyAsync(dks, hk.data(), sizeof(int) * gc, cudaMemcpyHostToDevice, st));
+            DpCall c; memset(&c, 0, sizeof c);
+            c.metric = dp_metric; c.p = J.p; c.mode = PM_PAIRWISE;
+            c.px = dsg; c.nx = gc; c.ptx = (int)mp;
+            c.py = dxp; c.pty = (int)mp; c.ys = 1; c.ny = nr * Tp - mp + 1;
+            c.R = (int)compute_r(m, J.p.r);  // from the ORIGINAL subsequence length (EL:2253, 2480)
+            c.raw = 1;
+            c.tab.weights = dw;
+            const double* thr = nullptr;
+            if (head_ok && nw >= 128) {
+              // head-then-abandon, see the per-subsequence loop below
+              const long long nq = gc * nr, n1 = nq * 32;
+              int2* list = nullptr; int* dlen = nullptr; double *d1 = nullptr, *thr_w = nullptr; long long* tmp = nullptr;
+              if ((rc = it.alloc(&list, (size_t)n1)) || (rc = it.alloc(&dlen, 1)) || (rc = it.alloc(&d1, (size_t)n1)) ||
+                  (rc = it.alloc(&thr_w, (size_t)nq)) || (rc = it.alloc(&tmp, (size_t)nq))) break;
+              const int n32 = (int)n1;
+              WB_CK(cudaMemcpyAsync(dlen, &n32, sizeof(int), cudaMemcpyHostToDevice, st));
+              k_scan_head_list<<<148 * 4, 256, 0, st>>>(list, n1, nr, 32, Tp);
+              WB_CK(cudaGetLastError());
+              DpCall ch = c;
+              ch.mode = PM_LISTP; ch.list = list; ch.list_len = dlen; ch.list_n = n1;
+              if ((rc = launch_dp(it, di, ch, 0, gc, 0, c.ny, d1, 0, nullptr, nullptr, &stats))) break;
+              k_window_min<<<(unsigned)((nq * 32 + 127) / 128), 128, 0, st>>>(d1, nq, 32, 32, thr_w, tmp, 1, 0);
+              WB_CK(cudaGetLastError());
+              stats.launches += 2;
+              thr = thr_w; c.thr_ld = nr; c.thr_div = Tp;
+            }
+            if ((rc = launch_dp(it, di, c, 0, gc, 0, c.ny, dgraw, ldd, nullptr, thr, &stats))) break;
+            k_window_min<<<(unsigned)((gc * nr * 32 + 127) / 128), 128, 0, st>>>(dgraw, gc * nr, (int)Tp, (int)nw, ddist, didx, J.ns, 1, dks, nr);
+            WB_CK(cudaGetLastError());
+            stats.launches += 1;
+          }
+        }
+      }
+      for (int64_t k = 0; k < J.ns && !rc && !grouped; ++k) {
         const int64_t m = J.soff[k + 1] - J.soff[k];
         const int64_t mp = poff[(size_t)k + 1] - poff[(size_t)k];
         if (deriv && m < 3) continue;  // EL:793-794: distance 0 (index unspecified in the reference; 0 here)
