@@ -1208,7 +1208,68 @@ static int subseq_worker(const SubseqJob& J, int dev, int64_t lo, int64_t hi, wb
           }
         }
       }
-      for (int64_t k = 0; k < J.ns && !rc && !grouped; ++k) {
+      // Unpaired scaled_dtw: the same grouping -- one DP launch per length group, LB_Kim per subsequence into a buffer laid out
+      // like the distances, ONE replay over all (subsequence, sample) queries.
+      const bool grouped_ucr = J.scaled && !J.paired;
+      if (grouped_ucr) {
+        std::map<int64_t, std::vector<int64_t>> groups;
+        for (int64_t k = 0; k < J.ns; ++k) groups[J.soff[k + 1] - J.soff[k]].push_back(k);
+        for (auto& kv : groups) {
+          if (rc) break;
+          const int64_t m = kv.first;
+          const std::vector<int64_t>& ks = kv.second;
+          const int64_t G = (int64_t)ks.size(), nw = Tp - m + 1, nr = rows;
+          const long long ldd = nr * Tp;
+          k_window_stats<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(dxp, rows, (int)Tp, (int)m, dmean, dstd);
+          WB_CK(cudaGetLastError());
+          stats.launches += 1;
+          const int64_t gstep = std::max<int64_t>(1, std::min<int64_t>(G, ((int64_t)1 << 25) / std::max<long long>(ldd, 1)));
+          for (int64_t g0 = 0; g0 < G && !rc; g0 += gstep) {
+            const int64_t gc = std::min(gstep, G - g0);
+            const long long nq = gc * nr;
+            Workspace it(st);
+            double *dsg = nullptr, *dgraw = nullptr, *gkim = nullptr, *gtau = nullptr, *ghval = nullptr;
+            long long* ghidx = nullptr; int *ghn = nullptr, *dks = nullptr;
+            if ((rc = it.alloc(&dsg, (size_t)(gc * m))) || (rc = it.alloc(&dks, (size_t)gc)) || (rc = it.alloc(&dgraw, (size_t)(gc * ldd))) ||
+                (rc = it.alloc(&gkim, (size_t)(gc * ldd))) || (rc = it.alloc(&gtau, (size_t)nq)) || (rc = it.alloc(&ghval, (size_t)nq)) ||
+                (rc = it.alloc(&ghidx, (size_t)nq)) || (rc = it.alloc(&ghn, (size_t)nq))) break;
+            ws.host_keep.emplace_back((size_t)(gc * m));
+            std::vector<double>& hg = ws.host_keep.back();
+            ws.host_keep_i.emplace_back((size_t)gc);
+            std::vector<int>& hk = ws.host_keep_i.back();
+            for (int64_t g = 0; g < gc; ++g) {
+              const int64_t k = ks[(size_t)(g0 + g)];
+              memcpy(hg.data() + g * m, hs.data() + poff[(size_t)k], sizeof(double) * m);
+              hk[(size_t)g] = (int)k;
+            }
+            WB_CK(cudaMemcpyAsync(dsg, hg.data(), sizeof(double) * gc * m, cudaMemcpyHostToDevice, st));
+            WB_CK(cudaMemcpyAsync(dks, hk.data(), sizeof(int) * gc, cudaMemcpyHostToDevice, st));
+            DpCall c; memset(&c, 0, sizeof c);
+            c.metric = dp_metric; c.p = J.p; c.mode = PM_PAIRWISE;
+            c.px = dsg; c.nx = gc; c.ptx = (int)m;
+            c.py = dxp; c.pty = (int)m; c.ys = 1; c.ny = nr * Tp - m + 1;
+            c.R = (int)compute_warp_width(m, J.p.r) + 1;  // band |i - j| <= warp width (EL:2033, 283-292)
+            c.sy = dmean; c.sy2 = dstd;
+            c.raw = 1;
+            if ((rc = launch_dp(it, di, c, 0, gc, 0, c.ny, dgraw, ldd, nullptr, nullptr, &stats))) break;
+            const long long npair = nr * nw;
+            for (int64_t g = 0; g < gc; ++g)
+              k_ucr_kim<<<(unsigned)((npair + 255) / 256), 256, 0, st>>>(dxp, nr, (int)Tp, (int)m, dsg + g * m, dmean, dstd, gkim + g * ldd);
+            k_fill<<<64, 256, 0, st>>>(gtau, nq, WB_INF);
+            k_fill<<<64, 256, 0, st>>>(ghval, nq, WB_INF);
+            WB_CK(cudaMemsetAsync(ghidx, 0, sizeof(long long) * nq, st));
+            WB_CK(cudaMemsetAsync(ghn, 0, sizeof(int) * nq, st));
+            ReplayArgs ra;
+            ra.d = dgraw; ra.m = nullptr; ra.lb = gkim; ra.ld = Tp; ra.nq = nq; ra.c0 = 0; ra.ncols = nw;
+            ra.k = 1; ra.kind = TK_NONE; ra.scale = 1.0; ra.tau = gtau; ra.hidx = ghidx; ra.hval = ghval; ra.hn = ghn;
+            k_replay<<<(unsigned)std::max<long long>(1, std::min<long long>((nq + 3) / 4, 148 * 16)), 128, 0, st>>>(ra);
+            k_finish_scan_group<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(ghval, ghidx, nr, gc, dks, ddist, didx, J.ns, 1);
+            WB_CK(cudaGetLastError());
+            stats.launches += (int)gc + 4;
+          }
+        }
+      }
+      for (int64_t k = 0; k < J.ns && !rc && !grouped && !grouped_ucr; ++k) {
         const int64_t m = J.soff[k + 1] - J.soff[k];
         const int64_t mp = poff[(size_t)k + 1] - poff[(size_t)k];
         if (deriv && m < 3) continue;  // EL:793-794: distance 0 (index unspecified in the reference; 0 here)
