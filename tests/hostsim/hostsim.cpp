@@ -59,7 +59,28 @@ extern "C" int hostsim_pair(int engine, int W, int metric, const wb_params* p, c
   int rc = 0;
   bool known = with_policy(metric, *p, t, [&](auto m) {
     m.begin_pair(pc);
-    if (engine == 3) {
+    if (engine == 4 || engine == 5) {
+      // the YS = 32 instantiations: y sits in lane 5 of an interleaved group (metrics.cuh interleave32_*), every other
+      // lane holds garbage; engine 4 = band (HB = W), 5 = row-scan
+      using MM = decltype(m);
+      std::vector<double> yi((size_t)interleave32_size(32, (int)ty), -4242.0);
+      for (int64_t t = 0; t < ty; ++t) yi[(size_t)interleave32_index(5, (int)t, (int)ty)] = y[t];
+      const double* yp = yi.data() + interleave32_base(5, (int)ty);
+      double mm = 0;
+      bool ok = true;
+      if (engine == 5) {
+        std::vector<double> b0((size_t)(nmax + 1) * bs, -777.0), b1((size_t)(nmax + 1) * bs, -888.0);
+        *out = rowscan_pair<MM, 32>(g, m, x, yp, b0.data(), b1.data(), (long long)bs, min_dist_raw, &mm);
+      } else {
+        switch (W) {
+          case 8: if ((ok = band_supported<MM>(g, 8))) *out = band_pair<MM, 8, 32>(g, m, x, yp, min_dist_raw, &mm); break;
+          case 16: if ((ok = band_supported<MM>(g, 16))) *out = band_pair<MM, 16, 32>(g, m, x, yp, min_dist_raw, &mm); break;
+          case 32: if ((ok = band_supported<MM>(g, 32))) *out = band_pair<MM, 32, 32>(g, m, x, yp, min_dist_raw, &mm); break;
+          default: ok = false;
+        }
+      }
+      if (!ok) rc = 1; else if (out_rowminmax) *out_rowminmax = mm;
+    } else if (engine == 3) {
       // band-register engine, HB = W
       using MM = decltype(m);
       double mm = 0;

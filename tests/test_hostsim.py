@@ -260,3 +260,27 @@ def test_subsequence_scan_with_head_then_abandon_matches_oracle(oracle, metric, 
             t, idx = _replay_first(d, M, "scale" if metric == "edr" else "ident", scale)
             assert t == od[i, k] and idx == oi[i, k], (metric, m, i, t, od[i, k], idx, oi[i, k])
     assert abandoned > 0 or metric == "edr"
+
+
+@pytest.mark.parametrize("metric", ["msm", "twe", "erp", "lcss", "edr", "adtw", "ddtw"])
+def test_interleaved_engine_variants_match_plain(oracle, metric):
+    """The YS = 32 instantiations of the band and row-scan engines (y read from an interleaved group, element stride 32)
+    return exactly what the plain ones return, value and row-minimum maximum."""
+    rng = np.random.default_rng(200 + hash(metric) % 1000)
+    mid = oracle.METRIC_IDS[metric]
+    checked = 0
+    for trial in range(40):
+        T = int(rng.integers(2, 60))
+        r = float(rng.choice([0, 0.05, 0.1, 0.2, 0.5, 1.0]))
+        x = np.cumsum(rng.standard_normal(T)); y = np.cumsum(rng.standard_normal(T))
+        p = _params(oracle, metric, r=r)
+        rc1, v1, m1 = sim.pair(1, 0, mid, p, x, y, ea=1)
+        rc5, v5, m5 = sim.pair(5, 0, mid, p, x, y, ea=1)
+        assert rc1 == 0 and rc5 == 0 and v5 == v1 and m5 == m1, (metric, T, r)
+        for HB in (8, 16, 32):
+            rc4, v4, m4 = sim.pair(4, HB, mid, p, x, y, ea=1)
+            if rc4 == 1:
+                continue
+            assert rc4 == 0 and v4 == v1 and m4 == m1, (metric, T, r, HB)
+            checked += 1
+    assert checked > 20
