@@ -1,7 +1,9 @@
 """Subsequence search with the elastic metrics on the CUDA path.
 
 Mirrors ``wildboar.distance.pairwise_subsequence_distance`` and ``paired_subsequence_distance``
-(reference: src/wildboar/distance/_distance.py:543-636, 639-729) for every ELASTIC entry of the reference's
+(reference: src/wildboar/distance/_distance.py:543-636, 639-729), ``subsequence_match`` / ``paired_subsequence_match``
+(:732-1080), ``distance_profile`` (:1477-1600, dilation 1 / no padding) and ``argmin_subsequence_distance`` (:1636-1790)
+for every ELASTIC entry of the reference's
 ``_SUBSEQUENCE_METRICS`` (_distance.py:143-178): ``dtw, wdtw, adtw, ddtw, wddtw, lcss, erp, edr, msm, twe`` and their
 ``scaled_`` forms (``scale=True``; ``scaled_dtw`` is the UCR-suite search, the others ScaledSubsequenceMetricWrap):
 same arguments, return shapes (``_format_return``), index of the first best window under the reference's scan.
