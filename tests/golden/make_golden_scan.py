@@ -9,6 +9,7 @@ Writes tests/golden/scan_golden.npz:
            (_cdistance.pyx:470-551) over adtw, wdtw, ddtw, wddtw, lcss, erp, edr, msm, twe
   sm|...   subsequence_match / paired_subsequence_match (_distance.py:732-1080) and distance_profile (:1477-1600) for
            every elastic subsequence metric, unscaled and scaled; jagged results padded with -1 / NaN
+  dd|...   distance_profile with dilation / padding (_dilated_distance_profile, _cdistance.pyx:804-935, 1728-1862)
   as|...   argmin_subsequence_distance (_distance.py:1636-1790), k in {1, 4}, scale in {False, True}
 """
 import os
@@ -35,6 +36,10 @@ SM_CASES = [("dtw", {"r": 0.1}), ("wdtw", {"r": 0.3, "g": 0.1}), ("adtw", {"r": 
             ("edr", {"r": 0.3, "epsilon": 0.8}), ("msm", {"r": 0.15, "c": 0.3}), ("twe", {"r": 0.2, "penalty": 0.5, "stiffness": 0.05})]
 SM_SUBS = (0, 1, 3)   # lengths 12, 30, 3
 AS_CASES = SM_CASES
+
+
+DD_CASES = [c for c in SM_CASES if c[0] not in ("wdtw", "wddtw")]
+DD_GEOMETRY = ((2, 0), (1, 3), (2, "same"), (3, 5), (5, 0))
 
 
 def pad(lst, fill, dtype):
@@ -112,6 +117,12 @@ def main():
                 out[f"as|{ci}|{int(scale)}|{k}|idx"], out[f"as|{ci}|{int(scale)}|{k}|dist"] = i_.astype(np.int64), d_
             i_, d_ = wd.argmin_subsequence_distance(ragged, X, k=3, metric=metric, metric_params=mp, scale=scale, return_distance=True)
             out[f"as|{ci}|{int(scale)}|ragged|idx"], out[f"as|{ci}|{int(scale)}|ragged|dist"] = i_.astype(np.int64), d_
+    Yd = np.stack([X[(q + 2) % n, 11 + q:18 + q] for q in range(n)])   # 7 points per subsequence (odd: padding="same" works)
+    for ci, (metric, mp) in enumerate(DD_CASES):
+        for scale in (False, True):
+            for di, (dil, pad) in enumerate(DD_GEOMETRY):
+                out[f"dd|{ci}|{int(scale)}|{di}"] = wd.distance_profile(Yd, X, metric=metric, metric_params=mp, scale=scale, dilation=dil,
+                                                                        padding=pad)
     path = os.path.join(HERE, "scan_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(out), "arrays")

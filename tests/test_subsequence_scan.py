@@ -242,8 +242,10 @@ def test_match_host_logic(wb):
         wb.subsequence_match(np.zeros(4), x, threshold=1.0, metric="euclidean")
     with pytest.raises(ValueError, match="must be the same"):
         wb.paired_subsequence_match([np.zeros(4)], x, metric="dtw")
-    with pytest.raises(ValueError, match="dilation=1, padding=0"):
-        wb.distance_profile(np.zeros(3), x, dilation=2, metric="dtw")
+    with pytest.raises(ValueError, match="wdtw / wddtw"):
+        wb.distance_profile(np.zeros(3), x, dilation=2, metric="wdtw")
+    with pytest.raises(ValueError, match="dilation must be"):
+        wb.distance_profile(np.zeros(3), x, dilation=0, metric="dtw")
     with pytest.raises(ValueError, match="larger than input"):
         wb.distance_profile(np.zeros((3, 11)), x, metric="dtw")
     with pytest.raises(ValueError, match="same number of samples"):
@@ -473,3 +475,52 @@ def test_match_post_filters_equal_the_reference_helpers(wb):
         assert np.isinf(thr) and same(ri, oi) and same(rd, od_)
     assert S._resolve_threshold(None, None, 3, True)[:2] == (np.inf, 10)
     assert S._resolve_threshold(0.5, None, 3, True) == (0.5, None, None)
+
+
+# ---------------------------------------------------------------------------------------------
+# distance_profile with dilation / padding
+# ---------------------------------------------------------------------------------------------
+from make_golden_scan import DD_CASES, DD_GEOMETRY  # noqa: E402
+
+
+def _dd_inputs(g):
+    X = g["X"]
+    n = X.shape[0]
+    return X, np.stack([X[(q + 2) % n, 11 + q:18 + q] for q in range(n)])
+
+
+def test_dilated_profile_orchestration_matches_reference_golden(wb, oracle, scan_golden, monkeypatch):
+    """CPU: everything of the dilated / padded profile except the device call -- window and kernel indices at the padded
+    borders, grouping by the number of points, the sequential window statistics divided by the FULL kernel length, the
+    float divisor -- with the oracle standing in for wb_cuda_subsequence_argmin."""
+    from wildboar_b200 import _shim
+    ids = {v: k for k, v in oracle.METRIC_IDS.items()}
+
+    def fake(metric_id, params, s, x, k, scaled=False):
+        metric = ids[metric_id]
+        kw = {name: getattr(params, name) for name in oracle.DEFAULTS[metric]}
+        return oracle.argmin_subsequence(metric, list(s), x, k=k, scaled=scaled, **kw)
+    monkeypatch.setattr(_shim, "subsequence_argmin", fake)
+    X, Yd = _dd_inputs(scan_golden)
+    for ci, (metric, mp) in enumerate(DD_CASES):
+        for scale in (False, True):
+            for di, (dil, pad_) in enumerate(DD_GEOMETRY):
+                got = wb.distance_profile(Yd, X, metric=metric, metric_params=mp, scale=scale, dilation=dil, padding=pad_)
+                assert _same(got, scan_golden[f"dd|{ci}|{int(scale)}|{di}"]), (metric, scale, dil, pad_)
+    with pytest.raises(ValueError, match="wdtw / wddtw"):
+        wb.distance_profile(Yd, X, metric="wdtw", dilation=2)
+    with pytest.raises(ValueError, match="odd subsequence length"):
+        wb.distance_profile(Yd[:, :6], X, metric="dtw", padding="same")
+    with pytest.raises(ValueError, match="larger than input"):
+        wb.distance_profile(Yd, X[:, :10], metric="dtw", dilation=3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ci", range(len(DD_CASES)))
+def test_dilated_profile_matches_reference_golden(W, scan_golden, ci):
+    metric, mp = DD_CASES[ci]
+    X, Yd = _dd_inputs(scan_golden)
+    for scale in (False, True):
+        for di, (dil, pad_) in enumerate(DD_GEOMETRY):
+            got = W.distance_profile(Yd, X, metric=("scaled_" if scale else "") + metric, metric_params=mp, dilation=dil, padding=pad_)
+            assert _same(got, scan_golden[f"dd|{ci}|{int(scale)}|{di}"]), (metric, scale, dil, pad_)

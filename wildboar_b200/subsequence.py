@@ -365,12 +365,13 @@ def paired_subsequence_match(y, x, threshold=None, *, dim=0, metric="dtw", metri
 
 
 def distance_profile(y, x, *, dilation=1, padding=0, dim=0, metric="dtw", metric_params=None, scale=False, n_jobs=None):
-    """Distance of the i:th subsequence to every window of the i:th sample (_distance.py:1477-1600, the
-    ``dilation=1, padding=0`` branch that ends in ``_distance_profile``, _cdistance.pyx:1655-1725).
+    """Distance of the i:th subsequence to every window of the i:th sample (_distance.py:1477-1600).
 
-    The dilated / padded branch (``_dilated_distance_profile``) is not part of the CUDA path and raises."""
-    if dilation != 1 or padding != 0:
-        raise ValueError("wildboar_b200.distance_profile covers dilation=1, padding=0; use wildboar.distance for the dilated form")
+    ``dilation=1, padding=0`` ends in ``_distance_profile`` (_cdistance.pyx:1655-1725, the subsequence metrics); any other
+    setting in ``_dilated_distance_profile`` (_cdistance.pyx:804-935, 1728-1862: dilated, zero-padded windows through
+    ``Metric._eadistance``), covered here for the elastic metrics without a series-length weight table (wdtw / wddtw raise)."""
+    if isinstance(dilation, bool) or not isinstance(dilation, numbers.Integral) or dilation < 1:
+        raise ValueError("dilation must be an int >= 1")
     y = np.squeeze(check_array(y, dtype=np.double, ensure_2d=False))
     x = np.squeeze(check_array(x, allow_3d=True, ensure_2d=False, dtype=np.double))
     if x.ndim == 1 and y.ndim != 1:
@@ -379,7 +380,16 @@ def distance_profile(y, x, *, dilation=1, padding=0, dim=0, metric="dtw", metric
         y = np.broadcast_to(y, shape=(x.shape[0], y.shape[0]))
     x_ = _check_ts_array(x)
     y_ = _check_ts_array(y)
-    if y_.shape[2] > x_.shape[2]:
+    shapelet_size = (y_.shape[2] - 1) * dilation + 1
+    if isinstance(padding, str):
+        if padding != "same":
+            raise ValueError("padding must be an int >= 0 or 'same'")
+        if y_.shape[2] % 2 == 0:
+            raise ValueError("padding='same' is only supported for odd subsequence length")
+        padding = shapelet_size // 2
+    elif isinstance(padding, bool) or not isinstance(padding, numbers.Integral) or padding < 0:
+        raise ValueError("padding must be an int >= 0 or 'same'")
+    if shapelet_size > x_.shape[2] + 2 * padding:
         raise ValueError("subsequence in y is larger than input in x.")
     if y_.shape[0] != x_.shape[0]:
         raise ValueError("y and x must have the same number of samples.")
@@ -387,8 +397,77 @@ def distance_profile(y, x, *, dilation=1, padding=0, dim=0, metric="dtw", metric
         raise ValueError(f"The parameter dim must be dim ({dim}) < n_dims ({x_.shape[1]})")
     metric, scaled = _check_subsequence_metric(metric, scale)
     m = _make_metric(metric, metric_params)
+    if dilation != 1 or padding != 0:
+        return np.squeeze(_dilated_profile(np.ascontiguousarray(y_[:, 0, :]), np.ascontiguousarray(x_[:, int(dim), :]), metric, m,
+                                           scaled, int(dilation), int(padding)))
     dp = _profile(np.ascontiguousarray(y_[:, 0, :]), x_[:, int(dim), :], metric, m, scaled, np.inf, _view_mean_std)
     return np.squeeze(dp)
+
+
+def _dilated_geometry(k_len, x_len, dilation, padding):
+    """Per output position of `dilated_distance_profile` (_cdistance.pyx:804-858, stride 1): the sample indices and the
+    kernel indices that enter the comparison (both truncated where the dilated kernel hangs over the zero padding)."""
+    kernel_size = (k_len - 1) * dilation + 1
+    output_size = x_len + 2 * padding - kernel_size + 1
+    geo = []
+    for o in range(output_size):
+        padding_offset = padding - o
+        if padding_offset > 0:
+            kernel_offset = padding_offset if padding_offset % dilation == 0 else padding_offset + dilation - (padding_offset % dilation)
+            input_offset = kernel_offset - padding_offset
+        else:
+            kernel_offset = 0
+            input_offset = abs(padding_offset)
+        convolution_size = min(x_len, input_offset + kernel_size - max(0, padding_offset)) - input_offset
+        js = np.arange(0, max(convolution_size, 0), dilation)
+        geo.append((input_offset + js, (js + kernel_offset) // dilation))
+    return geo
+
+
+def _dilated_profile(y, x, metric, m, scaled, dilation, padding):
+    """`_dilated_distance_profile` (_cdistance.pyx:1809-1862) on the device: every (sample, output position) pair is one
+    equal-length comparison `Metric._eadistance(x window, kernel part)` -- the window FIRST -- which is what
+    wb_cuda_subsequence_argmin evaluates for a "subsequence" = the window against a "sample" = the kernel part with one
+    window and k = 1.  Output positions are grouped by the number of points that enter (borders are truncated)."""
+    if metric in ("wdtw", "wddtw"):
+        raise ValueError("the dilated distance_profile is not accelerated for wdtw / wddtw (their weights span the series "
+                         "length while the compared windows are shorter); use wildboar.distance for it")
+    n, k_len = y.shape
+    x_len = x.shape[1]
+    if scaled:
+        # _distance.py:1581-1585: the subsequences are z-normalised with numpy before the driver is called
+        std = np.std(y, axis=-1, keepdims=True)
+        mean = np.mean(y, axis=-1, keepdims=True)
+        std[std < _EPSILON] = 1
+        y = (y - mean) / std
+    geo = _dilated_geometry(k_len, x_len, dilation, padding)
+    out = np.empty((n, len(geo)), dtype=np.double)
+    by_k = {}
+    for o, (xi, ki) in enumerate(geo):
+        by_k.setdefault(len(xi), []).append(o)
+    for k, positions in by_k.items():
+        if k < 1 or (metric == "ddtw" and k < 3):
+            raise ValueError("a border window of this dilated profile keeps %d point(s); the reference writes no value there "
+                             "and shifts the rest of the row -- use a smaller padding" % k)
+        xi = np.stack([geo[o][0] for o in positions])            # (P, k) sample indices
+        ki = np.stack([geo[o][1] for o in positions])            # (P, k) kernel indices
+        step = max(1, (1 << 24) // max(len(positions) * k, 1))   # samples per call: bounded host / device buffers
+        for a in range(0, n, step):
+            win = x[a:a + step][:, xi]                            # (s, P, k)
+            ker = y[a:a + step][:, ki]
+            if scaled:
+                # scaled_dilated_distance_profile (_cdistance.pyx:899-921): sequential sums over the k points that enter,
+                # divided by the FULL kernel length
+                mean = np.cumsum(win, axis=-1)[..., -1] / k_len
+                var = np.cumsum(win * win, axis=-1)[..., -1] / k_len - mean * mean
+                std = np.where(var > _EPSILON, np.sqrt(np.where(var > 0, var, 0.0)), 1.0)
+                win = (win - mean[..., None]) / std[..., None]
+            s_, P = win.shape[0], win.shape[1]
+            dist = _shim.subsequence_argmin(m.metric_id, m._params(), np.ascontiguousarray(win.reshape(s_ * P, k)),
+                                            np.ascontiguousarray(ker.reshape(s_ * P, k)), 1, scaled=False)[1][:, 0]
+            # `tmp_dist / (<float>k / k_len)`: a C float division, widened
+            out[a:a + step, positions] = dist.reshape(s_, P) / np.float64(np.float32(k) / np.float32(k_len))
+    return out
 
 
 def _seq_mean_std(a):
