@@ -229,7 +229,8 @@ int wb_cuda_subsequence_profile(int metric, const wb_params *params,
  * Metric._eadistance against the running bound (+inf until the k-heap is full, then its maximum, utils/_misc.pyx:62-107).
  * s: (nx, m) dense; scaled != 0: s already z-normalised by the caller with fast_mean_std (utils/_stats.pyx:22-42, std 0 -> 1)
  * and every window z-normalised on the device with the running IncStats; wdtw / wddtw weights over T / T - 2.
- * out_idx / out_dist: (nx, k) in the heap's array order.  Same device scheme as the profile (all windows of all samples in
+ * out_idx / out_dist: (nx, k) in the heap's array order.  The dilated / padded distance profile (`_dilated_distance_profile`,
+ * _cdistance.pyx:804-935) uses this entry point with k = 1, the dilated windows as `s` and the kernel parts as one-window samples.  Same device scheme as the profile (all windows of all samples in
  * one DP launch) followed by the exact replay of the scan, one warp per sample. */
 int wb_cuda_subsequence_argmin(int metric, const wb_params *params,
                                const double *s, int64_t n_s, int64_t m,
