@@ -230,12 +230,14 @@ int wb_cuda_subsequence_profile(int metric, const wb_params *params,
  * s: (nx, m) dense; scaled != 0: s already z-normalised by the caller with fast_mean_std (utils/_stats.pyx:22-42, std 0 -> 1)
  * and every window z-normalised on the device with the running IncStats; wdtw / wddtw weights over T / T - 2.
  * out_idx / out_dist: (nx, k) in the heap's array order.  The dilated / padded distance profile (`_dilated_distance_profile`,
- * _cdistance.pyx:804-935) uses this entry point with k = 1, the dilated windows as `s` and the kernel parts as one-window samples.  Same device scheme as the profile (all windows of all samples in
+ * _cdistance.pyx:804-935) uses this entry point with k = 1, the dilated windows as `s` and the kernel parts as one-window samples;
+ * weight_len > 0 sizes the wdtw / wddtw weight tables for a series of that many points (the series the reference reset() the
+ * metric with, _cdistance.pyx:1769) instead of T; 0 = T.  Same device scheme as the profile (all windows of all samples in
  * one DP launch) followed by the exact replay of the scan, one warp per sample. */
 int wb_cuda_subsequence_argmin(int metric, const wb_params *params,
                                const double *s, int64_t n_s, int64_t m,
                                const double *x, int64_t nx, int64_t T, int64_t x_stride,
-                               int scaled, int64_t k, int64_t *out_idx, double *out_dist,
+                               int scaled, int64_t k, int64_t weight_len, int64_t *out_idx, double *out_dist,
                                const int *devices, int n_devices, wb_stats *stats);
 
 /* Device-resident variant of wb_cuda_pairwise: d_x (nx, Tx), d_y (ny, Ty), d_out (nx, ny) are

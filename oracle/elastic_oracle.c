@@ -981,11 +981,12 @@ static void ea_scratch_free(ea_scratch *w) { free(w->cost); free(w->cost_prev); 
  * argmin_subsequence_distance, `_ArgminSubsequenceDistance` (scaled == 0, raw buffers) and `_ScaledArgminSubsequenceDistance`
  * (scaled != 0) CD:1380-1548: the running bound is the heap maximum once the k-heap is full (MI:62-107), the result the heap
  * array (heap order; entries >= *n_found are whatever calloc left: the reference reads uninitialised memory there). */
-static double subsequence_ea_scan(int metric, const orc_params *p, const double *S, int64_t s_len, double s_mean,
-                                  double s_std, const double *T, int64_t t_len, int scaled, int64_t k, int64_t *out_idx,
-                                  double *out_dist, int64_t *n_found, int64_t *index) {
+static double subsequence_ea_scan_w(int metric, const orc_params *p, const double *S, int64_t s_len, double s_mean,
+                                    double s_std, const double *T, int64_t t_len, int scaled, int64_t k, int64_t *out_idx,
+                                    double *out_dist, int64_t *n_found, int64_t *index, int64_t weight_len) {
   size_t n = (size_t)(t_len + 2);
-  ea_scratch w; ea_scratch_init(&w, metric, p, t_len);
+  /* weight tables span the series the metric was reset() with; the dilated profile compares shorter windows (CD:1769) */
+  ea_scratch w; ea_scratch_init(&w, metric, p, weight_len > 0 ? weight_len : t_len);
   double *sb = (double *)malloc(sizeof(double) * n), *xb = (double *)malloc(sizeof(double) * n);
   double *mean = (double *)malloc(sizeof(double) * n), *std = (double *)malloc(sizeof(double) * n);
   orc_heap hp; hp.h = (heap_el *)calloc((size_t)k, sizeof(heap_el)); hp.n = 0; hp.cap = k;
@@ -1011,6 +1012,12 @@ static double subsequence_ea_scan(int metric, const orc_params *p, const double 
   const double best = (k == 1 && hp.n == 1) ? hp.h[0].value : min_dist;
   free(sb); free(xb); free(mean); free(std); free(hp.h); ea_scratch_free(&w);
   return best;
+}
+
+static double subsequence_ea_scan(int metric, const orc_params *p, const double *S, int64_t s_len, double s_mean,
+                                  double s_std, const double *T, int64_t t_len, int scaled, int64_t k, int64_t *out_idx,
+                                  double *out_dist, int64_t *n_found, int64_t *index) {
+  return subsequence_ea_scan_w(metric, p, S, s_len, s_mean, s_std, T, t_len, scaled, k, out_idx, out_dist, n_found, index, 0);
 }
 
 double orc_scaled_subsequence_distance(int metric, const orc_params *p, const double *S, int64_t s_len, double s_mean,
@@ -1147,4 +1154,14 @@ int64_t orc_subsequence_matches(int metric, const orc_params *p, const double *S
   }
   free(cost); free(cost_prev); free(sb); free(xb); free(a1); free(a2); free(weights); free(mean); free(std);
   return n_matches;
+}
+
+/* orc_argmin_subsequence with the weight tables of wdtw / wddtw sized for a series of `weight_len` points (wddtw: weight_len - 2):
+ * what `_dilated_distance_profile` sees after metric.reset(X, X) (CD:1769) when it compares windows shorter than the series. */
+int64_t orc_argmin_subsequence_w(int metric, const orc_params *p, const double *S, int64_t s_len, double s_mean, double s_std,
+                                 const double *T, int64_t t_len, int scaled, int64_t k, int64_t weight_len, int64_t *out_idx,
+                                 double *out_dist) {
+  int64_t n_found = 0;
+  subsequence_ea_scan_w(metric, p, S, s_len, s_mean, s_std, T, t_len, scaled, k, out_idx, out_dist, &n_found, NULL, weight_len);
+  return n_found;
 }

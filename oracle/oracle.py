@@ -401,15 +401,15 @@ def seq_mean_std(s):
     return float(np.cumsum(s)[-1] / s.shape[0]), float(lib().orc_std(_dp(s), s.shape[0]))
 
 
-def argmin_subsequence(metric, subs, x, k=1, scaled=False, **params):
+def argmin_subsequence(metric, subs, x, k=1, scaled=False, weight_len=0, **params):
     """argmin_subsequence_distance (_distance.py:1636-1790, _cdistance.pyx:1380-1600): the k closest windows of the i:th
     sample to the i:th subsequence under the sequential scan with Metric._eadistance; (idx, dist) of shape (n, k) in heap
     order.  scaled: subsequence z-normalised with fast_mean_std (std 0 -> 1), windows with the running IncStats."""
     L = lib()
     dp = C.POINTER(C.c_double)
-    L.orc_argmin_subsequence.argtypes = [C.c_int, C.POINTER(Params), dp, C.c_int64, C.c_double, C.c_double, dp, C.c_int64,
-                                         C.c_int, C.c_int64, C.POINTER(C.c_int64), dp]
-    L.orc_argmin_subsequence.restype = C.c_int64
+    L.orc_argmin_subsequence_w.argtypes = [C.c_int, C.POINTER(Params), dp, C.c_int64, C.c_double, C.c_double, dp, C.c_int64,
+                                           C.c_int, C.c_int64, C.c_int64, C.POINTER(C.c_int64), dp]
+    L.orc_argmin_subsequence_w.restype = C.c_int64
     x = _arr(x)
     assert len(subs) == x.shape[0]
     p = make_params(metric, **params)
@@ -420,7 +420,7 @@ def argmin_subsequence(metric, subs, x, k=1, scaled=False, **params):
         mean, std = seq_mean_std(s) if scaled else (0.0, 1.0)
         if std == 0.0:
             std = 1.0
-        n = L.orc_argmin_subsequence(METRIC_IDS[metric], C.byref(p), _dp(s), s.shape[0], mean, std, _dp(x[i]), x.shape[1],
-                                     1 if scaled else 0, k, idx[i].ctypes.data_as(C.POINTER(C.c_int64)), _dp(dist[i]))
+        n = L.orc_argmin_subsequence_w(METRIC_IDS[metric], C.byref(p), _dp(s), s.shape[0], mean, std, _dp(x[i]), x.shape[1],
+                                       1 if scaled else 0, k, int(weight_len), idx[i].ctypes.data_as(C.POINTER(C.c_int64)), _dp(dist[i]))
         assert n == k or metric in ("ddtw", "wddtw", "lcss", "erp", "edr", "msm", "twe", "adtw"), (n, k)
     return idx, dist

@@ -38,7 +38,7 @@ SM_SUBS = (0, 1, 3)   # lengths 12, 30, 3
 AS_CASES = SM_CASES
 
 
-DD_CASES = [c for c in SM_CASES if c[0] not in ("wdtw", "wddtw")]
+DD_CASES = SM_CASES
 DD_GEOMETRY = ((2, 0), (1, 3), (2, "same"), (3, 5), (5, 0))
 
 

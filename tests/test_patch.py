@@ -81,10 +81,10 @@ def test_patch_routes_elastic_subsequence_metrics_only(wb, monkeypatch):
         assert wd.argmin_subsequence_distance(x[:, :5], x, k=2, metric="erp", scale=True) == "cuda"
         assert [c[0] for c in calls] == ["pairwise_subsequence_distance", "subsequence_match", "distance_profile", "argmin_subsequence_distance"]
         assert wd.distance_profile(x[:, :5], x, metric="dtw", dilation=2) == "cuda" and len(calls) == 5
-        # not elastic, or the dilated profile of the weighted metrics: the reference's own code paths
+        # not elastic: the reference's own code paths
         e = wd.pairwise_subsequence_distance(x[0, :5], x, metric="euclidean")
         assert isinstance(e, np.ndarray) and e.shape == (3,)
-        dp = wd.distance_profile(x[:, :5], x, metric="wdtw", dilation=2)
+        dp = wd.distance_profile(x[:, :5], x, metric="manhattan", dilation=2)
         assert isinstance(dp, np.ndarray) and len(calls) == 5
     finally:
         P.unpatch()

@@ -242,8 +242,6 @@ def test_match_host_logic(wb):
         wb.subsequence_match(np.zeros(4), x, threshold=1.0, metric="euclidean")
     with pytest.raises(ValueError, match="must be the same"):
         wb.paired_subsequence_match([np.zeros(4)], x, metric="dtw")
-    with pytest.raises(ValueError, match="wdtw / wddtw"):
-        wb.distance_profile(np.zeros(3), x, dilation=2, metric="wdtw")
     with pytest.raises(ValueError, match="dilation must be"):
         wb.distance_profile(np.zeros(3), x, dilation=0, metric="dtw")
     with pytest.raises(ValueError, match="larger than input"):
@@ -496,10 +494,10 @@ def test_dilated_profile_orchestration_matches_reference_golden(wb, oracle, scan
     from wildboar_b200 import _shim
     ids = {v: k for k, v in oracle.METRIC_IDS.items()}
 
-    def fake(metric_id, params, s, x, k, scaled=False):
+    def fake(metric_id, params, s, x, k, scaled=False, weight_len=0):
         metric = ids[metric_id]
         kw = {name: getattr(params, name) for name in oracle.DEFAULTS[metric]}
-        return oracle.argmin_subsequence(metric, list(s), x, k=k, scaled=scaled, **kw)
+        return oracle.argmin_subsequence(metric, list(s), x, k=k, scaled=scaled, weight_len=weight_len, **kw)
     monkeypatch.setattr(_shim, "subsequence_argmin", fake)
     X, Yd = _dd_inputs(scan_golden)
     for ci, (metric, mp) in enumerate(DD_CASES):
@@ -507,8 +505,6 @@ def test_dilated_profile_orchestration_matches_reference_golden(wb, oracle, scan
             for di, (dil, pad_) in enumerate(DD_GEOMETRY):
                 got = wb.distance_profile(Yd, X, metric=metric, metric_params=mp, scale=scale, dilation=dil, padding=pad_)
                 assert _same(got, scan_golden[f"dd|{ci}|{int(scale)}|{di}"]), (metric, scale, dil, pad_)
-    with pytest.raises(ValueError, match="wdtw / wddtw"):
-        wb.distance_profile(Yd, X, metric="wdtw", dilation=2)
     with pytest.raises(ValueError, match="odd subsequence length"):
         wb.distance_profile(Yd[:, :6], X, metric="dtw", padding="same")
     with pytest.raises(ValueError, match="larger than input"):

@@ -79,7 +79,7 @@ def lib():
                                                 I32P, _DP, _DP, ci, SP]
                 L.wb_cuda_dba_epoch.argtypes = [C.c_void_p, ci, PP, _DP, i64, i64, _IP, _IP, _DP, _DP, ci, _DP, _DP, SP]
                 L.wb_cuda_subsequence_profile.argtypes = [ci, PP, _DP, i64, i64, _DP, i64, i64, i64, ci, _DP, C.c_double, _DP, DV, ci, SP]
-                L.wb_cuda_subsequence_argmin.argtypes = [ci, PP, _DP, i64, i64, _DP, i64, i64, i64, ci, i64, _IP, _DP, DV, ci, SP]
+                L.wb_cuda_subsequence_argmin.argtypes = [ci, PP, _DP, i64, i64, _DP, i64, i64, i64, ci, i64, i64, _IP, _DP, DV, ci, SP]
                 L.wb_cuda_subsequence.argtypes = [ci, PP, _DP, _IP, i64, _DP, i64, i64, i64, ci, ci, _DP, _DP, _IP, DV, ci, SP]
                 L.wb_cuda_argmin.argtypes = [ci, PP, _DP, i64, i64, i64, _DP, i64, i64, i64, i64, _DP, ci, _IP, _DP,
                                              DV, ci, SP]
@@ -458,7 +458,7 @@ def subsequence_profile(metric_id, params, s, x, scaled=False, s_epsilon=None, t
     return out
 
 
-def subsequence_argmin(metric_id, params, s, x, k, scaled=False):
+def subsequence_argmin(metric_id, params, s, x, k, scaled=False, weight_len=0):
     """k closest windows of sample i to subsequence i (wb_cuda_subsequence_argmin): (idx, dist), (nx, k), heap order."""
     apply_engine_override(params)
     params.precision = 0
@@ -471,7 +471,7 @@ def subsequence_argmin(metric_id, params, s, x, k, scaled=False):
     cells = float(nx) * (T - m + 1) * _est_cells(1, int(m), int(m), params.r)
     dv, nd = _dev_array(_resolve_devices(cells))
     _check(lib().wb_cuda_subsequence_argmin(metric_id, C.byref(params), s.ctypes.data_as(_DP), n_s, m, xp, nx, T, xs,
-                                            1 if scaled else 0, int(k), idx.ctypes.data_as(_IP), dist.ctypes.data_as(_DP),
+                                            1 if scaled else 0, int(k), int(weight_len), idx.ctypes.data_as(_IP), dist.ctypes.data_as(_DP),
                                             dv, nd, C.byref(st)))
     _tls.stats = st.as_dict()
     return idx.astype(np.intp, copy=False), dist

@@ -1617,6 +1617,7 @@ struct ProfileJob {
   // argmin_subsequence_distance (argmin_k > 0, paired): the k closest windows under the sequential scan with
   // Metric._eadistance (CD:1380-1548) instead of the dense profile; windows raw (scaled == 0) or z-normalised
   int64_t argmin_k; int64_t* out_idx; double* out_dist;  // (nx, k), heap order
+  int64_t weight_len;  // > 0: wdtw / wddtw weight tables for a series of this many points instead of T (dilated profile)
 };
 
 static int subseq_profile_worker(const ProfileJob& J, int dev, int64_t lo, int64_t hi, wb_stats* st_out) {
@@ -1671,7 +1672,8 @@ static int subseq_profile_worker(const ProfileJob& J, int dev, int64_t lo, int64
         }
         const double *dw = nullptr, *dtw = nullptr;
         if (J.metric == M_WDTW || J.metric == M_WDDTW || J.metric == M_WLCSS || J.metric == M_TWE) {  // wlcss: argmin mode only
-          const int64_t tn = J.metric == M_TWE ? T + 1 : (deriv ? T - 2 : T);
+          const int64_t Tw = J.weight_len > 0 ? J.weight_len : T;  // series the reference reset() the metric with
+          const int64_t tn = J.metric == M_TWE ? T + 1 : (deriv ? Tw - 2 : Tw);
           ws.host_keep.push_back(J.metric == M_TWE ? make_tw(J.p.stiffness, tn) : make_weights(J.p.g, tn));
           std::vector<double>& h = ws.host_keep.back();
           double* d = nullptr;
@@ -2122,14 +2124,15 @@ int wb_cuda_subsequence_profile(int metric, const wb_params* params, const doubl
   wb::ProfileJob J;
   J.metric = metric; J.p = *params; J.s = s; J.ns = n_s; J.m = m; J.x = x; J.nx = nx; J.T = T; J.xs = x_stride;
   J.scaled = scaled ? 1 : 0; J.s_eps = s_epsilon; J.threshold = threshold; J.out = out;
-  J.argmin_k = 0; J.out_idx = nullptr; J.out_dist = nullptr;
+  J.argmin_k = 0; J.out_idx = nullptr; J.out_dist = nullptr; J.weight_len = 0;
   return run_row_sharded(nx, devices, n_devices, stats,
                          [&](int dev, int64_t lo, int64_t hi, wb_stats* st) { return subseq_profile_worker(J, dev, lo, hi, st); });
 }
 
 int wb_cuda_subsequence_argmin(int metric, const wb_params* params, const double* s, int64_t n_s, int64_t m,
                                const double* x, int64_t nx, int64_t T, int64_t x_stride, int scaled, int64_t k,
-                               int64_t* out_idx, double* out_dist, const int* devices, int n_devices, wb_stats* stats) {
+                               int64_t weight_len, int64_t* out_idx, double* out_dist, const int* devices, int n_devices,
+                               wb_stats* stats) {
   if (check_common(metric, params, x, nx, T)) return 1;
   if (!s || !out_idx || !out_dist) { set_err("null argument"); return 1; }
   if (params->precision != 0) { set_err("subsequence search runs in fp64"); return 1; }
@@ -2137,10 +2140,11 @@ int wb_cuda_subsequence_argmin(int metric, const wb_params* params, const double
   if (n_s != nx) { set_err("argmin_subsequence_distance pairs subsequence i with sample i"); return 1; }
   if (m < 1 || m > T) { set_err("the subsequence needs 1 <= length <= n_timestep"); return 1; }
   if (k < 1 || k > T - m + 1) { set_err("k must be in [1, n_timestep - m + 1]"); return 1; }
+  if (weight_len != 0 && weight_len < T) { set_err("weight_len must be 0 or >= n_timestep"); return 1; }
   wb::ProfileJob J;
   J.metric = metric; J.p = *params; J.s = s; J.ns = n_s; J.m = m; J.x = x; J.nx = nx; J.T = T; J.xs = x_stride;
   J.scaled = scaled ? 1 : 0; J.s_eps = nullptr; J.threshold = WB_INF; J.out = nullptr;
-  J.argmin_k = k; J.out_idx = out_idx; J.out_dist = out_dist;
+  J.argmin_k = k; J.out_idx = out_idx; J.out_dist = out_dist; J.weight_len = weight_len;
   return run_row_sharded(nx, devices, n_devices, stats,
                          [&](int dev, int64_t lo, int64_t hi, wb_stats* st) { return subseq_profile_worker(J, dev, lo, hi, st); });
 }

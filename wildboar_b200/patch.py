@@ -36,10 +36,7 @@ def _wrap_sub(name, orig, ours):
     def wrapper(*args, **kwargs):
         metric = kwargs.get("metric")  # defaults are euclidean / mass: not elastic
         base = metric[len("scaled_"):] if isinstance(metric, str) and metric.startswith("scaled_") else metric
-        # the dilated / padded profile is covered except for wdtw / wddtw (series-length weight tables)
-        plain = name != "distance_profile" or (kwargs.get("dilation", 1) == 1 and kwargs.get("padding", 0) == 0) or \
-            base not in ("wdtw", "wddtw")
-        if isinstance(base, str) and base in _s._SUBSEQUENCE_METRICS and plain:
+        if isinstance(base, str) and base in _s._SUBSEQUENCE_METRICS:
             return ours(*args, **kwargs)
         return orig(*args, **kwargs)
     wrapper.__wildboar_b200_original__ = orig

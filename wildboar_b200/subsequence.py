@@ -369,7 +369,7 @@ def distance_profile(y, x, *, dilation=1, padding=0, dim=0, metric="dtw", metric
 
     ``dilation=1, padding=0`` ends in ``_distance_profile`` (_cdistance.pyx:1655-1725, the subsequence metrics); any other
     setting in ``_dilated_distance_profile`` (_cdistance.pyx:804-935, 1728-1862: dilated, zero-padded windows through
-    ``Metric._eadistance``), covered here for the elastic metrics without a series-length weight table (wdtw / wddtw raise)."""
+    ``Metric._eadistance``; wdtw / wddtw keep the weight table of the full series, as ``metric.reset(X, X)`` sizes it)."""
     if isinstance(dilation, bool) or not isinstance(dilation, numbers.Integral) or dilation < 1:
         raise ValueError("dilation must be an int >= 1")
     y = np.squeeze(check_array(y, dtype=np.double, ensure_2d=False))
@@ -428,10 +428,8 @@ def _dilated_profile(y, x, metric, m, scaled, dilation, padding):
     """`_dilated_distance_profile` (_cdistance.pyx:1809-1862) on the device: every (sample, output position) pair is one
     equal-length comparison `Metric._eadistance(x window, kernel part)` -- the window FIRST -- which is what
     wb_cuda_subsequence_argmin evaluates for a "subsequence" = the window against a "sample" = the kernel part with one
-    window and k = 1.  Output positions are grouped by the number of points that enter (borders are truncated)."""
-    if metric in ("wdtw", "wddtw"):
-        raise ValueError("the dilated distance_profile is not accelerated for wdtw / wddtw (their weights span the series "
-                         "length while the compared windows are shorter); use wildboar.distance for it")
+    window and k = 1.  Output positions are grouped by the number of points that enter (borders are truncated); the weight
+    tables of wdtw / wddtw span the full series (`weight_len`), as the reference's `metric.reset(X, X)` leaves them."""
     n, k_len = y.shape
     x_len = x.shape[1]
     if scaled:
@@ -446,7 +444,7 @@ def _dilated_profile(y, x, metric, m, scaled, dilation, padding):
     for o, (xi, ki) in enumerate(geo):
         by_k.setdefault(len(xi), []).append(o)
     for k, positions in by_k.items():
-        if k < 1 or (metric == "ddtw" and k < 3):
+        if k < 1 or (metric in ("ddtw", "wddtw") and k < 3):
             raise ValueError("a border window of this dilated profile keeps %d point(s); the reference writes no value there "
                              "and shifts the rest of the row -- use a smaller padding" % k)
         xi = np.stack([geo[o][0] for o in positions])            # (P, k) sample indices
@@ -464,7 +462,8 @@ def _dilated_profile(y, x, metric, m, scaled, dilation, padding):
                 win = (win - mean[..., None]) / std[..., None]
             s_, P = win.shape[0], win.shape[1]
             dist = _shim.subsequence_argmin(m.metric_id, m._params(), np.ascontiguousarray(win.reshape(s_ * P, k)),
-                                            np.ascontiguousarray(ker.reshape(s_ * P, k)), 1, scaled=False)[1][:, 0]
+                                            np.ascontiguousarray(ker.reshape(s_ * P, k)), 1, scaled=False,
+                                            weight_len=x_len)[1][:, 0]  # wdtw / wddtw: metric.reset(X, X) sized the weights
             # `tmp_dist / (<float>k / k_len)`: a C float division, widened
             out[a:a + step, positions] = dist.reshape(s_, P) / np.float64(np.float32(k) / np.float32(k_len))
     return out
