@@ -19,6 +19,32 @@ def test_library_exports_every_declared_symbol(wb):
         assert hasattr(L, n), n
 
 
+def test_shim_argtypes_match_the_header_prototypes(wb):
+    """Every ctypes binding of the shim has as many arguments as the C prototype in include/wb_cuda.h, pointer / integer /
+    double in the same positions (a mismatch would be silent undefined behaviour at the ABI)."""
+    from wildboar_b200 import _shim
+    hdr = open(os.path.join(ROOT, "include", "wb_cuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = dict(re.findall(r"\b(?:int|void|const char \*)\s*\*?(wb_cuda_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", hdr))
+    L = _shim.lib()
+    checked = 0
+    for name, args in protos.items():
+        fn = getattr(L, name)
+        if fn.argtypes is None:
+            continue
+        params = [a.strip() for a in args.split(",") if a.strip() and a.strip() != "void"]
+        assert len(params) == len(fn.argtypes), (name, len(params), len(fn.argtypes))
+        for prm, ct in zip(params, fn.argtypes):
+            is_ptr = "*" in prm
+            ct_ptr = hasattr(ct, "contents") or ct in (ctypes.c_void_p, ctypes.c_char_p)
+            assert is_ptr == ct_ptr, (name, prm, ct)
+            if not is_ptr:
+                want = ctypes.c_double if prm.startswith("double") else (ctypes.c_int64 if prm.startswith("int64_t") else ctypes.c_int)
+                assert ct is want, (name, prm, ct)
+        checked += 1
+    assert checked >= 15
+
+
 def test_no_gpu_means_error_not_fallback(wb):
     if wb.device_count() > 0:
         pytest.skip("a GPU is present")
