@@ -10,7 +10,10 @@
  * against the reference's own Cython build (oracle/_ref, built by oracle/build_ref.sh)
  * when that build is present and (b) against the committed golden vectors in
  * tests/golden/ that were generated from that same reference build
- * (tests/golden/make_golden.py).
+ * (tests/golden/make_golden.py).  The SURVEY 8f restatements further down (alignments, DBA helpers,
+ * subsequence distances / scans / matches / profiles / k closest windows, IncStats) are pinned the same
+ * way by tests/test_next_rows.py and tests/test_subsequence_scan.py (golden vectors from
+ * tests/golden/make_golden_next.py and make_golden_scan.py).
  *
  * Citations are file:line in the reference tree (/root/reference/src/wildboar):
  *   EL = distance/_elastic.pyx   CD = distance/_cdistance.pyx
