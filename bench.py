@@ -58,7 +58,8 @@ def cells_per_pair(T, r, metric="dtw"):
     return T * (2 * R - 1) - R * (R - 1)
 
 
-from wildboar_b200.sharding import aggregate_throughput, max_over_ranks, row_block  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
+from sharding import aggregate_throughput, max_over_ranks, row_block  # noqa: E402
 
 
 class ClockSampler:
@@ -177,6 +178,152 @@ def run_reference_arm(args, wl, wl_name):
     print(json.dumps(line), flush=True)
 
 
+
+# ---------------------------------------------------------------------------------------------
+# per-config evidence (BASELINE configs[0], [1], [3], [4]): outside the headline timed region
+# ---------------------------------------------------------------------------------------------
+NINE = ["dtw", "wdtw", "ddtw", "adtw", "msm", "twe", "erp", "lcss", "edr"]
+
+
+def _oracle():
+    """The CPU oracle as the CHECKER of the spot checks below (never measured here, never on the product path)."""
+    from oracle import oracle as O
+    return O
+
+
+def spot_check(metric, params, x, y, res, n, seed, self_join=False, row0=0):
+    """Compare n random entries of the full-size device result with the oracle, bit for bit.
+    res[i - row0, j] must equal d(x_i, y_j); for the self join the entry and its mirror equal d(x_min, x_max)."""
+    O = _oracle()
+    rng = np.random.default_rng(seed)
+    rows = res.shape[0]
+    ii = rng.integers(0, rows, n) + row0
+    jj = rng.integers(0, res.shape[1], n)
+    if self_join:
+        lo_, hi_ = np.minimum(ii, jj), np.maximum(ii, jj)
+        keep = lo_ != hi_
+        want = np.zeros(n)
+        want[keep] = O.paired(metric, np.ascontiguousarray(x[hi_[keep]]), np.ascontiguousarray(x[lo_[keep]]), n_jobs=os.cpu_count() or 1, **params)
+    else:
+        want = O.paired(metric, np.ascontiguousarray(y[jj]), np.ascontiguousarray(x[ii]), n_jobs=os.cpu_count() or 1, **params)
+    got = res[ii - row0, jj]
+    return bool(np.array_equal(got, want)), int(n)
+
+
+def _timed_call(fn, reps=1):
+    """One warm-up call, then best of `reps`; returns (result, wall seconds, wb stats of the best call)."""
+    import wildboar_b200 as wb
+    fn()
+    best, best_st, out = None, None, None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out = fn()
+        dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, best_st = dt, wb.last_stats()
+    return out, best, best_st
+
+
+def _row(st, dt, ops, peak_g):
+    k = st["cells"] / (st["kernel_ms"] * 1e-3) / 1e9 if st["kernel_ms"] > 0 else None
+    return {"pairs": int(st["pairs"]), "cells": int(st["cells"]), "kernel_ms": round(st["kernel_ms"], 3), "e2e_ms": round(dt * 1e3, 3),
+            "kernel_gcups": round(k, 1) if k else None, "e2e_gcups": round(st["cells"] / dt / 1e9, 1),
+            "frac": round(k * ops / peak_g, 4) if k else None, "ops_per_cell": ops, "engine": st["engine"], "launches": st["launches"]}
+
+
+def extra_configs(wb, peak_inst, world, rank, dev, barrier, max_over_ranks_fn, quick=False):
+    """cfg1 / cfg2 (N = 1 only: single-GPU configs), cfg4 / cfg5 (every N: rank r computes the r-th eighth of the job, so
+    N = 8 is the whole config).  Every entry: kernel_gcups (CUDA events around the DP kernels), e2e_gcups (host numpy in,
+    host numpy out, wall clock), frac = kernel GCUPS x FP64 ops per cell / measured FP64 issue peak, and `parity`: a spot
+    check of the FULL-SIZE result against the CPU oracle (bit-equal), `parity_n` entries."""
+    peak_g = peak_inst / 1e9
+    out = {}
+    if world == 1:
+        # cfg1: 200 x 150 vs 200 x 150, dtw r = 0.1 -- whole matrix against the oracle
+        x, y = random_walks(200, 150, 1), random_walks(200, 150, 2)
+        res, dt, st = _timed_call(lambda: wb.pairwise_distance(x, y, metric="dtw", metric_params={"r": 0.1}), reps=20)
+        want = _oracle().pairwise("dtw", x, y, r=0.1, n_jobs=os.cpu_count() or 1)
+        e = _row(st, dt, FP64_OPS_PER_CELL["dtw"], peak_g)
+        e.update(parity=bool(np.array_equal(res, want)), parity_n=int(res.size), parity_kind="whole matrix == oracle")
+        out["cfg1"] = e
+        # cfg2: 5000 x 140, nine metrics, default parameters, singleton and two-array forms
+        n2 = 1000 if quick else 5000
+        X = random_walks(n2, 140, 1)
+        Xc = X.copy()
+        c2 = {}
+        for m in NINE:
+            ops = FP64_OPS_PER_CELL[m]
+            res, dt, st = _timed_call(lambda: wb.pairwise_distance(X, metric=m))
+            e = _row(st, dt, ops, peak_g)
+            ok, n = spot_check(m, {}, X, X, res, 300, 11, self_join=True)
+            ok = ok and bool(np.array_equal(res, res.T)) and not res.diagonal().any()
+            e.update(parity=ok, parity_n=n, parity_kind="300 random entries == oracle, matrix == its transpose, zero diagonal")
+            c2[m + "_singleton"] = e
+            res, dt, st = _timed_call(lambda: wb.pairwise_distance(X, Xc, metric=m))
+            e = _row(st, dt, ops, peak_g)
+            ok, n = spot_check(m, {}, X, Xc, res, 300, 12)
+            e.update(parity=ok, parity_n=n, parity_kind="300 random entries == oracle")
+            c2[m + "_two_array"] = e
+        out["cfg2"] = c2
+    # cfg4: argmin k = 1, dtw r = 0.05, 20 000 queries x 200 000 references x 256; rank r owns queries [2500 r, 2500 (r + 1))
+    nq_share, nref = (256, 20000) if quick else (2500, 200000)
+    q_all = random_walks(20000, 256, 3)
+    refs = random_walks(nref, 256, 4)
+    q = np.ascontiguousarray(q_all[rank * nq_share:(rank + 1) * nq_share])
+    call = lambda: wb.argmin_distance(q, refs, k=1, metric="dtw", metric_params={"r": 0.05}, return_distance=True)  # noqa: E731
+    call()
+    barrier()
+    t0 = time.perf_counter()
+    idx, dist = call()
+    dt = time.perf_counter() - t0
+    st = wb.last_stats()
+    barrier()
+    dt_max, k_max = max_over_ranks_fn([dt, st["kernel_ms"]])
+    nominal = world * nq_share * nref * cells_per_pair(256, 0.05)
+    sel = np.random.default_rng(40 + rank).choice(nq_share, 64, replace=False)
+    oi, od = _oracle().argmin("dtw", q[sel], refs, k=1, r=0.05, n_jobs=os.cpu_count() or 1)
+    pruned = st["lb_kim_pruned"] + st["lb_keogh_pruned"]
+    ok4 = bool(np.array_equal(idx[sel], oi) and np.array_equal(dist[sel], od))
+    ok4 = max_over_ranks_fn([0.0 if ok4 else 1.0])[0] == 0.0
+    out["cfg4"] = {"queries": world * nq_share, "references": nref, "k": 1, "pairs": world * nq_share * nref,
+                   "kernel_ms": round(k_max, 2), "e2e_ms": round(dt_max * 1e3, 2),
+                   "nominal_kernel_gcups": round(nominal / (k_max * 1e-3) / 1e9, 1), "nominal_e2e_gcups": round(nominal / dt_max / 1e9, 1),
+                   "kernel_gcups": round(nominal / (k_max * 1e-3) / 1e9, 1), "e2e_gcups": round(nominal / dt_max / 1e9, 1),
+                   "frac": None, "frac_note": "nominal cells (every pair counted in full); 97-99 % of the pairs never reach the DP, so no FP64 roofline fraction applies",
+                   "pruned_fraction_rank0": round(pruned / float(nq_share * nref), 4), "lb_kim_pruned_rank0": int(st["lb_kim_pruned"]),
+                   "lb_keogh_pruned_rank0": int(st["lb_keogh_pruned"]), "launches_rank0": st["launches"],
+                   "parity": ok4, "parity_n": 64 * world,
+                   "parity_kind": "64 random queries of EVERY rank's share replayed by the oracle's sequential scan against ALL references: indices and distances equal"}
+    del refs, q_all
+    # cfg5: msm / twe, r = 0.05, 2000 x 4096 vs 2000 x 4096; rank r owns x rows [250 r, 250 (r + 1))
+    n5, share5 = (256, 32) if quick else (2000, 250)
+    x5, y5 = random_walks(n5, 4096, 1), random_walks(n5, 4096, 2)
+    xs = np.ascontiguousarray(x5[rank * share5:(rank + 1) * share5])
+    c5 = {}
+    for m in ("msm", "twe"):
+        call = lambda: wb.pairwise_distance(xs, y5, metric=m, metric_params={"r": 0.05})  # noqa: E731
+        wb.pairwise_distance(xs[:8], y5, metric=m, metric_params={"r": 0.05})  # warm-up (module load, pools)
+        barrier()
+        t0 = time.perf_counter()
+        res = call()
+        dt = time.perf_counter() - t0
+        st = wb.last_stats()
+        barrier()
+        dt_max, k_max = max_over_ranks_fn([dt, st["kernel_ms"]])
+        cells = world * st["cells"]
+        ops = FP64_OPS_PER_CELL[m]
+        kg = cells / (k_max * 1e-3) / 1e9
+        ok, n = spot_check(m, {"r": 0.05}, x5, y5, res, 300, 50 + rank, row0=rank * share5)
+        ok = max_over_ranks_fn([0.0 if ok else 1.0])[0] == 0.0
+        c5[m] = {"pairs": int(world * st["pairs"]), "cells": int(cells), "kernel_ms": round(k_max, 2), "e2e_ms": round(dt_max * 1e3, 2),
+                 "kernel_gcups": round(kg, 1), "e2e_gcups": round(cells / dt_max / 1e9, 1), "frac": round(kg / world * ops / peak_g, 4),
+                 "ops_per_cell": ops, "engine": st["engine"], "strip": [st.get("strip_w"), st.get("strip_nr"), st.get("strip_warps"), st.get("strip_gring")],
+                 "parity": ok, "parity_n": n * world, "parity_kind": "300 random entries of EVERY rank's row block == oracle"}
+    out["cfg5"] = c5
+    out["note"] = ("rank r computes the r-th eighth of cfg4 (2500 queries) and cfg5 (250 x rows): N = 8 is the whole config; "
+                   "times are the max over ranks, GCUPS the aggregate; parity is checked on every rank's share")
+    return out
+
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
@@ -191,6 +338,8 @@ def main():
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"],
                     help="fp64 = bit-exact mode (the driver's bench line); fp32 = the optional fp32 mode (extra evidence only)")
     ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config evidence (cfg1 / cfg2 / cfg4 / cfg5) and the in-process multi-GPU run")
+    ap.add_argument("--quick-configs", action="store_true", help="DEV ONLY: reduced sizes for the per-config evidence")
     ap.add_argument("--profile-rows", type=int, default=0,
                     help="PROFILING ONLY (ncu): shrink the x row count so ~40 kernel replays stay short; "
                          "the JSON line is then marked and is not a bench value")
@@ -280,9 +429,9 @@ def main():
     checksum = float(out_d[:: max(nx // 64, 1), ::97].sum().item())
 
     # end to end through the public API: host numpy in, host numpy out, every step
-    e2e_steps = args.e2e_steps if args.e2e_steps is not None else args.steps
+    e2e_steps = args.e2e_steps if args.e2e_steps is not None else min(args.steps, 8)
     wb.set_devices([local])
-    wb.pairwise_distance(x_h[: max(nx // 8, 1)], y_h, metric=metric, metric_params={"r": r})  # warm-up
+    res = wb.pairwise_distance(x_h, y_h, metric=metric, metric_params={"r": r})  # warm-up (page-locked result pool, module load)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -291,8 +440,64 @@ def main():
     e2e_s = time.perf_counter() - t0
     e2e_stats = wb.last_stats()
     assert res.shape == (nx, ny)
+    # parity of the headline result itself: the device-resident matrix of the timed steps equals the host-API result, and
+    # 300 random entries of this rank's full-size slab equal the oracle bit for bit
+    same_as_dev = bool(np.array_equal(res[:: max(nx // 64, 1), ::97], out_d[:: max(nx // 64, 1), ::97].cpu().numpy()))
+    ok_h, n_h = spot_check(metric, {"r": r}, random_walks(wl["nx"], T, 1), y_h, res, 300, 30 + rank, row0=lo) if args.precision == "fp64" else (None, 0)
+    import zlib
+    slab_crc = zlib.crc32(memoryview(res).cast("B"))
+    headline_bad = max_over_ranks([0.0 if (same_as_dev and ok_h is not False) else 1.0], device=dev)[0]
 
     ms, e2e_ms, kernel_ms = max_over_ranks([ms, e2e_s * 1e3, kernel_ms], device=dev)
+
+    # optional fp64_fma mode beside the bit-exact one (same kernel, the DTW-family cost folded in by one DFMA): kernel
+    # GCUPS of one extra untimed pass + the largest relative deviation from the bit-exact result on a sample
+    fma = None
+    if args.precision == "fp64" and metric in ("dtw", "ddtw", "wdtw", "adtw") and not args.no_configs:
+        ref_sample = out_d[:: max(nx // 64, 1), ::97].clone()
+        p2 = wb.check_metric(metric)(r=r)._params()
+        p2.precision = 2
+        _shim.pairwise_dev(mid, p2, x_d.data_ptr(), nx, T, y_d.data_ptr(), ny, T, out_d.data_ptr(), stream.cuda_stream, want_stats=False)
+        st2 = _shim.pairwise_dev(mid, p2, x_d.data_ptr(), nx, T, y_d.data_ptr(), ny, T, out_d.data_ptr(), stream.cuda_stream)
+        rel = float(((out_d[:: max(nx // 64, 1), ::97] - ref_sample).abs() / ref_sample.abs().clamp_min(1e-300)).max().item())
+        k2, rel = max_over_ranks([st2["kernel_ms"], rel], device=dev)
+        fma = {"kernel_ms": k2, "kernel_gcups": cells_rank / (k2 * 1e-3) / 1e9, "max_rel_dev_from_bit_exact": rel,
+               "ops_per_cell": FP64_OPS_PER_CELL[metric] - 1,
+               "note": "wb_params.precision = 2 / set_precision('fp64_fma'): fma(v, v, min) -- within the north star's 1e-12, not bit-equal; the headline value is the bit-exact mode"}
+
+    # the library's own multi-GPU path (one process, one host thread per device, the caller's full matrix gathered
+    # into ONE array): rank 0 runs it on all N devices while the other ranks idle at the barrier; every row block of
+    # the result must equal, bit for bit (CRC-32 of the bytes), the slab the owning rank computed on its own device
+    inproc = None
+    if world > 1 and not args.no_configs:
+        crcs = [None] * world
+        dist.all_gather_object(crcs, (lo, hi, slab_crc))
+        barrier()
+        if rank == 0:
+            x_full = random_walks(wl["nx"], T, 1)
+            wb.set_devices(list(range(world)))
+            full = wb.pairwise_distance(x_full, y_h, metric=metric, metric_params={"r": r})  # warm-up (contexts, pools on every device)
+            t0 = time.perf_counter()
+            full = wb.pairwise_distance(x_full, y_h, metric=metric, metric_params={"r": r})
+            dt_in = time.perf_counter() - t0
+            st_in = wb.last_stats()
+            eq = all(zlib.crc32(memoryview(full[a:b]).cast("B")) == c for a, b, c in crcs)
+            inproc = {"value": cells_total / dt_in / 1e9, "unit": "GCUPS", "ms": dt_in * 1e3, "devices": world,
+                      "kernel_ms_max_over_devices": st_in["kernel_ms"], "bit_equal_to_per_rank_slabs": bool(eq),
+                      "api": f"wildboar_b200.set_devices(range({world})); pairwise_distance(x, y) -> one ({wl['nx']}, {ny}) array",
+                      "h2d_bytes": int((wl["nx"] + world * ny) * T * 8), "d2h_bytes": int(wl["nx"] * ny * 8)}
+            wb.set_devices([local])
+            del full, x_full
+        barrier()
+
+    cfgs = None
+    if not args.no_configs and args.precision == "fp64" and args.profile_rows == 0:
+        try:
+            cfgs = extra_configs(wb, peak_inst, world, rank, dev, barrier, lambda v: max_over_ranks(v, device=dev), quick=args.quick_configs)
+        except Exception as e:  # evidence must never take the headline down with it -- but it is reported, not hidden
+            if world > 1:
+                raise
+            cfgs = {"error": repr(e)}
 
     if rank == 0:
         value = aggregate_throughput(cells_total, args.steps, ms) / 1e9
@@ -307,6 +512,8 @@ def main():
             achieved = cells_rank * ops / (kernel_ms * 1e-3) / 1e9
             nominal = 148 * 128 * 1.965
             peak_inst = nominal * 1e9
+        klabel = _kernel_label(metric, st)
+        traffic, traffic_src = _recorded_traffic(args.workload, args.precision, klabel, world, args.profile_rows)
         line = {
             "metric": "pairwise_elastic_distance_gcups", "value": value, "unit": "GCUPS", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -316,11 +523,14 @@ def main():
                        "l2": "256 MB buffer written between timed iterations (L2 flush)", "mode": "fp64 bit-exact (-fmad=false)" if args.precision == "fp64" else "optional fp32 mode (<= 1e-4 relative)"},
             "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": int((nx + ny) * T * 8),
                     "d2h_bytes_per_step": int(nx * ny * 8), "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                    "api": "wildboar_b200.pairwise_distance(numpy, numpy) -> numpy", "device_ms_last_call": e2e_stats["total_ms"]},
+                    "api": "wildboar_b200.pairwise_distance(numpy, numpy) -> numpy (result in page-locked memory from the library's pool)",
+                    "device_ms_last_call": e2e_stats["total_ms"]},
             "gpu_launches": int(args.steps * st["launches"]),
             "clocks": clocks,
+            "parity": {"ok": headline_bad == 0.0, "checked": int(n_h * world),
+                       "kind": "300 random entries of EVERY rank's full-size e2e result == CPU oracle (bit-equal), and the device-resident result of the timed steps == the e2e result on a sample grid"},
             "roofline": {
-                "bound": "fp64_alu" if args.precision == "fp64" else "fp32_alu", "kernel": _kernel_label(metric, st), "achieved": achieved, "peak": peak_inst / 1e9,
+                "bound": "fp64_alu" if args.precision == "fp64" else "fp32_alu", "kernel": klabel, "achieved": achieved, "peak": peak_inst / 1e9,
                 "unit": "G FP64-pipe lane-inst/s", "frac": achieved / (peak_inst / 1e9),
                 "peak_source": ("measured in this run: wb_cuda_fp64_peak(mix=0), DADD issue rate, all SMs" if args.precision == "fp64"
                                 else "nominal FP32 issue rate 148 x 128 lanes x 1.965 GHz"),
@@ -328,10 +538,10 @@ def main():
                 "nominal_peak": nominal, "frac_of_nominal": achieved / nominal,
                 "dtw_mix_peak": peak_mix / 1e9, "frac_of_dtw_mix_peak": achieved / (peak_mix / 1e9),
                 "dtw_mix_peak_note": "register-only loop of the same instruction mix (3 FP64 arith + 2x(DSETP+2 FSEL)): practical issue ceiling, profiles/r01_issue_model.md",
-                # dram__bytes_read.sum + dram__bytes_write.sum of ONE full-size launch of this kernel, from the ncu capture of
-                # this very command line (profiles/r01e_traffic_full_cfg3.csv, profiles/r01d_l2_persist.md); ncu cannot run inside
-                # the timed bench, so the number is recorded here for the workload / device count it was measured on
-                "traffic": (16.68e9 if (args.workload == "cfg3" and world == 1 and args.precision == "fp64" and args.profile_rows == 0) else None),
+                # dram__bytes_read.sum + dram__bytes_write.sum of ONE full-size launch of this kernel: ncu cannot run inside the
+                # timed bench, so the number is READ from the committed capture of this command line (profiles/traffic.json, keyed
+                # by workload, precision, kernel configuration and device count) and is null when the configuration has changed
+                "traffic": traffic, "traffic_source": traffic_src,
                 "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                 "hbm": {"algorithmic_bytes": int((nx + ny) * T * 8 + nx * ny * 8),
                         "achieved_gbs": ((nx + ny) * T * 8 + nx * ny * 8) / (kernel_ms * 1e-3) / 1e9,
@@ -339,9 +549,17 @@ def main():
             },
             "checksum": checksum,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if fma is not None:
+            fma["frac"] = fma["kernel_gcups"] * fma["ops_per_cell"] / (peak_inst / 1e9)
+            line["fp64_fma"] = fma
+        if inproc is not None:
+            line["e2e_inprocess"] = inproc
+        if cfgs is not None:
+            line["configs"] = cfgs
+        if not args.no_cpu_baseline:
             try:
-                cb = time_cpu_sample(wl, target_s=12.0, steps=1)
+                # one warm-up call (inside time_cpu_sample's calibration), then best of 3
+                cb = time_cpu_sample(wl, target_s=6.0, steps=3)
                 line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
             except Exception as e:  # the baseline must never take the GPU number down with it
                 line["cpu_baseline"] = {"value": None, "unit": "GCUPS", "cores": os.cpu_count(), "kind": "unavailable", "sample": repr(e)}
@@ -349,6 +567,18 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _recorded_traffic(workload, precision, kernel_label, world, profile_rows):
+    """dram bytes per launch from the committed ncu capture of this configuration (profiles/traffic.json) or None."""
+    if profile_rows:
+        return None, None
+    try:
+        tab = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return None, None
+    e = tab.get(f"{workload}|{precision}|n{world}|{kernel_label}")
+    return (e["dram_bytes_per_launch"], e["source"]) if e else (None, None)
 
 
 def _kernel_label(metric, st):

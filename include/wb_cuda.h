@@ -20,6 +20,7 @@
  */
 #ifndef WB_CUDA_H
 #define WB_CUDA_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -51,7 +52,9 @@ typedef struct wb_params {
   double stiffness; /* twe                                                         */
   int32_t engine;   /* 0 auto, 1 force row-scan engine, 2 force strip engine, 3 force band-register engine */
   int32_t precision; /* 0: fp64, bit-equal to the reference (default); 1: fp32 arithmetic (<= 1e-4 relative;
-                        lcss / wlcss / edr always run in fp64)                                         */
+                        lcss / wlcss / edr always run in fp64); 2: fp64 with the DTW-family cost folded into the minimum
+                        by ONE fused multiply-add (<= 1e-12 relative, not bit-equal: the reference build has no FMA;
+                        every other metric computes exactly as in mode 0)                                  */
 } wb_params;
 
 /* timing / work counters of the last call (optional out-parameter) */
@@ -264,6 +267,26 @@ int wb_cuda_lb_keogh(const double *q, int64_t nq, int64_t q_stride,
 int wb_cuda_lb_kim(const double *q, int64_t nq, int64_t q_stride,
                    const double *x, int64_t nx, int64_t x_stride, int64_t T,
                    double *out, int device, wb_stats *stats);
+
+/* dtw_envelop and dtw_lb_keogh of wildboar.distance.dtw, batched over n series (all dense, C order).
+ * wb_cuda_dtw_envelope: lower/upper[i][k] = min/max of x[i][max(0,k-w) .. min(T-1,k+w)]; `w` is the resolved warp size
+ *   (distance/dtw.py:155-190: max(floor(T r), 1), T - 1 when that equals T); fails for w outside [0, T) like
+ *   _dtw_envelop (EL:1076-1092).
+ * wb_cuda_dtw_lb_keogh_terms: cb[i][k] = squared excess of x[i][k] over [lower[i][k], upper[i][k]], min_dist[i] =
+ *   sqrt(sum_k cb[i][k]) summed in time order -- _dtw_lb_keogh, EL:1095-1115 (cumulative_bound EL:228-260). */
+int wb_cuda_dtw_envelope(const double *x, int64_t n, int64_t T, int64_t x_stride, int64_t w,
+                         double *lower, double *upper, int device, wb_stats *stats);
+int wb_cuda_dtw_lb_keogh_terms(const double *x, const double *lower, const double *upper, int64_t n, int64_t T,
+                               double *min_dist, double *cb, int device, wb_stats *stats);
+
+/* Page-locked host memory for RESULT buffers (optional).  The host entry points accept any caller-owned `out`; when it
+ * is page-locked (from here, cudaHostAlloc or cudaHostRegister) the result slabs arrive by asynchronous DMA at PCIe
+ * speed instead of through the driver's pageable staging.  Released blocks are pooled (WILDBOAR_CUDA_PINNED_POOL_MB,
+ * default 4096) because page-locking costs ~0.3 ms per MB.  This is the allocation the reference does with
+ * `np.empty((x.shape[0], y.shape[0]))` in _pairwise_distance / _singleton_pairwise_distance (CD:1197, 1260).
+ * wb_cuda_host_alloc returns NULL when no page-locked memory can be had (the caller then uses ordinary memory). */
+void *wb_cuda_host_alloc(size_t bytes);
+void wb_cuda_host_free(void *p);
 
 /* Measured FP64 issue rate of the current device: runs a register-only DADD/DMUL chain on
  * every SM and returns FP64 warp-lane instructions per second (the ALU roofline denominator,

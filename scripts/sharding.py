@@ -1,4 +1,4 @@
-"""Row sharding helpers shared by bench.py and the multi-process tests.
+"""Row sharding helpers shared by bench.py and the multi-process tests (bench tooling, not part of the product package).
 
 The distance matrix shards by contiguous row blocks of x (the reference's thread partitioner,
 utils/_parallel.py:7-23); y is replicated; every rank writes only its own rows, so the data path

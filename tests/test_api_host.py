@@ -39,7 +39,8 @@ def test_shim_argtypes_match_the_header_prototypes(wb):
             ct_ptr = hasattr(ct, "contents") or ct in (ctypes.c_void_p, ctypes.c_char_p)
             assert is_ptr == ct_ptr, (name, prm, ct)
             if not is_ptr:
-                want = ctypes.c_double if prm.startswith("double") else (ctypes.c_int64 if prm.startswith("int64_t") else ctypes.c_int)
+                want = (ctypes.c_double if prm.startswith("double") else ctypes.c_int64 if prm.startswith("int64_t")
+                        else ctypes.c_size_t if prm.startswith("size_t") else ctypes.c_int)
                 assert ct is want, (name, prm, ct)
         checked += 1
     assert checked >= 15
@@ -123,3 +124,30 @@ def test_precision_switch(wb, monkeypatch):
         wb.get_precision()
     with pytest.raises(ValueError):
         wb.set_precision("fp16")
+
+
+def test_package_installs_with_pip_and_binds_every_symbol(wb, tmp_path):
+    """pyproject.toml + setup.py (the reference's packaging counterpart: setup.py:102-127, pyproject.toml:54-65):
+    `pip install .` builds / ships libwbcuda.so + wb_cuda.h, and the installed copy -- imported from another working
+    directory, without the repository on sys.path -- loads the library and binds every symbol of the header."""
+    import subprocess
+    import sys
+    target = tmp_path / "site"
+    r = subprocess.run([sys.executable, "-m", "pip", "install", "--no-build-isolation", "--no-deps", "--no-index", "--quiet",
+                        "--target", str(target), ROOT], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    code = (
+        "import os, re, ctypes, wildboar_b200 as wb\n"
+        "from wildboar_b200 import _shim\n"
+        f"assert os.path.realpath(wb.__file__).startswith(os.path.realpath({str(target)!r})), wb.__file__\n"
+        "hdr = open(os.path.join(wb.get_include(), 'wb_cuda.h')).read()\n"
+        "L = _shim.lib()\n"
+        "names = set(re.findall(r'\\b(wb_cuda_[a-z0-9_]+)\\s*\\(', hdr))\n"
+        "assert len(names) >= 25 and all(hasattr(L, n) for n in names)\n"
+        "assert os.path.dirname(wb.library_path()) == os.path.dirname(os.path.realpath(wb.__file__))\n"
+        "print('ok', wb.__version__, len(names))\n"
+    )
+    env = {k: v for k, v in os.environ.items() if k != "PYTHONPATH"}
+    env["PYTHONPATH"] = str(target)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(tmp_path), env=env)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr

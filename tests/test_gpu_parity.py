@@ -337,3 +337,112 @@ def test_fp32_argmin_indices_on_separated_data(fp32, oracle):
     assert clear.sum() > 32
     assert np.array_equal(idx[clear, 0], np.argmin(full, axis=1)[clear])
     _close32(dist[:, 0], full[np.arange(len(q)), idx[:, 0]], "argmin fp32 distances")
+
+
+# ---- round 2: host pipeline (page-locked results, device-side mirror), fp64_fma mode, advisor corners ----
+@pytest.mark.parametrize("metric", ["dtw", "msm", "erp", "ddtw"])
+def test_self_join_mirrored_on_the_device(W, oracle, metric, monkeypatch):
+    """Single-device self join: the kernel writes the lower triangle into the device-resident n x n matrix; with many
+    small slabs (row0 != 0 in every chunk but the first) the result is still the reference's mirrored upper triangle --
+    also for the asymmetric metrics, whose lower triangle is NOT d(x_j, x_i)."""
+    X = random_walks(333, 40, 51)
+    want = oracle.pairwise(metric, X, None, r=0.3, n_jobs=0)
+    monkeypatch.setenv("WILDBOAR_CUDA_SLAB_KB", "64")
+    got = W.pairwise_distance(X, metric=metric, metric_params={"r": 0.3})
+    _eq(got, want, metric + " self, 64 KB slabs")
+    assert np.array_equal(got, got.T) and not got.diagonal().any()
+    monkeypatch.delenv("WILDBOAR_CUDA_SLAB_KB")
+    _eq(W.pairwise_distance(X, metric=metric, metric_params={"r": 0.3}), want, metric + " self, one slab")
+    # multivariate self join, dim="mean": the mirrored entries carry the combined value
+    X3 = random_walks(90 * 3, 30, 52).reshape(90, 3, 30)
+    per_dim = [oracle.pairwise(metric, np.ascontiguousarray(X3[:, d]), None, r=0.3, n_jobs=0) for d in range(3)]
+    _eq(W.pairwise_distance(X3, dim="mean", metric=metric, metric_params={"r": 0.3}), np.mean(per_dim, axis=0), metric + " self mean")
+
+
+def test_results_land_in_page_locked_memory_and_the_pool_recycles(W, oracle, monkeypatch):
+    from wildboar_b200 import _shim
+    x, y = random_walks(600, 32, 53), random_walks(700, 32, 54)
+    want = oracle.pairwise("dtw", x, y, r=0.2, n_jobs=0)
+    monkeypatch.setenv("WILDBOAR_CUDA_SLAB_KB", "256")  # > 2 slabs: exercises the event-ordered double buffering
+    a = W.pairwise_distance(x, y, metric="dtw", metric_params={"r": 0.2})
+    assert isinstance(a.base, _shim._PinnedBlock) or isinstance(getattr(a.base, "base", None), _shim._PinnedBlock)
+    _eq(a, want, "pinned result")
+    ptr = a.ctypes.data
+    del a
+    b = W.pairwise_distance(x, y, metric="dtw", metric_params={"r": 0.2})
+    assert b.ctypes.data == ptr, "the released block was not recycled by the pool"
+    _eq(b, want, "recycled pinned result")
+    c = b.copy()  # ordinary memory; the pinned block goes back to the pool when b dies
+    del b
+    _eq(c, want, "copy")
+    monkeypatch.setenv("WILDBOAR_CUDA_PINNED_RESULTS", "0")
+    d = W.pairwise_distance(x, y, metric="dtw", metric_params={"r": 0.2})
+    assert not isinstance(d.base, _shim._PinnedBlock)
+    _eq(d, want, "pageable result")
+
+
+@pytest.fixture
+def fma(W):
+    W.set_precision("fp64_fma")
+    yield W
+    W.set_precision(None)
+
+
+@pytest.mark.parametrize("metric", ["dtw", "ddtw", "wdtw", "adtw", "wddtw"])
+def test_fp64_fma_mode_within_1e12(fma, oracle, metric):
+    """Optional fused-multiply-add mode (wb_params.precision = 2): <= 1e-12 relative against the reference (the north
+    star's fp64 tolerance) -- written here as the test's tolerance; the default mode stays bit-equal."""
+    worst = 0.0
+    for (nx, ny, Tx, Ty, r) in [(48, 100, 140, 140, 1.0), (40, 70, 512, 512, 0.1), (30, 45, 50, 77, 0.2), (6, 40, 3, 9, 0.5)]:
+        if metric == "wddtw" and Tx > Ty:
+            continue
+        x, y = random_walks(nx, Tx, 61), random_walks(ny, Ty, 62)
+        got = fma.pairwise_distance(x, y, metric=metric, metric_params={"r": r})
+        want = oracle.pairwise(metric, x, y, r=r, n_jobs=0)
+        err = np.abs(got - want) / np.maximum(np.abs(want), 1e-300)
+        assert err.max() <= 1e-12, (metric, Tx, Ty, r, float(err.max()))
+        worst = max(worst, float(err.max()))
+    assert fma.get_precision() == "fp64_fma"
+
+
+def test_fp64_fma_mode_leaves_other_metrics_bit_equal_and_argmin_indices_exact(fma, oracle):
+    x, y = random_walks(40, 90, 63), random_walks(70, 90, 64)
+    for metric in ("msm", "twe", "erp", "lcss", "edr"):
+        _eq(fma.pairwise_distance(x, y, metric=metric, metric_params={"r": 0.3}), oracle.pairwise(metric, x, y, r=0.3, n_jobs=0), metric)
+    q, refs = random_walks(64, 128, 65), random_walks(500, 128, 66)
+    idx, dist = fma.argmin_distance(q, refs, k=1, metric="dtw", metric_params={"r": 0.1}, return_distance=True)
+    oi, od = oracle.argmin("dtw", q, refs, k=1, r=0.1)
+    assert np.array_equal(idx, oi)
+    assert (np.abs(dist - od) <= 1e-12 * np.abs(od)).all()
+
+
+@pytest.mark.parametrize("k", [1, 3])
+def test_argmin_adtw_negative_penalty_matches_the_scan(W, oracle, k):
+    """adtw accepts a negative penalty (EL:3349); row minima are then not monotone and the reference's eadistance may
+    abandon a pair whose final distance is below the threshold -- the replay has to use the row-minimum maxima."""
+    q, refs = random_walks(24, 60, 71), random_walks(150, 60, 72)
+    for p in (-0.5, -3.0):
+        for r in (0.1, 1.0):
+            idx, dist = W.argmin_distance(q, refs, k=k, metric="adtw", metric_params={"r": r, "p": p}, return_distance=True)
+            oi, od = oracle.argmin("adtw", q, refs, k=k, r=r, p=p)
+            _eq(idx, oi, f"adtw p={p} r={r} idx")
+            _eq(dist, od, f"adtw p={p} r={r} dist")
+
+
+@pytest.mark.parametrize("n_dims", [8, 9, 17, 130])
+def test_dim_mean_single_output_follows_numpy_pairwise_summation(W, oracle, n_dims):
+    """np.mean(list_of_matrices, axis=0) on ONE output element with >= 8 dimensions is a contiguous reduction that numpy
+    sums pairwise; the mirror must return numpy's value there (advisor finding, round 1)."""
+    x = random_walks(n_dims, 25, 81).reshape(1, n_dims, 25)
+    y = random_walks(n_dims, 25, 82).reshape(1, n_dims, 25)
+    per_dim = [oracle.pairwise("dtw", x[:, d], y[:, d], r=0.2, n_jobs=0) for d in range(n_dims)]
+    got = W.pairwise_distance(x, y, dim="mean", metric="dtw", metric_params={"r": 0.2})
+    assert np.array_equal(np.asarray(got).reshape(1, 1), np.mean(per_dim, axis=0))
+    per_dim_p = [oracle.paired("dtw", x[:, d], y[:, d], r=0.2) for d in range(n_dims)]
+    got = W.paired_distance(x, y, dim="mean", metric="dtw", metric_params={"r": 0.2})
+    assert np.array_equal(np.asarray(got).reshape(1), np.mean(per_dim_p, axis=0))
+    # more than one output element: sequential over the dimensions (device-combined) == numpy
+    x3 = random_walks(3 * n_dims, 25, 83).reshape(3, n_dims, 25)
+    per_dim = [oracle.pairwise("dtw", np.ascontiguousarray(x3[:, d]), y[:, d], r=0.2, n_jobs=0) for d in range(n_dims)]
+    got = W.pairwise_distance(x3, y, dim="mean", metric="dtw", metric_params={"r": 0.2})
+    assert np.array_equal(np.asarray(got).reshape(3, 1), np.mean(per_dim, axis=0))

@@ -102,3 +102,76 @@ def test_device_lb_feeds_argmin_like_the_reference(wb, oracle):
     oi, od = oracle.argmin("dtw", q, refs, k=3, lower_bound=lb, r=0.1)
     assert np.array_equal(idx, oi) and np.array_equal(dist, od)
     assert (lb <= oracle.pairwise("dtw", q, refs, r=0.1, n_jobs=0) + 1e-12).all()
+
+
+# ---- dtw_envelop / dtw_lb_keogh (distance/dtw.py:155-243), second half of SURVEY 8f-2 ----
+@pytest.fixture(scope="module")
+def dtw_lb_golden():
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dtw_lb_golden.npz")
+    with np.load(path) as z:
+        return {k: z[k] for k in z.files}
+
+
+def _dtw_lb_cases(g):
+    for k in g:
+        if k.startswith("lower|"):
+            _, T, r = k.split("|")
+            yield int(T), float(r), r
+
+
+def test_oracle_envelope_matches_dtw_envelop_golden(oracle, dtw_lb_golden):
+    g = dtw_lb_golden
+    n = 0
+    for T, r, rs in _dtw_lb_cases(g):
+        w = oracle.lb_warp_size(T, r)
+        lo, hi = oracle.envelope(g[f"y|{T}"], w)
+        assert np.array_equal(lo, g[f"lower|{T}|{rs}"]) and np.array_equal(hi, g[f"upper|{T}|{rs}"]), (T, r)
+        # min_dist = sqrt of the sequential sum of the golden per-step terms; the terms are the squared excess
+        x = g[f"x|{T}"]
+        cb = np.where(x > hi, (x - hi) ** 2, np.where(x < lo, (x - lo) ** 2, 0.0))
+        assert np.array_equal(cb, g[f"cb|{T}|{rs}"]), (T, r)
+        s = 0.0
+        for v in cb:
+            s += v
+        assert np.sqrt(s) == g[f"min_dist|{T}|{rs}"], (T, r)
+        n += 1
+    assert n == 35
+
+
+def test_dtw_lb_host_validation(wb):
+    from wildboar_b200.dtw import dtw_envelop, dtw_lb_keogh
+    with pytest.raises(ValueError):
+        dtw_envelop(np.arange(5.0), r=1.5)
+    with pytest.raises(ValueError, match="can't be None"):
+        dtw_lb_keogh(np.arange(5.0))
+    with pytest.raises(ValueError, match="same number of timesteps"):
+        dtw_lb_keogh(np.arange(5.0), np.arange(6.0))
+    with pytest.raises(ValueError, match="same number of timesteps"):
+        dtw_lb_keogh(np.arange(5.0), lower=np.arange(4.0), upper=np.arange(5.0))
+
+
+@pytest.mark.gpu
+def test_device_dtw_envelop_and_lb_keogh_match_golden(wb, oracle, dtw_lb_golden):
+    from wildboar_b200 import _shim
+    from wildboar_b200.dtw import dtw_envelop, dtw_lb_keogh
+    wb.set_devices([0])
+    g = dtw_lb_golden
+    for T, r, rs in _dtw_lb_cases(g):
+        x, y = g[f"x|{T}"], g[f"y|{T}"]
+        lo, hi = dtw_envelop(y, r=r)
+        assert np.array_equal(lo, g[f"lower|{T}|{rs}"]) and np.array_equal(hi, g[f"upper|{T}|{rs}"]), (T, r)
+        md, cb = dtw_lb_keogh(x, y, r=r)
+        assert md == g[f"min_dist|{T}|{rs}"] and np.array_equal(cb, g[f"cb|{T}|{rs}"]), (T, r)
+        md2, cb2 = dtw_lb_keogh(x, lower=lo, upper=hi)
+        assert md2 == md and np.array_equal(cb2, cb)
+    # batched form behind the mirrors: many series in one call, against the oracle's envelope
+    X = random_walks(300, 190, 39)
+    lo, hi = _shim.dtw_envelope(X, 7)
+    for i in (0, 17, 299):
+        ol, oh = oracle.envelope(X[i], 7)
+        assert np.array_equal(lo[i], ol) and np.array_equal(hi[i], oh)
+    Q = random_walks(300, 190, 40)
+    md, cb = _shim.dtw_lb_keogh_terms(Q, lo, hi)
+    for i in (0, 17, 299):
+        assert md[i] == oracle.lb_keogh_one(Q[i], lo[i], hi[i])

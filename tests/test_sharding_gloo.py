@@ -19,9 +19,10 @@ def _free_port():
 
 def _worker(rank, world, port, tmp):
     sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
     import torch.distributed as dist
     from oracle import oracle as O
-    from wildboar_b200.sharding import aggregate_throughput, max_over_ranks, row_block
+    from sharding import aggregate_throughput, max_over_ranks, row_block
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -55,7 +56,8 @@ def test_row_sharding_world_size_2(tmp_path, oracle):
 
 
 def test_row_block_partition():
-    from wildboar_b200.sharding import row_block
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from sharding import row_block
     for n in (1, 7, 8, 10000, 10001):
         for nb in (1, 2, 3, 4, 8):
             if nb > n:

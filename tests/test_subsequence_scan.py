@@ -419,9 +419,13 @@ def test_subsequence_family_edge_shapes(W, oracle):
         od, oi = odist(base, subs, X[:1], **mp)
         assert np.array_equal(d, od[0]) and np.array_equal(i, oi[0]), metric
         # profile / matches / argmin with a single window
+        # the reference's undilated profile IGNORES dim and reads dimension 0 of x (&self.x[i, 0, 0], CD:1690-1699;
+        # checked against the live reference: distance_profile(Y, X3, dim=1) == distance_profile(Y, X3[:, 0]))
         dp = W.distance_profile(X, X3, dim=1, metric=metric, metric_params=mp)
-        want = oracle.subsequence_matches(base, X, X, np.inf, scaled, mean_std=_view_mean_std, **mp)
+        want = oracle.subsequence_matches(base, X, np.ascontiguousarray(X3[:, 0, :]), np.inf, scaled, mean_std=_view_mean_std, **mp)
         assert _same(np.atleast_1d(dp), want[:, 0]), metric
+        with pytest.raises(ValueError, match="dimensions of y"):
+            W.distance_profile(X[:, :9], X3, dim=1, dilation=2, metric=metric, metric_params=mp)
         ai, ad = W.argmin_subsequence_distance(X[:, :29], X3, dim=1, k=2, metric=base, scale=scaled, metric_params=mp, return_distance=True)
         oi2, od2 = oracle.argmin_subsequence(base, list(X[:, :29]), X, k=2, scaled=scaled, **mp)
         assert np.array_equal(ai, oi2) and np.array_equal(ad, od2), metric

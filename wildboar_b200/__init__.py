@@ -24,11 +24,25 @@ from .subsequence import (  # noqa: F401
     pairwise_subsequence_distance,
     subsequence_match,
 )
+__version__ = "0.2.0"
+
+
+def get_include():
+    """Directory that holds the C-ABI header ``wb_cuda.h`` (an installed package carries its own copy; a source checkout
+    uses ``include/`` at the repository root)."""
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    for d in (os.path.join(here, "include"), os.path.join(here, "..", "include")):
+        if os.path.isfile(os.path.join(d, "wb_cuda.h")):
+            return os.path.abspath(d)
+    raise FileNotFoundError("wb_cuda.h not found")
+
+
 from ._shim import device_count, get_precision, last_stats, library_path, set_devices, set_precision  # noqa: F401
 
 __all__ = [
     "pairwise_distance", "paired_distance", "argmin_distance", "check_metric",
     "pairwise_subsequence_distance", "paired_subsequence_distance", "subsequence_match", "paired_subsequence_match",
     "distance_profile", "argmin_subsequence_distance",
-    "device_count", "set_devices", "set_precision", "get_precision", "last_stats", "library_path",
+    "get_include", "device_count", "set_devices", "set_precision", "get_precision", "last_stats", "library_path",
 ]

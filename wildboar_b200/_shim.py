@@ -88,6 +88,12 @@ def lib():
                 L.wb_cuda_lb_keogh.argtypes = [_DP, i64, i64, _DP, i64, i64, i64, C.c_double, ci, _DP, ci, SP]
                 L.wb_cuda_lb_kim.argtypes = [_DP, i64, i64, _DP, i64, i64, i64, _DP, ci, SP]
                 L.wb_cuda_fp64_peak.argtypes = [ci, _DP, _DP]
+                L.wb_cuda_dtw_envelope.argtypes = [_DP, i64, i64, i64, i64, _DP, _DP, ci, SP]
+                L.wb_cuda_dtw_lb_keogh_terms.argtypes = [_DP, _DP, _DP, i64, i64, _DP, _DP, ci, SP]
+                L.wb_cuda_host_alloc.argtypes = [C.c_size_t]
+                L.wb_cuda_host_alloc.restype = C.c_void_p
+                L.wb_cuda_host_free.argtypes = [C.c_void_p]
+                L.wb_cuda_host_free.restype = None
                 _lib = L
     return _lib
 
@@ -119,23 +125,27 @@ def _resolve_devices(work_cells):
 
 
 _precision = None
+# wb_params.precision: bit-exact fp64 / optional fp32 mode / fp64 with fused multiply-add in the DTW-family cell
+_PRECISIONS = {"fp64": 0, "fp32": 1, "fp64_fma": 2}
 
 
 def set_precision(precision):
     """Arithmetic of the DP kernels: "fp64" (default: bit-equal to the reference) or "fp32"
     (optional mode of the north star: <= 1e-4 relative error, about 3x the throughput; lcss, wlcss and
-    edr are step functions of a threshold test and always run in fp64).  None = take
+    edr are step functions of a threshold test and always run in fp64) or "fp64_fma" (fp64 with the DTW-family
+    cost folded into the running minimum by one fused multiply-add: <= 1e-12 relative, ~15 % faster, not bit-equal
+    because the reference build has no FMA).  None = take
     WILDBOAR_CUDA_PRECISION from the environment (default fp64)."""
     global _precision
-    if precision is not None and precision not in ("fp64", "fp32"):
-        raise ValueError("precision must be 'fp64', 'fp32' or None")
+    if precision is not None and precision not in _PRECISIONS:
+        raise ValueError("precision must be 'fp64', 'fp32', 'fp64_fma' or None")
     _precision = precision
 
 
 def get_precision():
     p = _precision if _precision is not None else os.environ.get("WILDBOAR_CUDA_PRECISION", "fp64").strip().lower()
-    if p not in ("fp64", "fp32"):
-        raise ValueError("WILDBOAR_CUDA_PRECISION must be fp64 or fp32")
+    if p not in _PRECISIONS:
+        raise ValueError("WILDBOAR_CUDA_PRECISION must be fp64, fp32 or fp64_fma")
     return p
 
 
@@ -149,7 +159,7 @@ def apply_engine_override(params):
     stamps the selected precision into the parameter block."""
     e = os.environ.get("WILDBOAR_CUDA_ENGINE", "").strip().lower()
     params.engine = {"rowscan": 1, "strip": 2, "band": 3}.get(e, 0)
-    params.precision = 1 if get_precision() == "fp32" else 0
+    params.precision = _PRECISIONS[get_precision()]
     return params
 
 
@@ -169,6 +179,35 @@ def _rows(a):
     return a, a.ctypes.data_as(_DP), a.shape[0], a.shape[1], stride
 
 
+class _PinnedBlock:
+    """Page-locked result memory from the library's pool (wb_cuda_host_alloc), exposed through the array interface;
+    the block goes back to the pool when the last array viewing it is gone."""
+
+    def __init__(self, ptr, shape):
+        self._ptr = ptr
+        self.__array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+    def __del__(self):
+        p, self._ptr = self._ptr, None
+        if p and _lib is not None:
+            _lib.wb_cuda_host_free(p)
+
+
+_PINNED_MIN_BYTES = 1 << 20
+
+
+def result_array(shape):
+    """float64 result array: page-locked for results of 1 MB and more (the device writes them back by asynchronous DMA
+    at PCIe speed; see wb_cuda_host_alloc), ordinary numpy memory otherwise or when no page-locked memory is to be had.
+    WILDBOAR_CUDA_PINNED_RESULTS=0 turns the page-locked results off."""
+    n = int(np.prod(shape)) * 8
+    if n >= _PINNED_MIN_BYTES and os.environ.get("WILDBOAR_CUDA_PINNED_RESULTS", "1") != "0":
+        ptr = lib().wb_cuda_host_alloc(n)
+        if ptr:
+            return np.asarray(_PinnedBlock(ptr, shape))
+    return np.empty(shape, dtype=np.float64)
+
+
 def _dev_array(devs):
     return (C.c_int * len(devs))(*devs), len(devs)
 
@@ -183,13 +222,13 @@ def pairwise(metric_id, params, x, y):
     x, xp, nx, Tx, xs = _rows(x)
     st = WbStats()
     if y is None:
-        out = np.empty((nx, nx), dtype=np.float64)
+        out = result_array((nx, nx))
         dv, nd = _dev_array(_resolve_devices(_est_cells(nx * nx / 2, Tx, Tx, params.r)))
         _check(lib().wb_cuda_pairwise_self(metric_id, C.byref(params), xp, nx, Tx, xs, out.ctypes.data_as(_DP), dv, nd,
                                            C.byref(st)))
     else:
         y, yp, ny, Ty, ys = _rows(y)
-        out = np.empty((nx, ny), dtype=np.float64)
+        out = result_array((nx, ny))
         dv, nd = _dev_array(_resolve_devices(_est_cells(nx * ny, Tx, Ty, params.r)))
         _check(lib().wb_cuda_pairwise(metric_id, C.byref(params), xp, nx, Tx, xs, yp, ny, Ty, ys,
                                       out.ctypes.data_as(_DP), dv, nd, C.byref(st)))
@@ -232,14 +271,14 @@ def pairwise_nd(metric_id, params, x, y, combine):
     full = combine == "full"
     st = WbStats()
     if y is None:
-        out = np.empty((nd, nx, nx) if full else (nx, nx), dtype=np.float64)
+        out = result_array((nd, nx, nx) if full else (nx, nx))
         dv, ndv = _dev_array(_resolve_devices(nd * _est_cells(nx * nx / 2, Tx, Tx, params.r)))
         _check(lib().wb_cuda_pairwise_nd(metric_id, C.byref(params), xp, nx, nd, Tx, xss, xds, None, 0, 0, 0, 0,
                                          1 if full else 0, out.ctypes.data_as(_DP), dv, ndv, C.byref(st)))
     else:
         y, yp, ny, ndy, Ty, yss, yds = _samples(y)
         assert nd == ndy
-        out = np.empty((nd, nx, ny) if full else (nx, ny), dtype=np.float64)
+        out = result_array((nd, nx, ny) if full else (nx, ny))
         dv, ndv = _dev_array(_resolve_devices(nd * _est_cells(nx * ny, Tx, Ty, params.r)))
         _check(lib().wb_cuda_pairwise_nd(metric_id, C.byref(params), xp, nx, nd, Tx, xss, xds, yp, ny, Ty, yss, yds,
                                          1 if full else 0, out.ctypes.data_as(_DP), dv, ndv, C.byref(st)))
@@ -314,7 +353,7 @@ def pairwise_fitted(metric_id, params, x, fitted, combine="mean"):
     x, xp, nx, nd, Tx, xss, xds = _samples(x)
     full = combine == "full"
     n = fitted.shape[0]
-    out = np.empty((nd, nx, n) if full else (nx, n), dtype=np.float64)
+    out = result_array((nd, nx, n) if full else (nx, n))
     st = WbStats()
     _check(lib().wb_cuda_pairwise_fitted(metric_id, C.byref(params), xp, nx, nd, Tx, xss, xds, fitted._handle(),
                                          1 if full else 0, out.ctypes.data_as(_DP), C.byref(st)))
@@ -487,7 +526,7 @@ def lb_keogh(q, x, r, kind):
     q, qp, nq, T, qs = _rows(q)
     x, xp, nx, Tx, xs = _rows(x)
     assert T == Tx
-    out = np.empty((nq, nx), dtype=np.float64)
+    out = result_array((nq, nx))
     st = WbStats()
     _check(lib().wb_cuda_lb_keogh(qp, nq, qs, xp, nx, xs, T, float(r), int(kind), out.ctypes.data_as(_DP), _first_device(),
                                   C.byref(st)))
@@ -499,11 +538,39 @@ def lb_kim(q, x):
     q, qp, nq, T, qs = _rows(q)
     x, xp, nx, Tx, xs = _rows(x)
     assert T == Tx
-    out = np.empty((nq, nx), dtype=np.float64)
+    out = result_array((nq, nx))
     st = WbStats()
     _check(lib().wb_cuda_lb_kim(qp, nq, qs, xp, nx, xs, T, out.ctypes.data_as(_DP), _first_device(), C.byref(st)))
     _tls.stats = st.as_dict()
     return out
+
+
+def dtw_envelope(x, w):
+    """(lower, upper) envelopes of half-width w for every row of x (n, T)."""
+    x, xp, n, T, xs = _rows(x)
+    lo = np.empty((n, T), dtype=np.float64)
+    hi = np.empty((n, T), dtype=np.float64)
+    st = WbStats()
+    _check(lib().wb_cuda_dtw_envelope(xp, n, T, xs, int(w), lo.ctypes.data_as(_DP), hi.ctypes.data_as(_DP), _first_device(),
+                                      C.byref(st)))
+    _tls.stats = st.as_dict()
+    return lo, hi
+
+
+def dtw_lb_keogh_terms(x, lower, upper):
+    """(min_dist (n,), cb (n, T)): LB_Keogh of every row of x against the envelope rows, with the per-step terms."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    lower = np.ascontiguousarray(lower, dtype=np.float64)
+    upper = np.ascontiguousarray(upper, dtype=np.float64)
+    n, T = x.shape
+    assert lower.shape == (n, T) and upper.shape == (n, T)
+    md = np.empty(n, dtype=np.float64)
+    cb = np.empty((n, T), dtype=np.float64)
+    st = WbStats()
+    _check(lib().wb_cuda_dtw_lb_keogh_terms(x.ctypes.data_as(_DP), lower.ctypes.data_as(_DP), upper.ctypes.data_as(_DP), n, T,
+                                            md.ctypes.data_as(_DP), cb.ctypes.data_as(_DP), _first_device(), C.byref(st)))
+    _tls.stats = st.as_dict()
+    return md, cb
 
 
 def pairwise_dev(metric_id, params, x_ptr, nx, Tx, y_ptr, ny, Ty, out_ptr, stream=0, want_stats=True):

@@ -385,7 +385,12 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
   const int k = (int)io.k;
   int kind; double scale = 1.0;
   const bool dtwfam = is_dtw_family(c.metric);
-  if (dtwfam) kind = (c.metric == M_ADTW && c.p.p < 0) ? TK_NONE : TK_SQUARE;
+  // adtw with a negative penalty (AmercingDtwMetric accepts any float, EL:3349): the row minima are no longer monotone,
+  // so a pair whose final distance is below the threshold can still be abandoned by the reference's eadistance (a row
+  // minimum > t * t, EL:3390-3396).  It is then replayed like the non-DTW metrics: row-minimum maxima M from the
+  // row-ordered engines, rejected iff M > t * t.
+  const bool adtw_neg = c.metric == M_ADTW && c.p.p < 0;
+  if (dtwfam) kind = TK_SQUARE;
   else if (c.metric == M_LCSS || c.metric == M_WLCSS) { kind = TK_LCSS; scale = (double)std::min(c.Tx, c.Ty); }
   else if (c.metric == M_EDR) { kind = TK_SCALE; scale = (double)std::max(c.Tx, c.Ty); }
   else kind = TK_IDENT;
@@ -401,7 +406,7 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
   C = std::min<long long>(C, ((ny + 31) / 32) * 32);
   if (ws.alloc(&tau, (size_t)nq) || ws.alloc(&thr, (size_t)nq) || ws.alloc(&hval, (size_t)nq * k) ||
       ws.alloc(&hidx, (size_t)nq * k) || ws.alloc(&hn, (size_t)nq) || ws.alloc(&dbuf, (size_t)nq * C)) return 1;
-  if (!dtwfam && ws.alloc(&mbuf, (size_t)nq * C)) return 1;
+  if ((!dtwfam || adtw_neg) && ws.alloc(&mbuf, (size_t)nq * C)) return 1;
   if (io.lower_bound && ws.alloc(&lbuf, (size_t)nq * C)) return 1;
   // ---- optional on-device lower-bound cascade (dtw, equal lengths) ----
   const bool cascade = io.use_device_lb && c.metric == M_DTW && c.ptx == c.pty && c.ptx >= 2 && !c.degenerate &&

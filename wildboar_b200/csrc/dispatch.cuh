@@ -19,6 +19,15 @@ inline bool has_fp32_variant(int metric) { return !(metric == M_LCSS || metric =
 // Calls f(policy) with the policy object for `metric`; returns false for an unknown id.
 template <class Fn>
 inline bool with_policy(int metric, const wb_params& p, const Tables& t, Fn&& f) {
+  if (p.precision == 2) {
+    // optional fused-multiply-add mode (DTW family only: the other recurrences contain no multiplication)
+    switch (metric) {
+      case M_DTW: case M_DDTW: { DtwPolicy<false, false, double, true> m; m.w = nullptr; m.p = 0; f(m); return true; }
+      case M_WDTW: case M_WDDTW: { DtwPolicy<true, false, double, true> m; m.w = t.weights; m.p = 0; f(m); return true; }
+      case M_ADTW: { DtwPolicy<false, true, double, true> m; m.w = nullptr; m.p = p.p; f(m); return true; }
+      default: break;
+    }
+  }
   switch (metric) {
     case M_DTW: case M_DDTW: { DtwPolicy<false, false> m; m.w = nullptr; m.p = 0; f(m); return true; }
     case M_WDTW: case M_WDDTW: { DtwPolicy<true, false> m; m.w = t.weights; m.p = 0; f(m); return true; }

@@ -39,7 +39,8 @@ struct KArgsT {
   long long nyb;      // ceil(ny / 32)
   int mode;
   long long row0;     // PM_SELF: global index of local x row 0 (row-sharded self join)
-  int mirror;         // PM_SELF: also write out[j][i] (single-device full matrix)
+  int mirror;         // PM_SELF: also write element (j, i) of the full n x n matrix that `out` is a row block of (`out` = row
+                      //   `row0` of it, ld = n): out[(j - row0) * ld + (i + row0)]  (single-device self join)
   const int2* list;   // PM_LIST: pairs to evaluate, sorted by (i, j)
   const int* list_len;  // PM_LIST: number of pairs (device resident: no host round trip)
   F* gring;           // strip engine, GRING variant: boundary buffers in global memory, [warp][slot][lane]
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(NT, MINB) k_strip(KArgsT<typename M::real> a, 
       double* const po = result_ptr(a, t, lane, i, j);
       const double r = combine_dims(a, po, d);
       __stcs(po, r);
-      if (a.mode == PM_SELF && a.mirror) __stcs(&a.out[j * a.ld + i], r);
+      if (a.mode == PM_SELF && a.mirror) __stcs(&a.out[(j - a.row0) * a.ld + (i + a.row0)], r);
     }
     __syncwarp();
   }
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(NT) k_rowscan(KArgsT<typename M::real> a, M m)
       *po = r;
       if (a.mode != PM_PAIRED && a.mode != PM_LISTP) {
         if (a.out_m) a.out_m[i * a.ld + j] = (double)mmax;
-        if (a.mode == PM_SELF && a.mirror) a.out[j * a.ld + i] = r;
+        if (a.mode == PM_SELF && a.mirror) a.out[(j - a.row0) * a.ld + (i + a.row0)] = r;
       } else if (a.mode == PM_LISTP && a.out_m) {
         a.out_m[t * 32 + lane] = (double)mmax;  // one entry per list element, like the distances
       }
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(NT) k_band(KArgsT<typename M::real> a, M m) {
       *po = r;
       if (a.mode != PM_PAIRED && a.mode != PM_LISTP) {
         if (a.out_m) a.out_m[i * a.ld + j] = (double)mmax;
-        if (a.mode == PM_SELF && a.mirror) a.out[j * a.ld + i] = r;
+        if (a.mode == PM_SELF && a.mirror) a.out[(j - a.row0) * a.ld + (i + a.row0)] = r;
       } else if (a.mode == PM_LISTP && a.out_m) {
         a.out_m[t * 32 + lane] = (double)mmax;
       }

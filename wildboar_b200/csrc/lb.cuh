@@ -86,6 +86,25 @@ __global__ void __launch_bounds__(kLbNT) k_lb_keogh_matrix(LbMatArgs a) {
   }
 }
 
+// dtw_lb_keogh (distance/dtw.py:193-243 -> _dtw_lb_keogh EL:1095-1115 -> cumulative_bound EL:228-260 with mean 0 / std 1
+// and no best-so-far): cb[i][k] = squared excess of x[i][k] over [lower[i][k], upper[i][k]], min_dist[i] = sqrt of their
+// sum in time order.  One warp per series: the lanes compute the terms (coalesced), lane 0 adds them up sequentially.
+__global__ void __launch_bounds__(128) k_lb_keogh_terms(const double* __restrict__ x, const double* __restrict__ lo,
+                                                        const double* __restrict__ hi, long long n, int T,
+                                                        double* __restrict__ min_dist, double* __restrict__ cb) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const long long base = i * T;
+  for (int k = lane; k < T; k += 32) cb[base + k] = lb_excess_sq(x[base + k], lo[base + k], hi[base + k]);
+  __syncwarp();
+  if (lane == 0) {
+    double s = 0.0;
+    for (int k = 0; k < T; ++k) s += cb[base + k];
+    min_dist[i] = sqrt(s);
+  }
+}
+
 // DtwKimLowerBound.transform (LB:241-311): sum of squared terms over the first / last three points
 // (no sqrt in the reference).  q = queries (rows of the result), x = fitted samples (columns).
 __device__ __forceinline__ double kim_d(double a, double b) { const double v = a - b; return v * v; }

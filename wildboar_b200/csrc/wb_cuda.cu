@@ -11,6 +11,7 @@
 #include <cstring>
 #include <deque>
 #include <map>
+#include <mutex>
 #include <limits>
 #include <string>
 #include <thread>
@@ -103,6 +104,111 @@ static int device_info(DeviceInfo* di) {
     return 1;
   }
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Persistent per-device execution contexts.  A host call used to create two streams and half a dozen
+// events and to query the device attributes every time (~0.2 ms: more than the kernel of a 200 x 200
+// call).  Contexts are leased from a per-device free list instead (one lease per call and device, so the
+// library stays re-entrant: concurrent calls get different contexts) and live until the process ends.
+// ------------------------------------------------------------------------------------------
+struct DevCtx {
+  int dev = -1;
+  DeviceInfo di{};
+  cudaStream_t st = nullptr, cst = nullptr;  // compute / copy-back streams
+  cudaEvent_t done[2]{}, drained[2]{}, k0[2]{}, k1[2]{};  // slab pipeline (device_worker)
+};
+static std::mutex g_ctx_mu;
+static std::vector<DevCtx*> g_ctx_free[64];
+
+static DevCtx* ctx_acquire(int dev) {
+  if (cudaSetDevice(dev) != cudaSuccess) { set_err("cudaSetDevice failed"); cudaGetLastError(); return nullptr; }
+  if (dev >= 0 && dev < 64) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    if (!g_ctx_free[dev].empty()) { DevCtx* c = g_ctx_free[dev].back(); g_ctx_free[dev].pop_back(); return c; }
+  }
+  DevCtx* c = new DevCtx;
+  c->dev = dev;
+  if (device_info(&c->di)) { delete c; return nullptr; }
+  bool ok = cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->cst, cudaStreamNonBlocking) == cudaSuccess;
+  for (int b = 0; b < 2 && ok; ++b)
+    ok = cudaEventCreateWithFlags(&c->done[b], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->drained[b], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreate(&c->k0[b]) == cudaSuccess && cudaEventCreate(&c->k1[b]) == cudaSuccess;
+  if (!ok) { set_err("could not create the per-device streams / events"); cudaGetLastError(); delete c; return nullptr; }
+  return c;
+}
+static void ctx_release(DevCtx* c) {
+  if (!c) return;
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  if (c->dev >= 0 && c->dev < 64) g_ctx_free[c->dev].push_back(c);
+}
+struct CtxLease {
+  DevCtx* c;
+  explicit CtxLease(int dev) : c(ctx_acquire(dev)) {}
+  ~CtxLease() { ctx_release(c); }
+  CtxLease(const CtxLease&) = delete;
+  CtxLease& operator=(const CtxLease&) = delete;
+};
+
+// ------------------------------------------------------------------------------------------
+// Pinned host memory for results (wb_cuda_host_alloc / wb_cuda_host_free, include/wb_cuda.h).  A device-to-host
+// copy into pageable memory is staged by the driver through its own bounce buffers (~10 GB/s and
+// synchronous); into page-locked memory it is one DMA at PCIe speed and truly asynchronous.  Page-locking is
+// expensive (~0.3 ms per MB), so released blocks are kept in a pool (bounded by WILDBOAR_CUDA_PINNED_POOL_MB,
+// default 4096) and handed out again to later calls of similar size.
+// ------------------------------------------------------------------------------------------
+static std::mutex g_pin_mu;
+static std::map<void*, size_t> g_pin_live;         // blocks handed out: capacity
+static std::multimap<size_t, void*> g_pin_free;    // pooled blocks by capacity
+static size_t g_pin_pooled = 0;
+static size_t pin_pool_cap() {
+  static size_t cap = [] {
+    const char* e = getenv("WILDBOAR_CUDA_PINNED_POOL_MB");
+    const long long mb = e ? atoll(e) : 4096;
+    return (size_t)std::max<long long>(mb, 0) << 20;
+  }();
+  return cap;
+}
+static void* pinned_alloc(size_t bytes) {
+  if (bytes == 0) bytes = 1;
+  const size_t cap = (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);  // 2 MB granules
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    auto it = g_pin_free.lower_bound(cap);
+    if (it != g_pin_free.end() && it->first <= cap + cap / 4 + ((size_t)8 << 20)) {
+      void* p = it->second;
+      g_pin_live[p] = it->first;
+      g_pin_pooled -= it->first;
+      g_pin_free.erase(it);
+      return p;
+    }
+  }
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, cap, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  g_pin_live[p] = cap;
+  return p;
+}
+static void pinned_free(void* p) {
+  if (!p) return;
+  size_t cap = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    auto it = g_pin_live.find(p);
+    if (it == g_pin_live.end()) return;  // not ours
+    cap = it->second;
+    g_pin_live.erase(it);
+    if (g_pin_pooled + cap <= pin_pool_cap()) { g_pin_free.emplace(cap, p); g_pin_pooled += cap; return; }
+  }
+  cudaFreeHost(p);
+}
+// page-locked (cudaHostAlloc / cudaHostRegister) host memory?
+static bool is_pinned_host(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
 }
 
 // DP cells the reference evaluates per pair: sum_i (j_stop(i) - j_start(i)).
@@ -520,6 +626,7 @@ struct HostJob {
   // dimensions of one sample; combine 0 = "mean" (one matrix), 1 = "full" (n_dims matrices)  (DI:1289-1297)
   int64_t nd, xds, yds; int combine;
   const wb_fitted* fit;  // kinds 0 / 3: the second operand is already resident on the devices
+  int* self_mirrored;    // kind 1, in/out: non-null = the worker MAY mirror the lower triangle on the device; set to 1 when it did
 };
 
 static int h2d_rows(double* dst, const double* src, int64_t rows, int64_t T, int64_t stride, cudaStream_t st) {
@@ -541,12 +648,11 @@ struct Timer {
 
 // rows [lo, hi) of the job on device `dev`
 static int device_worker(const HostJob& J, int dev, int64_t lo, int64_t hi, wb_stats* st_out) {
-  WB_CK(cudaSetDevice(dev));
-  DeviceInfo di;
-  if (device_info(&di)) return 1;
-  cudaStream_t st, cst;
-  WB_CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  WB_CK(cudaStreamCreateWithFlags(&cst, cudaStreamNonBlocking));
+  CtxLease lease(dev);  // persistent streams / events of this device (one lease per call: re-entrant)
+  if (!lease.c) return 1;
+  DevCtx& cx = *lease.c;
+  const DeviceInfo di = cx.di;
+  cudaStream_t st = cx.st, cst = cx.cst;
   int rc = 0;
   wb_stats stats;
   memset(&stats, 0, sizeof stats);
@@ -641,43 +747,85 @@ static int device_worker(const HostJob& J, int dev, int64_t lo, int64_t hi, wb_s
       }
       // pairwise / self: chunk the row block so result slabs stream back while the next chunk computes
       const int64_t ncols = c.ny;
-      const size_t slab_budget = (size_t)48 << 20;  // small slabs: the un-overlapped tail copy stays short
+      size_t slab_budget = (size_t)48 << 20;  // small slabs: the un-overlapped tail copy stays short
+      if (const char* e = getenv("WILDBOAR_CUDA_SLAB_KB")) {  // test knob: forces many slabs on small inputs
+        const long long v = atoll(e);
+        if (v >= 1) slab_budget = (size_t)v << 10;
+      }
       int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(rows, (int64_t)(slab_budget / (sizeof(double) * std::max<int64_t>(ncols, 1)))));
       const int64_t nchunks = (rows + chunk - 1) / chunk;
       const int64_t nunits = nchunks * nmat;  // streaming unit u = (matrix u / nchunks, row chunk u % nchunks)
+      // page-locked result (wb_cuda_host_alloc, or registered by the caller): the slab copies are asynchronous DMAs and
+      // the whole pipeline is ordered by events, the host only enqueues; pageable: the copy blocks the host anyway
+      const bool out_pinned = is_pinned_host(J.out);
+      // Self join on ONE device: the lower triangle is written by the kernel itself into a device-resident n x n matrix
+      // (CD:1240-1246 copies it from the upper one; the values are the same doubles), so no host-side transpose pass is
+      // needed.  Row chunk u is final once the kernels of chunks 0..u have run (the mirrored entries of row j come from
+      // rows i < j), so the chunks still stream back in order while later chunks compute.
+      bool full_self = false;
+      if (J.kind == 1 && J.self_mirrored && lo == 0 && hi == J.nx && nmat == 1) {
+        size_t fr = 0, tot = 0;
+        const size_t need = sizeof(double) * (size_t)rows * (size_t)ncols;
+        if (cudaMemGetInfo(&fr, &tot) == cudaSuccess && need <= fr / 2) full_self = true;
+        cudaGetLastError();
+      }
       double* dbuf[2] = {nullptr, nullptr};
-      if ((rc = ws.alloc(&dbuf[0], (size_t)chunk * ncols))) break;
-      if (nunits > 1 && (rc = ws.alloc(&dbuf[1], (size_t)chunk * ncols))) break;
-      cudaEvent_t done[2], k0[2], k1[2];
-      for (int b = 0; b < 2; ++b) { cudaEventCreate(&done[b]); cudaEventCreate(&k0[b]); cudaEventCreate(&k1[b]); }
-      auto enqueue = [&](int64_t u) -> int {
+      if (full_self) {
+        if ((rc = ws.alloc(&dbuf[0], (size_t)rows * ncols))) break;
+        WB_CK(cudaMemsetAsync(dbuf[0], 0, sizeof(double) * (size_t)rows * ncols, st));  // zero diagonal
+        for (int64_t d = 0; d < nd; ++d) cs[(size_t)d].mirror = 1;
+        *J.self_mirrored = 1;
+      } else {
+        if (J.kind == 1 && J.self_mirrored) *J.self_mirrored = 0;
+        if ((rc = ws.alloc(&dbuf[0], (size_t)chunk * ncols))) break;
+        if (nunits > 1 && (rc = ws.alloc(&dbuf[1], (size_t)chunk * ncols))) break;
+      }
+      bool timed[2] = {false, false};
+      auto harvest = [&](int b) {  // kernel time of the unit that last used event pair b
+        if (!timed[b]) return;
+        float f = 0;
+        if (cudaEventSynchronize(cx.k1[b]) == cudaSuccess && cudaEventElapsedTime(&f, cx.k0[b], cx.k1[b]) == cudaSuccess) stats.kernel_ms += f;
+        timed[b] = false;
+      };
+      // software pipeline: the kernels of unit u+1 are enqueued BEFORE the copy of unit u is issued (a copy into
+      // pageable memory blocks the host until the slab has been staged; the device keeps computing meanwhile)
+      auto launch_unit = [&](int64_t u) -> int {
         const int b = (int)(u & 1);
         const int64_t mi = u / nchunks, ci = u % nchunks;
         const int64_t r0 = ci * chunk, nr = std::min(chunk, rows - r0);
-        if (J.kind == 1) WB_CK(cudaMemsetAsync(dbuf[b], 0, sizeof(double) * nr * ncols, st));
-        WB_CK(cudaEventRecord(k0[b], st));
+        double* const slab = full_self ? dbuf[0] + r0 * ncols : dbuf[b];
+        harvest(b);
+        // the copy of unit u-2 must have left the buffer before unit u overwrites it
+        if (!full_self && u >= 2) WB_CK(cudaStreamWaitEvent(st, cx.drained[b], 0));
+        if (J.kind == 1 && !full_self) WB_CK(cudaMemsetAsync(slab, 0, sizeof(double) * nr * ncols, st));
+        WB_CK(cudaEventRecord(cx.k0[b], st));
         for (int64_t d = mi * dpm; d < (mi + 1) * dpm; ++d)
-          if (launch_dp(ws, di, cs[(size_t)d], r0, nr, 0, ncols, dbuf[b], ncols, nullptr, nullptr, &stats)) return 1;
-        WB_CK(cudaEventRecord(k1[b], st));
-        WB_CK(cudaEventRecord(done[b], st));
+          if (launch_dp(ws, di, cs[(size_t)d], r0, nr, 0, ncols, slab, ncols, nullptr, nullptr, &stats)) return 1;
+        WB_CK(cudaEventRecord(cx.k1[b], st));
+        WB_CK(cudaEventRecord(cx.done[b], st));
+        timed[b] = true;
         return 0;
       };
-      if ((rc = enqueue(0))) break;
-      for (int64_t u = 0; u < nunits && !rc; ++u) {
+      auto copy_unit = [&](int64_t u) -> int {
         const int b = (int)(u & 1);
         const int64_t mi = u / nchunks, ci = u % nchunks;
         const int64_t r0 = ci * chunk, nr = std::min(chunk, rows - r0);
-        if (u + 1 < nunits) {
-          // buffer (u+1)&1 was drained by the copy of unit u-1 (synchronous for the host)
-          if ((rc = enqueue(u + 1))) break;
+        double* const slab = full_self ? dbuf[0] + r0 * ncols : dbuf[b];
+        WB_CK(cudaStreamWaitEvent(cst, cx.done[b], 0));
+        if (cudaMemcpyAsync(J.out + mi * J.nx * ncols + (lo + r0) * ncols, slab, sizeof(double) * nr * ncols, cudaMemcpyDeviceToHost, cst) != cudaSuccess) {
+          set_err("device-to-host copy of the result slab failed"); return 1;
         }
-        if (cudaStreamWaitEvent(cst, done[b], 0) != cudaSuccess) { set_err("cudaStreamWaitEvent failed"); rc = 1; break; }
-        if (cudaMemcpyAsync(J.out + mi * J.nx * ncols + (lo + r0) * ncols, dbuf[b], sizeof(double) * nr * ncols, cudaMemcpyDeviceToHost, cst) != cudaSuccess ||
-            cudaStreamSynchronize(cst) != cudaSuccess) { set_err("device-to-host copy of the result slab failed"); rc = 1; break; }
-        float f = 0;
-        if (cudaEventElapsedTime(&f, k0[b], k1[b]) == cudaSuccess) stats.kernel_ms += f;
+        WB_CK(cudaEventRecord(cx.drained[b], cst));
+        return 0;
+      };
+      if ((rc = launch_unit(0))) break;
+      for (int64_t u = 0; u < nunits && !rc; ++u) {
+        if (u + 1 < nunits && (rc = launch_unit(u + 1))) break;
+        rc = copy_unit(u);
       }
-      for (int b = 0; b < 2; ++b) { cudaEventDestroy(done[b]); cudaEventDestroy(k0[b]); cudaEventDestroy(k1[b]); }
+      (void)out_pinned;
+      if (!rc) { harvest(0); harvest(1); }
+      if (cudaStreamSynchronize(cst) != cudaSuccess && !rc) { set_err("device-to-host copy of the result slab failed"); rc = 1; }
       if (rc) break;
       WB_CK(cudaStreamSynchronize(st));
     } while (0);
@@ -685,8 +833,7 @@ static int device_worker(const HostJob& J, int dev, int64_t lo, int64_t hi, wb_s
     if (!rc) { cudaStreamSynchronize(st); stats.total_ms = total.ms(); }
   }
   cudaStreamSynchronize(st);
-  cudaStreamDestroy(st);
-  cudaStreamDestroy(cst);
+  cudaStreamSynchronize(cst);
   if (st_out) *st_out = stats;
   return rc;
 }
@@ -728,8 +875,11 @@ static int run_host_job(const HostJob& J, const int* devices, int n_devices, wb_
   std::vector<wb_stats> sts(G);
   std::vector<int> rcs(G, 0);
   std::vector<std::string> errs(G);
+  int mirrored = 0;
   if (G == 1) {
-    rcs[0] = device_worker(J, devs[0], off[0], off[1], &sts[0]);
+    HostJob J1 = J;
+    if (J.kind == 1) J1.self_mirrored = &mirrored;  // one device: the kernel writes the lower triangle as well
+    rcs[0] = device_worker(J1, devs[0], off[0], off[1], &sts[0]);
     errs[0] = g_err;
   } else {
     std::vector<std::thread> th;
@@ -738,16 +888,30 @@ static int run_host_job(const HostJob& J, const int* devices, int n_devices, wb_
     for (auto& t : th) t.join();
   }
   for (int b = 0; b < G; ++b) if (rcs[b]) { set_err(errs[b]); return rcs[b]; }
-  if (J.kind == 1) {
-    // lower triangle = copy of the upper one (CD:1240-1246), blocked for cache friendliness
+  if (J.kind == 1 && !mirrored) {
+    // lower triangle = copy of the upper one (CD:1240-1246): blocked transpose, destination row blocks spread over
+    // host threads (disjoint writes)
     const int64_t n = J.nx, B = 64;
     const int64_t nmat = (J.nd > 1 && J.combine == 1) ? J.nd : 1;
-    for (int64_t mi = 0; mi < nmat; ++mi) {
-      double* o = J.out + mi * n * n;
-      for (int64_t ib = 0; ib < n; ib += B)
-        for (int64_t jb = ib; jb < n; jb += B)
-          for (int64_t i = ib; i < std::min(ib + B, n); ++i)
-            for (int64_t j = std::max(jb, i + 1); j < std::min(jb + B, n); ++j) o[j * n + i] = o[i * n + j];
+    const int64_t nblk = (n + B - 1) / B;
+    const int nth = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::thread::hardware_concurrency(), (int64_t)16, n * n * nmat / (1 << 18)}));
+    auto mirror_blocks = [&](int t) {
+      for (int64_t mi = 0; mi < nmat; ++mi) {
+        double* o = J.out + mi * n * n;
+        // destination block row jb; block rows are dealt out round-robin (row jb costs jb + 1 blocks)
+        for (int64_t jbi = t; jbi < nblk; jbi += nth) {
+          const int64_t jb = jbi * B;
+          for (int64_t ib = 0; ib <= jb; ib += B)
+            for (int64_t i = ib; i < std::min(ib + B, n); ++i)
+              for (int64_t j = std::max(jb, i + 1); j < std::min(jb + B, n); ++j) o[j * n + i] = o[i * n + j];
+        }
+      }
+    };
+    if (nth == 1) mirror_blocks(0);
+    else {
+      std::vector<std::thread> th;
+      for (int t = 0; t < nth; ++t) th.emplace_back(mirror_blocks, t);
+      for (auto& t : th) t.join();
     }
   }
   if (stats) {
@@ -837,6 +1001,56 @@ static int run_lb(int op, const double* q, int64_t nq, int64_t qs, const double*
   }
   cudaStreamSynchronize(st);
   cudaStreamDestroy(st);
+  if (stats) *stats = local;
+  return rc;
+}
+
+// dtw_envelop / dtw_lb_keogh of wildboar.distance.dtw (dtw.py:155-243), batched over n series of one device call.
+// op 0: lower / upper envelopes (EL:1076-1092, half-width w); op 1: per-time-step LB_Keogh terms + their root sum.
+static int run_lb_series(int op, const double* x, int64_t n, int64_t T, int64_t xs, int64_t w, const double* lower,
+                         const double* upper, double* out_a, double* out_b, int device, wb_stats* stats) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { set_err("no CUDA device available: wildboar_b200 has no CPU fallback"); return 1; }
+  if (device < 0 || device >= ndev) { set_err("invalid device ordinal"); return 1; }
+  CtxLease lease(device);
+  if (!lease.c) return 1;
+  cudaStream_t st = lease.c->st;
+  wb_stats local; memset(&local, 0, sizeof local);
+  int rc = 0;
+  {
+    Workspace ws(st);
+    Timer total(st), kt(st);
+    total.start();
+    do {
+      double *dx = nullptr, *da = nullptr, *db = nullptr, *dlo = nullptr, *dhi = nullptr;
+      const size_t ne = (size_t)n * (size_t)T;
+      if ((rc = ws.alloc(&dx, ne)) || (rc = h2d_rows(dx, x, n, T, xs, st))) break;
+      if (op == 0) {
+        if ((rc = ws.alloc(&da, ne)) || (rc = ws.alloc(&db, ne))) break;
+        kt.start();
+        k_envelope_rows<<<(unsigned)std::min<size_t>((ne + 255) / 256, 4096), 256, 0, st>>>(dx, n, (int)T, (int)w, 1, nullptr, da, db);
+        kt.stop();
+        WB_CK(cudaGetLastError());
+        WB_CK(cudaMemcpyAsync(out_a, da, sizeof(double) * ne, cudaMemcpyDeviceToHost, st));
+        WB_CK(cudaMemcpyAsync(out_b, db, sizeof(double) * ne, cudaMemcpyDeviceToHost, st));
+      } else {
+        if ((rc = ws.alloc(&dlo, ne)) || (rc = ws.alloc(&dhi, ne)) || (rc = ws.alloc(&da, (size_t)n)) || (rc = ws.alloc(&db, ne))) break;
+        WB_CK(cudaMemcpyAsync(dlo, lower, sizeof(double) * ne, cudaMemcpyHostToDevice, st));
+        WB_CK(cudaMemcpyAsync(dhi, upper, sizeof(double) * ne, cudaMemcpyHostToDevice, st));
+        kt.start();
+        k_lb_keogh_terms<<<(unsigned)((n * 32 + 127) / 128), 128, 0, st>>>(dx, dlo, dhi, n, (int)T, da, db);
+        kt.stop();
+        WB_CK(cudaGetLastError());
+        WB_CK(cudaMemcpyAsync(out_a, da, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        WB_CK(cudaMemcpyAsync(out_b, db, sizeof(double) * ne, cudaMemcpyDeviceToHost, st));
+      }
+      local.launches = 1;
+      WB_CK(cudaStreamSynchronize(st));
+    } while (0);
+    total.stop();
+    if (!rc) { cudaStreamSynchronize(st); local.total_ms = total.ms(); local.kernel_ms = kt.ms(); local.pairs = n; local.cells = n * T; }
+  }
+  cudaStreamSynchronize(st);
   if (stats) *stats = local;
   return rc;
 }
@@ -1875,7 +2089,7 @@ static int check_common(int metric, const wb_params* p, const void* x, int64_t n
   if (n < 1 || T < 1) { set_err("empty input"); return 1; }
   if (T > (1 << 24)) { set_err("series too long"); return 1; }
   if (!(p->r >= 0.0 && p->r <= 1.0)) { set_err("r must be in [0, 1]"); return 1; }
-  if (p->precision != 0 && p->precision != 1) { set_err("precision must be 0 (fp64, bit-exact) or 1 (fp32)"); return 1; }
+  if (p->precision < 0 || p->precision > 2) { set_err("precision must be 0 (fp64, bit-exact), 1 (fp32) or 2 (fp64 with fused multiply-add)"); return 1; }
   return 0;
 }
 
@@ -2194,6 +2408,26 @@ int wb_cuda_lb_kim(const double* q, int64_t nq, int64_t q_stride, const double* 
   if (nq < 1 || nx < 1 || T < 1) { set_err("empty input"); return 1; }
   return run_lb(1, q, nq, q_stride, x, nx, x_stride, T, 0.0, 0, out, device, stats);
 }
+
+int wb_cuda_dtw_envelope(const double* x, int64_t n, int64_t T, int64_t x_stride, int64_t w, double* lower, double* upper,
+                         int device, wb_stats* stats) {
+  if (!x || !lower || !upper) { set_err("null argument"); return 1; }
+  if (n < 1 || T < 1) { set_err("empty input"); return 1; }
+  if (T > (1 << 24)) { set_err("series too long"); return 1; }
+  if (w < 0 || w >= T) { set_err("invalid r"); return 1; }  // EL:1077-1078
+  return run_lb_series(0, x, n, T, x_stride, w, nullptr, nullptr, lower, upper, device, stats);
+}
+
+int wb_cuda_dtw_lb_keogh_terms(const double* x, const double* lower, const double* upper, int64_t n, int64_t T,
+                               double* min_dist, double* cb, int device, wb_stats* stats) {
+  if (!x || !lower || !upper || !min_dist || !cb) { set_err("null argument"); return 1; }
+  if (n < 1 || T < 1) { set_err("empty input"); return 1; }
+  if (T > (1 << 24)) { set_err("series too long"); return 1; }
+  return run_lb_series(1, x, n, T, T, 0, lower, upper, min_dist, cb, device, stats);
+}
+
+void* wb_cuda_host_alloc(size_t bytes) { return pinned_alloc(bytes); }
+void wb_cuda_host_free(void* p) { pinned_free(p); }
 
 int wb_cuda_fp64_peak(int mix, double* inst_per_s, double* sm_mhz_est) {
   DeviceInfo di;

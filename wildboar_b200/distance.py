@@ -303,6 +303,16 @@ def _dim_slices(x_, dim, n_dims):
     raise ValueError("The parameter dim must be 0 <= dim < n_dims")
 
 
+def _nd_call(call, how, n_out, n_dims):
+    """Multivariate call with the dimensions combined on the device -- except in the one corner where the device's
+    strictly sequential sum over the dimensions is not numpy's order: a SINGLE output element with 8 or more dimensions
+    makes ``np.mean(list_of_matrices, axis=0)`` (_distance.py:1250-1253, 1289-1292) a contiguous 1-D reduction, which
+    numpy sums pairwise (8 accumulators).  There the per-dimension values are fetched and numpy does the mean."""
+    if how == "mean" and n_out == 1 and n_dims >= 8:
+        return np.mean(call("full"), axis=0)
+    return call(how)
+
+
 def _combine(distances, how):
     if how == "mean":
         return np.mean(distances, axis=0)
@@ -335,7 +345,7 @@ def pairwise_distance(x, y=None, *, dim="mean", metric="euclidean", metric_param
             dim = 0
         dims, how = _dim_slices(x_, dim, n_dims)
         if how is not None and n_dims > 1:  # all dimensions in ONE library call (combined on the device)
-            return _shim.pairwise_nd(m.metric_id, params, x_, None, how)
+            return _nd_call(lambda h: _shim.pairwise_nd(m.metric_id, params, x_, None, h), how, x_.shape[0] ** 2, n_dims)
         return _combine([_shim.pairwise(m.metric_id, params, x_[:, d, :], None) for d in dims], how)
     x = check_array(x, allow_3d=True, ensure_2d=False, dtype=np.double)
     y = check_array(y, allow_3d=True, ensure_2d=False, dtype=np.double)
@@ -350,7 +360,7 @@ def pairwise_distance(x, y=None, *, dim="mean", metric="euclidean", metric_param
         dim = 0
     dims, how = _dim_slices(x_, dim, n_dims)
     if how is not None and n_dims > 1:
-        distances = _shim.pairwise_nd(m.metric_id, params, x_, y_, how)
+        distances = _nd_call(lambda h: _shim.pairwise_nd(m.metric_id, params, x_, y_, h), how, x_.shape[0] * y_.shape[0], n_dims)
     else:
         distances = _combine([_shim.pairwise(m.metric_id, params, x_[:, d, :], y_[:, d, :]) for d in dims], how)
     return _format_return(distances, y.ndim, x.ndim)
@@ -382,7 +392,7 @@ def paired_distance(x, y, *, dim="mean", metric="euclidean", metric_params=None,
     y_ = _check_ts_array(y)
     dims, how = _dim_slices(x_, dim, n_dims)
     if how is not None and n_dims > 1:
-        distances = _shim.paired_nd(m.metric_id, params, x_, y_, how)
+        distances = _nd_call(lambda h: _shim.paired_nd(m.metric_id, params, x_, y_, h), how, x_.shape[0], n_dims)
     else:
         distances = _combine([_shim.paired(m.metric_id, params, x_[:, d, :], y_[:, d, :]) for d in dims], how)
     return _format_return(distances, y.ndim, x.ndim)

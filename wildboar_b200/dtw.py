@@ -22,7 +22,7 @@ from .distance import DtwMetric, WeightedDtwMetric, _check_scalar, check_array, 
 
 __all__ = [
     "dtw_alignment", "wdtw_alignment", "dtw_distance", "wdtw_distance", "ddtw_distance", "wddtw_distance",
-    "dtw_mapping", "jeong_weight", "dtw_average", "dtw_paths", "dtw_average_many",
+    "dtw_mapping", "jeong_weight", "dtw_average", "dtw_paths", "dtw_average_many", "dtw_envelop", "dtw_lb_keogh",
 ]
 
 
@@ -55,6 +55,42 @@ def wdtw_distance(x, y, *, r=1.0, g=0.05):
 def wddtw_distance(x, y, *, r=1.0, g=0.05):
     """dtw.py:126-152."""
     return pairwise_distance(_series(x, "x"), _series(y, "y"), metric="wddtw", metric_params={"r": r, "g": g})
+
+
+def dtw_envelop(x, *, r=1.0):
+    """Envelope for LB_Keogh: ``lower[k], upper[k]`` = min / max of ``x[k-w .. k+w]`` (distance/dtw.py:155-190;
+    ``w = max(floor(T r), 1)``, ``T - 1`` when that equals ``T``; ``_dtw_envelop`` EL:1076-1092 on the device kernel that
+    also feeds the LB transformers)."""
+    x = _series(x, "x")
+    warp_size = _compute_warp_size(x.shape[0], r)
+    if warp_size == x.shape[0]:
+        warp_size -= 1
+    if not 0 <= warp_size < x.shape[0]:
+        raise ValueError("invalid r")
+    lower, upper = _shim.dtw_envelope(x.reshape(1, -1), warp_size)
+    return lower[0], upper[0]
+
+
+def dtw_lb_keogh(x, y=None, *, lower=None, upper=None, r=1.0):
+    """LB_Keogh of x against the envelope of y (or a given envelope): ``(min_dist, per-time-step terms)``
+    (distance/dtw.py:193-243 -> ``_dtw_lb_keogh`` EL:1095-1115: squared excess over the envelope per step, summed in
+    time order, square root of the sum).  If y is given, lower and upper are ignored; otherwise both are required and r
+    is ignored."""
+    x = _series(x, "x")
+    if y is not None:
+        y = _series(y, "y")
+        if y.shape[0] != x.shape[0]:
+            raise ValueError("x (%d) and y (%d) must have the same number of timesteps" % (x.shape[0], y.shape[0]))
+        lower, upper = dtw_envelop(y, r=r)
+    elif lower is None or upper is None:
+        raise ValueError("both y, lower and upper can't be None")
+    lower = _series(lower, "lower")
+    upper = _series(upper, "upper")
+    if lower.shape[0] != upper.shape[0] or lower.shape[0] != x.shape[0]:
+        raise ValueError("lower (%d), upper (%d) and x (%d) have the same number of timesteps"
+                         % (lower.shape[0], upper.shape[0], x.shape[0]))
+    md, cb = _shim.dtw_lb_keogh_terms(x.reshape(1, -1), lower.reshape(1, -1), upper.reshape(1, -1))
+    return float(md[0]), cb[0]
 
 
 def jeong_weight(n, g=0.05):

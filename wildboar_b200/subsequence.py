@@ -398,9 +398,17 @@ def distance_profile(y, x, *, dilation=1, padding=0, dim=0, metric="dtw", metric
     metric, scaled = _check_subsequence_metric(metric, scale)
     m = _make_metric(metric, metric_params)
     if dilation != 1 or padding != 0:
-        return np.squeeze(_dilated_profile(np.ascontiguousarray(y_[:, 0, :]), np.ascontiguousarray(x_[:, int(dim), :]), metric, m,
+        # _DilatedDistanceProfile reads dimension `dim` of BOTH operands (&S[i, dim, 0], &X[i, dim, 0], CD:1778-1796); with a
+        # univariate y and dim > 0 the reference reads past the end of y, which is refused here.  Its metric check on this
+        # branch is check_metric (the full registry): every elastic metric of that registry is accepted except
+        # wlcss / scaled_wlcss, which the device scan does not carry (ValueError from _check_subsequence_metric above).
+        if dim >= y_.shape[1]:
+            raise ValueError(f"dim ({dim}) must be < the number of dimensions of y ({y_.shape[1]}) when dilation != 1 or padding != 0")
+        return np.squeeze(_dilated_profile(np.ascontiguousarray(y_[:, int(dim), :]), np.ascontiguousarray(x_[:, int(dim), :]), metric, m,
                                            scaled, int(dilation), int(padding)))
-    dp = _profile(np.ascontiguousarray(y_[:, 0, :]), x_[:, int(dim), :], metric, m, scaled, np.inf, _view_mean_std)
+    # _DistanceProfile ignores `dim` and always reads dimension 0 of both operands (&self.y[i, 0, 0], &self.x[i, 0, 0],
+    # CD:1690-1699); reproduced, so a multivariate x with dim > 0 gives the reference's answer
+    dp = _profile(np.ascontiguousarray(y_[:, 0, :]), x_[:, 0, :], metric, m, scaled, np.inf, _view_mean_std)
     return np.squeeze(dp)
 
 
