@@ -50,7 +50,8 @@ typedef struct wb_params {
   double epsilon;   /* lcss/wlcss/edr: threshold; NaN = edr default max(std)/4     */
   double penalty;   /* twe                                                         */
   double stiffness; /* twe                                                         */
-  int32_t engine;   /* 0 auto, 1 force row-scan engine, 2 force strip engine, 3 force band-register engine */
+  int32_t engine;   /* 0 auto, 1 force row-scan engine, 2 force strip engine, 3 force band-register engine,
+                       4 force the cooperative (lanes-per-pair) engine */
   int32_t precision; /* 0: fp64, bit-equal to the reference (default); 1: fp32 arithmetic (<= 1e-4 relative;
                         lcss / wlcss / edr always run in fp64); 2: fp64 with the DTW-family cost folded into the minimum
                         by ONE fused multiply-add (<= 1e-12 relative, not bit-equal: the reference build has no FMA;
@@ -64,11 +65,12 @@ typedef struct wb_stats {
   int64_t cells;        /* DP cells evaluated (reference cell count)          */
   int64_t pairs;        /* pairs evaluated                                               */
   int32_t launches;     /* kernels launched by this call                                 */
-  int32_t engine;       /* engine used for the DP (1 row-scan, 2 strip, 3 band-register) */
+  int32_t engine;       /* engine used for the DP (1 row-scan, 2 strip, 3 band-register, 4 cooperative) */
   int64_t lb_kim_pruned;   /* argmin cascade: pairs pruned by LB_Kim                     */
   int64_t lb_keogh_pruned; /* argmin cascade: pairs pruned by LB_Keogh (either direction)  */
-  int32_t strip_w;      /* strip engine, last launch: strip width W (columns held in registers) */
-  int32_t strip_nr;     /* rows per fast-path iteration (in-thread wavefront depth)            */
+  int32_t strip_w;      /* strip engine, last launch: strip width W (columns held in registers); cooperative engine:
+                           band coordinates per lane                                                           */
+  int32_t strip_nr;     /* rows per fast-path iteration (in-thread wavefront depth); cooperative engine: lanes per pair */
   int32_t strip_warps;  /* warps per CTA                                                       */
   int32_t strip_gring;  /* 1: boundary buffers in global memory (L2), 0: shared memory          */
 } wb_stats;

@@ -18,7 +18,7 @@ class WbParams(C.Structure):
 def build(force=False):
     srcs = [os.path.join(_HERE, "hostsim.cpp")] + [
         os.path.join(_ROOT, "wildboar_b200", "csrc", f)
-        for f in ("metrics.cuh", "engine_strip.cuh", "engine_rowscan.cuh", "engine_band.cuh", "dispatch.cuh", "prep.hpp")]
+        for f in ("metrics.cuh", "engine_strip.cuh", "engine_rowscan.cuh", "engine_band.cuh", "engine_coop.cuh", "dispatch.cuh", "prep.hpp")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared",
                                "-Wno-unknown-pragmas", "-o", _SO, srcs[0]])
@@ -47,6 +47,19 @@ def pair(engine, W, metric_id, params, x, y, ea=0, min_dist_raw=float("inf"), ns
     rc = lib().hostsim_pair(engine, W, metric_id, C.byref(params), x.ctypes.data_as(dp), len(x), y.ctypes.data_as(dp),
                             len(y), ea, min_dist_raw, ns_extra, bs, C.byref(out), C.byref(mm))
     return rc, out.value, mm.value
+
+
+def coop_pair(W, G, metric_id, params, x, y):
+    """(rc, distance) of one pair through the cooperative engine, G lanes emulated in lockstep (rc 1: geometry not
+    covered by this (W, G))."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    out = C.c_double(0)
+    dp = C.POINTER(C.c_double)
+    f = lib().hostsim_coop_pair
+    f.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(WbParams), dp, C.c_int64, dp, C.c_int64, dp]
+    rc = f(W, G, metric_id, C.byref(params), x.ctypes.data_as(dp), len(x), y.ctypes.data_as(dp), len(y), C.byref(out))
+    return rc, out.value
 
 
 def inc_window_stats(x, m):

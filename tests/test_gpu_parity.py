@@ -446,3 +446,45 @@ def test_dim_mean_single_output_follows_numpy_pairwise_summation(W, oracle, n_di
     per_dim = [oracle.pairwise("dtw", np.ascontiguousarray(x3[:, d]), y[:, d], r=0.2, n_jobs=0) for d in range(n_dims)]
     got = W.pairwise_distance(x3, y, dim="mean", metric="dtw", metric_params={"r": 0.2})
     assert np.array_equal(np.asarray(got).reshape(3, 1), np.mean(per_dim, axis=0))
+
+
+# ---- round 2: cooperative engine (a group of lanes per pair, band row in registers, warp shuffles) ----
+COOP_SHAPES = [(37, 53, 150, 150, 0.1), (20, 70, 140, 140, 1.0), (9, 40, 512, 512, 0.1), (30, 45, 50, 77, 0.2), (12, 33, 90, 61, 0.3),
+               (5, 11, 600, 600, 0.02)]
+
+
+@pytest.mark.parametrize("metric", METRICS)
+def test_coop_engine_matches_oracle(W, oracle, metric, monkeypatch):
+    """WILDBOAR_CUDA_ENGINE=coop forces k_coop for every metric: pairwise (equal and unequal lengths, W = 8 and W = 13
+    layouts, 4 to 32 lanes per pair), paired and the self join must equal the oracle bit for bit."""
+    monkeypatch.setenv("WILDBOAR_CUDA_ENGINE", "coop")
+    for (nx, ny, Tx, Ty, r) in COOP_SHAPES:
+        if metric in ("wddtw",) and Tx > Ty:
+            continue
+        x, y = random_walks(nx, Tx, 91), random_walks(ny, Ty, 92)
+        got = W.pairwise_distance(x, y, metric=metric, metric_params={"r": r})
+        assert W.last_stats()["engine"] == 4, W.last_stats()
+        _eq(got, oracle.pairwise(metric, x, y, r=r, n_jobs=0), f"coop {metric} {Tx}x{Ty} r={r}")
+    X = random_walks(75, 150, 93)
+    _eq(W.pairwise_distance(X, metric=metric, metric_params={"r": 0.1}), oracle.pairwise(metric, X, None, r=0.1, n_jobs=0), metric + " coop self")
+    assert W.last_stats()["engine"] == 4
+    _eq(W.paired_distance(X[:30], X[30:60], metric=metric, metric_params={"r": 0.1}),
+        oracle.paired(metric, X[:30], X[30:60], r=0.1, n_jobs=0), metric + " coop paired")
+    assert W.last_stats()["engine"] == 4
+
+
+def test_coop_engine_is_selected_for_small_problems_and_tall_bands(W, oracle):
+    """Automatic dispatch: cfg1 (200 x 200, too few pairs for a thread per pair) and cfg5's band (T = 4096, r = 0.05: per-pair
+    boundary buffers would spill out of L2) run on the cooperative engine; cfg3-like shapes stay on the strip engine."""
+    x, y = random_walks(200, 150, 1), random_walks(200, 150, 2)
+    _eq(W.pairwise_distance(x, y, metric="dtw", metric_params={"r": 0.1}), oracle.pairwise("dtw", x, y, r=0.1, n_jobs=0), "cfg1")
+    st = W.last_stats()
+    assert st["engine"] == 4 and st["strip_w"] == 8 and st["strip_nr"] == 4, st
+    x, y = random_walks(2000, 4096, 1)[:6], random_walks(2000, 4096, 2)[:40]
+    for metric in ("msm", "twe"):
+        _eq(W.pairwise_distance(x, y, metric=metric, metric_params={"r": 0.05}), oracle.pairwise(metric, x, y, r=0.05, n_jobs=0), "cfg5 " + metric)
+        st = W.last_stats()
+        assert st["engine"] == 4 and st["strip_w"] == 13 and st["strip_nr"] == 32, st
+    x, y = random_walks(10000, 512, 1)[:64], random_walks(10000, 512, 2)[:3000]
+    W.pairwise_distance(x, y, metric="dtw", metric_params={"r": 0.1})
+    assert W.last_stats()["engine"] == 2

@@ -284,3 +284,54 @@ def test_interleaved_engine_variants_match_plain(oracle, metric):
             assert rc4 == 0 and v4 == v1 and m4 == m1, (metric, T, r, HB)
             checked += 1
     assert checked > 20
+
+
+# ---- cooperative engine (engine_coop.cuh): a group of lanes per pair, emulated in lockstep on the host ----
+@pytest.mark.parametrize("metric", METRICS)
+def test_coop_engine_matches_oracle(oracle, metric):
+    """All 11 metrics x equal / unequal lengths x windows x (W, G) layouts, incl. the layouts the library ships (W = 8 and
+    W = 13): masked rows (start-up, drain, band outside the matrix, row 0 / column 0 rules, MSM's stale left edge and extra
+    cell) and the unrolled fast blocks with rotating column registers must reproduce the oracle bit for bit."""
+    rng = np.random.default_rng(1000 + hash(metric) % 1000)
+    mid = oracle.METRIC_IDS[metric]
+    checked = 0
+    for trial in range(36):
+        mode = trial % 6
+        if mode == 0:
+            Tx = Ty = int(rng.integers(4, 140))
+        elif mode == 1:
+            Tx = int(rng.integers(30, 100)); Ty = Tx + int(rng.integers(-6, 7))
+        elif mode == 2:
+            Tx, Ty = int(rng.integers(5, 30)), int(rng.integers(40, 120))
+        elif mode == 3:
+            Tx, Ty = int(rng.integers(40, 120)), int(rng.integers(5, 30))
+        elif mode == 4:
+            Tx = Ty = int(rng.integers(300, 700))      # long interior: many fast blocks
+        else:
+            Tx = Ty = 150                               # cfg1's shape (r = 0.1: H = 29 -> W = 8, G = 4)
+        if metric == "wddtw" and Tx > Ty:
+            Tx, Ty = Ty, Tx
+        r = 0.1 if mode == 5 else float(rng.choice([0.02, 0.05, 0.1, 0.2, 0.3, 0.5, 1.0]))
+        if mode == 4:
+            r = float(rng.choice([0.02, 0.05, 0.1]))
+        x = np.cumsum(rng.standard_normal(Tx)); y = np.cumsum(rng.standard_normal(Ty))
+        ref = oracle.pairwise(metric, x, y.reshape(1, -1), r=r)[0, 0]
+        p = _params(oracle, metric, r=r)
+        for W, G in [(3, 32), (4, 8), (4, 32), (8, 4), (8, 16), (8, 32), (13, 32)]:
+            rc, v = sim.coop_pair(W, G, mid, p, x, y)
+            if rc == 1:
+                continue  # no exact tiling of this band with (W, G)
+            assert rc == 0 and v == ref, (metric, W, G, Tx, Ty, r, v, ref)
+            checked += 1
+    assert checked > 60
+
+
+def test_coop_engine_cfg5_band_shape(oracle):
+    """The long-series configuration the engine exists for: H = 407 band coordinates over 32 lanes (23 wide, 9 narrow)."""
+    rng = np.random.default_rng(77)
+    T = 4096
+    x = np.cumsum(rng.standard_normal(T)); y = np.cumsum(rng.standard_normal(T))
+    for metric in ("msm", "twe"):
+        ref = oracle.pairwise(metric, x, y.reshape(1, -1), r=0.05)[0, 0]
+        rc, v = sim.coop_pair(13, 32, oracle.METRIC_IDS[metric], _params(oracle, metric, r=0.05), x, y)
+        assert rc == 0 and v == ref, (metric, v, ref)

@@ -155,10 +155,10 @@ def last_stats():
 
 
 def apply_engine_override(params):
-    """WILDBOAR_CUDA_ENGINE=rowscan|strip|band forces one DP engine (testing / cross-checks); also
+    """WILDBOAR_CUDA_ENGINE=rowscan|strip|band|coop forces one DP engine (testing / cross-checks); also
     stamps the selected precision into the parameter block."""
     e = os.environ.get("WILDBOAR_CUDA_ENGINE", "").strip().lower()
-    params.engine = {"rowscan": 1, "strip": 2, "band": 3}.get(e, 0)
+    params.engine = {"rowscan": 1, "strip": 2, "band": 3, "coop": 4}.get(e, 0)
     params.precision = _PRECISIONS[get_precision()]
     return params
 

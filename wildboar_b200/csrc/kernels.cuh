@@ -4,6 +4,7 @@
 #include "engine_rowscan.cuh"
 #include "engine_strip.cuh"
 #include "engine_band.cuh"
+#include "engine_coop.cuh"
 
 namespace wb {
 
@@ -53,6 +54,7 @@ struct KArgsT {
   int acc;            // 1: out = out + d
   double div;         // != 0: out = (...) / div
   long long ys;       // elements between consecutive y series (Ty for dense rows; 1 = every sliding window of one long buffer)
+  long long npairs;   // cooperative engine: pairs of this launch (nx * ny, nx for PM_PAIRED, list length for PM_LISTP)
   int yil;            // 1: y is interleaved in groups of 32 series (k_interleave32): element t of series j sits at
                       //    ((j >> 5) * Ty + t) * 32 + (j & 31), so the 32 lanes of a warp task read consecutive addresses
                       //    (row-scan and band kernels; dense rows of many short series are uncoalesced otherwise)
@@ -234,6 +236,66 @@ __global__ void __launch_bounds__(NT) k_band(KArgsT<typename M::real> a, M m) {
       } else if (a.mode == PM_LISTP && a.out_m) {
         a.out_m[t * 32 + lane] = (double)mmax;
       }
+    }
+    __syncwarp();
+  }
+}
+
+// ---- cooperative engine: G lanes per pair, the band row in the lanes' registers, neighbours by warp shuffle ----
+template <class M, int W>
+struct CoopDevGroup {
+  using F = typename M::real;
+  CoopLane<M, W>& L;
+  const F* x; const F* y;
+  int G;
+  CoopTmp<M, W> tmp;
+  template <class Fn> __device__ __forceinline__ void each(Fn f) { f(L, x, y, tmp); }
+  __device__ __forceinline__ void xchg_left() { L.left_in = __shfl_up_sync(0xffffffffu, L.last_out, 1, G); }
+  __device__ __forceinline__ void xchg_up() { L.up_in = __shfl_down_sync(0xffffffffu, L.c0, 1, G); }
+};
+
+// G (power of two, <= 32) lanes cooperate on one pair; a warp task = 32 / G consecutive pairs (pair e = i * ny + j: the
+// groups of a warp share the x row).  All pairs of a launch share the geometry, so every group of every warp runs the same
+// step sequence (full-mask shuffles).
+template <class M, int W, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_coop(KArgsT<typename M::real> a, M m, int G, CoopLayout lay) {
+  using F = typename M::real;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (G - 1);
+  const int slot = lane / G;
+  const int PG = 32 / G;
+  const long long npairs = (a.mode == PM_LISTP) ? (long long)__ldg(a.list_len) : a.npairs;
+  const long long ntasks = (npairs + PG - 1) / PG;
+  for (;;) {
+    const long long t = next_task(a.counter, lane);
+    if (t >= ntasks) break;
+    long long e = t * PG + slot;
+    bool valid = e < npairs;
+    if (!valid) e = npairs - 1;
+    long long i, j;
+    if (a.mode == PM_LISTP) { const int2 p = a.list[e]; i = p.x; j = p.y; }
+    else if (a.mode == PM_PAIRED) { i = e; j = e; }
+    else { i = e / a.ny; j = e - i * a.ny; }
+    if (a.mode == PM_SELF && j <= i + a.row0) valid = false;
+    if (__ballot_sync(0xffffffffu, valid) == 0u) continue;
+    M mm = m;
+    PairCtx pc;
+    pc.sx = a.sx ? a.sx[i] : 0.0;
+    pc.sy = a.sy ? a.sy[j] : 0.0;
+    pc.sy2 = a.sy2 ? a.sy2[j] : 0.0;
+    mm.begin_pair(pc);
+    CoopLane<M, W> L;
+    const F* const xp = a.x + i * a.Tx;
+    const F* const yp = a.y + j * a.ys;
+    L.init(a.g, mm, lay, gl, xp, yp);
+    CoopDevGroup<M, W> grp{L, xp, yp, G, {}};
+    coop_run<M, W>(grp, a.g, mm, lay);
+    if (valid && L.holds_result(a.g)) {
+      const double d = (double)mm.finish(L.result(a.g), a.g);
+      double* const po = (a.mode == PM_PAIRED) ? &a.out[i] : (a.mode == PM_LISTP ? &a.out[e] : &a.out[i * a.ld + j]);
+      const double r = combine_dims(a, po, d);
+      __stcs(po, r);
+      if (a.mode == PM_SELF && a.mirror) __stcs(&a.out[(j - a.row0) * a.ld + (i + a.row0)], r);
     }
     __syncwarp();
   }

@@ -343,6 +343,36 @@ static int launch_strip(Workspace& ws, const KArgsT<typename M::real>& a, const 
   return launch_strip_cfg<M, 4, 256, 2, EA, 2, false>(ws, a, m, 8, sms, smem_cap, cfg);
 }
 
+// Cooperative engine (engine_coop.cuh, k_coop): lanes-per-pair G and cells-per-lane W for a geometry.  Two
+// instantiations: W = 8 (256 threads, two CTAs per SM) for bands up to 256 coordinates and W = 13 (384 threads, one CTA)
+// up to 416; G = the smallest power of two that holds the layout.  Returns false when no layout tiles the band exactly.
+template <class M>
+static bool coop_pick(const Geom& g, int* W, int* G, CoopLayout* lay) {
+  const int ws[2] = {8, 13};
+  for (int q = 0; q < 2; ++q) {
+    for (int gg = 2; gg <= 32; gg *= 2) {
+      if (coop_supported<M>(g, ws[q], gg) && coop_layout(g, ws[q], gg, lay)) { *W = ws[q]; *G = gg; return true; }
+    }
+  }
+  return false;
+}
+
+template <class M, int W, int NT, int MINB>
+static int launch_coop_cfg(Workspace& ws, KArgsT<typename M::real> a, const M& m, int G, const CoopLayout& lay, int sms, wb_stats* cfg) {
+  auto kern = k_coop<M, W, NT, MINB>;
+  int per_sm = 0;
+  WB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, 0));
+  if (per_sm < 1) { set_err("cooperative kernel does not fit on an SM"); return 1; }
+  const long long ntasks = (a.npairs * G + 31) / 32;
+  long long grid = (long long)sms * per_sm;
+  const long long need = (ntasks * 32 + NT - 1) / NT;
+  grid = std::max<long long>(1, std::min(grid, need));
+  if (cfg) { cfg->strip_w = W; cfg->strip_nr = G; cfg->strip_warps = NT / 32; cfg->strip_gring = 0; }
+  kern<<<(unsigned)grid, NT, 0, ws.stream>>>(a, m, G, lay);
+  WB_CK(cudaGetLastError());
+  return 0;
+}
+
 // What one DP launch needs to know.
 struct DpCall {
   int metric;
@@ -511,11 +541,36 @@ static int launch_dp_t(Workspace& ws, const DeviceInfo& di, const DpCall& c, lon
   auto body = [&](auto m) {
     using M = decltype(m);
     bool strip_ok = strip_supported<M>(a.g, 4) && !c.need_rowmin &&
-                    !(out_m != nullptr) && c.p.engine != 1 && c.p.engine != 3;
+                    !(out_m != nullptr) && c.p.engine != 1 && c.p.engine != 3 && c.p.engine != 4;
     if (thr && !M::kColumnMinBound) strip_ok = false;  // exact abandoning needs row minima
     if (c.p.engine == 2 && !strip_ok) { set_err("strip engine forced but not applicable"); rc = 1; return; }
     if constexpr (!kF32) {
       if (!strip_ok && c.pyi && c0 == 0 && c.ys == 0) { a.y = c.pyi; a.yil = 1; }
+    }
+    // Cooperative engine (a group of lanes per pair, band row in registers): forced (engine 4), or chosen when a thread
+    // per pair is the wrong shape -- (1) tall bands whose per-pair boundary buffers would spill out of L2 (T = 4096,
+    // r = 0.05: 256 MB), (2) too few pairs to give every scheduler a few warps of 32 pairs.
+    if constexpr (!kF32) {
+      const bool plain = !c.need_rowmin && out_m == nullptr && thr == nullptr && c.mode != PM_LIST && !a.yil;
+      if (plain && (c.p.engine == 0 || c.p.engine == 4)) {
+        int cw = 0, cg = 0;
+        CoopLayout lay;
+        const long long npairs = (c.mode == PM_PAIRED) ? nrows : (c.mode == PM_LISTP ? c.list_n : nrows * ncols);
+        bool use = coop_pick<M>(a.g, &cw, &cg, &lay);
+        if (use && c.p.engine == 0) {
+          const bool tall = a.g.H >= 32 && strip_ring_slots(a.g, StripCfg<M>::WL) > 230;
+          const bool few = (npairs + 31) / 32 < (long long)di.sms * 16 && npairs * cg / 32 >= 8;
+          use = strip_ok ? (tall || few) : false;
+        }
+        if (use) {
+          engine = 4;
+          a.npairs = npairs;
+          rc = (cw == 8) ? launch_coop_cfg<M, 8, 256, 2>(ws, a, m, cg, lay, di.sms, stats)
+                         : launch_coop_cfg<M, 13, 384, 1>(ws, a, m, cg, lay, di.sms, stats);
+          return;
+        }
+        if (c.p.engine == 4) { set_err("cooperative engine forced but not applicable"); rc = 1; return; }
+      } else if (c.p.engine == 4) { set_err("cooperative engine forced but not applicable"); rc = 1; return; }
     }
     if (strip_ok) {
       engine = 2;
