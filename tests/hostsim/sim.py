@@ -15,13 +15,25 @@ class WbParams(C.Structure):
         ("engine", C.c_int32), ("precision", C.c_int32)]
 
 
+_SO_COOP = os.path.join(_HERE, "_hostsim_coop.so")
+_CSRC = os.path.join(_ROOT, "wildboar_b200", "csrc")
+_UNITS = {
+    _SO: ("hostsim.cpp", ("metrics.cuh", "engine_strip.cuh", "engine_rowscan.cuh", "engine_band.cuh", "dispatch.cuh", "prep.hpp")),
+    _SO_COOP: ("hostsim_coop.cpp", ("metrics.cuh", "engine_coop.cuh", "dispatch.cuh", "prep.hpp")),
+}
+
+
 def build(force=False):
-    srcs = [os.path.join(_HERE, "hostsim.cpp")] + [
-        os.path.join(_ROOT, "wildboar_b200", "csrc", f)
-        for f in ("metrics.cuh", "engine_strip.cuh", "engine_rowscan.cuh", "engine_band.cuh", "engine_coop.cuh", "dispatch.cuh", "prep.hpp")]
-    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared",
-                               "-Wno-unknown-pragmas", "-o", _SO, srcs[0]])
+    """Compile the two host-simulation objects (in parallel) when a source is newer than the object."""
+    procs = []
+    for so, (main, deps) in _UNITS.items():
+        srcs = [os.path.join(_HERE, main)] + [os.path.join(_CSRC, f) for f in deps]
+        if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            procs.append(subprocess.Popen(["g++", "-O1", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared",
+                                           "-Wno-unknown-pragmas", "-o", so, srcs[0]]))
+    for p in procs:
+        if p.wait() != 0:
+            raise RuntimeError("building the host simulation failed")
     return _SO
 
 
@@ -36,6 +48,17 @@ def lib():
         _lib.hostsim_pair.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(WbParams), dp, C.c_int64, dp, C.c_int64,
                                       C.c_int, C.c_double, C.c_int, C.c_int, dp, dp]
     return _lib
+
+
+_lib_coop = None
+
+
+def lib_coop():
+    global _lib_coop
+    if _lib_coop is None:
+        build()
+        _lib_coop = C.CDLL(_SO_COOP)
+    return _lib_coop
 
 
 def pair(engine, W, metric_id, params, x, y, ea=0, min_dist_raw=float("inf"), ns_extra=0, bs=1):
@@ -56,7 +79,7 @@ def coop_pair(W, G, metric_id, params, x, y):
     y = np.ascontiguousarray(y, dtype=np.float64)
     out = C.c_double(0)
     dp = C.POINTER(C.c_double)
-    f = lib().hostsim_coop_pair
+    f = lib_coop().hostsim_coop_pair
     f.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(WbParams), dp, C.c_int64, dp, C.c_int64, dp]
     rc = f(W, G, metric_id, C.byref(params), x.ctypes.data_as(dp), len(x), y.ctypes.data_as(dp), len(y), C.byref(out))
     return rc, out.value

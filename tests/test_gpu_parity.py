@@ -474,17 +474,29 @@ def test_coop_engine_matches_oracle(W, oracle, metric, monkeypatch):
 
 
 def test_coop_engine_is_selected_for_small_problems_and_tall_bands(W, oracle):
-    """Automatic dispatch: cfg1 (200 x 200, too few pairs for a thread per pair) and cfg5's band (T = 4096, r = 0.05: per-pair
-    boundary buffers would spill out of L2) run on the cooperative engine; cfg3-like shapes stay on the strip engine."""
-    x, y = random_walks(200, 150, 1), random_walks(200, 150, 2)
-    _eq(W.pairwise_distance(x, y, metric="dtw", metric_params={"r": 0.1}), oracle.pairwise("dtw", x, y, r=0.1, n_jobs=0), "cfg1")
+    """Automatic dispatch (measured, profiles/r02d_engines_coop_v3.jsonl): problems with too few pairs to give every SM a
+    few thread-per-pair warps (one query against a set, DBA-sized lists) and the DTW family on tall bands (T = 4096,
+    r = 0.05: per-pair boundary buffers would spill out of L2) run on the cooperative engine; cfg1 / cfg3-like shapes
+    stay on the strip engine."""
+    x, y = random_walks(1, 512, 1), random_walks(2000, 512, 2)
+    _eq(W.pairwise_distance(x, y, metric="dtw", metric_params={"r": 0.1}), oracle.pairwise("dtw", x, y, r=0.1, n_jobs=0), "1 x 2000")
     st = W.last_stats()
-    assert st["engine"] == 4 and st["strip_w"] == 8 and st["strip_nr"] == 4, st
+    assert st["engine"] == 4 and st["strip_w"] == 8 and st["strip_nr"] == 16, st
     x, y = random_walks(2000, 4096, 1)[:6], random_walks(2000, 4096, 2)[:40]
-    for metric in ("msm", "twe"):
+    for metric in ("msm", "twe", "dtw"):
         _eq(W.pairwise_distance(x, y, metric=metric, metric_params={"r": 0.05}), oracle.pairwise(metric, x, y, r=0.05, n_jobs=0), "cfg5 " + metric)
         st = W.last_stats()
         assert st["engine"] == 4 and st["strip_w"] == 13 and st["strip_nr"] == 32, st
+    x, y = random_walks(2000, 4096, 1)[:40], random_walks(2000, 4096, 2)[:1000]
+    got = W.pairwise_distance(x, y, metric="dtw", metric_params={"r": 0.05})
+    assert W.last_stats()["engine"] == 4        # tall band, DTW family: cooperative at any pair count
+    ii, jj = np.arange(0, 40, 7), np.arange(3, 1000, 171)
+    _eq(got[np.ix_(ii, jj)], oracle.pairwise("dtw", x[ii], y[jj], r=0.05, n_jobs=0), "cfg5 dtw sample")
+    W.pairwise_distance(x, y, metric="msm", metric_params={"r": 0.05})
+    assert W.last_stats()["engine"] == 2        # tall band, msm, enough warps: strip engine
+    x, y = random_walks(200, 150, 1), random_walks(200, 150, 2)
+    _eq(W.pairwise_distance(x, y, metric="dtw", metric_params={"r": 0.1}), oracle.pairwise("dtw", x, y, r=0.1, n_jobs=0), "cfg1")
+    assert W.last_stats()["engine"] == 2
     x, y = random_walks(10000, 512, 1)[:64], random_walks(10000, 512, 2)[:3000]
     W.pairwise_distance(x, y, metric="dtw", metric_params={"r": 0.1})
     assert W.last_stats()["engine"] == 2

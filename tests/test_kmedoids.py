@@ -1,0 +1,90 @@
+"""KMedoids mirror (wildboar_b200.neighbors.KMedoids; reference: src/wildboar/distance/_neighbors.py:615-930 and the PAM
+helpers of _cneighbors.pyx) against golden vectors generated from the reference (tests/golden/make_golden_kmedoids.py).
+
+CPU: the clustering logic alone on the reference's own distance matrices (metric="precomputed": no kernel involved).
+GPU: the whole estimator -- distance matrix from the device self join, then the same bookkeeping."""
+import ast
+import warnings
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def km_golden():
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kmedoids_golden.npz")
+    with np.load(path) as z:
+        return {k: z[k] for k in z.files}
+
+
+def _cases(g):
+    return list(enumerate(ast.literal_eval(str(g["meta_cases"]))))
+
+
+def _check(est, g, pre):
+    assert np.array_equal(est.medoid_indices_, g[pre + "|medoids"]), pre
+    assert np.array_equal(est.labels_, g[pre + "|labels"]), pre
+    assert est.inertia_ == g[pre + "|inertia"], pre
+    assert est.n_iter_ == g[pre + "|n_iter"], pre
+
+
+def test_kmedoids_bookkeeping_matches_reference_on_precomputed_matrices(wb, km_golden):
+    from wildboar_b200.neighbors import KMedoids
+    g = km_golden
+    for c, (metric, mp, k, alg, init, n_init, seed) in _cases(g):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            est = KMedoids(n_clusters=k, metric="precomputed", algorithm=alg, init=init, n_init=n_init, random_state=seed).fit(g[f"{c}|dist"])
+        _check(est, g, f"{c}|pre")
+        assert est.cluster_centers_ is None
+        assert np.array_equal(est.transform(g[f"{c}|dist"][:5]), g[f"{c}|dist"][:5][:, est.medoid_indices_])
+
+
+def test_kmedoids_pam_helpers_match_live_reference(wb, oracle):
+    from oracle import ref
+    if ref.load() is None:
+        pytest.skip("oracle/_ref not built")
+    from wildboar.distance._cneighbors import _pam_build, _pam_optimal_swap
+    from wildboar_b200.neighbors import _pam_build as my_build, _pam_optimal_swap as my_swap
+    rng = np.random.default_rng(3)
+    for trial in range(6):
+        n, k = int(rng.integers(12, 40)), int(rng.integers(2, 6))
+        X = np.cumsum(rng.standard_normal((n, 20)), axis=1)
+        D = oracle.pairwise("msm" if trial % 2 else "dtw", X, None, r=0.3)   # msm: asymmetric values mirrored, like the reference's matrix
+        med = _pam_build(D, k)
+        assert np.array_equal(my_build(D, k), med)
+        not_med = np.delete(np.arange(n), med)
+        djs, ejs = np.sort(D[med], axis=0)[[0, 1]]
+        want = _pam_optimal_swap(D, med.astype(np.intp), not_med.astype(np.intp), djs, ejs, k)
+        got = my_swap(D, med, not_med, djs, ejs, k)
+        assert (want is None and got is None) or (tuple(want)[:2] == got[:2] and want[2] == got[2]), (trial, want, got)
+
+
+def test_kmedoids_validation(wb):
+    from wildboar_b200.neighbors import KMedoids
+    x = np.zeros((6, 8))
+    for kw in (dict(n_clusters=0), dict(metric="euclidean"), dict(algorithm="slow"), dict(init="best"), dict(n_init=0), dict(max_iter=0),
+               dict(tol=-1.0), dict(metric_params=3)):
+        with pytest.raises(ValueError):
+            KMedoids(**kw).fit(x)
+    with pytest.raises(Exception):
+        KMedoids().transform(x)
+
+
+@pytest.mark.gpu
+def test_kmedoids_matches_reference_golden(wb, km_golden):
+    from wildboar_b200.neighbors import KMedoids
+    wb.set_devices([0])
+    g = km_golden
+    for c, (metric, mp, k, alg, init, n_init, seed) in _cases(g):
+        X, Q = g[f"{c}|X"], g[f"{c}|Q"]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            est = KMedoids(n_clusters=k, metric=metric, metric_params=mp, algorithm=alg, init=init, n_init=n_init, random_state=seed).fit(X)
+        _check(est, g, f"{c}|fit")
+        assert np.array_equal(est.cluster_centers_, g[f"{c}|fit|centers"])
+        assert np.array_equal(est.transform(Q), g[f"{c}|fit|transform"]), (c, metric)
+        assert np.array_equal(est.predict(Q), g[f"{c}|fit|predict"])
+        assert np.array_equal(KMedoids(n_clusters=k, metric=metric, metric_params=mp, algorithm=alg, init=init, n_init=n_init,
+                                       random_state=seed).fit_predict(X), g[f"{c}|fit|labels"])

@@ -242,13 +242,13 @@ __global__ void __launch_bounds__(NT) k_band(KArgsT<typename M::real> a, M m) {
 }
 
 // ---- cooperative engine: G lanes per pair, the band row in the lanes' registers, neighbours by warp shuffle ----
-template <class M, int W>
+template <class M, int W, int U>
 struct CoopDevGroup {
   using F = typename M::real;
-  CoopLane<M, W>& L;
+  CoopLane<M, W, U>& L;
   const F* x; const F* y;
   int G;
-  CoopTmp<M, W> tmp;
+  CoopTmp<M, W, U> tmp;
   template <class Fn> __device__ __forceinline__ void each(Fn f) { f(L, x, y, tmp); }
   __device__ __forceinline__ void xchg_left() { L.left_in = __shfl_up_sync(0xffffffffu, L.last_out, 1, G); }
   __device__ __forceinline__ void xchg_up() { L.up_in = __shfl_down_sync(0xffffffffu, L.c0, 1, G); }
@@ -257,7 +257,7 @@ struct CoopDevGroup {
 // G (power of two, <= 32) lanes cooperate on one pair; a warp task = 32 / G consecutive pairs (pair e = i * ny + j: the
 // groups of a warp share the x row).  All pairs of a launch share the geometry, so every group of every warp runs the same
 // step sequence (full-mask shuffles).
-template <class M, int W, int NT, int MINB>
+template <class M, int W, int U, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_coop(KArgsT<typename M::real> a, M m, int G, CoopLayout lay) {
   using F = typename M::real;
   const int lane = threadIdx.x & 31;
@@ -284,12 +284,12 @@ __global__ void __launch_bounds__(NT, MINB) k_coop(KArgsT<typename M::real> a, M
     pc.sy = a.sy ? a.sy[j] : 0.0;
     pc.sy2 = a.sy2 ? a.sy2[j] : 0.0;
     mm.begin_pair(pc);
-    CoopLane<M, W> L;
+    CoopLane<M, W, U> L;
     const F* const xp = a.x + i * a.Tx;
     const F* const yp = a.y + j * a.ys;
     L.init(a.g, mm, lay, gl, xp, yp);
-    CoopDevGroup<M, W> grp{L, xp, yp, G, {}};
-    coop_run<M, W>(grp, a.g, mm, lay);
+    CoopDevGroup<M, W, U> grp{L, xp, yp, G, {}};
+    coop_run<M, W, U>(grp, a.g, mm, lay);
     if (valid && L.holds_result(a.g)) {
       const double d = (double)mm.finish(L.result(a.g), a.g);
       double* const po = (a.mode == PM_PAIRED) ? &a.out[i] : (a.mode == PM_LISTP ? &a.out[e] : &a.out[i * a.ld + j]);

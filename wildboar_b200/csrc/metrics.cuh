@@ -437,6 +437,8 @@ struct TwePolicyT {
   struct Col { F yj, yjm, dy; };
   WB_HD Row row(int, F xi, F xim) const { Row r; r.xi = xi; r.xim = xim; r.dx = fabs(xim - xi); return r; }
   WB_HD Col col(int, F yj, F yjm) const { Col c; c.yj = yj; c.yjm = yjm; c.dy = fabs(yjm - yj); return c; }
+  // cooperative engine: y[j-1] is the left neighbour context's sample -- no need to hold it per column
+  WB_HD static void link(Col& c, const Col& prev, bool has_prev) { c.yjm = has_prev ? prev.yj : F(0); }
 
   struct Dv { F t; };
   static constexpr bool kHasDv = true;

@@ -339,6 +339,8 @@ static int launch_strip(Workspace& ws, const KArgsT<typename M::real>& a, const 
       return launch_strip_cfg<M, C::WT, C::NWT * 32, 1, EA, C::NRT, true>(ws, a, m, std::min(C::NWT, cap), sms, smem_cap, cfg);
     return launch_strip_cfg<M, 8, 256, 2, EA, 2, true>(ws, a, m, std::min(8, cap), sms, smem_cap, cfg);
   }
+  // (a deeper in-thread wavefront, NR = 4, for launches with fewer warp tasks than warp slots was measured on cfg1:
+  // 0.175 ms against 0.163 ms with NR = 2 -- profiles/r02e_engines_small.jsonl -- and dropped)
   if (a.g.H >= 16 || a.g.H < 8) return launch_strip_cfg<M, 8, 256, 2, EA, 2, false>(ws, a, m, 8, sms, smem_cap, cfg);
   return launch_strip_cfg<M, 4, 256, 2, EA, 2, false>(ws, a, m, 8, sms, smem_cap, cfg);
 }
@@ -357,9 +359,9 @@ static bool coop_pick(const Geom& g, int* W, int* G, CoopLayout* lay) {
   return false;
 }
 
-template <class M, int W, int NT, int MINB>
+template <class M, int W, int U, int NT, int MINB>
 static int launch_coop_cfg(Workspace& ws, KArgsT<typename M::real> a, const M& m, int G, const CoopLayout& lay, int sms, wb_stats* cfg) {
-  auto kern = k_coop<M, W, NT, MINB>;
+  auto kern = k_coop<M, W, U, NT, MINB>;
   int per_sm = 0;
   WB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, 0));
   if (per_sm < 1) { set_err("cooperative kernel does not fit on an SM"); return 1; }
@@ -558,15 +560,20 @@ static int launch_dp_t(Workspace& ws, const DeviceInfo& di, const DpCall& c, lon
         const long long npairs = (c.mode == PM_PAIRED) ? nrows : (c.mode == PM_LISTP ? c.list_n : nrows * ncols);
         bool use = coop_pick<M>(a.g, &cw, &cg, &lay);
         if (use && c.p.engine == 0) {
+          // measured (profiles/r02d_engines_coop_v3.jsonl): with fewer thread-per-pair warps than ~4 per SM the strip
+          // engine idles most schedulers (1 x 2000 x 512 dtw: 1.57 ms against 0.16 ms here); for tall bands (T = 4096,
+          // r = 0.05) the DTW family is 24 % faster here (1643 against 1320 GCUPS) while msm / twe only win while the
+          // strip engine is short of warps (32-row shares) -- their cells carry more context per column
+          const long long tpp_warps = (npairs + 31) / 32;
           const bool tall = a.g.H >= 32 && strip_ring_slots(a.g, StripCfg<M>::WL) > 230;
-          const bool few = (npairs + 31) / 32 < (long long)di.sms * 16 && npairs * cg / 32 >= 8;
-          use = strip_ok ? (tall || few) : false;
+          const bool few = tpp_warps < (long long)di.sms * 4;
+          use = strip_ok ? (few || (tall && (M::kColumnMinBound || tpp_warps < (long long)di.sms * 8))) : false;
         }
         if (use) {
           engine = 4;
           a.npairs = npairs;
-          rc = (cw == 8) ? launch_coop_cfg<M, 8, 256, 2>(ws, a, m, cg, lay, di.sms, stats)
-                         : launch_coop_cfg<M, 13, 384, 1>(ws, a, m, cg, lay, di.sms, stats);
+          rc = (cw == 8) ? launch_coop_cfg<M, 8, 8, 256, 2>(ws, a, m, cg, lay, di.sms, stats)
+                         : launch_coop_cfg<M, 13, 4, 384, 1>(ws, a, m, cg, lay, di.sms, stats);
           return;
         }
         if (c.p.engine == 4) { set_err("cooperative engine forced but not applicable"); rc = 1; return; }

@@ -36,7 +36,7 @@ except Exception:  # pragma: no cover
     class _NotFitted(ValueError, AttributeError):
         pass
 
-__all__ = ["NearestNeighbors", "KNeighborsClassifier", "KMeans"]
+__all__ = ["NearestNeighbors", "KNeighborsClassifier", "KMeans", "KMedoids"]
 
 
 class _NeighborsBase(_SkBase):
@@ -356,6 +356,227 @@ class KMeans(_SkBase):
         x = check_array(x, allow_3d=False, dtype=float, input_name="x")
         metric, mp = self._metric()
         return pairwise_distance(x, self.cluster_centers_, dim="mean", metric=metric, metric_params=mp)
+
+    def predict(self, x):
+        return self.transform(x).argmin(axis=1)
+
+    def fit_predict(self, x, y=None):
+        return self.fit(x).labels_
+
+
+# ---------------------------------------------------------------------------------------------
+# KMedoids (reference: _neighbors.py:615-930 + the PAM helpers of _cneighbors.pyx)
+# ---------------------------------------------------------------------------------------------
+def _seq_sum(v):
+    """Sum in index order (one rounding per addition), as the reference's C loops accumulate."""
+    return float(np.cumsum(v)[-1]) if len(v) else 0.0
+
+
+def _pam_build(D, n_clusters):
+    """BUILD initialisation, `_pam_build` of _cneighbors.pyx:70-108: greedy, cost changes accumulated in index order,
+    `>=` keeps the LAST best candidate."""
+    n = len(D)
+    medoids = np.zeros(n_clusters, dtype=np.intp)
+    medoids[0] = np.argmin(np.sum(D, axis=0))
+    not_medoids = np.delete(np.arange(n, dtype=np.intp), medoids[0])
+    Dj = D[medoids[0]].copy()
+    for cur in range(1, n_clusters):
+        best, best_val = (0, 0), 0.0
+        djn = Dj[not_medoids]
+        for i, id_i in enumerate(not_medoids):
+            cc = _seq_sum(np.maximum(0.0, djn - D[id_i, not_medoids]))
+            if cc >= best_val:
+                best_val, best = cc, (id_i, i)
+        medoids[cur] = best[0]
+        not_medoids = np.delete(not_medoids, best[1])
+        Dj = np.minimum(Dj, D[:, best[0]])
+    return medoids
+
+
+def _pam_optimal_swap(D, medoids, not_medoids, Djs, Ejs, n_clusters):
+    """SWAP step, `_pam_optimal_swap` of _cneighbors.pyx:13-67: the same four cases per non-medoid point, summed in index
+    order; strict `<` keeps the FIRST best swap (h outer, i inner)."""
+    best = (1, 1, 0.0)
+    djn, ejn = Djs[not_medoids], Ejs[not_medoids]
+    for id_h in not_medoids:
+        dh_row = D[id_h, not_medoids]   # D[id_h, id_j]
+        dh_col = D[not_medoids, id_h]   # D[id_j, id_h]
+        second = dh_row < ejn
+        gain = dh_col - djn
+        for id_i in medoids:
+            in_i = D[id_i, not_medoids] == djn
+            terms = np.where(in_i & second, gain, np.where(in_i & ~second, ejn - djn, np.where(~in_i & (dh_col < djn), gain, 0.0)))
+            cc = _seq_sum(terms)
+            cc += D[id_i, id_h] if D[id_h, id_i] < Ejs[id_i] else Ejs[id_i]
+            if cc < best[2]:
+                best = (int(id_i), int(id_h), float(cc))
+    return best if best[2] < 0 else None
+
+
+class KMedoids(_SkBase):
+    """KMedoids on an elastic metric (reference: _neighbors.py:677-930).
+
+    Same parameters, random-number consumption, ``medoid_indices_`` / ``labels_`` / ``inertia_`` / ``n_iter_`` /
+    ``cluster_centers_`` as the reference.  The one expensive step -- the n x n distance matrix
+    ``pairwise_distance(x, dim="mean")`` -- is one self join on the device (lower triangle mirrored by the kernel); the
+    medoid updates are the reference's matrix bookkeeping ("fast": per-cluster row sums; "pam": the BUILD / SWAP loops of
+    _cneighbors.pyx restated with their summation order).  ``transform`` / ``predict`` compare against the medoids only.
+    """
+
+    _param_names = ("n_clusters", "metric", "metric_params", "init", "n_init", "algorithm", "max_iter", "tol", "verbose",
+                    "n_jobs", "random_state")
+
+    def __init__(self, n_clusters=8, metric="dtw", metric_params=None, init="random", n_init="auto", algorithm="fast",
+                 max_iter=30, tol=1e-4, verbose=0, n_jobs=None, random_state=None):
+        self.n_clusters = n_clusters
+        self.metric = metric
+        self.metric_params = metric_params
+        self.init = init
+        self.n_init = n_init
+        self.algorithm = algorithm
+        self.max_iter = max_iter
+        self.tol = tol
+        self.verbose = verbose
+        self.n_jobs = n_jobs
+        self.random_state = random_state
+
+    def _validate_params(self):
+        name = type(self).__name__
+
+        def bad(param, what):
+            return ValueError(f"The {param!r} parameter of {name} must be {what}. Got {getattr(self, param)!r} instead.")
+
+        def is_int(v):
+            return isinstance(v, numbers.Integral) and not isinstance(v, bool)
+
+        if not is_int(self.n_clusters) or self.n_clusters < 1:
+            raise bad("n_clusters", "an int in the range [1, inf)")
+        if not (isinstance(self.metric, str) and (self.metric in _METRICS or self.metric == "precomputed")):
+            raise bad("metric", f"a str among {set(_METRICS) | {'precomputed'}} (the elastic metrics; others are not accelerated)")
+        if self.metric_params is not None and not isinstance(self.metric_params, dict):
+            raise bad("metric_params", "an instance of 'dict' or None")
+        if self.init not in ("random", "auto", "min"):
+            raise bad("init", "a str among {'auto', 'min', 'random'}")
+        if not (self.n_init == "auto" or (is_int(self.n_init) and self.n_init >= 1)):
+            raise bad("n_init", "a str among {'auto'} or an int in the range [1, inf)")
+        if self.algorithm not in ("fast", "pam"):
+            raise bad("algorithm", "a str among {'fast', 'pam'}")
+        if not is_int(self.max_iter) or self.max_iter < 1:
+            raise bad("max_iter", "an int in the range [1, inf)")
+        if isinstance(self.tol, bool) or not isinstance(self.tol, numbers.Real) or self.tol < 0:
+            raise bad("tol", "a float in the range [0.0, inf)")
+
+    def fit(self, x, y=None):
+        import warnings
+
+        from .distance import pairwise_distance
+        from .dtw import _check_random_state
+        self._validate_params()
+        x = check_array(x, allow_3d=True, dtype=float, input_name="x")
+        self.n_timesteps_in_ = x.shape[-1]
+        self.n_dims_in_ = x.shape[1] if x.ndim == 3 else 1
+        n_init = (1 if self.init == "auto" else 10) if self.n_init == "auto" else self.n_init
+        if n_init > 1 and self.init != "random":  # initial medoids are deterministic
+            n_init = 1
+        max_iter = self.max_iter
+        if self.algorithm == "pam" and self.n_clusters == 1 and self.max_iter != 0:
+            warnings.warn("n_clusters must be larger than 1 if max_iter larger than 0")
+            max_iter = 0
+        random_state = _check_random_state(self.random_state)
+        if self.metric == "precomputed":
+            dist = x
+        else:
+            dist = pairwise_distance(x, dim="mean", metric=self.metric, metric_params=self.metric_params)
+        best_iter, best_cost, best, best_reassign, last = 0, np.inf, None, None, None
+        for _ in range(n_init):
+            it, last, reassign = self._fit_one_init(dist, max_iter=max_iter, random_state=random_state)
+            if last["cost"] < best_cost:
+                best_cost, best, best_iter, best_reassign = last["cost"], last, it, reassign
+        if best_reassign:
+            self._assign(dist, last)  # (the reference re-assigns the LAST clusterer here, _neighbors.py:834-835)
+        self.cluster_centers_ = None if self.metric == "precomputed" else x[best["medoids"]]
+        self.inertia_ = best["cost"]
+        self.medoid_indices_ = best["medoids"]
+        self.n_iter_ = best_iter
+        self.labels_ = best["labels"]
+        return self
+
+    # _KMedoidsCluster (reference :615-633)
+    @staticmethod
+    def _assign(dist, c):
+        c["labels"] = dist[c["medoids"]].argmin(axis=0)
+
+    @staticmethod
+    def _cost(dist, c):
+        c["cost"] = np.take(dist, c["medoids"][c["labels"]]).sum() / dist.shape[0]
+
+    def _update(self, dist, c):
+        med = c["medoids"]
+        if self.algorithm == "fast":  # _FastKMedoidsCluster.update, :635-647
+            for idx in range(med.shape[0]):
+                members = np.where(c["labels"] == idx)[0]
+                if members.shape[0] == 0:
+                    continue
+                cost = dist[members, members.reshape(-1, 1)].sum(axis=1)
+                min_idx = cost.argmin()
+                if cost[min_idx] < cost[(members == med[idx]).argmax()]:
+                    med[idx] = members[min_idx]
+        else:  # _PamKMedoidsCluster.update, :655-672
+            not_med = np.delete(np.arange(dist.shape[0]), med)
+            swap = _pam_optimal_swap(dist, med, not_med, c["djs"], c["ejs"], med.shape[0])
+            if swap is not None:
+                i, j, _ = swap
+                med[med == i] = j
+                c["djs"], c["ejs"] = np.sort(dist[med], axis=0)[[0, 1]]
+
+    def _fit_one_init(self, dist, *, max_iter, random_state):
+        import math
+        import warnings
+        c = {"medoids": np.asarray(self._init_centers(dist, self.n_clusters, random_state)).copy()}
+        if self.algorithm == "pam":
+            c["djs"], c["ejs"] = np.sort(dist[c["medoids"]], axis=0)[[0, 1]]
+        self._assign(dist, c)
+        reassign = False
+        prev_cost = np.inf
+        it = 0
+        for it in range(max_iter):
+            self._update(dist, c)
+            self._cost(dist, c)
+            if self.verbose:
+                print(f"Iteration {it}/{self.max_iter}: current_cost={c['cost']}")
+            if math.isclose(c["cost"], prev_cost, rel_tol=self.tol):
+                reassign = True
+                break
+            prev_cost = c["cost"]
+            self._assign(dist, c)
+        if max_iter == 0:
+            self._cost(dist, c)
+        if it + 1 == self.max_iter:
+            try:
+                from sklearn.exceptions import ConvergenceWarning
+            except Exception:  # pragma: no cover
+                ConvergenceWarning = UserWarning
+            warnings.warn("Maximum number of iterations reached before convergence. Consider increasing max_iter to improve the fit",
+                          ConvergenceWarning)
+        return it, c, reassign
+
+    def _init_centers(self, dist, n_clusters, random_state):
+        if self.init == "random":
+            return random_state.choice(dist.shape[0], n_clusters, replace=False)
+        if self.init == "min" or (self.algorithm == "fast" and self.init == "auto"):
+            return np.argpartition(dist.sum(axis=1), n_clusters)[:n_clusters]
+        return _pam_build(dist, n_clusters)
+
+    def transform(self, x):
+        from .distance import pairwise_distance
+        if not hasattr(self, "medoid_indices_"):
+            raise _NotFitted(f"This {type(self).__name__} instance is not fitted yet. Call 'fit' with appropriate arguments before using this estimator.")
+        x = check_array(x, allow_3d=True, dtype=float, input_name="x")
+        if self.metric == "precomputed":
+            return x[:, self.medoid_indices_]
+        if x.shape[-1] != self.n_timesteps_in_:
+            raise ValueError(f"X has {x.shape[-1]} timesteps, but {type(self).__name__} is expecting {self.n_timesteps_in_} timesteps as input.")
+        return pairwise_distance(x, self.cluster_centers_, dim="mean", metric=self.metric, metric_params=self.metric_params)
 
     def predict(self, x):
         return self.transform(x).argmin(axis=1)
