@@ -367,9 +367,13 @@ def main():
         raise SystemExit("bench.py needs a B200: the CUDA path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpu_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        # host-side barrier for the in-process multi-GPU section: a rank waiting in an NCCL barrier keeps a spinning kernel
+        # on ITS GPU, which the one process that drives all GPUs would then have to share (measured: 2.2x slower kernels)
+        cpu_group = dist.new_group(backend="gloo")
     if rank == 0:
         _build.build()
     if world > 1:
@@ -431,10 +435,11 @@ def main():
     # end to end through the public API: host numpy in, host numpy out, every step
     e2e_steps = args.e2e_steps if args.e2e_steps is not None else min(args.steps, 8)
     wb.set_devices([local])
-    # warm-up: two calls, the first result still alive during the second -- the steady state of `res = f(...)` in a loop
-    # needs TWO page-locked result blocks in the library's pool, and page-locking 800 MB costs ~0.4 s once
-    res = wb.pairwise_distance(x_h, y_h, metric=metric, metric_params={"r": r})
-    res = wb.pairwise_distance(x_h, y_h, metric=metric, metric_params={"r": r})
+    # warm-up: the steady state of `res = f(...)` in a loop needs TWO page-locked result blocks in the library's pool (the
+    # previous result is still alive while the next is produced); blocks over 256 MB are page-locked by a background thread
+    # after the first request of that size (0.4 s for 800 MB, never on the caller's time), so three calls settle the pool
+    for _ in range(3):
+        res = wb.pairwise_distance(x_h, y_h, metric=metric, metric_params={"r": r})
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -476,10 +481,19 @@ def main():
         crcs = [None] * world
         dist.all_gather_object(crcs, (lo, hi, slab_crc))
         barrier()
+        # the other ranks give their GPUs up for this section: device buffers released, waiting on the HOST (gloo)
+        if rank != 0:
+            del x_d, y_d, out_d, flush
+            torch.cuda.empty_cache()
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)
         if rank == 0:
             x_full = random_walks(wl["nx"], T, 1)
             wb.set_devices(list(range(world)))
-            full = wb.pairwise_distance(x_full, y_h, metric=metric, metric_params={"r": r})  # warm-up (contexts, pools on every device)
+            # warm-up (contexts and pools on every device; the library page-locks a result block of this size in the background)
+            for _ in range(2):
+                full = wb.pairwise_distance(x_full, y_h, metric=metric, metric_params={"r": r})
+                del full
             t0 = time.perf_counter()
             full = wb.pairwise_distance(x_full, y_h, metric=metric, metric_params={"r": r})
             dt_in = time.perf_counter() - t0
@@ -491,7 +505,7 @@ def main():
                       "h2d_bytes": int((wl["nx"] + world * ny) * T * 8), "d2h_bytes": int(wl["nx"] * ny * 8)}
             wb.set_devices([local])
             del full, x_full
-        barrier()
+        dist.barrier(group=cpu_group)
 
     cfgs = None
     if not args.no_configs and args.precision == "fp64" and args.profile_rows == 0:

@@ -30,6 +30,17 @@ struct StripRunner {
   }
 };
 
+// band-register engine, both instantiations (plain rows / blocked interior rows): value AND row-minimum maximum must agree
+template <class M, int HB, int YS>
+static double band_both(const Geom& g, const M& m, const double* x, const double* yp, double min_dist, double* mm) {
+  double m0 = 0, m1 = 0;
+  const double d0 = band_pair<M, HB, YS, false>(g, m, x, yp, min_dist, &m0);
+  const double d1 = band_pair<M, HB, YS, true>(g, m, x, yp, min_dist, &m1);
+  *mm = m0;
+  const bool same = (d0 == d1 || (d0 != d0 && d1 != d1)) && (m0 == m1 || (m0 != m0 && m1 != m1));
+  return same ? d0 : -1e300;
+}
+
 // engine: 1 row-scan, 2 strip.  ea: 0 distance() / 1 eadistance() semantics for R (ddtw, edr).
 // Returns 0 ok, 1 unsupported by this engine, 2 bad args.
 extern "C" int hostsim_pair(int engine, int W, int metric, const wb_params* p, const double* x, int64_t Tx,
@@ -73,8 +84,8 @@ extern "C" int hostsim_pair(int engine, int W, int metric, const wb_params* p, c
         *out = rowscan_pair<MM, 32>(g, m, x, yp, b0.data(), b1.data(), (long long)bs, min_dist_raw, &mm);
       } else {
         switch (W) {
-          case 8: if ((ok = band_supported<MM>(g, 8))) *out = band_pair<MM, 8, 32>(g, m, x, yp, min_dist_raw, &mm); break;
-          case 16: if ((ok = band_supported<MM>(g, 16))) *out = band_pair<MM, 16, 32>(g, m, x, yp, min_dist_raw, &mm); break;
+          case 8: if ((ok = band_supported<MM>(g, 8))) *out = band_both<MM, 8, 32>(g, m, x, yp, min_dist_raw, &mm); break;
+          case 16: if ((ok = band_supported<MM>(g, 16))) *out = band_both<MM, 16, 32>(g, m, x, yp, min_dist_raw, &mm); break;
           case 32: if ((ok = band_supported<MM>(g, 32))) *out = band_pair<MM, 32, 32>(g, m, x, yp, min_dist_raw, &mm); break;
           default: ok = false;
         }
@@ -86,8 +97,8 @@ extern "C" int hostsim_pair(int engine, int W, int metric, const wb_params* p, c
       double mm = 0;
       bool ok = true;
       switch (W) {
-        case 8: if ((ok = band_supported<MM>(g, 8))) *out = band_pair<MM, 8>(g, m, x, y, min_dist_raw, &mm); break;
-        case 16: if ((ok = band_supported<MM>(g, 16))) *out = band_pair<MM, 16>(g, m, x, y, min_dist_raw, &mm); break;
+        case 8: if ((ok = band_supported<MM>(g, 8))) *out = band_both<MM, 8, 1>(g, m, x, y, min_dist_raw, &mm); break;
+        case 16: if ((ok = band_supported<MM>(g, 16))) *out = band_both<MM, 16, 1>(g, m, x, y, min_dist_raw, &mm); break;
         case 32: if ((ok = band_supported<MM>(g, 32))) *out = band_pair<MM, 32>(g, m, x, y, min_dist_raw, &mm); break;
         default: ok = false;
       }

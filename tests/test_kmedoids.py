@@ -88,3 +88,28 @@ def test_kmedoids_matches_reference_golden(wb, km_golden):
         assert np.array_equal(est.predict(Q), g[f"{c}|fit|predict"])
         assert np.array_equal(KMedoids(n_clusters=k, metric=metric, metric_params=mp, algorithm=alg, init=init, n_init=n_init,
                                        random_state=seed).fit_predict(X), g[f"{c}|fit|labels"])
+
+
+# ---- proximity-tree pivot loops (wildboar_b200.tree; reference: src/wildboar/tree/_cptree.pyx:273-289, 887-910) ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("metric,mp", [("dtw", {"r": 0.1}), ("msm", {"r": 0.2}), ("wdtw", {"r": 0.3, "g": 0.1}), ("erp", {"r": 0.2}),
+                                        ("twe", {"r": 0.15}), ("lcss", {"r": 0.5, "epsilon": 0.7})])
+def test_pivot_partition_keeps_the_operand_order_of_the_loop_it_replaces(wb, oracle, metric, mp):
+    from wildboar_b200.tree import find_min_branch, partition_pivots
+    wb.set_devices([0])
+    rng = np.random.default_rng(17)
+    X = np.cumsum(rng.standard_normal((90, 64)), axis=1)
+    for n_node, n_branch in ((90, 3), (17, 2), (40, 5)):
+        samples = rng.choice(90, n_node, replace=False)
+        pivots = rng.choice(samples, n_branch, replace=False)
+        # _partition_pivots: distance(metric, X, pivots[p], X, j) -- pivot first
+        want_d = oracle.pairwise(metric, X[pivots], X[samples], n_jobs=0, **mp).T
+        branch, d = partition_pivots(X, samples, pivots, metric=metric, metric_params=mp, return_distance=True)
+        assert np.array_equal(d, want_d) and np.array_equal(branch, want_d.argmin(axis=1)), (metric, n_node)
+        # find_min_branch: _distance(metric, sample, pivot) -- sample first
+        want_d = oracle.pairwise(metric, X[samples], X[pivots], n_jobs=0, **mp)
+        branch, d = find_min_branch(X[pivots], X[samples], metric=metric, metric_params=mp, return_distance=True)
+        assert np.array_equal(d, want_d) and np.array_equal(branch, want_d.argmin(axis=1)), (metric, n_node)
+    # ties: the first pivot wins (strict `<`)
+    Xt = np.vstack([X[:1], X[:1], X[1:5]])
+    assert np.array_equal(partition_pivots(Xt, [2, 3, 4], [0, 1], metric=metric, metric_params=mp), np.zeros(3, dtype=np.intp))

@@ -33,7 +33,7 @@ inline bool band_supported(const Geom& g, int HB) {
 // min_dist: abandon when a checked row's minimum exceeds it (raw dp domain); +inf disables.
 // row_min_max (optional): max over checked rows of the row minimum (for the exact replay).
 // YS: element stride of y (1: a plain series; 32: interleaved in groups of 32 series, kernels.cuh `KArgs::yil`).
-template <class M, int HB, int YS = 1>
+template <class M, int HB, int YS = 1, bool BLK = false>
 WB_HD typename M::real band_pair(const Geom& g, const M& m, const typename M::real* __restrict__ x,
                                  const typename M::real* __restrict__ yp, typename M::real min_dist,
                                  typename M::real* row_min_max) {
@@ -74,7 +74,82 @@ WB_HD typename M::real band_pair(const Geom& g, const M& m, const typename M::re
     i_first = 1;
   }
 
+  // ---- blocked interior rows (HB <= 16) ----
+  // Rows a + 1 (MSM: a + 2) .. T - R have their whole band inside the matrix and no row-0 / column-0 rule: NRB of them run
+  // per iteration without band-edge predicates, with the column contexts of the HB + NRB - 1 columns they touch held in
+  // registers (cell k of row r reads cols[1 + k + r]; after the block the array moves down by NRB and NRB new columns
+  // enter) and the per-diagonal values as loop invariants -- the generic row below re-derives a column context from two
+  // loads per cell and tests four predicates per cell (ncu, profiles/r01m_ncu_band.md: 50 instructions per msm cell).
+  constexpr int NRB = 4;
+  constexpr bool kBlocked = BLK && HB <= 16;  // (a separate instantiation: the blocked rows need ~2x the registers)
+  constexpr int NCB = kBlocked ? HB + NRB : 1;
+  typename M::Col cols[NCB];
+  typename M::Dv dvs[kBlocked ? HB : 1];
+  const int r_lo = M::kMsmBand ? a + 2 : a + 1, r_hi = T - R;
+  bool cols_ready = false;
+  const typename M::Col c0col = m.col(0, y[0], F(0));
+
   for (int i = i_first; i < T; ++i) {
+    if (kBlocked && i >= r_lo && i + NRB - 1 <= r_hi) {
+      if (!cols_ready) {
+#pragma unroll
+        for (int q = 0; q < NCB; ++q) {
+          const int j = imin2(imax2(i - a - 1 + q, 0), T - 1);
+          cols[q] = m.col(j, y[j], j > 0 ? y[j - 1] : F(0));
+        }
+        if (M::kHasDv) {
+#pragma unroll
+          for (int k = 0; k < HB; ++k) dvs[k < (kBlocked ? HB : 1) ? k : 0] = m.dv_diag(a - k);
+        }
+        cols_ready = true;
+      }
+      // samples of the NRB columns that enter after this block
+      F ynew[NRB];
+#pragma unroll
+      for (int u = 0; u < NRB; ++u) ynew[u] = y[imin2(i + NRB - a - 1 + HB + u, T - 1)];
+      F xprev = x[i - 1];
+#pragma unroll
+      for (int r = 0; r < NRB; ++r) {
+        const F xr = x[i + r];
+        const typename M::Row rw = m.row(i + r, xr, xprev);
+        xprev = xr;
+        F rowmin = Num<F>::inf();
+        F left = m.lsent();
+        F stale_next = stale;
+        if (M::kMsmBand) {
+          cy = m.cell(cy, Num<F>::inf(), Num<F>::inf(), rw, c0col, m.dv(i + r, 0));  // column 0: always evaluated, part of the row minimum
+          rowmin = cy;
+          stale_next = P[1];
+          left = stale;
+        }
+#pragma unroll
+        for (int k = 0; k < HB; ++k) {
+          if (k < H) {
+            const F up = (k + 1 < H) ? P[(k + 1 < HB) ? (k + 1) : (HB - 1)] : m.usent();
+            typename M::Col cj = cols[(1 + k + r) < NCB ? (1 + k + r) : 0];
+            ColLink<M>::apply(cj, cols[(k + r) < NCB ? (k + r) : 0], true);
+            const F d = m.cell(up, left, P[k], rw, cj, dvs[k < (kBlocked ? HB : 1) ? k : 0]);
+            P[k] = d;
+            rowmin = dmin2(rowmin, d);
+            left = d;
+          }
+        }
+        stale = stale_next;
+        mmax = dmax2(mmax, rowmin);
+        if (rowmin > min_dist) { if (row_min_max) *row_min_max = mmax; return Num<F>::inf(); }
+      }
+#pragma unroll
+      for (int q = 0; q + NRB < NCB; ++q) cols[q] = cols[q + NRB];
+#pragma unroll
+      for (int u = 0; u < NRB; ++u) {
+        const int q = HB + u;  // NCB - NRB + u
+        const int j = imin2(i + NRB - a - 1 + q, T - 1);
+        cols[q < NCB ? q : 0] = m.col(j, ynew[u], cols[(q - 1) < NCB ? (q - 1) : 0].yj);
+      }
+      i += NRB - 1;
+      continue;
+    }
+    cols_ready = false;
     const F xi = x[i];
     const F xim = (i > 0) ? x[i - 1] : F(0);
     const typename M::Row rw = m.row(i, xi, xim);

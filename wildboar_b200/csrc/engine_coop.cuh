@@ -65,16 +65,6 @@ WB_HD bool coop_supported(const Geom& g, int W, int G) {
   return coop_layout(g, W, G, &l);
 }
 
-// link(cur, prev, has_prev): metrics whose column context carries the previous column's sample (twe: y[j-1], 0 for
-// column 0) take it from the neighbouring context instead of holding it per column, so that field never occupies a
-// register -- policies may define `static void link(Col&, const Col&, bool)`.
-template <class M, class = void> struct CoopLink {
-  WB_HD static void apply(typename M::Col&, const typename M::Col&, bool) {}
-};
-template <class M> struct CoopLink<M, decltype(M::link(*(typename M::Col*)nullptr, *(const typename M::Col*)nullptr, true))> {
-  WB_HD static void apply(typename M::Col& c, const typename M::Col& prev, bool has_prev) { M::link(c, prev, has_prev); }
-};
-
 template <class M, int W, int U>
 struct CoopLane {
   using F = typename M::real;
@@ -101,7 +91,7 @@ struct CoopLane {
   template <int Q>
   WB_HD typename M::Col ctx(bool linked = true) const {
     typename M::Col c = cols[Q];
-    CoopLink<M>::apply(c, cols[Q > 0 ? Q - 1 : 0], linked);
+    ColLink<M>::apply(c, cols[Q > 0 ? Q - 1 : 0], linked);
     return c;
   }
 

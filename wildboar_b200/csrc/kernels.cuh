@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(NT) k_rowscan(KArgsT<typename M::real> a, M m)
 }
 
 // ---- band-register engine: thread per pair, the previous band row in HB registers (equal lengths, H <= HB) ----
-template <class M, int HB, int NT, int YS = 1>
+template <class M, int HB, int NT, int YS = 1, bool BLK = false>
 __global__ void __launch_bounds__(NT) k_band(KArgsT<typename M::real> a, M m) {
   using F = typename M::real;
   const int lane = threadIdx.x & 31;
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(NT) k_band(KArgsT<typename M::real> a, M m) {
     const F md = a.thr ? (F)a.thr[a.thr_div > 0 ? i * a.thr_ld + j / a.thr_div : i] : Num<F>::inf();
     F mmax = F(0);
     const F* const yp = (YS == 32) ? a.y + interleave32_base(j, a.Ty) : a.y + j * a.ys;
-    const double d = (double)band_pair<M, HB, YS>(a.g, mm, a.x + i * a.Tx, yp, md, &mmax);
+    const double d = (double)band_pair<M, HB, YS, BLK>(a.g, mm, a.x + i * a.Tx, yp, md, &mmax);
     if (valid) {
       double* const po = result_ptr(a, t, lane, i, j);
       const double r = combine_dims(a, po, d);

@@ -454,6 +454,17 @@ struct TwePolicyT {
   WB_HD F finish(F d, const Geom&) const { return d; }
 };
 
+// ColLink / link(cur, prev, has_prev) -- engines that keep the column contexts of neighbouring columns in registers
+// (engine_coop.cuh, the blocked rows of engine_band.cuh): metrics whose column context carries the previous column's sample (twe: y[j-1], 0 for
+// column 0) take it from the neighbouring context instead of holding it per column, so that field never occupies a
+// register -- policies may define `static void link(Col&, const Col&, bool)`.
+template <class M, class = void> struct ColLink {
+  WB_HD static void apply(typename M::Col&, const typename M::Col&, bool) {}
+};
+template <class M> struct ColLink<M, decltype(M::link(*(typename M::Col*)nullptr, *(const typename M::Col*)nullptr, true))> {
+  WB_HD static void apply(typename M::Col& c, const typename M::Col& prev, bool has_prev) { M::link(c, prev, has_prev); }
+};
+
 using ErpPolicy = ErpPolicyT<double>;
 using MsmPolicy = MsmPolicyT<double>;
 using TwePolicy = TwePolicyT<double>;

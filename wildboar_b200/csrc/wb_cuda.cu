@@ -163,6 +163,7 @@ static std::mutex g_pin_mu;
 static std::map<void*, size_t> g_pin_live;         // blocks handed out: capacity
 static std::multimap<size_t, void*> g_pin_free;    // pooled blocks by capacity
 static size_t g_pin_pooled = 0;
+static size_t g_pin_pending = 0;                   // large blocks being page-locked in the background
 static size_t pin_pool_cap() {
   static size_t cap = [] {
     const char* e = getenv("WILDBOAR_CUDA_PINNED_POOL_MB");
@@ -184,6 +185,30 @@ static void* pinned_alloc(size_t bytes) {
       g_pin_free.erase(it);
       return p;
     }
+  }
+  // Page-locking costs ~0.5 ms per MB (0.4 s for the 800 MB matrix of cfg3) -- more than the pageable copy path loses on
+  // a result that size.  Large blocks are therefore never allocated on the caller's time: the first request is answered
+  // with "none" (the caller uses ordinary memory), a background thread locks a block of that size into the pool, and the
+  // following calls find it there.
+  if (cap > ((size_t)256 << 20)) {
+    if (cap <= pin_pool_cap()) {
+      int dev = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+      std::thread([cap, dev]() {
+        if (cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); return; }  // the caller's device: no stray context elsewhere
+        {
+          std::lock_guard<std::mutex> lk(g_pin_mu);
+          if (g_pin_pooled + g_pin_pending + cap > pin_pool_cap()) return;
+          g_pin_pending += cap;
+        }
+        void* q = nullptr;
+        const bool ok = cudaHostAlloc(&q, cap, cudaHostAllocPortable) == cudaSuccess;
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        g_pin_pending -= cap;
+        if (ok) { g_pin_free.emplace(cap, q); g_pin_pooled += cap; }
+      }).detach();
+    }
+    return nullptr;
   }
   void* p = nullptr;
   if (cudaHostAlloc(&p, cap, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
@@ -373,6 +398,18 @@ static int launch_coop_cfg(Workspace& ws, KArgsT<typename M::real> a, const M& m
   kern<<<(unsigned)grid, NT, 0, ws.stream>>>(a, m, G, lay);
   WB_CK(cudaGetLastError());
   return 0;
+}
+
+// Band-register engine: run the interior rows blocked (engine_band.cuh)?  Measured (profiles/r02h_band_blocked.txt): with
+// DENSE y rows (argmin: every lane walks its own row, one 32-byte sector per lane and load) the blocked rows -- one load
+// per column per four rows instead of two per cell -- are 2-2.7x faster (2000 x 20 000 x 128, r = 0.05: msm 381 -> 181 ms,
+// twe 399 -> 157 ms, lcss 199 -> 66 ms); with coalesced y (sliding windows read in place, interleaved materialised
+// windows) loads are cheap, the kernel lives on resident warps, and the doubled register count (msm 90 -> 198) makes it
+// 1.5-3x SLOWER (msm scan 39 -> 117 ms).  So: blocked exactly for dense rows.
+template <class A>
+static bool band_blocked_auto(const A& a, bool abandoning) {
+  (void)abandoning;
+  return !a.yil && a.ys == a.Ty;
 }
 
 // What one DP launch needs to know.
@@ -600,14 +637,18 @@ static int launch_dp_t(Workspace& ws, const DeviceInfo& di, const DpCall& c, lon
         kern<<<(unsigned)grid, NT, 0, st>>>(a, m);
         if (cudaGetLastError() != cudaSuccess) { set_err("band kernel launch failed"); rc = 1; }
       };
+      // blocked interior rows (engine_band.cuh): about half the instructions per cell but twice the registers, i.e. half
+      // the resident warps -- WILDBOAR_CUDA_BAND_BLOCKED = 0 / 1 forces, default: see band_blocked_auto
+      static const int blk_env = [] { const char* e = getenv("WILDBOAR_CUDA_BAND_BLOCKED"); return e ? atoi(e) : -1; }();
+      const bool blk = a.g.H <= 16 && (blk_env >= 0 ? blk_env != 0 : band_blocked_auto(a, thr != nullptr));
       if (a.yil) {
         if constexpr (!kF32) {
-          if (a.g.H <= 8) go(k_band<M, 8, NT, 32>);
-          else if (a.g.H <= 16) go(k_band<M, 16, NT, 32>);
+          if (a.g.H <= 8) { if (blk) go(k_band<M, 8, NT, 32, true>); else go(k_band<M, 8, NT, 32>); }
+          else if (a.g.H <= 16) { if (blk) go(k_band<M, 16, NT, 32, true>); else go(k_band<M, 16, NT, 32>); }
           else go(k_band<M, 32, NT, 32>);
         }
-      } else if (a.g.H <= 8) go(k_band<M, 8, NT>);
-      else if (a.g.H <= 16) go(k_band<M, 16, NT>);
+      } else if (a.g.H <= 8) { if (blk) go(k_band<M, 8, NT, 1, true>); else go(k_band<M, 8, NT>); }
+      else if (a.g.H <= 16) { if (blk) go(k_band<M, 16, NT, 1, true>); else go(k_band<M, 16, NT>); }
       else go(k_band<M, 32, NT>);
     } else {
       if (c.p.engine == 3) { set_err("band engine forced but not applicable"); rc = 1; return; }
