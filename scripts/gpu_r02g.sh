@@ -8,7 +8,7 @@ tail -15 gpurun_out/pytest_gpu.log
 timeout 600 python scripts/bench_scan.py --no-ref > gpurun_out/scan_rows.jsonl 2> gpurun_out/scan.err; echo "scan rc=$?"; cut -c1-330 gpurun_out/scan_rows.jsonl; tail -3 gpurun_out/scan.err
 timeout 600 python scripts/probe_band_argmin.py > gpurun_out/band_argmin.jsonl 2>&1; cat gpurun_out/band_argmin.jsonl
 M="sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active,sm__issue_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum,gpu__time_duration.sum,launch__registers_per_thread,l1tex__t_sector_hit_rate.pct"
-timeout 600 ncu --metrics $M --clock-control none -k regex:k_band -c 6 --csv --log-file gpurun_out/ncu_band.csv python scripts/bench_scan.py --no-ref --quick > gpurun_out/ncu_band.log 2>&1
+timeout 600 ncu --metrics $M --clock-control none -k regex:k_band -c 8 --csv --log-file gpurun_out/ncu_band.csv python scripts/probe_band_argmin.py > gpurun_out/ncu_band.log 2>&1
 timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 python - <<'PY'
 import json

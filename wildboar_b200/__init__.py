@@ -38,11 +38,11 @@ def get_include():
     raise FileNotFoundError("wb_cuda.h not found")
 
 
-from ._shim import device_count, get_precision, last_stats, library_path, set_devices, set_precision  # noqa: F401
+from ._shim import device_count, get_precision, last_stats, library_path, pinned_copy, set_devices, set_precision  # noqa: F401
 
 __all__ = [
     "pairwise_distance", "paired_distance", "argmin_distance", "check_metric",
     "pairwise_subsequence_distance", "paired_subsequence_distance", "subsequence_match", "paired_subsequence_match",
     "distance_profile", "argmin_subsequence_distance",
-    "get_include", "device_count", "set_devices", "set_precision", "get_precision", "last_stats", "library_path",
+    "get_include", "pinned_copy", "device_count", "set_devices", "set_precision", "get_precision", "last_stats", "library_path",
 ]

@@ -208,6 +208,16 @@ def result_array(shape):
     return np.empty(shape, dtype=np.float64)
 
 
+def pinned_copy(a):
+    """A C-contiguous float64 copy of `a` in page-locked memory (the library's pool, like the result arrays): inputs that
+    live there reach the device by asynchronous DMA at PCIe speed instead of through the driver's pageable staging.  Falls
+    back to an ordinary copy when no page-locked memory is to be had (or for arrays under 1 MB)."""
+    a = np.asarray(a, dtype=np.float64)
+    out = result_array(a.shape)
+    out[...] = a
+    return out
+
+
 def _dev_array(devs):
     return (C.c_int * len(devs))(*devs), len(devs)
 
