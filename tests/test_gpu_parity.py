@@ -500,3 +500,39 @@ def test_coop_engine_is_selected_for_small_problems_and_tall_bands(W, oracle):
     x, y = random_walks(10000, 512, 1)[:64], random_walks(10000, 512, 2)[:3000]
     W.pairwise_distance(x, y, metric="dtw", metric_params={"r": 0.1})
     assert W.last_stats()["engine"] == 2
+
+
+def test_argmin_cfg4_all_references_many_chunks(W, oracle):
+    """BASELINE configs[3] at its full reference count: 64 of the 20 000 queries against ALL 200 000 references (dtw,
+    r = 0.05, k = 1 and 3).  49 chunks of 4096 columns: the thresholds, the heap and the LB cascade's state are carried
+    across every chunk boundary; indices, distances and heap order must equal the oracle's sequential scan."""
+    q = random_walks(20000, 256, 3)[np.random.default_rng(7).choice(20000, 64, replace=False)]
+    refs = random_walks(200000, 256, 4)
+    for k in (1, 3):
+        idx, dist = W.argmin_distance(q, refs, k=k, metric="dtw", metric_params={"r": 0.05}, return_distance=True)
+        st = W.last_stats()
+        oi, od = oracle.argmin("dtw", q, refs, k=k, r=0.05, n_jobs=0)
+        _eq(idx, oi, f"cfg4 all refs k={k} idx")
+        _eq(dist, od, f"cfg4 all refs k={k} dist")
+        assert st["lb_kim_pruned"] + st["lb_keogh_pruned"] > 0.9 * 64 * 200000
+    # a non-DTW metric over many chunks (row-minimum maxima replayed): 16 queries x 20 000 references
+    q2, r2 = random_walks(16, 128, 5), random_walks(20000, 128, 6)
+    for metric in ("msm", "erp"):
+        idx, dist = W.argmin_distance(q2, r2, k=2, metric=metric, metric_params={"r": 0.05}, return_distance=True)
+        oi, od = oracle.argmin(metric, q2, r2, k=2, r=0.05, n_jobs=0)
+        _eq(idx, oi, metric + " idx")
+        _eq(dist, od, metric + " dist")
+
+
+def test_cfg5_full_length_random_entries(W, oracle):
+    """BASELINE configs[4] at full length: a 64-row share against all 2000 series of length 4096 (msm / twe / dtw, r = 0.05),
+    80 random entries per metric against the oracle -- the shipped engine per metric (strip for msm / twe at this pair count,
+    cooperative for dtw)."""
+    x, y = random_walks(2000, 4096, 1)[:64], random_walks(2000, 4096, 2)
+    rng = np.random.default_rng(11)
+    ii, jj = rng.integers(0, 64, 80), rng.integers(0, 2000, 80)
+    for metric, engine in (("msm", 2), ("twe", 2), ("dtw", 4)):
+        got = W.pairwise_distance(x, y, metric=metric, metric_params={"r": 0.05})
+        assert W.last_stats()["engine"] == engine, (metric, W.last_stats())
+        want = oracle.paired(metric, np.ascontiguousarray(y[jj]), np.ascontiguousarray(x[ii]), r=0.05, n_jobs=0)
+        _eq(got[ii, jj], want, "cfg5 full length " + metric)
