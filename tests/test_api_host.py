@@ -151,3 +151,15 @@ def test_package_installs_with_pip_and_binds_every_symbol(wb, tmp_path):
     env["PYTHONPATH"] = str(target)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(tmp_path), env=env)
     assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
+
+
+def test_pinned_helpers_degrade_to_ordinary_memory_without_a_device(wb):
+    """result_array / pinned_copy ask the library for page-locked memory and use ordinary numpy memory when there is none
+    (no GPU here): the values and dtype are what the caller gave, whatever memory they live in."""
+    from wildboar_b200 import _shim
+    a = np.arange(300000, dtype=np.float64).reshape(300, 1000)
+    b = wb.pinned_copy(a[:, ::2])            # non-contiguous input, > 1 MB
+    assert b.dtype == np.float64 and b.flags.c_contiguous and np.array_equal(b, a[:, ::2])
+    r = _shim.result_array((7, 9))
+    assert r.shape == (7, 9) and r.dtype == np.float64
+    assert _shim.lib().wb_cuda_host_alloc(0) in (None, 0) or wb.device_count() > 0
