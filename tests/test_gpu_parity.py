@@ -268,6 +268,12 @@ def test_multi_gpu_row_sharding_is_transparent(W, oracle):
             i, d = W.argmin_distance(x, y, k=3, metric=metric, metric_params={"r": 0.2}, return_distance=True)
             oi, od = oracle.argmin(metric, x, y, k=3, r=0.2, n_jobs=0)
             _eq(i, oi, metric + " argmin idx"); _eq(d, od, metric + " argmin dist")
+        # a self join large enough for the multi-threaded host mirror (several devices: the lower triangle is transposed on
+        # the host, destination block rows dealt out over threads), asymmetric metric
+        X = random_walks(1500, 24, 33)
+        got = W.pairwise_distance(X, metric="msm", metric_params={"r": 0.3})
+        _eq(got, oracle.pairwise("msm", X, None, r=0.3, n_jobs=0), "msm self 1500, multi-device")
+        assert np.array_equal(got, got.T)
     finally:
         W.set_devices([0])
 
@@ -536,3 +542,35 @@ def test_cfg5_full_length_random_entries(W, oracle):
         assert W.last_stats()["engine"] == engine, (metric, W.last_stats())
         want = oracle.paired(metric, np.ascontiguousarray(y[jj]), np.ascontiguousarray(x[ii]), r=0.05, n_jobs=0)
         _eq(got[ii, jj], want, "cfg5 full length " + metric)
+
+
+def test_concurrent_calls_from_several_threads(W, oracle):
+    """The C ABI is re-entrant: every call leases its own device context (streams, events) and the page-locked pool and the
+    context free list are shared under a lock.  Four Python threads (the GIL is released inside the library) run different
+    metrics at once; every result must equal the oracle."""
+    import threading
+    x, y = random_walks(150, 100, 101), random_walks(400, 100, 102)
+    jobs = [("dtw", 0.1), ("msm", 0.2), ("twe", 0.1), ("erp", 0.3), ("lcss", 0.2), ("adtw", 0.1), ("wdtw", 0.2), ("edr", 0.1)]
+    want = {m: oracle.pairwise(m, x, y, r=r, n_jobs=0) for m, r in jobs}
+    got, errs = {}, []
+
+    def work(m, r):
+        try:
+            for _ in range(3):
+                got[m] = W.pairwise_distance(x, y, metric=m, metric_params={"r": r})
+                i, d = W.argmin_distance(x[:20], y, k=2, metric=m, metric_params={"r": r}, return_distance=True)
+                got[m + "|argmin"] = (i, d)
+        except Exception as e:  # noqa: BLE001
+            errs.append((m, repr(e)))
+
+    threads = [threading.Thread(target=work, args=j) for j in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs, errs
+    for m, r in jobs:
+        _eq(got[m], want[m], "concurrent " + m)
+        oi, od = oracle.argmin(m, x[:20], y, k=2, r=r, n_jobs=0)
+        _eq(got[m + "|argmin"][0], oi, "concurrent argmin idx " + m)
+        _eq(got[m + "|argmin"][1], od, "concurrent argmin dist " + m)

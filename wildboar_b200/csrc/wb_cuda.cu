@@ -159,11 +159,21 @@ struct CtxLease {
 // expensive (~0.3 ms per MB), so released blocks are kept in a pool (bounded by WILDBOAR_CUDA_PINNED_POOL_MB,
 // default 4096) and handed out again to later calls of similar size.
 // ------------------------------------------------------------------------------------------
-static std::mutex g_pin_mu;
-static std::map<void*, size_t> g_pin_live;         // blocks handed out: capacity
-static std::multimap<size_t, void*> g_pin_free;    // pooled blocks by capacity
-static size_t g_pin_pooled = 0;
-static size_t g_pin_pending = 0;                   // large blocks being page-locked in the background
+// (the pool lives in a heap object that is never destroyed: a background page-locking thread may still hold the mutex
+// while the process runs its static destructors)
+struct PinPool {
+  std::mutex mu;
+  std::map<void*, size_t> live;         // blocks handed out: capacity
+  std::multimap<size_t, void*> free_;   // pooled blocks by capacity
+  size_t pooled = 0;
+  size_t pending = 0;                   // large blocks being page-locked in the background
+};
+static PinPool& pin_pool() { static PinPool* p = new PinPool; return *p; }
+#define g_pin_mu (pin_pool().mu)
+#define g_pin_live (pin_pool().live)
+#define g_pin_free (pin_pool().free_)
+#define g_pin_pooled (pin_pool().pooled)
+#define g_pin_pending (pin_pool().pending)
 static size_t pin_pool_cap() {
   static size_t cap = [] {
     const char* e = getenv("WILDBOAR_CUDA_PINNED_POOL_MB");
