@@ -312,6 +312,20 @@ template <> struct StripCfg<TwePolicy> { static constexpr int WL = 10, NRL = 6, 
 template <> struct StripCfg<MsmPolicy> { static constexpr int WL = 10, NRL = 6, NWL = 12, WT = 8, NRT = 4, NWT = 12; };
 template <> struct StripCfg<EdrPolicy> { static constexpr int WL = 10, NRL = 6, NWL = 12, WT = 8, NRT = 4, NWT = 16; };
 
+// Launch shape for fewer warp tasks than resident warp slots.  Filling whole CTAs one after the other (grid =
+// ceil(tasks / warps per CTA)) leaves the SMs unevenly loaded -- cfg1: 1250 tasks in 157 CTAs of 8 warps puts 16 warps on
+// nine SMs and 8 on the others, and the launch lasts as long as the fullest SM.  Instead: as few CTA layers as needed
+// (grid = a multiple of the SM count, the block scheduler deals CTAs round-robin over the SMs) and only as many warps per
+// CTA as the tasks need, so every SM gets the same number of warps (+-1).
+static void balance_launch(long long ntasks, int sms, int per_sm, int max_warps, long long* grid, int* warps) {
+  const long long slots = (long long)sms * per_sm * max_warps;
+  if (ntasks >= slots) { *grid = (long long)sms * per_sm; *warps = max_warps; return; }
+  if (ntasks <= sms) { *grid = std::max<long long>(ntasks, 1); *warps = 1; return; }
+  const long long layers = std::min<long long>(per_sm, (ntasks + (long long)sms * max_warps - 1) / ((long long)sms * max_warps));
+  *grid = (long long)sms * layers;
+  *warps = (int)std::min<long long>(max_warps, (ntasks + *grid - 1) / *grid);
+}
+
 template <class M, int W, int NT, int MINB, bool EA, int NR, bool GRING>
 static int launch_strip_cfg(Workspace& ws, KArgsT<typename M::real> a, const M& m, int nwarps, int sms, size_t smem_cap, wb_stats* cfg) {
   using F = typename M::real;
@@ -327,7 +341,10 @@ static int launch_strip_cfg(Workspace& ws, KArgsT<typename M::real> a, const M& 
   if (per_sm < 1) { set_err("strip kernel does not fit on an SM"); return 1; }
   per_sm = std::min(per_sm, MINB);
   long long grid = (long long)sms * per_sm;
-  if (a.ntasks < grid * nwarps) grid = std::max<long long>(1, (a.ntasks + nwarps - 1) / nwarps);
+  if (a.ntasks < grid * nwarps) {
+    balance_launch(a.ntasks, sms, per_sm, nwarps, &grid, &nwarps);
+    if (!GRING) smem = (size_t)nwarps * per_warp;
+  }
   bool window_set = false;
   if (GRING) {
     F* ring = nullptr;
@@ -376,6 +393,8 @@ static int launch_strip(Workspace& ws, const KArgsT<typename M::real>& a, const 
   }
   // (a deeper in-thread wavefront, NR = 4, for launches with fewer warp tasks than warp slots was measured on cfg1:
   // 0.175 ms against 0.163 ms with NR = 2 -- profiles/r02e_engines_small.jsonl -- and dropped)
+  static const int narrow_w = [] { const char* e = getenv("WILDBOAR_CUDA_STRIP_NARROW_W"); return e ? atoi(e) : 0; }();  // tuning knob
+  if (narrow_w == 4 && a.g.H >= 8) return launch_strip_cfg<M, 4, 256, 2, EA, 2, false>(ws, a, m, 8, sms, smem_cap, cfg);
   if (a.g.H >= 16 || a.g.H < 8) return launch_strip_cfg<M, 8, 256, 2, EA, 2, false>(ws, a, m, 8, sms, smem_cap, cfg);
   return launch_strip_cfg<M, 4, 256, 2, EA, 2, false>(ws, a, m, 8, sms, smem_cap, cfg);
 }
@@ -401,11 +420,11 @@ static int launch_coop_cfg(Workspace& ws, KArgsT<typename M::real> a, const M& m
   WB_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, 0));
   if (per_sm < 1) { set_err("cooperative kernel does not fit on an SM"); return 1; }
   const long long ntasks = (a.npairs * G + 31) / 32;
-  long long grid = (long long)sms * per_sm;
-  const long long need = (ntasks * 32 + NT - 1) / NT;
-  grid = std::max<long long>(1, std::min(grid, need));
-  if (cfg) { cfg->strip_w = W; cfg->strip_nr = G; cfg->strip_warps = NT / 32; cfg->strip_gring = 0; }
-  kern<<<(unsigned)grid, NT, 0, ws.stream>>>(a, m, G, lay);
+  long long grid = 0;
+  int nwarps = NT / 32;
+  balance_launch(ntasks, sms, per_sm, NT / 32, &grid, &nwarps);
+  if (cfg) { cfg->strip_w = W; cfg->strip_nr = G; cfg->strip_warps = nwarps; cfg->strip_gring = 0; }
+  kern<<<(unsigned)grid, nwarps * 32, 0, ws.stream>>>(a, m, G, lay);
   WB_CK(cudaGetLastError());
   return 0;
 }
