@@ -37,7 +37,9 @@ struct KArgsT {
   long long thr_div;  //   one per (x row, group of thr_div consecutive y series), e.g. per (subsequence, sample) in a scan
   unsigned long long* counter;  // persistent-grid work counter (zeroed before launch)
   long long ntasks;   // warp tasks
-  long long nyb;      // ceil(ny / 32)
+  long long nyb;      // ceil(ny / lt)
+  int lt;             // lanes of a warp task that carry a pair (32; fewer when there are not enough pairs to give every
+                      //   resident warp slot a full task: more, emptier warps hide latency that fewer, fuller ones cannot)
   int mode;
   long long row0;     // PM_SELF: global index of local x row 0 (row-sharded self join)
   int mirror;         // PM_SELF: also write element (j, i) of the full n x n matrix that `out` is a row block of (`out` = row
@@ -79,10 +81,12 @@ __device__ __forceinline__ bool decode_task(const A& a, long long t, int lane, l
     i = p.x; j = p.y;
     return true;
   }
+  const int lt = a.lt;
+  const int sub = lane < lt ? lane : lane - lt * (lane / lt);  // surplus lanes repeat a pair of the task (their results are dropped)
   if (a.mode == PM_PAIRED) {
-    i = t * 32 + lane;
-    valid = i < a.nx;
-    if (!valid) i = a.nx - 1;
+    i = t * lt + sub;
+    valid = lane < lt && i < a.nx;
+    if (i >= a.nx) i = a.nx - 1;
     j = i;
     return true;
   }
@@ -91,12 +95,12 @@ __device__ __forceinline__ bool decode_task(const A& a, long long t, int lane, l
   // touching every y row at once (41 MB for cfg3, which the boundary buffers evict from L2)
   const long long jb = t / a.nx;
   i = t - jb * a.nx;
-  j = jb * 32 + lane;
-  valid = j < a.ny;
-  if (!valid) j = a.ny - 1;
+  j = jb * lt + sub;
+  valid = lane < lt && j < a.ny;
+  if (j >= a.ny) j = a.ny - 1;
   if (a.mode == PM_SELF) {
     const long long ig = i + a.row0;
-    if (jb * 32 + 31 <= ig) return false;
+    if (jb * lt + (lt - 1) <= ig) return false;
     if (j <= ig) valid = false;
   }
   return true;

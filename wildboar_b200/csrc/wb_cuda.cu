@@ -342,6 +342,18 @@ static int launch_strip_cfg(Workspace& ws, KArgsT<typename M::real> a, const M& 
   per_sm = std::min(per_sm, MINB);
   long long grid = (long long)sms * per_sm;
   if (a.ntasks < grid * nwarps) {
+    // (WILDBOAR_CUDA_TASK_LANES = lt < 32 puts fewer pairs into a warp task -- more, emptier warps.  Measured on cfg1,
+    // profiles/r02r_task_lanes_cfg1.txt: lt = 32 0.132 ms, 24 0.164 ms, 16 0.236 ms: the launch is bound by instructions
+    // issued, not by latency, so the knob stays a knob.)
+    if (a.mode == PM_PAIRWISE || a.mode == PM_SELF || a.mode == PM_PAIRED) {
+      static const int lt_env = [] { const char* e = getenv("WILDBOAR_CUDA_TASK_LANES"); return e ? atoi(e) : 0; }();
+      if (lt_env >= 1 && lt_env < 32) {
+        const long long n_in_task_dim = (a.mode == PM_PAIRED) ? a.nx : a.ny;
+        a.lt = lt_env;
+        a.nyb = (a.ny + lt_env - 1) / lt_env;
+        a.ntasks = ((a.mode == PM_PAIRED) ? 1 : a.nx) * ((n_in_task_dim + lt_env - 1) / lt_env);
+      }
+    }
     balance_launch(a.ntasks, sms, per_sm, nwarps, &grid, &nwarps);
     if (!GRING) smem = (size_t)nwarps * per_warp;
   }
@@ -594,6 +606,7 @@ static int launch_dp_t(Workspace& ws, const DeviceInfo& di, const DpCall& c, lon
   a.mode = c.mode; a.row0 = c.row0 + r0 - c0; a.mirror = c.mirror;
   a.list = c.list; a.list_len = c.list_len;
   a.acc = c.acc; a.div = c.div;
+  a.lt = 32;
   a.nyb = (ncols + 31) / 32;
   a.yil = 0;
   a.ntasks = (c.mode == PM_PAIRED) ? (nrows + 31) / 32 : nrows * a.nyb;
