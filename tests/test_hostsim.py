@@ -7,6 +7,12 @@ import sim
 from util import METRICS
 
 
+def _stable_hash(name):
+    """Python's hash() of a str changes from process to process (PYTHONHASHSEED): the seeds of these sweeps must not."""
+    import zlib
+    return zlib.crc32(name.encode())
+
+
 def _params(oracle, metric, **kw):
     op = oracle.make_params(metric, **kw)
     return sim.WbParams(op.r, op.g, op.p, op.c, op.epsilon, op.penalty, op.stiffness, 0, 0)
@@ -14,7 +20,7 @@ def _params(oracle, metric, **kw):
 
 @pytest.mark.parametrize("metric", METRICS)
 def test_engines_match_oracle(oracle, metric):
-    rng = np.random.default_rng(hash(metric) % 1000)
+    rng = np.random.default_rng(_stable_hash(metric) % 1000)
     mid = oracle.METRIC_IDS[metric]
     checked = 0
     for trial in range(40):
@@ -186,7 +192,7 @@ def test_scaled_subsequence_scan_scheme_matches_oracle(oracle, metric, mp):
 def test_band_engine_matches_rowscan_and_oracle(oracle, metric):
     """The band-register engine (engine_band.cuh: previous band row in registers) returns the row-scan engine's value AND
     its row-minimum maximum, bit for bit, with and without abandoning, for every metric and every narrow-band geometry."""
-    rng = np.random.default_rng(100 + hash(metric) % 1000)
+    rng = np.random.default_rng(100 + _stable_hash(metric) % 1000)
     mid = oracle.METRIC_IDS[metric]
     checked = abandoned = 0
     for trial in range(120):
@@ -266,7 +272,7 @@ def test_subsequence_scan_with_head_then_abandon_matches_oracle(oracle, metric, 
 def test_interleaved_engine_variants_match_plain(oracle, metric):
     """The YS = 32 instantiations of the band and row-scan engines (y read from an interleaved group, element stride 32)
     return exactly what the plain ones return, value and row-minimum maximum."""
-    rng = np.random.default_rng(200 + hash(metric) % 1000)
+    rng = np.random.default_rng(200 + _stable_hash(metric) % 1000)
     mid = oracle.METRIC_IDS[metric]
     checked = 0
     for trial in range(40):
@@ -292,7 +298,7 @@ def test_coop_engine_matches_oracle(oracle, metric):
     """All 11 metrics x equal / unequal lengths x windows x (W, G) layouts, incl. the layouts the library ships (W = 8 and
     W = 13): masked rows (start-up, drain, band outside the matrix, row 0 / column 0 rules, MSM's stale left edge and extra
     cell) and the unrolled fast blocks with rotating column registers must reproduce the oracle bit for bit."""
-    rng = np.random.default_rng(1000 + hash(metric) % 1000)
+    rng = np.random.default_rng(1000 + _stable_hash(metric) % 1000)
     mid = oracle.METRIC_IDS[metric]
     checked = 0
     for trial in range(36):
