@@ -113,3 +113,30 @@ def test_pivot_partition_keeps_the_operand_order_of_the_loop_it_replaces(wb, ora
     # ties: the first pivot wins (strict `<`)
     Xt = np.vstack([X[:1], X[:1], X[1:5]])
     assert np.array_equal(partition_pivots(Xt, [2, 3, 4], [0, 1], metric=metric, metric_params=mp), np.zeros(3, dtype=np.intp))
+
+
+# ---- MDS (wildboar_b200.manifold.MDS; reference: src/wildboar/distance/_manifold.py) ----
+# golden vectors: reference embeddings for seeded random walks (generated in the build container with oracle/_ref:
+# wd.MDS(n_components, metric_mds, n_init=2, max_iter=60, random_state, metric, metric_params).fit_transform(X))
+@pytest.mark.gpu
+def test_mds_matches_reference_golden(wb):
+    import os
+    from wildboar_b200.manifold import MDS
+    wb.set_devices([0])
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mds_golden.npz")
+    with np.load(path) as z:
+        g = {k: z[k] for k in z.files}
+    for c, (metric, mp, nc, mm, seed) in enumerate(ast.literal_eval(str(g["meta_cases"]))):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            est = MDS(n_components=nc, metric_mds=mm, n_init=2, max_iter=60, random_state=seed, metric=metric, metric_params=mp)
+            emb = est.fit_transform(g[f"{c}|X"])
+        assert np.array_equal(emb, g[f"{c}|emb"]), (c, metric)
+        assert est.mds_.stress_ == g[f"{c}|stress"]
+
+
+def test_mds_validation(wb):
+    from wildboar_b200.manifold import MDS
+    for kw in (dict(n_components=0), dict(metric="euclidean"), dict(metric_mds=1), dict(eps=-1.0), dict(n_init=0)):
+        with pytest.raises(ValueError):
+            MDS(**kw).fit(np.zeros((5, 8)))
