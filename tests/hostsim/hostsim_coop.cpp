@@ -67,9 +67,10 @@ extern "C" int hostsim_coop_pair(int W, int G, int metric, const wb_params* p, c
     using MM = decltype(m);
     m.begin_pair(pc);
     switch (W) {
-      // (W, U): the shipped layouts (8, 8) and (13, 4) plus odd ones that stress the shifting
+      // (W, U): the shipped layouts (8, 8), (13, 4) and (4, 8) plus odd ones that stress the shifting
       case 3: rc = coop_host_pair<MM, 3, 1>(g, m, G, x, y, out); break;
-      case 4: rc = coop_host_pair<MM, 4, 5>(g, m, G, x, y, out); break;
+      case 4: rc = coop_host_pair<MM, 4, 8>(g, m, G, x, y, out); break;
+      case 104: rc = coop_host_pair<MM, 4, 5>(g, m, G, x, y, out); break;
       case 8: rc = coop_host_pair<MM, 8, 8>(g, m, G, x, y, out); break;
       case 13: rc = coop_host_pair<MM, 13, 4>(g, m, G, x, y, out); break;
       case 108: rc = coop_host_pair<MM, 8, 3>(g, m, G, x, y, out); break;

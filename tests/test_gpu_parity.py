@@ -456,7 +456,7 @@ def test_dim_mean_single_output_follows_numpy_pairwise_summation(W, oracle, n_di
 
 # ---- round 2: cooperative engine (a group of lanes per pair, band row in registers, warp shuffles) ----
 COOP_SHAPES = [(37, 53, 150, 150, 0.1), (20, 70, 140, 140, 1.0), (9, 40, 512, 512, 0.1), (30, 45, 50, 77, 0.2), (12, 33, 90, 61, 0.3),
-               (5, 11, 600, 600, 0.02)]
+               (5, 11, 600, 600, 0.02), (14, 25, 96, 96, 0.1), (8, 19, 200, 200, 0.05)]   # the last two: H = 17 / 19 -> the W = 4 layout
 
 
 @pytest.mark.parametrize("metric", METRICS)

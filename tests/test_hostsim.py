@@ -323,7 +323,7 @@ def test_coop_engine_matches_oracle(oracle, metric):
         x = np.cumsum(rng.standard_normal(Tx)); y = np.cumsum(rng.standard_normal(Ty))
         ref = oracle.pairwise(metric, x, y.reshape(1, -1), r=r)[0, 0]
         p = _params(oracle, metric, r=r)
-        for W, G in [(3, 32), (4, 8), (4, 32), (8, 4), (8, 16), (8, 32), (13, 32), (108, 16)]:
+        for W, G in [(3, 32), (4, 8), (4, 32), (8, 4), (8, 16), (8, 32), (13, 32), (108, 16), (104, 16)]:
             rc, v = sim.coop_pair(W, G, mid, p, x, y)
             if rc == 1:
                 continue  # no exact tiling of this band with (W, G)

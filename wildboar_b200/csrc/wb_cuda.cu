@@ -411,13 +411,13 @@ static int launch_strip(Workspace& ws, const KArgsT<typename M::real>& a, const 
   return launch_strip_cfg<M, 4, 256, 2, EA, 2, false>(ws, a, m, 8, sms, smem_cap, cfg);
 }
 
-// Cooperative engine (engine_coop.cuh, k_coop): lanes-per-pair G and cells-per-lane W for a geometry.  Two
-// instantiations: W = 8 (256 threads, two CTAs per SM) for bands up to 256 coordinates and W = 13 (384 threads, one CTA)
-// up to 416; G = the smallest power of two that holds the layout.  Returns false when no layout tiles the band exactly.
+// Cooperative engine (engine_coop.cuh, k_coop): lanes-per-pair G and cells-per-lane W for a geometry.  Three
+// instantiations: W = 8 (256 threads, two CTAs per SM) for bands up to 256 coordinates, W = 13 (384 threads, one CTA)
+// up to 416, W = 4 for the narrow bands the other two cannot tile; G = the smallest power of two that holds the layout.  Returns false when no layout tiles the band exactly.
 template <class M>
 static bool coop_pick(const Geom& g, int* W, int* G, CoopLayout* lay) {
-  const int ws[2] = {8, 13};
-  for (int q = 0; q < 2; ++q) {
+  const int ws[3] = {8, 13, 4};  // W = 4 tiles every band of 12 .. 128 coordinates (the layouts of 8 and 13 leave gaps below 49)
+  for (int q = 0; q < 3; ++q) {
     for (int gg = 2; gg <= 32; gg *= 2) {
       if (coop_supported<M>(g, ws[q], gg) && coop_layout(g, ws[q], gg, lay)) { *W = ws[q]; *G = gg; return true; }
     }
@@ -652,6 +652,7 @@ static int launch_dp_t(Workspace& ws, const DeviceInfo& di, const DpCall& c, lon
           engine = 4;
           a.npairs = npairs;
           rc = (cw == 8) ? launch_coop_cfg<M, 8, 8, 256, 2>(ws, a, m, cg, lay, di.sms, stats)
+             : (cw == 4) ? launch_coop_cfg<M, 4, 8, 256, 2>(ws, a, m, cg, lay, di.sms, stats)
                          : launch_coop_cfg<M, 13, 4, 384, 1>(ws, a, m, cg, lay, di.sms, stats);
           return;
         }
