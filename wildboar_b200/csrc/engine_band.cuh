@@ -80,8 +80,11 @@ WB_HD typename M::real band_pair(const Geom& g, const M& m, const typename M::re
   // registers (cell k of row r reads cols[1 + k + r]; after the block the array moves down by NRB and NRB new columns
   // enter) and the per-diagonal values as loop invariants -- the generic row below re-derives a column context from two
   // loads per cell and tests four predicates per cell (ncu, profiles/r01m_ncu_band.md: 50 instructions per msm cell).
+  // (a separate instantiation: the blocked rows need ~2x the registers.  HB = 32 was tried for the policies whose column
+  // context is a single value (lcss, edr), two rows per block: 1.6x faster on 400 x 400 x 128, 1.4x SLOWER on
+  // 1000 x 5000 x 140 -- profiles/r02v_band_blocked_hb32_light.jsonl -- and is not used)
+  constexpr bool kBlocked = BLK && HB <= 16;
   constexpr int NRB = 4;
-  constexpr bool kBlocked = BLK && HB <= 16;  // (a separate instantiation: the blocked rows need ~2x the registers)
   constexpr int NCB = kBlocked ? HB + NRB : 1;
   typename M::Col cols[NCB];
   typename M::Dv dvs[kBlocked ? HB : 1];
