@@ -12,8 +12,18 @@ full pass over the rank's row block.
     torchrun --nproc-per-node N ... bench.py --gpus N ...         # one rank per GPU
 
 JSON line keys follow the driver's contract; additions: `roofline` (FP64-ALU bound, measured
-peak from the in-run DADD issue microbenchmark), `cpu_baseline` (the reference's Cython build
-from oracle/_ref on the host cores, or the C oracle port when that build is absent).
+peak from the in-run DADD issue microbenchmark; `traffic` read from the committed ncu capture in
+profiles/traffic.json), `cpu_baseline` (the reference's Cython build from oracle/_ref on the host
+cores, best of 3, or the C oracle port when that build is absent), and -- OUTSIDE the timed
+regions, requested by the round-1 review --
+  `parity`        300 random entries of every rank's full-size end-to-end result against the CPU oracle
+  `configs`       BASELINE configs[0], [1], [3], [4]: kernel / e2e GCUPS, roofline fraction and an oracle
+                  spot check of the full-size result each (cfg4 / cfg5: rank r computes the r-th eighth)
+  `fp64_fma`      kernel GCUPS of the optional fused-multiply-add mode beside the bit-exact headline
+  `e2e_inprocess` (N > 1) the library's OWN multi-device path: rank 0 drives all N GPUs from one process
+                  and its matrix is compared (CRC-32 per row block) with the slabs the ranks computed
+The oracle is used here only as the CHECKER of those spot checks and as the thing timed in the
+cpu_baseline / `--impl reference` arm; nothing on the measured path touches it.
 """
 import argparse
 import json
