@@ -32,7 +32,7 @@ def get_include():
     uses ``include/`` at the repository root)."""
     import os
     here = os.path.dirname(os.path.abspath(__file__))
-    for d in (os.path.join(here, "include"), os.path.join(here, "..", "include")):
+    for d in (os.path.join(here, "..", "include"), os.path.join(here, "include")):  # a source checkout's header wins over a build copy
         if os.path.isfile(os.path.join(d, "wb_cuda.h")):
             return os.path.abspath(d)
     raise FileNotFoundError("wb_cuda.h not found")
