@@ -397,13 +397,19 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
 
   double *tau = nullptr, *thr = nullptr, *hval = nullptr, *dbuf = nullptr, *mbuf = nullptr, *lbuf = nullptr;
   long long* hidx = nullptr; int* hn = nullptr;
+  // Columns per chunk.  The thresholds a chunk is pruned with are those at its start, so the FIRST chunks should be small
+  // (they run dense or nearly so) and the later ones large (few launches: with one query every chunk is ~6 launches of
+  // almost no work).  The chunk grows 4x per step from 1024 columns up to C = min(32768, 4 Mi / nq) -- nq * C values per
+  // buffer; for the cfg4 share (2500 queries) that is 1024 then 1600, as before; for one query 1024, 4096, 16384, 32768, ...
   long long C = (4LL << 20) / std::max<long long>(nq, 1);
-  C = std::max<long long>(32, std::min<long long>(4096, (C / 32) * 32));
-  if (const char* e = getenv("WILDBOAR_CUDA_ARGMIN_CHUNK")) {  // tuning / test knob: columns per chunk
+  C = std::max<long long>(32, std::min<long long>(32768, (C / 32) * 32));
+  long long c_first = std::min<long long>(C, 1024);
+  if (const char* e = getenv("WILDBOAR_CUDA_ARGMIN_CHUNK")) {  // tuning / test knob: fixed columns per chunk
     const long long v = atoll(e);
-    if (v >= 32) C = (v / 32) * 32;
+    if (v >= 32) { C = (v / 32) * 32; c_first = C; }
   }
   C = std::min<long long>(C, ((ny + 31) / 32) * 32);
+  c_first = std::min(c_first, C);
   if (ws.alloc(&tau, (size_t)nq) || ws.alloc(&thr, (size_t)nq) || ws.alloc(&hval, (size_t)nq * k) ||
       ws.alloc(&hidx, (size_t)nq * k) || ws.alloc(&hn, (size_t)nq) || ws.alloc(&dbuf, (size_t)nq * C)) return 1;
   if ((!dtwfam || adtw_neg) && ws.alloc(&mbuf, (size_t)nq * C)) return 1;
@@ -435,8 +441,11 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, st);
   int rc = 0;
-  for (long long c0 = 0; c0 < ny && !rc; c0 += C) {
-    const long long nc = std::min(C, ny - c0);
+  long long c_cur = c_first;
+  for (long long c0 = 0; c0 < ny && !rc; ) {
+    const long long nc = std::min(c_cur, ny - c0);
+    const long long c0_next = c0 + nc;
+    c_cur = std::min(C, c_cur * 4);
     k_thr_raw<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(tau, nq, kind, scale, thr);
     if (c.degenerate) {
       // ddtw with T < 3: eadistance() returns False for every pair (EL:3297-3298)
@@ -470,6 +479,7 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
     const long long blocks = std::max<long long>(1, std::min<long long>((nq + 3) / 4, 148 * 16));
     k_replay<<<(unsigned)blocks, 128, 0, st>>>(ra);
     if (stats) stats->launches += 2;
+    c0 = c0_next;
   }
   cudaEventRecord(e1, st);
   if (!rc) {
