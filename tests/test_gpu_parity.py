@@ -574,3 +574,23 @@ def test_concurrent_calls_from_several_threads(W, oracle):
         oi, od = oracle.argmin(m, x[:20], y, k=2, r=r, n_jobs=0)
         _eq(got[m + "|argmin"][0], oi, "concurrent argmin idx " + m)
         _eq(got[m + "|argmin"][1], od, "concurrent argmin dist " + m)
+
+
+def test_fitted_set_keeps_the_cascade_operands_between_calls(W, oracle):
+    """A device-resident reference set builds the reference-side operands of the LB cascade once (first argmin call) and
+    reuses them; a call with another window must not be served from that cache.  Every call equals the oracle's scan."""
+    from wildboar_b200 import _shim
+    from wildboar_b200.distance import DtwMetric
+    refs = random_walks(6000, 96, 121)
+    fit = _shim.FittedSet(refs.reshape(6000, 1, 96), devices=[0])
+    try:
+        for r, seed in ((0.05, 1), (0.05, 2), (0.2, 3), (0.05, 4), (0.2, 5)):
+            q = random_walks(40, 96, 130 + seed)
+            m = DtwMetric(r=r)
+            idx, dist = _shim.argmin_fitted(m.metric_id, m._params(), q, fit, 3, use_device_lb=True)
+            oi, od = oracle.argmin("dtw", q, refs, k=3, r=r, n_jobs=0)
+            _eq(idx, oi, f"fitted argmin r={r} call {seed} idx")
+            _eq(dist, od, f"fitted argmin r={r} call {seed} dist")
+            assert W.last_stats()["lb_kim_pruned"] + W.last_stats()["lb_keogh_pruned"] > 0
+    finally:
+        fit.close()

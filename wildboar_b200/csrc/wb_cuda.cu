@@ -758,6 +758,8 @@ struct wb_fitted {
   int64_t n, nd, T;
   std::vector<int> devs;
   std::vector<double*> ptr;
+  // per device: the reference-side operands of argmin's LB cascade, built on first use (argmin.cuh, LbCascCache)
+  mutable std::deque<wb::LbCascCache> casc;
 };
 namespace wb {
 
@@ -861,6 +863,7 @@ static int device_worker(const HostJob& J, int dev, int64_t lo, int64_t hi, wb_s
         c.ea = 1;
         if ((rc = prepare_operands(ws, c))) break;
         ArgminIo io;
+        if (J.fit) for (size_t q = 0; q < J.fit->devs.size() && q < J.fit->casc.size(); ++q) if (J.fit->devs[q] == dev) io.casc_cache = &J.fit->casc[q];
         io.k = J.k; io.lower_bound = J.lower_bound ? J.lower_bound + lo * J.ny : nullptr; io.lb_ld = J.ny;
         io.out_idx = J.out_idx + lo * J.k; io.out_dist = J.out + lo * J.k; io.use_device_lb = J.use_device_lb;
         rc = run_argmin(ws, di, c, io, &stats,
@@ -2361,6 +2364,7 @@ int wb_cuda_fit(const double* y, int64_t ny, int64_t n_dims, int64_t Ty, int64_t
       cudaGetLastError(); cudaStreamDestroy(st); set_err("out of device memory for the fitted set"); rc = 1; break;
     }
     f->ptr.push_back(p);
+    f->casc.emplace_back();
     for (int64_t k = 0; k < n_dims && !rc; ++k) rc = h2d_rows(p + k * ny * Ty, y + k * y_dim_stride, ny, Ty, y_stride, st);
     if (!rc && cudaStreamSynchronize(st) != cudaSuccess) { set_err("upload of the fitted set failed"); rc = 1; }
     cudaStreamDestroy(st);
@@ -2375,7 +2379,12 @@ void wb_cuda_fit_free(wb_fitted* f) {
   if (!f) return;
   for (size_t q = 0; q < f->ptr.size(); ++q) {
     // every library call synchronises before it returns, so no work is pending on the set
-    if (cudaSetDevice(f->devs[q]) == cudaSuccess) { cudaFreeAsync(f->ptr[q], 0); }
+    if (cudaSetDevice(f->devs[q]) == cudaSuccess) {
+      cudaFreeAsync(f->ptr[q], 0);
+      if (q < f->casc.size() && f->casc[q].envT) {
+        cudaFreeAsync(f->casc[q].envT, 0); cudaFreeAsync(f->casc[q].yvT, 0); cudaFreeAsync(f->casc[q].y0, 0); cudaFreeAsync(f->casc[q].yL, 0);
+      }
+    }
   }
   delete f;
 }
