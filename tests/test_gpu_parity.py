@@ -594,3 +594,92 @@ def test_fitted_set_keeps_the_cascade_operands_between_calls(W, oracle):
             assert W.last_stats()["lb_kim_pruned"] + W.last_stats()["lb_keogh_pruned"] > 0
     finally:
         fit.close()
+
+
+@pytest.mark.parametrize("metric,params", [("dtw", {"r": 0.1}), ("wdtw", {"r": 0.2, "g": 0.1}), ("adtw", {"r": 0.1, "p": 0.5})])
+def test_argmin_pipelined_reference_upload(W, oracle, metric, params, monkeypatch):
+    """Host-resident references are uploaded piece by piece while the scan is running (run_argmin / ensure_refs): tiny
+    pieces and tiny chunks force dozens of pieces, with chunk and piece boundaries that do not line up; strided rows
+    take the 2-D copy.  Results must equal the sequential scan and the all-at-once upload."""
+    q, refs_full = random_walks(23, 96, 61), random_walks(1100, 200, 62)
+    refs = refs_full[:, 50:146]            # rows 200 elements apart: a strided second operand
+    assert not refs.flags.c_contiguous
+    refs_c = np.ascontiguousarray(refs)
+    oi, od = oracle.argmin(metric, q, refs_c, k=3, n_jobs=0, **params)
+    monkeypatch.setenv("WILDBOAR_CUDA_ARGMIN_CHUNK", "96")
+    for kb, y in (("0", refs_c), ("8", refs_c), ("8", refs), ("30", refs_c), ("1", refs_c)):
+        monkeypatch.setenv("WILDBOAR_CUDA_PIPED_UPLOAD_KB", kb)
+        for lb in (True, False):
+            idx, dist = W.argmin_distance(q, y, k=3, metric=metric, metric_params=params, return_distance=True, device_lower_bound=lb)
+            _eq(idx, oi, f"{metric} piece={kb} KB cascade={lb} idx"); _eq(dist, od, f"{metric} piece={kb} KB cascade={lb} dist")
+
+
+def test_argmin_threshold_seeding_is_exact(W, oracle, monkeypatch):
+    """k = 1: the thresholds are seeded with the exact distance to sketch-nearest candidates (run_argmin / k_seed_candidates).
+    The seed only removes pairs that cannot be the minimum; ties must still resolve to the FIRST index, the candidate
+    itself must survive, and k > 1 must not be seeded (heap order)."""
+    monkeypatch.setenv("WILDBOAR_CUDA_SEED_MIN", "256")
+    monkeypatch.setenv("WILDBOAR_CUDA_ARGMIN_CHUNK", "96")
+    q, refs = random_walks(70, 128, 71), random_walks(1500, 128, 72)
+    refs[1200] = q[3]; refs[40] = q[3]; refs[700] = q[3]       # the same exact match three times: index 40 wins
+    refs[1499] = q[69]                                          # exact match in the last column
+    refs[900] = refs[17]; refs[18] = refs[17]                   # duplicated references: ties for whoever is nearest to them
+    q[5] = refs[17] + 1e-3
+    for r in (0.1, 0.02, 1.0):
+        oi, od = oracle.argmin("dtw", q, refs, k=1, r=r, n_jobs=0)
+        monkeypatch.delenv("WILDBOAR_CUDA_NO_SEED", raising=False)
+        idx, dist = W.argmin_distance(q, refs, k=1, metric="dtw", metric_params={"r": r}, return_distance=True)
+        st_seed = W.last_stats()
+        _eq(idx, oi, f"seeded r={r} idx"); _eq(dist, od, f"seeded r={r} dist")
+        monkeypatch.setenv("WILDBOAR_CUDA_NO_SEED", "1")
+        idx, dist = W.argmin_distance(q, refs, k=1, metric="dtw", metric_params={"r": r}, return_distance=True)
+        st_plain = W.last_stats()
+        _eq(idx, oi, f"unseeded r={r} idx"); _eq(dist, od, f"unseeded r={r} dist")
+        if r < 1.0:
+            assert st_seed["pairs"] < st_plain["pairs"], (st_seed, st_plain)   # fewer pairs reach the DP
+    monkeypatch.delenv("WILDBOAR_CUDA_NO_SEED", raising=False)
+    # pipelined upload: the candidates come from the first piece only (300 of the 1500 references)
+    monkeypatch.setenv("WILDBOAR_CUDA_PIPED_UPLOAD_KB", "300")
+    oi, od = oracle.argmin("dtw", q, refs, k=1, r=0.1, n_jobs=0)
+    idx, dist = W.argmin_distance(q, refs, k=1, metric="dtw", metric_params={"r": 0.1}, return_distance=True)
+    _eq(idx, oi, "seeded + piped idx"); _eq(dist, od, "seeded + piped dist")
+    monkeypatch.delenv("WILDBOAR_CUDA_PIPED_UPLOAD_KB", raising=False)
+    oi, od = oracle.argmin("dtw", q, refs, k=4, r=0.1, n_jobs=0)
+    idx, dist = W.argmin_distance(q, refs, k=4, metric="dtw", metric_params={"r": 0.1}, return_distance=True)
+    _eq(idx, oi, "k=4 idx (heap order)"); _eq(dist, od, "k=4 dist")
+    # a fitted (device-resident) set takes the same path with all references as candidates
+    from wildboar_b200 import _shim as sh
+    from wildboar_b200.distance import DtwMetric
+    m = DtwMetric(r=0.1)
+    fit = sh.FittedSet(refs.reshape(len(refs), 1, -1), devices=[sh._first_device()])
+    try:
+        oi, od = oracle.argmin("dtw", q, refs, k=1, r=0.1, n_jobs=0)
+        for _ in range(2):
+            ridx, rdist = sh.argmin_fitted(m.metric_id, m._params(), q, fit, 1, use_device_lb=True)
+            _eq(ridx, oi, "fitted seeded idx"); _eq(rdist, od, "fitted seeded dist")
+    finally:
+        fit.close()
+
+
+@pytest.mark.parametrize("T,r", [(128, 0.1), (131, 0.05), (9, 0.5), (5, 1.0), (64, 0.3)])
+def test_lb_prune_kernel_variants_prune_identically(W, oracle, T, r, monkeypatch):
+    """The register-tiled LB pass (Q queries per warp, query tiles staged in shared memory by bulk copies, 4 or 8 time steps
+    per register block) keeps per (query, reference block) the sums and vote positions of the one-query kernel: same
+    results AND the same pruning counts for every variant; ragged query groups and reference blocks included."""
+    monkeypatch.setenv("WILDBOAR_CUDA_ARGMIN_CHUNK", "160")
+    monkeypatch.setenv("WILDBOAR_CUDA_NO_SEED", "1")
+    q, refs = random_walks(37, T, 81), random_walks(1003, T, 82)
+    refs[600] = q[11]
+    oi, od = oracle.argmin("dtw", q, refs, k=2, r=r, n_jobs=0)
+    counts = set()
+    for env in ({"LB_Q": "0"}, {"LB_Q": "2"}, {"LB_Q": "4"}, {"LB_Q": "4", "LB_BS": "8"}, {"LB_Q": "4", "LB_MINB": "2"},
+                {"LB_Q": "8"}, {"LB_Q": "4", "LB_RB": "1"}, {"LB_Q": "8", "LB_RB": "3"}):
+        for k_ in ("LB_Q", "LB_BS", "LB_MINB", "LB_RB"):
+            monkeypatch.delenv("WILDBOAR_CUDA_" + k_, raising=False)
+        for k_, v in env.items():
+            monkeypatch.setenv("WILDBOAR_CUDA_" + k_, v)
+        idx, dist = W.argmin_distance(q, refs, k=2, metric="dtw", metric_params={"r": r}, return_distance=True)
+        _eq(idx, oi, f"{env} idx"); _eq(dist, od, f"{env} dist")
+        st = W.last_stats()
+        counts.add((st["lb_kim_pruned"], st["lb_keogh_pruned"], st["pairs"]))
+    assert len(counts) == 1, counts

@@ -17,6 +17,7 @@
 //     M > T(t) with the exact t.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 #include "dispatch.cuh"
@@ -44,7 +45,20 @@ struct ArgminIo {
   int64_t* out_idx;           // host (nq, k)
   double* out_dist;           // host (nq, k)
   int use_device_lb;
+  // Pipelined upload of the references (second operand in HOST memory, dtw / wdtw / adtw in fp64): the scan starts as soon
+  // as the first chunk's references are resident; the remaining rows are copied piecewise on `up_stream` while earlier
+  // chunks compute (run_argmin, `ensure_refs`).  y_host == nullptr: the references are already on the device.
+  const double* y_host = nullptr;  // (ny, T) rows, `y_hs` elements apart
+  int64_t y_hs = 0;
+  double* y_dev = nullptr;         // destination == the call's dense y (ny, T)
+  cudaStream_t up_stream = nullptr;
 };
+
+// bytes per upload piece (test knob WILDBOAR_CUDA_PIPED_UPLOAD_KB forces many pieces on small inputs; 0 disables the pipeline)
+inline long long piped_piece_bytes() {
+  if (const char* e = getenv("WILDBOAR_CUDA_PIPED_UPLOAD_KB")) return std::max<long long>(0, atoll(e)) << 10;
+  return 16LL << 20;
+}
 
 enum ThrKind : int { TK_SQUARE = 0, TK_IDENT = 1, TK_SCALE = 2, TK_LCSS = 3, TK_NONE = 4 };
 
@@ -61,11 +75,14 @@ __device__ __forceinline__ double ea_threshold(int kind, double t, double scale)
 
 // thresholds handed to the DP kernel for a chunk; LCSS's T(t) is not monotone in t, so no
 // device-side abandoning for it (the replay still applies the exact rule).
+// `seed` (optional, raw domain): an upper bound of the final threshold known in advance (run_argmin, threshold seeding)
 __global__ void k_thr_raw(const double* __restrict__ tau, long long n, int kind, double scale,
-                          double* __restrict__ thr) {
+                          double* __restrict__ thr, const double* __restrict__ seed = nullptr) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n) return;
-  thr[q] = (kind == TK_LCSS || kind == TK_NONE) ? WB_INF : ea_threshold(kind, tau[q], scale);
+  double t = (kind == TK_LCSS || kind == TK_NONE) ? WB_INF : ea_threshold(kind, tau[q], scale);
+  if (seed) t = fmin(t, seed[q]);
+  thr[q] = t;
 }
 
 struct HeapEl { long long index; double value; };
@@ -214,19 +231,21 @@ __global__ void k_envelope_T(const double* __restrict__ y, long long n, int T, i
 //   references: envT[pos][j] = (lower_down, upper_up), yvT[pos][j] = (y_down, y_up); y0 / yL: first / last sample (fp64, LB_Kim)
 //   queries   : qf[i][pos]   = (x_down, x_up, lower_down, upper_up)
 // pos = position in the permuted time order (time step (pos * stride) mod T).
-__global__ void k_envelope_casc(const double* __restrict__ y, long long n, int T, int w, int stride, float2* __restrict__ envT,
-                                float2* __restrict__ yvT, double* __restrict__ y0, double* __restrict__ yL) {
-  const long long total = n * (long long)T;
+// series [s0, s0 + ns) of the n references (the whole set, or the piece that has just been uploaded)
+__global__ void k_envelope_casc(const double* __restrict__ y, long long n, long long s0, long long ns, int T, int w, int stride,
+                                float2* __restrict__ envT, float2* __restrict__ yvT, double* __restrict__ y0, double* __restrict__ yL) {
+  const long long total = ns * (long long)T;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int pos = (int)(e / n);
-    const long long s = e - (long long)pos * n;
+    const int pos = (int)(e / ns);
+    const long long s = s0 + (e - (long long)pos * ns);
     const int k = (int)(((long long)pos * stride) % T);
     const double* p = y + s * T;
     const int a = max(0, k - w), b = min(T - 1, k + w);
     double l = p[a], h = p[a];
     for (int q = a + 1; q <= b; ++q) { const double v = p[q]; l = fmin(l, v); h = fmax(h, v); }
-    envT[e] = make_float2(__double2float_rd(l), __double2float_ru(h));
-    yvT[e] = make_float2(__double2float_rd(p[k]), __double2float_ru(p[k]));
+    const long long o = (long long)pos * n + s;
+    envT[o] = make_float2(__double2float_rd(l), __double2float_ru(h));
+    yvT[o] = make_float2(__double2float_rd(p[k]), __double2float_ru(p[k]));
     if (pos == 0) { y0[s] = p[0]; yL[s] = p[T - 1]; }
   }
 }
@@ -259,26 +278,40 @@ struct LbArgs {
   const float2* yvT;   // (T, ny) (y_down, y_up)
   const double* y0; const double* yL;  // (ny) first / last sample of the references
   long long nq, ny, c0, nc; int T;
-  const double* tau;  // per query, distance domain
+  const double* thr2;  // per query: the chunk's abandon threshold in the DP's raw (squared) domain, INF = none yet
   double* d; long long ld;  // chunk matrix: +INF = pruned, -1 = survivor (to be filled by the DP)
   unsigned long long* n_kim; unsigned long long* n_keogh;  // pruning statistics
+  int* counts;  // (nq) survivors per query row of this chunk (zeroed by the caller), or nullptr
+  int strag_n, strag_after;  // a (query, block) subtask with <= strag_n unpruned lanes after step strag_after hands them to the DP
 };
 
+// ---- k_lb_prune: one warp = one query x 32 consecutive references (lane = reference) ----
+// Task mapping: the eight warps of a CTA take EIGHT CONSECUTIVE QUERIES against the SAME block of 32 references, so the block's
+// envelope / value rows (2 x 256 B per time step) come from L2 once and from L1 for the other seven warps.  With one query
+// per CTA-wide row of reference blocks (the first version) every warp streamed its own rows from L2: 4 GB per launch of the
+// cfg4 share = 9.4 TB/s, i.e. the pass ran at the L2's throughput (profiles/r02e_ncu_argmin_cfg4.csv: L1 hit 12 %,
+// long_scoreboard 10.8 per issued instruction, issue active 36 %; now L1 hit 65 %, 0.435 -> 0.28 ms per launch).  The warps
+// are not synchronised -- each leaves its task when its own 32 pairs are decided -- they merely start together.
+// Kept as the fallback of k_lb_prune_tile for series too long for its shared-memory query tiles.
+// `counts` (optional): survivors per query row of this chunk, accumulated with one atomic per warp task (zeroed by the
+// caller) -- replaces a separate pass over the chunk matrix.
 __global__ void __launch_bounds__(256) k_lb_prune(LbArgs a) {
   const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   const long long nyb = (a.nc + 31) / 32;
-  const long long ntask = a.nq * nyb;
-  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long nqg = (a.nq + wpb - 1) / wpb;
+  const long long nct = nqg * nyb;
   const int T = a.T;
   unsigned long long c_kim = 0, c_keogh = 0;  // per-warp statistics (lane 0), one atomic per warp at the end
-  for (long long t = wid; t < ntask; t += nw) {
-    const long long i = t / nyb;
-    const long long jl = (t - i * nyb) * 32 + lane;
+  for (long long ct = blockIdx.x; ct < nct; ct += gridDim.x) {
+    const long long qg = ct / nyb;
+    const long long i = qg * wpb + wib;
+    if (i >= a.nq) continue;
+    const long long jl = (ct - qg * nyb) * 32 + lane;
     const bool valid = jl < a.nc;
     const long long j = a.c0 + (valid ? jl : a.nc - 1);
-    const double tau = a.tau[i];
-    const double lim = isinf(tau) ? WB_INF : tau * tau * (1.0 + 1e-9);  // prune only if LB^2 > lim
+    const double t2 = a.thr2[i];
+    const double lim = isinf(t2) ? WB_INF : t2 * (1.0 + 1e-9);  // prune only if LB^2 > lim
     const double* q = a.x + i * T;
     bool pruned = false;
     if (!isinf(lim)) {
@@ -310,19 +343,29 @@ __global__ void __launch_bounds__(256) k_lb_prune(LbArgs a) {
           s2 = __fmaf_rd(e2, e2, s2);
         };
         int k = 0;
-        // blocks of 8 steps (pointer increments, all 24 loads of a block issued up front), then one warp vote: leave
-        // when every lane is pruned -- or when only a straggler or two are left after a good part of the series:
-        // finishing their sums would keep the whole warp busy, handing them to the (early-abandoning) DP is cheaper.
-        // Pruning is optional, so this cannot change a result.
-        for (; k + 8 <= T; k += 8) {
-          float2 lh[8], yy[8]; float4 qq[8];
+        // blocks of 8 steps, software pipelined in halves of 4: while one half is being summed the loads of the next are in
+        // flight, then one warp vote per block: leave when every lane is pruned -- or when only a straggler or two are left
+        // after a good part of the series: finishing their sums would keep the whole warp busy, handing them to the
+        // (early-abandoning) DP is cheaper.  Pruning is optional, so this cannot change a result.
+        if (T >= 8) {
+          float2 lhA[4], yyA[4], lhB[4], yyB[4]; float4 qqA[4], qqB[4];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) { lh[u] = env[u * ny]; yy[u] = yv[u * ny]; qq[u] = qf[k + u]; }
+          for (int u = 0; u < 4; ++u) { lhA[u] = env[u * ny]; yyA[u] = yv[u * ny]; qqA[u] = qf[u]; }
+          for (; k + 8 <= T; k += 8) {
 #pragma unroll
-          for (int u = 0; u < 8; ++u) step(lh[u], yy[u], qq[u]);
-          env += 8 * ny; yv += 8 * ny;
-          const int alive = __popc(__ballot_sync(0xffffffffu, !(pruned || s1 > limf || s2 > limf)));
-          if (alive == 0 || (alive <= kLbStragglers && k + 7 >= kLbStragglerAfter)) { k = T; break; }
+            for (int u = 0; u < 4; ++u) { lhB[u] = env[(4 + u) * ny]; yyB[u] = yv[(4 + u) * ny]; qqB[u] = qf[k + 4 + u]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) step(lhA[u], yyA[u], qqA[u]);
+            env += 8 * ny; yv += 8 * ny;
+            if (k + 16 <= T) {  // first half of the next block (wasted when the warp leaves below)
+#pragma unroll
+              for (int u = 0; u < 4; ++u) { lhA[u] = env[u * ny]; yyA[u] = yv[u * ny]; qqA[u] = qf[k + 8 + u]; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) step(lhB[u], yyB[u], qqB[u]);
+            const int alive = __popc(__ballot_sync(0xffffffffu, !(pruned || s1 > limf || s2 > limf)));
+            if (alive == 0 || (alive <= a.strag_n && k + 7 >= a.strag_after)) { k = T; break; }
+          }
         }
         for (; k < T; ++k) { step(*env, *yv, qf[k]); env += ny; yv += ny; }
         p2 = pruned || s1 > limf || s2 > limf;
@@ -331,6 +374,10 @@ __global__ void __launch_bounds__(256) k_lb_prune(LbArgs a) {
       }
     }
     if (valid) a.d[i * a.ld + jl] = pruned ? WB_INF : -1.0;
+    if (a.counts) {
+      const int nsv = __popc(__ballot_sync(0xffffffffu, valid && !pruned));
+      if (lane == 0 && nsv) atomicAdd(a.counts + i, nsv);
+    }
   }
   if (lane == 0) {
     if (c_kim) atomicAdd(a.n_kim, c_kim);
@@ -338,21 +385,331 @@ __global__ void __launch_bounds__(256) k_lb_prune(LbArgs a) {
   }
 }
 
-// survivors per query row -> exclusive scan -> (i, j) list sorted by (i, j)
-__global__ void __launch_bounds__(128) k_row_count(const double* __restrict__ d, long long nq, long long nc, long long ld,
-                                                   int* __restrict__ counts) {
-  const int lane = threadIdx.x & 31;
-  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long q = wid; q < nq; q += nw) {
-    int c = 0;
-    for (long long jj = 0; jj < nc; jj += 32) {
-      const long long j = jj + lane;
-      c += __popc(__ballot_sync(0xffffffffu, j < nc && d[q * ld + j] < 0.0));
+// ---- k_lb_prune_tile<Q>: register tile of Q queries x 32 references per warp, query tiles staged in shared memory by TMA ----
+// A CTA task is a group of Q CONSECUTIVE QUERIES against a range of reference blocks.  The Q queries' cascade rows (Q x T
+// float4, contiguous in qf) arrive in shared memory by ONE bulk copy (cp.async.bulk + mbarrier), issued a whole task ahead
+// into the other of two buffers; the warps of the CTA draw reference blocks of the task from a shared counter.  A warp holds
+// the block's envelope / value rows of eight time steps in registers (loaded once, the next block of eight in flight
+// meanwhile) and runs all Q queries over them, the query samples coming as broadcast float4 reads from shared memory:
+// 512 / Q + 16 B per pair-step instead of 528 B move through the SM's load path, and no load of the inner loop waits on L2.
+// Every (query, block) subtask keeps its own sums and its own vote and leaves exactly where k_lb_prune leaves (same sums,
+// same vote positions: the pruning statistics are bit-identical); the warp moves on when all Q are decided.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WB_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WB_MBAR_DONE;\n"
+      "bra WB_MBAR_WAIT;\n"
+      "WB_MBAR_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+struct LbQMeta { double lim, x0, xL; };  // per query of a tile: prune limit (INF: no threshold yet), first / last sample
+
+inline size_t lb_tile_smem(int Q, int T) { return 2 * ((size_t)Q * T * sizeof(float4) + Q * sizeof(LbQMeta)) + 64; }  // + 2 mbarriers, 4 counters
+
+// Q queries per warp task, BS time steps per register block (4: 3 CTAs of 8 warps per SM; 8: 2), MINB = CTAs per SM the
+// register budget is cut for.  No CTA-wide barrier in the task loop: a buffer is handed back through a shared counter,
+// and the LAST warp to finish a task stages the CTA's task after next into the buffer it has just freed.
+template <int Q, int BS, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_lb_prune_tile(LbArgs a, int rb_per_task) {
+  static_assert(BS == 4 || BS == 8, "block of 4 or 8 time steps");
+  extern __shared__ __align__(128) unsigned char lb_smem[];
+  const int T = a.T;
+  float4* const qs = reinterpret_cast<float4*>(lb_smem);                       // [2][Q * T]
+  LbQMeta* const meta = reinterpret_cast<LbQMeta*>(qs + 2 * (size_t)Q * T);    // [2][Q]
+  unsigned long long* const mbar = reinterpret_cast<unsigned long long*>(meta + 2 * Q);  // [2]
+  int* const s_next = reinterpret_cast<int*>(mbar + 2);                        // [2] next reference block of the task
+  int* const s_done = s_next + 2;                                              // [2] warps that have finished the task
+  const int tid = threadIdx.x, lane = tid & 31, wpb = blockDim.x >> 5;
+  const long long nyb = (a.nc + 31) / 32;
+  const long long nqg = (a.nq + Q - 1) / Q;
+  const long long nsplit = (nyb + rb_per_task - 1) / rb_per_task;
+  const long long per = (nyb + nsplit - 1) / nsplit;
+  const long long nct = nqg * nsplit;
+  const long long ny = a.ny;
+  unsigned long long c_kim = 0, c_keogh = 0;
+
+  // stage task `ct` into buffer b (one whole warp): lanes 0..Q-1 write the per-query scalars, lane 0 resets the block
+  // counter and starts the bulk copy of the Q query rows; its arrive (release) publishes all of it with the data
+  auto stage = [&](long long ct, int b) {
+    const long long qg = ct / nsplit;
+    const long long i0 = qg * Q;
+    if (lane < Q) {
+      LbQMeta mq; mq.lim = WB_INF; mq.x0 = 0.0; mq.xL = 0.0;
+      const long long i = i0 + lane;
+      if (i < a.nq) {
+        const double t2 = a.thr2[i];
+        mq.lim = isinf(t2) ? WB_INF : t2 * (1.0 + 1e-9);  // prune only if LB^2 > lim
+        mq.x0 = a.x[i * T]; mq.xL = a.x[i * T + T - 1];
+      }
+      meta[b * Q + lane] = mq;
     }
-    if (lane == 0) counts[q] = c;
+    __syncwarp();
+    if (lane == 0) {
+      const unsigned bytes = (unsigned)(min((long long)Q, a.nq - i0) * T * (long long)sizeof(float4));
+      s_next[b] = (int)((ct - qg * nsplit) * per);
+      s_done[b] = 0;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the buffer's last generic reads precede the async write
+      mbar_expect_tx(&mbar[b], bytes);
+      bulk_g2s(qs + (size_t)b * Q * T, a.qf + i0 * T, bytes, &mbar[b]);
+    }
+  };
+
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid < 32) {
+    if ((long long)blockIdx.x < nct) stage(blockIdx.x, 0);
+    if ((long long)blockIdx.x + gridDim.x < nct) stage((long long)blockIdx.x + gridDim.x, 1);
+  }
+  int it = 0;
+  for (long long ct = blockIdx.x; ct < nct; ct += gridDim.x, ++it) {
+    const int b = it & 1;
+    mbar_wait(&mbar[b], (unsigned)((it >> 1) & 1));
+    const long long qg = ct / nsplit;
+    const long long i0 = qg * Q;
+    const int rb_hi = (int)min(nyb, ((ct - qg * nsplit) + 1) * per);
+    const float4* const qf = qs + (size_t)b * Q * T;
+    const LbQMeta* const mt = meta + b * Q;
+    for (;;) {
+      int rb = 0;
+      if (lane == 0) rb = atomicAdd(&s_next[b], 1);
+      rb = __shfl_sync(0xffffffffu, rb, 0);
+      if (rb >= rb_hi) break;
+      const long long jl = (long long)rb * 32 + lane;
+      const bool valid = jl < a.nc;
+      const long long j = a.c0 + (valid ? jl : a.nc - 1);
+      const float2* env = a.envT + j;
+      const float2* yv = a.yvT + j;
+      float2 lhA[BS], yyA[BS], lhB[BS], yyB[BS];
+      auto load_block = [&](float2 (&lh)[BS], float2 (&yy)[BS]) {
+#pragma unroll
+        for (int u = 0; u < BS; ++u) { lh[u] = env[u * ny]; yy[u] = yv[u * ny]; }
+      };
+      const double y0 = a.y0[j], yL = a.yL[j];
+      if (T >= 8) load_block(lhA, yyA);  // in flight during the LB_Kim tests (wasted when they prune the whole block for all Q)
+      float limf[Q], s1[Q], s2[Q];
+      unsigned active = 0;   // bit q (warp uniform): query q is still summing
+      unsigned prm = 0;      // bit q (per lane): this lane's pair with query q is pruned
+      // LB_Kim: every warping path contains (0,0) and (T-1,T-1)
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        s1[q] = 0.0f; s2[q] = 0.0f; limf[q] = 0.0f;
+        const LbQMeta mq = mt[q];
+        if (isinf(mq.lim)) continue;  // no threshold yet (or no such query): nothing is pruned
+        const double d0 = mq.x0 - y0;
+        const double d1 = mq.xL - yL;
+        const double lb = d0 * d0 + (T > 1 ? d1 * d1 : 0.0);
+        const bool pk = lb > mq.lim;
+        c_kim += __popc(__ballot_sync(0xffffffffu, pk && valid));
+        if (pk) prm |= 1u << q;
+        if (!__all_sync(0xffffffffu, pk)) { active |= 1u << q; limf[q] = __double2float_ru(mq.lim); }
+      }
+      if (active) {
+        // LB_Keogh in BOTH directions at once (time steps in the permuted order): s1 = query against the reference's
+        // envelope, s2 = reference against the query's envelope, in round-down fp32 on outward-rounded operands (rigorous
+        // lower bounds of the fp64 sums).  A lane is pruned as soon as EITHER sum exceeds the limit.
+        auto step = [&](float& t1, float& t2, const float2 lh, const float2 yy, const float4 qq) {
+          const float e1 = fmaxf(fmaxf(__fsub_rd(qq.x, lh.y), __fsub_rd(lh.x, qq.y)), 0.0f);
+          t1 = __fmaf_rd(e1, e1, t1);
+          const float e2 = fmaxf(fmaxf(__fsub_rd(yy.x, qq.w), __fsub_rd(qq.z, yy.y)), 0.0f);
+          t2 = __fmaf_rd(e2, e2, t2);
+        };
+        int k = 0;
+        if (T >= 8) {
+          // BS steps of every active query over one register block (the query samples: four broadcast reads from shared
+          // memory issued together); after every 8th step one warp vote per query: leave when every lane is pruned -- or
+          // when only a straggler or two are left after a good part of the series (handed to the early-abandoning DP)
+          auto sum_block = [&](const float2 (&lh)[BS], const float2 (&yy)[BS], int kb, bool vote) {
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+              if (!((active >> q) & 1u)) continue;
+              const float4* qq = qf + q * T + kb;
+#pragma unroll
+              for (int h = 0; h < BS; h += 4) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = qq[h + u];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) step(s1[q], s2[q], lh[h + u], yy[h + u], v[u]);
+              }
+              if (vote) {
+                const int alive = __popc(__ballot_sync(0xffffffffu, !(((prm >> q) & 1u) || s1[q] > limf[q] || s2[q] > limf[q])));
+                if (alive == 0 || (alive <= a.strag_n && kb + BS - 1 >= a.strag_after)) active &= ~(1u << q);
+              }
+            }
+          };
+          // 16 steps per trip for BS = 8, 8 for BS = 4: the two register blocks swap roles without moves, the block after
+          // the one being summed is in flight (its loads are wasted when the warp leaves after this block)
+          while (k + 8 <= T && active) {
+            env += BS * ny; yv += BS * ny;
+            if (BS == 4 || k + 16 <= T) load_block(lhB, yyB);
+            sum_block(lhA, yyA, k, BS == 8);
+            k += BS;
+            if (BS == 8 && !(k + 8 <= T && active)) break;
+            env += BS * ny; yv += BS * ny;
+            if (k + BS + 8 <= T) load_block(lhA, yyA);  // only when another trip follows
+            sum_block(lhB, yyB, k, true);
+            k += BS;
+          }
+        }
+        // T % 8 last steps for the queries that ran to the end
+        if (active) {
+          for (; k < T; ++k) {
+            const float2 lh1 = *env, yy1 = *yv;
+            env += ny; yv += ny;
+#pragma unroll
+            for (int q = 0; q < Q; ++q)
+              if ((active >> q) & 1u) step(s1[q], s2[q], lh1, yy1, qf[q * T + k]);
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        const long long i = i0 + q;
+        if (i >= a.nq) continue;
+        const bool pk = (prm >> q) & 1u;
+        // limf = 0 with zero sums where no Keogh pass ran (no threshold, or LB_Kim pruned all 32): 0 > 0 is false
+        const bool p2 = pk || s1[q] > limf[q] || s2[q] > limf[q];
+        c_keogh += __popc(__ballot_sync(0xffffffffu, p2 && !pk && valid));
+        if (valid) a.d[i * a.ld + jl] = p2 ? WB_INF : -1.0;
+        if (a.counts) {
+          const int nsv = __popc(__ballot_sync(0xffffffffu, valid && !p2));
+          if (lane == 0 && nsv) atomicAdd(a.counts + i, nsv);
+        }
+      }
+    }
+    // hand the buffer back; the last warp refills it for the CTA's task after next
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) {
+      __threadfence_block();
+      last = atomicAdd(&s_done[b], 1) == wpb - 1;
+      __threadfence_block();
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last && ct + 2LL * gridDim.x < nct) stage(ct + 2LL * gridDim.x, b);
+  }
+  if (lane == 0) {
+    if (c_kim) atomicAdd(a.n_kim, c_kim);
+    if (c_keogh) atomicAdd(a.n_keogh, c_keogh);
   }
 }
+
+// ------------------------------------------------------------------------------------------
+// Threshold seeding (k = 1).  The cascade prunes with the threshold a query has at the START of a chunk, and that starts
+// at +INF: the first chunks run dense or nearly so, and on the cfg4 share 2.1 % of all pairs reach the DP although only
+// 0.08 % would with the final thresholds.  Any exact distance d(q, y_j*) is an upper bound of the final nearest-neighbour
+// distance, so pruning / abandoning against min(running threshold, d*^2) can only remove pairs with d > d* >= the final
+// minimum: for k = 1 the result (first index of the minimal distance, and that distance) cannot change -- the candidate
+// itself and every tie survive (LB^2 <= d^2 = seed, column minima <= d^2 = seed, both tests are strict).  For k > 1 the
+// SET of neighbours would be safe too but not the heap-array order the reference returns, so seeding is k = 1 only.
+// Candidates: the 8 nearest references under the Euclidean distance of a 16-segment piecewise-aggregate sketch (fp32;
+// a heuristic, it only decides how tight the seed is), then their exact DP values (raw, squared domain) -- 8 nq pairs.
+// ------------------------------------------------------------------------------------------
+constexpr int kSeedP = 16;   // sketch dimensions
+constexpr int kSeedNC = 8;   // candidates per query
+constexpr int kSeedQB = 8;   // queries per CTA of the candidate search
+
+// sketch of series [0, n): mean of segment p = [p T / P, (p + 1) T / P); TR: transposed ([p][series]) for the references
+template <bool TR>
+__global__ void k_seed_sketch(const double* __restrict__ x, long long n, int T, float* __restrict__ out) {
+  const long long total = n * kSeedP;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long s = e / kSeedP;
+    const int p = (int)(e - s * kSeedP);
+    const int a = (int)((long long)p * T / kSeedP), b = (int)((long long)(p + 1) * T / kSeedP);
+    double acc = 0.0;
+    for (int t = a; t < b; ++t) acc += x[s * T + t];
+    const float v = (b > a) ? (float)(acc / (double)(b - a)) : 0.0f;
+    out[TR ? (long long)p * n + s : e] = v;
+  }
+}
+
+// per query the kSeedNC best of the 256 threads' own best reference (thread t scans references t, t + 256, ...)
+__global__ void __launch_bounds__(256) k_seed_candidates(const float* __restrict__ qp, const float* __restrict__ rp, long long nq,
+                                                         long long S, int2* __restrict__ cl) {
+  __shared__ float sq[kSeedQB][kSeedP];
+  __shared__ float sv[8];
+  __shared__ int st[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long q0 = (long long)blockIdx.x * kSeedQB;
+  if (tid < kSeedQB * kSeedP) {
+    const long long q = q0 + tid / kSeedP;
+    sq[tid / kSeedP][tid % kSeedP] = q < nq ? qp[q * kSeedP + tid % kSeedP] : 0.0f;
+  }
+  __syncthreads();
+  float best[kSeedQB]; int bidx[kSeedQB];
+#pragma unroll
+  for (int q = 0; q < kSeedQB; ++q) { best[q] = 3.0e38f; bidx[q] = -1; }
+  for (long long j = tid; j < S; j += 256) {
+    float r[kSeedP];
+#pragma unroll
+    for (int p = 0; p < kSeedP; ++p) r[p] = rp[(long long)p * S + j];
+#pragma unroll
+    for (int q = 0; q < kSeedQB; ++q) {
+      float d = 0.0f;
+#pragma unroll
+      for (int p = 0; p < kSeedP; ++p) { const float v = r[p] - sq[q][p]; d = fmaf(v, v, d); }
+      if (d < best[q]) { best[q] = d; bidx[q] = (int)j; }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kSeedQB; ++q) {
+    float v = best[q];
+    for (int r = 0; r < kSeedNC; ++r) {
+      // block-wide argmin of (v, thread)
+      float wv = v; int wt = tid;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+        const int ot = __shfl_xor_sync(0xffffffffu, wt, o);
+        if (ov < wv || (ov == wv && ot < wt)) { wv = ov; wt = ot; }
+      }
+      if (lane == 0) { sv[warp] = wv; st[warp] = wt; }
+      __syncthreads();
+      float bv = sv[0]; int bt = st[0];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) if (sv[w] < bv) { bv = sv[w]; bt = st[w]; }
+      if (tid == bt && q0 + q < nq) {
+        cl[(q0 + q) * kSeedNC + r] = make_int2((int)(q0 + q), bidx[q] < 0 ? 0 : bidx[q]);
+        v = 3.4e38f;  // taken
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void k_seed_min(const double* __restrict__ cd, long long nq, double* __restrict__ seed2) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  double m = cd[q * kSeedNC];
+#pragma unroll
+  for (int r = 1; r < kSeedNC; ++r) m = fmin(m, cd[q * kSeedNC + r]);
+  seed2[q] = m;
+}
+__global__ void k_set_int(int* p, int v) { *p = v; }
+
+// survivors per query row (counted by k_lb_prune) -> exclusive scan -> (i, j) list sorted by (i, j)
 __global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ counts, long long nq, int* __restrict__ starts,
                                                       int* __restrict__ total, unsigned long long* __restrict__ grand_total) {
   __shared__ int part[1024];
@@ -414,13 +771,19 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
   // Columns per chunk.  The thresholds a chunk is pruned with are those at its start, so the FIRST chunks should be small
   // (they run dense or nearly so) and the later ones large (few launches: with one query every chunk is ~6 launches of
   // almost no work).  The chunk grows 4x per step from 1024 columns up to C = min(32768, 4 Mi / nq) -- nq * C values per
-  // buffer; for the cfg4 share (2500 queries) that is 1024 then 1600, as before; for one query 1024, 4096, 16384, 32768, ...
+  // buffer; for the cfg4 share (2500 queries) that is 128, 512, then 1600; for one query 1024, 4096, 16384, 32768, ...
   long long C = (4LL << 20) / std::max<long long>(nq, 1);
   C = std::max<long long>(32, std::min<long long>(32768, (C / 32) * 32));
-  long long c_first = std::min<long long>(C, 1024);
+  // first chunk: it runs without thresholds (every pair in full), so just enough pairs to fill the device -- 256 Ki --
+  // between 128 and 1024 columns (cfg4 share, 2500 queries: 128 columns; kernels 81 -> 75 ms against 1024)
+  long long c_first = std::min<long long>(C, std::max<long long>(128, std::min<long long>(1024, (((256LL << 10) / std::max<long long>(nq, 1)) / 32) * 32)));
   if (const char* e = getenv("WILDBOAR_CUDA_ARGMIN_CHUNK")) {  // tuning / test knob: fixed columns per chunk
     const long long v = atoll(e);
     if (v >= 32) { C = (v / 32) * 32; c_first = C; }
+  }
+  if (const char* e = getenv("WILDBOAR_CUDA_ARGMIN_FIRST")) {  // tuning knob: columns of the first (dense) chunk
+    const long long v = atoll(e);
+    if (v >= 32) c_first = (v / 32) * 32;
   }
   C = std::min<long long>(C, ((ny + 31) / 32) * 32);
   c_first = std::min(c_first, C);
@@ -454,7 +817,7 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
             cudaMallocAsync((void**)&cc->yvT, sizeof(float2) * (size_t)ny * T, st) != cudaSuccess ||
             cudaMallocAsync((void**)&cc->y0, sizeof(double) * (size_t)ny, st) != cudaSuccess ||
             cudaMallocAsync((void**)&cc->yL, sizeof(double) * (size_t)ny, st) != cudaSuccess) { cudaGetLastError(); return 1; }
-        k_envelope_casc<<<2048, 256, 0, st>>>(c.py, ny, T, w, stride, cc->envT, cc->yvT, cc->y0, cc->yL);
+        k_envelope_casc<<<2048, 256, 0, st>>>(c.py, ny, 0, ny, T, w, stride, cc->envT, cc->yvT, cc->y0, cc->yL);
         if (cudaStreamSynchronize(st) != cudaSuccess) return 1;
         cc->T = T; cc->w = w; cc->stride = stride; cc->ny = ny; cc->py = c.py; cc->valid = true;
       }
@@ -465,9 +828,40 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
     }
     if (!cached) {
       if (ws.alloc(&envT, (size_t)ny * T) || ws.alloc(&yvT, (size_t)ny * T) || ws.alloc(&y0, (size_t)ny) || ws.alloc(&yL, (size_t)ny)) return 1;
-      k_envelope_casc<<<2048, 256, 0, st>>>(c.py, ny, T, w, stride, envT, yvT, y0, yL);
+      // host-resident references: the operands are built piece by piece as the rows arrive (ensure_refs)
+      if (!io.y_host) k_envelope_casc<<<2048, 256, 0, st>>>(c.py, ny, 0, ny, T, w, stride, envT, yvT, y0, yL);
     }
   }
+  // ---- pipelined upload of host-resident references ----
+  long long up_done = io.y_host ? 0 : ny;  // references [0, up_done) are resident (and their cascade operands built)
+  cudaEvent_t up_ev = nullptr;
+  if (io.y_host) {
+    // the destination was allocated in stream order on `st`: the copy stream may touch it only after that point
+    if (cudaEventCreateWithFlags(&up_ev, cudaEventDisableTiming) != cudaSuccess) return 1;
+    if (cudaEventRecord(up_ev, st) != cudaSuccess || cudaStreamWaitEvent(io.up_stream, up_ev, 0) != cudaSuccess) { cudaEventDestroy(up_ev); return 1; }
+  }
+  // make references [0, upto) resident before work that reads them is enqueued on `st`.  Pieces of >= 16 MB beyond what the
+  // chunk needs: a copy from pageable memory blocks the HOST until it is staged, the device meanwhile runs the chunks
+  // enqueued before it (a piece is several chunks of work, and is copied in less time than they take).
+  auto ensure_refs = [&](long long upto) -> int {
+    if (upto <= up_done) return 0;
+    const long long Ty = c.Ty;
+    const long long piece = std::max<long long>(1, piped_piece_bytes() / (long long)(sizeof(double) * Ty));
+    const long long to = std::min<long long>(ny, std::max(upto, up_done + piece));
+    const long long rows = to - up_done;
+    double* dst = io.y_dev + up_done * Ty;
+    const double* src = io.y_host + up_done * io.y_hs;
+    cudaError_t e = (io.y_hs == Ty)
+        ? cudaMemcpyAsync(dst, src, sizeof(double) * rows * Ty, cudaMemcpyHostToDevice, io.up_stream)
+        : cudaMemcpy2DAsync(dst, sizeof(double) * Ty, src, sizeof(double) * io.y_hs, sizeof(double) * Ty, rows, cudaMemcpyHostToDevice, io.up_stream);
+    if (e != cudaSuccess || cudaEventRecord(up_ev, io.up_stream) != cudaSuccess || cudaStreamWaitEvent(st, up_ev, 0) != cudaSuccess) return 1;
+    if (cascade && envT) {
+      const long long nblk = std::max<long long>(1, std::min<long long>(2048, (rows * c.ptx + 255) / 256));
+      k_envelope_casc<<<(unsigned)nblk, 256, 0, st>>>(c.py, ny, up_done, rows, c.ptx, std::max(c.R - 1, 0), lb_time_stride(c.ptx), envT, yvT, y0, yL);
+    }
+    up_done = to;
+    return 0;
+  };
   k_fill<<<256, 256, 0, st>>>(tau, nq, WB_INF);
   if (cudaMemsetAsync(hval, 0, sizeof(double) * nq * k, st) != cudaSuccess ||
       cudaMemsetAsync(hidx, 0, sizeof(long long) * nq * k, st) != cudaSuccess ||
@@ -477,29 +871,84 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, st);
   int rc = 0;
+  // ---- threshold seeding (k = 1; see k_seed_candidates) ----
+  double* seed2 = nullptr;
+  if (cascade && k == 1 && !getenv("WILDBOAR_CUDA_NO_SEED")) {
+    // references the candidates are drawn from: all of them when they are resident, the first piece of a pipelined upload
+    if (io.y_host) rc = ensure_refs(1);
+    const long long S = up_done;
+    long long s_min = 2048;
+    if (const char* e = getenv("WILDBOAR_CUDA_SEED_MIN")) s_min = std::max<long long>(256, atoll(e));  // test knob
+    if (!rc && S >= s_min && nq * (long long)kSeedNC < 2000000000LL) {
+      float *rp = nullptr, *qp = nullptr; int2* cl = nullptr; int* cl_len = nullptr; double* cd = nullptr;
+      if (ws.alloc(&rp, (size_t)S * kSeedP) || ws.alloc(&qp, (size_t)nq * kSeedP) || ws.alloc(&cl, (size_t)nq * kSeedNC) ||
+          ws.alloc(&cl_len, 1) || ws.alloc(&cd, (size_t)nq * kSeedNC) || ws.alloc(&seed2, (size_t)nq)) rc = 1;
+      if (!rc) {
+        const int T = c.ptx;
+        k_seed_sketch<true><<<(unsigned)std::min<long long>(148 * 16, (S * kSeedP + 255) / 256), 256, 0, st>>>(c.py, S, T, rp);
+        k_seed_sketch<false><<<(unsigned)std::min<long long>(148 * 16, (nq * kSeedP + 255) / 256), 256, 0, st>>>(c.px, nq, T, qp);
+        k_seed_candidates<<<(unsigned)((nq + kSeedQB - 1) / kSeedQB), 256, 0, st>>>(qp, rp, nq, S, cl);
+        k_set_int<<<1, 1, 0, st>>>(cl_len, (int)(nq * kSeedNC));
+        const int mode0 = c.mode, raw0 = c.raw;
+        c.mode = PM_LISTP; c.list = cl; c.list_len = cl_len; c.list_n = nq * kSeedNC; c.raw = 1;
+        rc = launch(0, nq, 0, ny, cd, 1, nullptr, nullptr, stats);
+        c.mode = mode0; c.list = nullptr; c.list_len = nullptr; c.list_n = 0; c.raw = raw0;
+        k_seed_min<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(cd, nq, seed2);
+        if (stats) stats->launches += 5;
+        // with thresholds from the start there is no dense first chunk to keep small
+        c_first = C;
+      }
+    }
+  }
   long long c_cur = c_first;
   for (long long c0 = 0; c0 < ny && !rc; ) {
     const long long nc = std::min(c_cur, ny - c0);
     const long long c0_next = c0 + nc;
     c_cur = std::min(C, c_cur * 4);
-    k_thr_raw<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(tau, nq, kind, scale, thr);
+    if ((rc = ensure_refs(c0_next))) break;
+    k_thr_raw<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(tau, nq, kind, scale, thr, seed2);
     if (c.degenerate) {
       // ddtw with T < 3: eadistance() returns False for every pair (EL:3297-3298)
       k_fill<<<256, 256, 0, st>>>(dbuf, nq * C, WB_INF);
-    } else if (cascade && c0 > 0) {
-      // chunk 0 has no threshold yet (tau = INF): nothing can be pruned, run it densely
+    } else if (cascade && (c0 > 0 || seed2)) {
+      // chunk 0 has no threshold yet (tau = INF) unless the thresholds were seeded: nothing can be pruned, run it densely
       LbArgs la;
       la.x = c.px; la.qf = qf; la.envT = envT; la.yvT = yvT; la.y0 = y0; la.yL = yL;
-      la.nq = nq; la.ny = ny; la.c0 = c0; la.nc = nc; la.T = c.ptx; la.tau = tau; la.d = dbuf; la.ld = C;
-      la.n_kim = lbstat; la.n_keogh = lbstat + 1;
-      k_lb_prune<<<148 * 8, 256, 0, st>>>(la);
-      k_row_count<<<148 * 4, 128, 0, st>>>(dbuf, nq, nc, C, counts);
+      la.nq = nq; la.ny = ny; la.c0 = c0; la.nc = nc; la.T = c.ptx; la.thr2 = thr; la.d = dbuf; la.ld = C;
+      la.n_kim = lbstat; la.n_keogh = lbstat + 1; la.counts = counts;
+      la.strag_n = kLbStragglers; la.strag_after = kLbStragglerAfter;
+      if (const char* e = getenv("WILDBOAR_CUDA_LB_STRAG")) {  // tuning knob "n,after"
+        int n_ = 0, a_ = 0;
+        if (sscanf(e, "%d,%d", &n_, &a_) == 2) { la.strag_n = n_; la.strag_after = a_; }
+      }
+      if (cudaMemsetAsync(counts, 0, sizeof(int) * nq, st) != cudaSuccess) { rc = 1; break; }
+      {
+        // register-tiled pass with shared-memory query tiles when they fit (two buffers of Q x T float4), else one query per warp
+        const char* lbq_env = getenv("WILDBOAR_CUDA_LB_Q");  // tuning / test knob: 0 = the one-query kernel
+        int lbq = lbq_env ? atoi(lbq_env) : 4;
+        while (lbq > 1 && lb_tile_smem(lbq, c.ptx) > (size_t)96 << 10) lbq >>= 1;
+        if (nq < 2 || lbq < 2) lbq = 0;
+        const char* rbt_env = getenv("WILDBOAR_CUDA_LB_RB");
+        const int rbt = (rbt_env && atoi(rbt_env) > 0) ? atoi(rbt_env) : 16;  // reference blocks per CTA task
+        const char* bs_env = getenv("WILDBOAR_CUDA_LB_BS");
+        const int lbs = (bs_env && atoi(bs_env) == 8) ? 8 : 4;  // time steps per register block
+        auto go = [&](auto kern, int per_sm) {
+          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 << 10);
+          kern<<<148 * per_sm, 256, lb_tile_smem(lbq, c.ptx), st>>>(la, rbt);
+        };
+        const char* mb_env = getenv("WILDBOAR_CUDA_LB_MINB");
+        const int mb = (mb_env && atoi(mb_env) == 2) ? 2 : 3;  // CTAs per SM the register budget is cut for (BS = 4)
+        if (lbq >= 8) go(k_lb_prune_tile<8, 4, 2>, 2);
+        else if (lbq >= 4) { if (lbs == 8) go(k_lb_prune_tile<4, 8, 2>, 2); else if (mb == 2) go(k_lb_prune_tile<4, 4, 2>, 2); else go(k_lb_prune_tile<4, 4, 3>, 3); }
+        else if (lbq >= 2) go(k_lb_prune_tile<2, 4, 3>, 3);
+        else k_lb_prune<<<148 * 8, 256, 0, st>>>(la);
+      }
       k_scan_counts<<<1, 1024, 0, st>>>(counts, nq, starts, list_len, lbstat + 2);
       k_fill_list<<<148 * 4, 128, 0, st>>>(dbuf, nq, nc, C, starts, list);
       c.mode = PM_LIST; c.list = list; c.list_len = list_len;
       rc = launch(0, nq, c0, nc, dbuf, C, nullptr, thr, nullptr);
       c.mode = PM_PAIRWISE; c.list = nullptr; c.list_len = nullptr;
-      if (stats) stats->launches += 5;
+      if (stats) stats->launches += 4;  // k_lb_prune, k_scan_counts, k_fill_list, the DP
       if (rc) break;
     } else {
       rc = launch(0, nq, c0, nc, dbuf, C, mbuf, (kind == TK_NONE || kind == TK_LCSS) ? nullptr : thr, stats);
@@ -537,6 +986,10 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
     }
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (up_ev) {
+    if (rc) cudaStreamSynchronize(io.up_stream);  // nothing may still be copying into a buffer the caller is about to free
+    cudaEventDestroy(up_ev);
+  }
   return rc;
 }
 

@@ -811,6 +811,7 @@ static int device_worker(const HostJob& J, int dev, int64_t lo, int64_t hi, wb_s
     const int64_t rows = hi - lo;
     const int64_t nd = std::max<int64_t>(J.nd, 1);
     double *dx = nullptr, *dy = nullptr;
+    bool argmin_piped = false;
     do {
       // operands are staged densely as (n_dims, samples, T)
       int64_t xn = 0, xT = 0, yn = 0, yT = 0;  // samples / length of the staged first and second operand
@@ -838,9 +839,15 @@ static int device_worker(const HostJob& J, int dev, int64_t lo, int64_t hi, wb_s
           for (size_t q = 0; q < J.fit->devs.size(); ++q) if (J.fit->devs[q] == dev) dy = J.fit->ptr[q];
           if (!dy) { set_err("the fitted set is not resident on this device"); rc = 1; break; }
         } else if ((rc = ws.alloc(&dy, (size_t)nd * J.ny * J.Ty))) break;
+        // argmin of dtw / wdtw / adtw (fp64) against HOST references: the rows are uploaded piecewise while the scan is
+        // already running (run_argmin); every other case needs the whole second operand first (slopes, per-series
+        // scalars, float copies, interleaved rows are derived from all of it)
+        argmin_piped = J.kind == 3 && !J.fit && nd == 1 && J.p.precision != 1 && piped_piece_bytes() > 0 &&
+                       (long long)sizeof(double) * J.ny * J.Ty > 2 * piped_piece_bytes() &&
+                       (J.metric == M_DTW || J.metric == M_WDTW || J.metric == M_ADTW);
         for (int64_t d = 0; d < nd && !rc; ++d) {
           if ((rc = h2d_rows(dx + d * rows * J.Tx, J.x + d * J.xds + lo * J.xs, rows, J.Tx, J.xs, st))) break;
-          if (!J.fit) rc = h2d_rows(dy + d * J.ny * J.Ty, J.y + d * J.yds, J.ny, J.Ty, J.ys, st);
+          if (!J.fit && !argmin_piped) rc = h2d_rows(dy + d * J.ny * J.Ty, J.y + d * J.yds, J.ny, J.Ty, J.ys, st);
         }
         if (rc) break;
       }
@@ -866,6 +873,7 @@ static int device_worker(const HostJob& J, int dev, int64_t lo, int64_t hi, wb_s
         if (J.fit) for (size_t q = 0; q < J.fit->devs.size() && q < J.fit->casc.size(); ++q) if (J.fit->devs[q] == dev) io.casc_cache = &J.fit->casc[q];
         io.k = J.k; io.lower_bound = J.lower_bound ? J.lower_bound + lo * J.ny : nullptr; io.lb_ld = J.ny;
         io.out_idx = J.out_idx + lo * J.k; io.out_dist = J.out + lo * J.k; io.use_device_lb = J.use_device_lb;
+        if (argmin_piped) { io.y_host = J.y; io.y_hs = J.ys; io.y_dev = dy; io.up_stream = cst; }
         rc = run_argmin(ws, di, c, io, &stats,
                         [&](long long r0, long long nr, long long c0, long long nc, double* o, long long ld, double* om,
                             const double* thr, wb_stats* s) { return launch_dp(ws, di, c, r0, nr, c0, nc, o, ld, om, thr, s); });
