@@ -664,8 +664,9 @@ def test_argmin_threshold_seeding_is_exact(W, oracle, monkeypatch):
 @pytest.mark.parametrize("T,r", [(128, 0.1), (131, 0.05), (9, 0.5), (5, 1.0), (64, 0.3)])
 def test_lb_prune_kernel_variants_prune_identically(W, oracle, T, r, monkeypatch):
     """The register-tiled LB pass (Q queries per warp, query tiles staged in shared memory by bulk copies, 4 or 8 time steps
-    per register block) keeps per (query, reference block) the sums and vote positions of the one-query kernel: same
-    results AND the same pruning counts for every variant; ragged query groups and reference blocks included."""
+    per register block, stragglers continued one pair per lane) computes per pair the sums of the one-query kernel in the
+    same order: same results for every variant, and the same pruning counts as a pass that never leaves a block early;
+    ragged query groups and reference blocks included."""
     monkeypatch.setenv("WILDBOAR_CUDA_ARGMIN_CHUNK", "160")
     monkeypatch.setenv("WILDBOAR_CUDA_NO_SEED", "1")
     q, refs = random_walks(37, T, 81), random_walks(1003, T, 82)
@@ -681,5 +682,20 @@ def test_lb_prune_kernel_variants_prune_identically(W, oracle, T, r, monkeypatch
         idx, dist = W.argmin_distance(q, refs, k=2, metric="dtw", metric_params={"r": r}, return_distance=True)
         _eq(idx, oi, f"{env} idx"); _eq(dist, od, f"{env} dist")
         st = W.last_stats()
-        counts.add((st["lb_kim_pruned"], st["lb_keogh_pruned"], st["pairs"]))
+        if env["LB_Q"] != "0":
+            counts.add((st["lb_kim_pruned"], st["lb_keogh_pruned"], st["pairs"]))
+        else:
+            one_query = (st["lb_kim_pruned"], st["lb_keogh_pruned"], st["pairs"])
     assert len(counts) == 1, counts
+    # the tiled pass finishes the sums of its stragglers (one pair per lane at the end of a CTA task) where the one-query
+    # kernel hands them to the DP undecided: same LB_Kim count, at least as many LB_Keogh prunes, no more DP pairs
+    tiled = next(iter(counts))
+    assert tiled[0] == one_query[0] and tiled[1] >= one_query[1] and tiled[2] <= one_query[2], (tiled, one_query)
+    # ... and exactly what the one-query kernel decides when it never leaves a block early
+    monkeypatch.setenv("WILDBOAR_CUDA_LB_Q", "0"); monkeypatch.setenv("WILDBOAR_CUDA_LB_STRAG", "0,0")
+    for k_ in ("LB_BS", "LB_MINB", "LB_RB"):
+        monkeypatch.delenv("WILDBOAR_CUDA_" + k_, raising=False)
+    idx, dist = W.argmin_distance(q, refs, k=2, metric="dtw", metric_params={"r": r}, return_distance=True)
+    _eq(idx, oi, "no stragglers idx"); _eq(dist, od, "no stragglers dist")
+    st = W.last_stats()
+    assert (st["lb_kim_pruned"], st["lb_keogh_pruned"], st["pairs"]) == tiled, (st, tiled)

@@ -137,25 +137,36 @@ __global__ void __launch_bounds__(128) k_replay(ReplayArgs a) {
     long long* hi = a.hidx + q * a.k;
     double* hv = a.hval + q * a.k;
     const double* drow = a.d + q * a.ld;
-    for (long long jj = 0; jj < a.ncols; jj += 32) {
-      const long long j = jj + lane;
-      const double dv = (j < a.ncols) ? drow[j] : WB_INF;
-      unsigned mask = __ballot_sync(0xffffffffu, dv < t);
-      while (mask) {
-        const int src = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const double ds = __shfl_sync(0xffffffffu, dv, src);
-        const long long js = jj + src;
-        bool acc = ds < t;
-        if (acc && a.lb) acc = !(a.lb[q * a.ld + js] >= t);
-        if (acc && a.m) acc = !(a.m[q * a.ld + js] > ea_threshold(a.kind, t, a.scale));
-        if (acc) {
-          if (lane == 0) {
-            heap_push(hi, hv, n, a.k, a.c0 + js, ds);
-            t = (n == a.k) ? hv[0] : WB_INF;
+    // eight groups of 32 columns per trip: the loads of a trip are issued together (one warp walks a whole row, and with
+    // one load in flight at a time the kernel ran at the latency of a dependent chain: 33 us for a 33 MB chunk matrix)
+    for (long long j0 = 0; j0 < a.ncols; j0 += 256) {
+      double dvs[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const long long j = j0 + u * 32 + lane;
+        dvs[u] = (j < a.ncols) ? __ldcs(drow + j) : WB_INF;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const long long jj = j0 + u * 32;
+        const double dv = dvs[u];
+        unsigned mask = __ballot_sync(0xffffffffu, dv < t);
+        while (mask) {
+          const int src = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const double ds = __shfl_sync(0xffffffffu, dv, src);
+          const long long js = jj + src;
+          bool acc = ds < t;
+          if (acc && a.lb) acc = !(a.lb[q * a.ld + js] >= t);
+          if (acc && a.m) acc = !(a.m[q * a.ld + js] > ea_threshold(a.kind, t, a.scale));
+          if (acc) {
+            if (lane == 0) {
+              heap_push(hi, hv, n, a.k, a.c0 + js, ds);
+              t = (n == a.k) ? hv[0] : WB_INF;
+            }
+            t = __shfl_sync(0xffffffffu, t, 0);
+            n = __shfl_sync(0xffffffffu, n, 0);
           }
-          t = __shfl_sync(0xffffffffu, t, 0);
-          n = __shfl_sync(0xffffffffu, n, 0);
         }
       }
     }
@@ -249,6 +260,55 @@ __global__ void k_envelope_casc(const double* __restrict__ y, long long n, long 
     if (pos == 0) { y0[s] = p[0]; yL[s] = p[T - 1]; }
   }
 }
+// The same operands through a shared-memory tile: a CTA takes 32 consecutive series, reads their rows coalesced into a
+// tile (row stride T + 1: lanes = series hit distinct banks), and writes the transposed arrays with lanes = series.  The
+// plain kernel above reads every window straight from global memory with lanes = series, i.e. 32 sectors per load
+// (5.1 ms for 200 000 x 256, 240 GB/s; this one moves the 1.2 GB at memory speed).
+__global__ void __launch_bounds__(256) k_envelope_casc_tile(const double* __restrict__ y, long long n, long long s0, long long ns, int T,
+                                                            int w, int stride, float2* __restrict__ envT, float2* __restrict__ yvT,
+                                                            double* __restrict__ y0, double* __restrict__ yL) {
+  extern __shared__ double env_tile[];  // 32 x (T + 1)
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const int ldt = T + 1;
+  const long long nblk = (ns + 31) / 32;
+  for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const long long sb = s0 + blk * 32;
+    const int nsb = (int)min(32LL, s0 + ns - sb);
+    const double* src = y + sb * T;
+    for (int e = tid; e < nsb * T; e += 256) {
+      const int r = e / T;
+      env_tile[r * ldt + (e - r * T)] = src[e];
+    }
+    __syncthreads();
+    if (lane < nsb) {
+      const double* p = env_tile + lane * ldt;
+      for (int pos = wrp; pos < T; pos += 8) {
+        const int k = (int)(((long long)pos * stride) % T);
+        const int a = max(0, k - w), b = min(T - 1, k + w);
+        double l = p[a], h = p[a];
+        for (int q = a + 1; q <= b; ++q) { const double v = p[q]; l = fmin(l, v); h = fmax(h, v); }
+        const long long o = (long long)pos * n + sb + lane;
+        envT[o] = make_float2(__double2float_rd(l), __double2float_ru(h));
+        yvT[o] = make_float2(__double2float_rd(p[k]), __double2float_ru(p[k]));
+        if (pos == 0) { y0[sb + lane] = p[0]; yL[sb + lane] = p[T - 1]; }
+      }
+    }
+    __syncthreads();
+  }
+}
+inline void launch_envelope_casc(cudaStream_t st, const double* y, long long n, long long s0, long long ns, int T, int w, int stride,
+                                 float2* envT, float2* yvT, double* y0, double* yL) {
+  const size_t smem = (size_t)32 * (T + 1) * sizeof(double);
+  if (smem <= ((size_t)200 << 10) && !getenv("WILDBOAR_CUDA_ENVELOPE_PLAIN")) {
+    cudaFuncSetAttribute(k_envelope_casc_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const long long nblk = (ns + 31) / 32;
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)220 << 10) / smem));
+    k_envelope_casc_tile<<<(unsigned)std::max<long long>(1, std::min<long long>(148LL * per_sm, nblk)), 256, smem, st>>>(y, n, s0, ns, T, w, stride, envT, yvT, y0, yL);
+  } else {
+    const long long nb = std::max<long long>(1, std::min<long long>(2048, (ns * T + 255) / 256));
+    k_envelope_casc<<<(unsigned)nb, 256, 0, st>>>(y, n, s0, ns, T, w, stride, envT, yvT, y0, yL);
+  }
+}
 __global__ void k_query_casc(const double* __restrict__ x, long long n, int T, int w, int stride, float4* __restrict__ qf) {
   const long long total = n * (long long)T;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -281,7 +341,12 @@ struct LbArgs {
   const double* thr2;  // per query: the chunk's abandon threshold in the DP's raw (squared) domain, INF = none yet
   double* d; long long ld;  // chunk matrix: +INF = pruned, -1 = survivor (to be filled by the DP)
   unsigned long long* n_kim; unsigned long long* n_keogh;  // pruning statistics
-  int* counts;  // (nq) survivors per query row of this chunk (zeroed by the caller), or nullptr
+  // survivors are appended to `list` as (query, chunk column) through the cursor `list_len` (zeroed by the caller; one atomic
+  // per (query, block) subtask): the DP's work list comes out of this pass directly -- no pass over the chunk matrix to
+  // count and collect them (4 ms of a 36 ms call).  The order of the list is whatever order the warps finish in; every
+  // pair is evaluated independently and lands in d[i][j], so the result does not depend on it.
+  int2* list; int* list_len;
+  unsigned long long* n_surv;  // statistics
   int strag_n, strag_after;  // a (query, block) subtask with <= strag_n unpruned lanes after step strag_after hands them to the DP
 };
 
@@ -293,8 +358,16 @@ struct LbArgs {
 // long_scoreboard 10.8 per issued instruction, issue active 36 %; now L1 hit 65 %, 0.435 -> 0.28 ms per launch).  The warps
 // are not synchronised -- each leaves its task when its own 32 pairs are decided -- they merely start together.
 // Kept as the fallback of k_lb_prune_tile for series too long for its shared-memory query tiles.
-// `counts` (optional): survivors per query row of this chunk, accumulated with one atomic per warp task (zeroed by the
-// caller) -- replaces a separate pass over the chunk matrix.
+// warp-aggregated append of this warp's survivors (query i, chunk columns jl) to the DP's work list; returns their number
+__device__ __forceinline__ int lb_append(const LbArgs& a, int lane, bool sv, long long i, long long jl) {
+  const unsigned m = __ballot_sync(0xffffffffu, sv);
+  if (!m) return 0;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(a.list_len, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (sv) a.list[base + __popc(m & ((1u << lane) - 1u))] = make_int2((int)i, (int)jl);
+  return __popc(m);
+}
 __global__ void __launch_bounds__(256) k_lb_prune(LbArgs a) {
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -302,7 +375,7 @@ __global__ void __launch_bounds__(256) k_lb_prune(LbArgs a) {
   const long long nqg = (a.nq + wpb - 1) / wpb;
   const long long nct = nqg * nyb;
   const int T = a.T;
-  unsigned long long c_kim = 0, c_keogh = 0;  // per-warp statistics (lane 0), one atomic per warp at the end
+  unsigned long long c_kim = 0, c_keogh = 0, c_surv = 0;  // per-warp statistics (lane 0), one atomic per warp at the end
   for (long long ct = blockIdx.x; ct < nct; ct += gridDim.x) {
     const long long qg = ct / nyb;
     const long long i = qg * wpb + wib;
@@ -374,14 +447,12 @@ __global__ void __launch_bounds__(256) k_lb_prune(LbArgs a) {
       }
     }
     if (valid) a.d[i * a.ld + jl] = pruned ? WB_INF : -1.0;
-    if (a.counts) {
-      const int nsv = __popc(__ballot_sync(0xffffffffu, valid && !pruned));
-      if (lane == 0 && nsv) atomicAdd(a.counts + i, nsv);
-    }
+    c_surv += lb_append(a, lane, valid && !pruned, i, jl);
   }
   if (lane == 0) {
     if (c_kim) atomicAdd(a.n_kim, c_kim);
     if (c_keogh) atomicAdd(a.n_keogh, c_keogh);
+    if (c_surv) atomicAdd(a.n_surv, c_surv);
   }
 }
 
@@ -422,13 +493,19 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 
 struct LbQMeta { double lim, x0, xL; };  // per query of a tile: prune limit (INF: no threshold yet), first / last sample
 
-inline size_t lb_tile_smem(int Q, int T) { return 2 * ((size_t)Q * T * sizeof(float4) + Q * sizeof(LbQMeta)) + 64; }  // + 2 mbarriers, 4 counters
+// a (query, reference) pair whose block of 32 was left by the straggler rule: continued lane-per-pair at the end of the CTA task
+struct LbStrag { int q, jl, k; float s1, s2; };
+// queue entries per task buffer: every (query, block) subtask of a task can queue strag_n pairs, so nothing overflows
+inline int lb_tile_qcap(int Q, int rb_per_task, int strag_n) { return Q * rb_per_task * std::max(strag_n, 0); }
+inline size_t lb_tile_smem(int Q, int T, int qcap) {
+  return 2 * ((size_t)Q * T * sizeof(float4) + Q * sizeof(LbQMeta) + (size_t)qcap * sizeof(LbStrag)) + 64;  // + 2 mbarriers, 6 counters
+}
 
 // Q queries per warp task, BS time steps per register block (4: 3 CTAs of 8 warps per SM; 8: 2), MINB = CTAs per SM the
 // register budget is cut for.  No CTA-wide barrier in the task loop: a buffer is handed back through a shared counter,
 // and the LAST warp to finish a task stages the CTA's task after next into the buffer it has just freed.
 template <int Q, int BS, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_lb_prune_tile(LbArgs a, int rb_per_task) {
+__global__ void __launch_bounds__(256, MINB) k_lb_prune_tile(LbArgs a, int rb_per_task, int qcap) {
   static_assert(BS == 4 || BS == 8, "block of 4 or 8 time steps");
   extern __shared__ __align__(128) unsigned char lb_smem[];
   const int T = a.T;
@@ -437,6 +514,8 @@ __global__ void __launch_bounds__(256, MINB) k_lb_prune_tile(LbArgs a, int rb_pe
   unsigned long long* const mbar = reinterpret_cast<unsigned long long*>(meta + 2 * Q);  // [2]
   int* const s_next = reinterpret_cast<int*>(mbar + 2);                        // [2] next reference block of the task
   int* const s_done = s_next + 2;                                              // [2] warps that have finished the task
+  int* const s_qn = s_done + 2;                                                // [2] stragglers queued by the task
+  LbStrag* const s_q = reinterpret_cast<LbStrag*>(s_qn + 4);                   // [2][qcap]
   const int tid = threadIdx.x, lane = tid & 31, wpb = blockDim.x >> 5;
   const long long nyb = (a.nc + 31) / 32;
   const long long nqg = (a.nq + Q - 1) / Q;
@@ -444,7 +523,7 @@ __global__ void __launch_bounds__(256, MINB) k_lb_prune_tile(LbArgs a, int rb_pe
   const long long per = (nyb + nsplit - 1) / nsplit;
   const long long nct = nqg * nsplit;
   const long long ny = a.ny;
-  unsigned long long c_kim = 0, c_keogh = 0;
+  unsigned long long c_kim = 0, c_keogh = 0, c_surv = 0;
 
   // stage task `ct` into buffer b (one whole warp): lanes 0..Q-1 write the per-query scalars, lane 0 resets the block
   // counter and starts the bulk copy of the Q query rows; its arrive (release) publishes all of it with the data
@@ -466,6 +545,7 @@ __global__ void __launch_bounds__(256, MINB) k_lb_prune_tile(LbArgs a, int rb_pe
       const unsigned bytes = (unsigned)(min((long long)Q, a.nq - i0) * T * (long long)sizeof(float4));
       s_next[b] = (int)((ct - qg * nsplit) * per);
       s_done[b] = 0;
+      s_qn[b] = 0;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the buffer's last generic reads precede the async write
       mbar_expect_tx(&mbar[b], bytes);
       bulk_g2s(qs + (size_t)b * Q * T, a.qf + i0 * T, bytes, &mbar[b]);
@@ -510,6 +590,7 @@ __global__ void __launch_bounds__(256, MINB) k_lb_prune_tile(LbArgs a, int rb_pe
       float limf[Q], s1[Q], s2[Q];
       unsigned active = 0;   // bit q (warp uniform): query q is still summing
       unsigned prm = 0;      // bit q (per lane): this lane's pair with query q is pruned
+      unsigned dfr = 0;      // bit q (per lane): this lane's pair with query q was queued as a straggler (decided later)
       // LB_Kim: every warping path contains (0,0) and (T-1,T-1)
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
@@ -553,8 +634,22 @@ __global__ void __launch_bounds__(256, MINB) k_lb_prune_tile(LbArgs a, int rb_pe
                 for (int u = 0; u < 4; ++u) step(s1[q], s2[q], lh[h + u], yy[h + u], v[u]);
               }
               if (vote) {
-                const int alive = __popc(__ballot_sync(0xffffffffu, !(((prm >> q) & 1u) || s1[q] > limf[q] || s2[q] > limf[q])));
-                if (alive == 0 || (alive <= a.strag_n && kb + BS - 1 >= a.strag_after)) active &= ~(1u << q);
+                const bool open = !(((prm >> q) & 1u) || s1[q] > limf[q] || s2[q] > limf[q]);
+                const int alive = __popc(__ballot_sync(0xffffffffu, open));
+                if (alive == 0) active &= ~(1u << q);
+                else if (alive <= a.strag_n && kb + BS - 1 >= a.strag_after) {
+                  // a straggler or two: the warp leaves, the open pairs are queued with their sums and continued one pair
+                  // per lane when the CTA task ends (the queue holds strag_n entries per subtask of the task, so it cannot overflow)
+                  active &= ~(1u << q);
+                  if (open && valid && kb + BS < T) {
+                    const int slot = atomicAdd(&s_qn[b], 1);
+                    if (slot < qcap) {
+                      LbStrag e; e.q = q; e.jl = (int)jl; e.k = kb + BS; e.s1 = s1[q]; e.s2 = s2[q];
+                      s_q[b * qcap + slot] = e;
+                      dfr |= 1u << q;
+                    }
+                  }
+                }
               }
             }
           };
@@ -590,15 +685,13 @@ __global__ void __launch_bounds__(256, MINB) k_lb_prune_tile(LbArgs a, int rb_pe
         const bool pk = (prm >> q) & 1u;
         // limf = 0 with zero sums where no Keogh pass ran (no threshold, or LB_Kim pruned all 32): 0 > 0 is false
         const bool p2 = pk || s1[q] > limf[q] || s2[q] > limf[q];
+        const bool later = (dfr >> q) & 1u;  // queued: written by whoever drains the queue
         c_keogh += __popc(__ballot_sync(0xffffffffu, p2 && !pk && valid));
-        if (valid) a.d[i * a.ld + jl] = p2 ? WB_INF : -1.0;
-        if (a.counts) {
-          const int nsv = __popc(__ballot_sync(0xffffffffu, valid && !p2));
-          if (lane == 0 && nsv) atomicAdd(a.counts + i, nsv);
-        }
+        if (valid && !later) a.d[i * a.ld + jl] = p2 ? WB_INF : -1.0;
+        c_surv += lb_append(a, lane, valid && !p2 && !later, i, jl);
       }
     }
-    // hand the buffer back; the last warp refills it for the CTA's task after next
+    // hand the buffer back; the last warp drains the task's straggler queue and refills the buffer for the CTA's task after next
     __syncwarp();
     int last = 0;
     if (lane == 0) {
@@ -607,11 +700,51 @@ __global__ void __launch_bounds__(256, MINB) k_lb_prune_tile(LbArgs a, int rb_pe
       __threadfence_block();
     }
     last = __shfl_sync(0xffffffffu, last, 0);
-    if (last && ct + 2LL * gridDim.x < nct) stage(ct + 2LL * gridDim.x, b);
+    if (last) {
+      // stragglers of this task, one pair per lane: the rest of the two LB_Keogh sums from where the block left them.  The
+      // task's reference rows are hot in L2, its query rows still in this buffer; 32 undecided pairs cost one warp a few
+      // thousand instructions here against 32 full DPs (80 000 instructions each) if they were handed on.
+      const int nqd = min(s_qn[b], qcap);
+      for (int base = 0; base < nqd; base += 32) {
+        const bool has = base + lane < nqd;
+        LbStrag e; e.q = 0; e.jl = 0; e.k = T; e.s1 = 0.0f; e.s2 = 0.0f;
+        if (has) e = s_q[b * qcap + base + lane];
+        const float limq = __double2float_ru(mt[e.q].lim);
+        const float4* qq = qf + e.q * T;
+        const long long j = a.c0 + e.jl;
+        const float2* env = a.envT + (long long)e.k * ny + j;
+        const float2* yv = a.yvT + (long long)e.k * ny + j;
+        float t1 = e.s1, t2 = e.s2;
+        int k = e.k;
+        auto step1 = [&](const float2 lh, const float2 yy, const float4 v) {
+          const float e1 = fmaxf(fmaxf(__fsub_rd(v.x, lh.y), __fsub_rd(lh.x, v.y)), 0.0f);
+          t1 = __fmaf_rd(e1, e1, t1);
+          const float e2 = fmaxf(fmaxf(__fsub_rd(yy.x, v.w), __fsub_rd(v.z, yy.y)), 0.0f);
+          t2 = __fmaf_rd(e2, e2, t2);
+        };
+        while (k + 8 <= T && !(t1 > limq || t2 > limq)) {
+          float2 lh[8], yy[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { lh[u] = env[u * ny]; yy[u] = yv[u * ny]; }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) step1(lh[u], yy[u], qq[k + u]);
+          env += 8 * ny; yv += 8 * ny; k += 8;
+        }
+        if (!(t1 > limq || t2 > limq)) {
+          for (; k < T; ++k) { step1(*env, *yv, qq[k]); env += ny; yv += ny; }
+        }
+        const bool p2 = t1 > limq || t2 > limq;
+        c_keogh += __popc(__ballot_sync(0xffffffffu, has && p2));
+        if (has) a.d[(i0 + e.q) * a.ld + e.jl] = p2 ? WB_INF : -1.0;
+        c_surv += lb_append(a, lane, has && !p2, i0 + e.q, e.jl);
+      }
+      if (ct + 2LL * gridDim.x < nct) stage(ct + 2LL * gridDim.x, b);
+    }
   }
   if (lane == 0) {
     if (c_kim) atomicAdd(a.n_kim, c_kim);
     if (c_keogh) atomicAdd(a.n_keogh, c_keogh);
+    if (c_surv) atomicAdd(a.n_surv, c_surv);
   }
 }
 
@@ -709,44 +842,6 @@ __global__ void k_seed_min(const double* __restrict__ cd, long long nq, double* 
 }
 __global__ void k_set_int(int* p, int v) { *p = v; }
 
-// survivors per query row (counted by k_lb_prune) -> exclusive scan -> (i, j) list sorted by (i, j)
-__global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ counts, long long nq, int* __restrict__ starts,
-                                                      int* __restrict__ total, unsigned long long* __restrict__ grand_total) {
-  __shared__ int part[1024];
-  const int tid = threadIdx.x;
-  const long long per = (nq + 1023) / 1024;
-  const long long lo = tid * per, hi = min(nq, lo + per);
-  int s = 0;
-  for (long long q = lo; q < hi; ++q) s += counts[q];
-  part[tid] = s;
-  __syncthreads();
-  if (tid == 0) {
-    int acc = 0;
-    for (int k = 0; k < 1024; ++k) { const int v = part[k]; part[k] = acc; acc += v; }
-    *total = acc;
-    atomicAdd(grand_total, (unsigned long long)acc);
-  }
-  __syncthreads();
-  int acc = part[tid];
-  for (long long q = lo; q < hi; ++q) { starts[q] = acc; acc += counts[q]; }
-}
-__global__ void __launch_bounds__(128) k_fill_list(const double* __restrict__ d, long long nq, long long nc, long long ld,
-                                                   const int* __restrict__ starts, int2* __restrict__ list) {
-  const int lane = threadIdx.x & 31;
-  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long q = wid; q < nq; q += nw) {
-    int base = starts[q];
-    for (long long jj = 0; jj < nc; jj += 32) {
-      const long long j = jj + lane;
-      const bool sv = j < nc && d[q * ld + j] < 0.0;
-      const unsigned m = __ballot_sync(0xffffffffu, sv);
-      if (sv) list[base + __popc(m & ((1u << lane) - 1u))] = make_int2((int)q, (int)j);
-      base += __popc(m);
-    }
-  }
-}
-
 // LaunchFn(r0, nrows, c0, ncols, out, ld, out_m, thr, stats) -> int
 template <class WS, class DI, class Call, class LaunchFn>
 int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stats, LaunchFn launch) {
@@ -772,7 +867,15 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
   // (they run dense or nearly so) and the later ones large (few launches: with one query every chunk is ~6 launches of
   // almost no work).  The chunk grows 4x per step from 1024 columns up to C = min(32768, 4 Mi / nq) -- nq * C values per
   // buffer; for the cfg4 share (2500 queries) that is 128, 512, then 1600; for one query 1024, 4096, 16384, 32768, ...
-  long long C = (4LL << 20) / std::max<long long>(nq, 1);
+  // Threshold seeding (k = 1, see k_seed_candidates) is decided here because it changes the schedule: with thresholds that
+  // are close to final from the start, a stale chunk-start threshold costs little, so the chunks are four times as wide
+  // (32 Mi values per buffer: an eighth of the launches; cfg4 share: kernels 55.7 ms at 1600 columns, 36.1 at 6400, 32.8 at 12 800) and there is no dense first chunk to keep small.
+  const long long seed_from = io.y_host ? std::min<long long>(ny, std::max<long long>(1, piped_piece_bytes() / (long long)(sizeof(double) * c.Ty))) : ny;
+  long long seed_min = 2048;
+  if (const char* e = getenv("WILDBOAR_CUDA_SEED_MIN")) seed_min = std::max<long long>(256, atoll(e));  // test knob
+  const bool will_seed = io.use_device_lb && c.metric == M_DTW && c.ptx == c.pty && c.ptx >= 2 && !c.degenerate && k == 1 &&
+                         seed_from >= seed_min && nq * (long long)kSeedNC < 2000000000LL && !getenv("WILDBOAR_CUDA_NO_SEED");
+  long long C = ((will_seed ? 32LL : 4LL) << 20) / std::max<long long>(nq, 1);
   C = std::max<long long>(32, std::min<long long>(32768, (C / 32) * 32));
   // first chunk: it runs without thresholds (every pair in full), so just enough pairs to fill the device -- 256 Ki --
   // between 128 and 1024 columns (cfg4 share, 2500 queries: 128 columns; kernels 81 -> 75 ms against 1024)
@@ -796,12 +899,11 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
                        nq * C < 2000000000LL;
   float4* qf = nullptr; float2 *envT = nullptr, *yvT = nullptr;
   double *y0 = nullptr, *yL = nullptr;
-  int *counts = nullptr, *starts = nullptr, *list_len = nullptr; int2* list = nullptr;
+  int* list_len = nullptr; int2* list = nullptr;
   unsigned long long* lbstat = nullptr;  // [0] kim-pruned, [1] keogh-pruned, [2] survivors
   if (cascade) {
     const int T = c.ptx, w = std::max(c.R - 1, 0);
-    if (ws.alloc(&qf, (size_t)nq * T) || ws.alloc(&counts, (size_t)nq) ||
-        ws.alloc(&starts, (size_t)nq) || ws.alloc(&list_len, 1) || ws.alloc(&list, (size_t)nq * C) ||
+    if (ws.alloc(&qf, (size_t)nq * T) || ws.alloc(&list_len, 1) || ws.alloc(&list, (size_t)nq * C) ||
         ws.alloc(&lbstat, 3)) return 1;
     if (cudaMemsetAsync(lbstat, 0, 3 * sizeof(unsigned long long), st) != cudaSuccess) return 1;
     const int stride = lb_time_stride(T);
@@ -817,7 +919,7 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
             cudaMallocAsync((void**)&cc->yvT, sizeof(float2) * (size_t)ny * T, st) != cudaSuccess ||
             cudaMallocAsync((void**)&cc->y0, sizeof(double) * (size_t)ny, st) != cudaSuccess ||
             cudaMallocAsync((void**)&cc->yL, sizeof(double) * (size_t)ny, st) != cudaSuccess) { cudaGetLastError(); return 1; }
-        k_envelope_casc<<<2048, 256, 0, st>>>(c.py, ny, 0, ny, T, w, stride, cc->envT, cc->yvT, cc->y0, cc->yL);
+        launch_envelope_casc(st, c.py, ny, 0, ny, T, w, stride, cc->envT, cc->yvT, cc->y0, cc->yL);
         if (cudaStreamSynchronize(st) != cudaSuccess) return 1;
         cc->T = T; cc->w = w; cc->stride = stride; cc->ny = ny; cc->py = c.py; cc->valid = true;
       }
@@ -829,7 +931,7 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
     if (!cached) {
       if (ws.alloc(&envT, (size_t)ny * T) || ws.alloc(&yvT, (size_t)ny * T) || ws.alloc(&y0, (size_t)ny) || ws.alloc(&yL, (size_t)ny)) return 1;
       // host-resident references: the operands are built piece by piece as the rows arrive (ensure_refs)
-      if (!io.y_host) k_envelope_casc<<<2048, 256, 0, st>>>(c.py, ny, 0, ny, T, w, stride, envT, yvT, y0, yL);
+      if (!io.y_host) launch_envelope_casc(st, c.py, ny, 0, ny, T, w, stride, envT, yvT, y0, yL);
     }
   }
   // ---- pipelined upload of host-resident references ----
@@ -856,8 +958,7 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
         : cudaMemcpy2DAsync(dst, sizeof(double) * Ty, src, sizeof(double) * io.y_hs, sizeof(double) * Ty, rows, cudaMemcpyHostToDevice, io.up_stream);
     if (e != cudaSuccess || cudaEventRecord(up_ev, io.up_stream) != cudaSuccess || cudaStreamWaitEvent(st, up_ev, 0) != cudaSuccess) return 1;
     if (cascade && envT) {
-      const long long nblk = std::max<long long>(1, std::min<long long>(2048, (rows * c.ptx + 255) / 256));
-      k_envelope_casc<<<(unsigned)nblk, 256, 0, st>>>(c.py, ny, up_done, rows, c.ptx, std::max(c.R - 1, 0), lb_time_stride(c.ptx), envT, yvT, y0, yL);
+      launch_envelope_casc(st, c.py, ny, up_done, rows, c.ptx, std::max(c.R - 1, 0), lb_time_stride(c.ptx), envT, yvT, y0, yL);
     }
     up_done = to;
     return 0;
@@ -873,13 +974,11 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
   int rc = 0;
   // ---- threshold seeding (k = 1; see k_seed_candidates) ----
   double* seed2 = nullptr;
-  if (cascade && k == 1 && !getenv("WILDBOAR_CUDA_NO_SEED")) {
+  if (cascade && will_seed) {
     // references the candidates are drawn from: all of them when they are resident, the first piece of a pipelined upload
     if (io.y_host) rc = ensure_refs(1);
     const long long S = up_done;
-    long long s_min = 2048;
-    if (const char* e = getenv("WILDBOAR_CUDA_SEED_MIN")) s_min = std::max<long long>(256, atoll(e));  // test knob
-    if (!rc && S >= s_min && nq * (long long)kSeedNC < 2000000000LL) {
+    if (!rc && S >= seed_min) {
       float *rp = nullptr, *qp = nullptr; int2* cl = nullptr; int* cl_len = nullptr; double* cd = nullptr;
       if (ws.alloc(&rp, (size_t)S * kSeedP) || ws.alloc(&qp, (size_t)nq * kSeedP) || ws.alloc(&cl, (size_t)nq * kSeedNC) ||
           ws.alloc(&cl_len, 1) || ws.alloc(&cd, (size_t)nq * kSeedNC) || ws.alloc(&seed2, (size_t)nq)) rc = 1;
@@ -915,26 +1014,28 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
       LbArgs la;
       la.x = c.px; la.qf = qf; la.envT = envT; la.yvT = yvT; la.y0 = y0; la.yL = yL;
       la.nq = nq; la.ny = ny; la.c0 = c0; la.nc = nc; la.T = c.ptx; la.thr2 = thr; la.d = dbuf; la.ld = C;
-      la.n_kim = lbstat; la.n_keogh = lbstat + 1; la.counts = counts;
+      la.n_kim = lbstat; la.n_keogh = lbstat + 1; la.n_surv = lbstat + 2; la.list = list; la.list_len = list_len;
       la.strag_n = kLbStragglers; la.strag_after = kLbStragglerAfter;
       if (const char* e = getenv("WILDBOAR_CUDA_LB_STRAG")) {  // tuning knob "n,after"
         int n_ = 0, a_ = 0;
         if (sscanf(e, "%d,%d", &n_, &a_) == 2) { la.strag_n = n_; la.strag_after = a_; }
       }
-      if (cudaMemsetAsync(counts, 0, sizeof(int) * nq, st) != cudaSuccess) { rc = 1; break; }
+      if (cudaMemsetAsync(list_len, 0, sizeof(int), st) != cudaSuccess) { rc = 1; break; }
       {
         // register-tiled pass with shared-memory query tiles when they fit (two buffers of Q x T float4), else one query per warp
         const char* lbq_env = getenv("WILDBOAR_CUDA_LB_Q");  // tuning / test knob: 0 = the one-query kernel
         int lbq = lbq_env ? atoi(lbq_env) : 4;
-        while (lbq > 1 && lb_tile_smem(lbq, c.ptx) > (size_t)96 << 10) lbq >>= 1;
-        if (nq < 2 || lbq < 2) lbq = 0;
         const char* rbt_env = getenv("WILDBOAR_CUDA_LB_RB");
-        const int rbt = (rbt_env && atoi(rbt_env) > 0) ? atoi(rbt_env) : 16;  // reference blocks per CTA task
+        const int rbt = (rbt_env && atoi(rbt_env) > 0) ? std::min(atoi(rbt_env), 64) : 16;  // reference blocks per CTA task
+        la.strag_n = std::min(la.strag_n, 8);
+        while (lbq > 1 && lb_tile_smem(lbq, c.ptx, lb_tile_qcap(lbq, rbt, la.strag_n)) > (size_t)96 << 10) lbq >>= 1;
+        if (nq < 2 || lbq < 2) lbq = 0;
+        const int qcap = lb_tile_qcap(lbq, rbt, la.strag_n);
         const char* bs_env = getenv("WILDBOAR_CUDA_LB_BS");
         const int lbs = (bs_env && atoi(bs_env) == 8) ? 8 : 4;  // time steps per register block
         auto go = [&](auto kern, int per_sm) {
           cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 << 10);
-          kern<<<148 * per_sm, 256, lb_tile_smem(lbq, c.ptx), st>>>(la, rbt);
+          kern<<<148 * per_sm, 256, lb_tile_smem(lbq, c.ptx, qcap), st>>>(la, rbt, qcap);
         };
         const char* mb_env = getenv("WILDBOAR_CUDA_LB_MINB");
         const int mb = (mb_env && atoi(mb_env) == 2) ? 2 : 3;  // CTAs per SM the register budget is cut for (BS = 4)
@@ -943,12 +1044,10 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
         else if (lbq >= 2) go(k_lb_prune_tile<2, 4, 3>, 3);
         else k_lb_prune<<<148 * 8, 256, 0, st>>>(la);
       }
-      k_scan_counts<<<1, 1024, 0, st>>>(counts, nq, starts, list_len, lbstat + 2);
-      k_fill_list<<<148 * 4, 128, 0, st>>>(dbuf, nq, nc, C, starts, list);
       c.mode = PM_LIST; c.list = list; c.list_len = list_len;
       rc = launch(0, nq, c0, nc, dbuf, C, nullptr, thr, nullptr);
       c.mode = PM_PAIRWISE; c.list = nullptr; c.list_len = nullptr;
-      if (stats) stats->launches += 4;  // k_lb_prune, k_scan_counts, k_fill_list, the DP
+      if (stats) stats->launches += 2;  // the LB pass, the DP
       if (rc) break;
     } else {
       rc = launch(0, nq, c0, nc, dbuf, C, mbuf, (kind == TK_NONE || kind == TK_LCSS) ? nullptr : thr, stats);

@@ -44,7 +44,7 @@ struct KArgsT {
   long long row0;     // PM_SELF: global index of local x row 0 (row-sharded self join)
   int mirror;         // PM_SELF: also write element (j, i) of the full n x n matrix that `out` is a row block of (`out` = row
                       //   `row0` of it, ld = n): out[(j - row0) * ld + (i + row0)]  (single-device self join)
-  const int2* list;   // PM_LIST: pairs to evaluate, sorted by (i, j)
+  const int2* list;   // PM_LIST: pairs to evaluate, in any order (the cascade appends them as its warps finish)
   const int* list_len;  // PM_LIST: number of pairs (device resident: no host round trip)
   F* gring;           // strip engine, GRING variant: boundary buffers in global memory, [warp][slot][lane]
   F* scratch;         // row-scan engine: 2 rows per thread, interleaved
