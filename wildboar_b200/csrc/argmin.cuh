@@ -700,6 +700,7 @@ __global__ void __launch_bounds__(256, MINB) k_lb_prune_tile(LbArgs a, int rb_pe
       __threadfence_block();
     }
     last = __shfl_sync(0xffffffffu, last, 0);
+    __syncwarp();  // lane 0's fence + atomic order the other warps' queue entries before every lane's reads below
     if (last) {
       // stragglers of this task, one pair per lane: the rest of the two LB_Keogh sums from where the block left them.  The
       // task's reference rows are hot in L2, its query rows still in this buffer; 32 undecided pairs cost one warp a few
@@ -779,6 +780,8 @@ __global__ void k_seed_sketch(const double* __restrict__ x, long long n, int T, 
 }
 
 // per query the kSeedNC best of the 256 threads' own best reference (thread t scans references t, t + 256, ...)
+// blockIdx.y = slice of the references (few queries: one CTA per query group would scan all of them alone -- 1.5 ms for
+// 200 000 references); every (query, slice) contributes its own kSeedNC candidates
 __global__ void __launch_bounds__(256) k_seed_candidates(const float* __restrict__ qp, const float* __restrict__ rp, long long nq,
                                                          long long S, int2* __restrict__ cl) {
   __shared__ float sq[kSeedQB][kSeedP];
@@ -794,7 +797,9 @@ __global__ void __launch_bounds__(256) k_seed_candidates(const float* __restrict
   float best[kSeedQB]; int bidx[kSeedQB];
 #pragma unroll
   for (int q = 0; q < kSeedQB; ++q) { best[q] = 3.0e38f; bidx[q] = -1; }
-  for (long long j = tid; j < S; j += 256) {
+  const int nsl = gridDim.y, sl = blockIdx.y;
+  const long long j_lo = S * sl / nsl, j_hi = S * (sl + 1) / nsl;
+  for (long long j = j_lo + tid; j < j_hi; j += 256) {
     float r[kSeedP];
 #pragma unroll
     for (int p = 0; p < kSeedP; ++p) r[p] = rp[(long long)p * S + j];
@@ -824,7 +829,7 @@ __global__ void __launch_bounds__(256) k_seed_candidates(const float* __restrict
 #pragma unroll
       for (int w = 1; w < 8; ++w) if (sv[w] < bv) { bv = sv[w]; bt = st[w]; }
       if (tid == bt && q0 + q < nq) {
-        cl[(q0 + q) * kSeedNC + r] = make_int2((int)(q0 + q), bidx[q] < 0 ? 0 : bidx[q]);
+        cl[((q0 + q) * nsl + sl) * kSeedNC + r] = make_int2((int)(q0 + q), bidx[q] < 0 ? (int)j_lo : bidx[q]);
         v = 3.4e38f;  // taken
       }
       __syncthreads();
@@ -832,12 +837,11 @@ __global__ void __launch_bounds__(256) k_seed_candidates(const float* __restrict
   }
 }
 
-__global__ void k_seed_min(const double* __restrict__ cd, long long nq, double* __restrict__ seed2) {
+__global__ void k_seed_min(const double* __restrict__ cd, long long nq, int per_query, double* __restrict__ seed2) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nq) return;
-  double m = cd[q * kSeedNC];
-#pragma unroll
-  for (int r = 1; r < kSeedNC; ++r) m = fmin(m, cd[q * kSeedNC + r]);
+  double m = cd[q * per_query];
+  for (int r = 1; r < per_query; ++r) m = fmin(m, cd[q * per_query + r]);
   seed2[q] = m;
 }
 __global__ void k_set_int(int* p, int v) { *p = v; }
@@ -979,20 +983,24 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
     if (io.y_host) rc = ensure_refs(1);
     const long long S = up_done;
     if (!rc && S >= seed_min) {
+      // reference slices per query group: enough CTAs to fill the device when the queries are few, each slice >= 256 references
+      const long long ngroups = (nq + kSeedQB - 1) / kSeedQB;
+      const int nsl = (int)std::max<long long>(1, std::min<long long>({32LL, (2LL * 148 + ngroups - 1) / ngroups, S / 256}));
+      const long long ncand = nq * nsl * kSeedNC;
       float *rp = nullptr, *qp = nullptr; int2* cl = nullptr; int* cl_len = nullptr; double* cd = nullptr;
-      if (ws.alloc(&rp, (size_t)S * kSeedP) || ws.alloc(&qp, (size_t)nq * kSeedP) || ws.alloc(&cl, (size_t)nq * kSeedNC) ||
-          ws.alloc(&cl_len, 1) || ws.alloc(&cd, (size_t)nq * kSeedNC) || ws.alloc(&seed2, (size_t)nq)) rc = 1;
+      if (ws.alloc(&rp, (size_t)S * kSeedP) || ws.alloc(&qp, (size_t)nq * kSeedP) || ws.alloc(&cl, (size_t)ncand) ||
+          ws.alloc(&cl_len, 1) || ws.alloc(&cd, (size_t)ncand) || ws.alloc(&seed2, (size_t)nq)) rc = 1;
       if (!rc) {
         const int T = c.ptx;
         k_seed_sketch<true><<<(unsigned)std::min<long long>(148 * 16, (S * kSeedP + 255) / 256), 256, 0, st>>>(c.py, S, T, rp);
         k_seed_sketch<false><<<(unsigned)std::min<long long>(148 * 16, (nq * kSeedP + 255) / 256), 256, 0, st>>>(c.px, nq, T, qp);
-        k_seed_candidates<<<(unsigned)((nq + kSeedQB - 1) / kSeedQB), 256, 0, st>>>(qp, rp, nq, S, cl);
-        k_set_int<<<1, 1, 0, st>>>(cl_len, (int)(nq * kSeedNC));
+        k_seed_candidates<<<dim3((unsigned)ngroups, (unsigned)nsl), 256, 0, st>>>(qp, rp, nq, S, cl);
+        k_set_int<<<1, 1, 0, st>>>(cl_len, (int)ncand);
         const int mode0 = c.mode, raw0 = c.raw;
-        c.mode = PM_LISTP; c.list = cl; c.list_len = cl_len; c.list_n = nq * kSeedNC; c.raw = 1;
+        c.mode = PM_LISTP; c.list = cl; c.list_len = cl_len; c.list_n = ncand; c.raw = 1;
         rc = launch(0, nq, 0, ny, cd, 1, nullptr, nullptr, stats);
         c.mode = mode0; c.list = nullptr; c.list_len = nullptr; c.list_n = 0; c.raw = raw0;
-        k_seed_min<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(cd, nq, seed2);
+        k_seed_min<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(cd, nq, nsl * kSeedNC, seed2);
         if (stats) stats->launches += 5;
         // with thresholds from the start there is no dense first chunk to keep small
         c_first = C;
