@@ -73,6 +73,8 @@ typedef struct wb_stats {
   int32_t strip_nr;     /* rows per fast-path iteration (in-thread wavefront depth); cooperative engine: lanes per pair */
   int32_t strip_warps;  /* warps per CTA                                                       */
   int32_t strip_gring;  /* 1: boundary buffers in global memory (L2), 0: shared memory          */
+  int64_t ambiguous;    /* argmin in neighbour-set mode (use_device_lb bit 1): queries whose k-nearest SET depends on the
+                           scan's history (a pair outside the set ties with the kth distance) -- redo them without the bit */
 } wb_stats;
 
 int wb_cuda_device_count(void);
@@ -117,8 +119,16 @@ int wb_cuda_paired_nd(int metric, const wb_params *params,
 /* k nearest y for every x under the reference's sequential early-abandoning scan.
  * out_idx / out_dist: (nx, k) in the reference heap's array order (utils/_misc.pyx:62-107).
  * lower_bound: optional (nx, ny) matrix, pairs with lower_bound >= running threshold are
- * skipped (CD:1331).  use_device_lb != 0 (dtw only): additionally prune with the on-device
- * LB_Kim / LB_Keogh cascade (never changes the result).
+ * skipped (CD:1331).  use_device_lb bit 0 (dtw only): additionally prune with the on-device
+ * LB_Kim / LB_Keogh cascade; for k = 1 the thresholds are also seeded with the exact distance to
+ * sketch-nearest candidates (neither ever changes the result).
+ * use_device_lb bit 1 (value 2, with bit 0; 1 < k <= 8): neighbour-SET mode for callers that only count
+ * the k nearest (KNeighborsClassifier.predict_proba, _neighbors.py:275-287: class votes).  The
+ * thresholds are seeded for k > 1 as well (kth smallest candidate distance), so out_idx / out_dist hold
+ * the same k neighbours as the reference but in THIS scan's heap order; stats->ambiguous counts the
+ * queries for which a pair outside the set ties with the kth distance (which of the tied pairs the
+ * reference keeps depends on its scan history) -- the caller repeats the call without the bit if it is
+ * not zero.
  * Replaces _argmin_distance, CD:1348-1378. */
 int wb_cuda_argmin(int metric, const wb_params *params,
                    const double *x, int64_t nx, int64_t Tx, int64_t x_stride,

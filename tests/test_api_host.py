@@ -46,6 +46,19 @@ def test_shim_argtypes_match_the_header_prototypes(wb):
     assert checked >= 15
 
 
+def test_shim_structs_match_the_header(wb):
+    """wb_stats / wb_params of the ctypes shim: same members, order and types as the structs of include/wb_cuda.h."""
+    from wildboar_b200 import _shim
+    hdr = open(os.path.join(ROOT, "include", "wb_cuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    ctype = {"double": ctypes.c_double, "int64_t": ctypes.c_int64, "int32_t": ctypes.c_int32, "int": ctypes.c_int}
+    for cname, cls in (("wb_stats", _shim.WbStats), ("wb_params", _shim.WbParams)):
+        body = re.search(r"typedef struct " + cname + r"\s*\{(.*?)\}\s*" + cname + r"\s*;", hdr, flags=re.S).group(1)
+        members = [(t, n) for t, n in re.findall(r"\b(double|int64_t|int32_t|int)\s+([a-z_0-9]+)\s*;", body)]
+        assert [n for _, n in members] == [n for n, _ in cls._fields_], (cname, members, cls._fields_)
+        assert [ctype[t] for t, _ in members] == [c for _, c in cls._fields_], cname
+
+
 def test_no_gpu_means_error_not_fallback(wb):
     if wb.device_count() > 0:
         pytest.skip("a GPU is present")

@@ -699,3 +699,43 @@ def test_lb_prune_kernel_variants_prune_identically(W, oracle, T, r, monkeypatch
     _eq(idx, oi, "no stragglers idx"); _eq(dist, od, "no stragglers dist")
     st = W.last_stats()
     assert (st["lb_kim_pruned"], st["lb_keogh_pruned"], st["pairs"]) == tiled, (st, tiled)
+
+
+def test_argmin_neighbour_set_mode(W, oracle, monkeypatch):
+    """use_device_lb bit 1 (KNeighborsClassifier.predict_proba only counts the k nearest): thresholds seeded for k > 1; the
+    k neighbours per query are the reference's as a SET (and their distances as a multiset), ties at the kth distance are
+    reported as ambiguous and the shim then falls back to the exact scan."""
+    from wildboar_b200 import _shim as sh
+    from wildboar_b200.distance import DtwMetric
+    monkeypatch.setenv("WILDBOAR_CUDA_SEED_MIN", "256")
+    monkeypatch.setenv("WILDBOAR_CUDA_ARGMIN_CHUNK", "128")
+    q, refs = random_walks(60, 96, 91), random_walks(1400, 96, 92)
+    m = DtwMetric(r=0.1)
+    fit = sh.FittedSet(refs.reshape(len(refs), 1, -1), devices=[sh._first_device()])
+    try:
+        for k in (2, 5, 8):
+            oi, od = oracle.argmin("dtw", q, refs, k=k, r=0.1, n_jobs=0)
+            idx, dist = sh._argmin_fitted(m.metric_id, m._params(), q, fit, k, None, 3)
+            st = sh._tls.stats
+            assert st["ambiguous"] == 0, st
+            _eq(np.sort(idx, axis=1), np.sort(oi, axis=1), f"k={k} neighbour sets")
+            _eq(np.sort(dist, axis=1), np.sort(od, axis=1), f"k={k} distance multisets")
+            plain_idx, _ = sh._argmin_fitted(m.metric_id, m._params(), q, fit, k, None, 1)
+            assert st["pairs"] < sh._tls.stats["pairs"], (st, sh._tls.stats)   # the seeded scan sends fewer pairs to the DP
+            _eq(plain_idx, oi, f"k={k} exact scan keeps the heap order")
+    finally:
+        fit.close()
+    # ties at the kth distance: four copies of one reference, all equally near to query 0 -- which of them the reference keeps
+    # depends on its scan history, so the mode reports the query and argmin_fitted(neighbour_set=True) returns the exact scan
+    refs2 = refs.copy()
+    for j in (100, 500, 900, 1300):
+        refs2[j] = q[0] + 0.01
+    fit = sh.FittedSet(refs2.reshape(len(refs2), 1, -1), devices=[sh._first_device()])
+    try:
+        oi, od = oracle.argmin("dtw", q, refs2, k=3, r=0.1, n_jobs=0)
+        sh._argmin_fitted(m.metric_id, m._params(), q, fit, 3, None, 3)
+        assert sh._tls.stats["ambiguous"] >= 1, sh._tls.stats
+        idx, dist = sh.argmin_fitted(m.metric_id, m._params(), q, fit, 3, use_device_lb=True, neighbour_set=True)
+        _eq(idx, oi, "fallback idx"); _eq(dist, od, "fallback dist")
+    finally:
+        fit.close()

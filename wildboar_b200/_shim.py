@@ -27,7 +27,8 @@ class WbParams(C.Structure):
 class WbStats(C.Structure):
     _fields_ = [("kernel_ms", C.c_double), ("total_ms", C.c_double), ("cells", C.c_int64), ("pairs", C.c_int64),
                 ("launches", C.c_int32), ("engine", C.c_int32), ("lb_kim_pruned", C.c_int64), ("lb_keogh_pruned", C.c_int64),
-                ("strip_w", C.c_int32), ("strip_nr", C.c_int32), ("strip_warps", C.c_int32), ("strip_gring", C.c_int32)]
+                ("strip_w", C.c_int32), ("strip_nr", C.c_int32), ("strip_warps", C.c_int32), ("strip_gring", C.c_int32),
+                ("ambiguous", C.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -371,7 +372,17 @@ def pairwise_fitted(metric_id, params, x, fitted, combine="mean"):
     return out
 
 
-def argmin_fitted(metric_id, params, x, fitted, k, lower_bound=None, use_device_lb=False):
+def argmin_fitted(metric_id, params, x, fitted, k, lower_bound=None, use_device_lb=False, neighbour_set=False):
+    """neighbour_set: the caller only needs the k nearest as a SET (include/wb_cuda.h, use_device_lb bit 1): the call is
+    repeated with the exact scan when the library reports a query whose set depends on the scan's history."""
+    if neighbour_set and use_device_lb and 1 < k <= 8:
+        idx, dist = _argmin_fitted(metric_id, params, x, fitted, k, lower_bound, 3)
+        if _tls.stats.get("ambiguous", 0) == 0:
+            return idx, dist
+    return _argmin_fitted(metric_id, params, x, fitted, k, lower_bound, 1 if use_device_lb else 0)
+
+
+def _argmin_fitted(metric_id, params, x, fitted, k, lower_bound, lb_flags):
     apply_engine_override(params)
     x, xp, nx, Tx, xs = _rows(x)
     idx = np.zeros((nx, k), dtype=np.int64)
@@ -382,7 +393,7 @@ def argmin_fitted(metric_id, params, x, fitted, k, lower_bound=None, use_device_
         lbp = lower_bound.ctypes.data_as(_DP)
     st = WbStats()
     _check(lib().wb_cuda_argmin_fitted(metric_id, C.byref(params), xp, nx, Tx, xs, fitted._handle(), k, lbp,
-                                       1 if use_device_lb else 0, idx.ctypes.data_as(_IP), dist.ctypes.data_as(_DP),
+                                       lb_flags, idx.ctypes.data_as(_IP), dist.ctypes.data_as(_DP),
                                        C.byref(st)))
     _tls.stats = st.as_dict()
     return idx.astype(np.intp, copy=False), dist

@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 #include "dispatch.cuh"
 #include "kernels.cuh"
 
@@ -44,7 +45,7 @@ struct ArgminIo {
   int64_t lb_ld;
   int64_t* out_idx;           // host (nq, k)
   double* out_dist;           // host (nq, k)
-  int use_device_lb;
+  int use_device_lb;          // bit 0: on-device LB cascade (dtw); bit 1: neighbour-SET mode (include/wb_cuda.h, wb_cuda_argmin)
   // Pipelined upload of the references (second operand in HOST memory, dtw / wdtw / adtw in fp64): the scan starts as soon
   // as the first chunk's references are resident; the remaining rows are copied piecewise on `up_stream` while earlier
   // chunks compute (run_argmin, `ensure_refs`).  y_host == nullptr: the references are already on the device.
@@ -125,6 +126,11 @@ struct ReplayArgs {
   int k, kind;
   double scale;
   double* tau; long long* hidx; double* hval; int* hn;
+  // neighbour-set mode (ArgminIo::use_device_lb bit 1): amb[q] = number of pairs left out of the heap although their
+  // distance EQUALS the heap's current maximum (rejected by the strict `<`, or evicted while a twin stayed); reset when the
+  // maximum drops.  Non-zero after the last chunk <=> which of the tied pairs is in the final set depends on the scan's
+  // history (in the reference as well) -- the caller repeats those queries with the exact scan.  nullptr: not tracked.
+  int* amb = nullptr;
 };
 
 __global__ void __launch_bounds__(128) k_replay(ReplayArgs a) {
@@ -137,6 +143,7 @@ __global__ void __launch_bounds__(128) k_replay(ReplayArgs a) {
     long long* hi = a.hidx + q * a.k;
     double* hv = a.hval + q * a.k;
     const double* drow = a.d + q * a.ld;
+    int amb = a.amb ? a.amb[q] : 0;
     // eight groups of 32 columns per trip: the loads of a trip are issued together (one warp walks a whole row, and with
     // one load in flight at a time the kernel ran at the latency of a dependent chain: 33 us for a 33 MB chunk matrix)
     for (long long j0 = 0; j0 < a.ncols; j0 += 256) {
@@ -150,26 +157,35 @@ __global__ void __launch_bounds__(128) k_replay(ReplayArgs a) {
       for (int u = 0; u < 8; ++u) {
         const long long jj = j0 + u * 32;
         const double dv = dvs[u];
-        unsigned mask = __ballot_sync(0xffffffffu, dv < t);
+        // t only decreases while the group is walked, so the candidates under the group-start t are a superset
+        unsigned mask = __ballot_sync(0xffffffffu, a.amb ? (dv <= t && dv < WB_INF) : (dv < t));
         while (mask) {
           const int src = __ffs(mask) - 1;
           mask &= mask - 1;
           const double ds = __shfl_sync(0xffffffffu, dv, src);
           const long long js = jj + src;
           bool acc = ds < t;
+          if (a.amb && !acc && ds == t && n == a.k) ++amb;  // tied with the current maximum and left out
           if (acc && a.lb) acc = !(a.lb[q * a.ld + js] >= t);
           if (acc && a.m) acc = !(a.m[q * a.ld + js] > ea_threshold(a.kind, t, a.scale));
           if (acc) {
+            const double t_old = t;
+            const int n_old = n;
             if (lane == 0) {
               heap_push(hi, hv, n, a.k, a.c0 + js, ds);
               t = (n == a.k) ? hv[0] : WB_INF;
             }
             t = __shfl_sync(0xffffffffu, t, 0);
             n = __shfl_sync(0xffffffffu, n, 0);
+            if (a.amb) {
+              if (n_old == a.k && t == t_old) ++amb;  // the evicted maximum had a twin that stays
+              else if (t != t_old) amb = 0;           // the maximum dropped: earlier ties are below... above it now
+            }
           }
         }
       }
     }
+    if (a.amb && lane == 0) a.amb[q] = amb;
     if (lane == 0) { a.tau[q] = t; a.hn[q] = n; }
     __syncwarp();
   }
@@ -837,12 +853,24 @@ __global__ void __launch_bounds__(256) k_seed_candidates(const float* __restrict
   }
 }
 
-__global__ void k_seed_min(const double* __restrict__ cd, long long nq, int per_query, double* __restrict__ seed2) {
+// seed2[q] = the kth smallest (1-based, kth <= kSeedNC) of the query's candidate DP values
+__global__ void k_seed_min(const double* __restrict__ cd, long long nq, int per_query, int kth, double* __restrict__ seed2) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nq) return;
-  double m = cd[q * per_query];
-  for (int r = 1; r < per_query; ++r) m = fmin(m, cd[q * per_query + r]);
-  seed2[q] = m;
+  double best[kSeedNC];  // ascending
+#pragma unroll
+  for (int r = 0; r < kSeedNC; ++r) best[r] = WB_INF;
+  for (int e = 0; e < per_query; ++e) {
+    double v = cd[q * per_query + e];
+#pragma unroll
+    for (int r = 0; r < kSeedNC; ++r) {
+      if (v < best[r]) { const double tmp = best[r]; best[r] = v; v = tmp; }
+    }
+  }
+  double out = best[0];
+#pragma unroll
+  for (int r = 1; r < kSeedNC; ++r) if (r < kth) out = best[r];
+  seed2[q] = out;
 }
 __global__ void k_set_int(int* p, int v) { *p = v; }
 
@@ -866,7 +894,7 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
   else kind = TK_IDENT;
 
   double *tau = nullptr, *thr = nullptr, *hval = nullptr, *dbuf = nullptr, *mbuf = nullptr, *lbuf = nullptr;
-  long long* hidx = nullptr; int* hn = nullptr;
+  long long* hidx = nullptr; int* hn = nullptr; int* amb = nullptr;
   // Columns per chunk.  The thresholds a chunk is pruned with are those at its start, so the FIRST chunks should be small
   // (they run dense or nearly so) and the later ones large (few launches: with one query every chunk is ~6 launches of
   // almost no work).  The chunk grows 4x per step from 1024 columns up to C = min(32768, 4 Mi / nq) -- nq * C values per
@@ -877,7 +905,12 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
   const long long seed_from = io.y_host ? std::min<long long>(ny, std::max<long long>(1, piped_piece_bytes() / (long long)(sizeof(double) * c.Ty))) : ny;
   long long seed_min = 2048;
   if (const char* e = getenv("WILDBOAR_CUDA_SEED_MIN")) seed_min = std::max<long long>(256, atoll(e));  // test knob
-  const bool will_seed = io.use_device_lb && c.metric == M_DTW && c.ptx == c.pty && c.ptx >= 2 && !c.degenerate && k == 1 &&
+  const bool lb_on = (io.use_device_lb & 1) != 0;
+  // neighbour-set mode: the caller needs the k nearest as a SET (class votes), so the thresholds may be seeded for k > 1 as
+  // well -- with the kth smallest candidate distance, an upper bound of the final kth distance: only pairs outside the final
+  // set are removed, the heap-array order is this scan's, and queries whose set is history dependent are counted (amb)
+  const bool set_mode = (io.use_device_lb & 2) != 0 && k > 1 && k <= kSeedNC;
+  const bool will_seed = lb_on && c.metric == M_DTW && c.ptx == c.pty && c.ptx >= 2 && !c.degenerate && (k == 1 || set_mode) &&
                          seed_from >= seed_min && nq * (long long)kSeedNC < 2000000000LL && !getenv("WILDBOAR_CUDA_NO_SEED");
   long long C = ((will_seed ? 32LL : 4LL) << 20) / std::max<long long>(nq, 1);
   C = std::max<long long>(32, std::min<long long>(32768, (C / 32) * 32));
@@ -899,7 +932,7 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
   if ((!dtwfam || adtw_neg) && ws.alloc(&mbuf, (size_t)nq * C)) return 1;
   if (io.lower_bound && ws.alloc(&lbuf, (size_t)nq * C)) return 1;
   // ---- optional on-device lower-bound cascade (dtw, equal lengths) ----
-  const bool cascade = io.use_device_lb && c.metric == M_DTW && c.ptx == c.pty && c.ptx >= 2 && !c.degenerate &&
+  const bool cascade = lb_on && c.metric == M_DTW && c.ptx == c.pty && c.ptx >= 2 && !c.degenerate &&
                        nq * C < 2000000000LL;
   float4* qf = nullptr; float2 *envT = nullptr, *yvT = nullptr;
   double *y0 = nullptr, *yL = nullptr;
@@ -971,6 +1004,7 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
   if (cudaMemsetAsync(hval, 0, sizeof(double) * nq * k, st) != cudaSuccess ||
       cudaMemsetAsync(hidx, 0, sizeof(long long) * nq * k, st) != cudaSuccess ||
       cudaMemsetAsync(hn, 0, sizeof(int) * nq, st) != cudaSuccess) return 1;
+  if (set_mode && (ws.alloc(&amb, (size_t)nq) || cudaMemsetAsync(amb, 0, sizeof(int) * nq, st) != cudaSuccess)) return 1;
 
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -1000,7 +1034,7 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
         c.mode = PM_LISTP; c.list = cl; c.list_len = cl_len; c.list_n = ncand; c.raw = 1;
         rc = launch(0, nq, 0, ny, cd, 1, nullptr, nullptr, stats);
         c.mode = mode0; c.list = nullptr; c.list_len = nullptr; c.list_n = 0; c.raw = raw0;
-        k_seed_min<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(cd, nq, nsl * kSeedNC, seed2);
+        k_seed_min<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(cd, nq, nsl * kSeedNC, k, seed2);
         if (stats) stats->launches += 5;
         // with thresholds from the start there is no dense first chunk to keep small
         c_first = C;
@@ -1067,7 +1101,7 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
     }
     ReplayArgs ra;
     ra.d = dbuf; ra.m = mbuf; ra.lb = lbuf; ra.ld = C; ra.nq = nq; ra.c0 = c0; ra.ncols = nc;
-    ra.k = k; ra.kind = kind; ra.scale = scale; ra.tau = tau; ra.hidx = hidx; ra.hval = hval; ra.hn = hn;
+    ra.k = k; ra.kind = kind; ra.scale = scale; ra.tau = tau; ra.hidx = hidx; ra.hval = hval; ra.hn = hn; ra.amb = amb;
     const long long blocks = std::max<long long>(1, std::min<long long>((nq + 3) / 4, 148 * 16));
     k_replay<<<(unsigned)blocks, 128, 0, st>>>(ra);
     if (stats) stats->launches += 2;
@@ -1080,6 +1114,11 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
         cudaStreamSynchronize(st) != cudaSuccess) rc = 1;
     float f = 0;
     if (!rc && stats && cudaEventElapsedTime(&f, e0, e1) == cudaSuccess) stats->kernel_ms += f;
+    if (!rc && stats && amb) {
+      std::vector<int> h((size_t)nq);
+      if (cudaMemcpy(h.data(), amb, sizeof(int) * nq, cudaMemcpyDeviceToHost) == cudaSuccess)
+        for (long long q = 0; q < nq; ++q) stats->ambiguous += h[(size_t)q] != 0;
+    }
     if (!rc && stats && cascade) {
       unsigned long long h[3] = {0, 0, 0};
       if (cudaMemcpy(h, lbstat, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess) {

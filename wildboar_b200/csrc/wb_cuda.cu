@@ -1078,6 +1078,7 @@ static int run_host_job(const HostJob& J, const int* devices, int n_devices, wb_
       stats->total_ms = std::max(stats->total_ms, sts[b].total_ms);
       stats->cells += sts[b].cells; stats->pairs += sts[b].pairs; stats->launches += sts[b].launches;
       stats->lb_kim_pruned += sts[b].lb_kim_pruned; stats->lb_keogh_pruned += sts[b].lb_keogh_pruned;
+      stats->ambiguous += sts[b].ambiguous;
       stats->engine = std::max(stats->engine, sts[b].engine);
       if (sts[b].strip_w) { stats->strip_w = sts[b].strip_w; stats->strip_nr = sts[b].strip_nr; stats->strip_warps = sts[b].strip_warps; stats->strip_gring = sts[b].strip_gring; }
     }

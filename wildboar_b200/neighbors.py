@@ -117,11 +117,14 @@ class _NeighborsBase(_SkBase):
         m = _make_metric(self.metric, self.metric_params)
         return _shim.pairwise_fitted(m.metric_id, m._params(), _check_ts_array(x), self._fitted, "mean")
 
-    def _argmin(self, x, k, sorted_):
+    def _argmin(self, x, k, sorted_, neighbour_set=False):
+        # neighbour_set: the caller counts the k nearest (class votes) and does not look at their order, so the library may
+        # seed its pruning thresholds for k > 1 as well (wb_cuda.h, use_device_lb bit 1; exact set, repeated with the plain
+        # scan when a tie at the kth distance makes the reference's set depend on its scan history)
         m = _make_metric(self.metric, self.metric_params)
         k = min(k, self._fit_X.shape[0])
         idx, dist = _shim.argmin_fitted(m.metric_id, m._params(), _check_ts_array(x)[:, 0, :], self._fitted, k,
-                                        use_device_lb=m.name == "dtw")
+                                        use_device_lb=m.name == "dtw", neighbour_set=neighbour_set)
         if sorted_:
             order = np.argsort(dist, axis=1, kind="stable")
             idx = np.take_along_axis(idx, order, axis=1)
@@ -201,7 +204,7 @@ class KNeighborsClassifier(_NeighborsBase):
             dists = self._pairwise_mean(x)
             closest = np.argpartition(dists, self.n_neighbors, axis=1)[:, : self.n_neighbors]
         else:
-            closest, _ = self._argmin(x, self.n_neighbors, False)
+            closest, _ = self._argmin(x, self.n_neighbors, False, neighbour_set=True)  # only counted below
         preds = self._y[closest]
         probs = np.empty((x.shape[0], len(self.classes_)), dtype=float)
         for i in range(len(self.classes_)):
