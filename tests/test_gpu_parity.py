@@ -739,3 +739,35 @@ def test_argmin_neighbour_set_mode(W, oracle, monkeypatch):
         _eq(idx, oi, "fallback idx"); _eq(dist, od, "fallback dist")
     finally:
         fit.close()
+
+
+def test_argmin_sorted_uses_the_set_mode_and_stays_exact(W, oracle, monkeypatch):
+    """argmin_distance(sorted=True) and NearestNeighbors.kneighbors return the neighbours by distance, so they may run in the
+    neighbour-set mode; rows with equal distances (duplicated references among the k nearest) must come back exactly as the
+    reference orders them -- through the exact scan."""
+    from wildboar_b200.neighbors import NearestNeighbors
+    monkeypatch.setenv("WILDBOAR_CUDA_SEED_MIN", "256")
+    q, refs = random_walks(50, 80, 95), random_walks(1200, 80, 96)
+
+    def want(refs_, k):
+        oi, od = oracle.argmin("dtw", q, refs_, k=k, r=0.1, n_jobs=0)
+        order = np.argsort(od, axis=1, kind="stable")
+        return np.take_along_axis(oi, order, axis=1), np.take_along_axis(od, order, axis=1)
+
+    for k in (3, 5):
+        idx, dist = W.argmin_distance(q, refs, k=k, metric="dtw", metric_params={"r": 0.1}, sorted=True, return_distance=True)
+        st = W.last_stats()
+        wi, wd = want(refs, k)
+        _eq(idx, wi, f"k={k} sorted idx"); _eq(dist, wd, f"k={k} sorted dist")
+        assert st["ambiguous"] == 0
+    nn = NearestNeighbors(n_neighbors=4, metric="dtw", metric_params={"r": 0.1}).fit(refs)
+    nd, ni = nn.kneighbors(q)
+    wi, wd = want(refs, 4)
+    _eq(ni, wi, "kneighbors idx"); _eq(nd, wd, "kneighbors dist")
+    # the nearest reference of query 0 three times: equal distances inside the row -> exact scan, the reference's order
+    refs2 = refs.copy()
+    j0 = int(want(refs, 1)[0][0, 0])
+    refs2[(j0 + 400) % 1200] = refs2[j0]; refs2[(j0 + 800) % 1200] = refs2[j0]
+    idx, dist = W.argmin_distance(q, refs2, k=3, metric="dtw", metric_params={"r": 0.1}, sorted=True, return_distance=True)
+    wi, wd = want(refs2, 3)
+    _eq(idx, wi, "tied rows idx"); _eq(dist, wd, "tied rows dist")

@@ -312,7 +312,30 @@ def paired_nd(metric_id, params, x, y, combine):
     return out
 
 
-def argmin(metric_id, params, x, y, k, lower_bound=None, use_device_lb=False):
+def _set_mode_result_ok(dist, ordered):
+    """Result of a neighbour-set call (include/wb_cuda.h, use_device_lb bit 1): usable when no query was reported as
+    ambiguous and -- if the caller is going to SORT the neighbours by distance -- no row holds two equal distances (their
+    order after sorting would depend on the heap order, which the mode does not preserve)."""
+    if _tls.stats.get("ambiguous", 0) != 0:
+        return False
+    if ordered and dist.shape[1] > 1:
+        sd = np.sort(dist, axis=1)
+        if bool((sd[:, 1:] == sd[:, :-1]).any()):
+            return False
+    return True
+
+
+def argmin(metric_id, params, x, y, k, lower_bound=None, use_device_lb=False, neighbour_set=False, ordered=False):
+    """neighbour_set: the caller consumes the k nearest as a set, or (ordered=True) sorted by distance -- never in heap
+    order; the exact scan answers instead whenever the set-mode result would not be unique."""
+    if neighbour_set and use_device_lb and 1 < k <= 8:
+        idx, dist = _argmin(metric_id, params, x, y, k, lower_bound, 3)
+        if _set_mode_result_ok(dist, ordered):
+            return idx, dist
+    return _argmin(metric_id, params, x, y, k, lower_bound, 1 if use_device_lb else 0)
+
+
+def _argmin(metric_id, params, x, y, k, lower_bound, lb_flags):
     apply_engine_override(params)
     x, xp, nx, Tx, xs = _rows(x)
     y, yp, ny, Ty, ys = _rows(y)
@@ -325,7 +348,7 @@ def argmin(metric_id, params, x, y, k, lower_bound=None, use_device_lb=False):
     st = WbStats()
     dv, nd = _dev_array(_resolve_devices(_est_cells(nx * ny, Tx, Ty, params.r)))
     _check(lib().wb_cuda_argmin(metric_id, C.byref(params), xp, nx, Tx, xs, yp, ny, Ty, ys, k, lbp,
-                                1 if use_device_lb else 0, idx.ctypes.data_as(_IP), dist.ctypes.data_as(_DP), dv, nd,
+                                lb_flags, idx.ctypes.data_as(_IP), dist.ctypes.data_as(_DP), dv, nd,
                                 C.byref(st)))
     _tls.stats = st.as_dict()
     return idx.astype(np.intp, copy=False), dist
@@ -372,12 +395,12 @@ def pairwise_fitted(metric_id, params, x, fitted, combine="mean"):
     return out
 
 
-def argmin_fitted(metric_id, params, x, fitted, k, lower_bound=None, use_device_lb=False, neighbour_set=False):
-    """neighbour_set: the caller only needs the k nearest as a SET (include/wb_cuda.h, use_device_lb bit 1): the call is
-    repeated with the exact scan when the library reports a query whose set depends on the scan's history."""
+def argmin_fitted(metric_id, params, x, fitted, k, lower_bound=None, use_device_lb=False, neighbour_set=False, ordered=False):
+    """neighbour_set: the caller only needs the k nearest as a SET, or (ordered=True) sorted by distance (include/wb_cuda.h,
+    use_device_lb bit 1): the call is repeated with the exact scan when the set-mode result would not be unique."""
     if neighbour_set and use_device_lb and 1 < k <= 8:
         idx, dist = _argmin_fitted(metric_id, params, x, fitted, k, lower_bound, 3)
-        if _tls.stats.get("ambiguous", 0) == 0:
+        if _set_mode_result_ok(dist, ordered):
             return idx, dist
     return _argmin_fitted(metric_id, params, x, fitted, k, lower_bound, 1 if use_device_lb else 0)
 
