@@ -669,6 +669,7 @@ def test_lb_prune_kernel_variants_prune_identically(W, oracle, T, r, monkeypatch
     ragged query groups and reference blocks included."""
     monkeypatch.setenv("WILDBOAR_CUDA_ARGMIN_CHUNK", "160")
     monkeypatch.setenv("WILDBOAR_CUDA_NO_SEED", "1")
+    monkeypatch.setenv("WILDBOAR_CUDA_LB_KEEP", "1")   # no adaptive switch-off of the pass: the counts are compared
     q, refs = random_walks(37, T, 81), random_walks(1003, T, 82)
     refs[600] = q[11]
     oi, od = oracle.argmin("dtw", q, refs, k=2, r=r, n_jobs=0)
@@ -771,3 +772,55 @@ def test_argmin_sorted_uses_the_set_mode_and_stays_exact(W, oracle, monkeypatch)
     idx, dist = W.argmin_distance(q, refs2, k=3, metric="dtw", metric_params={"r": 0.1}, sorted=True, return_distance=True)
     wi, wd = want(refs2, 3)
     _eq(idx, wi, "tied rows idx"); _eq(dist, wd, "tied rows dist")
+
+
+def test_argmin_seeding_is_off_with_a_caller_lower_bound(W, oracle, monkeypatch):
+    """The elastic ensemble masks every sample's own column with +inf in `lower_bound` (the reference skips pairs whose bound
+    reaches the threshold whatever their distance): the distance to a sketch-nearest candidate -- here the sample itself,
+    distance 0 -- is then no bound on what the scan accepts, so the thresholds must not be seeded."""
+    monkeypatch.setenv("WILDBOAR_CUDA_SEED_MIN", "256")
+    from wildboar_b200 import _shim as sh
+    from wildboar_b200.distance import DtwMetric
+    m = DtwMetric(r=0.1)
+    x = random_walks(700, 64, 97)
+    mask = np.full((700, 700), -np.inf)
+    np.fill_diagonal(mask, np.inf)
+    for k in (1, 3):
+        oi, od = oracle.argmin("dtw", x, x, k=k, r=0.1, lower_bound=mask, n_jobs=0)
+        # (the public argmin_distance refuses non-finite bounds like the reference's check_array; the ensemble calls the shim)
+        idx, dist = sh.argmin(m.metric_id, m._params(), x, x, k, lower_bound=mask, use_device_lb=True)
+        _eq(idx, oi, f"masked self join k={k} idx"); _eq(dist, od, f"masked self join k={k} dist")
+        assert not (idx[:, 0] == np.arange(700)).any()
+
+
+@pytest.mark.parametrize("metric,params", [("ddtw", {"r": 0.1}), ("adtw", {"r": 0.1, "p": 0.3}), ("adtw", {"r": 0.2, "p": 0.0})])
+@pytest.mark.parametrize("k", [1, 4])
+def test_argmin_cascade_covers_ddtw_and_adtw(W, oracle, metric, params, k, monkeypatch):
+    """The LB cascade bounds the banded DTW of the prepared operands: valid for ddtw (slope series, eadistance's window) and for
+    adtw with a non-negative penalty (DTW's cost plus penalties); seeded (k = 1) and unseeded (k = 4), many chunks."""
+    monkeypatch.setenv("WILDBOAR_CUDA_SEED_MIN", "256")
+    monkeypatch.setenv("WILDBOAR_CUDA_ARGMIN_CHUNK", "96")
+    q, refs = random_walks(45, 100, 98), random_walks(1300, 100, 99)
+    refs[900] = q[4]; refs[77] = q[4]
+    oi, od = oracle.argmin(metric, q, refs, k=k, n_jobs=0, **params)
+    for lb in (True, False):
+        idx, dist = W.argmin_distance(q, refs, k=k, metric=metric, metric_params=params, return_distance=True, device_lower_bound=lb)
+        _eq(idx, oi, f"{metric} cascade={lb} idx"); _eq(dist, od, f"{metric} cascade={lb} dist")
+        st = W.last_stats()
+        if lb and metric == "adtw":   # (ddtw of random walks compares noise: its bounds prune next to nothing)
+            assert st["lb_kim_pruned"] + st["lb_keogh_pruned"] > 0, st
+
+
+def test_argmin_cascade_switches_itself_off_where_it_does_not_prune(W, oracle, monkeypatch):
+    """ddtw of random walks: the slope series are noise, their envelopes contain almost every sample and the LB pass prunes
+    next to nothing -- after the first columns it is dropped (the pruned fraction is read back once); results unchanged."""
+    q, refs = random_walks(30, 128, 101), random_walks(6000, 128, 102)
+    oi, od = oracle.argmin("ddtw", q, refs, k=2, r=0.05, n_jobs=0)
+    idx, dist = W.argmin_distance(q, refs, k=2, metric="ddtw", metric_params={"r": 0.05}, return_distance=True)
+    _eq(idx, oi, "ddtw idx"); _eq(dist, od, "ddtw dist")
+    st_auto = W.last_stats()
+    monkeypatch.setenv("WILDBOAR_CUDA_LB_KEEP", "1")
+    idx, dist = W.argmin_distance(q, refs, k=2, metric="ddtw", metric_params={"r": 0.05}, return_distance=True)
+    _eq(idx, oi, "ddtw idx (pass kept)"); _eq(dist, od, "ddtw dist (pass kept)")
+    st_keep = W.last_stats()
+    assert st_auto["launches"] < st_keep["launches"], (st_auto, st_keep)

@@ -905,12 +905,20 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
   const long long seed_from = io.y_host ? std::min<long long>(ny, std::max<long long>(1, piped_piece_bytes() / (long long)(sizeof(double) * c.Ty))) : ny;
   long long seed_min = 2048;
   if (const char* e = getenv("WILDBOAR_CUDA_SEED_MIN")) seed_min = std::max<long long>(256, atoll(e));  // test knob
-  const bool lb_on = (io.use_device_lb & 1) != 0;
+  // The cascade bounds the banded DTW of the PREPARED operands: dtw itself, ddtw (DTW of the slope series; R as
+  // eadistance() takes it), and adtw with a penalty >= 0 (its cost is DTW's plus non-negative penalties, so every lower
+  // bound of DTW is one of adtw; the survivors and the seeds go through adtw's own recurrence).  wdtw's weights start near
+  // zero on the diagonal (w(0) = 0.0017 for g = 0.05, T = 256), which leaves nothing of the bound.
+  const bool lb_metric = c.metric == M_DTW || c.metric == M_DDTW || (c.metric == M_ADTW && c.p.p >= 0);
+  const bool lb_on = (io.use_device_lb & 1) != 0 && lb_metric;
   // neighbour-set mode: the caller needs the k nearest as a SET (class votes), so the thresholds may be seeded for k > 1 as
   // well -- with the kth smallest candidate distance, an upper bound of the final kth distance: only pairs outside the final
   // set are removed, the heap-array order is this scan's, and queries whose set is history dependent are counted (amb)
   const bool set_mode = (io.use_device_lb & 2) != 0 && k > 1 && k <= kSeedNC;
-  const bool will_seed = lb_on && c.metric == M_DTW && c.ptx == c.pty && c.ptx >= 2 && !c.degenerate && (k == 1 || set_mode) &&
+  // A caller-supplied lower_bound matrix rules seeding out: pairs with lower_bound >= threshold are SKIPPED by the
+  // reference whatever their distance (the elastic ensemble masks each sample's own column with +inf that way,
+  // ensemble/_elastic.py), so the distance to a candidate is no bound on what the scan can still accept.
+  const bool will_seed = lb_on && !io.lower_bound && c.ptx == c.pty && c.ptx >= 2 && !c.degenerate && (k == 1 || set_mode) &&
                          seed_from >= seed_min && nq * (long long)kSeedNC < 2000000000LL && !getenv("WILDBOAR_CUDA_NO_SEED");
   long long C = ((will_seed ? 32LL : 4LL) << 20) / std::max<long long>(nq, 1);
   C = std::max<long long>(32, std::min<long long>(32768, (C / 32) * 32));
@@ -932,7 +940,7 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
   if ((!dtwfam || adtw_neg) && ws.alloc(&mbuf, (size_t)nq * C)) return 1;
   if (io.lower_bound && ws.alloc(&lbuf, (size_t)nq * C)) return 1;
   // ---- optional on-device lower-bound cascade (dtw, equal lengths) ----
-  const bool cascade = lb_on && c.metric == M_DTW && c.ptx == c.pty && c.ptx >= 2 && !c.degenerate &&
+  const bool cascade = lb_on && c.ptx == c.pty && c.ptx >= 2 && !c.degenerate &&
                        nq * C < 2000000000LL;
   float4* qf = nullptr; float2 *envT = nullptr, *yvT = nullptr;
   double *y0 = nullptr, *yL = nullptr;
@@ -945,7 +953,7 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
     if (cudaMemsetAsync(lbstat, 0, 3 * sizeof(unsigned long long), st) != cudaSuccess) return 1;
     const int stride = lb_time_stride(T);
     k_query_casc<<<1024, 256, 0, st>>>(c.px, nq, T, w, stride, qf);
-    LbCascCache* cc = io.casc_cache;
+    LbCascCache* cc = c.metric == M_DDTW ? nullptr : io.casc_cache;  // ddtw: the operands are this call's slope buffers
     bool cached = false;
     if (cc) {
       // built ONCE per fitted set, by the first call, under the lock and finished before anyone else may read it; a later
@@ -1042,7 +1050,21 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
     }
   }
   long long c_cur = c_first;
+  // The cascade pays for itself only where the bounds bite: ddtw of noise-like series (the slopes of a random walk) has
+  // envelopes that contain almost every sample, nothing is pruned and the pass is 7 % on top of the DP.  After the first
+  // few thousand columns (thresholds have settled) the pruned fraction is read back ONCE; below a fifth the remaining
+  // chunks run without the pass -- pruning is optional, so the result cannot change.
+  bool casc_on = cascade, casc_checked = false;
+  long long casc_cols = 0;
+  const long long casc_check_after = std::min<long long>(4096, std::max<long long>(ny / 4, 1));
   for (long long c0 = 0; c0 < ny && !rc; ) {
+    if (casc_on && !casc_checked && casc_cols >= casc_check_after && !getenv("WILDBOAR_CUDA_LB_KEEP")) {
+      casc_checked = true;
+      unsigned long long h[3] = {0, 0, 0};
+      if (cudaMemcpyAsync(h, lbstat, sizeof h, cudaMemcpyDeviceToHost, st) == cudaSuccess && cudaStreamSynchronize(st) == cudaSuccess &&
+          (double)(h[0] + h[1]) < 0.2 * (double)nq * (double)casc_cols)
+        casc_on = false;
+    }
     const long long nc = std::min(c_cur, ny - c0);
     const long long c0_next = c0 + nc;
     c_cur = std::min(C, c_cur * 4);
@@ -1051,7 +1073,8 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
     if (c.degenerate) {
       // ddtw with T < 3: eadistance() returns False for every pair (EL:3297-3298)
       k_fill<<<256, 256, 0, st>>>(dbuf, nq * C, WB_INF);
-    } else if (cascade && (c0 > 0 || seed2)) {
+    } else if (casc_on && (c0 > 0 || seed2)) {
+      casc_cols += nc;
       // chunk 0 has no threshold yet (tau = INF) unless the thresholds were seeded: nothing can be pruned, run it densely
       LbArgs la;
       la.x = c.px; la.qf = qf; la.envT = envT; la.yvT = yvT; la.y0 = y0; la.yL = yL;

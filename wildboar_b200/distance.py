@@ -432,7 +432,7 @@ def argmin_distance(x, y=None, *, dim=0, k=1, metric="euclidean", metric_params=
         # sorted=True: the neighbours are returned by distance, not in heap order, so the library may use its neighbour-set
         # mode (seeded thresholds for 1 < k <= 8; _shim.argmin falls back to the exact scan when the result is not unique)
         indices, distances = _shim.argmin(m.metric_id, params, x[:, dim, :], y[:, dim, :], k, lower_bound,
-                                          use_device_lb=bool(device_lower_bound) and m.name == "dtw",
+                                          use_device_lb=bool(device_lower_bound) and m.name in ("dtw", "ddtw", "adtw"),
                                           neighbour_set=bool(sorted), ordered=True)
         if sorted:
             sort = np.argsort(distances, axis=1, kind="stable")

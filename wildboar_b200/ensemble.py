@@ -91,7 +91,7 @@ def _loo_neighbors(x, metric, metric_params, k):
     mask = np.full((n, n), -np.inf)
     np.fill_diagonal(mask, np.inf)
     idx, _ = _shim.argmin(m.metric_id, m._params(), xd, xd, min(k, n - 1), lower_bound=mask,
-                          use_device_lb=m.name == "dtw")
+                          use_device_lb=m.name in ("dtw", "ddtw", "adtw"))
     return idx
 
 

@@ -124,7 +124,7 @@ class _NeighborsBase(_SkBase):
         m = _make_metric(self.metric, self.metric_params)
         k = min(k, self._fit_X.shape[0])
         idx, dist = _shim.argmin_fitted(m.metric_id, m._params(), _check_ts_array(x)[:, 0, :], self._fitted, k,
-                                        use_device_lb=m.name == "dtw", neighbour_set=neighbour_set or bool(sorted_),
+                                        use_device_lb=m.name in ("dtw", "ddtw", "adtw"), neighbour_set=neighbour_set or bool(sorted_),
                                         ordered=bool(sorted_))
         if sorted_:
             order = np.argsort(dist, axis=1, kind="stable")
