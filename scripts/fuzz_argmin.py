@@ -57,5 +57,26 @@ for case in range(n_cases):
     if not ok:
         bad += 1
         print("MISMATCH case", case, dict(T=T, r=r, nq=nq, ny=ny, k=k, metric=metric, params=params, sorted=srt, scale=scale, offset=offset), env, flush=True)
-print(f"fuzz: {n_cases} cases, {bad} mismatches, {time.time() - t_start:.0f} s")
+# adversarial sets: every distance equal (constant / identical series), zeros, queries that ARE references, steps of one ulp
+for name, mk in (("identical refs", lambda: (np.cumsum(rng.standard_normal((9, 40)), axis=1), np.tile(np.cumsum(rng.standard_normal((1, 40)), axis=1), (700, 1)))),
+                 ("all zeros", lambda: (np.zeros((5, 33)), np.zeros((600, 33)))),
+                 ("constant series", lambda: (np.full((7, 64), 3.25), np.repeat(np.arange(500.0)[:, None] % 7, 64, axis=1))),
+                 ("queries are references", lambda: (lambda r: (r[::37].copy(), r))(np.cumsum(rng.standard_normal((900, 50)), axis=1))),
+                 ("one-ulp neighbours", lambda: (lambda b: (b[:3].copy(), np.stack([np.nextafter(b[i % 3], np.inf if i % 2 else -np.inf) for i in range(400)])))(np.cumsum(rng.standard_normal((3, 48)), axis=1)))):
+    for k_ in KNOBS:
+        os.environ.pop(k_, None)
+    os.environ["WILDBOAR_CUDA_SEED_MIN"] = "256"
+    q, refs = mk()
+    for metric in ("dtw", "ddtw", "adtw"):
+        for k, srt in ((1, False), (3, False), (3, True), (8, True)):
+            params = {"r": 0.1} if metric != "adtw" else {"r": 0.1, "p": 0.5}
+            oi, od = O.argmin(metric, q, refs, k=k, n_jobs=0, **params)
+            if srt:
+                order = np.argsort(od, axis=1, kind="stable")
+                oi, od = np.take_along_axis(oi, order, axis=1), np.take_along_axis(od, order, axis=1)
+            idx, dist = wb.argmin_distance(q, refs, k=k, metric=metric, metric_params=params, sorted=srt, return_distance=True)
+            if not (np.array_equal(idx, oi) and np.array_equal(dist, od)):
+                bad += 1
+                print("MISMATCH adversarial", name, metric, k, srt, flush=True)
+print(f"fuzz: {n_cases} cases + adversarial sets, {bad} mismatches, {time.time() - t_start:.0f} s")
 sys.exit(1 if bad else 0)

@@ -15,6 +15,19 @@
 //   * lcss/erp/edr/msm/twe: abandoning is not monotone, so the row-scan engine
 //     also returns M = max over checked rows of the row minimum; the pair is rejected iff
 //     M > T(t) with the exact t.
+//
+// What keeps the chunks cheap (dtw, ddtw, adtw with p >= 0):
+//   * LB cascade: LB_Kim, then LB_Keogh in both directions, in rigorous round-down fp32 on outward-rounded operands,
+//     as a register tile -- 4 queries x 32 references per warp, the query rows staged in shared memory by bulk copies
+//     (cp.async.bulk + mbarrier, a task ahead), stragglers finished one pair per lane (k_lb_prune_tile); the survivors
+//     are appended to the DP's work list by the pass itself.
+//   * threshold seeding (k = 1; 1 < k <= 8 where the caller consumes the neighbours as a set or sorted): the exact
+//     distances to sketch-nearest candidates bound the final threshold from the start (k_seed_candidates).
+//   * host-resident references are uploaded piecewise on the copy stream while earlier chunks compute (ensure_refs).
+// Tuning / test knobs (environment, read per call): WILDBOAR_CUDA_ARGMIN_CHUNK / _ARGMIN_FIRST (chunk widths), _NO_SEED,
+// _SEED_MIN (references needed to seed), _PIPED_UPLOAD_KB (piece size, 0 = whole upload first), _LB_Q / _LB_BS / _LB_MINB /
+// _LB_RB (tile shape: queries per warp, steps per register block, CTAs per SM, reference blocks per CTA task),
+// _LB_STRAG "n,after" (straggler rule), _LB_KEEP (never drop a pass that does not prune), _ENVELOPE_PLAIN.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdio>
