@@ -19,7 +19,7 @@
 // What keeps the chunks cheap (dtw, ddtw, adtw with p >= 0):
 //   * LB cascade: LB_Kim, then LB_Keogh in both directions, in rigorous round-down fp32 on outward-rounded operands,
 //     as a register tile -- 4 queries x 32 references per warp, the query rows staged in shared memory by bulk copies
-//     (cp.async.bulk + mbarrier, a task ahead), stragglers finished one pair per lane (k_lb_prune_tile); the survivors
+//     (cp.async.bulk + mbarrier, two tasks ahead), stragglers finished one pair per lane (k_lb_prune_tile); the survivors
 //     are appended to the DP's work list by the pass itself.
 //   * threshold seeding (k = 1; 1 < k <= 8 where the caller consumes the neighbours as a set or sorted): the exact
 //     distances to sketch-nearest candidates bound the final threshold from the start (k_seed_candidates).
@@ -30,6 +30,7 @@
 // _LB_STRAG "n,after" (straggler rule), _LB_KEEP (never drop a pass that does not prune), _ENVELOPE_PLAIN.
 #pragma once
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
@@ -487,8 +488,8 @@ __global__ void __launch_bounds__(256) k_lb_prune(LbArgs a) {
 
 // ---- k_lb_prune_tile<Q>: register tile of Q queries x 32 references per warp, query tiles staged in shared memory by TMA ----
 // A CTA task is a group of Q CONSECUTIVE QUERIES against a range of reference blocks.  The Q queries' cascade rows (Q x T
-// float4, contiguous in qf) arrive in shared memory by ONE bulk copy (cp.async.bulk + mbarrier), issued a whole task ahead
-// into the other of two buffers; the warps of the CTA draw reference blocks of the task from a shared counter.  A warp holds
+// float4, contiguous in qf) arrive in shared memory by ONE bulk copy (cp.async.bulk + mbarrier), issued two tasks ahead
+// into one of three buffers; the warps of the CTA draw reference blocks of the task from a shared counter.  A warp holds
 // the block's envelope / value rows of eight time steps in registers (loaded once, the next block of eight in flight
 // meanwhile) and runs all Q queries over them, the query samples coming as broadcast float4 reads from shared memory:
 // 512 / Q + 16 B per pair-step instead of 528 B move through the SM's load path, and no load of the inner loop waits on L2.
@@ -524,10 +525,15 @@ struct LbQMeta { double lim, x0, xL; };  // per query of a tile: prune limit (IN
 
 // a (query, reference) pair whose block of 32 was left by the straggler rule: continued lane-per-pair at the end of the CTA task
 struct LbStrag { int q, jl, k; float s1, s2; };
+// Task buffers per CTA.  A buffer is refilled when the LAST warp has left its task, so with two buffers a warp that is a whole
+// task ahead of the slowest one finds nothing staged: ncu's source view had 10 % of the pass's samples (and 8 % of its
+// instructions) in the mbarrier wait.  With three the warps run up to two tasks apart, and because they draw reference blocks
+// from the task's counter the fast ones simply take more of the next task.
+constexpr int kLbBufs = 3;
 // queue entries per task buffer: every (query, block) subtask of a task can queue strag_n pairs, so nothing overflows
 inline int lb_tile_qcap(int Q, int rb_per_task, int strag_n) { return Q * rb_per_task * std::max(strag_n, 0); }
 inline size_t lb_tile_smem(int Q, int T, int qcap) {
-  return 2 * ((size_t)Q * T * sizeof(float4) + Q * sizeof(LbQMeta) + (size_t)qcap * sizeof(LbStrag)) + 64;  // + 2 mbarriers, 6 counters
+  return kLbBufs * ((size_t)Q * T * sizeof(float4) + Q * sizeof(LbQMeta) + (size_t)qcap * sizeof(LbStrag)) + 128;  // + mbarriers, counters
 }
 
 // Q queries per warp task, BS time steps per register block (4: 3 CTAs of 8 warps per SM; 8: 2), MINB = CTAs per SM the
@@ -538,13 +544,14 @@ __global__ void __launch_bounds__(256, MINB) k_lb_prune_tile(LbArgs a, int rb_pe
   static_assert(BS == 4 || BS == 8, "block of 4 or 8 time steps");
   extern __shared__ __align__(128) unsigned char lb_smem[];
   const int T = a.T;
-  float4* const qs = reinterpret_cast<float4*>(lb_smem);                       // [2][Q * T]
-  LbQMeta* const meta = reinterpret_cast<LbQMeta*>(qs + 2 * (size_t)Q * T);    // [2][Q]
-  unsigned long long* const mbar = reinterpret_cast<unsigned long long*>(meta + 2 * Q);  // [2]
-  int* const s_next = reinterpret_cast<int*>(mbar + 2);                        // [2] next reference block of the task
-  int* const s_done = s_next + 2;                                              // [2] warps that have finished the task
-  int* const s_qn = s_done + 2;                                                // [2] stragglers queued by the task
-  LbStrag* const s_q = reinterpret_cast<LbStrag*>(s_qn + 4);                   // [2][qcap]
+  constexpr int NB = kLbBufs;
+  float4* const qs = reinterpret_cast<float4*>(lb_smem);                        // [NB][Q * T]
+  LbQMeta* const meta = reinterpret_cast<LbQMeta*>(qs + NB * (size_t)Q * T);    // [NB][Q]
+  unsigned long long* const mbar = reinterpret_cast<unsigned long long*>(meta + NB * Q);  // [NB]
+  int* const s_next = reinterpret_cast<int*>(mbar + NB);                        // [NB] next reference block of the task
+  int* const s_done = s_next + NB;                                              // [NB] warps that have finished the task
+  int* const s_qn = s_done + NB;                                                // [NB] stragglers queued by the task
+  LbStrag* const s_q = reinterpret_cast<LbStrag*>(s_qn + NB + (NB & 1));        // [NB][qcap]
   const int tid = threadIdx.x, lane = tid & 31, wpb = blockDim.x >> 5;
   const long long nyb = (a.nc + 31) / 32;
   const long long nqg = (a.nq + Q - 1) / Q;
@@ -582,18 +589,18 @@ __global__ void __launch_bounds__(256, MINB) k_lb_prune_tile(LbArgs a, int rb_pe
   };
 
   if (tid == 0) {
-    mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1);
+    for (int b = 0; b < NB; ++b) mbar_init(&mbar[b], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   if (tid < 32) {
-    if ((long long)blockIdx.x < nct) stage(blockIdx.x, 0);
-    if ((long long)blockIdx.x + gridDim.x < nct) stage((long long)blockIdx.x + gridDim.x, 1);
+    for (int b = 0; b < NB; ++b)
+      if ((long long)blockIdx.x + (long long)b * gridDim.x < nct) stage((long long)blockIdx.x + (long long)b * gridDim.x, b);
   }
   int it = 0;
   for (long long ct = blockIdx.x; ct < nct; ct += gridDim.x, ++it) {
-    const int b = it & 1;
-    mbar_wait(&mbar[b], (unsigned)((it >> 1) & 1));
+    const int b = it % NB;
+    mbar_wait(&mbar[b], (unsigned)((it / NB) & 1));
     const long long qg = ct / nsplit;
     const long long i0 = qg * Q;
     const int rb_hi = (int)min(nyb, ((ct - qg * nsplit) + 1) * per);
@@ -768,7 +775,7 @@ __global__ void __launch_bounds__(256, MINB) k_lb_prune_tile(LbArgs a, int rb_pe
         if (has) a.d[(i0 + e.q) * a.ld + e.jl] = p2 ? WB_INF : -1.0;
         c_surv += lb_append(a, lane, has && !p2, i0 + e.q, e.jl);
       }
-      if (ct + 2LL * gridDim.x < nct) stage(ct + 2LL * gridDim.x, b);
+      if (ct + (long long)NB * gridDim.x < nct) stage(ct + (long long)NB * gridDim.x, b);
     }
   }
   if (lane == 0) {
@@ -1100,7 +1107,7 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
       }
       if (cudaMemsetAsync(list_len, 0, sizeof(int), st) != cudaSuccess) { rc = 1; break; }
       {
-        // register-tiled pass with shared-memory query tiles when they fit (two buffers of Q x T float4), else one query per warp
+        // register-tiled pass with shared-memory query tiles when they fit (three buffers of Q x T float4), else one query per warp
         const char* lbq_env = getenv("WILDBOAR_CUDA_LB_Q");  // tuning / test knob: 0 = the one-query kernel
         int lbq = lbq_env ? atoi(lbq_env) : 4;
         const char* rbt_env = getenv("WILDBOAR_CUDA_LB_RB");
