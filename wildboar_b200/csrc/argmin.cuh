@@ -369,7 +369,8 @@ struct LbArgs {
   const double* y0; const double* yL;  // (ny) first / last sample of the references
   long long nq, ny, c0, nc; int T;
   const double* thr2;  // per query: the chunk's abandon threshold in the DP's raw (squared) domain, INF = none yet
-  double* d; long long ld;  // chunk matrix: +INF = pruned, -1 = survivor (to be filled by the DP)
+  double* d; long long ld;  // chunk matrix, pre-filled with +INF by the caller (= pruned); the pass writes nothing into it:
+                            // the survivors go to the work list and the DP stores their distances
   unsigned long long* n_kim; unsigned long long* n_keogh;  // pruning statistics
   // survivors are appended to `list` as (query, chunk column) through the cursor `list_len` (zeroed by the caller; one atomic
   // per (query, block) subtask): the DP's work list comes out of this pass directly -- no pass over the chunk matrix to
@@ -405,7 +406,7 @@ __global__ void __launch_bounds__(256) k_lb_prune(LbArgs a) {
   const long long nqg = (a.nq + wpb - 1) / wpb;
   const long long nct = nqg * nyb;
   const int T = a.T;
-  unsigned long long c_kim = 0, c_keogh = 0, c_surv = 0;  // per-warp statistics (lane 0), one atomic per warp at the end
+  unsigned c_kim = 0, c_keogh = 0, c_surv = 0;  // per-warp statistics (lane 0; a warp sees far fewer than 2^32 pairs per launch), one atomic per warp at the end
   for (long long ct = blockIdx.x; ct < nct; ct += gridDim.x) {
     const long long qg = ct / nyb;
     const long long i = qg * wpb + wib;
@@ -476,13 +477,12 @@ __global__ void __launch_bounds__(256) k_lb_prune(LbArgs a) {
         pruned = p2;
       }
     }
-    if (valid) a.d[i * a.ld + jl] = pruned ? WB_INF : -1.0;
     c_surv += lb_append(a, lane, valid && !pruned, i, jl);
   }
   if (lane == 0) {
-    if (c_kim) atomicAdd(a.n_kim, c_kim);
-    if (c_keogh) atomicAdd(a.n_keogh, c_keogh);
-    if (c_surv) atomicAdd(a.n_surv, c_surv);
+    if (c_kim) atomicAdd(a.n_kim, (unsigned long long)c_kim);
+    if (c_keogh) atomicAdd(a.n_keogh, (unsigned long long)c_keogh);
+    if (c_surv) atomicAdd(a.n_surv, (unsigned long long)c_surv);
   }
 }
 
@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(256, MINB) k_lb_prune_tile(LbArgs a, int rb_pe
   const long long per = (nyb + nsplit - 1) / nsplit;
   const long long nct = nqg * nsplit;
   const long long ny = a.ny;
-  unsigned long long c_kim = 0, c_keogh = 0, c_surv = 0;
+  unsigned c_kim = 0, c_keogh = 0, c_surv = 0;  // per-warp statistics: far fewer than 2^32 pairs per warp and launch
 
   // stage task `ct` into buffer b (one whole warp): lanes 0..Q-1 write the per-query scalars, lane 0 resets the block
   // counter and starts the bulk copy of the Q query rows; its arrive (release) publishes all of it with the data
@@ -723,7 +723,6 @@ __global__ void __launch_bounds__(256, MINB) k_lb_prune_tile(LbArgs a, int rb_pe
         const bool p2 = pk || s1[q] > limf[q] || s2[q] > limf[q];
         const bool later = (dfr >> q) & 1u;  // queued: written by whoever drains the queue
         c_keogh += __popc(__ballot_sync(0xffffffffu, p2 && !pk && valid));
-        if (valid && !later) a.d[i * a.ld + jl] = p2 ? WB_INF : -1.0;
         c_surv += lb_append(a, lane, valid && !p2 && !later, i, jl);
       }
     }
@@ -772,16 +771,15 @@ __global__ void __launch_bounds__(256, MINB) k_lb_prune_tile(LbArgs a, int rb_pe
         }
         const bool p2 = t1 > limq || t2 > limq;
         c_keogh += __popc(__ballot_sync(0xffffffffu, has && p2));
-        if (has) a.d[(i0 + e.q) * a.ld + e.jl] = p2 ? WB_INF : -1.0;
         c_surv += lb_append(a, lane, has && !p2, i0 + e.q, e.jl);
       }
       if (ct + (long long)NB * gridDim.x < nct) stage(ct + (long long)NB * gridDim.x, b);
     }
   }
   if (lane == 0) {
-    if (c_kim) atomicAdd(a.n_kim, c_kim);
-    if (c_keogh) atomicAdd(a.n_keogh, c_keogh);
-    if (c_surv) atomicAdd(a.n_surv, c_surv);
+    if (c_kim) atomicAdd(a.n_kim, (unsigned long long)c_kim);
+    if (c_keogh) atomicAdd(a.n_keogh, (unsigned long long)c_keogh);
+    if (c_surv) atomicAdd(a.n_surv, (unsigned long long)c_surv);
   }
 }
 
@@ -1106,6 +1104,9 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
         if (sscanf(e, "%d,%d", &n_, &a_) == 2) { la.strag_n = n_; la.strag_after = a_; }
       }
       if (cudaMemsetAsync(list_len, 0, sizeof(int), st) != cudaSuccess) { rc = 1; break; }
+      // every pair of the chunk starts out as "pruned"; only the survivors' entries are overwritten (by the DP).  One streaming
+      // fill instead of a 256-byte store per (query, block) subtask from inside the pass
+      k_fill<<<148 * 8, 256, 0, st>>>(dbuf, nq * C, WB_INF);
       {
         // register-tiled pass with shared-memory query tiles when they fit (three buffers of Q x T float4), else one query per warp
         const char* lbq_env = getenv("WILDBOAR_CUDA_LB_Q");  // tuning / test knob: 0 = the one-query kernel
