@@ -37,6 +37,7 @@
 #include <vector>
 #include "dispatch.cuh"
 #include "kernels.cuh"
+#include "stage.hpp"
 
 namespace wb {
 
@@ -67,6 +68,9 @@ struct ArgminIo {
   int64_t y_hs = 0;
   double* y_dev = nullptr;         // destination == the call's dense y (ny, T)
   cudaStream_t up_stream = nullptr;
+  // pageable y_host: two page-locked staging buffers of piped_piece_bytes() each (filled by HostCopyPool, stage.hpp); nullptr:
+  // y_host is page-locked already, or no staging memory was to be had -- the pieces are copied straight from y_host
+  char* stage_buf[2] = {nullptr, nullptr};
 };
 
 // bytes per upload piece (test knob WILDBOAR_CUDA_PIPED_UPLOAD_KB forces many pieces on small inputs; 0 disables the pipeline)
@@ -1008,6 +1012,12 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
   // make references [0, upto) resident before work that reads them is enqueued on `st`.  Pieces of >= 16 MB beyond what the
   // chunk needs: a copy from pageable memory blocks the HOST until it is staged, the device meanwhile runs the chunks
   // enqueued before it (a piece is several chunks of work, and is copied in less time than they take).
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  bool stage_used[2] = {false, false};
+  int stage_n = 0;
+  const bool staged = io.y_host && io.stage_buf[0] && io.stage_buf[1];
+  if (staged && (cudaEventCreateWithFlags(&stage_ev[0], cudaEventDisableTiming) != cudaSuccess ||
+                 cudaEventCreateWithFlags(&stage_ev[1], cudaEventDisableTiming) != cudaSuccess)) return 1;
   auto ensure_refs = [&](long long upto) -> int {
     if (upto <= up_done) return 0;
     const long long Ty = c.Ty;
@@ -1016,9 +1026,25 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
     const long long rows = to - up_done;
     double* dst = io.y_dev + up_done * Ty;
     const double* src = io.y_host + up_done * io.y_hs;
-    cudaError_t e = (io.y_hs == Ty)
-        ? cudaMemcpyAsync(dst, src, sizeof(double) * rows * Ty, cudaMemcpyHostToDevice, io.up_stream)
-        : cudaMemcpy2DAsync(dst, sizeof(double) * Ty, src, sizeof(double) * io.y_hs, sizeof(double) * Ty, rows, cudaMemcpyHostToDevice, io.up_stream);
+    cudaError_t e = cudaSuccess;
+    if (staged) {
+      // pageable source: piece-sized parts through the two page-locked buffers -- several threads copy a part in, one DMA
+      // takes it to the device while the next part is being copied
+      for (long long r0 = 0; r0 < rows && e == cudaSuccess; r0 += piece) {
+        const long long nr = std::min(piece, rows - r0);
+        const int sb = stage_n++ & 1;
+        if (stage_used[sb] && cudaEventSynchronize(stage_ev[sb]) != cudaSuccess) return 1;  // its last DMA has left the buffer
+        HostCopyPool::get().copy_rows(io.stage_buf[sb], (const char*)(src + r0 * io.y_hs), (size_t)nr, sizeof(double) * (size_t)Ty,
+                                      sizeof(double) * (size_t)io.y_hs);
+        e = cudaMemcpyAsync(dst + r0 * Ty, io.stage_buf[sb], sizeof(double) * nr * Ty, cudaMemcpyHostToDevice, io.up_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(stage_ev[sb], io.up_stream);
+        stage_used[sb] = true;
+      }
+    } else {
+      e = (io.y_hs == Ty)
+          ? cudaMemcpyAsync(dst, src, sizeof(double) * rows * Ty, cudaMemcpyHostToDevice, io.up_stream)
+          : cudaMemcpy2DAsync(dst, sizeof(double) * Ty, src, sizeof(double) * io.y_hs, sizeof(double) * Ty, rows, cudaMemcpyHostToDevice, io.up_stream);
+    }
     if (e != cudaSuccess || cudaEventRecord(up_ev, io.up_stream) != cudaSuccess || cudaStreamWaitEvent(st, up_ev, 0) != cudaSuccess) return 1;
     if (cascade && envT) {
       launch_envelope_casc(st, c.py, ny, up_done, rows, c.ptx, std::max(c.R - 1, 0), lb_time_stride(c.ptx), envT, yvT, y0, yL);
@@ -1177,9 +1203,10 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
   }
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   if (up_ev) {
-    if (rc) cudaStreamSynchronize(io.up_stream);  // nothing may still be copying into a buffer the caller is about to free
+    if (rc || staged) cudaStreamSynchronize(io.up_stream);  // nothing may still be copying from / into a buffer the caller is about to free
     cudaEventDestroy(up_ev);
   }
+  for (int sb = 0; sb < 2; ++sb) if (stage_ev[sb]) cudaEventDestroy(stage_ev[sb]);
   return rc;
 }
 

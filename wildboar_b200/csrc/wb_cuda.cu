@@ -873,10 +873,21 @@ static int device_worker(const HostJob& J, int dev, int64_t lo, int64_t hi, wb_s
         if (J.fit) for (size_t q = 0; q < J.fit->devs.size() && q < J.fit->casc.size(); ++q) if (J.fit->devs[q] == dev) io.casc_cache = &J.fit->casc[q];
         io.k = J.k; io.lower_bound = J.lower_bound ? J.lower_bound + lo * J.ny : nullptr; io.lb_ld = J.ny;
         io.out_idx = J.out_idx + lo * J.k; io.out_dist = J.out + lo * J.k; io.use_device_lb = J.use_device_lb;
-        if (argmin_piped) { io.y_host = J.y; io.y_hs = J.ys; io.y_dev = dy; io.up_stream = cst; }
+        char* stage_bufs[2] = {nullptr, nullptr};
+        if (argmin_piped) {
+          io.y_host = J.y; io.y_hs = J.ys; io.y_dev = dy; io.up_stream = cst;
+          // pageable references: staged through two page-locked buffers by several copy threads (stage.hpp)
+          if (!is_pinned_host(J.y) && !getenv("WILDBOAR_CUDA_NO_STAGING")) {
+            const size_t pb = (size_t)piped_piece_bytes() + sizeof(double) * (size_t)J.Ty;
+            stage_bufs[0] = (char*)pinned_alloc(pb);
+            stage_bufs[1] = stage_bufs[0] ? (char*)pinned_alloc(pb) : nullptr;
+            if (stage_bufs[0] && stage_bufs[1]) { io.stage_buf[0] = stage_bufs[0]; io.stage_buf[1] = stage_bufs[1]; }
+          }
+        }
         rc = run_argmin(ws, di, c, io, &stats,
                         [&](long long r0, long long nr, long long c0, long long nc, double* o, long long ld, double* om,
                             const double* thr, wb_stats* s) { return launch_dp(ws, di, c, r0, nr, c0, nc, o, ld, om, thr, s); });
+        for (char* sbuf : stage_bufs) if (sbuf) pinned_free(sbuf);  // run_argmin has waited for the last DMA out of them
         if (rc) break;
         WB_CK(cudaStreamSynchronize(st));
         break;
