@@ -924,7 +924,11 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
   // Threshold seeding (k = 1, see k_seed_candidates) is decided here because it changes the schedule: with thresholds that
   // are close to final from the start, a stale chunk-start threshold costs little, so the chunks are four times as wide
   // (32 Mi values per buffer: an eighth of the launches; cfg4 share: kernels 55.7 ms at 1600 columns, 36.1 at 6400, 32.8 at 12 800) and there is no dense first chunk to keep small.
-  const long long seed_from = io.y_host ? std::min<long long>(ny, std::max<long long>(1, piped_piece_bytes() / (long long)(sizeof(double) * c.Ty))) : ny;
+  // pipelined upload: the candidates are drawn from the first few pieces (the scan waits for them; with the staged copy a
+  // piece of 16 MB arrives in half a millisecond)
+  long long seed_pieces = 4;
+  if (const char* e = getenv("WILDBOAR_CUDA_SEED_PIECES")) seed_pieces = std::max<long long>(1, atoll(e));
+  const long long seed_from = io.y_host ? std::min<long long>(ny, seed_pieces * std::max<long long>(1, piped_piece_bytes() / (long long)(sizeof(double) * c.Ty))) : ny;
   long long seed_min = 2048;
   if (const char* e = getenv("WILDBOAR_CUDA_SEED_MIN")) seed_min = std::max<long long>(256, atoll(e));  // test knob
   // The cascade bounds the banded DTW of the PREPARED operands: dtw itself, ddtw (DTW of the slope series; R as
@@ -1066,7 +1070,7 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
   double* seed2 = nullptr;
   if (cascade && will_seed) {
     // references the candidates are drawn from: all of them when they are resident, the first piece of a pipelined upload
-    if (io.y_host) rc = ensure_refs(1);
+    if (io.y_host) rc = ensure_refs(seed_from);
     const long long S = up_done;
     if (!rc && S >= seed_min) {
       // reference slices per query group: enough CTAs to fill the device when the queries are few, each slice >= 256 references
