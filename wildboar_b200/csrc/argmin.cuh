@@ -923,7 +923,7 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
   // buffer; for the cfg4 share (2500 queries) that is 128, 512, then 1600; for one query 1024, 4096, 16384, 32768, ...
   // Threshold seeding (k = 1, see k_seed_candidates) is decided here because it changes the schedule: with thresholds that
   // are close to final from the start, a stale chunk-start threshold costs little, so the chunks are four times as wide
-  // (32 Mi values per buffer: an eighth of the launches; cfg4 share: kernels 55.7 ms at 1600 columns, 36.1 at 6400, 32.8 at 12 800) and there is no dense first chunk to keep small.
+  // (32 Mi values per buffer: an eighth of the launches; cfg4 share, seeded: kernels 55.7 ms at 1600 columns, 36.1 at 6400, 32.8 at 12 800) and there is no dense first chunk to keep small.
   // pipelined upload: the candidates are drawn from the first few pieces (the scan waits for them; with the staged copy a
   // piece of 16 MB arrives in half a millisecond)
   long long seed_pieces = 4;
@@ -946,7 +946,12 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
   // ensemble/_elastic.py), so the distance to a candidate is no bound on what the scan can still accept.
   const bool will_seed = lb_on && !io.lower_bound && c.ptx == c.pty && c.ptx >= 2 && !c.degenerate && (k == 1 || set_mode) &&
                          seed_from >= seed_min && nq * (long long)kSeedNC < 2000000000LL && !getenv("WILDBOAR_CUDA_NO_SEED");
-  long long C = ((will_seed ? 32LL : 4LL) << 20) / std::max<long long>(nq, 1);
+  // ... and the unseeded cascade gains as much from wide chunks once its thresholds have settled (heap-order k = 5 on the cfg4
+  // share: 54.5 ms at 1664 columns, 31.3 ms at 12 800 with the first chunks still 128, 512, 2048, ...: a chunk costs its
+  // launches, the staler thresholds add 7 % to the DP's pairs).  Without the cascade every pair of a chunk goes through the
+  // DP and only its early abandoning profits from fresh thresholds, so those scans keep the narrow chunks.
+  const bool casc_ok = lb_on && c.ptx == c.pty && c.ptx >= 2 && !c.degenerate;
+  long long C = ((casc_ok ? 32LL : 4LL) << 20) / std::max<long long>(nq, 1);
   C = std::max<long long>(32, std::min<long long>(32768, (C / 32) * 32));
   // first chunk: it runs without thresholds (every pair in full), so just enough pairs to fill the device -- 256 Ki --
   // between 128 and 1024 columns (cfg4 share, 2500 queries: 128 columns; kernels 81 -> 75 ms against 1024)
