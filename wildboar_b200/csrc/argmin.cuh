@@ -1147,7 +1147,7 @@ int run_argmin(WS& ws, const DI& di, Call& c, const ArgminIo& io, wb_stats* stat
         const char* lbq_env = getenv("WILDBOAR_CUDA_LB_Q");  // tuning / test knob: 0 = the one-query kernel
         int lbq = lbq_env ? atoi(lbq_env) : 4;
         const char* rbt_env = getenv("WILDBOAR_CUDA_LB_RB");
-        const int rbt = (rbt_env && atoi(rbt_env) > 0) ? std::min(atoi(rbt_env), 64) : 16;  // reference blocks per CTA task
+        const int rbt = (rbt_env && atoi(rbt_env) > 0) ? std::min(atoi(rbt_env), 64) : 32;  // reference blocks per CTA task (8 / 16 / 32: 29.8 / 28.9 / 28.5 ms, r02bb)
         la.strag_n = std::min(la.strag_n, 8);
         while (lbq > 1 && lb_tile_smem(lbq, c.ptx, lb_tile_qcap(lbq, rbt, la.strag_n)) > (size_t)96 << 10) lbq >>= 1;
         if (nq < 2 || lbq < 2) lbq = 0;
