@@ -297,13 +297,13 @@ def extra_configs(wb, peak_inst, world, rank, dev, barrier, max_over_ranks_fn, q
     # the same call with the references in page-locked memory (wb.pinned_copy): the piecewise upload then runs at PCIe speed
     # instead of the pageable-copy rate and hides completely behind the scan
     refs_pin = None
-    for _ in range(40):   # blocks over 256 MB are page-locked by a background thread: the first requests get ordinary memory
+    for _ in range(12):   # blocks over 256 MB are page-locked by a background thread: the first request gets ordinary memory
         cand = wb.pinned_copy(refs)
         if type(getattr(cand, "base", None)).__name__ == "_PinnedBlock":
             refs_pin = cand
             break
         del cand
-        time.sleep(0.25)
+        time.sleep(0.75)  # (page-locking 410 MB takes a few tenths of a second; asking again sooner only queues more of it)
     dt_pin = -1.0
     if refs_pin is not None:
         wb.argmin_distance(q, refs_pin, k=1, metric="dtw", metric_params={"r": 0.05}, return_distance=True)
@@ -344,6 +344,7 @@ def extra_configs(wb, peak_inst, world, rank, dev, barrier, max_over_ranks_fn, q
                    "parity": ok4, "parity_n": 64 * world,
                    "parity_kind": "64 random queries of EVERY rank's share replayed by the oracle's sequential scan against ALL references: indices and distances equal"}
     del refs, q_all
+    time.sleep(1.0)  # let the library's background page-locking (above) finish: it holds the driver's lock while it runs
     # cfg5: msm / twe, r = 0.05, 2000 x 4096 vs 2000 x 4096; rank r owns x rows [250 r, 250 (r + 1))
     n5, share5 = (256, 32) if quick else (2000, 250)
     x5, y5 = random_walks(n5, 4096, 1), random_walks(n5, 4096, 2)
@@ -367,6 +368,7 @@ def extra_configs(wb, peak_inst, world, rank, dev, barrier, max_over_ranks_fn, q
         ok, n = spot_check(m, {"r": 0.05}, x5, y5, res, 300, 50 + rank, row0=rank * share5)
         ok = max_over_ranks_fn([0.0 if ok else 1.0])[0] == 0.0
         c5[m] = {"pairs": int(world * st["pairs"]), "cells": int(cells), "kernel_ms": round(k_max, 2), "e2e_ms": round(dt_max * 1e3, 2),
+                 "device_total_ms_rank0": round(st["total_ms"], 2),
                  "kernel_gcups": round(kg, 1), "e2e_gcups": round(cells / dt_max / 1e9, 1), "frac": round(kg / world * ops / peak_g, 4),
                  "ops_per_cell": ops, "engine": st["engine"], "strip": [st.get("strip_w"), st.get("strip_nr"), st.get("strip_warps"), st.get("strip_gring")],
                  "parity": ok, "parity_n": n * world, "parity_kind": "300 random entries of EVERY rank's row block == oracle"}
