@@ -352,9 +352,10 @@ def extra_configs(wb, peak_inst, world, rank, dev, barrier, max_over_ranks_fn, q
     c5 = {}
     for m in ("msm", "twe"):
         call = lambda: wb.pairwise_distance(xs, y5, metric=m, metric_params={"r": 0.05})  # noqa: E731
-        # warm-up (module load, pools) on enough rows for the engine of the timed call: 8 rows are few enough pairs for the
-        # cooperative engine, and the strip kernel's first launch (lazy module load) then fell into the timed call
-        wb.pairwise_distance(xs[:32], y5, metric=m, metric_params={"r": 0.05})
+        # warm-up = the call itself, once: the first call of a shape pays one-off host-side costs of 50-100 ms (first launch of
+        # its kernel, growth of the device's memory pool to the shape's buffers; profiles/r02bn_hostgap.log) that a smaller
+        # warm-up call does not take off the timed one
+        call()
         barrier()
         t0 = time.perf_counter()
         res = call()
